@@ -1,0 +1,222 @@
+/*
+ * gwat_b200.h -- C ABI of the B200-native batched likelihood engine.
+ *
+ * This is the drop-in boundary for ONE path of scottperkins/gw_analysis_tools (GWAT):
+ *   frequency-domain waveform -> detector projection -> noise-weighted inner product -> log-likelihood,
+ *   and the finite-difference Fisher stencil built from the same responses,
+ * evaluated for whole ensembles of walkers at once on one B200.
+ *
+ * Plain C: pointers, sizes and PODs only.  No torch / CUDA types appear in any signature; `stream` arguments are
+ * cudaStream_t passed as void* (NULL = the context's own stream).  Every entry point returns 0 on success or a
+ * negative gwat_b200_status; nothing here ever calls exit() (the reference does, src/detector_util.cpp:1155-1158).
+ * There is NO CPU fallback: if no CUDA device is usable, gwat_b200_ctx_create fails with GWAT_B200_ERR_CUDA.
+ *
+ * Each declaration cites the reference interface (path relative to the GWAT repository root) it replaces.
+ */
+#ifndef GWAT_B200_H
+#define GWAT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWAT_B200_ABI_VERSION 1
+#define GWAT_B200_MAX_DETECTORS 8
+#define GWAT_B200_MAX_MOD 8 /* max ppE terms, and max gIMR modifications per coefficient family */
+#define GWAT_B200_MAX_DIM 32 /* max sampling / Fisher dimension */
+
+typedef enum gwat_b200_status {
+	GWAT_B200_OK = 0,
+	GWAT_B200_ERR_ARG = -1,       /* NULL pointer, bad size, unknown detector ... */
+	GWAT_B200_ERR_METHOD = -2,    /* generation_method string not supported by this library */
+	GWAT_B200_ERR_CUDA = -3,      /* CUDA runtime error (message in gwat_b200_last_error) */
+	GWAT_B200_ERR_STATE = -4,     /* network/grid not set, or context built for another shape */
+	GWAT_B200_ERR_UNSUPPORTED = -5 /* valid GWAT option that is outside this library's path (LISA, horizon coords, autodiff ...) */
+} gwat_b200_status;
+
+/*
+ * Flattened gen_params_base<double>  (include/gwat/util.h:121-378).
+ * Same field names and units (solar masses, Mpc, radians, seconds) as the reference class; pointer members of the
+ * reference (betappe/bppe, delta_*, *i) become fixed-size arrays so the record is a POD that can live in device memory.
+ * Defaults of the reference are reproduced by gwat_b200_source_init().
+ */
+typedef struct gwat_b200_source {
+	double mass1, mass2;
+	double Luminosity_Distance;
+	double spin1[3], spin2[3];
+	double tc, phiRef, f_ref;
+	double psi, incl_angle;
+	double RA, DEC, gmst;
+	double theta, phi;               /* horizon coordinates (accepted, only used when horizon_coord != 0 -> unsupported) */
+	double theta_l, phi_l;           /* equatorial orientation of L (equatorial_orientation != 0 -> unsupported) */
+	double tidal1, tidal2, tidal_s, tidal_a, tidal_weighted, delta_tidal_weighted;
+	double diss_tidal1, diss_tidal2, diss_tidal_s, diss_tidal_a, diss_tidal_weighted;
+	double chip, phip;               /* reduced PhenomPv2 parameterisation, used when chip != -1 */
+	double betappe[GWAT_B200_MAX_MOD];
+	double bppe[GWAT_B200_MAX_MOD];
+	double delta_phi[GWAT_B200_MAX_MOD];
+	double delta_sigma[GWAT_B200_MAX_MOD];
+	double delta_beta[GWAT_B200_MAX_MOD];
+	double delta_alpha[GWAT_B200_MAX_MOD];
+	int phii[GWAT_B200_MAX_MOD];
+	int sigmai[GWAT_B200_MAX_MOD];
+	int betai[GWAT_B200_MAX_MOD];
+	int alphai[GWAT_B200_MAX_MOD];
+	int Nmod, Nmod_phi, Nmod_sigma, Nmod_beta, Nmod_alpha;
+	int PNorder;
+	int shift_time, shift_phase, sky_average;
+	int tidal_love, tidal_love_error;
+	int NSflag1, NSflag2;
+	int dep_postmerger;
+	int equatorial_orientation, horizon_coord;
+	int reserved_[2];
+} gwat_b200_source;
+
+/*
+ * Flattened MCMC_modification_struct  (include/gwat/mcmc_gw.h:50-88): which extra sampling dimensions exist and what
+ * they mean.  GAUSS_QUAD / log10F / weights of the reference struct are properties of the network here
+ * (gwat_b200_set_network), the fisher_* overrides are arguments of the Fisher calls.
+ */
+typedef struct gwat_b200_mod {
+	int ppE_Nmod;
+	double bppe[GWAT_B200_MAX_MOD];
+	int gIMR_Nmod_phi, gIMR_Nmod_sigma, gIMR_Nmod_beta, gIMR_Nmod_alpha;
+	int gIMR_phii[GWAT_B200_MAX_MOD];
+	int gIMR_sigmai[GWAT_B200_MAX_MOD];
+	int gIMR_betai[GWAT_B200_MAX_MOD];
+	int gIMR_alphai[GWAT_B200_MAX_MOD];
+	int NSflag1, NSflag2;
+	int tidal_love, tidal_love_error;
+} gwat_b200_mod;
+
+typedef struct gwat_b200_ctx gwat_b200_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------------------------ */
+
+int gwat_b200_abi_version(void);
+
+/* Fill a source / modification record with the reference's member defaults (include/gwat/util.h:125-285,
+ * include/gwat/mcmc_gw.h:52-67). */
+void gwat_b200_source_init(gwat_b200_source *src);
+void gwat_b200_mod_init(gwat_b200_mod *mod);
+
+/* One context per GPU and per submitting thread group.  Owns the device copies of the frequency grid, PSDs, data and
+ * all scratch; replaces the file-static globals mcmc_data/mcmc_noise/mcmc_frequencies/mcmc_detectors/...
+ * (include/gwat/mcmc_gw.h:22-46).  `device` is the CUDA ordinal. */
+int gwat_b200_ctx_create(gwat_b200_ctx **ctx, int device);
+void gwat_b200_ctx_destroy(gwat_b200_ctx *ctx);
+/* Human-readable description of the last failure on this context ("" if none); NULL ctx -> last create failure. */
+const char *gwat_b200_last_error(const gwat_b200_ctx *ctx);
+
+/*
+ * Upload the detector network: D detectors sharing one frequency grid of L bins (the reference only supports the shared
+ * grid too: create_coherent_GW_detection, src/waveform_util.cpp:140-145).
+ *   detectors[d]         GWAT detector names ("Hanford", "Livingston", "Virgo", "Kagra", "Indigo", "CE", "ET1".."ET3";
+ *                        src/detector_util.cpp:1083-1158)
+ *   frequencies[L]       Hz
+ *   psd[D*L]             detector-major, as the gwatpy flat layout (src/gwatpy_wrapping.cpp:125-130)
+ *   data_re/im[D*L]      frequency-domain strain; may both be NULL when only waveforms/Fishers are wanted
+ *   weights[L]           quadrature weights for "GAUSSLEG" (NULL for "SIMPSONS")
+ *   integration_method   "SIMPSONS" | "GAUSSLEG"   (Log_Likelihood_internal, src/mcmc_gw.cpp:801-868)
+ *   log10F               GAUSSLEG nodes are in log10(f)  (src/mcmc_gw.cpp:822-826)
+ */
+int gwat_b200_set_network(gwat_b200_ctx *ctx, int num_detectors, const char *const *detectors, int length,
+                          const double *frequencies, const double *psd, const double *data_re, const double *data_im,
+                          const double *weights, const char *integration_method, int log10F);
+
+/* ---- log-likelihood --------------------------------------------------------------------------------------------- */
+
+/*
+ * W evaluations of MCMC_likelihood_wrapper (src/mcmc_gw.cpp:2569-2791, extrinsic branch) in one call:
+ *   MCMC_prep_params (:2492) -> repack_parameters("MCMC_"+method) (src/fisher.cpp:2167) -> MCMC_likelihood_extrinsic (:2374).
+ *   params[W*dimension]  row-major sampling vectors (RA, sin DEC, psi, cos iota, phiRef, tc, ln DL, ln Mc, eta, ... )
+ *   gmst                 replaces the global mcmc_gmst
+ *   T_segment            segment duration; the reference forms tc_ref = T - tc with T = 1/(frequencies[1]-frequencies[0])
+ *                        taken on a double** (pointer arithmetic, src/mcmc_gw.cpp:2466) -- here T is explicit.
+ *   logL[W]              out
+ * Host pointers.  NaN/invalid parameter points give NaN (the samplers reject those, src/mcmc_sampler_internals.cpp:101).
+ */
+int gwat_b200_loglike_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                                 int dimension, int W, const double *params, double gmst, double T_segment,
+                                 double *logL);
+/* Same, with params/logL already in device memory of ctx's GPU; asynchronous on `stream`. */
+int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                                     int dimension, int W, const double *d_params, double gmst, double T_segment,
+                                     double *d_logL, void *stream);
+
+/*
+ * W evaluations of the body of MCMC_likelihood_extrinsic below its tc_ref line (src/mcmc_gw.cpp:2473-2486):
+ * create_coherent_GW_detection (src/waveform_util.cpp:129) + sum_d Log_Likelihood_internal (src/mcmc_gw.cpp:801),
+ * from physical parameters; sources[w].tc is used as given (i.e. it is the reference's tc_ref).
+ */
+int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *generation_method, int W, const gwat_b200_source *sources,
+                            double *logL);
+
+/* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
+
+/*
+ * W evaluations of fourier_waveform<double> (src/waveform_generator.cpp:104-294) on the context's grid.
+ * Outputs are split real/imag like fourier_waveform_py (src/gwatpy_wrapping.cpp), shape [W*L] row-major; any may be NULL.
+ */
+int gwat_b200_fourier_waveform_batch(gwat_b200_ctx *ctx, const char *generation_method, int W,
+                                     const gwat_b200_source *sources, double *hplus_re, double *hplus_im,
+                                     double *hcross_re, double *hcross_im);
+
+/*
+ * W evaluations of create_coherent_GW_detection_reuse_WF (src/waveform_util.cpp:153-184): responses of all D detectors
+ * of the network including the inter-detector time-of-arrival phase.  resp_re/im shape [W*D*L].
+ */
+int gwat_b200_coherent_response_batch(gwat_b200_ctx *ctx, const char *generation_method, int W,
+                                      const gwat_b200_source *sources, double *resp_re, double *resp_im);
+
+/*
+ * W evaluations of fourier_detector_response<double> (src/waveform_util.cpp:1070-1088, equatorial branch :936-985) for
+ * ONE named detector, no time-of-arrival shift.  resp_re/im shape [W*L].
+ */
+int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *generation_method, const char *detector,
+                                              int W, const gwat_b200_source *sources, double *resp_re,
+                                              double *resp_im);
+
+/* ---- Fisher matrices --------------------------------------------------------------------------------------------- */
+
+/*
+ * S evaluations of fisher_numerical (src/fisher.cpp:81-145) for one detector of the network against a reference
+ * detector, central differences of `order` 2 or 4 with the reference's epsilon = 1e-8 (src/fisher.cpp:361).
+ *   generation_method    as the reference takes it, e.g. "IMRPhenomD" or "MCMC_IMRPhenomD"
+ *   detector_index       which detector of the network supplies the antenna pattern and the PSD
+ *   reference_index      the detector tc refers to (the reference's reference_detector)
+ *   fisher[S*dim*dim]    out, row-major per source
+ * With detector_index < 0 the matrices of all detectors are summed (MCMC_fisher_wrapper, src/mcmc_gw.cpp:2298-2312).
+ */
+int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *generation_method, int detector_index,
+                                     int reference_index, int dimension, int order, int S,
+                                     const gwat_b200_source *sources, double *fisher);
+
+/* ---- helpers that mirror small reference utilities (evaluated on the GPU like everything else) ------------------- */
+
+/* repack_parameters<double> for the "MCMC_"+method parameterisations (src/fisher.cpp:2167-2507), after the dCS/EdGB unit
+ * change of MCMC_prep_params (src/mcmc_gw.cpp:2560-2565): sampling vectors -> physical records. */
+int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                                int dimension, int W, const double *params, double gmst, gwat_b200_source *sources);
+
+/* Antenna patterns and time-of-arrival differences for W sky positions:
+ * detector_response_functions_equatorial (src/detector_util.cpp:1037) and DTOA_DETECTOR (:677) for every detector of the
+ * network relative to detector 0.  Outputs shape [W*D]. */
+int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const double *DEC, const double *psi,
+                            double gmst, double *Fplus, double *Fcross, double *dtoa);
+
+/* ---- introspection used by bench.py / the tests ------------------------------------------------------------------ */
+
+/* Number of kernels this library has launched on ctx since creation (for the bench's gpu_launches). */
+long long gwat_b200_launch_count(const gwat_b200_ctx *ctx);
+/* Device-time (ms, CUDA events on the context's stream) of the hot kernel launches of the last *_batch call. */
+double gwat_b200_last_kernel_ms(const gwat_b200_ctx *ctx);
+/* Active (walker,bin) pairs (f below the model's cutoff) evaluated by the last likelihood call. */
+long long gwat_b200_last_active_bins(const gwat_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWAT_B200_H */

@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of the oracle ``oracle/_ref/libgwat_ref.so``.
+
+That library is the reference's own C++ sources (compiled from /root/reference by ``oracle/Makefile``) behind the small
+C driver ``oracle/ref_driver.cpp``.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module; nothing under ``gw_analysis_tools_b200/`` does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from gw_analysis_tools_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libgwat_ref.so")
+
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle not built: run `make -C oracle` (needs /root/reference) -> " + LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.oracle_ref_log_likelihood_internal.restype = C.c_double
+        _lib.oracle_ref_sizeof_source.restype = C.c_size_t
+        _lib.oracle_ref_sizeof_mod.restype = C.c_size_t
+        assert _lib.oracle_ref_sizeof_source() == C.sizeof(abi.Source)
+        assert _lib.oracle_ref_sizeof_mod() == C.sizeof(abi.Mod)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dets(names):
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    return arr
+
+
+def _src_array(sources):
+    if isinstance(sources, abi.Source):
+        sources = [sources]
+    if isinstance(sources, C.Array):
+        return sources, len(sources)
+    arr = (abi.Source * len(sources))(*sources)
+    return arr, len(sources)
+
+
+def max_threads():
+    return lib().oracle_ref_max_threads()
+
+
+def fourier_waveform(method, src, f):
+    f = _f64(f)
+    L = f.size
+    out = [np.zeros(L) for _ in range(4)]
+    lib().oracle_ref_fourier_waveform(method.encode(), C.byref(src), _p(f), L, *[_p(o) for o in out])
+    return out[0] + 1j * out[1], out[2] + 1j * out[3]
+
+
+def fourier_detector_response(method, detector, src, f):
+    f = _f64(f)
+    L = f.size
+    re, im = np.zeros(L), np.zeros(L)
+    lib().oracle_ref_fourier_detector_response(method.encode(), detector.encode(), C.byref(src), _p(f), L, _p(re), _p(im))
+    return re + 1j * im
+
+
+def coherent_response(method, src, detectors, f):
+    f = _f64(f)
+    L, D = f.size, len(detectors)
+    re, im = np.zeros((D, L)), np.zeros((D, L))
+    lib().oracle_ref_coherent_response(method.encode(), C.byref(src), D, _dets(detectors), _p(f), L, _p(re), _p(im))
+    return re + 1j * im
+
+
+def log_likelihood_internal(data, psd, f, weights, resp, log10F=False, integ="SIMPSONS"):
+    f = _f64(f)
+    dre, dim = _f64(data.real), _f64(data.imag)
+    rre, rim = _f64(resp.real), _f64(resp.imag)
+    psd, weights = _f64(psd), _f64(weights)
+    return lib().oracle_ref_log_likelihood_internal(_p(dre), _p(dim), _p(psd), _p(f), _p(weights), _p(rre), _p(rim),
+                                                     f.size, int(log10F), integ.encode())
+
+
+def loglike_batch(method, sources, detectors, f, psd, data, weights=None, integ="SIMPSONS", log10F=False, nthreads=0):
+    arr, W = _src_array(sources)
+    f, psd, weights = _f64(f), _f64(psd), _f64(weights)
+    dre, dim = _f64(data.real), _f64(data.imag)
+    out = np.zeros(W)
+    lib().oracle_ref_loglike_batch(method.encode(), W, arr, len(detectors), _dets(detectors), _p(f), f.size, _p(psd),
+                                   _p(dre), _p(dim), _p(weights), integ.encode(), int(log10F), int(nthreads), _p(out))
+    return out
+
+
+def loglike_mcmc_batch(method, mod, params, gmst, T_segment, detectors, f, psd, data, weights=None, integ="SIMPSONS",
+                       log10F=False, nthreads=0, return_sources=False):
+    params = _f64(params)
+    W, P = params.shape
+    f, psd, weights = _f64(f), _f64(psd), _f64(weights)
+    dre = _f64(data.real) if data is not None else None
+    dim = _f64(data.imag) if data is not None else None
+    out = np.zeros(W)
+    srcs = (abi.Source * W)() if return_sources else None
+    lib().oracle_ref_loglike_mcmc_batch(method.encode(), C.byref(mod) if mod is not None else None, P, W, _p(params),
+                                        C.c_double(gmst), C.c_double(T_segment), len(detectors), _dets(detectors),
+                                        _p(f), f.size, _p(psd), _p(dre), _p(dim), _p(weights), integ.encode(),
+                                        int(log10F), int(nthreads), _p(out) if data is not None else None, srcs)
+    return (out, srcs) if return_sources else out
+
+
+def fisher_numerical_batch(method, sources, detectors, f, psd, dimension, order=4, detector_index=-1,
+                           reference_index=0, nthreads=0):
+    arr, S = _src_array(sources)
+    f, psd = _f64(f), _f64(psd)
+    out = np.zeros((S, dimension, dimension))
+    lib().oracle_ref_fisher_numerical_batch(method.encode(), detector_index, reference_index, dimension, order, S, arr,
+                                            len(detectors), _dets(detectors), _p(f), f.size, _p(psd), int(nthreads),
+                                            _p(out))
+    return out
+
+
+def antenna_batch(RA, DEC, psi, gmst, detectors):
+    RA, DEC, psi = _f64(RA), _f64(DEC), _f64(psi)
+    W, D = RA.size, len(detectors)
+    fp, fc, dt = np.zeros((W, D)), np.zeros((W, D)), np.zeros((W, D))
+    lib().oracle_ref_antenna_batch(W, _p(RA), _p(DEC), _p(psi), C.c_double(gmst), D, _dets(detectors), _p(fp), _p(fc),
+                                   _p(dt))
+    return fp, fc, dt
+
+
+def populate_noise(f, curve):
+    f = _f64(f)
+    asd = np.zeros(f.size)
+    lib().oracle_ref_populate_noise(_p(f), curve.encode(), _p(asd), f.size)
+    return asd
+
+
+def phenomd_intermediates(src):
+    out = np.zeros(11)
+    lib().oracle_ref_phenomd_intermediates(C.byref(src), _p(out))
+    return dict(zip(["M", "eta", "chirpmass", "chi_pn", "A0", "fRD", "fdamp", "f1", "f3", "f1_phase", "f2_phase"], out))

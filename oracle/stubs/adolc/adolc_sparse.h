@@ -1,0 +1,7 @@
+// TEST INFRASTRUCTURE ONLY (oracle build). Stand-in umbrella header for ADOL-C.
+#ifndef ORACLE_STUB_ADOLC_SPARSE_H
+#define ORACLE_STUB_ADOLC_SPARSE_H
+#include "adolc/adouble.h"
+#include "adolc/taping.h"
+#include "adolc/drivers/drivers.h"
+#endif
