@@ -1,0 +1,71 @@
+// Per-(walker, bin) evaluation on top of the carrier: polarisations, detector responses, likelihood integrands.
+// GWAT_HD code shared by the CUDA kernels (gwat_engine.cu) and the CPU-side test harness.
+//
+// Reference being replaced, per bin:
+//   waveform[j] = amp * exp(-i phase)                                   src/IMRPhenomD.cpp:497-498
+//   h+ = (1+cos^2 i)/2 h,  hx = -i cos(i) h                             src/waveform_generator.cpp:188-199
+//   r_d = F+ h+ + Fx hx                                                 src/waveform_util.cpp:871-872
+//   r_d *= exp(i (-2 pi DTOA_d) f)                                      src/waveform_util.cpp:177-179
+//   |r|^2/S and Re(d conj(r))/S                                         src/mcmc_gw.cpp:815,838
+#ifndef GWAT_BINS_H
+#define GWAT_BINS_H
+
+#include "gwat_setup.h"
+
+namespace gwat {
+
+struct cplx {
+	double re, im;
+};
+
+// What the kernels read per frequency bin (built once per grid by the host, see gwat_grid.h).
+struct BinGrid {
+	const double *f;      // [L] Hz
+	const double *sf_hi;  // [L] f^(fl(1/6)) double-double
+	const double *sf_lo;
+	const double *logf;   // [L] ln f
+};
+
+GWAT_HD double bin_sixth_root(const DCoef &c, double sf_hi, double sf_lo)
+{
+	return dd_mul_to_double(c.sM_hi, c.sM_lo, sf_hi, sf_lo);
+}
+
+// The (2,2) carrier h = A exp(-i phi) of the IMRPhenomD families, time and phase shifts applied.
+template <class Fam>
+GWAT_HD cplx carrier_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf)
+{
+	const DCoef &c = w.d;
+	if (f > c.fcut) return cplx{0.0, 0.0};
+	double amp, phase;
+	phenomd_bin<Fam>(c, f, bin_sixth_root(c, sf_hi, sf_lo), logf, amp, phase);
+	phase = phenomd_apply_time_phase(c, f, phase);
+	double sn, cs;
+	sincos(phase, &sn, &cs);
+	return cplx{amp * cs, -(amp * sn)};
+}
+
+// fourier_waveform semantics for the IMRPhenomD families.
+template <class Fam>
+GWAT_HD void polarizations_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, cplx &hp, cplx &hc)
+{
+	const cplx h = carrier_bin<Fam>(w, f, sf_hi, sf_lo, logf);
+	hp = cplx{h.re * w.pfac, h.im * w.pfac};
+	hc = cplx{h.im * w.cfac, -h.re * w.cfac};
+}
+
+// Response of detector d including the arrival-time phase (create_coherent_GW_detection_reuse_WF semantics);
+// with_shift = false gives fourier_detector_response semantics.
+GWAT_HD cplx project_bin(const DetCoef &dc, cplx hp, cplx hc, double f, bool with_shift)
+{
+	cplx r{dc.Fplus * hp.re + dc.Fcross * hc.re, dc.Fplus * hp.im + dc.Fcross * hc.im};
+	if (with_shift) {
+		double sn, cs;
+		sincos(mul_rn(dc.tshift, f), &sn, &cs);
+		r = cplx{r.re * cs - r.im * sn, r.re * sn + r.im * cs};
+	}
+	return r;
+}
+
+}  // namespace gwat
+#endif

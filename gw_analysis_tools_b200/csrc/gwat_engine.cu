@@ -1,0 +1,773 @@
+// gwat_b200 engine: CUDA kernels for sm_100a and the C ABI of include/gwat_b200.h.
+//
+// Data layout in HBM (per context = per GPU):
+//   grid tables      f[L], sf_hi[L], sf_lo[L], logf[L]                      shared by every walker, L2-resident
+//   network tables   wq[D][L] = quadrature coefficient / PSD,  data_re[D][L], data_im[D][L]
+//   per call         params[W][P] -> WalkerCoef[W] (setup kernel) -> partial[W][chunks][2] -> logL[W]
+// Kernels:
+//   k_setup_mcmc / k_setup_src   one thread per walker: sampling vector or physical record -> WalkerCoef
+//   k_loglike                    grid (bin chunks, walkers); threads stride over consecutive bins (coalesced table reads,
+//                                region branches diverge only at the per-walker boundaries); amplitude/phase in FP64,
+//                                detector projection and PSD weighting in registers, warp-shuffle + shared-memory
+//                                reduction to one partial per (walker, chunk)
+//   k_finish                     deterministic sum of the partials -> logL
+//   k_waveform / k_response      the same per-bin code writing polarisations / responses (API parity entry points)
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define GWAT_TABLE_QUALIFIER static __device__ const
+#include "gwat_tables.inc"
+#undef GWAT_TABLE_QUALIFIER
+namespace hosttab {  // the same generated tables for host-side use (detector rows)
+#define GWAT_TABLE_QUALIFIER static const
+#include "gwat_tables.inc"
+#undef GWAT_TABLE_QUALIFIER
+}  // namespace hosttab
+
+#include "gwat_bins.h"
+#include "gwat_grid.h"
+#include "gwat_method.h"
+#include "gwat_repack.h"
+
+using namespace gwat;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ Tables device_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N}; }
+
+struct GridPtrs {
+	const double *f, *sf_hi, *sf_lo, *logf;
+	const double *wq, *dre, *dim;  // [D][L]
+	int L;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Block-wide sum of two values; result valid in thread 0.
+__device__ __forceinline__ void block_sum2(double &a, double &b)
+{
+	__shared__ double sa[kThreads / 32], sb[kThreads / 32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	a = warp_sum(a);
+	b = warp_sum(b);
+	if (lane == 0) {
+		sa[wid] = a;
+		sb[wid] = b;
+	}
+	__syncthreads();
+	if (wid == 0) {
+		a = lane < kThreads / 32 ? sa[lane] : 0.0;
+		b = lane < kThreads / 32 ? sb[lane] : 0.0;
+		a = warp_sum(a);
+		b = warp_sum(b);
+	}
+}
+
+__device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D)
+{
+	const DCoef &c = w.d;
+	bool ok = isfinite(c.fcut) && isfinite(c.A0) && isfinite(c.fRD) && isfinite(c.fdamp) && isfinite(c.tc) &&
+	          isfinite(c.phic) && isfinite(c.beta0) && isfinite(c.alpha0) && isfinite(c.ic[4]) && isfinite(w.pfac);
+	for (int d = 0; d < D; d++) ok = ok && isfinite(w.det[d].Fplus) && isfinite(w.det[d].Fcross) && isfinite(w.det[d].tshift);
+	return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+
+template <class Fam>
+__global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ params, int W, RepackPlan plan, Network net,
+                                                   double gmst, double T_segment, WalkerCoef *__restrict__ out,
+                                                   gwat_b200_source *__restrict__ src_out)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	gwat_b200_source s;
+	repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, T_segment, s);
+	if (src_out) src_out[w] = s;
+	if (out) {
+		WalkerCoef wc;
+		walker_setup<Fam>(s, net, device_tables(), wc);
+		wc.valid = coef_is_finite(wc, net.D) ? 1 : 0;
+		out[w] = wc;
+	}
+}
+
+template <class Fam>
+__global__ void __launch_bounds__(128) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net,
+                                                  WalkerCoef *__restrict__ out)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	const gwat_b200_source s = src[w];
+	WalkerCoef wc;
+	walker_setup<Fam>(s, net, device_tables(), wc);
+	wc.valid = coef_is_finite(wc, net.D) ? 1 : 0;
+	out[w] = wc;
+}
+
+// Stage one walker's coefficient block in shared memory.
+__device__ __forceinline__ void load_walker(const WalkerCoef *__restrict__ src, WalkerCoef &dst)
+{
+	static_assert(sizeof(WalkerCoef) % sizeof(double) == 0, "WalkerCoef must be a whole number of doubles");
+	const double *s = reinterpret_cast<const double *>(src);
+	double *d = reinterpret_cast<double *>(&dst);
+	for (int i = threadIdx.x; i < (int)(sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) d[i] = s[i];
+	__syncthreads();
+}
+
+template <class Fam, int D>
+__global__ void __launch_bounds__(kThreads) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int bins_per_cta,
+                                                     double *__restrict__ partial)
+{
+	__shared__ WalkerCoef w;
+	load_walker(coefs + blockIdx.y, w);
+	const int begin = blockIdx.x * bins_per_cta;
+	const int end = min(g.L, begin + bins_per_cta);
+	double acc = 0.0, nact = 0.0;
+	if (w.valid) {
+		for (int i = begin + threadIdx.x; i < end; i += kThreads) {
+			const double f = g.f[i];
+			if (f > w.d.fcut) continue;  // the model is exactly zero there: no contribution to either inner product
+			cplx hp, hc;
+			polarizations_bin<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
+			nact += 1.0;
+#pragma unroll
+			for (int d = 0; d < D; d++) {
+				const cplx r = project_bin(w.det[d], hp, hc, f, true);
+				const size_t k = (size_t)d * g.L + i;
+				const double hh = r.re * r.re + r.im * r.im;
+				const double dh = g.dre[k] * r.re + g.dim[k] * r.im;
+				acc += g.wq[k] * (hh - 2.0 * dh);
+			}
+		}
+	}
+	block_sum2(acc, nact);
+	if (threadIdx.x == 0) {
+		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+		p[0] = w.valid ? acc : NAN;
+		p[1] = nact;
+	}
+}
+
+// logL[w] = -1/2 * prefactor * sum_chunks partial        (Log_Likelihood_internal: -0.5*(HH - 2*DH), src/mcmc_gw.cpp:866)
+__global__ void k_finish(const double *__restrict__ partial, int W, int chunks, double prefactor, double *__restrict__ logL,
+                         unsigned long long *__restrict__ active_total)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	double s = 0, n = 0;
+	for (int c = 0; c < chunks; c++) {
+		s += partial[2 * ((size_t)w * chunks + c)];
+		n += partial[2 * ((size_t)w * chunks + c) + 1];
+	}
+	logL[w] = -0.5 * (prefactor * s);
+	if (active_total) atomicAdd(active_total, (unsigned long long)n);
+}
+
+template <class Fam>
+__global__ void __launch_bounds__(kThreads) k_waveform(const WalkerCoef *__restrict__ coefs, GridPtrs g, double *hp_re,
+                                                      double *hp_im, double *hc_re, double *hc_im)
+{
+	__shared__ WalkerCoef w;
+	load_walker(coefs + blockIdx.y, w);
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= g.L) return;
+	cplx hp{NAN, NAN}, hc{NAN, NAN};
+	if (w.valid) polarizations_bin<Fam>(w, g.f[i], g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
+	const size_t k = (size_t)blockIdx.y * g.L + i;
+	if (hp_re) hp_re[k] = hp.re;
+	if (hp_im) hp_im[k] = hp.im;
+	if (hc_re) hc_re[k] = hc.re;
+	if (hc_im) hc_im[k] = hc.im;
+}
+
+// responses of detectors [d0, d0+nd) of the network; out shape [W][nd][L]
+template <class Fam>
+__global__ void __launch_bounds__(kThreads) k_response(const WalkerCoef *__restrict__ coefs, GridPtrs g, int d0, int nd,
+                                                      int with_shift, double *re, double *im)
+{
+	__shared__ WalkerCoef w;
+	load_walker(coefs + blockIdx.y, w);
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= g.L) return;
+	cplx hp{NAN, NAN}, hc{NAN, NAN};
+	const double f = g.f[i];
+	if (w.valid) polarizations_bin<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
+	for (int d = 0; d < nd; d++) {
+		const cplx r = project_bin(w.det[d0 + d], hp, hc, f, with_shift != 0);
+		const size_t k = ((size_t)blockIdx.y * nd + d) * g.L + i;
+		re[k] = r.re;
+		im[k] = r.im;
+	}
+}
+
+__global__ void k_antenna(int W, const double *RA, const double *DEC, const double *psi, double gmst, Network net,
+                          double *Fp, double *Fc, double *dt)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	DetCoef dc[GWAT_B200_MAX_DETECTORS];
+	detector_setup(net, RA[w], DEC[w], psi[w], gmst, dc);
+	for (int d = 0; d < net.D; d++) {
+		Fp[(size_t)w * net.D + d] = dc[d].Fplus;
+		Fc[(size_t)w * net.D + d] = dc[d].Fcross;
+		dt[(size_t)w * net.D + d] = dtoa_between(net.row[0] + 9, net.row[d] + 9, RA[w], DEC[w], gmst);
+	}
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct gwat_b200_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+	std::mutex mu;
+	// network
+	int D = 0, L = 0;
+	bool have_data = false, gaussleg = false, log10F = false;
+	Network net{};
+	double pref_like = 0, pref_fisher = 0;
+	double *d_grid = nullptr;  // f, sf_hi, sf_lo, logf : 4*L
+	double *d_net = nullptr;   // wq, dre, dim : 3*D*L
+	std::vector<double> h_f;
+	// scratch (grown on demand)
+	size_t cap_walkers = 0, cap_partial = 0, cap_params = 0, cap_out = 0, cap_src = 0;
+	WalkerCoef *d_coef = nullptr;
+	double *d_partial = nullptr;
+	double *d_params = nullptr;
+	double *d_out = nullptr;
+	gwat_b200_source *d_src = nullptr;
+	unsigned long long *d_active = nullptr;
+	// introspection
+	long long launches = 0;
+	double last_ms = 0;
+	long long last_active = 0;
+};
+
+namespace {
+
+std::string g_create_error;
+
+int fail(gwat_b200_ctx *c, int code, const std::string &msg)
+{
+	if (c) c->err = msg;
+	else g_create_error = msg;
+	return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                              \
+	do {                                                                                                   \
+		cudaError_t e_ = (expr);                                                                             \
+		if (e_ != cudaSuccess)                                                                               \
+			return fail(ctx, GWAT_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+	} while (0)
+
+template <class T>
+int grow(gwat_b200_ctx *c, T *&ptr, size_t &cap, size_t need)
+{
+	if (need <= cap) return 0;
+	if (ptr) CUDA_TRY(c, cudaFree(ptr));
+	ptr = nullptr;
+	cap = 0;
+	const size_t n = need + need / 4;
+	CUDA_TRY(c, cudaMalloc((void **)&ptr, n * sizeof(T)));
+	cap = n;
+	return 0;
+}
+
+GridPtrs grid_ptrs(const gwat_b200_ctx *c)
+{
+	GridPtrs g;
+	const size_t L = c->L, DL = (size_t)c->D * c->L;
+	g.f = c->d_grid;
+	g.sf_hi = c->d_grid + L;
+	g.sf_lo = c->d_grid + 2 * L;
+	g.logf = c->d_grid + 3 * L;
+	g.wq = c->d_net;
+	g.dre = c->d_net + DL;
+	g.dim = c->d_net + 2 * DL;
+	g.L = c->L;
+	return g;
+}
+
+int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, RepackPlan &plan)
+{
+	std::memset(&plan, 0, sizeof(plan));
+	plan.dimension = dimension;
+	plan.pv2 = desc.pv2;
+	plan.nrt = desc.nrt;
+	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
+	plan.gimr = desc.gimr && !plan.ppe;
+	plan.alpha_unit_fix = (desc.theory == THEORY_DCS || desc.theory == THEORY_EDGB);
+	plan.mcmc = 1;
+	if (mod) plan.mod = *mod;
+	else {
+		std::memset(&plan.mod, 0, sizeof(plan.mod));
+		plan.mod.tidal_love = 1;
+	}
+	if (dimension < 1 || dimension > GWAT_B200_MAX_DIM) return -1;
+	if (plan.mod.ppE_Nmod < 0 || plan.mod.ppE_Nmod > GWAT_B200_MAX_MOD) return -1;
+	int base = desc.pv2 ? 15 : 11;
+	if (desc.nrt && !desc.pv2) base += plan.mod.tidal_love ? 1 : 2;
+	int mods = 0;
+	if (plan.ppe) mods = plan.mod.ppE_Nmod;
+	else if (plan.gimr)
+		mods = plan.mod.gIMR_Nmod_phi + plan.mod.gIMR_Nmod_sigma + plan.mod.gIMR_Nmod_beta + plan.mod.gIMR_Nmod_alpha;
+	if (dimension != base + mods) return -1;
+	return 0;
+}
+
+// Run the statement given as trailing arguments with `Fam` bound to the kernel family of `desc`.
+#define GWAT_DISPATCH_FAMILY(desc, ...)                                                                                  \
+	do {                                                                                                                   \
+		switch ((desc).family_id) {                                                                                          \
+		case FAM_D: { typedef Family<BASE_D, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                              \
+		case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }                  \
+		case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }                       \
+		case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                          \
+		default: return fail(ctx, GWAT_B200_ERR_METHOD, std::string("generation_method not implemented: ") + (desc).base);   \
+		}                                                                                                                    \
+	} while (0)
+
+template <class Fam>
+int launch_loglike(gwat_b200_ctx *ctx, int W, int chunks, int bins_per_cta, cudaStream_t st)
+{
+	const GridPtrs g = grid_ptrs(ctx);
+	const dim3 grid(chunks, W);
+	switch (ctx->D) {
+	case 1: k_loglike<Fam, 1><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 2: k_loglike<Fam, 2><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 3: k_loglike<Fam, 3><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 4: k_loglike<Fam, 4><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 5: k_loglike<Fam, 5><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	default: return -1;
+	}
+	return 0;
+}
+
+// How the bin axis is cut into CTAs: enough CTAs to fill 148 SMs a few times over, chunks a multiple of the block size.
+void choose_chunks(int W, int L, int &chunks, int &bins_per_cta)
+{
+	const long long target_ctas = 148LL * 8;
+	long long want = (target_ctas + W - 1) / W;
+	long long max_chunks = (L + kThreads - 1) / kThreads;
+	if (want < 1) want = 1;
+	if (want > max_chunks) want = max_chunks;
+	long long per = (L + want - 1) / want;
+	per = ((per + kThreads - 1) / kThreads) * kThreads;
+	// keep the per-thread trip count bounded so the tail CTA of a long grid does not dominate
+	const long long cap = 64LL * kThreads;
+	if (per > cap) per = cap;
+	bins_per_cta = (int)per;
+	chunks = (int)((L + per - 1) / per);
+}
+
+// The shared tail of every likelihood entry point: coefficients are in ctx->d_coef.
+int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_logL, cudaStream_t st)
+{
+	int chunks, bins_per_cta;
+	choose_chunks(W, ctx->L, chunks, bins_per_cta);
+	if (grow(ctx, ctx->d_partial, ctx->cap_partial, (size_t)2 * W * chunks)) return GWAT_B200_ERR_CUDA;
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), st));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, chunks, bins_per_cta, st)) return fail(
+	                               ctx, GWAT_B200_ERR_STATE, "unsupported detector count"));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+	k_finish<<<(W + 127) / 128, 128, 0, st>>>(ctx->d_partial, W, chunks, ctx->pref_like, d_logL, ctx->d_active);
+	ctx->launches += 2;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return 0;
+}
+
+int collect_stats(gwat_b200_ctx *ctx, cudaStream_t st)
+{
+	unsigned long long act = 0;
+	CUDA_TRY(ctx, cudaMemcpyAsync(&act, ctx->d_active, sizeof(act), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	float ms = 0;
+	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->last_ms = ms;
+	ctx->last_active = (long long)act;
+	return 0;
+}
+
+int check_ready(gwat_b200_ctx *ctx, bool need_data)
+{
+	if (!ctx) return GWAT_B200_ERR_ARG;
+	if (ctx->L <= 0) return fail(ctx, GWAT_B200_ERR_STATE, "gwat_b200_set_network has not been called");
+	if (need_data && !ctx->have_data) return fail(ctx, GWAT_B200_ERR_STATE, "the network was set without data");
+	return 0;
+}
+
+template <class Fam>
+void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, cudaStream_t st)
+{
+	k_setup_src<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_src, W, ctx->net, ctx->d_coef);
+}
+
+int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st)
+{
+	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, h_src, sizeof(gwat_b200_source) * W, cudaMemcpyHostToDevice, st));
+	GWAT_DISPATCH_FAMILY(desc, launch_setup_src<Fam>(ctx, W, ctx->d_src, st));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int gwat_b200_abi_version(void) { return GWAT_B200_ABI_VERSION; }
+
+void gwat_b200_source_init(gwat_b200_source *src)
+{
+	if (src) source_defaults(*src);
+}
+
+void gwat_b200_mod_init(gwat_b200_mod *mod)
+{
+	if (!mod) return;
+	std::memset(mod, 0, sizeof(*mod));
+	mod->tidal_love = 1;
+}
+
+int gwat_b200_ctx_create(gwat_b200_ctx **out, int device)
+{
+	if (!out) return GWAT_B200_ERR_ARG;
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0)
+		return fail(nullptr, GWAT_B200_ERR_CUDA,
+		            std::string("no usable CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+	if (device < 0 || device >= n) return fail(nullptr, GWAT_B200_ERR_ARG, "device ordinal out of range");
+	gwat_b200_ctx *c = new gwat_b200_ctx;
+	c->device = device;
+	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&c->d_active, sizeof(unsigned long long))) != cudaSuccess) {
+		const std::string msg = std::string("context creation: ") + cudaGetErrorString(e);
+		delete c;
+		return fail(nullptr, GWAT_B200_ERR_CUDA, msg);
+	}
+	*out = c;
+	return GWAT_B200_OK;
+}
+
+void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(c->d_grid);
+	cudaFree(c->d_net);
+	cudaFree(c->d_coef);
+	cudaFree(c->d_partial);
+	cudaFree(c->d_params);
+	cudaFree(c->d_out);
+	cudaFree(c->d_src);
+	cudaFree(c->d_active);
+	cudaEventDestroy(c->ev0);
+	cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char *gwat_b200_last_error(const gwat_b200_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detectors, int L, const double *f,
+                          const double *psd, const double *data_re, const double *data_im, const double *weights,
+                          const char *integration_method, int log10F)
+{
+	if (!ctx) return GWAT_B200_ERR_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (D < 1 || D > GWAT_B200_MAX_DETECTORS || !detectors || L < 4 || !f || !psd)
+		return fail(ctx, GWAT_B200_ERR_ARG, "set_network: bad detector count, length or NULL array");
+	if ((data_re == nullptr) != (data_im == nullptr)) return fail(ctx, GWAT_B200_ERR_ARG, "set_network: data_re/data_im");
+	const std::string integ = integration_method ? integration_method : "SIMPSONS";
+	const bool gl = integ == "GAUSSLEG";
+	if (!gl && integ != "SIMPSONS") return fail(ctx, GWAT_B200_ERR_ARG, "set_network: integration_method must be SIMPSONS or GAUSSLEG");
+	if (gl && !weights) return fail(ctx, GWAT_B200_ERR_ARG, "set_network: GAUSSLEG needs weights");
+	Network net{};
+	net.D = D;
+	for (int d = 0; d < D; d++) {
+		const int id = detector_index(detectors[d]);
+		if (id < 0) return fail(ctx, GWAT_B200_ERR_ARG, std::string("set_network: unsupported detector ") + (detectors[d] ? detectors[d] : "(null)"));
+	}
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	for (int d = 0; d < D; d++) std::memcpy(net.row[d], hosttab::gwat_detector_table[detector_index(detectors[d])], sizeof(double) * 13);
+
+	std::vector<double> hi, lo, lg;
+	build_frequency_tables(f, L, hi, lo, lg);
+	std::vector<double> grid((size_t)4 * L);
+	std::memcpy(grid.data(), f, sizeof(double) * L);
+	std::memcpy(grid.data() + L, hi.data(), sizeof(double) * L);
+	std::memcpy(grid.data() + 2 * (size_t)L, lo.data(), sizeof(double) * L);
+	std::memcpy(grid.data() + 3 * (size_t)L, lg.data(), sizeof(double) * L);
+	const size_t DL = (size_t)D * L;
+	std::vector<double> netbuf(3 * DL, 0.0);
+	for (int d = 0; d < D; d++)
+		for (int i = 0; i < L; i++) {
+			const size_t k = (size_t)d * L + i;
+			netbuf[k] = quadrature_coefficient(i, L, gl, log10F != 0, weights, f) / psd[k];
+			if (data_re) {
+				netbuf[DL + k] = data_re[k];
+				netbuf[2 * DL + k] = data_im[k];
+			}
+		}
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->d_grid) cudaFree(ctx->d_grid);
+	if (ctx->d_net) cudaFree(ctx->d_net);
+	ctx->d_grid = ctx->d_net = nullptr;
+	ctx->L = 0;
+	CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_grid, sizeof(double) * grid.size()));
+	CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_net, sizeof(double) * netbuf.size()));
+	CUDA_TRY(ctx, cudaMemcpy(ctx->d_grid, grid.data(), sizeof(double) * grid.size(), cudaMemcpyHostToDevice));
+	CUDA_TRY(ctx, cudaMemcpy(ctx->d_net, netbuf.data(), sizeof(double) * netbuf.size(), cudaMemcpyHostToDevice));
+	ctx->D = D;
+	ctx->L = L;
+	ctx->net = net;
+	ctx->have_data = data_re != nullptr;
+	ctx->gaussleg = gl;
+	ctx->log10F = log10F != 0;
+	ctx->pref_like = quadrature_prefactor(L, gl, f, false);
+	ctx->pref_fisher = quadrature_prefactor(L, gl, f, true);
+	ctx->h_f.assign(f, f + L);
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension,
+                                     int W, const double *d_params, double gmst, double T_segment, double *d_logL,
+                                     void *stream)
+{
+	if (int rc = check_ready(ctx, true)) return rc;
+	if (W < 0 || (W > 0 && (!d_params || !d_logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	RepackPlan plan;
+	if (make_plan(desc, mod, dimension, plan) != 0)
+		return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: dimension does not match the method and modification struct");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_params, W, plan, ctx->net, gmst, T_segment,
+	                                                                              ctx->d_coef, nullptr));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return run_loglike(ctx, desc, W, d_logL, st);
+}
+
+int gwat_b200_loglike_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                                 const double *params, double gmst, double T_segment, double *logL)
+{
+	if (int rc = check_ready(ctx, true)) return rc;
+	if (W < 0 || (W > 0 && (!params || !logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	{
+		std::lock_guard<std::mutex> lock(ctx->mu);
+		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+		if (grow(ctx, ctx->d_params, ctx->cap_params, (size_t)W * dimension)) return GWAT_B200_ERR_CUDA;
+		if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (int rc = gwat_b200_loglike_mcmc_batch_dev(ctx, method, mod, dimension, W, ctx->d_params, gmst, T_segment, ctx->d_out, nullptr))
+		return rc;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaMemcpyAsync(logL, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+	return collect_stats(ctx, ctx->stream);
+}
+
+int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *sources, double *logL)
+{
+	if (int rc = check_ready(ctx, true)) return rc;
+	if (W < 0 || (W > 0 && (!sources || !logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (int rc = setup_from_sources(ctx, desc, W, sources, ctx->stream)) return rc;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	if (int rc = run_loglike(ctx, desc, W, ctx->d_out, ctx->stream)) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(logL, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+	return collect_stats(ctx, ctx->stream);
+}
+
+int gwat_b200_fourier_waveform_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *sources,
+                                     double *hplus_re, double *hplus_im, double *hcross_re, double *hcross_im)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && !sources)) return fail(ctx, GWAT_B200_ERR_ARG, "fourier_waveform_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (int rc = setup_from_sources(ctx, desc, W, sources, st)) return rc;
+	const size_t n = (size_t)W * ctx->L;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, 4 * n)) return GWAT_B200_ERR_CUDA;
+	double *o = ctx->d_out;
+	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const GridPtrs g = grid_ptrs(ctx);
+	GWAT_DISPATCH_FAMILY(desc, k_waveform<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n, o + 2 * n, o + 3 * n));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	double *host[4] = {hplus_re, hplus_im, hcross_re, hcross_im};
+	for (int k = 0; k < 4; k++)
+		if (host[k]) CUDA_TRY(ctx, cudaMemcpyAsync(host[k], o + k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return GWAT_B200_OK;
+}
+
+static int response_common(gwat_b200_ctx *ctx, const char *method, int d0, int nd, int with_shift, int W,
+                           const gwat_b200_source *sources, double *re, double *im)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (int rc = setup_from_sources(ctx, desc, W, sources, st)) return rc;
+	const size_t n = (size_t)W * nd * ctx->L;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, 2 * n)) return GWAT_B200_ERR_CUDA;
+	double *o = ctx->d_out;
+	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const GridPtrs g = grid_ptrs(ctx);
+	GWAT_DISPATCH_FAMILY(desc, k_response<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, d0, nd, with_shift, o, o + n));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	CUDA_TRY(ctx, cudaMemcpyAsync(re, o, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(im, o + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_coherent_response_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *sources,
+                                      double *resp_re, double *resp_im)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && (!sources || !resp_re || !resp_im))) return fail(ctx, GWAT_B200_ERR_ARG, "coherent_response_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	return response_common(ctx, method, 0, ctx->D, 1, W, sources, resp_re, resp_im);
+}
+
+int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *method, const char *detector, int W,
+                                              const gwat_b200_source *sources, double *resp_re, double *resp_im)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && (!sources || !resp_re || !resp_im))) return fail(ctx, GWAT_B200_ERR_ARG, "fourier_detector_response_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	const int id = detector_index(detector);
+	int d0 = -1;
+	if (id >= 0) {
+		for (int d = 0; d < ctx->D; d++)
+			if (std::memcmp(ctx->net.row[d], hosttab::gwat_detector_table[id], sizeof(double) * 13) == 0) d0 = d;
+	}
+	if (d0 < 0) return fail(ctx, GWAT_B200_ERR_ARG, "fourier_detector_response_batch: detector is not part of the network");
+	return response_common(ctx, method, d0, 1, 0, W, sources, resp_re, resp_im);
+}
+
+int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                                const double *params, double gmst, gwat_b200_source *sources)
+{
+	if (!ctx) return GWAT_B200_ERR_ARG;
+	if (W < 0 || (W > 0 && (!params || !sources))) return fail(ctx, GWAT_B200_ERR_ARG, "repack_mcmc_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	RepackPlan plan;
+	if (make_plan(desc, mod, dimension, plan) != 0)
+		return fail(ctx, GWAT_B200_ERR_ARG, "repack_mcmc_batch: dimension does not match the method and modification struct");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (grow(ctx, ctx->d_params, ctx->cap_params, (size_t)W * dimension)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, st));
+	// T_segment = 0 and the sign flip below leave tc as sampled: this entry point mirrors repack_parameters alone
+	typedef Family<BASE_D, PPE_NONE, false, false> AnyFam;
+	k_setup_mcmc<AnyFam><<<(W + 127) / 128, 128, 0, st>>>(ctx->d_params, W, plan, ctx->net, gmst, 0.0, nullptr, ctx->d_src);
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	CUDA_TRY(ctx, cudaMemcpyAsync(sources, ctx->d_src, sizeof(gwat_b200_source) * W, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	for (int w = 0; w < W; w++) sources[w].tc = -sources[w].tc;
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const double *DEC, const double *psi, double gmst,
+                            double *Fplus, double *Fcross, double *dtoa)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && (!RA || !DEC || !psi || !Fplus || !Fcross || !dtoa))) return fail(ctx, GWAT_B200_ERR_ARG, "antenna_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const size_t nin = 3 * (size_t)W, nout = 3 * (size_t)W * ctx->D;
+	if (grow(ctx, ctx->d_params, ctx->cap_params, nin)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, nout)) return GWAT_B200_ERR_CUDA;
+	double *in = ctx->d_params, *o = ctx->d_out;
+	const size_t WD = (size_t)W * ctx->D;
+	CUDA_TRY(ctx, cudaMemcpyAsync(in, RA, sizeof(double) * W, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(in + W, DEC, sizeof(double) * W, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(in + 2 * (size_t)W, psi, sizeof(double) * W, cudaMemcpyHostToDevice, st));
+	k_antenna<<<(W + 127) / 128, 128, 0, st>>>(W, in, in + W, in + 2 * (size_t)W, gmst, ctx->net, o, o + WD, o + 2 * WD);
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	CUDA_TRY(ctx, cudaMemcpyAsync(Fplus, o, sizeof(double) * WD, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(Fcross, o + WD, sizeof(double) * WD, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(dtoa, o + 2 * WD, sizeof(double) * WD, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *, int, int, int, int, int, const gwat_b200_source *, double *)
+{
+	return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: not built yet");
+}
+
+long long gwat_b200_launch_count(const gwat_b200_ctx *c) { return c ? c->launches : 0; }
+double gwat_b200_last_kernel_ms(const gwat_b200_ctx *c) { return c ? c->last_ms : 0.0; }
+long long gwat_b200_last_active_bins(const gwat_b200_ctx *c) { return c ? c->last_active : 0; }
+
+}  // extern "C"

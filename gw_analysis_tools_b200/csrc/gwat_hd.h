@@ -1,0 +1,145 @@
+// Host/device portability layer and exact-arithmetic helpers for the gwat_b200 kernels.
+//
+// All waveform mathematics lives in headers of `GWAT_HD` functions so that the very same source is compiled
+//   * by nvcc for sm_100a (the product: kernels in gwat_engine.cu), and
+//   * by g++ as plain C++ for tests/host_harness.cpp (TEST ONLY: lets the CPU-only test tier check the kernels' logic
+//     against the oracle without a GPU; it is not reachable from the C ABI).
+#ifndef GWAT_HD_H
+#define GWAT_HD_H
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GWAT_HD __host__ __device__ __forceinline__
+#define GWAT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define GWAT_HD inline
+#define GWAT_HD_NOINLINE inline
+#endif
+
+#define GWAT_PI 3.14159265358979323846
+#define GWAT_TWOPI 6.283185307179586476925286766559005768
+
+namespace gwat {
+
+// ---- arithmetic that must not be contracted into FMAs ---------------------------------------------------------------
+// The reference is built by g++ -O2 for baseline x86-64: every a*b+c there rounds twice.  Where the phase is large
+// (1e3..1e6 rad) a fused multiply-add changes the result by up to half an ulp of the big term, so the phase chain uses
+// these helpers, which nvcc is not allowed to contract.  Amplitudes use ordinary operators (FMA contraction welcome).
+GWAT_HD double mul_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+	return __dmul_rn(a, b);
+#else
+	return a * b;
+#endif
+}
+GWAT_HD double add_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+	return __dadd_rn(a, b);
+#else
+	return a + b;
+#endif
+}
+GWAT_HD double sub_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+	return __dsub_rn(a, b);
+#else
+	return a - b;
+#endif
+}
+GWAT_HD double fma_rn(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+	return __fma_rn(a, b, c);
+#else
+	return fma(a, b, c);
+#endif
+}
+
+// ---- double-double (unevaluated sum hi+lo) --------------------------------------------------------------------------
+struct dd {
+	double hi, lo;
+};
+
+GWAT_HD dd two_sum(double a, double b)
+{
+	double s = add_rn(a, b);
+	double bb = sub_rn(s, a);
+	double e = add_rn(sub_rn(a, sub_rn(s, bb)), sub_rn(b, bb));
+	return dd{s, e};
+}
+GWAT_HD dd quick_two_sum(double a, double b)
+{
+	double s = add_rn(a, b);
+	double e = sub_rn(b, sub_rn(s, a));
+	return dd{s, e};
+}
+GWAT_HD dd two_prod(double a, double b)
+{
+	double p = mul_rn(a, b);
+	double e = fma_rn(a, b, -p);
+	return dd{p, e};
+}
+GWAT_HD dd dd_mul(dd a, dd b)
+{
+	dd p = two_prod(a.hi, b.hi);
+	double e = add_rn(p.lo, add_rn(mul_rn(a.hi, b.lo), mul_rn(a.lo, b.hi)));
+	return quick_two_sum(p.hi, e);
+}
+GWAT_HD dd dd_mul_d(dd a, double b)
+{
+	dd p = two_prod(a.hi, b);
+	double e = add_rn(p.lo, mul_rn(a.lo, b));
+	return quick_two_sum(p.hi, e);
+}
+GWAT_HD dd dd_add(dd a, dd b)
+{
+	dd s = two_sum(a.hi, b.hi);
+	double e = add_rn(s.lo, add_rn(a.lo, b.lo));
+	return quick_two_sum(s.hi, e);
+}
+// correctly rounded (to within a few 1e-32 relative) product of two double-doubles, returned as one double
+GWAT_HD double dd_mul_to_double(double ahi, double alo, double bhi, double blo)
+{
+	double p = mul_rn(ahi, bhi);
+	double e = fma_rn(ahi, bhi, -p);
+	e = fma_rn(ahi, blo, e);
+	e = fma_rn(alo, bhi, e);
+	return add_rn(p, e);
+}
+
+// The reference raises (M*f) to the power 1./6. -- the DOUBLE nearest to 1/6, not 1/6 itself (src/IMRPhenomD.cpp:882).
+// x^(fl(1/6)) = x^(1/6) * exp(-GWAT_SIXTH_DEFECT * ln x), a shift of up to ~0.7 ulp that has to be reproduced.
+#define GWAT_SIXTH 0.16666666666666666
+#define GWAT_SIXTH_DEFECT 9.2518585385429707e-18 /* 1/6 - fl(1/6) */
+
+// x^(fl(1/6)) as a double-double, accurate to ~1e-30 relative, for x > 0.
+GWAT_HD dd pow_sixth_dd(double x)
+{
+	// Newton iteration on y^6 = x in double-double, from the double estimate y0 = sqrt(cbrt(x)).
+	double y0 = sqrt(cbrt(x));
+	dd y = dd{y0, 0.0};
+	for (int it = 0; it < 2; it++) {
+		dd y2 = dd_mul(y, y);
+		dd y3 = dd_mul(y2, y);
+		dd y6 = dd_mul(y3, y3);
+		// residual r = y^6 - x  (x exact)
+		dd r = dd_add(y6, dd{-x, 0.0});
+		// y <- y - r / (6 y^5);   y^5 = y^6 / y  ~ y6.hi / y.hi  (double accuracy suffices for the correction)
+		double corr = (r.hi + r.lo) / (6.0 * (y6.hi / y.hi));
+		y = dd_add(y, dd{-corr, 0.0});
+	}
+	// exponent defect: multiply by (1 - defect*ln x)
+	double shift = -GWAT_SIXTH_DEFECT * log(x);
+	dd t = dd_mul_d(y, shift);
+	return dd_add(y, t);
+}
+
+GWAT_HD double sq(double x) { return x * x; }
+GWAT_HD double cube(double x) { return x * x * x; }
+
+}  // namespace gwat
+#endif

@@ -1,0 +1,184 @@
+// Sampling vector -> physical parameter record, per walker, on the device (GWAT_HD code).
+//
+// Reference being replaced (run on the host, once per likelihood call, with heap allocation of the beta arrays):
+//   MCMC_prep_params                         src/mcmc_gw.cpp:2492-2568   flags, f_ref = 20, dCS/EdGB unit change
+//   repack_parameters<double>("MCMC_"+m)     src/fisher.cpp:2167-2507    vector -> gen_params
+//   tc_ref = T - tc                          src/mcmc_gw.cpp:2466-2473   (T explicit here, see gwat_b200.h)
+// and, for the Fisher stencil, the inverse map and the non-MCMC parameterisation:
+//   unpack_parameters                        src/fisher.cpp:1841-2162
+//   repack_non_parameter_options             src/fisher.cpp:2513-2572
+#ifndef GWAT_REPACK_H
+#define GWAT_REPACK_H
+
+#include "gwat_model.h"
+
+namespace gwat {
+
+// What the host resolved from the method string + MCMC_modification_struct, passed to the kernels by value.
+struct RepackPlan {
+	int dimension;
+	int pv2;            // 15-dimensional precessing layout instead of the 11-dimensional aligned one
+	int nrt;            // tidal parameter(s) at index 11 (12)
+	int ppe;            // last ppE_Nmod entries are betas (ppE_* and theory-mapped methods)
+	int gimr;           // last (phi+sigma+beta+alpha) entries are fractional deviations
+	int alpha_unit_fix; // dCS/EdGB: entry [base] is sqrt(alpha) in km -> alpha^2 in s^4 (src/mcmc_gw.cpp:2560-2565)
+	int mcmc;           // "MCMC_" parameterisation (sin DEC, cos iota, ln DL, ln Mc); else the physical one
+	gwat_b200_mod mod;
+};
+
+GWAT_HD void source_defaults(gwat_b200_source &s)
+{
+	// member defaults of gen_params_base (include/gwat/util.h:125-285)
+	s.mass1 = s.mass2 = s.Luminosity_Distance = 0;
+	for (int i = 0; i < 3; i++) s.spin1[i] = s.spin2[i] = 0;
+	s.tc = 0;
+	s.phiRef = 0;
+	s.f_ref = 0;
+	s.psi = 0;
+	s.incl_angle = 0;
+	s.RA = s.DEC = s.gmst = 0;
+	s.theta = s.phi = s.theta_l = s.phi_l = 0;
+	s.tidal1 = s.tidal2 = s.tidal_s = s.tidal_a = s.tidal_weighted = s.delta_tidal_weighted = -1;
+	s.diss_tidal1 = s.diss_tidal2 = s.diss_tidal_s = s.diss_tidal_a = s.diss_tidal_weighted = -1;
+	s.chip = -1;
+	s.phip = -1;
+	for (int i = 0; i < GWAT_B200_MAX_MOD; i++) {
+		s.betappe[i] = s.bppe[i] = 0;
+		s.delta_phi[i] = s.delta_sigma[i] = s.delta_beta[i] = s.delta_alpha[i] = 0;
+		s.phii[i] = s.sigmai[i] = s.betai[i] = s.alphai[i] = 0;
+	}
+	s.Nmod = s.Nmod_phi = s.Nmod_sigma = s.Nmod_beta = s.Nmod_alpha = 0;
+	s.PNorder = 35;
+	s.shift_time = 1;
+	s.shift_phase = 1;
+	s.sky_average = 0;
+	s.tidal_love = 1;
+	s.tidal_love_error = 0;
+	s.NSflag1 = s.NSflag2 = 0;
+	s.dep_postmerger = 0;
+	s.equatorial_orientation = 0;
+	s.horizon_coord = 0;
+	s.reserved_[0] = s.reserved_[1] = 0;
+}
+
+// calculate_mass1 / calculate_mass2 (src/util.cpp:1516-1540)
+GWAT_HD double mass1_of(double chirpmass, double eta)
+{
+	const double etapow = pow(eta, 3. / 5);
+	return 1. / 2 * (chirpmass / etapow + sqrt(1. - 4 * eta) * chirpmass / etapow);
+}
+GWAT_HD double mass2_of(double chirpmass, double eta)
+{
+	const double etapow = pow(eta, 3. / 5);
+	return 1. / 2 * (chirpmass / etapow - sqrt(1. - 4 * eta) * chirpmass / etapow);
+}
+
+GWAT_HD double clamped_acos(double x)
+{
+	// "Fishers don't necessarily respect the bounds of acos" (src/fisher.cpp:2190-2213)
+	if (x > 1) return 0;
+	if (x < -1) return GWAT_PI;
+	return acos(x);
+}
+
+// The modification tails shared by both parameterisations (src/fisher.cpp:2399-2505)
+GWAT_HD void repack_tails(const double *v, const RepackPlan &plan, gwat_b200_source &s)
+{
+	const int dim = plan.dimension;
+	if (plan.nrt && !plan.pv2) {
+		if (s.tidal_love) {
+			s.tidal_s = exp(v[11]);
+		} else {
+			s.tidal1 = exp(v[11]);
+			s.tidal2 = exp(v[12]);
+		}
+	}
+	if (plan.ppe) {
+		const int base = dim - s.Nmod;
+		for (int i = 0; i < s.Nmod; i++) s.betappe[i] = v[base + i];
+	} else if (plan.gimr) {
+		const int mods = s.Nmod_phi + s.Nmod_sigma + s.Nmod_beta + s.Nmod_alpha;
+		int at = dim - mods;
+		for (int i = 0; i < s.Nmod_phi; i++) s.delta_phi[i] = v[at++];
+		for (int i = 0; i < s.Nmod_sigma; i++) s.delta_sigma[i] = v[at++];
+		for (int i = 0; i < s.Nmod_beta; i++) s.delta_beta[i] = v[at++];
+		for (int i = 0; i < s.Nmod_alpha; i++) s.delta_alpha[i] = v[at++];
+	}
+}
+
+// The non-parameter options MCMC_prep_params sets (src/mcmc_gw.cpp:2494-2559).
+GWAT_HD void apply_mod_options(const RepackPlan &plan, gwat_b200_source &s)
+{
+	const gwat_b200_mod &m = plan.mod;
+	s.tidal_love = m.tidal_love;
+	s.tidal_love_error = m.tidal_love_error;
+	s.NSflag1 = m.NSflag1;
+	s.NSflag2 = m.NSflag2;
+	if (plan.ppe) {
+		s.Nmod = m.ppE_Nmod;
+		for (int i = 0; i < GWAT_B200_MAX_MOD; i++) s.bppe[i] = m.bppe[i];
+	} else if (plan.gimr) {
+		s.Nmod_phi = m.gIMR_Nmod_phi;
+		s.Nmod_sigma = m.gIMR_Nmod_sigma;
+		s.Nmod_beta = m.gIMR_Nmod_beta;
+		s.Nmod_alpha = m.gIMR_Nmod_alpha;
+		for (int i = 0; i < GWAT_B200_MAX_MOD; i++) {
+			s.phii[i] = m.gIMR_phii[i];
+			s.sigmai[i] = m.gIMR_sigmai[i];
+			s.betai[i] = m.gIMR_betai[i];
+			s.alphai[i] = m.gIMR_alphai[i];
+		}
+	}
+}
+
+// One walker of MCMC_likelihood_wrapper's parameter handling: param[dimension] -> record with tc = T_segment - tc.
+GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, double gmst, double T_segment,
+                                gwat_b200_source &s)
+{
+	source_defaults(s);
+	// MCMC_prep_params
+	s.sky_average = 0;
+	s.f_ref = 20;
+	s.shift_time = 1;
+	s.shift_phase = 1;
+	s.gmst = gmst;
+	s.equatorial_orientation = 0;
+	s.horizon_coord = 0;
+	apply_mod_options(plan, s);
+	double v[GWAT_B200_MAX_DIM];
+	for (int i = 0; i < plan.dimension; i++) v[i] = param[i];
+	if (plan.alpha_unit_fix) {
+		const int base = plan.dimension - plan.mod.ppE_Nmod;
+		const double x = v[base] / (GWAT_C_SI / 1000.);
+		v[base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
+	}
+	// repack_parameters, "MCMC_" branch, sky_average = false
+	s.mass1 = mass1_of(exp(v[7]), v[8]);
+	s.mass2 = mass2_of(exp(v[7]), v[8]);
+	s.Luminosity_Distance = exp(v[6]);
+	s.RA = v[0];
+	s.DEC = asin(v[1]);
+	s.psi = v[2];
+	s.incl_angle = acos(v[3]);
+	s.phiRef = v[4];
+	s.tc = v[5];
+	if (plan.pv2) {
+		const double th1 = clamped_acos(v[11]), th2 = clamped_acos(v[12]);
+		// transform_sph_cart (src/util.cpp:1909-1914)
+		s.spin1[0] = v[9] * sin(th1) * cos(v[13]);
+		s.spin1[1] = v[9] * sin(th1) * sin(v[13]);
+		s.spin1[2] = v[9] * cos(th1);
+		s.spin2[0] = v[10] * sin(th2) * cos(v[14]);
+		s.spin2[1] = v[10] * sin(th2) * sin(v[14]);
+		s.spin2[2] = v[10] * cos(th2);
+	} else {
+		s.spin1[2] = v[9];
+		s.spin2[2] = v[10];
+	}
+	repack_tails(v, plan, s);
+	// MCMC_likelihood_extrinsic: tc is measured back from the end of the segment (src/mcmc_gw.cpp:2467,2473)
+	s.tc = T_segment - s.tc;
+}
+
+}  // namespace gwat
+#endif

@@ -1,0 +1,204 @@
+"""ctypes binding of the product library ``libgwat_b200.so`` (the C ABI of ``include/gwat_b200.h``).
+
+This is plumbing only: every numerical operation happens in the CUDA kernels behind the C ABI.  There is no CPU path;
+``load_library`` raises if the extension was not built and ``Context`` raises if no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgwat_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+EXPORTS = [
+    "gwat_b200_abi_version", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
+    "gwat_b200_ctx_destroy", "gwat_b200_last_error", "gwat_b200_set_network", "gwat_b200_loglike_mcmc_batch",
+    "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_fourier_waveform_batch",
+    "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
+    "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
+    "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
+]
+
+
+class GwatB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("gwat_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def load_library():
+    """Load the CUDA extension.  Fails loudly when it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("gwat_b200 CUDA extension missing: %s (run __graft_entry__.build()); there is no CPU fallback"
+                              % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.gwat_b200_last_error.restype = C.c_char_p
+        lib.gwat_b200_last_error.argtypes = [C.c_void_p]
+        lib.gwat_b200_launch_count.restype = C.c_longlong
+        lib.gwat_b200_launch_count.argtypes = [C.c_void_p]
+        lib.gwat_b200_last_active_bins.restype = C.c_longlong
+        lib.gwat_b200_last_active_bins.argtypes = [C.c_void_p]
+        lib.gwat_b200_last_kernel_ms.restype = C.c_double
+        lib.gwat_b200_last_kernel_ms.argtypes = [C.c_void_p]
+        lib.gwat_b200_ctx_destroy.argtypes = [C.c_void_p]
+        lib.gwat_b200_ctx_destroy.restype = None
+        if lib.gwat_b200_abi_version() != abi.ABI_VERSION:
+            raise ImportError("gwat_b200 ABI mismatch")
+        _lib = lib
+    return _lib
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _src_array(sources):
+    if isinstance(sources, abi.Source):
+        sources = [sources]
+    if isinstance(sources, C.Array):
+        return sources, len(sources)
+    return (abi.Source * len(sources))(*sources), len(sources)
+
+
+class Context:
+    """One GPU's worth of state: the detector network, the frequency grid and scratch buffers."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.gwat_b200_ctx_create(C.byref(self._h), int(device))
+        if rc != 0:
+            raise GwatB200Error(rc, self._lib.gwat_b200_last_error(None).decode())
+        self.device = int(device)
+        self.D = 0
+        self.L = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gwat_b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GwatB200Error(rc, self._lib.gwat_b200_last_error(self._h).decode())
+
+    # ---- network ---------------------------------------------------------------------------------------------------
+    def set_network(self, detectors, frequencies, psd, data=None, weights=None, integration_method="SIMPSONS",
+                    log10F=False):
+        f = _f64(frequencies)
+        psd = _f64(psd)
+        D, L = len(detectors), f.size
+        assert psd.shape == (D, L), "psd must have shape [D][L]"
+        dre = dim = None
+        if data is not None:
+            data = np.asarray(data)
+            assert data.shape == (D, L)
+            dre, dim = _f64(data.real), _f64(data.imag)
+        w = _f64(weights)
+        names = (C.c_char_p * D)(*[d.encode() for d in detectors])
+        self._check(self._lib.gwat_b200_set_network(self._h, D, names, L, _p(f), _p(psd), _p(dre), _p(dim), _p(w),
+                                                    integration_method.encode(), int(bool(log10F))))
+        self.D, self.L = D, L
+
+    # ---- likelihood ------------------------------------------------------------------------------------------------
+    def loglike_mcmc_batch(self, method, params, gmst, T_segment, mod=None):
+        params = _f64(params)
+        W, P = params.shape
+        out = np.empty(W)
+        self._check(self._lib.gwat_b200_loglike_mcmc_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                                           P, W, _p(params), C.c_double(gmst), C.c_double(T_segment), _p(out)))
+        return out
+
+    def loglike_mcmc_batch_dev(self, method, d_params_ptr, W, P, gmst, T_segment, d_logL_ptr, mod=None, stream=None):
+        """Device-pointer variant (integers from ``tensor.data_ptr()``); asynchronous on ``stream`` (a raw cudaStream_t)."""
+        self._check(self._lib.gwat_b200_loglike_mcmc_batch_dev(
+            self._h, method.encode(), C.byref(mod) if mod is not None else None, int(P), int(W), C.c_void_p(d_params_ptr),
+            C.c_double(gmst), C.c_double(T_segment), C.c_void_p(d_logL_ptr), C.c_void_p(stream or 0)))
+
+    def loglike_batch(self, method, sources):
+        arr, W = _src_array(sources)
+        out = np.empty(W)
+        self._check(self._lib.gwat_b200_loglike_batch(self._h, method.encode(), W, arr, _p(out)))
+        return out
+
+    # ---- waveforms / responses -----------------------------------------------------------------------------------------
+    def fourier_waveform_batch(self, method, sources):
+        arr, W = _src_array(sources)
+        o = [np.empty((W, self.L)) for _ in range(4)]
+        self._check(self._lib.gwat_b200_fourier_waveform_batch(self._h, method.encode(), W, arr, *[_p(x) for x in o]))
+        return o[0] + 1j * o[1], o[2] + 1j * o[3]
+
+    def coherent_response_batch(self, method, sources):
+        arr, W = _src_array(sources)
+        re, im = np.empty((W, self.D, self.L)), np.empty((W, self.D, self.L))
+        self._check(self._lib.gwat_b200_coherent_response_batch(self._h, method.encode(), W, arr, _p(re), _p(im)))
+        return re + 1j * im
+
+    def fourier_detector_response_batch(self, method, detector, sources):
+        arr, W = _src_array(sources)
+        re, im = np.empty((W, self.L)), np.empty((W, self.L))
+        self._check(self._lib.gwat_b200_fourier_detector_response_batch(self._h, method.encode(), detector.encode(), W, arr,
+                                                                        _p(re), _p(im)))
+        return re + 1j * im
+
+    def fisher_numerical_batch(self, method, sources, dimension, order=4, detector_index=-1, reference_index=0):
+        arr, S = _src_array(sources)
+        out = np.empty((S, dimension, dimension))
+        self._check(self._lib.gwat_b200_fisher_numerical_batch(self._h, method.encode(), int(detector_index),
+                                                               int(reference_index), int(dimension), int(order), S, arr,
+                                                               _p(out)))
+        return out
+
+    # ---- helpers ---------------------------------------------------------------------------------------------------
+    def repack_mcmc_batch(self, method, params, gmst, mod=None):
+        params = _f64(params)
+        W, P = params.shape
+        out = (abi.Source * W)()
+        self._check(self._lib.gwat_b200_repack_mcmc_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                                          P, W, _p(params), C.c_double(gmst), out))
+        return out
+
+    def antenna_batch(self, RA, DEC, psi, gmst):
+        RA, DEC, psi = _f64(RA), _f64(DEC), _f64(psi)
+        W = RA.size
+        fp, fc, dt = np.empty((W, self.D)), np.empty((W, self.D)), np.empty((W, self.D))
+        self._check(self._lib.gwat_b200_antenna_batch(self._h, W, _p(RA), _p(DEC), _p(psi), C.c_double(gmst), _p(fp), _p(fc),
+                                                      _p(dt)))
+        return fp, fc, dt
+
+    # ---- introspection ---------------------------------------------------------------------------------------------
+    @property
+    def launch_count(self):
+        return int(self._lib.gwat_b200_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.gwat_b200_last_kernel_ms(self._h))
+
+    @property
+    def last_active_bins(self):
+        return int(self._lib.gwat_b200_last_active_bins(self._h))
