@@ -10,13 +10,9 @@
 #ifndef GWAT_BINS_H
 #define GWAT_BINS_H
 
-#include "gwat_setup.h"
+#include "gwat_phenomp.h"
 
 namespace gwat {
-
-struct cplx {
-	double re, im;
-};
 
 // What the kernels read per frequency bin (built once per grid by the host, see gwat_grid.h).
 struct BinGrid {
@@ -26,10 +22,6 @@ struct BinGrid {
 	const double *logf;   // [L] ln f
 };
 
-GWAT_HD double bin_sixth_root(const DCoef &c, double sf_hi, double sf_lo)
-{
-	return dd_mul_to_double(c.sM_hi, c.sM_lo, sf_hi, sf_lo);
-}
 
 // The (2,2) carrier h = A exp(-i phi) of the IMRPhenomD families, time and phase shifts applied.
 template <class Fam>
@@ -49,6 +41,10 @@ GWAT_HD cplx carrier_bin(const WalkerCoef &w, double f, double sf_hi, double sf_
 template <class Fam>
 GWAT_HD void polarizations_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, cplx &hp, cplx &hc)
 {
+	if (Fam::base == BASE_P) {
+		phenomp_polarizations_bin<Fam>(w, f, sf_hi, sf_lo, logf, hp, hc);
+		return;
+	}
 	const cplx h = carrier_bin<Fam>(w, f, sf_hi, sf_lo, logf);
 	hp = cplx{h.re * w.pfac, h.im * w.pfac};
 	hc = cplx{h.im * w.cfac, -h.re * w.cfac};

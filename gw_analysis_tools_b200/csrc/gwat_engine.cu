@@ -81,11 +81,18 @@ __device__ __forceinline__ void block_sum2(double &a, double &b)
 	}
 }
 
-__device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D)
+__device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool pv2)
 {
 	const DCoef &c = w.d;
-	bool ok = isfinite(c.fcut) && isfinite(c.A0) && isfinite(c.fRD) && isfinite(c.fdamp) && isfinite(c.tc) &&
-	          isfinite(c.phic) && isfinite(c.beta0) && isfinite(c.alpha0) && isfinite(c.ic[4]) && isfinite(w.pfac);
+	bool ok = isfinite(c.fcut) && isfinite(c.A0) && isfinite(c.fRD) && isfinite(c.fdamp) && isfinite(c.beta0) &&
+	          isfinite(c.alpha0) && isfinite(c.ic[4]) && isfinite(w.pfac);
+	if (pv2) {
+		const PCoef &p = w.p;
+		ok = ok && isfinite(p.A0) && isfinite(p.tc) && isfinite(p.phic) && isfinite(p.tcorr_2pi) && isfinite(p.alpha_const) &&
+		     isfinite(p.epsilon_offset) && isfinite(p.c2z) && isfinite(p.acoef[4]) && isfinite(p.Y[0]) && isfinite(p.SP);
+	} else {
+		ok = ok && isfinite(c.tc) && isfinite(c.phic);
+	}
 	for (int d = 0; d < D; d++) ok = ok && isfinite(w.det[d].Fplus) && isfinite(w.det[d].Fcross) && isfinite(w.det[d].tshift);
 	return ok;
 }
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ p
 	if (out) {
 		WalkerCoef wc;
 		walker_setup<Fam>(s, net, device_tables(), wc);
-		wc.valid = coef_is_finite(wc, net.D) ? 1 : 0;
+		wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
 		out[w] = wc;
 	}
 }
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(128) k_setup_src(const gwat_b200_source *__res
 	const gwat_b200_source s = src[w];
 	WalkerCoef wc;
 	walker_setup<Fam>(s, net, device_tables(), wc);
-	wc.valid = coef_is_finite(wc, net.D) ? 1 : 0;
+	wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
 	out[w] = wc;
 }
 
@@ -233,6 +240,26 @@ __global__ void k_antenna(int W, const double *RA, const double *DEC, const doub
 		Fc[(size_t)w * net.D + d] = dc[d].Fcross;
 		dt[(size_t)w * net.D + d] = dtoa_between(net.row[0] + 9, net.row[d] + 9, RA[w], DEC[w], gmst);
 	}
+}
+
+// FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so the DFMA issue peak is measured here with 8
+// independent dependent-FMA chains per thread (enough ILP to cover the 4-cycle-class latency at 8 warps per scheduler).
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double seed)
+{
+	double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 1.0000001, c = 1e-9;
+	for (int i = 0; i < iters; i++) {
+		a0 = fma(a0, m, c);
+		a1 = fma(a1, m, c);
+		a2 = fma(a2, m, c);
+		a3 = fma(a3, m, c);
+		a4 = fma(a4, m, c);
+		a5 = fma(a5, m, c);
+		a6 = fma(a6, m, c);
+		a7 = fma(a7, m, c);
+	}
+	const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+	if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
 }
 
 }  // namespace
@@ -349,6 +376,10 @@ int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, R
 		case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }                  \
 		case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }                       \
 		case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                          \
+		case FAM_P: { typedef Family<BASE_P, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                              \
+		case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }                  \
+		case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }                       \
+		case FAM_P_GIMR: { typedef Family<BASE_P, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                          \
 		default: return fail(ctx, GWAT_B200_ERR_METHOD, std::string("generation_method not implemented: ") + (desc).base);   \
 		}                                                                                                                    \
 	} while (0)
@@ -764,6 +795,33 @@ int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const d
 int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *, int, int, int, int, int, const gwat_b200_source *, double *)
 {
 	return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: not built yet");
+}
+
+int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops)
+{
+	if (!ctx || !tflops) return GWAT_B200_ERR_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, 16)) return GWAT_B200_ERR_CUDA;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const int blocks = sms * 8, iters = 1 << 16;
+	double best = 0;
+	for (int rep = 0; rep < 5; rep++) {
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+		k_dfma_peak<<<blocks, 256, 0, st>>>(ctx->d_out, iters, 1.0 + rep);
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		float ms = 0;
+		CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		const double flops = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+		const double tf = flops / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	ctx->launches += 5;
+	*tflops = best;
+	return GWAT_B200_OK;
 }
 
 long long gwat_b200_launch_count(const gwat_b200_ctx *c) { return c ? c->launches : 0; }

@@ -105,6 +105,10 @@ struct DCoef {
 	double nrt_fmerger, nrt_fmerger12;
 };
 
+struct cplx {
+	double re, im;
+};
+
 // Per-walker, per-detector projection constants.
 struct DetCoef {
 	double Fplus, Fcross;  // antenna patterns (detector_response_functions_equatorial, src/detector_util.cpp:900)
@@ -118,7 +122,7 @@ struct PCoef {
 	double acoef[5], ecoef[5];
 	double alpha_const;    // alpha0 - alpha_offset
 	double epsilon_offset;
-	double Yre[5], Yim[5];  // -2Y_{2m}(thetaJN, 0), m = -2..2
+	double Y[5];  // -2Y_{2m}(thetaJN, 0), m = -2..2 (real at zero azimuth)
 	double c2z, s2z;        // polarisation rotation by 2 zeta (src/waveform_generator.cpp:257-266)
 	double phic, tc, f_ref, tcorr_2pi;
 };

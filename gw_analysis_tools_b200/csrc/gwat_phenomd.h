@@ -190,6 +190,12 @@ GWAT_HD void mf_powers(double M, double f, double sixth, MfPowers &p)
 	p.m53 = 1. / p.five3;
 }
 
+// Per-bin sixth root: walker factor times grid factor, both double-double, rounded once (see gwat_grid.h).
+GWAT_HD double bin_sixth_root(const DCoef &c, double sf_hi, double sf_lo)
+{
+	return dd_mul_to_double(c.sM_hi, c.sM_lo, sf_hi, sf_lo);
+}
+
 // (M f)^(fl(1/6)) the way the reference gets it, pow(M*f, 1./6.), for setup-time evaluations at single frequencies.
 GWAT_HD double sixth_root_direct(double M, double f)
 {

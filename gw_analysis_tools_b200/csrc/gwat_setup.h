@@ -369,19 +369,5 @@ GWAT_HD void copy_modifications(const gwat_b200_source &in, SrcQ &s)
 	}
 }
 
-template <class Fam>
-GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const Tables &t, WalkerCoef &w)
-{
-	SrcQ s;
-	populate_source(src, s);
-	copy_modifications<Fam>(src, s);
-	phenomd_setup<Fam>(s, t.fit, t.qnm, t.qnm_n, w.d);
-	const double ci = cos(s.incl_angle);
-	w.cfac = ci;
-	w.pfac = .5 * (1. + ci * ci);
-	detector_setup(net, src.RA, src.DEC, src.psi, src.gmst, w.det);
-	w.valid = 1;
-}
-
 }  // namespace gwat
 #endif

@@ -22,7 +22,7 @@ EXPORTS = [
     "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
-    "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
+    "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
 
 
@@ -191,6 +191,12 @@ class Context:
         return fp, fc, dt
 
     # ---- introspection ---------------------------------------------------------------------------------------------
+    def measure_fp64_peak(self):
+        """Measured DFMA issue peak of this GPU in TFLOP/s (the FP64 roofline denominator)."""
+        out = C.c_double()
+        self._check(self._lib.gwat_b200_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
     @property
     def launch_count(self):
         return int(self._lib.gwat_b200_launch_count(self._h))

@@ -209,6 +209,9 @@ int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const d
 
 /* ---- introspection used by bench.py / the tests ------------------------------------------------------------------ */
 
+/* Measured FP64 FMA issue peak of ctx's GPU in TFLOP/s (a DFMA-chain microbenchmark; the roofline denominator of the
+ * FP64-bound kernels -- the driver-written MEASURED_PEAKS.json carries no FP64 figure). */
+int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops);
 /* Number of kernels this library has launched on ctx since creation (for the bench's gpu_launches). */
 long long gwat_b200_launch_count(const gwat_b200_ctx *ctx);
 /* Device-time (ms, CUDA events on the context's stream) of the hot kernel launches of the last *_batch call. */
