@@ -202,7 +202,8 @@ def run_b200(args):
     d_out = torch.empty(W, dtype=torch.float64, device="cuda")
     h_out = torch.empty(W, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the C ABI treats a NULL stream as "the context's own", and torch's default stream handle is 0
+    stream = torch.cuda.Stream()
     torch.cuda.synchronize()
 
     def step_resident(k):
@@ -230,11 +231,12 @@ def run_b200(args):
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms, active = [], []
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record(stream)
-        step_resident(k)
-        ev[k][1].record(stream)
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record(stream)
+            step_resident(k)
+            ev[k][1].record(stream)
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t_resident = sum(step_ms) * 1e-3
@@ -339,7 +341,7 @@ def _mod_ref(mod):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5])

@@ -29,11 +29,16 @@ GWAT_HD cplx carrier_bin(const WalkerCoef &w, double f, double sf_hi, double sf_
 {
 	const DCoef &c = w.d;
 	if (f > c.fcut) return cplx{0.0, 0.0};
+	// NRT: the Planck taper multiplies everything above 1.2 f_merger by exactly zero (src/IMRPhenomD_NRT.cpp:582-585, 745)
+	if (Fam::nrt && f > c.nrt_fmerger12) return cplx{0.0, 0.0};
 	double amp, phase;
-	phenomd_bin<Fam>(c, f, bin_sixth_root(c, sf_hi, sf_lo), logf, amp, phase);
+	MfPowers p;
+	phenomd_bin<Fam>(c, f, bin_sixth_root(c, sf_hi, sf_lo), logf, amp, phase, p);
+	if (Fam::nrt) nrt_bin(c, f, p, logf, amp, phase);
 	phase = phenomd_apply_time_phase(c, f, phase);
 	double sn, cs;
 	sincos(phase, &sn, &cs);
+	if (Fam::nrt) amp *= nrt_taper_factor(c, f);
 	return cplx{amp * cs, -(amp * sn)};
 }
 

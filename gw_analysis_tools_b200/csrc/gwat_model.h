@@ -87,6 +87,7 @@ struct DCoef {
 	double c8, c9, c10, c11;    // log-dependent 2.5PN / 3PN pieces
 	double pi53, pi2;           // pi^(5/3), pi^2 (applied per bin, after the log)
 	double tf2;                 // 3/(128 eta) * pi^(-5/3)
+	double k128;                // 3/(128 eta)
 	double inv_eta;
 	double sig1M, sig2q, sig3q, sig4q;
 	// intermediate and merger-ringdown phase

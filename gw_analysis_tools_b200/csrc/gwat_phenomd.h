@@ -310,9 +310,8 @@ GWAT_HD double phenomd_amp_mr(const DCoef &c, double f)
 //   sixth = (M f)^(fl(1/6)),  logf = ln f
 // Reference: the loop body of construct_waveform, src/IMRPhenomD.cpp:484-494.
 template <class Fam>
-GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, double &amp, double &phase)
+GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, double &amp, double &phase, MfPowers &p)
 {
-	MfPowers p;
 	if (f < c.f1p || f < c.f1a || Fam::base == BASE_P || Fam::nrt) {
 		mf_powers(c.M, f, sixth, p);
 	} else {
@@ -329,6 +328,13 @@ GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, do
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, p, logf);
 	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f);
 	else phase = phenomd_phase_int<Fam>(c, f, logf);
+}
+
+template <class Fam>
+GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, double &amp, double &phase)
+{
+	MfPowers p;
+	phenomd_bin<Fam>(c, f, sixth, logf, amp, phase, p);
 }
 
 // phase -= tc (f - f_ref) + phic     (src/IMRPhenomD.cpp:497), unfused like the reference

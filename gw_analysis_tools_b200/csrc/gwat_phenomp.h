@@ -366,6 +366,7 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 	SrcQ s;
 	populate_source(src, s);
 	copy_modifications<Fam>(src, s);
+	if (Fam::nrt) nrt_prepare_source(src, s);
 	if (Fam::base == BASE_P) {
 		// prep_source_parameters, src/waveform_generator.cpp:1271-1283: chip given -> reduced transform
 		const bool reduced = (src.chip + 1) > 1e-10;

@@ -9,7 +9,7 @@
 #ifndef GWAT_SETUP_H
 #define GWAT_SETUP_H
 
-#include "gwat_phenomd.h"
+#include "gwat_nrt.h"
 
 namespace gwat {
 
@@ -131,6 +131,10 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	double cph[12], camp[7];
 	pn_amplitude_coeffs(s, camp);
 	pn_phase_coeffs(s, cph);
+	if (Fam::nrt) {
+		nrt_moments(s);
+		nrt_adjust_pn_phase(s, cph);
+	}
 	const double c8_gr = cph[8];
 	const double alpha1_fit = lam.alpha[1];  // the reference re-evaluates fit element 14 for the time shift (:456)
 	apply_gimr<Fam>(s, lam, cph);
@@ -249,6 +253,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.pi53 = pi.five3;
 	c.pi2 = pi.sq;
 	c.tf2 = 3. / (128. * eta) * pi.m53;
+	c.k128 = 3. / (128. * eta);
 	c.sig1M = lam.sigma[1] * M;
 	c.sig2q = (3. / 4.) * lam.sigma[2];
 	c.sig3q = (3. / 5) * lam.sigma[3];
@@ -256,6 +261,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.Nmod = 0;
 	c.n_gimr_neg = 0;
 	setup_family_extras<Fam>(s, c);
+	if (Fam::nrt) nrt_setup(s, c);
 
 	// C1 matching of the three phase regions (phase_connection_coefficients, :1614-1674): the connection coefficients are
 	// found in sequence, each with the not-yet-known ones at zero.

@@ -80,6 +80,9 @@ int make_network(int D, const char *const *dets, Network &net)
 	case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; CALL; break; }          \
 	case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; CALL; break; }               \
 	case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; CALL; break; }                  \
+	case FAM_D_NRT: { typedef Family<BASE_D, PPE_NONE, false, true> Fam; CALL; break; }                   \
+	case FAM_D_NRT_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, true> Fam; CALL; break; }       \
+	case FAM_D_NRT_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, true> Fam; CALL; break; }            \
 	case FAM_P: { typedef Family<BASE_P, PPE_NONE, false, false> Fam; CALL; break; }                      \
 	case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; CALL; break; }          \
 	case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; CALL; break; }               \

@@ -91,7 +91,8 @@ def test_repack_matches_reference(ctx, oracle):
             for name in ("mass1", "mass2", "Luminosity_Distance", "RA", "DEC", "psi", "incl_angle", "phiRef"):
                 assert abs(getattr(a, name) - getattr(b, name)) <= 4e-16 * max(1.0, abs(getattr(b, name))), name
             assert abs((wl.T_segment - a.tc) - b.tc) <= 1e-15 * wl.T_segment
-            for i in range(3):
+            # the aligned-spin repack of the reference leaves the in-plane components uninitialised (src/fisher.cpp:2276-2277)
+            for i in (range(3) if cfg == 2 else [2]):
                 assert abs(a.spin1[i] - b.spin1[i]) <= 1e-15 and abs(a.spin2[i] - b.spin2[i]) <= 1e-15
 
 
