@@ -15,6 +15,7 @@
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -46,7 +47,10 @@ constexpr int kThreads = 256;
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ Tables device_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N}; }
+__device__ __forceinline__ Tables device_tables()
+{
+	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS}};
+}
 
 struct GridPtrs {
 	const double *f, *sf_hi, *sf_lo, *logf;
@@ -103,7 +107,7 @@ __device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool 
 
 template <class Fam>
 __global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ params, int W, RepackPlan plan, Network net,
-                                                   double gmst, double T_segment, WalkerCoef *__restrict__ out,
+                                                   int theory, double gmst, double T_segment, WalkerCoef *__restrict__ out,
                                                    gwat_b200_source *__restrict__ src_out)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,21 +117,21 @@ __global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ p
 	if (src_out) src_out[w] = s;
 	if (out) {
 		WalkerCoef wc;
-		walker_setup<Fam>(s, net, device_tables(), wc);
+		walker_setup<Fam>(s, net, device_tables(), theory, wc);
 		wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
 		out[w] = wc;
 	}
 }
 
 template <class Fam>
-__global__ void __launch_bounds__(128) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net,
+__global__ void __launch_bounds__(128) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net, int theory,
                                                   WalkerCoef *__restrict__ out)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= W) return;
 	const gwat_b200_source s = src[w];
 	WalkerCoef wc;
-	walker_setup<Fam>(s, net, device_tables(), wc);
+	walker_setup<Fam>(s, net, device_tables(), theory, wc);
 	wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
 	out[w] = wc;
 }
@@ -228,6 +232,131 @@ __global__ void __launch_bounds__(kThreads) k_response(const WalkerCoef *__restr
 	}
 }
 
+// ---- Fisher stencil ------------------------------------------------------------------------------------------------------
+// calculate_derivatives, non-sky-averaged branch (src/fisher.cpp:340-557): for every source and parameter i, the detector
+// response at theta_i +- eps (and +- 2 eps for order 4), eps = 1e-8 absolute.
+struct FisherPlan {
+	RepackPlan rp;
+	int npts;       // 2 or 4 stencil points per parameter
+	int det_is_ref; // detector == reference detector: no arrival-time handling at all
+	int theory;
+	double det_row[13], ref_row[13];
+};
+
+template <class Fam>
+__global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__restrict__ src, int S, FisherPlan fp,
+                                                     WalkerCoef *__restrict__ coefs, double *__restrict__ scale,
+                                                     int *__restrict__ eta_bc)
+{
+	const int dim = fp.rp.dimension;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= S * dim * fp.npts) return;
+	const int k = t % fp.npts, i = (t / fp.npts) % dim, sidx = t / (fp.npts * dim);
+	const double epsilon = 1e-8;
+	const gwat_b200_source orig = src[sidx];
+	double v[GWAT_B200_MAX_DIM];
+	int logfac[GWAT_B200_MAX_DIM];
+	unpack_fisher(orig, fp.rp, v, logfac);
+	const bool bc = (i == 8 && v[8] > .25 - epsilon);  // eta at its upper boundary: one-sided difference (:369-383)
+	if (k == 0) {
+		scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
+		eta_bc[(size_t)sidx * dim + i] = bc ? 1 : 0;
+	}
+	const double step = (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
+	const double base = v[i];
+	if (step > 0 && bc) v[i] = base;
+	else v[i] = base + step;
+	gwat_b200_source sp;
+	repack_fisher_point(v, orig, fp.rp, sp);
+	double tshift = 0;
+	if (!fp.det_is_ref) {
+		const double dtoa = dtoa_between(fp.ref_row + 9, fp.det_row + 9, sp.RA, sp.DEC, sp.gmst);
+		if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;  // +-eps: phase factor on the response (:403-408, 425-430)
+		else sp.tc -= dtoa;                          // +-2eps: shift of tc instead (:436-438, 451-453)  [reference quirk, kept]
+	}
+	Network net;
+	net.D = 1;
+	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[j];
+	WalkerCoef wc;
+	walker_setup<Fam>(sp, net, device_tables(), fp.theory, wc);
+	wc.det[0].tshift = tshift;
+	wc.valid = coef_is_finite(wc, 1, Fam::base == BASE_P) ? 1 : 0;
+	coefs[t] = wc;
+}
+
+// deriv[s][i][bin] = stencil combination of the responses, times the log-parameter factor (:462-484, 548-554)
+template <class Fam>
+__global__ void __launch_bounds__(kThreads) k_fisher_deriv(const WalkerCoef *__restrict__ coefs, GridPtrs g, int npts,
+                                                          const double *__restrict__ scale, const int *__restrict__ eta_bc,
+                                                          double *__restrict__ dre, double *__restrict__ dim_)
+{
+	__shared__ WalkerCoef w[4];
+	{
+		const double *sp = reinterpret_cast<const double *>(coefs + (size_t)blockIdx.y * npts);
+		double *dp = reinterpret_cast<double *>(&w[0]);
+		for (int i = threadIdx.x; i < (int)(npts * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
+		__syncthreads();
+	}
+	const int bin = blockIdx.x * kThreads + threadIdx.x;
+	if (bin >= g.L) return;
+	const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
+	cplx r[4];
+	for (int k = 0; k < npts; k++) {
+		if (!w[k].valid) {
+			r[k] = cplx{NAN, NAN};
+			continue;
+		}
+		cplx hp, hc;
+		polarizations_bin<Fam>(w[k], f, hi, lo, lg, hp, hc);
+		r[k] = project_bin(w[k].det[0], hp, hc, f, true);
+	}
+	const double epsilon = 1e-8;
+	const bool bc = eta_bc[blockIdx.y] != 0;
+	cplx d;
+	if (npts == 2) {
+		const double den = bc ? epsilon : 2. * epsilon;
+		d = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
+	} else {
+		const double den = bc ? 6. * epsilon : 12. * epsilon;
+		d = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
+		         (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
+	}
+	const double sc = scale[blockIdx.y];
+	const size_t o = (size_t)blockIdx.y * g.L + bin;
+	dre[o] = d.re * sc;
+	dim_[o] = d.im * sc;
+}
+
+// F_jk (+)= prefactor * sum_bins coef * Re(d_j conj(d_k)) / S      (calculate_fisher_elements, src/fisher.cpp:2704-2781)
+__global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__restrict__ dre, const double *__restrict__ dim_,
+                                                             const double *__restrict__ wq, int L, int dim, double prefactor,
+                                                             int accumulate, double *__restrict__ out)
+{
+	// blockIdx.x enumerates the pairs j >= k, blockIdx.y the source
+	int j = 0, k = blockIdx.x;
+	while (k > j) {
+		k -= j + 1;
+		j++;
+	}
+	const size_t sbase = (size_t)blockIdx.y * dim;
+	const double *ajr = dre + (sbase + j) * L, *aji = dim_ + (sbase + j) * L;
+	const double *akr = dre + (sbase + k) * L, *aki = dim_ + (sbase + k) * L;
+	double acc = 0, unused = 0;
+	for (int i = threadIdx.x; i < L; i += kThreads) acc += wq[i] * (ajr[i] * akr[i] + aji[i] * aki[i]);
+	block_sum2(acc, unused);
+	if (threadIdx.x == 0) {
+		const double val = prefactor * acc;
+		double *o = out + (size_t)blockIdx.y * dim * dim;
+		if (accumulate) {
+			o[j * dim + k] += val;
+			if (j != k) o[k * dim + j] += val;
+		} else {
+			o[j * dim + k] = val;
+			o[k * dim + j] = val;
+		}
+	}
+}
+
 __global__ void k_antenna(int W, const double *RA, const double *DEC, const double *psi, double gmst, Network net,
                           double *Fp, double *Fc, double *dt)
 {
@@ -280,7 +409,7 @@ struct gwat_b200_ctx {
 	Network net{};
 	double pref_like = 0, pref_fisher = 0;
 	double *d_grid = nullptr;  // f, sf_hi, sf_lo, logf : 4*L
-	double *d_net = nullptr;   // wq, dre, dim : 3*D*L
+	double *d_net = nullptr;   // wq, dre, dim, wq_fisher : 4*D*L
 	std::vector<double> h_f;
 	// scratch (grown on demand)
 	size_t cap_walkers = 0, cap_partial = 0, cap_params = 0, cap_out = 0, cap_src = 0;
@@ -290,6 +419,9 @@ struct gwat_b200_ctx {
 	double *d_out = nullptr;
 	gwat_b200_source *d_src = nullptr;
 	unsigned long long *d_active = nullptr;
+	size_t cap_deriv = 0, cap_scale = 0, cap_fisher = 0, cap_bc = 0;
+	double *d_deriv = nullptr, *d_scale = nullptr, *d_fisher = nullptr;
+	int *d_bc = nullptr;
 	// introspection
 	long long launches = 0;
 	double last_ms = 0;
@@ -458,9 +590,9 @@ int check_ready(gwat_b200_ctx *ctx, bool need_data)
 }
 
 template <class Fam>
-void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, cudaStream_t st)
+void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st)
 {
-	k_setup_src<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_src, W, ctx->net, ctx->d_coef);
+	k_setup_src<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_src, W, ctx->net, theory, ctx->d_coef);
 }
 
 int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st)
@@ -468,7 +600,7 @@ int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const 
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, h_src, sizeof(gwat_b200_source) * W, cudaMemcpyHostToDevice, st));
-	GWAT_DISPATCH_FAMILY(desc, launch_setup_src<Fam>(ctx, W, ctx->d_src, st));
+	GWAT_DISPATCH_FAMILY(desc, launch_setup_src<Fam>(ctx, W, ctx->d_src, desc.theory, st));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -532,6 +664,10 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 	cudaFree(c->d_out);
 	cudaFree(c->d_src);
 	cudaFree(c->d_active);
+	cudaFree(c->d_deriv);
+	cudaFree(c->d_scale);
+	cudaFree(c->d_fisher);
+	cudaFree(c->d_bc);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
@@ -570,7 +706,7 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 	std::memcpy(grid.data() + 2 * (size_t)L, lo.data(), sizeof(double) * L);
 	std::memcpy(grid.data() + 3 * (size_t)L, lg.data(), sizeof(double) * L);
 	const size_t DL = (size_t)D * L;
-	std::vector<double> netbuf(3 * DL, 0.0);
+	std::vector<double> netbuf(4 * DL, 0.0);
 	for (int d = 0; d < D; d++)
 		for (int i = 0; i < L; i++) {
 			const size_t k = (size_t)d * L + i;
@@ -579,6 +715,8 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 				netbuf[DL + k] = data_re[k];
 				netbuf[2 * DL + k] = data_im[k];
 			}
+			// the Fisher routines always integrate with Simpson's rule (src/fisher.cpp:128-131)
+			netbuf[3 * DL + k] = quadrature_coefficient(i, L, false, false, nullptr, f) / psd[k];
 		}
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	if (ctx->d_grid) cudaFree(ctx->d_grid);
@@ -596,7 +734,7 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 	ctx->gaussleg = gl;
 	ctx->log10F = log10F != 0;
 	ctx->pref_like = quadrature_prefactor(L, gl, f, false);
-	ctx->pref_fisher = quadrature_prefactor(L, gl, f, true);
+	ctx->pref_fisher = quadrature_prefactor(L, false, f, true);
 	ctx->h_f.assign(f, f + L);
 	return GWAT_B200_OK;
 }
@@ -618,7 +756,7 @@ int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *method, con
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
-	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_params, W, plan, ctx->net, gmst, T_segment,
+	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
 	                                                                              ctx->d_coef, nullptr));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -759,7 +897,7 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, st));
 	// T_segment = 0 and the sign flip below leave tc as sampled: this entry point mirrors repack_parameters alone
 	typedef Family<BASE_D, PPE_NONE, false, false> AnyFam;
-	k_setup_mcmc<AnyFam><<<(W + 127) / 128, 128, 0, st>>>(ctx->d_params, W, plan, ctx->net, gmst, 0.0, nullptr, ctx->d_src);
+	k_setup_mcmc<AnyFam><<<(W + 127) / 128, 128, 0, st>>>(ctx->d_params, W, plan, ctx->net, 0, gmst, 0.0, nullptr, ctx->d_src);
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	CUDA_TRY(ctx, cudaMemcpyAsync(sources, ctx->d_src, sizeof(gwat_b200_source) * W, cudaMemcpyDeviceToHost, st));
@@ -795,9 +933,96 @@ int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const d
 	return GWAT_B200_OK;
 }
 
-int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *, int, int, int, int, int, const gwat_b200_source *, double *)
+int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int detector_index, int reference_index,
+                                     int dimension, int order, int S, const gwat_b200_source *sources, double *fisher)
 {
-	return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: not built yet");
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (S < 0 || (S > 0 && (!sources || !fisher))) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: NULL array");
+	if (S == 0) return GWAT_B200_OK;
+	if (order != 2 && order != 4) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: order must be 2 or 4");
+	if (detector_index >= ctx->D || reference_index < 0 || reference_index >= ctx->D)
+		return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: detector index out of range");
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	if (sources[0].sky_average) return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers are outside this path");
+	// the modification layout is taken from the first source (all sources of a batch share it, as they share the method)
+	gwat_b200_mod mod;
+	gwat_b200_mod_init(&mod);
+	mod.ppE_Nmod = sources[0].Nmod;
+	mod.gIMR_Nmod_phi = sources[0].Nmod_phi;
+	mod.gIMR_Nmod_sigma = sources[0].Nmod_sigma;
+	mod.gIMR_Nmod_beta = sources[0].Nmod_beta;
+	mod.gIMR_Nmod_alpha = sources[0].Nmod_alpha;
+	mod.tidal_love = sources[0].tidal_love;
+	FisherPlan fp;
+	std::memset(&fp, 0, sizeof(fp));
+	RepackPlan &plan = fp.rp;
+	plan.dimension = dimension;
+	plan.pv2 = desc.pv2;
+	plan.nrt = desc.nrt;
+	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
+	plan.gimr = desc.gimr && !plan.ppe;
+	plan.mcmc = desc.mcmc;
+	plan.mod = mod;
+	{
+		int base = desc.pv2 ? (desc.mcmc ? 15 : 13) : 11;
+		if (desc.nrt && !desc.pv2) base += mod.tidal_love ? 1 : 2;
+		int mods = 0;
+		if (plan.ppe) mods = mod.ppE_Nmod;
+		else if (plan.gimr) mods = mod.gIMR_Nmod_phi + mod.gIMR_Nmod_sigma + mod.gIMR_Nmod_beta + mod.gIMR_Nmod_alpha;
+		if (dimension != base + mods || dimension > GWAT_B200_MAX_DIM)
+			return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: dimension does not match the method and the sources' modifications");
+	}
+	fp.npts = order == 4 ? 4 : 2;
+	fp.theory = desc.theory;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const int L = ctx->L, dim = dimension;
+	// sources per pass: bounded by a 512 MiB derivative buffer
+	size_t per_source = (size_t)dim * L * 16;
+	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)512 << 20) / per_source));
+	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * fp.npts)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * L)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
+	const GridPtrs g = grid_ptrs(ctx);
+	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * L;
+	const int d0 = detector_index < 0 ? 0 : detector_index;
+	const int d1 = detector_index < 0 ? ctx->D : detector_index + 1;
+	const int npairs = dim * (dim + 1) / 2;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+	for (int s0 = 0; s0 < S; s0 += chunk) {
+		const int ns = std::min(chunk, S - s0);
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, sources + s0, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, st));
+		for (int d = d0; d < d1; d++) {
+			std::memcpy(fp.det_row, ctx->net.row[d], sizeof(fp.det_row));
+			std::memcpy(fp.ref_row, ctx->net.row[reference_index], sizeof(fp.ref_row));
+			fp.det_is_ref = (std::memcmp(fp.det_row, fp.ref_row, sizeof(fp.det_row)) == 0) ? 1 : 0;
+			const int nthreads = ns * dim * fp.npts;
+			GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
+			                                                                                        ctx->d_scale, ctx->d_bc));
+			const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
+			double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
+			GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
+			                                                                         dre, dim_));
+			k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * L, L, dim,
+			                                                          ctx->pref_fisher, d > d0 ? 1 : 0, ctx->d_fisher);
+			ctx->launches += 3;
+			CUDA_TRY(ctx, cudaGetLastError());
+		}
+		CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * dim * dim, ctx->d_fisher, sizeof(double) * ns * dim * dim,
+		                              cudaMemcpyDeviceToHost, st));
+	}
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	float ms = 0;
+	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->last_ms = ms;
+	return GWAT_B200_OK;
 }
 
 int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops)

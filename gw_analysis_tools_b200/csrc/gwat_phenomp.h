@@ -361,11 +361,12 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 
 // ---- one walker, start to finish (all families) ---------------------------------------------------------------------
 template <class Fam>
-GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const Tables &t, WalkerCoef &w)
+GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const Tables &t, int theory, WalkerCoef &w)
 {
 	SrcQ s;
 	populate_source(src, s);
 	copy_modifications<Fam>(src, s);
+	if (Fam::ppe != PPE_NONE) apply_theory(theory, t.dz, s);
 	if (Fam::nrt) nrt_prepare_source(src, s);
 	if (Fam::base == BASE_P) {
 		// prep_source_parameters, src/waveform_generator.cpp:1271-1283: chip given -> reduced transform

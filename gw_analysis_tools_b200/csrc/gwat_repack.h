@@ -180,5 +180,159 @@ GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, dou
 	s.tc = T_segment - s.tc;
 }
 
+// ---- Fisher stencil: physical record <-> parameter vector ------------------------------------------------------------
+// transform_cart_sph (src/util.cpp:1882-1891)
+GWAT_HD void cart_to_sph(const double *c, double *sph)
+{
+	sph[0] = sqrt(c[0] * c[0] + c[2] * c[2] + c[1] * c[1]);
+	sph[1] = acos(c[2] / sph[0]);
+	sph[2] = atan2(c[1], c[0]);
+	if (sph[2] < 0) sph[2] += 2 * GWAT_PI;
+}
+
+GWAT_HD double chirpmass_from(double m1, double m2) { return pow(m1 * m2, 3. / 5) / pow(m1 + m2, 1. / 5); }
+GWAT_HD double eta_from(double m1, double m2) { return (m1 * m2) / ((m1 + m2) * (m1 + m2)); }
+
+// unpack_parameters, non-sky-averaged branches (src/fisher.cpp:1843-1966, 2038-2160).  `logf[i]` != 0 marks the
+// parameters whose derivative is multiplied by the parameter itself afterwards (d/d ln x).
+GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, double *v, int *logfac)
+{
+	const int dim = plan.dimension;
+	for (int i = 0; i < dim; i++) logfac[i] = 0;
+	v[0] = in.RA;
+	v[2] = in.psi;
+	v[4] = in.phiRef;
+	v[5] = in.tc;
+	v[8] = eta_from(in.mass1, in.mass2);
+	if (plan.mcmc) {
+		v[1] = sin(in.DEC);
+		v[3] = cos(in.incl_angle);
+		v[6] = log(in.Luminosity_Distance);
+		v[7] = log(chirpmass_from(in.mass1, in.mass2));
+	} else {
+		logfac[6] = 1;
+		logfac[7] = 1;
+		v[1] = in.DEC;
+		v[3] = in.incl_angle;
+		v[6] = in.Luminosity_Distance;
+		v[7] = chirpmass_from(in.mass1, in.mass2);
+	}
+	if (plan.pv2) {
+		if (plan.mcmc) {
+			double s1[3], s2[3];
+			cart_to_sph(in.spin1, s1);
+			cart_to_sph(in.spin2, s2);
+			v[9] = s1[0];
+			v[10] = s2[0];
+			v[11] = cos(s1[1]);
+			v[12] = cos(s2[1]);
+			v[13] = s1[2];
+			v[14] = s2[2];
+		} else {
+			v[9] = in.spin1[2];
+			v[10] = in.spin2[2];
+			v[11] = in.chip;
+			v[12] = in.phip;
+		}
+	} else {
+		v[9] = in.spin1[2];
+		v[10] = in.spin2[2];
+	}
+	if (plan.nrt && !plan.pv2) {
+		if (in.tidal_love) {
+			logfac[11] = plan.mcmc ? 0 : 1;
+			v[11] = log(in.tidal_s);
+		} else {
+			logfac[11] = logfac[12] = plan.mcmc ? 0 : 1;
+			v[11] = log(in.tidal1);
+			v[12] = log(in.tidal2);
+		}
+	}
+	if (plan.ppe) {
+		const int base = dim - in.Nmod;
+		for (int i = 0; i < in.Nmod; i++) v[base + i] = in.betappe[i];
+	} else if (plan.gimr) {
+		int at = dim - (in.Nmod_phi + in.Nmod_sigma + in.Nmod_beta + in.Nmod_alpha);
+		for (int i = 0; i < in.Nmod_phi; i++) v[at++] = in.delta_phi[i];
+		for (int i = 0; i < in.Nmod_sigma; i++) v[at++] = in.delta_sigma[i];
+		for (int i = 0; i < in.Nmod_beta; i++) v[at++] = in.delta_beta[i];
+		for (int i = 0; i < in.Nmod_alpha; i++) v[at++] = in.delta_alpha[i];
+	}
+}
+
+// One stencil point: repack_non_parameter_options + repack_parameters (src/fisher.cpp:2513-2572, 2167-2507) starting
+// from a default-constructed record, as calculate_derivatives does (src/fisher.cpp:176-177, 385).
+GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, const RepackPlan &plan,
+                                 gwat_b200_source &s)
+{
+	source_defaults(s);
+	// repack_non_parameter_options
+	s.sky_average = orig.sky_average;
+	s.tidal_love = orig.tidal_love;
+	s.tidal_love_error = orig.tidal_love_error;
+	s.f_ref = orig.f_ref;
+	s.gmst = orig.gmst;
+	s.horizon_coord = orig.horizon_coord;
+	s.equatorial_orientation = orig.equatorial_orientation;
+	s.NSflag1 = orig.NSflag1;
+	s.NSflag2 = orig.NSflag2;
+	s.shift_time = 0;
+	s.shift_phase = orig.shift_phase;
+	s.dep_postmerger = orig.dep_postmerger;
+	if (plan.ppe) {
+		s.Nmod = orig.Nmod;
+		for (int i = 0; i < GWAT_B200_MAX_MOD; i++) s.bppe[i] = orig.bppe[i];
+	} else if (plan.gimr) {
+		s.Nmod_phi = orig.Nmod_phi;
+		s.Nmod_sigma = orig.Nmod_sigma;
+		s.Nmod_beta = orig.Nmod_beta;
+		s.Nmod_alpha = orig.Nmod_alpha;
+		for (int i = 0; i < GWAT_B200_MAX_MOD; i++) {
+			s.phii[i] = orig.phii[i];
+			s.sigmai[i] = orig.sigmai[i];
+			s.betai[i] = orig.betai[i];
+			s.alphai[i] = orig.alphai[i];
+		}
+	}
+	// repack_parameters
+	s.RA = v[0];
+	s.psi = v[2];
+	s.phiRef = v[4];
+	s.tc = v[5];
+	if (plan.mcmc) {
+		s.mass1 = mass1_of(exp(v[7]), v[8]);
+		s.mass2 = mass2_of(exp(v[7]), v[8]);
+		s.Luminosity_Distance = exp(v[6]);
+		s.DEC = asin(v[1]);
+		s.incl_angle = acos(v[3]);
+	} else {
+		s.mass1 = mass1_of(v[7], v[8]);
+		s.mass2 = mass2_of(v[7], v[8]);
+		s.Luminosity_Distance = v[6];
+		s.DEC = v[1];
+		s.incl_angle = v[3];
+	}
+	if (plan.pv2) {
+		if (plan.mcmc) {
+			const double th1 = clamped_acos(v[11]), th2 = clamped_acos(v[12]);
+			s.spin1[0] = v[9] * sin(th1) * cos(v[13]);
+			s.spin1[1] = v[9] * sin(th1) * sin(v[13]);
+			s.spin1[2] = v[9] * cos(th1);
+			s.spin2[0] = v[10] * sin(th2) * cos(v[14]);
+			s.spin2[1] = v[10] * sin(th2) * sin(v[14]);
+			s.spin2[2] = v[10] * cos(th2);
+		} else {
+			s.spin1[2] = v[9];
+			s.spin2[2] = v[10];
+			s.chip = v[11];
+			s.phip = v[12];
+		}
+	} else {
+		s.spin1[2] = v[9];
+		s.spin2[2] = v[10];
+	}
+	repack_tails(v, plan, s);
+}
+
 }  // namespace gwat
 #endif

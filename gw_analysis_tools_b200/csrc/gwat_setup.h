@@ -10,6 +10,7 @@
 #define GWAT_SETUP_H
 
 #include "gwat_nrt.h"
+#include "gwat_theory.h"
 
 namespace gwat {
 
@@ -344,6 +345,7 @@ struct Tables {
 	const double (*fit)[11];
 	const double (*qnm)[5];
 	int qnm_n;
+	DzTable dz;
 };
 
 // prep_source_parameters: hand the modification arrays over (src/waveform_generator.cpp:1296-1314)

@@ -14,8 +14,11 @@ from gw_analysis_tools_b200 import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libgwat_ref.so")
 
+LIB_PATH_FMA = os.path.join(_HERE, "_ref", "libgwat_ref_fma.so")  # `make -C oracle noise`: same sources, FMA contraction on
+
 _dp = C.POINTER(C.c_double)
 _lib = None
+_lib_fma = None
 
 
 def available():
@@ -34,6 +37,16 @@ def lib():
         assert _lib.oracle_ref_sizeof_source() == C.sizeof(abi.Source)
         assert _lib.oracle_ref_sizeof_mod() == C.sizeof(abi.Mod)
     return _lib
+
+
+def lib_fma():
+    """The FMA-contracted build of the same reference sources: used only to measure the reference's own rounding noise."""
+    global _lib_fma
+    if _lib_fma is None:
+        if not os.path.exists(LIB_PATH_FMA):
+            raise RuntimeError("noise-floor oracle not built: run `make -C oracle noise`")
+        _lib_fma = C.CDLL(LIB_PATH_FMA)
+    return _lib_fma
 
 
 def _p(a):
@@ -122,11 +135,11 @@ def loglike_mcmc_batch(method, mod, params, gmst, T_segment, detectors, f, psd, 
 
 
 def fisher_numerical_batch(method, sources, detectors, f, psd, dimension, order=4, detector_index=-1,
-                           reference_index=0, nthreads=0):
+                           reference_index=0, nthreads=0, fma_build=False):
     arr, S = _src_array(sources)
     f, psd = _f64(f), _f64(psd)
     out = np.zeros((S, dimension, dimension))
-    lib().oracle_ref_fisher_numerical_batch(method.encode(), detector_index, reference_index, dimension, order, S, arr,
+    (lib_fma() if fma_build else lib()).oracle_ref_fisher_numerical_batch(method.encode(), detector_index, reference_index, dimension, order, S, arr,
                                             len(detectors), _dets(detectors), _p(f), f.size, _p(psd), int(nthreads),
                                             _p(out))
     return out

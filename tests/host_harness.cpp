@@ -10,12 +10,13 @@
 #include "../gw_analysis_tools_b200/csrc/gwat_bins.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_grid.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_method.h"
+#include "../gw_analysis_tools_b200/csrc/gwat_repack.h"
 
 using namespace gwat;
 
 namespace {
 
-Tables host_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N}; }
+Tables host_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS}}; }
 
 struct Grid {
 	std::vector<double> f, hi, lo, lg;
@@ -29,11 +30,11 @@ Grid make_grid(const double *f, int L)
 }
 
 template <class Fam>
-void waveform_t(const gwat_b200_source *src, const Network &net, const Grid &g, double *hp_re, double *hp_im,
+void waveform_t(int theory, const gwat_b200_source *src, const Network &net, const Grid &g, double *hp_re, double *hp_im,
                 double *hc_re, double *hc_im)
 {
 	WalkerCoef w;
-	walker_setup<Fam>(*src, net, host_tables(), w);
+	walker_setup<Fam>(*src, net, host_tables(), theory, w);
 	for (size_t i = 0; i < g.f.size(); i++) {
 		cplx hp, hc;
 		polarizations_bin<Fam>(w, g.f[i], g.hi[i], g.lo[i], g.lg[i], hp, hc);
@@ -45,10 +46,10 @@ void waveform_t(const gwat_b200_source *src, const Network &net, const Grid &g, 
 }
 
 template <class Fam>
-void response_t(const gwat_b200_source *src, const Network &net, const Grid &g, bool shift, double *re, double *im)
+void response_t(int theory, const gwat_b200_source *src, const Network &net, const Grid &g, bool shift, double *re, double *im)
 {
 	WalkerCoef w;
-	walker_setup<Fam>(*src, net, host_tables(), w);
+	walker_setup<Fam>(*src, net, host_tables(), theory, w);
 	const size_t L = g.f.size();
 	for (size_t i = 0; i < L; i++) {
 		cplx hp, hc;
@@ -100,7 +101,7 @@ int hh_fourier_waveform(const char *method, const gwat_b200_source *src, const d
 	Network net;
 	net.D = 0;
 	const Grid g = make_grid(f, L);
-	DISPATCH_FAMILY(desc, waveform_t<Fam>(src, net, g, hp_re, hp_im, hc_re, hc_im));
+	DISPATCH_FAMILY(desc, waveform_t<Fam>(desc.theory, src, net, g, hp_re, hp_im, hc_re, hc_im));
 	return 0;
 }
 
@@ -112,7 +113,7 @@ int hh_coherent_response(const char *method, const gwat_b200_source *src, int D,
 	Network net;
 	if (make_network(D, dets, net) != 0) return -1;
 	const Grid g = make_grid(f, L);
-	DISPATCH_FAMILY(desc, response_t<Fam>(src, net, g, with_shift != 0, re, im));
+	DISPATCH_FAMILY(desc, response_t<Fam>(desc.theory, src, net, g, with_shift != 0, re, im));
 	return 0;
 }
 
@@ -120,10 +121,11 @@ int hh_coherent_response(const char *method, const gwat_b200_source *src, int D,
 int hh_phenomd_setup_probe(const gwat_b200_source *src, double *out)
 {
 	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
+	const int theory = 0;
 	Network net;
 	net.D = 0;
 	WalkerCoef w;
-	walker_setup<Fam>(*src, net, host_tables(), w);
+	walker_setup<Fam>(*src, net, host_tables(), theory, w);
 	const DCoef &c = w.d;
 	double v[] = {c.fRD, c.fdamp, c.f1a, c.f3a, c.f1p, c.f2p, c.A0, c.tc, c.phic, c.beta0, c.beta1, c.alpha0, c.alpha1};
 	std::memcpy(out, v, sizeof(v));
@@ -134,10 +136,102 @@ int hh_phenomd_setup_probe(const gwat_b200_source *src, double *out)
 extern "C" int hh_debug_dcoef(const gwat_b200_source *src, double *out)
 {
 	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
+	const int theory = 0;
 	Network net;
 	net.D = 0;
 	WalkerCoef w;
-	walker_setup<Fam>(*src, net, host_tables(), w);
+	walker_setup<Fam>(*src, net, host_tables(), theory, w);
 	std::memcpy(out, &w.d, sizeof(DCoef));
 	return (int)(sizeof(DCoef) / sizeof(double));
+}
+
+// Fisher matrix of one source on the host, through the same GWAT_HD pieces the Fisher kernels use (unpack/repack of the
+// stencil points, walker setup, per-bin response); the stencil combination and the Simpson assembly are restated here
+// (they live in __global__ kernels in the product).  psd is for `detector`.
+template <class Fam>
+int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_source *src, const char *detector,
+             const char *reference, int dim, int order, const Grid &g, const double *psd, double *out)
+{
+	RepackPlan plan;
+	std::memset(&plan, 0, sizeof(plan));
+	plan.dimension = dim;
+	plan.pv2 = desc.pv2;
+	plan.nrt = desc.nrt;
+	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
+	plan.gimr = desc.gimr && !plan.ppe;
+	plan.mcmc = mcmc;
+	const int idd = detector_index(detector), idr = detector_index(reference);
+	if (idd < 0 || idr < 0) return -1;
+	const double *det_row = gwat_detector_table[idd], *ref_row = gwat_detector_table[idr];
+	const bool same = idd == idr;
+	const int npts = order == 4 ? 4 : 2;
+	const size_t L = g.f.size();
+	const double eps = 1e-8;
+	double v0[GWAT_B200_MAX_DIM];
+	int logfac[GWAT_B200_MAX_DIM];
+	unpack_fisher(*src, plan, v0, logfac);
+	std::vector<std::vector<cplx>> deriv(dim, std::vector<cplx>(L));
+	for (int i = 0; i < dim; i++) {
+		const bool bc = (i == 8 && v0[8] > .25 - eps);
+		std::vector<std::vector<cplx>> r(npts, std::vector<cplx>(L));
+		for (int k = 0; k < npts; k++) {
+			double v[GWAT_B200_MAX_DIM];
+			for (int j = 0; j < dim; j++) v[j] = v0[j];
+			const double step = (k == 0) ? eps : (k == 1) ? -eps : (k == 2) ? 2 * eps : -2 * eps;
+			if (!(step > 0 && bc)) v[i] = v0[i] + step;
+			gwat_b200_source sp;
+			repack_fisher_point(v, *src, plan, sp);
+			double tshift = 0;
+			if (!same) {
+				const double dtoa = dtoa_between(ref_row + 9, det_row + 9, sp.RA, sp.DEC, sp.gmst);
+				if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;
+				else sp.tc -= dtoa;
+			}
+			Network net;
+			net.D = 1;
+			std::memcpy(net.row[0], det_row, sizeof(double) * 13);
+			WalkerCoef w;
+			walker_setup<Fam>(sp, net, host_tables(), theory, w);
+			w.det[0].tshift = tshift;
+			for (size_t b = 0; b < L; b++) {
+				cplx hp, hc;
+				polarizations_bin<Fam>(w, g.f[b], g.hi[b], g.lo[b], g.lg[b], hp, hc);
+				r[k][b] = project_bin(w.det[0], hp, hc, g.f[b], true);
+			}
+		}
+		const double sc = logfac[i] ? v0[i] : 1.0;
+		for (size_t b = 0; b < L; b++) {
+			cplx d;
+			if (npts == 2) {
+				const double den = bc ? eps : 2. * eps;
+				d = cplx{(r[0][b].re - r[1][b].re) / den, (r[0][b].im - r[1][b].im) / den};
+			} else {
+				const double den = bc ? 6. * eps : 12. * eps;
+				d = cplx{(((-r[2][b].re + 8. * r[0][b].re) - 8. * r[1][b].re) + r[3][b].re) / den,
+				         (((-r[2][b].im + 8. * r[0][b].im) - 8. * r[1][b].im) + r[3][b].im) / den};
+			}
+			deriv[i][b] = cplx{d.re * sc, d.im * sc};
+		}
+	}
+	const double pref = quadrature_prefactor((int)L, false, g.f.data(), true);
+	for (int j = 0; j < dim; j++)
+		for (int k = 0; k <= j; k++) {
+			double acc = 0;
+			for (size_t b = 0; b < L; b++)
+				acc += quadrature_coefficient((int)b, (int)L, false, false, nullptr, g.f.data()) *
+				       ((deriv[j][b].re * deriv[k][b].re + deriv[j][b].im * deriv[k][b].im) / psd[b]);
+			out[j * dim + k] = out[k * dim + j] = pref * acc;
+		}
+	return 0;
+}
+
+extern "C" int hh_fisher_numerical(const char *method, const char *detector, const char *reference, int dim, int order,
+                                   const gwat_b200_source *src, const double *f, int L, const double *psd, double *out)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0) return -2;
+	const Grid g = make_grid(f, L);
+	int rc = 0;
+	DISPATCH_FAMILY(desc, rc = fisher_t<Fam>(desc.theory, desc.mcmc, desc, src, detector, reference, dim, order, g, psd, out));
+	return rc;
 }

@@ -1,0 +1,76 @@
+"""CPU tier: the C-ABI library loads without a GPU, exports every symbol the header declares, and refuses to run without CUDA."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from gw_analysis_tools_b200 import abi, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gwat_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gwat_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_python_binds():
+    assert sorted(engine.EXPORTS) == declared_functions()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+    assert lib.gwat_b200_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "gwat_b200.h"\nint main(void){printf("%zu %zu\\n", sizeof(gwat_b200_source), sizeof(gwat_b200_mod));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    a, b = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(a) == C.sizeof(abi.Source) and int(b) == C.sizeof(abi.Mod)
+
+
+def test_defaults_match_reference_members():
+    lib = engine.load_library()
+    s = abi.Source()
+    lib.gwat_b200_source_init(C.byref(s))
+    d = abi.source_defaults()
+    for name, _ in abi.Source._fields_:
+        a, b = getattr(s, name), getattr(d, name)
+        if hasattr(a, "__len__"):
+            assert list(a) == list(b), name
+        else:
+            assert a == b, name
+    assert s.tidal1 == -1 and s.chip == -1 and s.shift_time == 1 and s.tidal_love == 1 and s.PNorder == 35
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to create a context (and says why); it never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.GwatB200Error) as e:
+        engine.Context(0)
+    assert e.value.code == abi.ERR_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gw_analysis_tools_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".h", ".cu", ".cpp", ".inc")):
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                path = os.path.join(dirpath, fn)
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+                assert not re.search(r'#include\s+"[^"]*(oracle|host_harness)', text), path
+                assert "libgwat_ref" not in text and "libgwat_host_harness" not in text and "dlopen" not in text, path

@@ -1,0 +1,148 @@
+"""CPU tier: the kernels' GWAT_HD mathematics, compiled as plain C++ (tests/host_harness.cpp), against the golden vectors
+generated from the reference's own code, and the oracle itself against the same vectors.
+
+Tolerances are BASELINE.json's: waveform <= 1e-10 of max|h|, logL <= 1e-9 relative.  Fisher matrices are compared with the
+normalised measure max_ij |dF_ij| / sqrt(F_ii F_jj).  Finite differences with eps = 1e-8 amplify rounding noise by 1e8, so
+the reference does not reproduce ITSELF to 1e-6 under a change of instruction selection: the golden file stores, next to
+every matrix, the same measure between the reference and the reference rebuilt with FMA contraction (`noise`).  The bound
+used here is max(1e-6, 8 x that noise floor; the floor is itself a single sample of the noise).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from gw_analysis_tools_b200 import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+WF_TOL = 1e-10
+FISHER_NORM_TOL = 1e-6
+FISHER_NOISE_FACTOR = 8.0
+_dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def hh():
+    path = os.path.join(ROOT, "tests", "_build", "libgwat_host_harness.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build_harness()
+    return C.CDLL(path)
+
+
+@pytest.fixture(scope="module")
+def gold_wf():
+    return np.load(os.path.join(GOLD, "waveforms_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold_fisher():
+    return np.load(os.path.join(GOLD, "fisher_v1.npz"))
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_waveform_and_response_vs_golden(hh, gold_wf, case):
+    name, method, kw, gspec = case
+    f = cases.grid(gspec)
+    src = cases.source_from_bytes(gold_wf[name + "/src"])
+    L = f.size
+    o = [np.zeros(L) for _ in range(4)]
+    assert hh.hh_fourier_waveform(method.encode(), C.byref(src), _p(f), L, *[_p(x) for x in o]) == 0
+    assert _relerr(o[0] + 1j * o[1], gold_wf[name + "/hp"]) <= WF_TOL
+    assert _relerr(o[2] + 1j * o[3], gold_wf[name + "/hc"]) <= WF_TOL
+    D = len(cases.DETECTORS)
+    re, im = np.zeros((D, L)), np.zeros((D, L))
+    dets = (C.c_char_p * D)(*[d.encode() for d in cases.DETECTORS])
+    assert hh.hh_coherent_response(method.encode(), C.byref(src), D, dets, _p(f), L, 1, _p(re), _p(im)) == 0
+    for d in range(D):
+        assert _relerr(re[d] + 1j * im[d], gold_wf[name + "/resp"][d]) <= WF_TOL
+    if name + "/single_L" in gold_wf:
+        assert hh.hh_coherent_response(method.encode(), C.byref(src), D, dets, _p(f), L, 0, _p(re), _p(im)) == 0
+        assert _relerr(re[1] + 1j * im[1], gold_wf[name + "/single_L"]) <= WF_TOL
+
+
+def test_modified_families_differ_from_gr(gold_wf):
+    """The modification terms are really exercised: each modified case is far (>> tolerance) from its GR counterpart."""
+    for name, base in [("ppE_ins", "D_bbh"), ("ppE_imr", "D_bbh"), ("gIMR", "D_bbh"), ("gIMR_log", "D_bbh"), ("dCS", "D_bbh"),
+                       ("EdGB", "D_low"), ("ppE_P_ins", "P_full"), ("gIMR_P", "P_full"), ("dCS_P", "P_full")]:
+        assert _relerr(gold_wf[name + "/hp"], gold_wf[base + "/hp"]) > 1e-4, name
+
+
+@pytest.mark.parametrize("case", cases.FISHER_CASES, ids=[c[0] for c in cases.FISHER_CASES])
+def test_fisher_vs_golden(hh, gold_fisher, case):
+    name, method, kw, dim = case
+    f = cases.grid(cases.FISHER_GRID)
+    psd = workloads.aligo_analytic_psd(f)
+    src = cases.source_from_bytes(gold_fisher[name + "/src"])
+    for order in (2, 4):
+        for det in cases.DETECTORS[:2]:
+            out = np.zeros((dim, dim))
+            rc = hh.hh_fisher_numerical(method.encode(), det.encode(), b"Hanford", dim, order, C.byref(src), _p(f), f.size,
+                                        _p(psd), _p(out))
+            assert rc == 0
+            ref = gold_fisher["%s/o%d/%s" % (name, order, det)]
+            dg = np.sqrt(np.abs(np.diag(ref)))
+            tol = max(FISHER_NORM_TOL, FISHER_NOISE_FACTOR * float(gold_fisher["%s/o%d/%s/noise" % (name, order, det)]))
+            assert (np.abs(out - ref) / np.outer(dg, dg)).max() <= tol, (name, order, det, tol)
+            assert np.allclose(out, out.T)
+
+
+def test_unknown_method_is_rejected(hh):
+    f = cases.grid(cases.GRID_BBH)
+    src = cases.source(cases.BBH)
+    o = [np.zeros(f.size) for _ in range(4)]
+    for bad in ("IMRPhenomXYZ", "", "IMRPhenomPv3", "EA_IMRPhenomD_NRT"):
+        assert hh.hh_fourier_waveform(bad.encode(), C.byref(src), _p(f), f.size, *[_p(x) for x in o]) == -2
+
+
+def test_grid_tables_reproduce_glibc_pow():
+    """f^(fl(1/6)) * M^(fl(1/6)) in double-double, rounded once, equals glibc's pow(M*f, 1./6.) to <= 1 ulp."""
+    rng = np.random.default_rng(3)
+    f = rng.uniform(5, 4096, 20000)
+    M = rng.uniform(2, 200, 20000) * 4.925491025543576e-06
+    ld = np.longdouble
+    sf = np.power(f.astype(ld), ld(1.0 / 6.0))
+    sm = np.power(M.astype(ld), ld(1.0 / 6.0))
+    mine = (sf * sm).astype(np.float64)
+    ref = np.power(M * f, 1.0 / 6.0)
+    ulp = np.abs(mine - ref) / np.spacing(ref)
+    assert ulp.max() <= 1.0
+    assert (ulp == 0).mean() > 0.85
+
+
+# ---- the oracle itself is pinned by the same vectors ---------------------------------------------------------------------
+
+def test_oracle_reproduces_golden(oracle, gold_wf):
+    for name, method, kw, gspec in cases.CASES[::4]:
+        f = cases.grid(gspec)
+        src = cases.source_from_bytes(gold_wf[name + "/src"])
+        hp, hc = oracle.fourier_waveform(method, src, f)
+        assert np.array_equal(hp, gold_wf[name + "/hp"]) and np.array_equal(hc, gold_wf[name + "/hc"])
+        resp = oracle.coherent_response(method, src, cases.DETECTORS, f)
+        psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+        ll = oracle.loglike_batch(method, [src], cases.DETECTORS, f, psd, cases.derived_data(resp))[0]
+        assert ll == float(gold_wf[name + "/logL"])
+
+
+def test_oracle_sample_value_from_survey(oracle):
+    """SURVEY.md Appendix A quotes logL = 1.495080331741781e+04 for this configuration of the reference."""
+    from gw_analysis_tools_b200 import abi
+    f = 20 + 0.25 * np.arange(8192)
+    psd = np.tile(oracle.populate_noise(f, "aLIGO_analytic") ** 2, (3, 1))
+    inj = abi.source_defaults(**cases.BBH)
+    data = oracle.coherent_response("IMRPhenomD", inj, cases.DETECTORS, f)
+    tmpl = abi.source_defaults(**dict(cases.BBH, mass1=36.4 * 1.0005))
+    ll = oracle.loglike_batch("IMRPhenomD", [tmpl], cases.DETECTORS, f, psd, data)[0]
+    assert abs(ll - 1.495080331741781e+04) <= 1e-9 * 1.5e4
+    assert np.allclose(oracle.populate_noise(f, "aLIGO_analytic") ** 2, workloads.aligo_analytic_psd(f), rtol=1e-15, atol=0)

@@ -101,6 +101,17 @@ def main():
         assert len(D) == 9 and len(loc) == 3
         rows.append((name, D, loc, gf))
 
+    # redshift(luminosity distance) piecewise half-power series of the default cosmology PLANCK15
+    # (include/gwat/D_Z_Config.h: boundaries_D[0], COEFF_VEC_DZ[0]; evaluated by Z_from_DL, src/util.cpp:356-382)
+    dz = strip_comments(open(os.path.join(REF, "include/gwat/D_Z_Config.h")).read())
+    bD = numbers(array_body(dz, "boundaries_D"))
+    cDZ = numbers(array_body(dz, "COEFF_VEC_DZ"))
+    ncos = int(re.search(r"num_cosmologies\s*=\s*(\d+)", dz).group(1))
+    nseg, ndeg = 3, 12
+    assert len(bD) == ncos * (nseg + 1) and len(cDZ) == ncos * nseg * ndeg, (len(bD), len(cDZ))
+    bD0 = bD[:nseg + 1]
+    cDZ0 = cDZ[:nseg * ndeg]
+
     r = repr
     with open(OUT, "w") as o:
         o.write("// GENERATED by tools/gen_tables.py from the reference's numerical data tables -- do not edit.\n")
@@ -115,6 +126,13 @@ def main():
         o.write("GWAT_TABLE_QUALIFIER double gwat_phenomd_fit[19][11] = {\n")
         for i in range(19):
             o.write("{" + ",".join(r(x) for x in lam[i * 11:(i + 1) * 11]) + "},\n")
+        o.write("};\n\n")
+        o.write("// PLANCK15 z(D_L/Mpc): segment boundaries and, per segment, coefficients of sum_k c_k (sqrt D_L)^k\n")
+        o.write("#define GWAT_DZ_SEGMENTS %d\n#define GWAT_DZ_DEGREE %d\n" % (nseg, ndeg))
+        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_boundaries[GWAT_DZ_SEGMENTS + 1] = {" + ",".join(r(x) for x in bD0) + "};\n")
+        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_coeffs[GWAT_DZ_SEGMENTS][GWAT_DZ_DEGREE] = {\n")
+        for i in range(nseg):
+            o.write("{" + ",".join(r(x) for x in cDZ0[i * ndeg:(i + 1) * ndeg]) + "},\n")
         o.write("};\n\n")
         o.write("#define GWAT_NUM_KNOWN_DETECTORS %d\n" % len(rows))
         o.write("// per detector: 9 response-tensor entries (row-major), 3 vertex coordinates [m], geometric factor\n")
