@@ -384,6 +384,9 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 		w.pfac = .5 * (1. + ci * ci);
 	}
 	detector_setup(net, src.RA, src.DEC, src.psi, src.gmst, w.det);
+	// options of the reference that are outside this path are refused loudly (NaN), never silently approximated:
+	// horizon/equatorial-orientation inputs, sky-averaged amplitudes, and the wall-clock-seeded tidal_love_error draw
+	if (src.horizon_coord || src.equatorial_orientation || src.sky_average || (Fam::nrt && src.tidal_love_error)) w.d.A0 = NAN;
 	w.valid = 1;
 }
 

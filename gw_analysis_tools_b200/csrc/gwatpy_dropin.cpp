@@ -1,0 +1,470 @@
+// Host-side mirror of the gwatpy-facing C API of GWAT for the accelerated path -> libgwat_b200_gwatpy.so
+//
+// gwatpy loads libgwat.so with ctypes and calls `extern "C"` functions declared in include/gwat/gwatpy_wrapping.h
+// (implemented in src/gwatpy_wrapping.cpp).  This file exports the on-path subset of those functions under the SAME names
+// with the SAME argument lists, implemented on top of the C ABI of include/gwat_b200.h, so gwatpy (or any ctypes user)
+// can point at this library for them.  The objects the reference hands to Python as opaque pointers
+// (gen_params_base<double>*, MCMC_modification_struct*) are opaque here too; their layout is private to this file.
+//
+// Everything numerical runs in the CUDA kernels behind the C ABI.  The only host arithmetic in this file is the handful of
+// scalar mass conversions gwatpy exposes (calculate_*_py), which are not part of the hot path.
+//
+// Deliberate deviations from the reference's wrappers (all documented in INTEGRATION.md):
+//  * MCMC_likelihood_extrinsic computes the segment duration from pointer arithmetic on a double** (src/mcmc_gw.cpp:2466);
+//    here T = 1/(frequencies[1]-frequencies[0]) -- the evident intent.  *_T variants take T explicitly.
+//  * the detector letters are mapped letter by letter ("H","L","V","K","C"); the reference compares the REST of the string
+//    (src/gwatpy_wrapping.cpp:131-140), which only works for the default order "HLV".
+//  * unknown detectors / methods return NaN (or a negative status) instead of calling exit(1).
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gwat_b200.h"
+
+namespace {
+
+struct GenParams {  // what gen_params_base_py returns
+	gwat_b200_source s;
+	std::string cosmology;
+};
+struct ModStruct {  // what MCMC_modification_struct_py returns
+	gwat_b200_mod m;
+};
+
+// One process-wide context; the uploaded network is cached and only re-uploaded when the caller's arrays change.
+struct Session {
+	std::mutex mu;
+	gwat_b200_ctx *ctx = nullptr;
+	uint64_t net_key = 0;
+	std::string last_error;
+};
+Session &session()
+{
+	static Session s;
+	return s;
+}
+
+uint64_t fnv(uint64_t h, const void *p, size_t n)
+{
+	const unsigned char *b = static_cast<const unsigned char *>(p);
+	for (size_t i = 0; i < n; i++) {
+		h ^= b[i];
+		h *= 1099511628211ULL;
+	}
+	return h;
+}
+
+const char *detector_from_letter(char c)
+{
+	switch (c) {
+	case 'H': return "Hanford";
+	case 'L': return "Livingston";
+	case 'V': return "Virgo";
+	case 'K': return "Kagra";
+	case 'C': return "CE";
+	default: return nullptr;
+	}
+}
+
+int ensure_ctx(Session &S)
+{
+	if (S.ctx) return 0;
+	int dev = 0;
+	if (const char *e = std::getenv("GWAT_B200_DEVICE")) dev = std::atoi(e);
+	const int rc = gwat_b200_ctx_create(&S.ctx, dev);
+	if (rc != 0) {
+		S.last_error = gwat_b200_last_error(nullptr);
+		std::fprintf(stderr, "gwat_b200: %s\n", S.last_error.c_str());
+	}
+	return rc;
+}
+
+// Upload (or reuse) the network described by gwatpy's flat detector-major arrays.
+int ensure_network(Session &S, int D, const char *const *dets, int L, const double *f, const double *psd, const double *dre,
+                   const double *dim, const double *weights, const char *integ, bool log10F)
+{
+	if (int rc = ensure_ctx(S)) return rc;
+	uint64_t key = 1469598103934665603ULL;
+	key = fnv(key, &D, sizeof(D));
+	key = fnv(key, &L, sizeof(L));
+	for (int d = 0; d < D; d++) key = fnv(key, dets[d], std::strlen(dets[d]));
+	key = fnv(key, f, sizeof(double) * L);
+	key = fnv(key, psd, sizeof(double) * (size_t)D * L);
+	if (dre) key = fnv(key, dre, sizeof(double) * (size_t)D * L);
+	if (dim) key = fnv(key, dim, sizeof(double) * (size_t)D * L);
+	const bool gl = integ && std::string(integ) == "GAUSSLEG";
+	if (gl && weights) key = fnv(key, weights, sizeof(double) * L);
+	key = fnv(key, integ ? integ : "", integ ? std::strlen(integ) : 0);
+	key = fnv(key, &log10F, sizeof(log10F));
+	if (key == S.net_key) return 0;
+	const int rc = gwat_b200_set_network(S.ctx, D, dets, L, f, psd, dre, dim, gl ? weights : nullptr, integ, log10F ? 1 : 0);
+	if (rc != 0) {
+		S.last_error = gwat_b200_last_error(S.ctx);
+		std::fprintf(stderr, "gwat_b200: %s\n", S.last_error.c_str());
+		S.net_key = 0;
+		return rc;
+	}
+	S.net_key = key;
+	return 0;
+}
+
+int report(Session &S, int rc)
+{
+	if (rc != 0) {
+		S.last_error = gwat_b200_last_error(S.ctx);
+		std::fprintf(stderr, "gwat_b200: %s\n", S.last_error.c_str());
+	}
+	return rc;
+}
+
+// a throw-away one-detector network on the caller's grid, for the waveform / single-response entry points
+int ensure_grid_only(Session &S, const char *detector, int L, const double *f)
+{
+	std::vector<double> ones(L, 1.0);
+	const char *dets[1] = {detector};
+	return ensure_network(S, 1, dets, L, f, ones.data(), nullptr, nullptr, nullptr, "SIMPSONS", false);
+}
+
+const double NaN = std::numeric_limits<double>::quiet_NaN();
+
+double likelihood_common(bool mcmc_vector, const double *parameters, const gwat_b200_mod *mod, int dimension,
+                         const gwat_b200_source *src, int W, const char *generation_method, const int *data_length,
+                         const double *frequencies, const double *dataREAL, const double *dataIMAG, const double *psd,
+                         const double *weights, const char *integration_method, bool log10F, const char *detectors,
+                         int num_detectors, double gmst, double T_segment, double *out)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (num_detectors < 1 || num_detectors > GWAT_B200_MAX_DETECTORS || !detectors || !data_length) return NaN;
+	const int L = data_length[0];
+	for (int d = 1; d < num_detectors; d++)
+		if (data_length[d] != L) return NaN;  // the reference only supports a shared grid too (src/waveform_util.cpp:140-145)
+	const char *dets[GWAT_B200_MAX_DETECTORS];
+	for (int d = 0; d < num_detectors; d++) {
+		dets[d] = detector_from_letter(detectors[d]);
+		if (!dets[d]) return NaN;
+	}
+	if (ensure_network(S, num_detectors, dets, L, frequencies, psd, dataREAL, dataIMAG, weights, integration_method, log10F)) return NaN;
+	int rc;
+	if (mcmc_vector) {
+		const double T = T_segment > 0 ? T_segment : 1. / (frequencies[1] - frequencies[0]);
+		rc = gwat_b200_loglike_mcmc_batch(S.ctx, generation_method, mod, dimension, W, parameters, gmst, T, out);
+	} else {
+		// MCMC_likelihood_extrinsic: tc_ref = T - tc  (src/mcmc_gw.cpp:2467,2473)
+		std::vector<gwat_b200_source> tmp(src, src + W);
+		const double T = T_segment > 0 ? T_segment : 1. / (frequencies[1] - frequencies[0]);
+		for (auto &s : tmp) s.tc = T - s.tc;
+		rc = gwat_b200_loglike_batch(S.ctx, generation_method, W, tmp.data(), out);
+	}
+	if (report(S, rc)) return NaN;
+	return out[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- object constructors / destructors (src/gwatpy_wrapping.cpp:244-420) ------------------------------------------------
+void *gen_params_base_py(double mass1, double mass2, double *spin1, double *spin2, double Luminosity_Distance, double incl_angle,
+                         double RA, double DEC, double psi, double gmst, double tc, double phiRef, double f_ref, double theta_l,
+                         double phi_l, double theta, double phi, char *cosmology, bool equatorial_orientation, bool horizon_coord,
+                         bool NSflag1, bool NSflag2, bool dep_postmerger, bool shift_time, bool shift_phase, bool sky_average,
+                         double LISA_alpha0, double LISA_phi0, int Nmod_phi, int Nmod_sigma, int Nmod_beta, int Nmod_alpha,
+                         int *phii, int *sigmai, int *betai, int *alphai, double *delta_phi, double *delta_sigma,
+                         double *delta_beta, double *delta_alpha, int Nmod, double *bppe, double *betappe)
+{
+	(void)LISA_alpha0;
+	(void)LISA_phi0;
+	GenParams *p = new GenParams;
+	gwat_b200_source &s = p->s;
+	gwat_b200_source_init(&s);
+	s.mass1 = mass1;
+	s.mass2 = mass2;
+	for (int i = 0; i < 3; i++) {
+		s.spin1[i] = spin1 ? spin1[i] : 0;
+		s.spin2[i] = spin2 ? spin2[i] : 0;
+	}
+	s.Luminosity_Distance = Luminosity_Distance;
+	s.incl_angle = incl_angle;
+	s.RA = RA;
+	s.DEC = DEC;
+	s.psi = psi;
+	s.gmst = gmst;
+	s.tc = tc;
+	s.phiRef = phiRef;
+	s.f_ref = f_ref;
+	s.theta_l = theta_l;
+	s.phi_l = phi_l;
+	s.theta = theta;
+	s.phi = phi;
+	p->cosmology = cosmology ? cosmology : "PLANCK15";
+	s.equatorial_orientation = equatorial_orientation;
+	s.horizon_coord = horizon_coord;
+	s.NSflag1 = NSflag1;
+	s.NSflag2 = NSflag2;
+	s.dep_postmerger = dep_postmerger;
+	s.shift_time = shift_time;
+	s.shift_phase = shift_phase;
+	s.sky_average = sky_average;
+	auto clampn = [](int n) { return n < 0 ? 0 : (n > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : n); };
+	s.Nmod_phi = clampn(Nmod_phi);
+	s.Nmod_sigma = clampn(Nmod_sigma);
+	s.Nmod_beta = clampn(Nmod_beta);
+	s.Nmod_alpha = clampn(Nmod_alpha);
+	s.Nmod = clampn(Nmod);
+	for (int i = 0; i < s.Nmod_phi; i++) { s.phii[i] = phii[i]; s.delta_phi[i] = delta_phi[i]; }
+	for (int i = 0; i < s.Nmod_sigma; i++) { s.sigmai[i] = sigmai[i]; s.delta_sigma[i] = delta_sigma[i]; }
+	for (int i = 0; i < s.Nmod_beta; i++) { s.betai[i] = betai[i]; s.delta_beta[i] = delta_beta[i]; }
+	for (int i = 0; i < s.Nmod_alpha; i++) { s.alphai[i] = alphai[i]; s.delta_alpha[i] = delta_alpha[i]; }
+	for (int i = 0; i < s.Nmod; i++) { s.bppe[i] = bppe[i]; s.betappe[i] = betappe[i]; }
+	return p;
+}
+void gen_params_base_py_destructor(void *p) { delete static_cast<GenParams *>(p); }
+
+// Accessor the reference does not have: tidal fields are plain members there and gwatpy never sets them through the
+// constructor; exposed so NRT waveforms are reachable from Python.
+void gen_params_base_set_tidal_py(void *p, double tidal1, double tidal2, double tidal_s, double tidal_weighted, bool tidal_love)
+{
+	gwat_b200_source &s = static_cast<GenParams *>(p)->s;
+	s.tidal1 = tidal1;
+	s.tidal2 = tidal2;
+	s.tidal_s = tidal_s;
+	s.tidal_weighted = tidal_weighted;
+	s.tidal_love = tidal_love;
+}
+void gen_params_base_set_chip_py(void *p, double chip, double phip)
+{
+	static_cast<GenParams *>(p)->s.chip = chip;
+	static_cast<GenParams *>(p)->s.phip = phip;
+}
+// copy of the flat record, for tests and for users who want to go to the C ABI directly
+void gen_params_base_get_flat_py(void *p, gwat_b200_source *out) { *out = static_cast<GenParams *>(p)->s; }
+
+void *MCMC_modification_struct_py(int ppE_Nmod, double *bppe, int gIMR_Nmod_phi, int *gIMR_phii, int gIMR_Nmod_sigma,
+                                  int *gIMR_sigmai, int gIMR_Nmod_beta, int *gIMR_betai, int gIMR_Nmod_alpha, int *gIMR_alphai,
+                                  bool NSflag1, bool NSflag2)
+{
+	ModStruct *m = new ModStruct;
+	gwat_b200_mod_init(&m->m);
+	auto clampn = [](int n) { return n < 0 ? 0 : (n > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : n); };
+	m->m.ppE_Nmod = clampn(ppE_Nmod);
+	for (int i = 0; i < m->m.ppE_Nmod; i++) m->m.bppe[i] = bppe[i];
+	m->m.gIMR_Nmod_phi = clampn(gIMR_Nmod_phi);
+	m->m.gIMR_Nmod_sigma = clampn(gIMR_Nmod_sigma);
+	m->m.gIMR_Nmod_beta = clampn(gIMR_Nmod_beta);
+	m->m.gIMR_Nmod_alpha = clampn(gIMR_Nmod_alpha);
+	for (int i = 0; i < m->m.gIMR_Nmod_phi; i++) m->m.gIMR_phii[i] = gIMR_phii[i];
+	for (int i = 0; i < m->m.gIMR_Nmod_sigma; i++) m->m.gIMR_sigmai[i] = gIMR_sigmai[i];
+	for (int i = 0; i < m->m.gIMR_Nmod_beta; i++) m->m.gIMR_betai[i] = gIMR_betai[i];
+	for (int i = 0; i < m->m.gIMR_Nmod_alpha; i++) m->m.gIMR_alphai[i] = gIMR_alphai[i];
+	m->m.NSflag1 = NSflag1;
+	m->m.NSflag2 = NSflag2;
+	return m;
+}
+void MCMC_modification_struct_py_destructor(void *m) { delete static_cast<ModStruct *>(m); }
+
+// ---- waveforms and responses (src/gwatpy_wrapping.cpp: fourier_waveform_py, fourier_detector_response_py) -------------------
+int fourier_waveform_py(double *frequencies, int length, double *wf_plus_real, double *wf_plus_imaginary, double *wf_cross_real,
+                        double *wf_cross_imaginary, char *generation_method, void *parameters)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
+	const int rc = gwat_b200_fourier_waveform_batch(S.ctx, generation_method, 1, &static_cast<GenParams *>(parameters)->s,
+	                                                wf_plus_real, wf_plus_imaginary, wf_cross_real, wf_cross_imaginary);
+	return report(S, rc) == 0 ? 1 : 0;  // the reference returns status 1 on success (src/waveform_generator.cpp:113,293)
+}
+
+int fourier_detector_response_py(double *frequencies, int length, double *response_real, double *response_imaginary,
+                                 char *detector, char *generation_method, void *parameters)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, detector, length, frequencies)) return 0;
+	const int rc = gwat_b200_fourier_detector_response_batch(S.ctx, generation_method, detector, 1,
+	                                                         &static_cast<GenParams *>(parameters)->s, response_real,
+	                                                         response_imaginary);
+	return report(S, rc) == 0 ? 1 : 0;
+}
+
+// batched versions (new): W parameter objects at once, outputs [W][length]
+int fourier_waveform_batch_py(double *frequencies, int length, int W, void **parameters, char *generation_method,
+                              double *wf_plus_real, double *wf_plus_imaginary, double *wf_cross_real, double *wf_cross_imaginary)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
+	std::vector<gwat_b200_source> src(W);
+	for (int w = 0; w < W; w++) src[w] = static_cast<GenParams *>(parameters[w])->s;
+	const int rc = gwat_b200_fourier_waveform_batch(S.ctx, generation_method, W, src.data(), wf_plus_real, wf_plus_imaginary,
+	                                                wf_cross_real, wf_cross_imaginary);
+	return report(S, rc) == 0 ? 1 : 0;
+}
+
+// ---- likelihoods (src/gwatpy_wrapping.cpp:96-241) ---------------------------------------------------------------------------
+double MCMC_likelihood_extrinsic_py(bool save_waveform, void *parameters, char *generation_method, int *data_length,
+                                    double *frequencies, double *dataREAL, double *dataIMAG, double *psd, double *weights,
+                                    char *integration_method, bool log10F, char *detectors, int num_detectors)
+{
+	(void)save_waveform;
+	double out = NaN;
+	const gwat_b200_source &s = static_cast<GenParams *>(parameters)->s;
+	return likelihood_common(false, nullptr, nullptr, 0, &s, 1, generation_method, data_length, frequencies, dataREAL, dataIMAG,
+	                         psd, weights, integration_method, log10F, detectors, num_detectors, s.gmst, -1, &out);
+}
+
+// The reference's pyv2 wrapper runs MCMC_prep_params in a translation unit whose static mcmc_gmst is never set, i.e. with
+// gmst = 0 (include/gwat/mcmc_gw.h:35); the same-named function keeps that, the *_gmst variant takes it explicitly.
+double MCMC_likelihood_extrinsic_pyv2(bool save_waveform, double *parameters, void *mod_struct, int dimension,
+                                      char *generation_method, int *data_length, double *frequencies, double *dataREAL,
+                                      double *dataIMAG, double *psd, double *weights, char *integration_method, bool log10F,
+                                      char *detectors, int num_detectors)
+{
+	(void)save_waveform;
+	double out = NaN;
+	return likelihood_common(true, parameters, mod_struct ? &static_cast<ModStruct *>(mod_struct)->m : nullptr, dimension, nullptr, 1,
+	                         generation_method, data_length, frequencies, dataREAL, dataIMAG, psd, weights, integration_method,
+	                         log10F, detectors, num_detectors, 0.0, -1, &out);
+}
+
+// NEW: W sampling vectors in one call; parameters[W][dimension] row-major, out[W].
+// gmst and T_segment are explicit (T_segment <= 0: 1/(f[1]-f[0])).  Returns 0 on success.
+int MCMC_likelihood_extrinsic_batch_py(double *parameters, int W, void *mod_struct, int dimension, char *generation_method,
+                                       int *data_length, double *frequencies, double *dataREAL, double *dataIMAG, double *psd,
+                                       double *weights, char *integration_method, bool log10F, char *detectors,
+                                       int num_detectors, double gmst, double T_segment, double *out)
+{
+	if (W <= 0) return 0;
+	const double r = likelihood_common(true, parameters, mod_struct ? &static_cast<ModStruct *>(mod_struct)->m : nullptr, dimension,
+	                                   nullptr, W, generation_method, data_length, frequencies, dataREAL, dataIMAG, psd, weights,
+	                                   integration_method, log10F, detectors, num_detectors, gmst, T_segment, out);
+	(void)r;
+	return session().last_error.empty() ? 0 : -1;
+}
+
+// repack_parameters_py (src/gwatpy_wrapping.cpp): sampling vector -> the gen_params object, "MCMC_"+method layout.
+// The non-parameter options already stored in the object (gmst, flags, modification layout) are kept.
+void repack_parameters_py(double *parameters, void *gen_param, char *generation_method, int dim)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_ctx(S)) return;
+	GenParams *g = static_cast<GenParams *>(gen_param);
+	gwat_b200_mod mod;
+	gwat_b200_mod_init(&mod);
+	mod.ppE_Nmod = g->s.Nmod;
+	for (int i = 0; i < GWAT_B200_MAX_MOD; i++) mod.bppe[i] = g->s.bppe[i];
+	mod.gIMR_Nmod_phi = g->s.Nmod_phi;
+	mod.gIMR_Nmod_sigma = g->s.Nmod_sigma;
+	mod.gIMR_Nmod_beta = g->s.Nmod_beta;
+	mod.gIMR_Nmod_alpha = g->s.Nmod_alpha;
+	for (int i = 0; i < GWAT_B200_MAX_MOD; i++) {
+		mod.gIMR_phii[i] = g->s.phii[i];
+		mod.gIMR_sigmai[i] = g->s.sigmai[i];
+		mod.gIMR_betai[i] = g->s.betai[i];
+		mod.gIMR_alphai[i] = g->s.alphai[i];
+	}
+	mod.NSflag1 = g->s.NSflag1;
+	mod.NSflag2 = g->s.NSflag2;
+	mod.tidal_love = g->s.tidal_love;
+	std::string m(generation_method ? generation_method : "");
+	if (m.compare(0, 5, "MCMC_") == 0) m.erase(0, 5);
+	gwat_b200_source out;
+	if (report(S, gwat_b200_repack_mcmc_batch(S.ctx, m.c_str(), &mod, dim, 1, parameters, g->s.gmst, &out))) return;
+	// only the sampled quantities move; flags that MCMC_prep_params (not repack_parameters) would set stay as they were
+	gwat_b200_source keep = g->s;
+	g->s = out;
+	g->s.f_ref = keep.f_ref;
+	g->s.shift_time = keep.shift_time;
+	g->s.shift_phase = keep.shift_phase;
+	g->s.sky_average = keep.sky_average;
+	g->s.gmst = keep.gmst;
+}
+
+// ---- detector helpers ---------------------------------------------------------------------------------------------------
+double DTOA_DETECTOR_py(double RA, double DEC, double GMST_rad, char *det1, char *det2)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_ctx(S)) return NaN;
+	const char *dets[2] = {det1, det2};
+	const double f[4] = {1, 2, 3, 4}, ones[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+	S.net_key = 0;
+	if (report(S, gwat_b200_set_network(S.ctx, 2, dets, 4, f, ones, nullptr, nullptr, nullptr, "SIMPSONS", 0))) return NaN;
+	double psi = 0, fp[2], fc[2], dt[2];
+	if (report(S, gwat_b200_antenna_batch(S.ctx, 1, &RA, &DEC, &psi, GMST_rad, fp, fc, dt))) return NaN;
+	return dt[1];
+}
+
+void detector_response_equatorial_py(char *detector, double ra, double dec, double psi, double gmst, bool *active_polarizations,
+                                     double *response_functions)
+{
+	(void)active_polarizations;  // only the tensor polarisations are on this path
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	response_functions[0] = response_functions[1] = NaN;
+	if (ensure_ctx(S)) return;
+	const char *dets[1] = {detector};
+	const double f[4] = {1, 2, 3, 4}, ones[4] = {1, 1, 1, 1};
+	S.net_key = 0;
+	if (report(S, gwat_b200_set_network(S.ctx, 1, dets, 4, f, ones, nullptr, nullptr, nullptr, "SIMPSONS", 0))) return;
+	double fp, fc, dt;
+	if (report(S, gwat_b200_antenna_batch(S.ctx, 1, &ra, &dec, &psi, gmst, &fp, &fc, &dt))) return;
+	response_functions[0] = fp;
+	response_functions[1] = fc;
+}
+
+// ---- scalar conveniences gwatpy exposes (not on the hot path; plain host arithmetic, src/util.cpp:1492-1540) --------------------
+int calculate_chirpmass_py(double mass1, double mass2, double *out)
+{
+	*out = std::pow(mass1 * mass2, 3. / 5) / std::pow(mass1 + mass2, 1. / 5);
+	return 0;
+}
+int calculate_eta_py(double mass1, double mass2, double *out)
+{
+	*out = (mass1 * mass2) / std::pow(mass1 + mass2, 2);
+	return 0;
+}
+int calculate_mass1_py(double chirpmass, double eta, double *out)
+{
+	const double etapow = std::pow(eta, 3. / 5);
+	*out = 1. / 2 * (chirpmass / etapow + std::sqrt(1. - 4 * eta) * chirpmass / etapow);
+	return 0;
+}
+int calculate_mass2_py(double chirpmass, double eta, double *out)
+{
+	const double etapow = std::pow(eta, 3. / 5);
+	*out = 1. / 2 * (chirpmass / etapow - std::sqrt(1. - 4 * eta) * chirpmass / etapow);
+	return 0;
+}
+int calculate_chirpmass_vectorized_py(double *mass1, double *mass2, double *out, int length)
+{
+	for (int i = 0; i < length; i++) calculate_chirpmass_py(mass1[i], mass2[i], out + i);
+	return 0;
+}
+int calculate_eta_vectorized_py(double *mass1, double *mass2, double *out, int length)
+{
+	for (int i = 0; i < length; i++) calculate_eta_py(mass1[i], mass2[i], out + i);
+	return 0;
+}
+int calculate_mass1_vectorized_py(double *chirpmass, double *eta, double *out, int length)
+{
+	for (int i = 0; i < length; i++) calculate_mass1_py(chirpmass[i], eta[i], out + i);
+	return 0;
+}
+int calculate_mass2_vectorized_py(double *chirpmass, double *eta, double *out, int length)
+{
+	for (int i = 0; i < length; i++) calculate_mass2_py(chirpmass[i], eta[i], out + i);
+	return 0;
+}
+
+// Why the last call failed ("" if it did not).
+const char *gwat_b200_gwatpy_last_error(void) { return session().last_error.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+"""The gwatpy-facing mirror (libgwat_b200_gwatpy.so): same extern "C" names and argument lists as the reference's
+src/gwatpy_wrapping.cpp for the accelerated path, called here exactly the way gwatpy's ctypes code calls libgwat.so
+(gwatpy/gwatpy/mcmc_routines.py, waveform_generator_ext.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from gw_analysis_tools_b200 import abi, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gw_analysis_tools_b200", "libgwat_b200_gwatpy.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+ON_PATH_SYMBOLS = ["gen_params_base_py", "gen_params_base_py_destructor", "MCMC_modification_struct_py",
+                   "MCMC_modification_struct_py_destructor", "fourier_waveform_py", "fourier_detector_response_py",
+                   "MCMC_likelihood_extrinsic_py", "MCMC_likelihood_extrinsic_pyv2", "repack_parameters_py", "DTOA_DETECTOR_py",
+                   "detector_response_equatorial_py", "calculate_chirpmass_py", "calculate_eta_py", "calculate_mass1_py",
+                   "calculate_mass2_py", "calculate_chirpmass_vectorized_py", "calculate_eta_vectorized_py",
+                   "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py"]
+
+
+def _lib():
+    lib = C.CDLL(LIB)
+    lib.gen_params_base_py.restype = C.c_void_p
+    lib.MCMC_modification_struct_py.restype = C.c_void_p
+    lib.MCMC_likelihood_extrinsic_py.restype = C.c_double
+    lib.MCMC_likelihood_extrinsic_pyv2.restype = C.c_double
+    lib.DTOA_DETECTOR_py.restype = C.c_double
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _gen_params(lib, kw):
+    s = abi.source_defaults(**kw)
+    d3 = C.c_double * 3
+    i0, d0 = (C.c_int * 8)(*s.phii), (C.c_double * 8)(*s.delta_phi)
+    return lib.gen_params_base_py(
+        C.c_double(s.mass1), C.c_double(s.mass2), d3(*s.spin1), d3(*s.spin2), C.c_double(s.Luminosity_Distance),
+        C.c_double(s.incl_angle), C.c_double(s.RA), C.c_double(s.DEC), C.c_double(s.psi), C.c_double(s.gmst), C.c_double(s.tc),
+        C.c_double(s.phiRef), C.c_double(s.f_ref), C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), b"PLANCK15",
+        C.c_bool(False), C.c_bool(False), C.c_bool(False), C.c_bool(False), C.c_bool(False), C.c_bool(bool(s.shift_time)),
+        C.c_bool(bool(s.shift_phase)), C.c_bool(False), C.c_double(0), C.c_double(0), C.c_int(s.Nmod_phi), C.c_int(s.Nmod_sigma),
+        C.c_int(s.Nmod_beta), C.c_int(s.Nmod_alpha), i0, (C.c_int * 8)(*s.sigmai), (C.c_int * 8)(*s.betai),
+        (C.c_int * 8)(*s.alphai), d0, (C.c_double * 8)(*s.delta_sigma), (C.c_double * 8)(*s.delta_beta),
+        (C.c_double * 8)(*s.delta_alpha), C.c_int(s.Nmod), (C.c_double * 8)(*s.bppe), (C.c_double * 8)(*s.betappe))
+
+
+def test_exports_the_on_path_gwatpy_symbols():
+    lib = C.CDLL(LIB)
+    for name in ON_PATH_SYMBOLS:
+        assert hasattr(lib, name), name
+
+
+def test_symbol_names_exist_in_reference_header_when_available():
+    hdr = "/root/reference/include/gwat/gwatpy_wrapping.h"
+    if not os.path.exists(hdr):
+        pytest.skip("reference not mounted")
+    text = open(hdr).read()
+    for name in ON_PATH_SYMBOLS:
+        if name == "MCMC_likelihood_extrinsic_batch_py":
+            continue  # the one new entry point
+        assert name + "(" in text.replace(" (", "("), name
+
+
+def test_host_side_mass_helpers_match_definitions():
+    lib = C.CDLL(LIB)
+    out = C.c_double()
+    lib.calculate_chirpmass_py(C.c_double(36.0), C.c_double(29.0), C.byref(out))
+    assert abs(out.value - (36.0 * 29.0) ** 0.6 / 65.0 ** 0.2) < 1e-13
+    mc = out.value
+    lib.calculate_eta_py(C.c_double(36.0), C.c_double(29.0), C.byref(out))
+    eta = out.value
+    lib.calculate_mass1_py(C.c_double(mc), C.c_double(eta), C.byref(out))
+    assert abs(out.value - 36.0) < 1e-11
+
+
+@pytest.mark.gpu
+def test_gwatpy_calls_match_golden():
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "waveforms_v1.npz"))
+    lib = _lib()
+    for name, method, kw, gspec in [c for c in cases.CASES if c[0] in ("D_bbh", "P_full", "ppE_ins", "gIMR")]:
+        f = cases.grid(gspec)
+        L = f.size
+        gp = _gen_params(lib, kw)
+        o = [np.zeros(L) for _ in range(4)]
+        assert lib.fourier_waveform_py(_p(f), L, *[_p(x) for x in o], method.encode(), C.c_void_p(gp)) == 1
+        assert np.abs(o[0] + 1j * o[1] - gold[name + "/hp"]).max() <= 1e-10 * np.abs(gold[name + "/hp"]).max()
+        assert np.abs(o[2] + 1j * o[3] - gold[name + "/hc"]).max() <= 1e-10 * np.abs(gold[name + "/hc"]).max()
+        if name + "/single_L" in gold:
+            re, im = np.zeros(L), np.zeros(L)
+            assert lib.fourier_detector_response_py(_p(f), L, _p(re), _p(im), b"Livingston", method.encode(), C.c_void_p(gp)) == 1
+            assert np.abs(re + 1j * im - gold[name + "/single_L"]).max() <= 1e-10 * np.abs(gold[name + "/single_L"]).max()
+        lib.gen_params_base_py_destructor(C.c_void_p(gp))
+    d = lib.DTOA_DETECTOR_py(C.c_double(.275), C.c_double(-.44), C.c_double(2.1), b"Hanford", b"Livingston")
+    assert 0 < abs(d) < 0.011
+
+
+@pytest.mark.gpu
+def test_gwatpy_likelihood_v2_and_batch(oracle):
+    wl = workloads.make(1, W=12, L=2048)
+    lib = _lib()
+    # gmst = 0: the reference's pyv2 wrapper never sets mcmc_gmst in its translation unit
+    _, src = oracle.loglike_mcmc_batch(wl.method, wl.mod, wl.inj[None, :], 0.0, wl.T_segment, wl.detectors, wl.f, wl.psd, None,
+                                       return_sources=True)
+    data = oracle.coherent_response(wl.method, src[0], wl.detectors, wl.f)
+    ref = oracle.loglike_mcmc_batch(wl.method, wl.mod, wl.params, 0.0, wl.T_segment, wl.detectors, wl.f, wl.psd, data)
+    D, L = wl.D, wl.L
+    lengths = (C.c_int * D)(*([L] * D))
+    ff = np.tile(wl.f, D)
+    dre, dim = np.ascontiguousarray(data.real).ravel(), np.ascontiguousarray(data.imag).ravel()
+    psd = wl.psd.ravel().copy()
+    wts = np.ones(D * L)
+    mod = lib.MCMC_modification_struct_py(0, None, 0, None, 0, None, 0, None, 0, None, C.c_bool(False), C.c_bool(False))
+    one = lib.MCMC_likelihood_extrinsic_pyv2(C.c_bool(False), _p(wl.params[3].copy()), C.c_void_p(mod), wl.P, wl.method.encode(),
+                                             lengths, _p(ff), _p(dre), _p(dim), _p(psd), _p(wts), b"SIMPSONS", C.c_bool(False),
+                                             b"HL", D)
+    assert abs(one - ref[3]) <= 1e-9 * abs(ref[3])
+    out = np.zeros(wl.W)
+    rc = lib.MCMC_likelihood_extrinsic_batch_py(_p(wl.params), wl.W, C.c_void_p(mod), wl.P, wl.method.encode(), lengths, _p(ff),
+                                                _p(dre), _p(dim), _p(psd), _p(wts), b"SIMPSONS", C.c_bool(False), b"HL", D,
+                                                C.c_double(0.0), C.c_double(wl.T_segment), _p(out))
+    assert rc == 0
+    assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-9
+    lib.MCMC_modification_struct_py_destructor(C.c_void_p(mod))
