@@ -32,7 +32,7 @@ namespace hosttab {  // the same generated tables for host-side use (detector ro
 #undef GWAT_TABLE_QUALIFIER
 }  // namespace hosttab
 
-#include "gwat_bins.h"
+#include "gwat_like.h"
 #include "gwat_grid.h"
 #include "gwat_method.h"
 #include "gwat_repack.h"
@@ -42,6 +42,13 @@ using namespace gwat;
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef GWAT_LOGLIKE_MIN_CTAS
+#define GWAT_LOGLIKE_MIN_CTAS 3
+#endif
+#ifndef GWAT_LOGLIKE_THREADS
+#define GWAT_LOGLIKE_THREADS 256
+#endif
+constexpr int kLikeThreads = GWAT_LOGLIKE_THREADS;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -52,11 +59,7 @@ __device__ __forceinline__ Tables device_tables()
 	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS}};
 }
 
-struct GridPtrs {
-	const double *f, *sf_hi, *sf_lo, *logf;
-	const double *wq, *dre, *dim;  // [D][L]
-	int L;
-};
+typedef LikeGrid GridPtrs;
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -66,8 +69,10 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Block-wide sum of two values; result valid in thread 0.
+template <int NT = kThreads>
 __device__ __forceinline__ void block_sum2(double &a, double &b)
 {
+	constexpr int kThreads = NT;
 	__shared__ double sa[kThreads / 32], sb[kThreads / 32];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	a = warp_sum(a);
@@ -147,7 +152,7 @@ __device__ __forceinline__ void load_walker(const WalkerCoef *__restrict__ src, 
 }
 
 template <class Fam, int D>
-__global__ void __launch_bounds__(kThreads) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int bins_per_cta,
+__global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int bins_per_cta,
                                                      double *__restrict__ partial)
 {
 	__shared__ WalkerCoef w;
@@ -155,24 +160,8 @@ __global__ void __launch_bounds__(kThreads) k_loglike(const WalkerCoef *__restri
 	const int begin = blockIdx.x * bins_per_cta;
 	const int end = min(g.L, begin + bins_per_cta);
 	double acc = 0.0, nact = 0.0;
-	if (w.valid) {
-		for (int i = begin + threadIdx.x; i < end; i += kThreads) {
-			const double f = g.f[i];
-			if (f > w.d.fcut) continue;  // the model is exactly zero there: no contribution to either inner product
-			cplx hp, hc;
-			polarizations_bin<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
-			nact += 1.0;
-#pragma unroll
-			for (int d = 0; d < D; d++) {
-				const cplx r = project_bin(w.det[d], hp, hc, f, true);
-				const size_t k = (size_t)d * g.L + i;
-				const double hh = r.re * r.re + r.im * r.im;
-				const double dh = g.dre[k] * r.re + g.dim[k] * r.im;
-				acc += g.wq[k] * (hh - 2.0 * dh);
-			}
-		}
-	}
-	block_sum2(acc, nact);
+	if (w.valid) loglike_run<Fam, D>(w, g, begin + threadIdx.x, end, kLikeThreads, acc, nact);
+	block_sum2<kLikeThreads>(acc, nact);
 	if (threadIdx.x == 0) {
 		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
 		p[0] = w.valid ? acc : NAN;
@@ -405,7 +394,8 @@ struct gwat_b200_ctx {
 	std::mutex mu;
 	// network
 	int D = 0, L = 0;
-	bool have_data = false, gaussleg = false, log10F = false;
+	bool have_data = false, gaussleg = false, log10F = false, uniform = false;
+	double df = 0;
 	Network net{};
 	double pref_like = 0, pref_fisher = 0;
 	double *d_grid = nullptr;  // f, sf_hi, sf_lo, logf : 4*L
@@ -470,6 +460,8 @@ GridPtrs grid_ptrs(const gwat_b200_ctx *c)
 	g.dre = c->d_net + DL;
 	g.dim = c->d_net + 2 * DL;
 	g.L = c->L;
+	g.uniform = c->uniform ? 1 : 0;
+	g.df = c->df;
 	return g;
 }
 
@@ -525,11 +517,11 @@ int launch_loglike(gwat_b200_ctx *ctx, int W, int chunks, int bins_per_cta, cuda
 	const GridPtrs g = grid_ptrs(ctx);
 	const dim3 grid(chunks, W);
 	switch (ctx->D) {
-	case 1: k_loglike<Fam, 1><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 2: k_loglike<Fam, 2><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 3: k_loglike<Fam, 3><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 4: k_loglike<Fam, 4><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 5: k_loglike<Fam, 5><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 1: k_loglike<Fam, 1><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 2: k_loglike<Fam, 2><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 3: k_loglike<Fam, 3><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 4: k_loglike<Fam, 4><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 5: k_loglike<Fam, 5><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
 	default: return -1;
 	}
 	return 0;
@@ -540,13 +532,13 @@ void choose_chunks(int W, int L, int &chunks, int &bins_per_cta)
 {
 	const long long target_ctas = 148LL * 8;
 	long long want = (target_ctas + W - 1) / W;
-	long long max_chunks = (L + kThreads - 1) / kThreads;
+	long long max_chunks = (L + kLikeThreads - 1) / kLikeThreads;
 	if (want < 1) want = 1;
 	if (want > max_chunks) want = max_chunks;
 	long long per = (L + want - 1) / want;
-	per = ((per + kThreads - 1) / kThreads) * kThreads;
+	per = ((per + kLikeThreads - 1) / kLikeThreads) * kLikeThreads;
 	// keep the per-thread trip count bounded so the tail CTA of a long grid does not dominate
-	const long long cap = 64LL * kThreads;
+	const long long cap = 64LL * kLikeThreads;
 	if (per > cap) per = cap;
 	bins_per_cta = (int)per;
 	chunks = (int)((L + per - 1) / per);
@@ -736,6 +728,14 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 	ctx->pref_like = quadrature_prefactor(L, gl, f, false);
 	ctx->pref_fisher = quadrature_prefactor(L, false, f, true);
 	ctx->h_f.assign(f, f + L);
+	// uniform grid?  (then the per-detector arrival-time phase advances by a constant rotation per bin, gwat_like.h)
+	{
+		const double df = (f[L - 1] - f[0]) / (L - 1);
+		bool uni = df > 0;
+		for (int i = 0; i < L && uni; i++) uni = std::fabs(f[i] - (f[0] + i * df)) <= 1e-9 * df;
+		ctx->uniform = uni;
+		ctx->df = df;
+	}
 	return GWAT_B200_OK;
 }
 

@@ -138,6 +138,38 @@ GWAT_HD dd pow_sixth_dd(double x)
 	return dd_add(y, t);
 }
 
+// Reciprocal / reciprocal square root to ~1 ulp without the IEEE-exact routines' special-case paths.  Used for amplitudes
+// and for phase terms of O(1..100) rad, where one ulp is < 1e-14 rad; the leading TaylorF2 term keeps the exact division.
+GWAT_HD double fast_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	// the hardware seed is good to 2^-23; each Newton step squares the error
+	double e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	return r;
+#else
+	return 1.0 / x;
+#endif
+}
+GWAT_HD double fast_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	const double h = 0.5 * x;
+	r = r * fma(-h * r, r, 1.5);
+	r = r * fma(-h * r, r, 1.5);
+	return r;
+#else
+	return 1.0 / sqrt(x);
+#endif
+}
+GWAT_HD double fast_sqrt(double x) { return x * fast_rsqrt(x); }
+
 GWAT_HD double sq(double x) { return x * x; }
 GWAT_HD double cube(double x) { return x * x * x; }
 

@@ -1,0 +1,198 @@
+// Fused per-bin likelihood terms (GWAT_HD code): what k_loglike runs in its inner loop.
+//
+// The reference forms, per walker and per detector, three length-L complex arrays and two length-L real integrands
+// (src/waveform_generator.cpp:188-199,257-266; src/waveform_util.cpp:865-873,177-179; src/mcmc_gw.cpp:814-857) and sums them.
+// Here one bin's contribution to   sum_d  w_d (|r_d|^2 - 2 Re(data_d conj(r_d)))   is formed in registers:
+//   r_d      = A e^{-i phi} (ga_d P + gb_d Q) e^{+i t_d f}           t_d = -2 pi DTOA_d
+//   |r_d|^2  = A^2 |ga_d P + gb_d Q|^2                                (no trigonometry)
+//   Re(data_d conj r_d) = A Re( e^{+i phi} conj(ga_d P + gb_d Q) [data_d e^{-i t_d f}] )
+// so the only transcendental per bin is ONE sincos of the carrier phase (plus one of alpha for IMRPhenomPv2), instead of
+// 1 + D (2 + D for Pv2) complex exponentials.  On a uniform grid e^{-i t_d f} advances by a constant rotation per step of
+// the thread's stride; the state is re-seeded with a full-precision sincos at the start of every thread's run, so the
+// accumulated rounding stays below 1e-14 (runs are <= 64 steps).  Non-uniform (Gauss-Legendre) grids evaluate it directly.
+// All of this is algebra on the reference's formulas: results agree to rounding (tests: logL <= 1e-9 relative).
+#ifndef GWAT_LIKE_H
+#define GWAT_LIKE_H
+
+#include "gwat_bins.h"
+
+namespace gwat {
+
+GWAT_HD int min_int(int a, int b) { return a < b ? a : b; }
+
+struct LikeGrid {
+	const double *f, *sf_hi, *sf_lo, *logf;
+	const double *wq, *dre, *dim;  // [D][L]
+	int L;
+	int uniform;   // f[i] = f[0] + i*df to rounding
+	double df;
+};
+
+// Carrier amplitude (including the walker's overall scale) and phase argument of e^{-i phi} at one active bin, and for
+// IMRPhenomPv2 the twist factors P, Q.  Returns false when the bin contributes nothing.
+// `mr_decay`: when > 0 it is exp(-mr_rate (f - fRD)) supplied by the caller (advanced by a constant factor per step on a
+// uniform grid) and saves the exponential of the merger-ringdown amplitude.
+template <class Fam>
+GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, double mr_decay, double &amp,
+                           double &arg, cplx &P, cplx &Q)
+{
+	const DCoef &c = w.d;
+	if (f > c.fcut) return false;
+	if (Fam::nrt && f > c.nrt_fmerger12) return false;
+	const double sixth = bin_sixth_root(c, sf_hi, sf_lo);
+	MfPowers p;
+	const bool full = f < c.f1p || f < c.f1a || Fam::base == BASE_P || Fam::nrt;
+	if (full) {
+		// mf_powers with the quotient shared: 1/(Mf)^(7/6) = (Mf)^(1/2) / (Mf)^(5/3) -- amplitude side only
+		mf_powers(c.M, f, sixth, p);
+	} else {
+		p.Mf = mul_rn(c.M, f);
+		p.sixth = sixth;
+		p.seven6 = mul_rn(mul_rn(sixth, c.M), f);
+	}
+	double shape;
+	if (f < c.f1a) shape = phenomd_amp_ins(c, p);
+	else if (f > c.f3a) {
+		const double df = f - c.fRD;
+		shape = mr_decay > 0 ? c.mr_num * mr_decay * fast_rcp(df * df + c.mr_w2) : phenomd_amp_mr(c, f);
+	} else shape = phenomd_amp_int(c, p.Mf);
+	const double inv76 = full ? (p.m53 * (p.third * p.sixth)) : fast_rcp(p.seven6);
+	double phase;
+	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, p, logf);
+	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
+	else phase = phenomd_phase_int<Fam>(c, f, logf);
+
+	if (Fam::base == BASE_D) {
+		amp = c.A0 * (shape * inv76);
+		if (Fam::nrt) {
+			nrt_bin(c, f, p, logf, amp, phase);
+			amp *= nrt_taper_factor(c, f);
+		}
+		arg = phenomd_apply_time_phase(c, f, phase);
+		P = cplx{1.0, 0.0};
+		Q = cplx{0.0, -1.0};
+		return true;
+	}
+	// ---- IMRPhenomPv2 twist-up ----------------------------------------------------------------------------------------
+	const PCoef &pc = w.p;
+	amp = (pc.A0 * (shape * inv76)) * 0.5;
+	const PiPowers pi = pi_powers();
+	const double oc = p.third * pi.third;  // omega^(1/3)
+	const double x = p.two3 * pi.two3;     // omega^(2/3); sqrt(x) = oc up to rounding
+	const double roc = fast_rcp(oc);
+	const double x2 = x * x, eta = pc.eta;
+	const double Lorb = (eta * (1.0 + pc.lc1 * x + pc.lc2 * x2)) * roc;
+	const double sb = pc.SP * fast_rcp(Lorb + pc.SL);  // tan(beta)
+	const double cb = fast_rsqrt(1.0 + sb * sb);       // cos(beta)
+	const double sinb = fabs(sb) * cb;                  // 2 cos(beta/2) sin(beta/2) with the reference's positive half-angle roots
+	const double c2h = 0.5 * (1.0 + cb), s2h = 0.5 * (1.0 - cb);  // cos^2(beta/2), sin^2(beta/2)
+	// Wigner d^2_{m,2}: a_m, m = -2..2  (= s^4, 2 c s^3, sqrt6 s^2 c^2, 2 c^3 s, c^4 in half-angle terms)
+	const double a0 = s2h * s2h, a1 = sinb * s2h, a2 = 2.44948974278317788 * (s2h * c2h), a3 = sinb * c2h, a4 = c2h * c2h;
+	const double roc2 = roc * roc, roc3 = roc2 * roc;
+	const double logom = add_rn(c.logpiM, logf);
+	const double alpha = ((((pc.acoef[0] * roc3 + pc.acoef[1] * roc2) + pc.acoef[2] * roc) + pc.acoef[3] * logom) + pc.acoef[4] * oc) +
+	                     pc.alpha_const;
+	const double epsilon = ((((pc.ecoef[0] * roc3 + pc.ecoef[1] * roc2) + pc.ecoef[2] * roc) + pc.ecoef[3] * logom) + pc.ecoef[4] * oc) -
+	                       pc.epsilon_offset;
+	double s1, c1;
+	sincos(alpha, &s1, &c1);
+	const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;
+	// sum_m Y_m (d^2_{-m} e^{-i m alpha} +- d^2_m e^{+i m alpha}) with real Y_m, grouped by |m|
+	const double *Y = pc.Y;  // m = -2..2
+	const double Pm2 = a4 + a0, Pm1 = a1 - a3, P0 = 2.0 * a2, Pp1 = a3 - a1, Pp2 = a0 + a4;
+	const double Nm2 = a0 - a4, Nm1 = a1 + a3, Np1 = a3 + a1, Np2 = a4 - a0;
+	const double A1 = Y[3] * Pp1 + Y[1] * Pm1, A2 = Y[4] * Pp2 + Y[0] * Pm2;   // cos coefficients of Re(P)
+	const double B1 = Y[3] * Np1 - Y[1] * Nm1, B2 = Y[4] * Np2 - Y[0] * Nm2;   // sin coefficients of Im(P)
+	const double C1 = Y[3] * Pp1 - Y[1] * Pm1, C2 = Y[4] * Pp2 - Y[0] * Pm2;   // sin coefficients of Re(Q)
+	const double D1 = Y[3] * Np1 + Y[1] * Nm1, D2 = Y[4] * Np2 + Y[0] * Nm2;   // cos coefficients of -Im(Q)
+	P = cplx{Y[2] * P0 + c1 * A1 + c2 * A2, s1 * B1 + s2 * B2};
+	Q = cplx{s1 * C1 + s2 * C2, -(c1 * D1 + c2 * D2)};
+	phase = add_rn(phase, mul_rn(2., epsilon));
+	double a = sub_rn(phase, mul_rn(pc.tc, sub_rn(f, pc.f_ref)));
+	a = sub_rn(a, pc.phic);
+	arg = add_rn(a, mul_rn(pc.tcorr_2pi, f));
+	return true;
+}
+
+// One thread's run of bins: first, first+stride, ... < end.  Accumulates sum_d w_d (|r_d|^2 - 2 Re(d conj r_d)) into acc
+// and the number of active bins into nact.
+template <class Fam, int D>
+GWAT_HD void loglike_run(const WalkerCoef &w, const LikeGrid &g, int first, int end, int stride, double &acc, double &nact)
+{
+	if (first >= end) return;
+	// rotation state z_d = e^{-i t_d f} and its per-step multiplier
+	cplx z[D], E[D];
+	double decay = 0.0, decay_step = 1.0;  // exp(-mr_rate (f - fRD)) and its per-step factor (uniform grids)
+	if (g.uniform) {
+		const double f0 = g.f[first];
+		if (f0 > w.d.fcut) return;  // ascending grid: nothing below the cutoff is left for this thread
+		const double step = g.df * stride;
+		// kept within [1e-280, 1e280]: outside, fall back to evaluating the exponential per bin
+		const double a0 = -w.d.mr_rate * (f0 - w.d.fRD), a1 = -w.d.mr_rate * (g.f[min_int(end - 1, g.L - 1)] - w.d.fRD);
+		if (fabs(a0) < 600.0 && fabs(a1) < 600.0) {
+			decay = exp(a0);
+			decay_step = exp(-w.d.mr_rate * step);
+		}
+#pragma unroll
+		for (int d = 0; d < D; d++) {
+			double sn, cs;
+			sincos(mul_rn(w.det[d].tshift, f0), &sn, &cs);
+			z[d] = cplx{cs, -sn};
+			sincos(mul_rn(w.det[d].tshift, step), &sn, &cs);
+			E[d] = cplx{cs, -sn};
+		}
+	}
+	for (int i = first; i < end; i += stride) {
+#if defined(__CUDA_ARCH__)
+		// The walker's ~150 coefficients live in shared memory.  Without this barrier the compiler hoists all of them into
+		// registers as loop invariants (250+ registers, 1 CTA/SM); with it they are re-read (broadcast LDS) where used.
+		asm volatile("" ::: "memory");
+#endif
+		const double f = g.f[i];
+		double amp, arg;
+		cplx P, Q;
+		const bool active = carrier_terms<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], decay, amp, arg, P, Q);
+		decay *= decay_step;
+		if (!active) {
+			if (g.uniform && (f > w.d.fcut || (Fam::nrt && f > w.d.nrt_fmerger12))) break;  // ascending grid: the rest is zero too
+			if (g.uniform) {
+#pragma unroll
+				for (int d = 0; d < D; d++) z[d] = cplx{z[d].re * E[d].re - z[d].im * E[d].im, z[d].re * E[d].im + z[d].im * E[d].re};
+			}
+			continue;
+		}
+		nact += 1.0;
+		double sn, cs;
+		sincos(arg, &sn, &cs);
+		double hh = 0.0, Sre = 0.0, Sim = 0.0;
+#pragma unroll
+		for (int d = 0; d < D; d++) {
+			const DetCoef &dc = w.det[d];
+			const size_t k = (size_t)d * g.L + i;
+			const double wq = g.wq[k];
+			// G = ga P + gb Q
+			const double Gre = dc.ga * P.re + dc.gb * Q.re, Gim = dc.ga * P.im + dc.gb * Q.im;
+			hh += wq * (Gre * Gre + Gim * Gim);
+			cplx zd;
+			if (g.uniform) {
+				zd = z[d];
+				z[d] = cplx{zd.re * E[d].re - zd.im * E[d].im, zd.re * E[d].im + zd.im * E[d].re};
+			} else {
+				double s_, c_;
+				sincos(mul_rn(dc.tshift, f), &s_, &c_);
+				zd = cplx{c_, -s_};
+			}
+			// t = data * z ;  S += w * conj(G) * t
+			const double dr = g.dre[k], di = g.dim[k];
+			const double tre = dr * zd.re - di * zd.im, tim = dr * zd.im + di * zd.re;
+			Sre += wq * (Gre * tre + Gim * tim);
+			Sim += wq * (Gre * tim - Gim * tre);
+		}
+		// Re(e^{+i arg} S) = cos(arg) Sre - sin(arg) Sim
+		const double dh = amp * (cs * Sre - sn * Sim);
+		acc += (amp * amp) * hh - 2.0 * dh;
+	}
+}
+
+}  // namespace gwat
+#endif

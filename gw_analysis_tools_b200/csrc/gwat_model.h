@@ -81,7 +81,7 @@ struct DCoef {
 	double ains[7];  // TaylorF2 amplitude coefficients times pi^(k/3)
 	double rho[3];
 	double ic[5], ix1, ix2, ix3;  // intermediate amplitude: Newton form on nodes [x1,x1,x2,x3,x3] in x = M f
-	double mr_num, mr_rate, mr_w2, fRD, fdamp;
+	double mr_num, mr_rate, mr_w2, fRD, fdamp, inv_fdamp;
 	// inspiral phase
 	double k1, k2, k3, k4, k7;  // static TaylorF2 phase coefficients times pi^(k/3) (k3 also times M)
 	double c8, c9, c10, c11;    // log-dependent 2.5PN / 3PN pieces
@@ -114,12 +114,18 @@ struct cplx {
 struct DetCoef {
 	double Fplus, Fcross;  // antenna patterns (detector_response_functions_equatorial, src/detector_util.cpp:900)
 	double tshift;         // -2 pi * DTOA: the response is multiplied by exp(i * tshift * f) (src/waveform_util.cpp:173-178)
+	// fused-likelihood constants (gwat_like.h): the response is  carrier * (ga * P + gb * Q)  with walker constants
+	//   IMRPhenomD families: P = 1, Q = -i      ga = F+ (1+cos^2 i)/2,  gb = Fx cos i
+	//   IMRPhenomPv2:        P = h+ twist factor, Q = hx twist factor (before the 2 zeta rotation)
+	//                        ga = F+ cos 2z - Fx sin 2z,  gb = F+ sin 2z + Fx cos 2z
+	double ga, gb;
 };
 
 // PhenomPv2 twist-up constants of one walker.
 struct PCoef {
 	double A0;  // rescaled amplitude (src/IMRPhenomP.cpp:258)
 	double SP, SL, eta;
+	double lc1, lc2;  // L2PN series coefficients 1.5 + eta/6, 3.375 - 19 eta/8 - eta^2/24
 	double acoef[5], ecoef[5];
 	double alpha_const;    // alpha0 - alpha_offset
 	double epsilon_offset;

@@ -267,7 +267,7 @@ GWAT_HD double phenomd_phase_int(const DCoef &c, double f, double logf)
 	const double lg = add_rn(c.logM, logf);
 	double t = add_rn(c.beta0, mul_rn(c.beta1, Mf));
 	t = add_rn(t, mul_rn(c.beta2, lg));
-	t = sub_rn(t, c.beta3_3 / Mf3);
+	t = sub_rn(t, mul_rn(c.beta3_3, fast_rcp(Mf3)));
 	double ph = mul_rn(c.inv_eta, t);
 	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, f, ph);
 	return ph;
@@ -275,15 +275,16 @@ GWAT_HD double phenomd_phase_int(const DCoef &c, double f, double logf)
 
 // Merger-ringdown phase (reference: phase_mr, src/IMRPhenomD.cpp:1485-1503).
 template <class Fam>
-GWAT_HD double phenomd_phase_mr(const DCoef &c, double f)
+GWAT_HD double phenomd_phase_mr(const DCoef &c, double f, double sixth)
 {
 	const double Mf = mul_rn(c.M, f);
-	const double Mfcube = mul_rn(mul_rn(Mf, Mf), Mf);
-	const double Mf34 = sqrt(sqrt(Mfcube));
+	// (M f)^(3/4) = s^4 sqrt(s) with s = (M f)^(1/6): one square root instead of the reference's sqrt(sqrt((Mf)^3))
+	const double s2 = sixth * sixth;
+	const double Mf34 = (s2 * s2) * fast_sqrt(sixth);
 	double t = add_rn(c.alpha0, mul_rn(c.alpha1, Mf));
-	t = sub_rn(t, mul_rn(c.alpha2, 1. / Mf));
+	t = sub_rn(t, mul_rn(c.alpha2, fast_rcp(Mf)));
 	t = add_rn(t, mul_rn(c.alpha3_43, Mf34));
-	t = add_rn(t, mul_rn(c.alpha4, atan(sub_rn(f, c.alpha5fRD) / c.fdamp)));
+	t = add_rn(t, mul_rn(c.alpha4, atan(mul_rn(sub_rn(f, c.alpha5fRD), c.inv_fdamp))));
 	double ph = mul_rn(c.inv_eta, t);
 	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, f, ph);
 	return ph;
@@ -303,7 +304,7 @@ GWAT_HD double phenomd_amp_int(const DCoef &c, double Mf)
 GWAT_HD double phenomd_amp_mr(const DCoef &c, double f)
 {
 	const double df = f - c.fRD;
-	return c.mr_num * exp(-c.mr_rate * df) / (df * df + c.mr_w2);
+	return c.mr_num * exp(-c.mr_rate * df) * fast_rcp(df * df + c.mr_w2);
 }
 
 // Amplitude (scaled by A0 M^{7/6}) and phase of the carrier at one bin with f <= fcut.
@@ -326,7 +327,7 @@ GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, do
 	amp = c.A0 * (shape / p.seven6);
 
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, p, logf);
-	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f);
+	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
 	else phase = phenomd_phase_int<Fam>(c, f, logf);
 }
 

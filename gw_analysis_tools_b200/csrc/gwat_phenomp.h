@@ -238,6 +238,8 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 	p.SP = s.SP;
 	p.SL = s.SL;
 	p.eta = s.eta;
+	p.lc1 = 1.5 + s.eta / 6.0;
+	p.lc2 = 3.375 - (19.0 * s.eta) / 8. - (s.eta * s.eta) / 24.0;
 	const double q = s.mass1 / s.mass2;
 	euler_angle_coeffs(q, s.chil, s.chip, p.acoef, p.ecoef);
 	// offsets of the angles at f_ref; the reference forms (M f_ref)^(1/3) with pow(x, 1./3.)
@@ -299,7 +301,7 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 	const double amp = (p.A0 * (shape / mp.seven6)) / 2.;
 	double phase;
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, mp, logf);
-	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f);
+	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
 	else phase = phenomd_phase_int<Fam>(c, f, logf);
 
 	// Wigner d^2_{m,+-2}(beta): tan(beta) = S_perp / (L + S_parallel)
@@ -384,6 +386,16 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 		w.pfac = .5 * (1. + ci * ci);
 	}
 	detector_setup(net, src.RA, src.DEC, src.psi, src.gmst, w.det);
+	for (int d = 0; d < net.D; d++) {
+		DetCoef &dc = w.det[d];
+		if (Fam::base == BASE_P) {
+			dc.ga = dc.Fplus * w.p.c2z - dc.Fcross * w.p.s2z;
+			dc.gb = dc.Fplus * w.p.s2z + dc.Fcross * w.p.c2z;
+		} else {
+			dc.ga = dc.Fplus * w.pfac;
+			dc.gb = dc.Fcross * w.cfac;
+		}
+	}
 	// options of the reference that are outside this path are refused loudly (NaN), never silently approximated:
 	// horizon/equatorial-orientation inputs, sky-averaged amplitudes, and the wall-clock-seeded tidal_love_error draw
 	if (src.horizon_coord || src.equatorial_orientation || src.sky_average || (Fam::nrt && src.tidal_love_error)) w.d.A0 = NAN;

@@ -173,6 +173,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.pichirp = GWAT_PI * s.chirpmass;
 	c.fRD = s.fRD;
 	c.fdamp = s.fdamp;
+	c.inv_fdamp = 1. / s.fdamp;
 	c.inv_eta = 1. / eta;
 
 	// ---- amplitude -----------------------------------------------------------------------------------------------------
@@ -311,7 +312,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	sync_int_mr();
 	{
 		const double intv = phenomd_phase_int<Fam>(c, f2p, log_f2p);
-		const double mr = phenomd_phase_mr<Fam>(c, f2p);
+		const double mr = phenomd_phase_mr<Fam>(c, f2p, sixth_root_direct(M, f2p));
 		lam.alpha[0] = eta * intv - eta * mr;
 	}
 	sync_int_mr();

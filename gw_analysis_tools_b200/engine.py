@@ -11,7 +11,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgwat_b200.so")
+LIB_PATH = os.environ.get("GWAT_B200_LIB") or os.path.join(_HERE, "libgwat_b200.so")  # env override: kernel experiments only
 
 _dp = C.POINTER(C.c_double)
 _lib = None

@@ -1,13 +1,15 @@
 // TEST INFRASTRUCTURE ONLY.  Compiles the kernels' GWAT_HD mathematics (gw_analysis_tools_b200/csrc/*.h) as plain C++ so
 // the CPU-only test tier (`pytest -m "not gpu"`) can check the per-walker setup and the per-bin code against the oracle
 // without a GPU.  This file is NOT part of the product: the C ABI (libgwat_b200.so) has no CPU path and never links this.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #define GWAT_TABLE_QUALIFIER static const
 #include "../gw_analysis_tools_b200/csrc/gwat_tables.inc"
-#include "../gw_analysis_tools_b200/csrc/gwat_bins.h"
+#include "../gw_analysis_tools_b200/csrc/gwat_like.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_grid.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_method.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_repack.h"
@@ -75,19 +77,19 @@ int make_network(int D, const char *const *dets, Network &net)
 
 }  // namespace
 
-#define DISPATCH_FAMILY(desc, CALL)                                                                     \
+#define DISPATCH_FAMILY(desc, ...)                                                                      \
 	switch (desc.family_id) {                                                                             \
-	case FAM_D: { typedef Family<BASE_D, PPE_NONE, false, false> Fam; CALL; break; }                      \
-	case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; CALL; break; }          \
-	case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; CALL; break; }               \
-	case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; CALL; break; }                  \
-	case FAM_D_NRT: { typedef Family<BASE_D, PPE_NONE, false, true> Fam; CALL; break; }                   \
-	case FAM_D_NRT_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, true> Fam; CALL; break; }       \
-	case FAM_D_NRT_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, true> Fam; CALL; break; }            \
-	case FAM_P: { typedef Family<BASE_P, PPE_NONE, false, false> Fam; CALL; break; }                      \
-	case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; CALL; break; }          \
-	case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; CALL; break; }               \
-	case FAM_P_GIMR: { typedef Family<BASE_P, PPE_NONE, true, false> Fam; CALL; break; }                  \
+	case FAM_D: { typedef Family<BASE_D, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                      \
+	case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }          \
+	case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }               \
+	case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                  \
+	case FAM_D_NRT: { typedef Family<BASE_D, PPE_NONE, false, true> Fam; __VA_ARGS__; break; }                   \
+	case FAM_D_NRT_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, true> Fam; __VA_ARGS__; break; }       \
+	case FAM_D_NRT_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, true> Fam; __VA_ARGS__; break; }            \
+	case FAM_P: { typedef Family<BASE_P, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                      \
+	case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }          \
+	case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }               \
+	case FAM_P_GIMR: { typedef Family<BASE_P, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                  \
 	default: return -2;                                                                                   \
 	}
 
@@ -234,4 +236,63 @@ extern "C" int hh_fisher_numerical(const char *method, const char *detector, con
 	int rc = 0;
 	DISPATCH_FAMILY(desc, rc = fisher_t<Fam>(desc.theory, desc.mcmc, desc, src, detector, reference, dim, order, g, psd, out));
 	return rc;
+}
+
+
+// The fused likelihood inner loop (gwat_like.h) with the kernel's exact work partition: chunks of `bins_per_cta` bins,
+// 256 "threads" striding through each chunk, partial sums combined afterwards.
+template <class Fam, int D>
+double loglike_t(int theory, const gwat_b200_source *src, const Network &net, const Grid &g, const std::vector<double> &wq,
+                 const double *dre, const double *dim, bool uniform, double df, double prefactor, int bins_per_cta)
+{
+	WalkerCoef w;
+	walker_setup<Fam>(*src, net, host_tables(), theory, w);
+	LikeGrid lg;
+	lg.f = g.f.data();
+	lg.sf_hi = g.hi.data();
+	lg.sf_lo = g.lo.data();
+	lg.logf = g.lg.data();
+	lg.wq = wq.data();
+	lg.dre = dre;
+	lg.dim = dim;
+	lg.L = (int)g.f.size();
+	lg.uniform = uniform ? 1 : 0;
+	lg.df = df;
+	double total = 0, nact = 0;
+	for (int begin = 0; begin < lg.L; begin += bins_per_cta) {
+		const int end = std::min(lg.L, begin + bins_per_cta);
+		for (int tid = 0; tid < 256; tid++) {
+			double acc = 0;
+			loglike_run<Fam, D>(w, lg, begin + tid, end, 256, acc, nact);
+			total += acc;
+		}
+	}
+	return -0.5 * (prefactor * total);
+}
+
+extern "C" int hh_loglike(const char *method, int W, const gwat_b200_source *src, int D, const char *const *dets, const double *f,
+                          int L, const double *psd, const double *dre, const double *dim, const double *weights, int gaussleg,
+                          int log10F, int bins_per_cta, double *out)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0) return -2;
+	Network net;
+	if (make_network(D, dets, net) != 0) return -1;
+	if (D != 2 && D != 3) return -3;
+	const Grid g = make_grid(f, L);
+	std::vector<double> wq((size_t)D * L);
+	for (int d = 0; d < D; d++)
+		for (int i = 0; i < L; i++) wq[(size_t)d * L + i] = quadrature_coefficient(i, L, gaussleg != 0, log10F != 0, weights, f) / psd[(size_t)d * L + i];
+	const double pref = quadrature_prefactor(L, gaussleg != 0, f, false);
+	const double df = (f[L - 1] - f[0]) / (L - 1);
+	bool uni = df > 0;
+	for (int i = 0; i < L && uni; i++) uni = std::fabs(f[i] - (f[0] + i * df)) <= 1e-9 * df;
+	for (int wi = 0; wi < W; wi++) {
+		if (D == 2) {
+			DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 2>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta));
+		} else {
+			DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 3>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta));
+		}
+	}
+	return 0;
 }

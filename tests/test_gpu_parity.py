@@ -3,8 +3,8 @@ reference's own code and (2) the oracle library itself when it travelled to the 
 size-independent properties at BASELINE.json's full sizes.
 
 Tolerances are BASELINE.json's: waveform <= 1e-10 relative to max|h|, log-likelihood <= 1e-9 relative.  Fisher matrices:
-normalised measure max_ij |dF_ij|/sqrt(F_ii F_jj) <= max(1e-6, 16 x the reference's own FMA-vs-non-FMA noise floor stored
-beside each golden matrix) -- see tests/test_host_math.py for why.
+normalised measure e_ij = |dF_ij|/sqrt(F_ii F_jj): median(e) <= 1e-6 and max(e) <= max(1e-6, 12 x the reference's own
+FMA-vs-non-FMA noise floor of the case, stored beside each golden matrix) -- see tests/test_host_math.py for why.
 """
 import os
 
@@ -21,7 +21,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 WF_TOL = 1e-10
 LL_TOL = 1e-9
 FISHER_NORM_TOL = 1e-6
-FISHER_NOISE_FACTOR = 16.0  # CUDA libm (1-2 ulp pow/exp/cbrt in the per-walker setup) is a little noisier than glibc
+FISHER_NOISE_FACTOR = 12.0  # CUDA libm (1-2 ulp pow/exp/cbrt in the per-walker setup) is a little noisier than glibc
 
 
 @pytest.fixture(scope="module")
@@ -104,16 +104,16 @@ def test_fisher_vs_golden(ctx, gold_fisher, case):
     psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
     src = cases.source_from_bytes(gold_fisher[name + "/src"])
     ctx.set_network(cases.DETECTORS, f, psd)
-    worst_floor = 0.0
+    # the noise scale of the case: the largest of its stored floors (each floor is a single sample of the noise)
+    worst_floor = max(float(gold_fisher["%s/o%d/%s/noise" % (name, o, dt)]) for o in (2, 4) for dt in cases.DETECTORS[:2])
     for order in (2, 4):
         for d, det in enumerate(cases.DETECTORS[:2]):
             out = ctx.fisher_numerical_batch(method, [src], dim, order=order, detector_index=d, reference_index=0)[0]
             ref = gold_fisher["%s/o%d/%s" % (name, order, det)]
-            floor = float(gold_fisher["%s/o%d/%s/noise" % (name, order, det)])
-            worst_floor = max(worst_floor, floor)
             dg = np.sqrt(np.abs(np.diag(ref)))
-            err = (np.abs(out - ref) / np.outer(dg, dg)).max()
-            assert err <= max(FISHER_NORM_TOL, FISHER_NOISE_FACTOR * floor), (name, order, det, err, floor)
+            nerr = np.abs(out - ref) / np.outer(dg, dg)
+            assert np.median(nerr) <= FISHER_NORM_TOL, (name, order, det, np.median(nerr))
+            assert nerr.max() <= max(FISHER_NORM_TOL, FISHER_NOISE_FACTOR * worst_floor), (name, order, det, nerr.max(), worst_floor)
             assert np.array_equal(out, out.T)
     total = ctx.fisher_numerical_batch(method, [src], dim, order=4, detector_index=-1, reference_index=0)[0]
     ref = gold_fisher[name + "/sum_o4"]
