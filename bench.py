@@ -108,10 +108,18 @@ def make_injection(ctx, wl):
     ctx.set_network(wl.detectors, wl.f, wl.psd, wl.data)
 
 
+def host_threads():
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is not it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(wl, sample, nthreads=0, repeats=1):
     """evals/s of the reference's CPU path (oracle/_ref) on `sample` walkers of the workload, all host threads."""
     from oracle import gwat_ref
-    nthreads = nthreads or gwat_ref.max_threads()
+    nthreads = nthreads or host_threads()
     p = wl.params[:sample]
     best = None
     for _ in range(repeats):
@@ -144,7 +152,7 @@ def run_reference(args):
     _, src = gwat_ref.loglike_mcmc_batch(wl.method, wl.mod, wl.inj[None, :], wl.gmst, wl.T_segment, wl.detectors, wl.f, wl.psd,
                                          None, return_sources=True)
     wl.data = gwat_ref.coherent_response(wl.method, src[0], wl.detectors, wl.f)
-    nthreads = gwat_ref.max_threads()
+    nthreads = host_threads()
     sample = min(wl.W, args.cpu_sample)
     for _ in range(args.warmup):
         cpu_reference_rate(wl, min(sample, 4 * nthreads), nthreads)

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -49,6 +50,8 @@ constexpr int kThreads = 256;
 #define GWAT_LOGLIKE_THREADS 256
 #endif
 constexpr int kLikeThreads = GWAT_LOGLIKE_THREADS;
+// one warp per CTA: the per-walker setup is a long dependent FP64 chain, so it is spread over as many SMs as possible
+constexpr int kSetupThreads = 32;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -111,7 +114,7 @@ __device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool 
 // ---------------------------------------------------------------------------------------------------------------------
 
 template <class Fam>
-__global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ params, int W, RepackPlan plan, Network net,
+__global__ void __launch_bounds__(kSetupThreads) k_setup_mcmc(const double *__restrict__ params, int W, RepackPlan plan, Network net,
                                                    int theory, double gmst, double T_segment, WalkerCoef *__restrict__ out,
                                                    gwat_b200_source *__restrict__ src_out)
 {
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(128) k_setup_mcmc(const double *__restrict__ p
 }
 
 template <class Fam>
-__global__ void __launch_bounds__(128) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net, int theory,
+__global__ void __launch_bounds__(kSetupThreads) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net, int theory,
                                                   WalkerCoef *__restrict__ out)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +164,126 @@ __global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike
 	const int end = min(g.L, begin + bins_per_cta);
 	double acc = 0.0, nact = 0.0;
 	if (w.valid) loglike_run<Fam, D>(w, g, begin + threadIdx.x, end, kLikeThreads, acc, nact);
+	block_sum2<kLikeThreads>(acc, nact);
+	if (threadIdx.x == 0) {
+		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+		p[0] = w.valid ? acc : NAN;
+		p[1] = nact;
+	}
+}
+
+// ---- bulk-copy (TMA) staging of the grid tiles ---------------------------------------------------------------------------
+// The likelihood kernel streams 4 + 3 D table values per bin that are shared by every walker.  One elected thread per CTA
+// issues `cp.async.bulk` (UBLKCP) copies of whole 256-bin tiles into a two-stage shared-memory ring and signals an
+// mbarrier; the compute threads read their bin from shared memory (conflict-free: consecutive threads, consecutive
+// doubles) instead of waiting on 13 scattered L2 round trips per bin.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_addr(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_LOOP:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra WAIT_DONE;\n"
+	    "bra WAIT_LOOP;\n"
+	    "WAIT_DONE:\n"
+	    "}\n" ::"r"(smem_addr(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
+// Table access from a staged shared-memory tile: rows 4.. of the tile are wq[D], dre[D], dim[D].
+template <int TILE, int D>
+struct TileTab {
+	const double *base;  // &tile[stage][4][thread]
+	__device__ __forceinline__ double wq(int d) const { return base[d * TILE]; }
+	__device__ __forceinline__ double dre(int d) const { return base[(D + d) * TILE]; }
+	__device__ __forceinline__ double dim(int d) const { return base[(2 * D + d) * TILE]; }
+};
+
+template <class Fam, int D>
+__global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike_tma(const WalkerCoef *__restrict__ coefs, GridPtrs g,
+                                                                                  int bins_per_cta, double *__restrict__ partial)
+{
+	constexpr int NARR = 4 + 3 * D;
+	constexpr int TILE = kLikeThreads;
+	constexpr unsigned TILE_BYTES = TILE * sizeof(double);
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double(*tile)[NARR][TILE] = reinterpret_cast<double(*)[NARR][TILE]>(smem_raw);  // [2][NARR][TILE]
+	__shared__ WalkerCoef w;
+	__shared__ __align__(8) unsigned long long bar[2];
+	if (threadIdx.x == 0) {
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	load_walker(coefs + blockIdx.y, w);  // ends with __syncthreads(): the barriers are initialised for everyone
+
+	const int begin = blockIdx.x * bins_per_cta;
+	const int end = min(g.ld, begin + bins_per_cta);
+	int ntiles = (end - begin + TILE - 1) / TILE;
+	const bool uniform = g.uniform != 0;
+	const double fmax = walker_fmax<Fam>(w);
+	if (!w.valid) ntiles = 0;
+	if (uniform && ntiles > 0) {
+		// ascending grid: tiles that start above the model's cutoff contribute exactly zero -- never fetched
+		const double f_begin = g.f[begin];
+		if (f_begin > fmax) ntiles = 0;
+		else {
+			const double span = (fmax - f_begin) / g.df;  // bins of this chunk at or below the cutoff
+			const int live = (int)fmin(span, 2.0e9) / TILE + 1;
+			ntiles = min(ntiles, live);
+		}
+	}
+	const double *src[NARR];
+	src[0] = g.f;
+	src[1] = g.sf_hi;
+	src[2] = g.sf_lo;
+	src[3] = g.logf;
+#pragma unroll
+	for (int d = 0; d < D; d++) {
+		src[4 + d] = g.wq + (size_t)d * g.ld;
+		src[4 + D + d] = g.dre + (size_t)d * g.ld;
+		src[4 + 2 * D + d] = g.dim + (size_t)d * g.ld;
+	}
+	auto issue = [&](int t) {
+		const int s_ = t & 1;
+		mbar_expect_tx(&bar[s_], NARR * TILE_BYTES);
+#pragma unroll
+		for (int a = 0; a < NARR; a++) bulk_g2s(&tile[s_][a][0], src[a] + begin + (size_t)t * TILE, TILE_BYTES, &bar[s_]);
+	};
+	if (threadIdx.x == 0) {
+		if (ntiles > 0) issue(0);
+		if (ntiles > 1) issue(1);
+	}
+	double acc = 0.0, nact = 0.0;
+	LikeState<D> st;
+	for (int t = 0; t < ntiles; t++) {
+		const int s_ = t & 1;
+		mbar_wait(&bar[s_], (t >> 1) & 1);
+		// (the asm above is also the compiler barrier that keeps the walker's coefficients in shared memory, not registers)
+		const double f = tile[s_][0][threadIdx.x];
+		if (t == 0 && uniform) like_state_init<D>(w, f, g.df * TILE, f + g.df * TILE * (ntiles - 1), st);
+		const TileTab<TILE, D> tab{&tile[s_][4][threadIdx.x]};
+		like_bin<Fam, D>(w, uniform, st, f, tile[s_][1][threadIdx.x], tile[s_][2][threadIdx.x], tile[s_][3][threadIdx.x], tab, acc, nact);
+		__syncthreads();  // everyone is done with this stage before it is refilled
+		if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
+	}
 	block_sum2<kLikeThreads>(acc, nact);
 	if (threadIdx.x == 0) {
 		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
@@ -394,7 +517,12 @@ struct gwat_b200_ctx {
 	std::mutex mu;
 	// network
 	int D = 0, L = 0;
+	int ld = 0;  // L padded to a whole number of 256-bin tiles (bulk-copy granularity of the likelihood kernel)
 	bool have_data = false, gaussleg = false, log10F = false, uniform = false;
+	// Bulk-copy (TMA) staging of the grid tiles is implemented (k_loglike_tma) but OFF by default: the tables are 2 MB and
+	// L2-resident, the kernel is FP64-bound, and the staged variant measured 10 % slower (sync + shared-memory footprint);
+	// GWAT_B200_TMA=1 selects it for A/B measurements.
+	bool use_tma = false;
 	double df = 0;
 	Network net{};
 	double pref_like = 0, pref_fisher = 0;
@@ -451,11 +579,12 @@ int grow(gwat_b200_ctx *c, T *&ptr, size_t &cap, size_t need)
 GridPtrs grid_ptrs(const gwat_b200_ctx *c)
 {
 	GridPtrs g;
-	const size_t L = c->L, DL = (size_t)c->D * c->L;
+	const size_t L = c->ld, DL = (size_t)c->D * c->ld;
 	g.f = c->d_grid;
 	g.sf_hi = c->d_grid + L;
 	g.sf_lo = c->d_grid + 2 * L;
 	g.logf = c->d_grid + 3 * L;
+	g.ld = c->ld;
 	g.wq = c->d_net;
 	g.dre = c->d_net + DL;
 	g.dim = c->d_net + 2 * DL;
@@ -511,20 +640,36 @@ int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, R
 		}                                                                                                                    \
 	} while (0)
 
+template <class Fam, int D>
+int launch_loglike_d(gwat_b200_ctx *ctx, const GridPtrs &g, dim3 grid, int bins_per_cta, cudaStream_t st)
+{
+	if (ctx->use_tma) {
+		constexpr size_t smem = (size_t)2 * (4 + 3 * D) * kLikeThreads * sizeof(double);
+		static bool configured[64] = {};
+		if (!configured[ctx->device & 63]) {
+			if (cudaFuncSetAttribute(k_loglike_tma<Fam, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+			configured[ctx->device & 63] = true;
+		}
+		k_loglike_tma<Fam, D><<<grid, kLikeThreads, smem, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial);
+	} else {
+		k_loglike<Fam, D><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial);
+	}
+	return 0;
+}
+
 template <class Fam>
 int launch_loglike(gwat_b200_ctx *ctx, int W, int chunks, int bins_per_cta, cudaStream_t st)
 {
 	const GridPtrs g = grid_ptrs(ctx);
 	const dim3 grid(chunks, W);
 	switch (ctx->D) {
-	case 1: k_loglike<Fam, 1><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 2: k_loglike<Fam, 2><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 3: k_loglike<Fam, 3><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 4: k_loglike<Fam, 4><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
-	case 5: k_loglike<Fam, 5><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial); break;
+	case 1: return launch_loglike_d<Fam, 1>(ctx, g, grid, bins_per_cta, st);
+	case 2: return launch_loglike_d<Fam, 2>(ctx, g, grid, bins_per_cta, st);
+	case 3: return launch_loglike_d<Fam, 3>(ctx, g, grid, bins_per_cta, st);
+	case 4: return launch_loglike_d<Fam, 4>(ctx, g, grid, bins_per_cta, st);
+	case 5: return launch_loglike_d<Fam, 5>(ctx, g, grid, bins_per_cta, st);
 	default: return -1;
 	}
-	return 0;
 }
 
 // How the bin axis is cut into CTAs: enough CTAs to fill 148 SMs a few times over, chunks a multiple of the block size.
@@ -584,7 +729,7 @@ int check_ready(gwat_b200_ctx *ctx, bool need_data)
 template <class Fam>
 void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st)
 {
-	k_setup_src<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_src, W, ctx->net, theory, ctx->d_coef);
+	k_setup_src<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_src, W, ctx->net, theory, ctx->d_coef);
 }
 
 int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st)
@@ -632,6 +777,7 @@ int gwat_b200_ctx_create(gwat_b200_ctx **out, int device)
 	if (device < 0 || device >= n) return fail(nullptr, GWAT_B200_ERR_ARG, "device ordinal out of range");
 	gwat_b200_ctx *c = new gwat_b200_ctx;
 	c->device = device;
+	if (const char *e = std::getenv("GWAT_B200_TMA")) c->use_tma = (e[0] == '1');
 	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&c->d_active, sizeof(unsigned long long))) != cudaSuccess) {
@@ -692,23 +838,29 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 
 	std::vector<double> hi, lo, lg;
 	build_frequency_tables(f, L, hi, lo, lg);
-	std::vector<double> grid((size_t)4 * L);
-	std::memcpy(grid.data(), f, sizeof(double) * L);
-	std::memcpy(grid.data() + L, hi.data(), sizeof(double) * L);
-	std::memcpy(grid.data() + 2 * (size_t)L, lo.data(), sizeof(double) * L);
-	std::memcpy(grid.data() + 3 * (size_t)L, lg.data(), sizeof(double) * L);
-	const size_t DL = (size_t)D * L;
+	// device layout: every table padded to `ld`, a whole number of tiles; the padding is inert (f = +inf is above every
+	// cutoff, weights and data are zero)
+	const int ld = ((L + kLikeThreads - 1) / kLikeThreads) * kLikeThreads;
+	std::vector<double> grid((size_t)4 * ld);
+	for (int i = 0; i < ld; i++) {
+		const bool in = i < L;
+		grid[i] = in ? f[i] : INFINITY;
+		grid[(size_t)ld + i] = in ? hi[i] : 1.0;
+		grid[2 * (size_t)ld + i] = in ? lo[i] : 0.0;
+		grid[3 * (size_t)ld + i] = in ? lg[i] : 0.0;
+	}
+	const size_t DL = (size_t)D * ld;
 	std::vector<double> netbuf(4 * DL, 0.0);
 	for (int d = 0; d < D; d++)
 		for (int i = 0; i < L; i++) {
-			const size_t k = (size_t)d * L + i;
-			netbuf[k] = quadrature_coefficient(i, L, gl, log10F != 0, weights, f) / psd[k];
+			const size_t k = (size_t)d * ld + i, kin = (size_t)d * L + i;
+			netbuf[k] = quadrature_coefficient(i, L, gl, log10F != 0, weights, f) / psd[kin];
 			if (data_re) {
-				netbuf[DL + k] = data_re[k];
-				netbuf[2 * DL + k] = data_im[k];
+				netbuf[DL + k] = data_re[kin];
+				netbuf[2 * DL + k] = data_im[kin];
 			}
 			// the Fisher routines always integrate with Simpson's rule (src/fisher.cpp:128-131)
-			netbuf[3 * DL + k] = quadrature_coefficient(i, L, false, false, nullptr, f) / psd[k];
+			netbuf[3 * DL + k] = quadrature_coefficient(i, L, false, false, nullptr, f) / psd[kin];
 		}
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	if (ctx->d_grid) cudaFree(ctx->d_grid);
@@ -721,6 +873,7 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 	CUDA_TRY(ctx, cudaMemcpy(ctx->d_net, netbuf.data(), sizeof(double) * netbuf.size(), cudaMemcpyHostToDevice));
 	ctx->D = D;
 	ctx->L = L;
+	ctx->ld = ld;
 	ctx->net = net;
 	ctx->have_data = data_re != nullptr;
 	ctx->gaussleg = gl;
@@ -756,7 +909,7 @@ int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *method, con
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
-	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + 127) / 128, 128, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
+	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
 	                                                                              ctx->d_coef, nullptr));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -897,7 +1050,7 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, st));
 	// T_segment = 0 and the sign flip below leave tc as sampled: this entry point mirrors repack_parameters alone
 	typedef Family<BASE_D, PPE_NONE, false, false> AnyFam;
-	k_setup_mcmc<AnyFam><<<(W + 127) / 128, 128, 0, st>>>(ctx->d_params, W, plan, ctx->net, 0, gmst, 0.0, nullptr, ctx->d_src);
+	k_setup_mcmc<AnyFam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(ctx->d_params, W, plan, ctx->net, 0, gmst, 0.0, nullptr, ctx->d_src);
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	CUDA_TRY(ctx, cudaMemcpyAsync(sources, ctx->d_src, sizeof(gwat_b200_source) * W, cudaMemcpyDeviceToHost, st));
@@ -990,7 +1143,7 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
 	const GridPtrs g = grid_ptrs(ctx);
-	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * L;
+	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
 	const int d0 = detector_index < 0 ? 0 : detector_index;
 	const int d1 = detector_index < 0 ? ctx->D : detector_index + 1;
 	const int npairs = dim * (dim + 1) / 2;
@@ -1009,7 +1162,7 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 			double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
 			GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
 			                                                                         dre, dim_));
-			k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * L, L, dim,
+			k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * ctx->ld, L, dim,
 			                                                          ctx->pref_fisher, d > d0 ? 1 : 0, ctx->d_fisher);
 			ctx->launches += 3;
 			CUDA_TRY(ctx, cudaGetLastError());

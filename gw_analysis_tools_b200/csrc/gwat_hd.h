@@ -120,9 +120,10 @@ GWAT_HD double dd_mul_to_double(double ahi, double alo, double bhi, double blo)
 GWAT_HD dd pow_sixth_dd(double x)
 {
 	// Newton iteration on y^6 = x in double-double, from the double estimate y0 = sqrt(cbrt(x)).
+	// y0 is good to ~2 ulp, one quadratic step in double-double takes it to ~1e-31
 	double y0 = sqrt(cbrt(x));
 	dd y = dd{y0, 0.0};
-	for (int it = 0; it < 2; it++) {
+	for (int it = 0; it < 1; it++) {
 		dd y2 = dd_mul(y, y);
 		dd y3 = dd_mul(y2, y);
 		dd y6 = dd_mul(y3, y3);

@@ -22,8 +22,9 @@ GWAT_HD int min_int(int a, int b) { return a < b ? a : b; }
 
 struct LikeGrid {
 	const double *f, *sf_hi, *sf_lo, *logf;
-	const double *wq, *dre, *dim;  // [D][L]
+	const double *wq, *dre, *dim;  // [D][ld]
 	int L;
+	int ld;        // leading dimension of the per-detector tables (L padded to a whole number of tiles)
 	int uniform;   // f[i] = f[0] + i*df to rounding
 	double df;
 };
@@ -60,7 +61,7 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	double phase;
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, p, logf);
 	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
-	else phase = phenomd_phase_int<Fam>(c, f, logf);
+	else phase = phenomd_phase_int<Fam>(c, f, logf, sixth);
 
 	if (Fam::base == BASE_D) {
 		amp = c.A0 * (shape * inv76);
@@ -114,33 +115,116 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	return true;
 }
 
-// One thread's run of bins: first, first+stride, ... < end.  Accumulates sum_d w_d (|r_d|^2 - 2 Re(d conj r_d)) into acc
-// and the number of active bins into nact.
+// Per-thread running state of the recurrences (uniform grids): z_d = e^{-i t_d f}, its per-step multiplier, and the
+// ringdown-amplitude decay exp(-mr_rate (f - fRD)) with its per-step factor.
+template <int D>
+struct LikeState {
+	cplx z[D], E[D];
+	double decay, decay_step;
+};
+
+// Seed the state at the thread's first frequency f0; `step` is the frequency distance between its consecutive bins and
+// f_last the last frequency it may visit.
+template <int D>
+GWAT_HD void like_state_init(const WalkerCoef &w, double f0, double step, double f_last, LikeState<D> &st)
+{
+	st.decay = 0.0;
+	st.decay_step = 1.0;
+	// kept within double range: outside, the exponential is evaluated per bin instead
+	const double a0 = -w.d.mr_rate * (f0 - w.d.fRD), a1 = -w.d.mr_rate * (f_last - w.d.fRD);
+	if (fabs(a0) < 600.0 && fabs(a1) < 600.0) {
+		st.decay = exp(a0);
+		st.decay_step = exp(-w.d.mr_rate * step);
+	}
+#pragma unroll
+	for (int d = 0; d < D; d++) {
+		double sn, cs;
+		sincos(mul_rn(w.det[d].tshift, f0), &sn, &cs);
+		st.z[d] = cplx{cs, -sn};
+		sincos(mul_rn(w.det[d].tshift, step), &sn, &cs);
+		st.E[d] = cplx{cs, -sn};
+	}
+}
+
+// One bin: adds  sum_d w_d (|r_d|^2 - 2 Re(d conj r_d))  to acc (and 1 to nact when the bin is below the model's cutoff) and
+// advances the recurrences.  wq/dre/dim are the D per-detector values of this bin.
+// `tab` supplies the per-detector table values of this bin lazily -- tab.wq(d), tab.dre(d), tab.dim(d) -- so they are
+// fetched where they are consumed instead of being held in registers across the carrier evaluation.
+template <class Fam, int D, class Tab>
+GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, double f, double sf_hi, double sf_lo, double logf,
+                      const Tab &tab, double &acc, double &nact)
+{
+	double amp, arg;
+	cplx P, Q;
+	const bool active = carrier_terms<Fam>(w, f, sf_hi, sf_lo, logf, uniform ? st.decay : 0.0, amp, arg, P, Q);
+	if (uniform) st.decay *= st.decay_step;
+	if (!active) {
+		if (uniform) {
+#pragma unroll
+			for (int d = 0; d < D; d++)
+				st.z[d] = cplx{st.z[d].re * st.E[d].re - st.z[d].im * st.E[d].im, st.z[d].re * st.E[d].im + st.z[d].im * st.E[d].re};
+		}
+		return;
+	}
+	nact += 1.0;
+	double sn, cs;
+	sincos(arg, &sn, &cs);
+	double hh = 0.0, Sre = 0.0, Sim = 0.0;
+#pragma unroll
+	for (int d = 0; d < D; d++) {
+		const DetCoef &dc = w.det[d];
+		// G = ga P + gb Q
+		const double Gre = dc.ga * P.re + dc.gb * Q.re, Gim = dc.ga * P.im + dc.gb * Q.im;
+		const double wq = tab.wq(d);
+		hh += wq * (Gre * Gre + Gim * Gim);
+		cplx zd;
+		if (uniform) {
+			zd = st.z[d];
+			st.z[d] = cplx{zd.re * st.E[d].re - zd.im * st.E[d].im, zd.re * st.E[d].im + zd.im * st.E[d].re};
+		} else {
+			double s_, c_;
+			sincos(mul_rn(dc.tshift, f), &s_, &c_);
+			zd = cplx{c_, -s_};
+		}
+		// t = data * z ;  S += w * conj(G) * t
+		const double dr = tab.dre(d), di = tab.dim(d);
+		const double tre = dr * zd.re - di * zd.im, tim = dr * zd.im + di * zd.re;
+		Sre += wq * (Gre * tre + Gim * tim);
+		Sim += wq * (Gre * tim - Gim * tre);
+	}
+	// Re(e^{+i arg} S) = cos(arg) Sre - sin(arg) Sim
+	const double dh = amp * (cs * Sre - sn * Sim);
+	acc += (amp * amp) * hh - 2.0 * dh;
+}
+
+// Table access straight from global memory (L2-resident tables).
+struct GlobalTab {
+	const double *wq_, *dre_, *dim_;
+	size_t ld;
+	GWAT_HD double wq(int d) const { return wq_[d * ld]; }
+	GWAT_HD double dre(int d) const { return dre_[d * ld]; }
+	GWAT_HD double dim(int d) const { return dim_[d * ld]; }
+};
+
+// Highest frequency at which the walker's model is non-zero.
+template <class Fam>
+GWAT_HD double walker_fmax(const WalkerCoef &w)
+{
+	return (Fam::nrt && w.d.nrt_fmerger12 < w.d.fcut) ? w.d.nrt_fmerger12 : w.d.fcut;
+}
+
+// One thread's run of bins read straight from global memory: first, first+stride, ... < end.
 template <class Fam, int D>
 GWAT_HD void loglike_run(const WalkerCoef &w, const LikeGrid &g, int first, int end, int stride, double &acc, double &nact)
 {
 	if (first >= end) return;
-	// rotation state z_d = e^{-i t_d f} and its per-step multiplier
-	cplx z[D], E[D];
-	double decay = 0.0, decay_step = 1.0;  // exp(-mr_rate (f - fRD)) and its per-step factor (uniform grids)
-	if (g.uniform) {
+	const bool uniform = g.uniform != 0;
+	const double fmax = walker_fmax<Fam>(w);
+	LikeState<D> st;
+	if (uniform) {
 		const double f0 = g.f[first];
-		if (f0 > w.d.fcut) return;  // ascending grid: nothing below the cutoff is left for this thread
-		const double step = g.df * stride;
-		// kept within [1e-280, 1e280]: outside, fall back to evaluating the exponential per bin
-		const double a0 = -w.d.mr_rate * (f0 - w.d.fRD), a1 = -w.d.mr_rate * (g.f[min_int(end - 1, g.L - 1)] - w.d.fRD);
-		if (fabs(a0) < 600.0 && fabs(a1) < 600.0) {
-			decay = exp(a0);
-			decay_step = exp(-w.d.mr_rate * step);
-		}
-#pragma unroll
-		for (int d = 0; d < D; d++) {
-			double sn, cs;
-			sincos(mul_rn(w.det[d].tshift, f0), &sn, &cs);
-			z[d] = cplx{cs, -sn};
-			sincos(mul_rn(w.det[d].tshift, step), &sn, &cs);
-			E[d] = cplx{cs, -sn};
-		}
+		if (f0 > fmax) return;  // ascending grid: nothing below the cutoff is left for this thread
+		like_state_init<D>(w, f0, g.df * stride, g.f[min_int(end - 1, g.L - 1)], st);
 	}
 	for (int i = first; i < end; i += stride) {
 #if defined(__CUDA_ARCH__)
@@ -149,48 +233,9 @@ GWAT_HD void loglike_run(const WalkerCoef &w, const LikeGrid &g, int first, int 
 		asm volatile("" ::: "memory");
 #endif
 		const double f = g.f[i];
-		double amp, arg;
-		cplx P, Q;
-		const bool active = carrier_terms<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], decay, amp, arg, P, Q);
-		decay *= decay_step;
-		if (!active) {
-			if (g.uniform && (f > w.d.fcut || (Fam::nrt && f > w.d.nrt_fmerger12))) break;  // ascending grid: the rest is zero too
-			if (g.uniform) {
-#pragma unroll
-				for (int d = 0; d < D; d++) z[d] = cplx{z[d].re * E[d].re - z[d].im * E[d].im, z[d].re * E[d].im + z[d].im * E[d].re};
-			}
-			continue;
-		}
-		nact += 1.0;
-		double sn, cs;
-		sincos(arg, &sn, &cs);
-		double hh = 0.0, Sre = 0.0, Sim = 0.0;
-#pragma unroll
-		for (int d = 0; d < D; d++) {
-			const DetCoef &dc = w.det[d];
-			const size_t k = (size_t)d * g.L + i;
-			const double wq = g.wq[k];
-			// G = ga P + gb Q
-			const double Gre = dc.ga * P.re + dc.gb * Q.re, Gim = dc.ga * P.im + dc.gb * Q.im;
-			hh += wq * (Gre * Gre + Gim * Gim);
-			cplx zd;
-			if (g.uniform) {
-				zd = z[d];
-				z[d] = cplx{zd.re * E[d].re - zd.im * E[d].im, zd.re * E[d].im + zd.im * E[d].re};
-			} else {
-				double s_, c_;
-				sincos(mul_rn(dc.tshift, f), &s_, &c_);
-				zd = cplx{c_, -s_};
-			}
-			// t = data * z ;  S += w * conj(G) * t
-			const double dr = g.dre[k], di = g.dim[k];
-			const double tre = dr * zd.re - di * zd.im, tim = dr * zd.im + di * zd.re;
-			Sre += wq * (Gre * tre + Gim * tim);
-			Sim += wq * (Gre * tim - Gim * tre);
-		}
-		// Re(e^{+i arg} S) = cos(arg) Sre - sin(arg) Sim
-		const double dh = amp * (cs * Sre - sn * Sim);
-		acc += (amp * amp) * hh - 2.0 * dh;
+		if (uniform && f > fmax) break;  // ascending grid: the rest is zero too
+		const GlobalTab tab{g.wq + i, g.dre + i, g.dim + i, (size_t)g.ld};
+		like_bin<Fam, D>(w, uniform, st, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], tab, acc, nact);
 	}
 }
 

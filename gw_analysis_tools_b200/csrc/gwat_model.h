@@ -98,6 +98,8 @@ struct DCoef {
 	// ppE / gIMR extras (used only by the families that have them)
 	int Nmod;
 	double betappe[GWAT_B200_MAX_MOD], bppe[GWAT_B200_MAX_MOD];
+	int bint[GWAT_B200_MAX_MOD];  // bppe as an integer when it is one (|b| <= 32), else INT_MIN-like sentinel 9999
+	double ppe_scale;             // (pi Mc / M)^(1/3): (pi Mc f)^(1/3) = ppe_scale * (M f)^(1/3)
 	int n_gimr_neg;
 	double gimr_neg_coef[4];
 	int gimr_neg_pow[4];

@@ -178,13 +178,17 @@ GWAT_HD void nrt_bin(const DCoef &c, double f, const MfPowers &p, double logf, d
 	const double coeff = mul_rn(c.k128, xm52);  // 3/(128 eta) * x^(-5/2)
 	phase = add_rn(phase, mul_rn(coeff, mul_rn(c.nrt_ss_coeff, x72)));
 	// tidal amplitude (already in strain units: it is multiplied by the same A0 M^{7/6} prefactor in the reference)
+	// x = (pi M f)^(2/3):  x^(13/4) = x^3 (pi M f)^(1/6),  x^2.89 = exp(2.89 * 2/3 * ln(pi M f)); ln(pi M f) = ln(pi M) + ln f
+	// comes from the walker constant and the grid table.  (The reference calls pow() twice and log() once per bin here.)
 	const double x4 = (x2 * x2);
-	const double ampNRT = c.nrt_amp_coeff * pow(x, 13. / 4.) * (1 + (449. / 108) * x + (22672. / 9.) * pow(x, 2.89)) / (1 + 13477.8 * x4);
+	const double log_piMf = c.logpiM + logf;
+	const double x134 = x3 * (1.2102032422537643 * p.sixth);  // pi^(1/6) (M f)^(1/6)
+	const double x289 = exp((2.89 * (2. / 3.)) * log_piMf);
+	const double ampNRT = c.nrt_amp_coeff * x134 * (1 + (449. / 108) * x + (22672. / 9.) * x289) * fast_rcp(1 + 13477.8 * x4);
 	amp += c.A0 * ampNRT;
 	// dissipative tide
 	const double piMf = mul_rn(GWAT_PI * c.M, f);
-	phase = add_rn(phase, mul_rn(mul_rn(c.nrt_diss_coeff, piMf), log(piMf)));
-	(void)logf;
+	phase = add_rn(phase, mul_rn(mul_rn(c.nrt_diss_coeff, piMf), log_piMf));
 }
 
 GWAT_HD double nrt_taper_factor(const DCoef &c, double f)

@@ -206,10 +206,33 @@ GWAT_HD double sixth_root_direct(double M, double f)
 // ppE phase terms sum_i beta_i (pi Mc f)^(b_i/3) (reference: src/ppE_IMRPhenomD.cpp:25-38,54-99).  The reference forms
 // u = pow(pi*Mc*f, 1./3.) and then pow(u, b_i) per term; so do we (the phases involved are small, libm-vs-CUDA pow
 // differences are far below the tolerance).
-GWAT_HD double ppe_phase_terms(const DCoef &c, double f, double acc)
+GWAT_HD double ppe_phase_terms(const DCoef &c, double mf_third, double acc)
 {
-	const double u = pow(c.pichirp * f, 1. / 3.);
-	for (int i = 0; i < c.Nmod; i++) acc = add_rn(acc, mul_rn(pow(u, c.bppe[i]), c.betappe[i]));
+	// u = (pi Mc f)^(1/3) from the already available (M f)^(1/3); integer exponents (every theory mapping and almost
+	// every ppE use has b in -13..6) by repeated multiplication, anything else through pow().  The ppE phases are O(1..100)
+	// rad, so the few-ulp difference to the reference's pow(pow(pi*Mc*f, 1./3.), b) is < 1e-13 rad.
+	const double u = c.ppe_scale * mf_third;
+	double ru = 0.0;
+	for (int i = 0; i < c.Nmod; i++) {
+		double t;
+		const int b = c.bint[i];
+		if (b == 9999) {
+			t = pow(u, c.bppe[i]);
+		} else {
+			const int n = b < 0 ? -b : b;
+			double base = u;
+			if (b < 0) {
+				if (ru == 0.0) ru = fast_rcp(u);
+				base = ru;
+			}
+			t = 1.0;
+			for (int k = n; k > 0; k >>= 1) {
+				if (k & 1) t *= base;
+				base *= base;
+			}
+		}
+		acc = add_rn(acc, mul_rn(t, c.betappe[i]));
+	}
 	return acc;
 }
 // gIMR negative-PN-order inspiral terms 3/(128 eta) dphi_i (pi M f)^((i-5)/3), i = -4..-1 (src/gIMRPhenomD.cpp:149-166)
@@ -225,10 +248,14 @@ GWAT_HD double gimr_negative_pn_terms(const DCoef &c, double f, double acc)
 	return acc;
 }
 // Extra inspiral-phase terms of the modified families, accumulated onto `ph` in the reference's order.
+// (M f)^(1/6) to a few ulp, for setup-time evaluations where the sixth root only feeds amplitudes or the (M f)^(3/4) term of
+// the merger-ringdown phase (never the leading TaylorF2 term).
+GWAT_HD double sixth_root_approx(double M, double f) { return sqrt(cbrt(M * f)); }
+
 template <class Fam>
-GWAT_HD double phase_ins_extra(const DCoef &c, double f, double ph)
+GWAT_HD double phase_ins_extra(const DCoef &c, double f, double mf_third, double ph)
 {
-	if (Fam::ppe != PPE_NONE) ph = ppe_phase_terms(c, f, ph);
+	if (Fam::ppe != PPE_NONE) ph = ppe_phase_terms(c, mf_third, ph);
 	if (Fam::gimr) ph = gimr_negative_pn_terms(c, f, ph);
 	return ph;
 }
@@ -254,13 +281,13 @@ GWAT_HD double phenomd_phase_ins(const DCoef &c, double f, const MfPowers &p, do
 	sg = add_rn(sg, mul_rn(c.sig3q, p.five3));
 	sg = add_rn(sg, mul_rn(c.sig4q, p.sq));
 	double ph = add_rn(tf2, mul_rn(c.inv_eta, sg));
-	if (Fam::ppe != PPE_NONE || Fam::gimr) ph = phase_ins_extra<Fam>(c, f, ph);
+	if (Fam::ppe != PPE_NONE || Fam::gimr) ph = phase_ins_extra<Fam>(c, f, p.third, ph);
 	return ph;
 }
 
 // Intermediate phase (reference: phase_int, src/IMRPhenomD.cpp:1577-1589).  log(Mf) is formed as ln M + ln f.
 template <class Fam>
-GWAT_HD double phenomd_phase_int(const DCoef &c, double f, double logf)
+GWAT_HD double phenomd_phase_int(const DCoef &c, double f, double logf, double sixth)
 {
 	const double Mf = mul_rn(c.M, f);
 	const double Mf3 = mul_rn(mul_rn(Mf, Mf), Mf);
@@ -269,7 +296,7 @@ GWAT_HD double phenomd_phase_int(const DCoef &c, double f, double logf)
 	t = add_rn(t, mul_rn(c.beta2, lg));
 	t = sub_rn(t, mul_rn(c.beta3_3, fast_rcp(Mf3)));
 	double ph = mul_rn(c.inv_eta, t);
-	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, f, ph);
+	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, sixth * sixth, ph);
 	return ph;
 }
 
@@ -286,7 +313,7 @@ GWAT_HD double phenomd_phase_mr(const DCoef &c, double f, double sixth)
 	t = add_rn(t, mul_rn(c.alpha3_43, Mf34));
 	t = add_rn(t, mul_rn(c.alpha4, atan(mul_rn(sub_rn(f, c.alpha5fRD), c.inv_fdamp))));
 	double ph = mul_rn(c.inv_eta, t);
-	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, f, ph);
+	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, s2, ph);
 	return ph;
 }
 
@@ -328,7 +355,7 @@ GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, do
 
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, p, logf);
 	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
-	else phase = phenomd_phase_int<Fam>(c, f, logf);
+	else phase = phenomd_phase_int<Fam>(c, f, logf, sixth);
 }
 
 template <class Fam>
@@ -441,9 +468,12 @@ GWAT_HD void setup_family_extras(const SrcQ &s, DCoef &c)
 	c.n_gimr_neg = 0;
 	if (Fam::ppe != PPE_NONE) {
 		c.Nmod = s.Nmod;
+		c.ppe_scale = cbrt(GWAT_PI * s.chirpmass / s.M);
 		for (int i = 0; i < s.Nmod && i < GWAT_B200_MAX_MOD; i++) {
 			c.betappe[i] = s.betappe[i];
 			c.bppe[i] = s.bppe[i];
+			const double r = rint(s.bppe[i]);
+			c.bint[i] = (r == s.bppe[i] && fabs(r) <= 32) ? (int)r : 9999;
 		}
 	}
 	if (Fam::gimr && s.Nmod_phi != 0) {

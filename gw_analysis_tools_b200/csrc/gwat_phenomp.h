@@ -28,17 +28,27 @@ GWAT_HD double l2pn(double eta, double x, double sqrt_x)
 struct Vec3 {
 	double x, y, z;
 };
-GWAT_HD void rot_z(double angle, Vec3 &v)
+// Rotations about z and y by an angle given through its cosine and sine.  The reference's ROTATEZ/ROTATEY macros
+// (include/gwat/IMRPhenomP.h:17-27) call cos/sin of the same three angles up to four times each; here each angle's
+// cosine and sine are evaluated once and reused (identical inputs, identical values).
+struct CosSin {
+	double c, s;
+};
+GWAT_HD CosSin cos_sin(double angle)
 {
-	const double c = cos(angle), s = sin(angle);
-	const double t1 = v.x * c - v.y * s, t2 = v.x * s + v.y * c;
+	CosSin r;
+	sincos(angle, &r.s, &r.c);
+	return r;
+}
+GWAT_HD void rot_z(const CosSin &a, Vec3 &v)
+{
+	const double t1 = v.x * a.c - v.y * a.s, t2 = v.x * a.s + v.y * a.c;
 	v.x = t1;
 	v.y = t2;
 }
-GWAT_HD void rot_y(double angle, Vec3 &v)
+GWAT_HD void rot_y(const CosSin &a, Vec3 &v)
 {
-	const double c = cos(angle), s = sin(angle);
-	const double t1 = v.x * c + v.z * s, t2 = -v.x * s + v.z * c;
+	const double t1 = v.x * a.c + v.z * a.s, t2 = -v.x * a.s + v.z * a.c;
 	v.x = t1;
 	v.z = t2;
 }
@@ -67,7 +77,7 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 
 	// L at f_ref (the reference fills the inspiral power table at f_ref: src/IMRPhenomP.cpp:1117-1123)
 	const PiPowers pi = pi_powers();
-	const double sixth = sixth_root_direct(s.M, s.f_ref);
+	const double sixth = sixth_root_approx(s.M, s.f_ref);  // feeds L(f_ref), an angle-level quantity
 	const double mf_third = mul_rn(sixth, sixth);
 	const double mf_two3 = mul_rn(mf_third, mf_third);
 	const double x = mf_two3 * pi.two3;
@@ -88,30 +98,33 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 	s.phi_aligned = -phiJ;
 
 	const double incl = s.incl_angle, phiRef = s.phiRef;
-	const Vec3 N{sin(incl) * cos(GWAT_PI / 2. - phiRef), sin(incl) * sin(GWAT_PI / 2. - phiRef), cos(incl)};
+	const CosSin ci = cos_sin(incl), cp = cos_sin(phiRef), cq = cos_sin(GWAT_PI / 2. - phiRef);
+	const CosSin rJz = cos_sin(-phiJ), rJy = cos_sin(-thetaJ);
+	const Vec3 N{ci.s * cq.c, ci.s * cq.s, ci.c};
 	Vec3 t = N;
-	rot_z(-phiJ, t);
-	rot_y(-thetaJ, t);
+	rot_z(rJz, t);
+	rot_y(rJy, t);
 	const double kappa = -atan2(t.y, t.x);
+	const CosSin rK = cos_sin(kappa);
 
 	t = Vec3{0., 0., 1.};
-	rot_z(-phiJ, t);
-	rot_y(-thetaJ, t);
-	rot_z(kappa, t);
+	rot_z(rJz, t);
+	rot_y(rJy, t);
+	rot_z(rK, t);
 	s.alpha0 = atan2(t.y, t.x);
 
 	t = N;
-	rot_z(-phiJ, t);
-	rot_y(-thetaJ, t);
-	rot_z(kappa, t);
+	rot_z(rJz, t);
+	rot_y(rJy, t);
+	rot_z(rK, t);
 	const double Nx_Jf = t.x, Nz_Jf = t.z;
 	s.thetaJN = acos(Nz_Jf);
 
 	// polarisation-frame mismatch angle zeta between the (P,Q,N) triad of PhenomP and the LAL wave frame
-	t = Vec3{-cos(incl) * sin(phiRef), -cos(incl) * cos(phiRef), sin(incl)};
-	rot_z(-phiJ, t);
-	rot_y(-thetaJ, t);
-	rot_z(kappa, t);
+	t = Vec3{-ci.c * cp.s, -ci.c * cp.c, ci.s};
+	rot_z(rJz, t);
+	rot_y(rJy, t);
+	rot_z(rK, t);
 	const double XdotP = t.x * 0. + t.y * -1. + t.z * 0.;
 	const double XdotQ = t.x * Nz_Jf + t.y * 0. + t.z * -Nx_Jf;
 	s.zeta_polariz = atan2(XdotQ, XdotP);
@@ -266,10 +279,14 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 			t_corr = 0;  // the reference bails out with 0 as well (:567-572)
 		} else {
 			double xs[10], ys[10];
+#pragma unroll
 			for (int j = 0; j < n; j++) {
 				const double f = start + j * step;
 				double a_unused, ph;
-				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, sixth_root_direct(c.M, f), log(f), a_unused, ph);
+				// the samples straddle fRD > f2p: merger-ringdown phase, where the sixth root only enters through (Mf)^(3/4);
+				// below f1p (never for physical parameters) the exact root is used
+				const double root = f < c.f1p ? sixth_root_direct(c.M, f) : sixth_root_approx(c.M, f);
+				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, log(f), a_unused, ph);
 				xs[j] = f;
 				ys[j] = -ph;
 			}
@@ -302,7 +319,7 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 	double phase;
 	if (f < c.f1p) phase = phenomd_phase_ins<Fam>(c, f, mp, logf);
 	else if (f > c.f2p) phase = phenomd_phase_mr<Fam>(c, f, sixth);
-	else phase = phenomd_phase_int<Fam>(c, f, logf);
+	else phase = phenomd_phase_int<Fam>(c, f, logf, sixth);
 
 	// Wigner d^2_{m,+-2}(beta): tan(beta) = S_perp / (L + S_parallel)
 	const PiPowers pi = pi_powers();

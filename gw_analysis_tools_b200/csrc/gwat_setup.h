@@ -64,23 +64,33 @@ GWAT_HD void populate_source(const gwat_b200_source &in, SrcQ &s)
 }
 
 // ---- detectors -------------------------------------------------------------------------------------------------------
-// Antenna patterns of an interferometer with response tensor D (row-major 3x3) for a source at (ra, dec) with
-// polarisation angle psi at Greenwich sidereal time gmst.  Same construction as LAL's XLALComputeDetAMResponse, which the
-// reference transcribes (src/detector_util.cpp:900-1013).
-GWAT_HD void antenna_pattern(const double *D, double geometric_factor, double ra, double dec, double psi, double gmst,
-                             double &Fplus, double &Fcross)
+// Sky-position trigonometry shared by the antenna patterns and the arrival-time differences of all detectors.  The
+// reference recomputes cos/sin of the same (gmst - ra), dec for every detector and again in DTOA_earth_centered_coord
+// (src/detector_util.cpp:780-784, 915-922); identical inputs give identical values, so they are evaluated once.
+struct SkyTrig {
+	double cosgha, singha, cosdec, sindec, cospsi, sinpsi;
+};
+GWAT_HD SkyTrig sky_trig(double ra, double dec, double psi, double gmst)
 {
+	SkyTrig t;
 	const double gha = gmst - ra;
-	const double cosgha = cos(gha), singha = sin(gha);
-	const double cosdec = cos(dec), sindec = sin(dec);
-	const double cospsi = cos(psi), sinpsi = sin(psi);
+	sincos(gha, &t.singha, &t.cosgha);
+	sincos(dec, &t.sindec, &t.cosdec);
+	sincos(psi, &t.sinpsi, &t.cospsi);
+	return t;
+}
+
+// Antenna patterns of an interferometer with response tensor D (row-major 3x3).  Same construction as LAL's
+// XLALComputeDetAMResponse, which the reference transcribes (src/detector_util.cpp:900-1013).
+GWAT_HD void antenna_pattern(const double *D, double geometric_factor, const SkyTrig &t, double &Fplus, double &Fcross)
+{
 	double X[3], Y[3];
-	X[0] = -cospsi * singha - sinpsi * cosgha * sindec;
-	X[1] = -cospsi * cosgha + sinpsi * singha * sindec;
-	X[2] = sinpsi * cosdec;
-	Y[0] = sinpsi * singha - cospsi * cosgha * sindec;
-	Y[1] = sinpsi * cosgha + cospsi * singha * sindec;
-	Y[2] = cospsi * cosdec;
+	X[0] = -t.cospsi * t.singha - t.sinpsi * t.cosgha * t.sindec;
+	X[1] = -t.cospsi * t.cosgha + t.sinpsi * t.singha * t.sindec;
+	X[2] = t.sinpsi * t.cosdec;
+	Y[0] = t.sinpsi * t.singha - t.cospsi * t.cosgha * t.sindec;
+	Y[1] = t.sinpsi * t.cosgha + t.cospsi * t.singha * t.sindec;
+	Y[2] = t.cospsi * t.cosdec;
 	double fp = 0, fc = 0;
 	for (int i = 0; i < 3; i++) {
 		const double DX = D[3 * i + 0] * X[0] + D[3 * i + 1] * X[1] + D[3 * i + 2] * X[2];
@@ -94,14 +104,17 @@ GWAT_HD void antenna_pattern(const double *D, double geometric_factor, double ra
 
 // Arrival-time difference t(loc1) - t(loc2) of a plane wave from (ra, dec)  (DTOA_earth_centered_coord,
 // src/detector_util.cpp:766-788).
-GWAT_HD double dtoa_between(const double *loc1, const double *loc2, double ra, double dec, double gmst)
+GWAT_HD double dtoa_between(const double *loc1, const double *loc2, const SkyTrig &t)
 {
 	const double dx0 = loc1[0] - loc2[0], dx1 = loc1[1] - loc2[1], dx2 = loc1[2] - loc2[2];
-	const double hour_angle = gmst - ra;
-	const double e0 = cos(dec) * cos(hour_angle);
-	const double e1 = cos(dec) * -sin(hour_angle);
-	const double e2 = sin(dec);
+	const double e0 = t.cosdec * t.cosgha;
+	const double e1 = t.cosdec * -t.singha;
+	const double e2 = t.sindec;
 	return (dx0 * e0 + dx1 * e1 + dx2 * e2) / GWAT_C_SI;
+}
+GWAT_HD double dtoa_between(const double *loc1, const double *loc2, double ra, double dec, double gmst)
+{
+	return dtoa_between(loc1, loc2, sky_trig(ra, dec, 0.0, gmst));
 }
 
 // The detector network as the kernels see it: rows of the generated detector table (tensor, location, factor).
@@ -112,9 +125,10 @@ struct Network {
 
 GWAT_HD void detector_setup(const Network &net, double ra, double dec, double psi, double gmst, DetCoef *out)
 {
+	const SkyTrig t = sky_trig(ra, dec, psi, gmst);
 	for (int d = 0; d < net.D; d++) {
-		antenna_pattern(net.row[d], net.row[d][12], ra, dec, psi, gmst, out[d].Fplus, out[d].Fcross);
-		const double dtoa = dtoa_between(net.row[0] + 9, net.row[d] + 9, ra, dec, gmst);
+		antenna_pattern(net.row[d], net.row[d][12], t, out[d].Fplus, out[d].Fcross);
+		const double dtoa = dtoa_between(net.row[0] + 9, net.row[d] + 9, t);
 		// tc = -DTOA; tc *= 2*M_PI;   (src/waveform_util.cpp:173-174)
 		out[d].tshift = (-dtoa) * (2 * GWAT_PI);
 	}
@@ -194,7 +208,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		// (amp_connection_coeffs, :1679-1702; the reference expands the solution into closed-form monomial
 		// coefficients, here it stays in Newton divided-difference form in x = M f).
 		MfPowers p1;
-		mf_powers(M, s.f1, sixth_root_direct(M, s.f1), p1);
+		mf_powers(M, s.f1, sixth_root_approx(M, s.f1), p1);  // amplitude only
 		const double v1 = phenomd_amp_ins(c, p1);
 		const double v2 = lam.v2;
 		const double v3 = phenomd_amp_mr(c, s.f3);
@@ -300,7 +314,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		mf_powers(M, f1p, sixth_root_direct(M, f1p), p);
 		// at exactly f1p the per-bin code would take the intermediate branch; the matching needs the inspiral expression
 		const double ins = phenomd_phase_ins<Fam>(c, f1p, p, log_f1p);
-		const double intv = phenomd_phase_int<Fam>(c, f1p, log_f1p);
+		const double intv = phenomd_phase_int<Fam>(c, f1p, log_f1p, p.sixth);
 		lam.beta[0] = eta * ins - eta * intv;
 	}
 	sync_int_mr();
@@ -311,8 +325,9 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	}
 	sync_int_mr();
 	{
-		const double intv = phenomd_phase_int<Fam>(c, f2p, log_f2p);
-		const double mr = phenomd_phase_mr<Fam>(c, f2p, sixth_root_direct(M, f2p));
+		const double root2 = sixth_root_approx(M, f2p);
+		const double intv = phenomd_phase_int<Fam>(c, f2p, log_f2p, root2);
+		const double mr = phenomd_phase_mr<Fam>(c, f2p, root2);
 		lam.alpha[0] = eta * intv - eta * mr;
 	}
 	sync_int_mr();

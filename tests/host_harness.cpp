@@ -256,6 +256,7 @@ double loglike_t(int theory, const gwat_b200_source *src, const Network &net, co
 	lg.dre = dre;
 	lg.dim = dim;
 	lg.L = (int)g.f.size();
+	lg.ld = lg.L;
 	lg.uniform = uniform ? 1 : 0;
 	lg.df = df;
 	double total = 0, nact = 0;
