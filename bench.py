@@ -42,6 +42,16 @@ UNIT = "evals/s"
 FLOP_EQ = {"IMRPhenomD": (270, 90), "IMRPhenomPv2": (670, 90), "IMRPhenomD_NRT": (530, 90), "dCS_IMRPhenomD": (320, 90)}
 
 
+def ncu_traffic(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_loglike launch of this workload, from the committed
+    `ncu --set full` capture (profiles/traffic.json names the capture); None when no capture exists for the config."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t["cfg%d" % config]["k_loglike_dram_bytes"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def flop_eq_per_bin(method, D):
     a, b = FLOP_EQ[method]
     return a + b * D
@@ -294,7 +304,7 @@ def run_b200(args):
                 "peak_source": "DFMA-chain microbenchmark run in this process (gwat_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "work": "%d flop-eq per active (walker,bin) [SURVEY 8(d)] x %.4g active bins per launch (%.1f%% of W*L)" % (
                     feq, act, 100.0 * act / (W * L)),
-                "kernel_ms": k_ms, "traffic": None,
+                "kernel_ms": k_ms, "traffic": ncu_traffic(args.config),
                 "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",

@@ -509,42 +509,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 // context
 // ---------------------------------------------------------------------------------------------------------------------
 
-struct gwat_b200_ctx {
-	int device = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	std::string err;
-	std::mutex mu;
-	// network
-	int D = 0, L = 0;
-	int ld = 0;  // L padded to a whole number of 256-bin tiles (bulk-copy granularity of the likelihood kernel)
-	bool have_data = false, gaussleg = false, log10F = false, uniform = false;
-	// Bulk-copy (TMA) staging of the grid tiles is implemented (k_loglike_tma) but OFF by default: the tables are 2 MB and
-	// L2-resident, the kernel is FP64-bound, and the staged variant measured 10 % slower (sync + shared-memory footprint);
-	// GWAT_B200_TMA=1 selects it for A/B measurements.
-	bool use_tma = false;
-	double df = 0;
-	Network net{};
-	double pref_like = 0, pref_fisher = 0;
-	double *d_grid = nullptr;  // f, sf_hi, sf_lo, logf : 4*L
-	double *d_net = nullptr;   // wq, dre, dim, wq_fisher : 4*D*L
-	std::vector<double> h_f;
-	// scratch (grown on demand)
-	size_t cap_walkers = 0, cap_partial = 0, cap_params = 0, cap_out = 0, cap_src = 0;
-	WalkerCoef *d_coef = nullptr;
-	double *d_partial = nullptr;
-	double *d_params = nullptr;
-	double *d_out = nullptr;
-	gwat_b200_source *d_src = nullptr;
-	unsigned long long *d_active = nullptr;
-	size_t cap_deriv = 0, cap_scale = 0, cap_fisher = 0, cap_bc = 0;
-	double *d_deriv = nullptr, *d_scale = nullptr, *d_fisher = nullptr;
-	int *d_bc = nullptr;
-	// introspection
-	long long launches = 0;
-	double last_ms = 0;
-	long long last_active = 0;
-};
+#include "gwat_engine_internal.h"
 
 namespace {
 
@@ -743,6 +708,82 @@ int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const 
 	return 0;
 }
 
+// ---- Fisher passes shared by the host-source entry point and the sampler's device-parameter entry point ------------------
+int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim)
+{
+	// sources per pass: bounded by a 512 MiB derivative buffer
+	const size_t per_source = (size_t)dim * ctx->L * 16;
+	return (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)512 << 20) / per_source));
+}
+
+int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts)
+{
+	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
+	return 0;
+}
+
+// ctx->d_src[0..ns) -> ctx->d_fisher[ns][dim][dim], detectors d0..d1-1 summed
+int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int ns, int chunk, int d0, int d1,
+                 int reference_index, cudaStream_t st)
+{
+	const int L = ctx->L, dim = fp.rp.dimension;
+	const GridPtrs g = grid_ptrs(ctx);
+	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
+	const int npairs = dim * (dim + 1) / 2;
+	for (int d = d0; d < d1; d++) {
+		std::memcpy(fp.det_row, ctx->net.row[d], sizeof(fp.det_row));
+		std::memcpy(fp.ref_row, ctx->net.row[reference_index], sizeof(fp.ref_row));
+		fp.det_is_ref = (std::memcmp(fp.det_row, fp.ref_row, sizeof(fp.det_row)) == 0) ? 1 : 0;
+		const int nthreads = ns * dim * fp.npts;
+		GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
+		                                                                                        ctx->d_scale, ctx->d_bc));
+		const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
+		double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
+		GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
+		                                                                         dre, dim_));
+		k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * ctx->ld, L, dim,
+		                                                          ctx->pref_fisher, d > d0 ? 1 : 0, ctx->d_fisher);
+		ctx->launches += 3;
+		CUDA_TRY(ctx, cudaGetLastError());
+	}
+	return 0;
+}
+
+// Swap one of the extra scratch sets into the context for the duration of a call (the caller holds ctx->mu).
+struct LaneSwap {
+	gwat_b200_ctx *c;
+	LikeLane *l;
+	LaneSwap(gwat_b200_ctx *ctx, int lane) : c(ctx), l(lane > 0 ? &ctx->extra[lane - 1] : nullptr) { swap(); }
+	~LaneSwap() { swap(); }
+	void swap()
+	{
+		if (!l) return;
+		std::swap(c->d_coef, l->d_coef);
+		std::swap(c->cap_walkers, l->cap_walkers);
+		std::swap(c->d_partial, l->d_partial);
+		std::swap(c->cap_partial, l->cap_partial);
+		std::swap(c->d_active, l->d_active);
+		std::swap(c->ev0, l->ev0);
+		std::swap(c->ev1, l->ev1);
+	}
+};
+
+// sampling vector -> physical record, tc left as sampled (repack_parameters without the likelihood's tc flip)
+__global__ void k_repack_only(const double *__restrict__ params, int W, RepackPlan plan, double gmst, gwat_b200_source *__restrict__ out)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	gwat_b200_source s;
+	repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, 0.0, s);
+	s.tc = -s.tc;
+	out[w] = s;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -808,6 +849,13 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 	cudaFree(c->d_bc);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
+	for (LikeLane &l : c->extra) {
+		cudaFree(l.d_coef);
+		cudaFree(l.d_partial);
+		cudaFree(l.d_active);
+		if (l.ev0) cudaEventDestroy(l.ev0);
+		if (l.ev1) cudaEventDestroy(l.ev1);
+	}
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -897,23 +945,10 @@ int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *method, con
                                      void *stream)
 {
 	if (int rc = check_ready(ctx, true)) return rc;
-	if (W < 0 || (W > 0 && (!d_params || !d_logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: NULL array");
-	if (W == 0) return GWAT_B200_OK;
-	MethodDesc desc;
-	if (parse_method(method, desc) != 0 || desc.mcmc)
-		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
-	RepackPlan plan;
-	if (make_plan(desc, mod, dimension, plan) != 0)
-		return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: dimension does not match the method and modification struct");
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
-	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
-	                                                                              ctx->d_coef, nullptr));
-	ctx->launches += 1;
-	CUDA_TRY(ctx, cudaGetLastError());
-	return run_loglike(ctx, desc, W, d_logL, st);
+	return gwat_internal::loglike_mcmc_lane(ctx, 0, method, mod, dimension, W, d_params, gmst, T_segment, d_logL,
+	                                        stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 int gwat_b200_loglike_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
@@ -1136,37 +1171,14 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	// sources per pass: bounded by a 512 MiB derivative buffer
 	size_t per_source = (size_t)dim * L * 16;
 	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)512 << 20) / per_source));
-	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * fp.npts)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * L)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
-	const GridPtrs g = grid_ptrs(ctx);
-	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts)) return rc;
 	const int d0 = detector_index < 0 ? 0 : detector_index;
 	const int d1 = detector_index < 0 ? ctx->D : detector_index + 1;
-	const int npairs = dim * (dim + 1) / 2;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 	for (int s0 = 0; s0 < S; s0 += chunk) {
 		const int ns = std::min(chunk, S - s0);
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, sources + s0, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, st));
-		for (int d = d0; d < d1; d++) {
-			std::memcpy(fp.det_row, ctx->net.row[d], sizeof(fp.det_row));
-			std::memcpy(fp.ref_row, ctx->net.row[reference_index], sizeof(fp.ref_row));
-			fp.det_is_ref = (std::memcmp(fp.det_row, fp.ref_row, sizeof(fp.det_row)) == 0) ? 1 : 0;
-			const int nthreads = ns * dim * fp.npts;
-			GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
-			                                                                                        ctx->d_scale, ctx->d_bc));
-			const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
-			double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
-			GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
-			                                                                         dre, dim_));
-			k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * ctx->ld, L, dim,
-			                                                          ctx->pref_fisher, d > d0 ? 1 : 0, ctx->d_fisher);
-			ctx->launches += 3;
-			CUDA_TRY(ctx, cudaGetLastError());
-		}
+		if (int rc = fisher_chunk(ctx, desc, fp, ns, chunk, d0, d1, reference_index, st)) return rc;
 		CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * dim * dim, ctx->d_fisher, sizeof(double) * ns * dim * dim,
 		                              cudaMemcpyDeviceToHost, st));
 	}
@@ -1210,3 +1222,74 @@ double gwat_b200_last_kernel_ms(const gwat_b200_ctx *c) { return c ? c->last_ms 
 long long gwat_b200_last_active_bins(const gwat_b200_ctx *c) { return c ? c->last_active : 0; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// internal interface (gwat_engine_internal.h)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace gwat_internal {
+
+int set_error(gwat_b200_ctx *ctx, int code, const std::string &msg) { return fail(ctx, code, msg); }
+
+int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                      const double *d_params, double gmst, double T_segment, double *d_logL, cudaStream_t st)
+{
+	if (int rc = check_ready(ctx, true)) return rc;
+	if (lane < 0 || lane > 2) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc: lane out of range");
+	if (W < 0 || (W > 0 && (!d_params || !d_logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	RepackPlan plan;
+	if (make_plan(desc, mod, dimension, plan) != 0)
+		return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: dimension does not match the method and modification struct");
+	if (lane > 0) {
+		LikeLane &l = ctx->extra[lane - 1];
+		if (!l.ev0) {
+			CUDA_TRY(ctx, cudaEventCreate(&l.ev0));
+			CUDA_TRY(ctx, cudaEventCreate(&l.ev1));
+			CUDA_TRY(ctx, cudaMalloc((void **)&l.d_active, sizeof(unsigned long long)));
+		}
+	}
+	LaneSwap swap(ctx, lane);
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
+	                                                                              ctx->d_coef, nullptr));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return run_loglike(ctx, desc, W, d_logL, st);
+}
+
+int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int S,
+                    const double *d_params, double gmst, double *d_fisher, cudaStream_t st)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (S <= 0) return GWAT_B200_OK;
+	if (order != 2 && order != 4) return fail(ctx, GWAT_B200_ERR_ARG, "fisher: order must be 2 or 4");
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	RepackPlan rp;
+	if (make_plan(desc, mod, dimension, rp) != 0)
+		return fail(ctx, GWAT_B200_ERR_ARG, "fisher: dimension does not match the method and modification struct");
+	FisherPlan fp;
+	std::memset(&fp, 0, sizeof(fp));
+	fp.rp = rp;
+	fp.rp.alpha_unit_fix = 0;  // the stencil works on the physical record; units were fixed by the repack below
+	fp.npts = order == 4 ? 4 : 2;
+	fp.theory = desc.theory;
+	const int dim = dimension;
+	const int chunk = fisher_chunk_size(ctx, S, dim);
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts)) return rc;
+	for (int s0 = 0; s0 < S; s0 += chunk) {
+		const int ns = std::min(chunk, S - s0);
+		k_repack_only<<<(ns + 127) / 128, 128, 0, st>>>(d_params + (size_t)s0 * dim, ns, rp, gmst, ctx->d_src);
+		ctx->launches += 1;
+		if (int rc = fisher_chunk(ctx, desc, fp, ns, chunk, 0, ctx->D, 0, st)) return rc;
+		CUDA_TRY(ctx, cudaMemcpyAsync(d_fisher + (size_t)s0 * dim * dim, ctx->d_fisher, sizeof(double) * ns * dim * dim,
+		                              cudaMemcpyDeviceToDevice, st));
+	}
+	return GWAT_B200_OK;
+}
+
+}  // namespace gwat_internal

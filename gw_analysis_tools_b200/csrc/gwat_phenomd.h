@@ -77,11 +77,12 @@ GWAT_HD double erad_rational_0815(double eta, double chi1, double chi2)
 GWAT_HD double qnm_eval(const double (*knots)[5], int n, double a, int col)
 {
 	if (!(a >= knots[0][0] && a <= knots[n - 1][0])) return NAN;
-	int lo = 0, hi = n - 1;
-	while (hi > lo + 1) {
-		const int mid = (hi + lo) / 2;
-		if (knots[mid][0] > a) hi = mid; else lo = mid;
-	}
+	// gsl_interp_bsearch semantics (knots[lo] <= a < knots[lo+1], last interval closed), reached from a guess instead of a
+	// bisection: the table is uniform (0.002) except for a few 0.001 steps at either end, so the walk is 0-3 steps long
+	int lo = (int)((a - knots[0][0]) * ((n - 1) / (knots[n - 1][0] - knots[0][0])));
+	lo = lo < 0 ? 0 : (lo > n - 2 ? n - 2 : lo);
+	while (lo > 0 && knots[lo][0] > a) lo--;
+	while (lo < n - 2 && !(knots[lo + 1][0] > a)) lo++;
 	const double x_lo = knots[lo][0], x_hi = knots[lo + 1][0];
 	const double dx = x_hi - x_lo;
 	const double y_lo = knots[lo][col], y_hi = knots[lo + 1][col];

@@ -1,0 +1,793 @@
+// gwat_b200 ensemble sampler: the batched parallel-tempering Metropolis-Hastings step of include/gwat_b200_sampler.h.
+//
+// Device state (all in HBM, sized for chain_N = C chains of dimension P, history length H):
+//   pos[C][P], prop[C][P], ll/lp/llprop/lpprop[C]      current and proposed states
+//   hist[C][H][P]                                       per-chain ring buffer for differential evolution
+//   fvals[C][P], fvecs[C][P][P]                         Fisher eigen-systems (row i = eigenvector i)
+//   widths[C][P+3], counters[C][NCOUNTERS], gauss_ct[C][P][4], type_last[C][4]
+// One step of one lane (= contiguous range of chains on its own stream):
+//   [Fisher refresh of the chains whose schedule says so]  k_gather -> engine Fisher pass -> k_fisher_eigen
+//   k_propose      one thread per chain: draw the step type, build the proposal, evaluate its prior
+//   engine         k_setup_mcmc + k_loglike + k_finish on the proposals (lane scratch of the context)
+//   k_accept       one thread per chain: Metropolis-Hastings, counters, history, width tuning, cold-chain record
+// After every swp_freq steps the lanes join for the swap sweep: k_swap_prepare (thresholds, parallel) -> k_swap_scan (the
+// reference's sequential sweep over adjacent chains, one thread, 4 dependent instructions per pair) -> k_swap_apply.
+// The host never reads device results inside gwat_b200_sampler_run: the step types are pure functions of (seed, step,
+// chain), so the host replays them to know which chains refresh their Fisher matrix at which step.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gwat_engine_internal.h"
+#include "gwat_method.h"
+#include "gwat_sampler_math.h"
+
+using namespace gwat;
+using namespace gwat::smp;
+
+namespace {
+
+constexpr int NCT = GWAT_B200_SAMPLER_NCOUNTERS;
+
+struct StepConst {
+	uint64_t seed;
+	int C, P, H;
+	int history_update, check_stepsize_freq;
+	int fisher_exist;
+	int record_cold;
+};
+
+struct DevState {
+	double *pos, *prop, *ll, *lp, *llprop, *lpprop, *temps;
+	double *hist;
+	int *hist_pos;
+	double *fvals, *fvecs;
+	double *widths;
+	long long *counters;
+	int *gauss_ct;        // [C][P][4]: accept, reject, last accept, last reject
+	long long *type_last; // [C][4]: DE last accept/reject, Fisher last accept/reject
+	int *info;            // [C]: step type | selected dimension << 8
+	int *cold_slot;       // [C]: index among the cold chains, or -1
+	double *cold;         // [cap_steps][n_cold][P]
+};
+
+__global__ void k_init(DevState d, StepConst k, gwat_b200_prior prior, PriorPlan pp)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= k.C) return;
+	const int P = k.P;
+	d.lp[c] = standard_log_prior(prior, pp, d.pos + (size_t)c * P);
+	for (int i = 0; i < P; i++) {
+		d.hist[((size_t)c * k.H) * P + i] = d.pos[(size_t)c * P + i];
+		d.widths[(size_t)c * (P + 3) + i] = .05;  // allocate_sampler_mem, src/mcmc_sampler_internals.cpp:1998-2004
+		d.fvals[(size_t)c * P + i] = 0;
+		for (int j = 0; j < P; j++) d.fvecs[((size_t)c * P + i) * P + j] = (i == j) ? 1.0 : 0.0;
+		for (int j = 0; j < 4; j++) d.gauss_ct[((size_t)c * P + i) * 4 + j] = 0;
+	}
+	d.widths[(size_t)c * (P + 3) + P + 0] = 1;    // DE
+	d.widths[(size_t)c * (P + 3) + P + 1] = .05;  // MMALA (unused)
+	d.widths[(size_t)c * (P + 3) + P + 2] = .5;   // Fisher
+	d.hist_pos[c] = 0;
+	for (int j = 0; j < NCT; j++) d.counters[(size_t)c * NCT + j] = 0;
+	for (int j = 0; j < 4; j++) d.type_last[(size_t)c * 4 + j] = 0;
+}
+
+__global__ void k_propose(DevState d, StepConst k, gwat_b200_prior prior, PriorPlan pp, long long step, int c0, int n)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const int c = c0 + t, P = k.P;
+	const double T = d.temps[c];
+	double bounds[4];
+	step_boundaries(T, k.fisher_exist != 0, step > k.H, bounds);
+	double alpha, u_acc, u_pick, u_pick2, n0, n1;
+	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u_acc);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_PICK, u_pick, u_pick2);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_NORMAL, n0, n1);
+	const double z = normal_from(n0, n1);
+	const int type = step_type(alpha, bounds);
+	const double *cur = d.pos + (size_t)c * P;
+	double *prop = d.prop + (size_t)c * P;
+	const double *w = d.widths + (size_t)c * (P + 3);
+	int sel = 0;
+	if (type == STEP_GAUSS) {
+		sel = propose_gaussian(cur, prop, P, w, u_pick, z);
+	} else if (type == STEP_DE) {
+		int i, j;
+		de_pick(k.H, u_pick, u_pick2, i, j);
+		double beta, unused;
+		uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_DE_SCALE, beta, unused);
+		propose_de(cur, prop, P, d.hist + ((size_t)c * k.H + i) * P, d.hist + ((size_t)c * k.H + j) * P, beta, z, w[P + 0]);
+	} else {
+		propose_fisher(cur, prop, P, d.fvals + (size_t)c * P, d.fvecs + (size_t)c * P * P, T, u_pick, z, w[P + 2]);
+	}
+	d.lpprop[c] = standard_log_prior(prior, pp, prop);
+	d.info[c] = type | (sel << 8);
+}
+
+__global__ void k_accept(DevState d, StepConst k, long long step, int c0, int n, long long cold_row)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const int c = c0 + t, P = k.P;
+	const double T = d.temps[c];
+	double alpha, u_acc;
+	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u_acc);
+	const int type = d.info[c] & 0xff, sel = d.info[c] >> 8;
+	double *cur = d.pos + (size_t)c * P;
+	const bool acc = mh_accept(d.ll[c], d.llprop[c], d.lp[c], d.lpprop[c], T, u_acc);
+	long long *ct = d.counters + (size_t)c * NCT;
+	if (acc) {
+		const double *prop = d.prop + (size_t)c * P;
+		for (int i = 0; i < P; i++) cur[i] = prop[i];
+		d.ll[c] = d.llprop[c];
+		d.lp[c] = d.lpprop[c];
+	}
+	ct[acc ? GWAT_B200_CT_STEP_ACCEPT : GWAT_B200_CT_STEP_REJECT] += 1;
+	if (type == STEP_GAUSS) {  // assign_ct_p / assign_ct_m (:2992-3015)
+		ct[acc ? GWAT_B200_CT_GAUSS_ACCEPT : GWAT_B200_CT_GAUSS_REJECT] += 1;
+		d.gauss_ct[((size_t)c * P + sel) * 4 + (acc ? 0 : 1)] += 1;
+	} else if (type == STEP_DE) {
+		ct[acc ? GWAT_B200_CT_DE_ACCEPT : GWAT_B200_CT_DE_REJECT] += 1;
+	} else {
+		ct[acc ? GWAT_B200_CT_FISHER_ACCEPT : GWAT_B200_CT_FISHER_REJECT] += 1;
+	}
+	// PTMCMC_MH_step_incremental (src/mcmc_sampler.cpp:4603-4642), chain_pos = step + 1 from here on
+	const long long chain_pos = step + 1;
+	const bool primed = step > k.H;
+	if (!primed || chain_pos % k.history_update == 0) {  // update_history (:2198-2219)
+		int hp = d.hist_pos[c];
+		hp = (hp < k.H - 1) ? hp + 1 : 0;
+		d.hist_pos[c] = hp;
+		double *h = d.hist + ((size_t)c * k.H + hp) * P;
+		for (int i = 0; i < P; i++) h[i] = cur[i];
+	}
+	if (chain_pos % k.check_stepsize_freq == 0) {  // update_step_widths (:1623-1703)
+		double bounds[4];
+		step_boundaries(T, k.fisher_exist != 0, primed, bounds);
+		const double p_gauss = bounds[0], p_de = bounds[1] - bounds[0], p_fisher = bounds[3] - bounds[2];
+		const double lo = .2, hi = .60 - .2 / T;  // :1953-1954
+		double *w = d.widths + (size_t)c * (P + 3);
+		if (p_gauss != 0) {
+			for (int i = 0; i < P; i++) {
+				int *g = d.gauss_ct + ((size_t)c * P + i) * 4;
+				w[i] = tuned_width(w[i], g[0] - g[2], g[1] - g[3], lo, hi);
+				g[2] = g[0];
+				g[3] = g[1];
+			}
+		}
+		long long *tl = d.type_last + (size_t)c * 4;
+		if (p_de != 0) {
+			w[P + 0] = tuned_width(w[P + 0], ct[GWAT_B200_CT_DE_ACCEPT] - tl[0], ct[GWAT_B200_CT_DE_REJECT] - tl[1], lo, hi);
+			tl[0] = ct[GWAT_B200_CT_DE_ACCEPT];
+			tl[1] = ct[GWAT_B200_CT_DE_REJECT];
+		}
+		if (p_fisher != 0) {
+			w[P + 2] = tuned_width(w[P + 2], ct[GWAT_B200_CT_FISHER_ACCEPT] - tl[2], ct[GWAT_B200_CT_FISHER_REJECT] - tl[3], lo, hi);
+			tl[2] = ct[GWAT_B200_CT_FISHER_ACCEPT];
+			tl[3] = ct[GWAT_B200_CT_FISHER_REJECT];
+		}
+	}
+	if (k.record_cold && d.cold_slot[c] >= 0 && cold_row >= 0) {
+		double *o = d.cold + ((size_t)cold_row + d.cold_slot[c]) * P;
+		for (int i = 0; i < P; i++) o[i] = cur[i];
+	}
+}
+
+// ---- Fisher refresh --------------------------------------------------------------------------------------------------------
+__global__ void k_gather(const double *__restrict__ pos, const int *__restrict__ idx, int n, int P, double *__restrict__ out)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n * P) return;
+	out[t] = pos[(size_t)idx[t / P] * P + t % P];
+}
+// transformations + eigen-system; idx == nullptr: write to slot t (the stand-alone entry point)
+__global__ void k_fisher_eigen(double *__restrict__ F, const double *__restrict__ params, const int *__restrict__ idx, int n, int P,
+                               int pv2, int alpha_unit_fix, int ppE_Nmod, double *__restrict__ fvals, double *__restrict__ fvecs,
+                               long long *__restrict__ counters)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	double *A = F + (size_t)t * P * P;
+	fisher_transformations(A, P, pv2 != 0, alpha_unit_fix != 0, ppE_Nmod, params + (size_t)t * P);
+	double work[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM], vals[GWAT_B200_MAX_DIM], vecs[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM];
+	for (int i = 0; i < P * P; i++) work[i] = A[i];
+	const bool ok = jacobi_eigen(work, P, vals, vecs);
+	const int c = idx ? idx[t] : t;
+	if (ok) {
+		for (int i = 0; i < P; i++) fvals[(size_t)c * P + i] = vals[i];
+		for (int i = 0; i < P * P; i++) fvecs[(size_t)c * P * P + i] = vecs[i];
+	}
+	if (counters) counters[(size_t)c * NCT + (ok ? GWAT_B200_CT_FISHER_UPDATES : GWAT_B200_CT_FISHER_NAN)] += 1;
+}
+
+// ---- swap sweep --------------------------------------------------------------------------------------------------------------
+// Pair i = (slot i, slot i+1).  The reference accepts when !(exp((l1-l2)/T2 - (l1-l2)/T1) < alpha); with l2 = ll[i+1] fixed
+// that is a threshold on l1 (the likelihood of whatever state sits in slot i when the sweep arrives), computed here for
+// all pairs at once so that the sequential part is one comparison per pair.
+//   kind 0: never swap (equal temperatures), 1: swap iff l1 >= thr, 2: swap iff l1 <= thr, 3: always swap
+__global__ void k_swap_prepare(const double *__restrict__ ll, const double *__restrict__ temps, uint64_t seed, long long sweep, int C,
+                               double *__restrict__ thr, int *__restrict__ kind)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= C - 1) return;
+	const double T1 = temps[i], T2 = temps[i + 1];
+	double alpha, unused;
+	uniform2(seed, (uint64_t)sweep, (uint32_t)i, DRAW_SWAP, alpha, unused);
+	if (T1 == T2) {
+		kind[i] = 0;
+		thr[i] = 0;
+		return;
+	}
+	const double g = 1. / T2 - 1. / T1;  // (l1-l2) * g >= ln(alpha)
+	const double la = log(alpha);        // alpha = 0 -> -inf -> always
+	if (g == 0 || la == -INFINITY) {
+		kind[i] = (la <= 0) ? 3 : 0;
+		thr[i] = 0;
+	} else if (g > 0) {
+		kind[i] = 1;
+		thr[i] = ll[i + 1] + la / g;
+	} else {
+		kind[i] = 2;
+		thr[i] = ll[i + 1] + la / g;
+	}
+}
+// src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118)
+__global__ void k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
+                            int *__restrict__ src, long long *__restrict__ counters)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	double carry = ll[0];
+	int carry_src = 0;
+	for (int i = 0; i < C - 1; i++) {
+		const int kd = kind[i];
+		const double th = thr[i];
+		const bool sw = (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
+		if (sw) {
+			src[i] = i + 1;  // slot i receives the untouched state of slot i+1; the carried state moves on to slot i+1
+		} else {
+			src[i] = carry_src;
+			carry = ll[i + 1];
+			carry_src = i + 1;
+		}
+		const int which = sw ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
+		counters[(size_t)i * NCT + which] += 1;
+		counters[(size_t)(i + 1) * NCT + which] += 1;
+	}
+	src[C - 1] = carry_src;
+}
+__global__ void k_swap_apply(const int *__restrict__ src, int C, int P, const double *__restrict__ pos, const double *__restrict__ ll,
+                             const double *__restrict__ lp, double *__restrict__ pos2, double *__restrict__ ll2, double *__restrict__ lp2)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= C * P) return;
+	const int c = t / P, i = t % P, s = src[c];
+	pos2[t] = pos[(size_t)s * P + i];
+	if (i == 0) {
+		ll2[c] = ll[s];
+		lp2[c] = lp[s];
+	}
+}
+
+__global__ void k_prior(const double *__restrict__ params, int W, gwat_b200_prior prior, PriorPlan pp, double *__restrict__ out)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	out[w] = standard_log_prior(prior, pp, params + (size_t)w * pp.dimension);
+}
+
+#define SCUDA(ctx, expr)                                                                                        \
+	do {                                                                                                          \
+		cudaError_t e_ = (expr);                                                                                    \
+		if (e_ != cudaSuccess)                                                                                      \
+			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+template <class T>
+cudaError_t dalloc(T *&p, size_t n)
+{
+	return cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+// model layout: which prior, where the modifications start
+int make_prior_plan(const char *method, const gwat_b200_mod *mod, int dimension, PriorPlan &pp, MethodDesc &desc, bool &alpha_fix,
+                    int &ppE_Nmod)
+{
+	if (parse_method(method, desc) != 0 || desc.mcmc) return -1;
+	const int tidal_love = mod ? mod->tidal_love : 1;
+	int base = desc.pv2 ? 15 : 11;
+	if (desc.nrt) base += tidal_love ? 1 : 2;
+	if (dimension < base || dimension > GWAT_B200_MAX_DIM) return -2;
+	pp.pv2 = desc.pv2;
+	pp.nrt = desc.nrt;
+	pp.tidal_love = tidal_love;
+	pp.dimension = dimension;
+	pp.first_mod = base;
+	alpha_fix = (desc.theory == THEORY_DCS || desc.theory == THEORY_EDGB);
+	ppE_Nmod = mod ? mod->ppE_Nmod : 0;
+	return 0;
+}
+
+}  // namespace
+
+struct gwat_b200_sampler {
+	gwat_b200_ctx *ctx = nullptr;
+	std::string method;
+	gwat_b200_mod mod;
+	gwat_b200_sampler_options opt;
+	gwat_b200_prior prior;
+	PriorPlan pp;
+	MethodDesc desc;
+	bool alpha_fix = false;
+	int ppE_Nmod = 0;
+	double gmst = 0, T_segment = 0;
+	StepConst k;
+	DevState d{};
+	double *pos2 = nullptr, *ll2 = nullptr, *lp2 = nullptr;  // swap double buffers
+	double *swap_thr = nullptr;
+	int *swap_kind = nullptr, *swap_src = nullptr;
+	// Fisher refresh scratch
+	int *d_fidx = nullptr;
+	double *d_fparams = nullptr, *d_fmat = nullptr;
+	int *h_fidx = nullptr;  // pinned, one slice per (step in flight, lane)
+	size_t h_fidx_cap = 0;
+	int nlanes = 1, lane_c0[2] = {0, 0}, lane_n[2] = {0, 0};
+	cudaStream_t st[2] = {nullptr, nullptr};
+	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_join = nullptr, ev_fisher = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	bool fisher_pending = false;
+	// host mirror of the schedule
+	std::vector<double> h_temps;
+	std::vector<int> h_fisher_ct;
+	long long step = 0, sweep = 0;
+	int since_swap = 0;
+	int n_cold = 0;
+	long long cold_cap = 0;
+	double last_ms = 0;
+	long long last_launches = 0;
+};
+
+namespace {
+
+int ensure_cold(gwat_b200_sampler *s, long long steps_total)
+{
+	if (!s->opt.record_cold || s->n_cold == 0 || steps_total <= s->cold_cap) return 0;
+	long long cap = std::max<long long>(steps_total, s->cold_cap * 2);
+	double *p = nullptr;
+	const size_t row = (size_t)s->n_cold * s->k.P;
+	SCUDA(s->ctx, dalloc(p, (size_t)cap * row));
+	if (s->d.cold && s->step > 0)
+		SCUDA(s->ctx, cudaMemcpy(p, s->d.cold, (size_t)s->step * row * sizeof(double), cudaMemcpyDeviceToDevice));
+	cudaFree(s->d.cold);
+	s->d.cold = p;
+	s->cold_cap = cap;
+	return 0;
+}
+
+// chains of lane `ln` whose Fisher eigen-system is refreshed before step `step` (fisher_step, :434-437 and :627)
+void fisher_schedule(gwat_b200_sampler *s, int ln, long long step, std::vector<int> &flagged)
+{
+	flagged.clear();
+	if (!s->opt.fisher_exist) return;
+	const bool primed = step > s->k.H;
+	for (int c = s->lane_c0[ln]; c < s->lane_c0[ln] + s->lane_n[ln]; c++) {
+		double bounds[4], alpha, u;
+		step_boundaries(s->h_temps[c], true, primed, bounds);
+		uniform2(s->k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u);
+		if (step_type(alpha, bounds) != STEP_FISHER) continue;
+		if (s->h_fisher_ct[c] == s->opt.fisher_update_number) {
+			flagged.push_back(c);
+			s->h_fisher_ct[c] = 0;
+		}
+		s->h_fisher_ct[c] += 1;
+	}
+}
+
+int fisher_refresh(gwat_b200_sampler *s, int ln, const std::vector<int> &flagged, int *h_slice)
+{
+	gwat_b200_ctx *ctx = s->ctx;
+	const int n = (int)flagged.size(), P = s->k.P;
+	cudaStream_t st = s->st[ln];
+	std::memcpy(h_slice, flagged.data(), sizeof(int) * n);
+	int *d_idx = s->d_fidx + s->lane_c0[ln];
+	double *d_par = s->d_fparams + (size_t)s->lane_c0[ln] * P;
+	double *d_mat = s->d_fmat + (size_t)s->lane_c0[ln] * P * P;
+	// the engine's Fisher scratch is shared by both lanes: passes are ordered through ev_fisher
+	if (s->fisher_pending) SCUDA(ctx, cudaStreamWaitEvent(st, s->ev_fisher, 0));
+	SCUDA(ctx, cudaMemcpyAsync(d_idx, h_slice, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+	k_gather<<<(n * P + 255) / 256, 256, 0, st>>>(s->d.pos, d_idx, n, P, d_par);
+	if (int rc = gwat_internal::fisher_mcmc_dev(ctx, s->method.c_str(), &s->mod, P, s->opt.fisher_deriv_order, n, d_par, s->gmst, d_mat, st))
+		return rc;
+	k_fisher_eigen<<<(n + 31) / 32, 32, 0, st>>>(d_mat, d_par, d_idx, n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, s->d.fvals,
+	                                             s->d.fvecs, s->d.counters);
+	SCUDA(ctx, cudaEventRecord(s->ev_fisher, st));
+	s->fisher_pending = true;
+	s->last_launches += 2;
+	return 0;
+}
+
+int swap_sweep(gwat_b200_sampler *s)
+{
+	gwat_b200_ctx *ctx = s->ctx;
+	const int C = s->k.C, P = s->k.P;
+	cudaStream_t st = s->st[0];
+	// join: lane 1 -> lane 0
+	if (s->nlanes > 1) {
+		SCUDA(ctx, cudaEventRecord(s->ev_lane[1], s->st[1]));
+		SCUDA(ctx, cudaStreamWaitEvent(st, s->ev_lane[1], 0));
+	}
+	double gate, unused;
+	uniform2(s->k.seed, (uint64_t)s->sweep, 0u, DRAW_SWAP_GATE, gate, unused);
+	if (gate < s->opt.swap_rate && C > 1) {  // src/mcmc_sampler.cpp:4646-4654
+		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->swap_thr, s->swap_kind);
+		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->d.counters);
+		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
+		std::swap(s->d.pos, s->pos2);
+		std::swap(s->d.ll, s->ll2);
+		std::swap(s->d.lp, s->lp2);
+		s->last_launches += 3;
+	}
+	s->sweep += 1;
+	if (s->nlanes > 1) {
+		SCUDA(ctx, cudaEventRecord(s->ev_join, st));
+		SCUDA(ctx, cudaStreamWaitEvent(s->st[1], s->ev_join, 0));
+	}
+	SCUDA(ctx, cudaGetLastError());
+	return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gwat_b200_prior_init(gwat_b200_prior *p)
+{
+	if (!p) return;
+	std::memset(p, 0, sizeof(*p));
+	const double big = 1e300;
+	auto open = [&](double *b) { b[0] = -big; b[1] = big; };
+	open(p->mass1_prior); open(p->mass2_prior); open(p->spin1_prior); open(p->spin2_prior); open(p->a1_prior); open(p->a2_prior);
+	open(p->ctheta1_prior); open(p->ctheta2_prior); open(p->phi1_prior); open(p->phi2_prior); open(p->tidal1_prior);
+	open(p->tidal2_prior); open(p->tidal_s_prior); open(p->RA_bounds); open(p->sinDEC_bounds); open(p->DL_prior);
+	for (int i = 0; i < GWAT_B200_MAX_MOD; i++) open(p->mod_priors[i]);
+	p->T_merger = 0;
+	p->tidal_love = 1;
+}
+
+void gwat_b200_sampler_options_init(gwat_b200_sampler_options *o)
+{
+	if (!o) return;
+	std::memset(o, 0, sizeof(*o));
+	o->swp_freq = 5;
+	o->swap_rate = 1. / o->swp_freq;
+	o->history_length = 1000;
+	o->history_update = 10;
+	o->fisher_exist = 1;
+	o->fisher_update_number = 200;
+	o->fisher_deriv_order = 4;
+	o->check_stepsize_freq = 50;
+	o->seed = 1;
+	o->lanes = 2;
+}
+
+int gwat_b200_log_prior_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                              const gwat_b200_prior *prior, const double *params, double *logP)
+{
+	if (!ctx || !prior || W < 0 || (W > 0 && (!params || !logP))) return GWAT_B200_ERR_ARG;
+	if (W == 0) return GWAT_B200_OK;
+	PriorPlan pp;
+	MethodDesc desc;
+	bool af;
+	int nm;
+	if (int rc = make_prior_plan(method, mod, dimension, pp, desc, af, nm))
+		return gwat_internal::set_error(ctx, rc == -1 ? GWAT_B200_ERR_METHOD : GWAT_B200_ERR_ARG, "log_prior_batch: unknown method or dimension too small for it");
+	gwat_b200_prior pd = *prior;
+	pd.tidal_love = pp.tidal_love;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	double *d_par = nullptr, *d_out = nullptr;
+	SCUDA(ctx, dalloc(d_par, (size_t)W * dimension));
+	SCUDA(ctx, dalloc(d_out, (size_t)W));
+	SCUDA(ctx, cudaMemcpyAsync(d_par, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, ctx->stream));
+	k_prior<<<(W + 127) / 128, 128, 0, ctx->stream>>>(d_par, W, pd, pp, d_out);
+	ctx->launches += 1;
+	SCUDA(ctx, cudaMemcpyAsync(logP, d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+	SCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_par);
+	cudaFree(d_out);
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int W,
+                                const double *params, double gmst, double *fisher, double *eigenvalues, double *eigenvectors)
+{
+	if (!ctx || W < 0 || (W > 0 && !params)) return GWAT_B200_ERR_ARG;
+	if (W == 0) return GWAT_B200_OK;
+	PriorPlan pp;
+	MethodDesc desc;
+	bool af;
+	int nm;
+	if (int rc = make_prior_plan(method, mod, dimension, pp, desc, af, nm))
+		return gwat_internal::set_error(ctx, rc == -1 ? GWAT_B200_ERR_METHOD : GWAT_B200_ERR_ARG, "mcmc_fisher_batch: unknown method or dimension too small for it");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const int P = dimension;
+	double *d_par = nullptr, *d_mat = nullptr, *d_vals = nullptr, *d_vecs = nullptr;
+	SCUDA(ctx, dalloc(d_par, (size_t)W * P));
+	SCUDA(ctx, dalloc(d_mat, (size_t)W * P * P));
+	SCUDA(ctx, dalloc(d_vals, (size_t)W * P));
+	SCUDA(ctx, dalloc(d_vecs, (size_t)W * P * P));
+	cudaStream_t st = ctx->stream;
+	SCUDA(ctx, cudaMemcpyAsync(d_par, params, sizeof(double) * W * P, cudaMemcpyHostToDevice, st));
+	int rc = gwat_internal::fisher_mcmc_dev(ctx, method, mod, P, order, W, d_par, gmst, d_mat, st);
+	if (rc == 0) {
+		SCUDA(ctx, cudaMemsetAsync(d_vals, 0xff, sizeof(double) * W * P, st));  // NaN where the decomposition fails
+		SCUDA(ctx, cudaMemsetAsync(d_vecs, 0xff, sizeof(double) * W * P * P, st));
+		k_fisher_eigen<<<(W + 31) / 32, 32, 0, st>>>(d_mat, d_par, nullptr, W, P, pp.pv2, af ? 1 : 0, nm, d_vals, d_vecs, nullptr);
+		ctx->launches += 1;
+		if (fisher) SCUDA(ctx, cudaMemcpyAsync(fisher, d_mat, sizeof(double) * W * P * P, cudaMemcpyDeviceToHost, st));
+		if (eigenvalues) SCUDA(ctx, cudaMemcpyAsync(eigenvalues, d_vals, sizeof(double) * W * P, cudaMemcpyDeviceToHost, st));
+		if (eigenvectors) SCUDA(ctx, cudaMemcpyAsync(eigenvectors, d_vecs, sizeof(double) * W * P * P, cudaMemcpyDeviceToHost, st));
+		SCUDA(ctx, cudaStreamSynchronize(st));
+	}
+	cudaFree(d_par);
+	cudaFree(d_mat);
+	cudaFree(d_vals);
+	cudaFree(d_vecs);
+	return rc;
+}
+
+void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
+{
+	if (!s) return;
+	cudaSetDevice(s->ctx->device);
+	for (int i = 0; i < 2; i++)
+		if (s->st[i]) cudaStreamSynchronize(s->st[i]);
+	DevState &d = s->d;
+	void *ptrs[] = {d.pos, d.prop, d.ll, d.lp, d.llprop, d.lpprop, d.temps, d.hist, d.hist_pos, d.fvals, d.fvecs, d.widths, d.counters,
+	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src,
+	                s->d_fidx, s->d_fparams, s->d_fmat};
+	for (void *p : ptrs) cudaFree(p);
+	if (s->h_fidx) cudaFreeHost(s->h_fidx);
+	for (int i = 0; i < 2; i++) {
+		if (s->ev_lane[i]) cudaEventDestroy(s->ev_lane[i]);
+		if (s->st[i]) cudaStreamDestroy(s->st[i]);
+	}
+	for (cudaEvent_t e : {s->ev_join, s->ev_fisher, s->ev_t0, s->ev_t1})
+		if (e) cudaEventDestroy(e);
+	delete s;
+}
+
+int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, const gwat_b200_sampler_options *options,
+                             const gwat_b200_prior *prior, const double *chain_temps, const double *initial_positions, double gmst,
+                             double T_segment, gwat_b200_sampler **out)
+{
+	if (!ctx || !out || !options || !prior || !chain_temps || !initial_positions) return GWAT_B200_ERR_ARG;
+	*out = nullptr;
+	const gwat_b200_sampler_options &o = *options;
+	if (o.chain_N < 1 || o.swp_freq < 1 || o.history_length < 2 || o.history_update < 1 || o.check_stepsize_freq < 1 ||
+	    o.fisher_update_number < 1 || (o.fisher_deriv_order != 2 && o.fisher_deriv_order != 4))
+		return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_create: invalid options");
+	gwat_b200_sampler *s = new gwat_b200_sampler;
+	s->ctx = ctx;
+	s->method = method ? method : "";
+	if (mod) s->mod = *mod;
+	else gwat_b200_mod_init(&s->mod);
+	s->opt = o;
+	s->prior = *prior;
+	if (int rc = make_prior_plan(method, &s->mod, o.dimension, s->pp, s->desc, s->alpha_fix, s->ppE_Nmod)) {
+		delete s;
+		return gwat_internal::set_error(ctx, rc == -1 ? GWAT_B200_ERR_METHOD : GWAT_B200_ERR_ARG,
+		                                "sampler_create: unknown generation_method, or dimension does not fit it");
+	}
+	s->prior.tidal_love = s->pp.tidal_love;
+	s->gmst = gmst;
+	s->T_segment = T_segment;
+	const int C = o.chain_N, P = o.dimension, H = o.history_length;
+	s->k = StepConst{o.seed, C, P, H, o.history_update, o.check_stepsize_freq, o.fisher_exist, o.record_cold};
+	s->nlanes = (o.lanes >= 2 && C >= 2) ? 2 : 1;
+	s->lane_c0[0] = 0;
+	s->lane_n[0] = s->nlanes == 2 ? C / 2 : C;
+	s->lane_c0[1] = s->lane_n[0];
+	s->lane_n[1] = C - s->lane_n[0];
+	s->h_temps.assign(chain_temps, chain_temps + C);
+	s->h_fisher_ct.assign(C, o.fisher_update_number);  // :2011
+	std::vector<int> cold_slot(C, -1);
+	for (int c = 0; c < C; c++)
+		if (chain_temps[c] == 1.0) cold_slot[c] = s->n_cold++;
+
+	std::unique_lock<std::mutex> lock(ctx->mu);
+	auto bail = [&](int rc) {
+		lock.unlock();
+		gwat_b200_sampler_destroy(s);
+		return rc;
+	};
+#define SC_TRY(expr)                                                                                                       \
+	do {                                                                                                                     \
+		cudaError_t e_ = (expr);                                                                                               \
+		if (e_ != cudaSuccess)                                                                                                 \
+			return bail(gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_))); \
+	} while (0)
+	SC_TRY(cudaSetDevice(ctx->device));
+	DevState &d = s->d;
+	SC_TRY(dalloc(d.pos, (size_t)C * P));
+	SC_TRY(dalloc(d.prop, (size_t)C * P));
+	SC_TRY(dalloc(s->pos2, (size_t)C * P));
+	for (double **p : {&d.ll, &d.lp, &d.llprop, &d.lpprop, &d.temps, &s->ll2, &s->lp2, &s->swap_thr}) SC_TRY(dalloc(*p, (size_t)C));
+	SC_TRY(dalloc(d.hist, (size_t)C * H * P));
+	SC_TRY(dalloc(d.hist_pos, (size_t)C));
+	SC_TRY(dalloc(d.fvals, (size_t)C * P));
+	SC_TRY(dalloc(d.fvecs, (size_t)C * P * P));
+	SC_TRY(dalloc(d.widths, (size_t)C * (P + 3)));
+	SC_TRY(dalloc(d.counters, (size_t)C * NCT));
+	SC_TRY(dalloc(d.gauss_ct, (size_t)C * P * 4));
+	SC_TRY(dalloc(d.type_last, (size_t)C * 4));
+	SC_TRY(dalloc(d.info, (size_t)C));
+	SC_TRY(dalloc(d.cold_slot, (size_t)C));
+	SC_TRY(dalloc(s->swap_kind, (size_t)C));
+	SC_TRY(dalloc(s->swap_src, (size_t)C));
+	SC_TRY(dalloc(s->d_fidx, (size_t)C));
+	SC_TRY(dalloc(s->d_fparams, (size_t)C * P));
+	SC_TRY(dalloc(s->d_fmat, (size_t)C * P * P));
+	for (int i = 0; i < s->nlanes; i++) {
+		SC_TRY(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
+		SC_TRY(cudaEventCreateWithFlags(&s->ev_lane[i], cudaEventDisableTiming));
+	}
+	SC_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+	SC_TRY(cudaEventCreateWithFlags(&s->ev_fisher, cudaEventDisableTiming));
+	SC_TRY(cudaEventCreate(&s->ev_t0));
+	SC_TRY(cudaEventCreate(&s->ev_t1));
+	cudaStream_t st = s->st[0];
+	SC_TRY(cudaMemcpyAsync(d.pos, initial_positions, sizeof(double) * C * P, cudaMemcpyHostToDevice, st));
+	SC_TRY(cudaMemcpyAsync(d.temps, chain_temps, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+	SC_TRY(cudaMemcpyAsync(d.cold_slot, cold_slot.data(), sizeof(int) * C, cudaMemcpyHostToDevice, st));
+	k_init<<<(C + 127) / 128, 128, 0, st>>>(d, s->k, s->prior, s->pp);
+	if (int rc = gwat_internal::loglike_mcmc_lane(ctx, 1, s->method.c_str(), &s->mod, P, C, d.pos, gmst, T_segment, d.ll, st)) return bail(rc);
+	SC_TRY(cudaStreamSynchronize(st));
+	std::vector<double> lp(C), ll(C);
+	SC_TRY(cudaMemcpy(lp.data(), d.lp, sizeof(double) * C, cudaMemcpyDeviceToHost));
+	SC_TRY(cudaMemcpy(ll.data(), d.ll, sizeof(double) * C, cudaMemcpyDeviceToHost));
+	for (int c = 0; c < C; c++)
+		if (!(lp[c] > -INFINITY) || !(ll[c] == ll[c]))
+			return bail(gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_create: initial position of chain " + std::to_string(c) +
+			                                                                 " has zero prior or an undefined likelihood"));
+#undef SC_TRY
+	lock.unlock();
+	*out = s;
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
+{
+	if (!s || n_steps < 0) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	if (int rc = ensure_cold(s, s->step + n_steps)) return rc;
+	const int P = s->k.P;
+	const long long launches0 = ctx->launches;
+	s->last_launches = 0;
+	// pinned staging for the Fisher index lists: one slice per (step, lane) of this call, so no slice is rewritten while
+	// an earlier asynchronous copy may still read it
+	std::vector<std::vector<int>> flagged_all;
+	if (s->opt.fisher_exist) {
+		const size_t need = (size_t)s->k.C * 8;  // grown below if a call flags more (bounded by C per step)
+		if (s->h_fidx_cap < need) {
+			if (s->h_fidx) cudaFreeHost(s->h_fidx);
+			SCUDA(ctx, cudaMallocHost((void **)&s->h_fidx, need * sizeof(int)));
+			s->h_fidx_cap = need;
+		}
+	}
+	size_t h_used = 0;
+	SCUDA(ctx, cudaEventRecord(s->ev_t0, s->st[0]));
+	if (s->nlanes > 1) {
+		SCUDA(ctx, cudaEventRecord(s->ev_join, s->st[0]));
+		SCUDA(ctx, cudaStreamWaitEvent(s->st[1], s->ev_join, 0));
+	}
+	std::vector<int> flagged;
+	for (int it = 0; it < n_steps; it++) {
+		const long long step = s->step;
+		const long long cold_row = (s->opt.record_cold && s->n_cold) ? step * s->n_cold : -1;
+		for (int ln = 0; ln < s->nlanes; ln++) {
+			const int c0 = s->lane_c0[ln], n = s->lane_n[ln];
+			if (n == 0) continue;
+			cudaStream_t st = s->st[ln];
+			fisher_schedule(s, ln, step, flagged);
+			if (!flagged.empty()) {
+				if (h_used + flagged.size() > s->h_fidx_cap) {
+					// staging exhausted: drain the streams, then reuse it from the start
+					for (int i = 0; i < s->nlanes; i++) SCUDA(ctx, cudaStreamSynchronize(s->st[i]));
+					h_used = 0;
+				}
+				if (int rc = fisher_refresh(s, ln, flagged, s->h_fidx + h_used)) return rc;
+				h_used += flagged.size();
+			}
+			k_propose<<<(n + 63) / 64, 64, 0, st>>>(s->d, s->k, s->prior, s->pp, step, c0, n);
+			if (int rc = gwat_internal::loglike_mcmc_lane(ctx, 1 + ln, s->method.c_str(), &s->mod, P, n, s->d.prop + (size_t)c0 * P, s->gmst,
+			                                              s->T_segment, s->d.llprop + c0, st))
+				return rc;
+			k_accept<<<(n + 63) / 64, 64, 0, st>>>(s->d, s->k, step, c0, n, cold_row);
+			s->last_launches += 2;
+		}
+		s->step += 1;
+		s->since_swap += 1;
+		if (s->since_swap == s->opt.swp_freq) {
+			if (int rc = swap_sweep(s)) return rc;
+			s->since_swap = 0;
+		}
+	}
+	if (s->nlanes > 1) {
+		SCUDA(ctx, cudaEventRecord(s->ev_lane[1], s->st[1]));
+		SCUDA(ctx, cudaStreamWaitEvent(s->st[0], s->ev_lane[1], 0));
+	}
+	SCUDA(ctx, cudaEventRecord(s->ev_t1, s->st[0]));
+	SCUDA(ctx, cudaStreamSynchronize(s->st[0]));
+	SCUDA(ctx, cudaGetLastError());
+	float ms = 0;
+	SCUDA(ctx, cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+	s->last_ms = ms;
+	s->last_launches += ctx->launches - launches0;
+	s->fisher_pending = false;
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_state(gwat_b200_sampler *s, double *positions, double *logL, double *logP)
+{
+	if (!s) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const int C = s->k.C, P = s->k.P;
+	if (positions) SCUDA(ctx, cudaMemcpy(positions, s->d.pos, sizeof(double) * C * P, cudaMemcpyDeviceToHost));
+	if (logL) SCUDA(ctx, cudaMemcpy(logL, s->d.ll, sizeof(double) * C, cudaMemcpyDeviceToHost));
+	if (logP) SCUDA(ctx, cudaMemcpy(logP, s->d.lp, sizeof(double) * C, cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_counters(gwat_b200_sampler *s, long long *counters, double *widths)
+{
+	if (!s) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const int C = s->k.C, P = s->k.P;
+	if (counters) SCUDA(ctx, cudaMemcpy(counters, s->d.counters, sizeof(long long) * C * NCT, cudaMemcpyDeviceToHost));
+	if (widths) SCUDA(ctx, cudaMemcpy(widths, s->d.widths, sizeof(double) * C * (P + 3), cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_fisher_state(gwat_b200_sampler *s, double *eigenvalues, double *eigenvectors)
+{
+	if (!s) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const int C = s->k.C, P = s->k.P;
+	if (eigenvalues) SCUDA(ctx, cudaMemcpy(eigenvalues, s->d.fvals, sizeof(double) * C * P, cudaMemcpyDeviceToHost));
+	if (eigenvectors) SCUDA(ctx, cudaMemcpy(eigenvectors, s->d.fvecs, sizeof(double) * C * P * P, cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_cold(gwat_b200_sampler *s, long long first_step, int n, double *out, int *n_cold)
+{
+	if (!s) return GWAT_B200_ERR_ARG;
+	if (n_cold) *n_cold = s->n_cold;
+	if (!out) return GWAT_B200_OK;
+	gwat_b200_ctx *ctx = s->ctx;
+	if (!s->opt.record_cold) return gwat_internal::set_error(ctx, GWAT_B200_ERR_STATE, "sampler_cold: the sampler was created without record_cold");
+	if (first_step < 0 || n < 0 || first_step + n > s->step) return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_cold: step range not recorded");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t row = (size_t)s->n_cold * s->k.P;
+	if (n > 0 && row > 0)
+		SCUDA(ctx, cudaMemcpy(out, s->d.cold + (size_t)first_step * row, sizeof(double) * n * row, cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+double gwat_b200_sampler_last_ms(const gwat_b200_sampler *s) { return s ? s->last_ms : 0; }
+long long gwat_b200_sampler_last_launches(const gwat_b200_sampler *s) { return s ? s->last_launches : 0; }
+
+}  // extern "C"

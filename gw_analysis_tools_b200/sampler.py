@@ -1,0 +1,175 @@
+"""ctypes binding of the device-resident parallel-tempering sampler (``include/gwat_b200_sampler.h``).
+
+Plumbing only, like ``engine.py``: proposals, priors, likelihoods, acceptance and swaps all run in CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .engine import Context, GwatB200Error, _f64, _p  # noqa: F401
+
+_d2 = C.c_double * 2
+
+COUNTERS = ["step_accept", "step_reject", "gauss_accept", "gauss_reject", "de_accept", "de_reject", "fisher_accept",
+            "fisher_reject", "swap_accept", "swap_reject", "fisher_updates", "fisher_nan"]
+
+EXPORTS = [
+    "gwat_b200_prior_init", "gwat_b200_sampler_options_init", "gwat_b200_sampler_create", "gwat_b200_sampler_destroy",
+    "gwat_b200_sampler_run", "gwat_b200_sampler_state", "gwat_b200_sampler_counters", "gwat_b200_sampler_cold",
+    "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
+]
+
+
+class Prior(C.Structure):
+    """``gwat_b200_prior`` = the fields of ``priorData`` (include/gwat/standardPriorLibrary.h:8-35) the standard priors read."""
+
+    _fields_ = [(n, _d2) for n in ("mass1_prior", "mass2_prior", "spin1_prior", "spin2_prior", "a1_prior", "a2_prior", "ctheta1_prior",
+                                   "ctheta2_prior", "phi1_prior", "phi2_prior", "tidal1_prior", "tidal2_prior", "tidal_s_prior",
+                                   "RA_bounds", "sinDEC_bounds", "DL_prior")] + [
+        ("T_merger", C.c_double), ("mod_priors", _d2 * abi.MAX_MOD), ("tidal_love", C.c_int), ("reserved_", C.c_int)]
+
+    def as_dict(self):
+        d = {n: list(getattr(self, n)) for n, t in self._fields_ if t is _d2}
+        d["T_merger"] = self.T_merger
+        d["tidal_love"] = self.tidal_love
+        d["mod_priors"] = [list(r) for r in self.mod_priors]
+        return d
+
+
+class Options(C.Structure):
+    _fields_ = [("chain_N", C.c_int), ("dimension", C.c_int), ("swp_freq", C.c_int), ("swap_rate", C.c_double),
+                ("history_length", C.c_int), ("history_update", C.c_int), ("fisher_exist", C.c_int),
+                ("fisher_update_number", C.c_int), ("fisher_deriv_order", C.c_int), ("check_stepsize_freq", C.c_int),
+                ("seed", C.c_ulonglong), ("lanes", C.c_int), ("record_cold", C.c_int), ("reserved_", C.c_int)]
+
+
+def prior_defaults(**kw):
+    from .engine import load_library
+    p = Prior()
+    load_library().gwat_b200_prior_init(C.byref(p))
+    for k, v in kw.items():
+        cur = getattr(p, k)
+        if k == "mod_priors":
+            for i, (lo, hi) in enumerate(v):
+                cur[i][0], cur[i][1] = lo, hi
+        elif hasattr(cur, "__len__"):
+            cur[0], cur[1] = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def options_defaults(**kw):
+    from .engine import load_library
+    o = Options()
+    load_library().gwat_b200_sampler_options_init(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    if "swp_freq" in kw and "swap_rate" not in kw:
+        o.swap_rate = 1.0 / o.swp_freq  # src/mcmc_sampler.cpp:4316
+    return o
+
+
+def log_prior_batch(ctx, method, params, prior, mod=None):
+    params = _f64(params)
+    W, P = params.shape
+    out = np.empty(W)
+    ctx._check(ctx._lib.gwat_b200_log_prior_batch(ctx._h, method.encode(), C.byref(mod) if mod is not None else None, P, W,
+                                                  C.byref(prior), _p(params), _p(out)))
+    return out
+
+
+def mcmc_fisher_batch(ctx, method, params, gmst, order=4, mod=None):
+    """Fisher matrices as the reference's ``MCMC_fisher_wrapper`` returns them, and their eigen-systems."""
+    params = _f64(params)
+    W, P = params.shape
+    F, vals, vecs = np.empty((W, P, P)), np.empty((W, P)), np.empty((W, P, P))
+    ctx._check(ctx._lib.gwat_b200_mcmc_fisher_batch(ctx._h, method.encode(), C.byref(mod) if mod is not None else None, P, int(order), W,
+                                                    _p(params), C.c_double(gmst), _p(F), _p(vals), _p(vecs)))
+    return F, vals, vecs
+
+
+class Sampler:
+    """All chains of a PTMCMC run, resident on one GPU.  ``ctx`` must already hold the network and the data."""
+
+    def __init__(self, ctx, method, temps, initial_positions, prior, gmst, T_segment, mod=None, **options):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        init = _f64(initial_positions)
+        temps = _f64(temps)
+        self.C, self.P = init.shape
+        assert temps.shape == (self.C,)
+        self.options = options_defaults(chain_N=self.C, dimension=self.P, **options)
+        self._lib.gwat_b200_sampler_last_ms.restype = C.c_double
+        self._lib.gwat_b200_sampler_last_ms.argtypes = [C.c_void_p]
+        self._lib.gwat_b200_sampler_last_launches.restype = C.c_longlong
+        self._lib.gwat_b200_sampler_last_launches.argtypes = [C.c_void_p]
+        self._lib.gwat_b200_sampler_destroy.argtypes = [C.c_void_p]
+        self._lib.gwat_b200_sampler_destroy.restype = None
+        self._h = C.c_void_p()
+        ctx._check(self._lib.gwat_b200_sampler_create(ctx._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                                      C.byref(self.options), C.byref(prior), _p(temps), _p(init), C.c_double(gmst),
+                                                      C.c_double(T_segment), C.byref(self._h)))
+        self.steps = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gwat_b200_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, n_steps):
+        self._ctx._check(self._lib.gwat_b200_sampler_run(self._h, int(n_steps)))
+        self.steps += int(n_steps)
+
+    def state(self):
+        pos, ll, lp = np.empty((self.C, self.P)), np.empty(self.C), np.empty(self.C)
+        self._ctx._check(self._lib.gwat_b200_sampler_state(self._h, _p(pos), _p(ll), _p(lp)))
+        return pos, ll, lp
+
+    def counters(self):
+        ct = np.empty((self.C, len(COUNTERS)), dtype=np.int64)
+        w = np.empty((self.C, self.P + 3))
+        self._ctx._check(self._lib.gwat_b200_sampler_counters(self._h, ct.ctypes.data_as(C.POINTER(C.c_longlong)), _p(w)))
+        return {n: ct[:, i] for i, n in enumerate(COUNTERS)}, w
+
+    def fisher_state(self):
+        vals, vecs = np.empty((self.C, self.P)), np.empty((self.C, self.P, self.P))
+        self._ctx._check(self._lib.gwat_b200_sampler_fisher_state(self._h, _p(vals), _p(vecs)))
+        return vals, vecs
+
+    def cold_chains(self, first_step=0, n=None):
+        nc = C.c_int()
+        self._ctx._check(self._lib.gwat_b200_sampler_cold(self._h, C.c_longlong(0), 0, None, C.byref(nc)))
+        n = self.steps - first_step if n is None else n
+        out = np.empty((n, nc.value, self.P))
+        self._ctx._check(self._lib.gwat_b200_sampler_cold(self._h, C.c_longlong(first_step), int(n), _p(out), C.byref(nc)))
+        return out
+
+    @property
+    def last_ms(self):
+        return self._lib.gwat_b200_sampler_last_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return self._lib.gwat_b200_sampler_last_launches(self._h)
+
+
+def prior_for(wl):
+    """Standard-prior bounds that contain a synthetic workload (``workloads.make``): masses 1-100 Msun (0.5-3 for the
+    neutron-star config), D_L 1 Mpc - 10 Gpc, full spin and angle ranges, tc within 0.1 s of the injected value."""
+    import math
+    ns = "NRT" in wl.method
+    return prior_defaults(
+        mass1_prior=(0.5, 3.0) if ns else (1.0, 100.0), mass2_prior=(0.5, 3.0) if ns else (1.0, 100.0),
+        spin1_prior=(-0.05, 0.05) if ns else (-0.95, 0.95), spin2_prior=(-0.05, 0.05) if ns else (-0.95, 0.95),
+        a1_prior=(0.0, 0.95), a2_prior=(0.0, 0.95), ctheta1_prior=(-1.0, 1.0), ctheta2_prior=(-1.0, 1.0),
+        phi1_prior=(0.0, 2 * math.pi), phi2_prior=(0.0, 2 * math.pi), tidal1_prior=(1.0, 5000.0), tidal2_prior=(1.0, 5000.0),
+        tidal_s_prior=(1.0, 5000.0), RA_bounds=(0.0, 2 * math.pi), sinDEC_bounds=(-1.0, 1.0), DL_prior=(1.0, 10000.0),
+        T_merger=float(wl.inj[5]), tidal_love=1, mod_priors=[(0.0, 50.0)] * abi.MAX_MOD)

@@ -1,0 +1,119 @@
+/* gwat_b200_sampler.h -- the batched parallel-tempering Metropolis-Hastings step on the device (SURVEY.md 8f N1 + N3).
+ *
+ * What it replaces in the reference (one chain per CPU task, one likelihood per callback):
+ *   mcmc_step                 src/mcmc_sampler_internals.cpp:35-146     proposal -> prior -> logL -> MH accept
+ *   gaussian_step             :364-421      one random coordinate, per-dimension widths
+ *   diff_ev_step              :846-977      differential evolution from the chain's own history
+ *   fisher_step/update_fisher :424-629, 643-713   jump along an eigenvector of the Fisher matrix (MCMC_fisher_wrapper,
+ *                                           src/mcmc_gw.cpp:2230-2300, + MCMC_fisher_transformations :2136-2189)
+ *   assign_probabilities      :1196-1364    step-type probabilities from temperature / Fisher / history state (non-RJ)
+ *   update_step_widths        :1623-1703    x0.9 / x1.1 width tuning towards the target acceptance band
+ *   update_history            :2198-2219    ring buffer feeding differential evolution
+ *   chain_swap/single_chain_swap :1086-1184 sequential sweep over adjacent chains, exp((l1-l2)/T2 - (l1-l2)/T1)
+ *   PTMCMC_MH_step_incremental src/mcmc_sampler.cpp:4571-4660 (non-pool loop): swp_freq steps per chain, then one swap sweep
+ *                                           with probability swap_rate
+ *   logPriorStandard_{D,P,D_NRT,P_NRT}[_mod]::eval   src/standardPriorLibrary.cpp:321-526
+ *
+ * Everything runs on the device: positions, likelihoods, histories, Fisher eigen-systems and counters live in HBM; one call
+ * advances every chain by n steps without a host round-trip per step.  The chains are cut into two halves that run on two
+ * CUDA streams, so the latency-bound per-walker setup of one half overlaps the FP64-bound bin kernel of the other.
+ *
+ * Random numbers: Philox4x32-10 keyed by `seed`, counter = (step, chain, purpose) -- every draw is a pure function of
+ * those three, so a run is reproducible for any lane split or GPU count, and tests can replay the draws on the CPU.
+ * (The reference seeds one gsl_rng per chain with chain+1, :1939; bit-identical streams are neither possible nor needed.)
+ *
+ * Not built (outside this path): RJMCMC / nested models, KDE and MMALA proposals, block sampling, dynamic temperature
+ * allocation, the thread-pool scheduler, checkpoint files.
+ */
+#ifndef GWAT_B200_SAMPLER_H
+#define GWAT_B200_SAMPLER_H
+
+#include "gwat_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* priorData of include/gwat/standardPriorLibrary.h:8-35 (the fields the standard priors read), [min, max] pairs */
+typedef struct gwat_b200_prior {
+	double mass1_prior[2], mass2_prior[2];
+	double spin1_prior[2], spin2_prior[2];         /* aligned-spin models */
+	double a1_prior[2], a2_prior[2];               /* precessing models: magnitudes, cos tilts, azimuths */
+	double ctheta1_prior[2], ctheta2_prior[2];
+	double phi1_prior[2], phi2_prior[2];
+	double tidal1_prior[2], tidal2_prior[2], tidal_s_prior[2];
+	double RA_bounds[2], sinDEC_bounds[2];
+	double DL_prior[2];
+	double T_merger;                               /* tc must lie within +-0.1 s of it */
+	double mod_priors[GWAT_B200_MAX_MOD][2];       /* ppE / gIMR / theory parameters */
+	int tidal_love;
+	int reserved_;
+} gwat_b200_prior;
+
+typedef struct gwat_b200_sampler_options {
+	int chain_N;                /* total chains (all temperatures, all ensembles), index order = the reference's chain order */
+	int dimension;
+	int swp_freq;               /* steps between swap sweeps */
+	double swap_rate;           /* probability that a sweep happens (the reference sets 1/swp_freq, src/mcmc_sampler.cpp:4316) */
+	int history_length;         /* 1000 */
+	int history_update;         /* 10 */
+	int fisher_exist;           /* 0: Gaussian steps only (the reference never uses DE without a Fisher, :1222-1231) */
+	int fisher_update_number;   /* 200 when tuning, else the run length */
+	int fisher_deriv_order;     /* 4 (include/gwat/mcmc_gw.h:45) */
+	int check_stepsize_freq;    /* 50 when tuning, else the run length */
+	unsigned long long seed;
+	int lanes;                  /* 1 or 2 concurrent halves */
+	int record_cold;            /* keep the positions of the T=1 chains of every step in a device buffer (gwat_b200_sampler_cold) */
+	int reserved_;
+} gwat_b200_sampler_options;
+
+typedef struct gwat_b200_sampler gwat_b200_sampler;
+
+void gwat_b200_prior_init(gwat_b200_prior *p);                    /* wide-open bounds, tidal_love = 1 */
+void gwat_b200_sampler_options_init(gwat_b200_sampler_options *o); /* the reference's defaults listed above */
+
+/* The network (grid, PSDs, data) must already be set on ctx.  chain_temps[chain_N]; initial_positions[chain_N][dimension].
+ * Evaluates prior and likelihood of the initial positions (all must have a finite prior, as assign_initial_pos requires). */
+int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                             const gwat_b200_sampler_options *options, const gwat_b200_prior *prior, const double *chain_temps,
+                             const double *initial_positions, double gmst, double T_segment, gwat_b200_sampler **out);
+void gwat_b200_sampler_destroy(gwat_b200_sampler *s);
+
+/* Advance every chain by n_steps (swap sweeps every swp_freq steps).  Returns when the device has finished. */
+int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps);
+
+/* Current state, any pointer may be NULL: positions[chain_N][dimension], logL[chain_N], logP[chain_N] */
+int gwat_b200_sampler_state(gwat_b200_sampler *s, double *positions, double *logL, double *logP);
+/* counters[chain_N][GWAT_B200_SAMPLER_NCOUNTERS] (see the enum), widths[chain_N][dimension + 3]: Gaussian widths per dimension,
+ * then the DE, (unused) and Fisher widths */
+enum {
+	GWAT_B200_CT_STEP_ACCEPT = 0, GWAT_B200_CT_STEP_REJECT, GWAT_B200_CT_GAUSS_ACCEPT, GWAT_B200_CT_GAUSS_REJECT,
+	GWAT_B200_CT_DE_ACCEPT, GWAT_B200_CT_DE_REJECT, GWAT_B200_CT_FISHER_ACCEPT, GWAT_B200_CT_FISHER_REJECT,
+	GWAT_B200_CT_SWAP_ACCEPT, GWAT_B200_CT_SWAP_REJECT, GWAT_B200_CT_FISHER_UPDATES, GWAT_B200_CT_FISHER_NAN,
+	GWAT_B200_SAMPLER_NCOUNTERS
+};
+int gwat_b200_sampler_counters(gwat_b200_sampler *s, long long *counters, double *widths);
+/* Fisher eigen-systems the chains currently jump along (fisher_vals / fisher_vecs of the reference's sampler struct):
+ * eigenvalues[chain_N][dimension], eigenvectors[chain_N][dimension][dimension], row i = eigenvector i */
+int gwat_b200_sampler_fisher_state(gwat_b200_sampler *s, double *eigenvalues, double *eigenvectors);
+/* With record_cold: positions of the T == 1 chains for steps [first_step, first_step + n) of the steps run so far:
+ * out[n][n_cold][dimension]; returns the number of cold chains through *n_cold when out is NULL. */
+int gwat_b200_sampler_cold(gwat_b200_sampler *s, long long first_step, int n, double *out, int *n_cold);
+/* wall time on the device of the last gwat_b200_sampler_run (CUDA events), and kernels launched by it */
+double gwat_b200_sampler_last_ms(const gwat_b200_sampler *s);
+long long gwat_b200_sampler_last_launches(const gwat_b200_sampler *s);
+
+/* Building blocks, exposed for tests and for callers that keep their own sampler loop:
+ * log prior of W sampling vectors (host arrays) with the standard prior of the method's family */
+int gwat_b200_log_prior_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension, int W,
+                              const gwat_b200_prior *prior, const double *params, double *logP);
+/* Fisher matrices as MCMC_fisher_wrapper returns them (sum over detectors + MCMC_fisher_transformations), then their
+ * eigen-systems: fisher[W][dim][dim], eigenvalues[W][dim] ascending, eigenvectors[W][dim][dim] (row i = i-th vector). */
+int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension,
+                                int order, int W, const double *params, double gmst, double *fisher, double *eigenvalues,
+                                double *eigenvectors);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -297,3 +297,54 @@ extern "C" int hh_loglike(const char *method, int W, const gwat_b200_source *src
 	}
 	return 0;
 }
+
+// ---- sampler mathematics (gwat_sampler_math.h) as plain C++ -----------------------------------------------------------------
+#include "../gw_analysis_tools_b200/csrc/gwat_sampler_math.h"
+
+extern "C" void hh_philox(const unsigned *counter, const unsigned *key, unsigned *out)
+{
+	uint32_t r[4];
+	smp::philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1], r);
+	for (int i = 0; i < 4; i++) out[i] = r[i];
+}
+extern "C" void hh_uniform2(unsigned long long seed, unsigned long long step, unsigned chain, unsigned purpose, double *out)
+{
+	smp::uniform2(seed, step, chain, purpose, out[0], out[1]);
+}
+extern "C" double hh_normal_from(double u0, double u1) { return smp::normal_from(u0, u1); }
+extern "C" void hh_step_boundaries(double T, int fisher_exist, int primed, double *out) { smp::step_boundaries(T, fisher_exist, primed, out); }
+extern "C" double hh_log_prior(const gwat_b200_prior *prior, int pv2, int nrt, int dimension, const double *pos)
+{
+	smp::PriorPlan pp;
+	pp.pv2 = pv2;
+	pp.nrt = nrt;
+	pp.tidal_love = prior->tidal_love;
+	pp.dimension = dimension;
+	pp.first_mod = (pv2 ? 15 : 11) + (nrt ? (prior->tidal_love ? 1 : 2) : 0);
+	return smp::standard_log_prior(*prior, pp, pos);
+}
+extern "C" int hh_jacobi(const double *A, int n, double *vals, double *vecs)
+{
+	std::vector<double> work(A, A + n * n);
+	return smp::jacobi_eigen(work.data(), n, vals, vecs) ? 1 : 0;
+}
+extern "C" void hh_fisher_transformations(double *F, int dim, int pv2, int alpha_fix, int nmod, const double *param)
+{
+	smp::fisher_transformations(F, dim, pv2, alpha_fix, nmod, param);
+}
+extern "C" int hh_propose(int type, const double *cur, double *prop, int dim, const double *widths, double u_pick, double u_pick2,
+                          double z, double beta, int H, const double *hist, const double *vals, const double *vecs, double T)
+{
+	if (type == smp::STEP_GAUSS) return smp::propose_gaussian(cur, prop, dim, widths, u_pick, z);
+	if (type == smp::STEP_DE) {
+		int i, j;
+		smp::de_pick(H, u_pick, u_pick2, i, j);
+		smp::propose_de(cur, prop, dim, hist + (size_t)i * dim, hist + (size_t)j * dim, beta, z, widths[dim]);
+		return i * H + j;
+	}
+	smp::propose_fisher(cur, prop, dim, vals, vecs, T, u_pick, z, widths[dim + 2]);
+	return 0;
+}
+extern "C" int hh_mh_accept(double cll, double pll, double clp, double plp, double T, double u) { return smp::mh_accept(cll, pll, clp, plp, T, u) ? 1 : 0; }
+extern "C" int hh_swap_decision(double ll1, double ll2, double T1, double T2, double alpha) { return smp::swap_decision(ll1, ll2, T1, T2, alpha); }
+extern "C" double hh_tuned_width(double w, long long acc, long long rej, double lo, double hi) { return smp::tuned_width(w, acc, rej, lo, hi); }

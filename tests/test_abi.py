@@ -8,13 +8,15 @@ import sys
 import pytest
 
 from gw_analysis_tools_b200 import abi, engine
+from gw_analysis_tools_b200 import sampler as sampler_binding
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "gwat_b200.h")
+SAMPLER_HEADER = os.path.join(ROOT, "include", "gwat_b200_sampler.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+def declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(gwat_b200_[a-z0-9_]+)\s*\(", text)))
 
@@ -23,20 +25,25 @@ def test_header_declares_what_python_binds():
     assert sorted(engine.EXPORTS) == declared_functions()
 
 
+def test_sampler_header_declares_what_python_binds():
+    assert sorted(sampler_binding.EXPORTS) == declared_functions(SAMPLER_HEADER)
+
+
 def test_library_exports_every_declared_symbol():
     lib = engine.load_library()
-    for name in declared_functions():
+    for name in declared_functions() + declared_functions(SAMPLER_HEADER):
         assert hasattr(lib, name), name
     assert lib.gwat_b200_abi_version() == abi.ABI_VERSION
 
 
 def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "gwat_b200.h"\nint main(void){printf("%zu %zu\\n", sizeof(gwat_b200_source), sizeof(gwat_b200_mod));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "gwat_b200_sampler.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(gwat_b200_source), sizeof(gwat_b200_mod), sizeof(gwat_b200_prior), sizeof(gwat_b200_sampler_options));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
-    a, b = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    a, b, c, d = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(a) == C.sizeof(abi.Source) and int(b) == C.sizeof(abi.Mod)
+    assert int(c) == C.sizeof(sampler_binding.Prior) and int(d) == C.sizeof(sampler_binding.Options)
 
 
 def test_defaults_match_reference_members():
