@@ -655,16 +655,27 @@ void choose_chunks(int W, int L, int &chunks, int &bins_per_cta)
 }
 
 // The shared tail of every likelihood entry point: coefficients are in ctx->d_coef.
-int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_logL, cudaStream_t st)
+int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_logL, cudaStream_t st, cudaStream_t st_heavy = nullptr,
+                cudaEvent_t ev_a = nullptr, cudaEvent_t ev_b = nullptr)
 {
 	int chunks, bins_per_cta;
 	choose_chunks(W, ctx->L, chunks, bins_per_cta);
 	if (grow(ctx, ctx->d_partial, ctx->cap_partial, (size_t)2 * W * chunks)) return GWAT_B200_ERR_CUDA;
-	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), st));
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, chunks, bins_per_cta, st)) return fail(
+	cudaStream_t sl = st;
+	if (st_heavy && st_heavy != st && ev_a && ev_b) {
+		CUDA_TRY(ctx, cudaEventRecord(ev_a, st));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(st_heavy, ev_a, 0));
+		sl = st_heavy;
+	}
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), sl));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, sl));
+	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, chunks, bins_per_cta, sl)) return fail(
 	                               ctx, GWAT_B200_ERR_STATE, "unsupported detector count"));
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, sl));
+	if (sl != st) {
+		CUDA_TRY(ctx, cudaEventRecord(ev_b, sl));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_b, 0));
+	}
 	k_finish<<<(W + 127) / 128, 128, 0, st>>>(ctx->d_partial, W, chunks, ctx->pref_like, d_logL, ctx->d_active);
 	ctx->launches += 2;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -855,6 +866,8 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 		cudaFree(l.d_active);
 		if (l.ev0) cudaEventDestroy(l.ev0);
 		if (l.ev1) cudaEventDestroy(l.ev1);
+		if (l.ev_a) cudaEventDestroy(l.ev_a);
+		if (l.ev_b) cudaEventDestroy(l.ev_b);
 	}
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -1231,7 +1244,7 @@ namespace gwat_internal {
 int set_error(gwat_b200_ctx *ctx, int code, const std::string &msg) { return fail(ctx, code, msg); }
 
 int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gwat_b200_mod *mod, int dimension, int W,
-                      const double *d_params, double gmst, double T_segment, double *d_logL, cudaStream_t st)
+                      const double *d_params, double gmst, double T_segment, double *d_logL, cudaStream_t st, cudaStream_t st_heavy)
 {
 	if (int rc = check_ready(ctx, true)) return rc;
 	if (lane < 0 || lane > 2) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc: lane out of range");
@@ -1249,15 +1262,18 @@ int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gw
 			CUDA_TRY(ctx, cudaEventCreate(&l.ev0));
 			CUDA_TRY(ctx, cudaEventCreate(&l.ev1));
 			CUDA_TRY(ctx, cudaMalloc((void **)&l.d_active, sizeof(unsigned long long)));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&l.ev_a, cudaEventDisableTiming));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&l.ev_b, cudaEventDisableTiming));
 		}
 	}
+	cudaEvent_t ev_a = lane > 0 ? ctx->extra[lane - 1].ev_a : nullptr, ev_b = lane > 0 ? ctx->extra[lane - 1].ev_b : nullptr;
 	LaneSwap swap(ctx, lane);
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
 	                                                                              ctx->d_coef, nullptr));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
-	return run_loglike(ctx, desc, W, d_logL, st);
+	return run_loglike(ctx, desc, W, d_logL, st, st_heavy, ev_a, ev_b);
 }
 
 int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int S,

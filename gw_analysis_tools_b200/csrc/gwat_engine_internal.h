@@ -18,6 +18,7 @@ struct LikeLane {
 	size_t cap_partial = 0;
 	unsigned long long *d_active = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // hand-off between the light and the heavy stream of a lane
 };
 
 struct gwat_b200_ctx {
@@ -63,8 +64,11 @@ struct gwat_b200_ctx {
 namespace gwat_internal {
 // All of these expect the caller to hold ctx->mu and to have made ctx->device current.
 // lane 0 = the context's own scratch, 1..2 = ctx->extra[lane-1]
+// st_heavy (optional): the bin kernel is launched there instead, chained to `st` by events, so that a caller can give the
+// short latency-bound kernels (setup, finish, its own bookkeeping) a higher stream priority than the long FP64-bound one.
 int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gwat_b200_mod *mod, int dimension, int W,
-                      const double *d_params, double gmst, double T_segment, double *d_logL, cudaStream_t st);
+                      const double *d_params, double gmst, double T_segment, double *d_logL, cudaStream_t st,
+                      cudaStream_t st_heavy = nullptr);
 // Fisher matrices of MCMC_fisher_wrapper (src/mcmc_gw.cpp:2230-2300) before MCMC_fisher_transformations: sampling vectors on
 // the device -> sum over the network's detectors of fisher_numerical("MCMC_"+method, detector d, reference detector 0).
 // d_fisher: device [S][dimension][dimension].  Synchronous with respect to `st` only.

@@ -185,10 +185,9 @@ __global__ void k_gather(const double *__restrict__ pos, const int *__restrict__
 	if (t >= n * P) return;
 	out[t] = pos[(size_t)idx[t / P] * P + t % P];
 }
-// transformations + eigen-system; idx == nullptr: write to slot t (the stand-alone entry point)
-__global__ void k_fisher_eigen(double *__restrict__ F, const double *__restrict__ params, const int *__restrict__ idx, int n, int P,
-                               int pv2, int alpha_unit_fix, int ppE_Nmod, double *__restrict__ fvals, double *__restrict__ fvecs,
-                               long long *__restrict__ counters)
+// transformations + eigen-system of matrix t, written to slot t of the outputs; ok[t] = 0 when the result has a NaN
+__global__ void k_fisher_eigen(double *__restrict__ F, const double *__restrict__ params, int n, int P, int pv2, int alpha_unit_fix,
+                               int ppE_Nmod, double *__restrict__ out_vals, double *__restrict__ out_vecs, int *__restrict__ ok_out)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
@@ -197,12 +196,25 @@ __global__ void k_fisher_eigen(double *__restrict__ F, const double *__restrict_
 	double work[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM], vals[GWAT_B200_MAX_DIM], vecs[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM];
 	for (int i = 0; i < P * P; i++) work[i] = A[i];
 	const bool ok = jacobi_eigen(work, P, vals, vecs);
-	const int c = idx ? idx[t] : t;
 	if (ok) {
-		for (int i = 0; i < P; i++) fvals[(size_t)c * P + i] = vals[i];
-		for (int i = 0; i < P * P; i++) fvecs[(size_t)c * P * P + i] = vecs[i];
+		for (int i = 0; i < P; i++) out_vals[(size_t)t * P + i] = vals[i];
+		for (int i = 0; i < P * P; i++) out_vecs[(size_t)t * P * P + i] = vecs[i];
 	}
-	if (counters) counters[(size_t)c * NCT + (ok ? GWAT_B200_CT_FISHER_UPDATES : GWAT_B200_CT_FISHER_NAN)] += 1;
+	if (ok_out) ok_out[t] = ok ? 1 : 0;
+}
+// staged eigen-systems -> the chains they belong to (update_fisher's tail, :676-711: a NaN result keeps the old system)
+__global__ void k_fisher_commit(const int *__restrict__ idx, const int *__restrict__ ok, int n, int P, const double *__restrict__ vals,
+                                const double *__restrict__ vecs, double *__restrict__ fvals, double *__restrict__ fvecs,
+                                long long *__restrict__ counters)
+{
+	const int t = blockIdx.x;
+	if (t >= n) return;
+	const int c = idx[t];
+	if (ok[t]) {
+		for (int i = threadIdx.x; i < P; i += blockDim.x) fvals[(size_t)c * P + i] = vals[(size_t)t * P + i];
+		for (int i = threadIdx.x; i < P * P; i += blockDim.x) fvecs[(size_t)c * P * P + i] = vecs[(size_t)t * P * P + i];
+	}
+	if (threadIdx.x == 0) counters[(size_t)c * NCT + (ok[t] ? GWAT_B200_CT_FISHER_UPDATES : GWAT_B200_CT_FISHER_NAN)] += 1;
 }
 
 // ---- swap sweep --------------------------------------------------------------------------------------------------------------
@@ -330,15 +342,21 @@ struct gwat_b200_sampler {
 	double *pos2 = nullptr, *ll2 = nullptr, *lp2 = nullptr;  // swap double buffers
 	double *swap_thr = nullptr;
 	int *swap_kind = nullptr, *swap_src = nullptr;
-	// Fisher refresh scratch
-	int *d_fidx = nullptr;
-	double *d_fparams = nullptr, *d_fmat = nullptr;
-	int *h_fidx = nullptr;  // pinned, one slice per (step in flight, lane)
-	size_t h_fidx_cap = 0;
+	// Fisher refresh pipeline, per lane: device staging slots (one per step in flight) and a longer ring of pinned index lists
+	struct RefreshLane {
+		int ND = 1, NP = 1;
+		std::vector<int *> d_idx, d_ok;
+		std::vector<double *> d_par, d_mat, d_vals, d_vecs;
+		std::vector<cudaEvent_t> ev_gathered, ev_done, ev_h2d;
+		std::vector<int> n_in_slot;
+		std::vector<char> h_used;
+		int *h_idx = nullptr;  // pinned [NP][lane_n]
+		long long next_sched = 0, h_counter = 0;
+	} rf[2];
+	int lookahead = 0;
 	int nlanes = 1, lane_c0[2] = {0, 0}, lane_n[2] = {0, 0};
-	cudaStream_t st[2] = {nullptr, nullptr};
-	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_join = nullptr, ev_fisher = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-	bool fisher_pending = false;
+	cudaStream_t st[2] = {nullptr, nullptr}, st_like[2] = {nullptr, nullptr}, st_fisher = nullptr;
+	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
 	// host mirror of the schedule
 	std::vector<double> h_temps;
 	std::vector<int> h_fisher_ct;
@@ -386,26 +404,50 @@ void fisher_schedule(gwat_b200_sampler *s, int ln, long long step, std::vector<i
 	}
 }
 
-int fisher_refresh(gwat_b200_sampler *s, int ln, const std::vector<int> &flagged, int *h_slice)
+// Start the refresh that step `t` of lane `ln` will need: gather the flagged chains' CURRENT positions on the lane's stream,
+// then Fisher matrices and eigen-systems on the side stream, into the staging slot of step t.
+int refresh_schedule(gwat_b200_sampler *s, int ln, long long t, std::vector<int> &flagged)
 {
 	gwat_b200_ctx *ctx = s->ctx;
-	const int n = (int)flagged.size(), P = s->k.P;
+	gwat_b200_sampler::RefreshLane &r = s->rf[ln];
+	fisher_schedule(s, ln, t, flagged);
+	const int n = (int)flagged.size(), P = s->k.P, ds = (int)(t % r.ND);
+	r.n_in_slot[ds] = n;
+	if (n == 0) return 0;
+	const int ps = (int)(r.h_counter++ % r.NP);
+	if (r.h_used[ps]) SCUDA(ctx, cudaEventSynchronize(r.ev_h2d[ps]));  // the copy that last read this pinned slice is done
+	int *h = r.h_idx + (size_t)ps * s->lane_n[ln];
+	std::memcpy(h, flagged.data(), sizeof(int) * n);
 	cudaStream_t st = s->st[ln];
-	std::memcpy(h_slice, flagged.data(), sizeof(int) * n);
-	int *d_idx = s->d_fidx + s->lane_c0[ln];
-	double *d_par = s->d_fparams + (size_t)s->lane_c0[ln] * P;
-	double *d_mat = s->d_fmat + (size_t)s->lane_c0[ln] * P * P;
-	// the engine's Fisher scratch is shared by both lanes: passes are ordered through ev_fisher
-	if (s->fisher_pending) SCUDA(ctx, cudaStreamWaitEvent(st, s->ev_fisher, 0));
-	SCUDA(ctx, cudaMemcpyAsync(d_idx, h_slice, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-	k_gather<<<(n * P + 255) / 256, 256, 0, st>>>(s->d.pos, d_idx, n, P, d_par);
-	if (int rc = gwat_internal::fisher_mcmc_dev(ctx, s->method.c_str(), &s->mod, P, s->opt.fisher_deriv_order, n, d_par, s->gmst, d_mat, st))
+	SCUDA(ctx, cudaMemcpyAsync(r.d_idx[ds], h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+	SCUDA(ctx, cudaEventRecord(r.ev_h2d[ps], st));
+	r.h_used[ps] = 1;
+	k_gather<<<(n * P + 255) / 256, 256, 0, st>>>(s->d.pos, r.d_idx[ds], n, P, r.d_par[ds]);
+	SCUDA(ctx, cudaEventRecord(r.ev_gathered[ds], st));
+	cudaStream_t sf = s->st_fisher;
+	SCUDA(ctx, cudaStreamWaitEvent(sf, r.ev_gathered[ds], 0));
+	if (int rc = gwat_internal::fisher_mcmc_dev(ctx, s->method.c_str(), &s->mod, P, s->opt.fisher_deriv_order, n, r.d_par[ds], s->gmst,
+	                                            r.d_mat[ds], sf))
 		return rc;
-	k_fisher_eigen<<<(n + 31) / 32, 32, 0, st>>>(d_mat, d_par, d_idx, n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, s->d.fvals,
-	                                             s->d.fvecs, s->d.counters);
-	SCUDA(ctx, cudaEventRecord(s->ev_fisher, st));
-	s->fisher_pending = true;
+	k_fisher_eigen<<<(n + 31) / 32, 32, 0, sf>>>(r.d_mat[ds], r.d_par[ds], n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, r.d_vals[ds],
+	                                             r.d_vecs[ds], r.d_ok[ds]);
+	SCUDA(ctx, cudaEventRecord(r.ev_done[ds], sf));
 	s->last_launches += 2;
+	return 0;
+}
+
+// Install the eigen-systems staged for step `t` (no-op when none were flagged).
+int refresh_commit(gwat_b200_sampler *s, int ln, long long t)
+{
+	gwat_b200_ctx *ctx = s->ctx;
+	gwat_b200_sampler::RefreshLane &r = s->rf[ln];
+	const int ds = (int)(t % r.ND), n = r.n_in_slot[ds], P = s->k.P;
+	if (n == 0) return 0;
+	cudaStream_t st = s->st[ln];
+	SCUDA(ctx, cudaStreamWaitEvent(st, r.ev_done[ds], 0));
+	k_fisher_commit<<<n, 64, 0, st>>>(r.d_idx[ds], r.d_ok[ds], n, P, r.d_vals[ds], r.d_vecs[ds], s->d.fvals, s->d.fvecs, s->d.counters);
+	r.n_in_slot[ds] = 0;
+	s->last_launches += 1;
 	return 0;
 }
 
@@ -526,7 +568,7 @@ int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	if (rc == 0) {
 		SCUDA(ctx, cudaMemsetAsync(d_vals, 0xff, sizeof(double) * W * P, st));  // NaN where the decomposition fails
 		SCUDA(ctx, cudaMemsetAsync(d_vecs, 0xff, sizeof(double) * W * P * P, st));
-		k_fisher_eigen<<<(W + 31) / 32, 32, 0, st>>>(d_mat, d_par, nullptr, W, P, pp.pv2, af ? 1 : 0, nm, d_vals, d_vecs, nullptr);
+		k_fisher_eigen<<<(W + 31) / 32, 32, 0, st>>>(d_mat, d_par, W, P, pp.pv2, af ? 1 : 0, nm, d_vals, d_vecs, nullptr);
 		ctx->launches += 1;
 		if (fisher) SCUDA(ctx, cudaMemcpyAsync(fisher, d_mat, sizeof(double) * W * P * P, cudaMemcpyDeviceToHost, st));
 		if (eigenvalues) SCUDA(ctx, cudaMemcpyAsync(eigenvalues, d_vals, sizeof(double) * W * P, cudaMemcpyDeviceToHost, st));
@@ -544,19 +586,32 @@ void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 {
 	if (!s) return;
 	cudaSetDevice(s->ctx->device);
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < 2; i++) {
 		if (s->st[i]) cudaStreamSynchronize(s->st[i]);
+		if (s->st_like[i]) cudaStreamSynchronize(s->st_like[i]);
+	}
 	DevState &d = s->d;
 	void *ptrs[] = {d.pos, d.prop, d.ll, d.lp, d.llprop, d.lpprop, d.temps, d.hist, d.hist_pos, d.fvals, d.fvecs, d.widths, d.counters,
-	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src,
-	                s->d_fidx, s->d_fparams, s->d_fmat};
+	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src};
 	for (void *p : ptrs) cudaFree(p);
-	if (s->h_fidx) cudaFreeHost(s->h_fidx);
+	if (s->st_fisher) cudaStreamSynchronize(s->st_fisher);
+	for (gwat_b200_sampler::RefreshLane &r : s->rf) {
+		for (int *p : r.d_idx) cudaFree(p);
+		for (int *p : r.d_ok) cudaFree(p);
+		for (auto *v : {&r.d_par, &r.d_mat, &r.d_vals, &r.d_vecs})
+			for (double *p : *v) cudaFree(p);
+		for (auto *v : {&r.ev_gathered, &r.ev_done, &r.ev_h2d})
+			for (cudaEvent_t e : *v)
+				if (e) cudaEventDestroy(e);
+		if (r.h_idx) cudaFreeHost(r.h_idx);
+	}
 	for (int i = 0; i < 2; i++) {
 		if (s->ev_lane[i]) cudaEventDestroy(s->ev_lane[i]);
 		if (s->st[i]) cudaStreamDestroy(s->st[i]);
+		if (s->st_like[i]) cudaStreamDestroy(s->st_like[i]);
 	}
-	for (cudaEvent_t e : {s->ev_join, s->ev_fisher, s->ev_t0, s->ev_t1})
+	if (s->st_fisher) cudaStreamDestroy(s->st_fisher);
+	for (cudaEvent_t e : {s->ev_join, s->ev_t0, s->ev_t1})
 		if (e) cudaEventDestroy(e);
 	delete s;
 }
@@ -629,15 +684,52 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(dalloc(d.cold_slot, (size_t)C));
 	SC_TRY(dalloc(s->swap_kind, (size_t)C));
 	SC_TRY(dalloc(s->swap_src, (size_t)C));
-	SC_TRY(dalloc(s->d_fidx, (size_t)C));
-	SC_TRY(dalloc(s->d_fparams, (size_t)C * P));
-	SC_TRY(dalloc(s->d_fmat, (size_t)C * P * P));
+	int prio_lo = 0, prio_hi = 0;
+	SC_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	s->lookahead = std::max(0, std::min(o.fisher_lookahead, 64));
 	for (int i = 0; i < s->nlanes; i++) {
-		SC_TRY(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
+		// short latency-bound kernels on a high-priority stream, the FP64-bound bin kernel on a low-priority one: the other
+		// lane's setup is then scheduled into the SM slots the bin kernel frees instead of waiting for its last CTA
+		SC_TRY(cudaStreamCreateWithPriority(&s->st[i], cudaStreamNonBlocking, prio_hi));
+		SC_TRY(cudaStreamCreateWithPriority(&s->st_like[i], cudaStreamNonBlocking, prio_lo));
 		SC_TRY(cudaEventCreateWithFlags(&s->ev_lane[i], cudaEventDisableTiming));
+		if (!o.fisher_exist) continue;
+		gwat_b200_sampler::RefreshLane &r = s->rf[i];
+		const size_t n = (size_t)s->lane_n[i];
+		r.ND = s->lookahead + 1;
+		r.NP = s->lookahead + 33;
+		r.n_in_slot.assign(r.ND, 0);
+		r.h_used.assign(r.NP, 0);
+		for (int k = 0; k < r.ND; k++) {
+			int *pi = nullptr, *po = nullptr;
+			double *a = nullptr, *b = nullptr, *c = nullptr, *e = nullptr;
+			SC_TRY(dalloc(pi, n));
+			r.d_idx.push_back(pi);
+			SC_TRY(dalloc(po, n));
+			r.d_ok.push_back(po);
+			SC_TRY(dalloc(a, n * P));
+			r.d_par.push_back(a);
+			SC_TRY(dalloc(b, n * P * P));
+			r.d_mat.push_back(b);
+			SC_TRY(dalloc(c, n * P));
+			r.d_vals.push_back(c);
+			SC_TRY(dalloc(e, n * P * P));
+			r.d_vecs.push_back(e);
+			cudaEvent_t e1 = nullptr, e2 = nullptr;
+			SC_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+			r.ev_gathered.push_back(e1);
+			SC_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+			r.ev_done.push_back(e2);
+		}
+		for (int k = 0; k < r.NP; k++) {
+			cudaEvent_t e1 = nullptr;
+			SC_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+			r.ev_h2d.push_back(e1);
+		}
+		SC_TRY(cudaMallocHost((void **)&r.h_idx, std::max<size_t>(1, (size_t)r.NP * n) * sizeof(int)));
 	}
+	SC_TRY(cudaStreamCreateWithPriority(&s->st_fisher, cudaStreamNonBlocking, prio_hi));
 	SC_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
-	SC_TRY(cudaEventCreateWithFlags(&s->ev_fisher, cudaEventDisableTiming));
 	SC_TRY(cudaEventCreate(&s->ev_t0));
 	SC_TRY(cudaEventCreate(&s->ev_t1));
 	cudaStream_t st = s->st[0];
@@ -670,18 +762,6 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 	const int P = s->k.P;
 	const long long launches0 = ctx->launches;
 	s->last_launches = 0;
-	// pinned staging for the Fisher index lists: one slice per (step, lane) of this call, so no slice is rewritten while
-	// an earlier asynchronous copy may still read it
-	std::vector<std::vector<int>> flagged_all;
-	if (s->opt.fisher_exist) {
-		const size_t need = (size_t)s->k.C * 8;  // grown below if a call flags more (bounded by C per step)
-		if (s->h_fidx_cap < need) {
-			if (s->h_fidx) cudaFreeHost(s->h_fidx);
-			SCUDA(ctx, cudaMallocHost((void **)&s->h_fidx, need * sizeof(int)));
-			s->h_fidx_cap = need;
-		}
-	}
-	size_t h_used = 0;
 	SCUDA(ctx, cudaEventRecord(s->ev_t0, s->st[0]));
 	if (s->nlanes > 1) {
 		SCUDA(ctx, cudaEventRecord(s->ev_join, s->st[0]));
@@ -695,19 +775,19 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 			const int c0 = s->lane_c0[ln], n = s->lane_n[ln];
 			if (n == 0) continue;
 			cudaStream_t st = s->st[ln];
-			fisher_schedule(s, ln, step, flagged);
-			if (!flagged.empty()) {
-				if (h_used + flagged.size() > s->h_fidx_cap) {
-					// staging exhausted: drain the streams, then reuse it from the start
-					for (int i = 0; i < s->nlanes; i++) SCUDA(ctx, cudaStreamSynchronize(s->st[i]));
-					h_used = 0;
+			if (s->opt.fisher_exist) {
+				// Fisher refreshes run `lookahead` steps ahead of their use, on the side stream (0 = at the step that uses them,
+				// which is the reference's schedule exactly)
+				gwat_b200_sampler::RefreshLane &r = s->rf[ln];
+				while (r.next_sched <= step + s->lookahead) {
+					if (int rc = refresh_schedule(s, ln, r.next_sched, flagged)) return rc;
+					r.next_sched += 1;
 				}
-				if (int rc = fisher_refresh(s, ln, flagged, s->h_fidx + h_used)) return rc;
-				h_used += flagged.size();
+				if (int rc = refresh_commit(s, ln, step)) return rc;
 			}
 			k_propose<<<(n + 63) / 64, 64, 0, st>>>(s->d, s->k, s->prior, s->pp, step, c0, n);
 			if (int rc = gwat_internal::loglike_mcmc_lane(ctx, 1 + ln, s->method.c_str(), &s->mod, P, n, s->d.prop + (size_t)c0 * P, s->gmst,
-			                                              s->T_segment, s->d.llprop + c0, st))
+			                                              s->T_segment, s->d.llprop + c0, st, s->st_like[ln]))
 				return rc;
 			k_accept<<<(n + 63) / 64, 64, 0, st>>>(s->d, s->k, step, c0, n, cold_row);
 			s->last_launches += 2;
@@ -725,12 +805,13 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 	}
 	SCUDA(ctx, cudaEventRecord(s->ev_t1, s->st[0]));
 	SCUDA(ctx, cudaStreamSynchronize(s->st[0]));
+	// refreshes scheduled ahead for steps of the next call: let them finish, they use the context's Fisher scratch
+	if (s->st_fisher) SCUDA(ctx, cudaStreamSynchronize(s->st_fisher));
 	SCUDA(ctx, cudaGetLastError());
 	float ms = 0;
 	SCUDA(ctx, cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
 	s->last_ms = ms;
 	s->last_launches += ctx->launches - launches0;
-	s->fisher_pending = false;
 	return GWAT_B200_OK;
 }
 

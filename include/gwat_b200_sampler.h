@@ -64,7 +64,10 @@ typedef struct gwat_b200_sampler_options {
 	unsigned long long seed;
 	int lanes;                  /* 1 or 2 concurrent halves */
 	int record_cold;            /* keep the positions of the T=1 chains of every step in a device buffer (gwat_b200_sampler_cold) */
-	int reserved_;
+	int fisher_lookahead;       /* 0: a chain's Fisher matrix is recomputed at the step that first uses it, at the position it has
+	                               then (the reference's schedule).  k > 0: it is computed k steps earlier, at the position the
+	                               chain has then, on a side stream that overlaps the likelihood kernels; same refresh cadence,
+	                               same use, a matrix that is k steps staler out of the ~400 steps it is used for. */
 } gwat_b200_sampler_options;
 
 typedef struct gwat_b200_sampler gwat_b200_sampler;
