@@ -159,14 +159,14 @@ __global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike
                                                      double *__restrict__ partial)
 {
 	__shared__ WalkerCoef w;
-	load_walker(coefs + blockIdx.y, w);
-	const int begin = blockIdx.x * bins_per_cta;
+	load_walker(coefs + blockIdx.x, w);
+	const int begin = blockIdx.y * bins_per_cta;
 	const int end = min(g.L, begin + bins_per_cta);
 	double acc = 0.0, nact = 0.0;
 	if (w.valid) loglike_run<Fam, D>(w, g, begin + threadIdx.x, end, kLikeThreads, acc, nact);
 	block_sum2<kLikeThreads>(acc, nact);
 	if (threadIdx.x == 0) {
-		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+		double *p = partial + 2 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
 		p[0] = w.valid ? acc : NAN;
 		p[1] = nact;
 	}
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike
 		mbar_init(&bar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	load_walker(coefs + blockIdx.y, w);  // ends with __syncthreads(): the barriers are initialised for everyone
+	load_walker(coefs + blockIdx.x, w);  // ends with __syncthreads(): the barriers are initialised for everyone
 
-	const int begin = blockIdx.x * bins_per_cta;
+	const int begin = blockIdx.y * bins_per_cta;
 	const int end = min(g.ld, begin + bins_per_cta);
 	int ntiles = (end - begin + TILE - 1) / TILE;
 	const bool uniform = g.uniform != 0;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike
 	}
 	block_sum2<kLikeThreads>(acc, nact);
 	if (threadIdx.x == 0) {
-		double *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+		double *p = partial + 2 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
 		p[0] = w.valid ? acc : NAN;
 		p[1] = nact;
 	}
@@ -350,9 +350,10 @@ __global__ void __launch_bounds__(kThreads) k_response(const WalkerCoef *__restr
 struct FisherPlan {
 	RepackPlan rp;
 	int npts;       // 2 or 4 stencil points per parameter
-	int det_is_ref; // detector == reference detector: no arrival-time handling at all
 	int theory;
-	double det_row[13], ref_row[13];
+	int nd;               // detectors handled by one pass (1..5)
+	int det_is_ref[5];    // detector == reference detector: no arrival-time handling at all
+	double det_row[5][13], ref_row[13];
 };
 
 template <class Fam>
@@ -362,15 +363,15 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 {
 	const int dim = fp.rp.dimension;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= S * dim * fp.npts) return;
-	const int k = t % fp.npts, i = (t / fp.npts) % dim, sidx = t / (fp.npts * dim);
+	if (t >= fp.nd * S * dim * fp.npts) return;
+	const int k = t % fp.npts, i = (t / fp.npts) % dim, sidx = (t / (fp.npts * dim)) % S, d = t / (fp.npts * dim * S);
 	const double epsilon = 1e-8;
 	const gwat_b200_source orig = src[sidx];
 	double v[GWAT_B200_MAX_DIM];
 	int logfac[GWAT_B200_MAX_DIM];
 	unpack_fisher(orig, fp.rp, v, logfac);
 	const bool bc = (i == 8 && v[8] > .25 - epsilon);  // eta at its upper boundary: one-sided difference (:369-383)
-	if (k == 0) {
+	if (k == 0 && d == 0) {
 		scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
 		eta_bc[(size_t)sidx * dim + i] = bc ? 1 : 0;
 	}
@@ -381,14 +382,14 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	gwat_b200_source sp;
 	repack_fisher_point(v, orig, fp.rp, sp);
 	double tshift = 0;
-	if (!fp.det_is_ref) {
-		const double dtoa = dtoa_between(fp.ref_row + 9, fp.det_row + 9, sp.RA, sp.DEC, sp.gmst);
+	if (!fp.det_is_ref[d]) {
+		const double dtoa = dtoa_between(fp.ref_row + 9, fp.det_row[d] + 9, sp.RA, sp.DEC, sp.gmst);
 		if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;  // +-eps: phase factor on the response (:403-408, 425-430)
 		else sp.tc -= dtoa;                          // +-2eps: shift of tc instead (:436-438, 451-453)  [reference quirk, kept]
 	}
 	Network net;
 	net.D = 1;
-	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[j];
+	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[d][j];
 	WalkerCoef wc;
 	walker_setup<Fam>(sp, net, device_tables(), fp.theory, wc);
 	wc.det[0].tshift = tshift;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) k_fisher_deriv(const WalkerCoef *__r
 {
 	__shared__ WalkerCoef w[4];
 	{
-		const double *sp = reinterpret_cast<const double *>(coefs + (size_t)blockIdx.y * npts);
+		const double *sp = reinterpret_cast<const double *>(coefs + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * npts);
 		double *dp = reinterpret_cast<double *>(&w[0]);
 		for (int i = threadIdx.x; i < (int)(npts * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
 		__syncthreads();
@@ -434,15 +435,16 @@ __global__ void __launch_bounds__(kThreads) k_fisher_deriv(const WalkerCoef *__r
 		         (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
 	}
 	const double sc = scale[blockIdx.y];
-	const size_t o = (size_t)blockIdx.y * g.L + bin;
+	const size_t o = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.L + bin;
 	dre[o] = d.re * sc;
 	dim_[o] = d.im * sc;
 }
 
-// F_jk (+)= prefactor * sum_bins coef * Re(d_j conj(d_k)) / S      (calculate_fisher_elements, src/fisher.cpp:2704-2781)
+// F_jk = sum_d prefactor * sum_bins coef_d * Re(d_j conj(d_k)) / S_d   (calculate_fisher_elements, src/fisher.cpp:2704-2781, and the
+// detector loop of the callers: one partial Fisher per detector, added in detector order)
 __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__restrict__ dre, const double *__restrict__ dim_,
-                                                             const double *__restrict__ wq, int L, int dim, double prefactor,
-                                                             int accumulate, double *__restrict__ out)
+                                                             const double *__restrict__ wq, int ld, int L, int dim, int ns, int nd,
+                                                             double prefactor, double *__restrict__ out)
 {
 	// blockIdx.x enumerates the pairs j >= k, blockIdx.y the source
 	int j = 0, k = blockIdx.x;
@@ -450,22 +452,25 @@ __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__re
 		k -= j + 1;
 		j++;
 	}
-	const size_t sbase = (size_t)blockIdx.y * dim;
-	const double *ajr = dre + (sbase + j) * L, *aji = dim_ + (sbase + j) * L;
-	const double *akr = dre + (sbase + k) * L, *aki = dim_ + (sbase + k) * L;
-	double acc = 0, unused = 0;
-	for (int i = threadIdx.x; i < L; i += kThreads) acc += wq[i] * (ajr[i] * akr[i] + aji[i] * aki[i]);
-	block_sum2(acc, unused);
-	if (threadIdx.x == 0) {
-		const double val = prefactor * acc;
-		double *o = out + (size_t)blockIdx.y * dim * dim;
-		if (accumulate) {
-			o[j * dim + k] += val;
-			if (j != k) o[k * dim + j] += val;
-		} else {
-			o[j * dim + k] = val;
-			o[k * dim + j] = val;
+	double total = 0;
+	for (int d = 0; d < nd; d++) {
+		const size_t sbase = ((size_t)d * ns + blockIdx.y) * dim;
+		const double *ajr = dre + (sbase + j) * L, *aji = dim_ + (sbase + j) * L;
+		const double *akr = dre + (sbase + k) * L, *aki = dim_ + (sbase + k) * L;
+		const double *w = wq + (size_t)d * ld;
+		double acc = 0, unused = 0;
+		for (int i = threadIdx.x; i < L; i += kThreads) acc += w[i] * (ajr[i] * akr[i] + aji[i] * aki[i]);
+		block_sum2(acc, unused);
+		if (threadIdx.x == 0) {
+			const double val = prefactor * acc;
+			total = (d == 0) ? val : total + val;
 		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		double *o = out + (size_t)blockIdx.y * dim * dim;
+		o[j * dim + k] = total;
+		o[k * dim + j] = total;
 	}
 }
 
@@ -504,6 +509,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 }
 
 }  // namespace
+
 
 // ---------------------------------------------------------------------------------------------------------------------
 // context
@@ -626,7 +632,9 @@ template <class Fam>
 int launch_loglike(gwat_b200_ctx *ctx, int W, int chunks, int bins_per_cta, cudaStream_t st)
 {
 	const GridPtrs g = grid_ptrs(ctx);
-	const dim3 grid(chunks, W);
+	// walkers vary fastest: CTAs in flight together work on the same stretch of the grid tables, so a tile is fetched from
+	// HBM once per pass even when the tables (cfg5: 109 MB) do not fit in L2
+	const dim3 grid(W, chunks);
 	switch (ctx->D) {
 	case 1: return launch_loglike_d<Fam, 1>(ctx, g, grid, bins_per_cta, st);
 	case 2: return launch_loglike_d<Fam, 2>(ctx, g, grid, bins_per_cta, st);
@@ -720,48 +728,50 @@ int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const 
 }
 
 // ---- Fisher passes shared by the host-source entry point and the sampler's device-parameter entry point ------------------
-int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim)
+int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim, int nd)
 {
-	// sources per pass: bounded by a 512 MiB derivative buffer
-	const size_t per_source = (size_t)dim * ctx->L * 16;
-	return (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)512 << 20) / per_source));
+	// sources per pass: bounded by a 2 GiB derivative buffer
+	const size_t per_source = (size_t)dim * ctx->L * 16 * nd;
+	const size_t by_memory = ((size_t)2048 << 20) / per_source, by_grid = 65535 / (size_t)dim;  // gridDim.y = sources * dim
+	return (int)std::max<size_t>(1, std::min<size_t>((size_t)S, std::min(by_memory, by_grid)));
 }
 
-int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts)
+int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts, int nd)
 {
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts * nd)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L * nd)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
 	return 0;
 }
 
-// ctx->d_src[0..ns) -> ctx->d_fisher[ns][dim][dim], detectors d0..d1-1 summed
+// ctx->d_src[0..ns) -> ctx->d_fisher[ns][dim][dim], detectors d0..d1-1 summed; one launch of each kernel for all detectors
 int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int ns, int chunk, int d0, int d1,
                  int reference_index, cudaStream_t st)
 {
-	const int L = ctx->L, dim = fp.rp.dimension;
+	const int L = ctx->L, dim = fp.rp.dimension, nd = d1 - d0;
 	const GridPtrs g = grid_ptrs(ctx);
 	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
 	const int npairs = dim * (dim + 1) / 2;
-	for (int d = d0; d < d1; d++) {
-		std::memcpy(fp.det_row, ctx->net.row[d], sizeof(fp.det_row));
-		std::memcpy(fp.ref_row, ctx->net.row[reference_index], sizeof(fp.ref_row));
-		fp.det_is_ref = (std::memcmp(fp.det_row, fp.ref_row, sizeof(fp.det_row)) == 0) ? 1 : 0;
-		const int nthreads = ns * dim * fp.npts;
-		GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
-		                                                                                        ctx->d_scale, ctx->d_bc));
-		const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
-		double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
-		GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
-		                                                                         dre, dim_));
-		k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d * ctx->ld, L, dim,
-		                                                          ctx->pref_fisher, d > d0 ? 1 : 0, ctx->d_fisher);
-		ctx->launches += 3;
-		CUDA_TRY(ctx, cudaGetLastError());
+	fp.nd = nd;
+	std::memcpy(fp.ref_row, ctx->net.row[reference_index], sizeof(fp.ref_row));
+	for (int d = 0; d < nd; d++) {
+		std::memcpy(fp.det_row[d], ctx->net.row[d0 + d], sizeof(fp.det_row[d]));
+		fp.det_is_ref[d] = (std::memcmp(fp.det_row[d], fp.ref_row, sizeof(fp.ref_row)) == 0) ? 1 : 0;
 	}
+	const int nthreads = nd * ns * dim * fp.npts;
+	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
+	                                                                                        ctx->d_scale, ctx->d_bc));
+	const dim3 gd((L + kThreads - 1) / kThreads, ns * dim, nd);
+	double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L * nd;
+	GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
+	                                                                         dre, dim_));
+	k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d0 * ctx->ld, ctx->ld, L, dim, ns, nd,
+	                                                          ctx->pref_fisher, ctx->d_fisher);
+	ctx->launches += 3;
+	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
 }
 
@@ -1181,12 +1191,10 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
 	const int L = ctx->L, dim = dimension;
-	// sources per pass: bounded by a 512 MiB derivative buffer
-	size_t per_source = (size_t)dim * L * 16;
-	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)512 << 20) / per_source));
-	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts)) return rc;
 	const int d0 = detector_index < 0 ? 0 : detector_index;
 	const int d1 = detector_index < 0 ? ctx->D : detector_index + 1;
+	const int chunk = fisher_chunk_size(ctx, S, dim, d1 - d0);
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, d1 - d0)) return rc;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 	for (int s0 = 0; s0 < S; s0 += chunk) {
 		const int ns = std::min(chunk, S - s0);
@@ -1276,6 +1284,25 @@ int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gw
 	return run_loglike(ctx, desc, W, d_logL, st, st_heavy, ev_a, ev_b);
 }
 
+int polarizations_dev(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *h_sources, double **d_out, cudaStream_t st)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	if (int rc = setup_from_sources(ctx, desc, W, h_sources, st)) return rc;
+	const size_t n = (size_t)W * ctx->L;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, 4 * n)) return GWAT_B200_ERR_CUDA;
+	double *o = ctx->d_out;
+	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const GridPtrs g = grid_ptrs(ctx);
+	GWAT_DISPATCH_FAMILY(desc, k_waveform<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n, o + 2 * n, o + 3 * n));
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	*d_out = o;
+	return GWAT_B200_OK;
+}
+
 int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int S,
                     const double *d_params, double gmst, double *d_fisher, cudaStream_t st)
 {
@@ -1295,8 +1322,8 @@ int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod 
 	fp.npts = order == 4 ? 4 : 2;
 	fp.theory = desc.theory;
 	const int dim = dimension;
-	const int chunk = fisher_chunk_size(ctx, S, dim);
-	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts)) return rc;
+	const int chunk = fisher_chunk_size(ctx, S, dim, ctx->D);
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, ctx->D)) return rc;
 	for (int s0 = 0; s0 < S; s0 += chunk) {
 		const int ns = std::min(chunk, S - s0);
 		k_repack_only<<<(ns + 127) / 128, 128, 0, st>>>(d_params + (size_t)s0 * dim, ns, rp, gmst, ctx->d_src);

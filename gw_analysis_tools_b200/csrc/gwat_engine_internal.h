@@ -74,6 +74,9 @@ int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gw
 // d_fisher: device [S][dimension][dimension].  Synchronous with respect to `st` only.
 int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int S,
                     const double *d_params, double gmst, double *d_fisher, cudaStream_t st);
+// Polarisations of W sources (host records) on the context's grid, left on the device: *d_out = [hp_re | hp_im | hc_re | hc_im],
+// each [W][L] (the context's output scratch: valid until the next call that produces outputs).
+int polarizations_dev(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *h_sources, double **d_out, cudaStream_t st);
 int set_error(gwat_b200_ctx *ctx, int code, const std::string &msg);
 }  // namespace gwat_internal
 #endif

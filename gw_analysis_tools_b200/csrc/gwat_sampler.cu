@@ -185,22 +185,86 @@ __global__ void k_gather(const double *__restrict__ pos, const int *__restrict__
 	if (t >= n * P) return;
 	out[t] = pos[(size_t)idx[t / P] * P + t % P];
 }
-// transformations + eigen-system of matrix t, written to slot t of the outputs; ok[t] = 0 when the result has a NaN
-__global__ void k_fisher_eigen(double *__restrict__ F, const double *__restrict__ params, int n, int P, int pv2, int alpha_unit_fix,
-                               int ppE_Nmod, double *__restrict__ out_vals, double *__restrict__ out_vecs, int *__restrict__ ok_out)
+// transformations + eigen-system of matrix t = blockIdx.x, written to slot t of the outputs; ok[t] = 0 when the result has a NaN.
+// One warp per matrix: the cyclic Jacobi sweep of jacobi_eigen (gwat_sampler_math.h) with lane k owning row/column k of each
+// rotation -- the same rotations in the same order, 3 warp-synchronous updates per rotation instead of 3 serial loops.
+__global__ void __launch_bounds__(32) k_fisher_eigen(double *__restrict__ F, const double *__restrict__ params, int n_mat, int P, int pv2,
+                                                    int alpha_unit_fix, int ppE_Nmod, double *__restrict__ out_vals,
+                                                    double *__restrict__ out_vecs, int *__restrict__ ok_out)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
-	double *A = F + (size_t)t * P * P;
-	fisher_transformations(A, P, pv2 != 0, alpha_unit_fix != 0, ppE_Nmod, params + (size_t)t * P);
-	double work[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM], vals[GWAT_B200_MAX_DIM], vecs[GWAT_B200_MAX_DIM * GWAT_B200_MAX_DIM];
-	for (int i = 0; i < P * P; i++) work[i] = A[i];
-	const bool ok = jacobi_eigen(work, P, vals, vecs);
-	if (ok) {
-		for (int i = 0; i < P; i++) out_vals[(size_t)t * P + i] = vals[i];
-		for (int i = 0; i < P * P; i++) out_vecs[(size_t)t * P * P + i] = vecs[i];
+	constexpr int N = GWAT_B200_MAX_DIM;
+	__shared__ double A[N * N], V[N * N], vals[N];
+	__shared__ int order[N];
+	const int t = blockIdx.x, lane = threadIdx.x, n = P;
+	if (t >= n_mat) return;
+	double *Fg = F + (size_t)t * P * P;
+	if (lane == 0) fisher_transformations(Fg, P, pv2 != 0, alpha_unit_fix != 0, ppE_Nmod, params + (size_t)t * P);
+	__syncwarp();
+	for (int i = lane; i < n * n; i += 32) {
+		A[i] = Fg[i];
+		V[i] = (i / n == i % n) ? 1.0 : 0.0;
 	}
-	if (ok_out) ok_out[t] = ok ? 1 : 0;
+	__syncwarp();
+	for (int sweep = 0; sweep < 60; sweep++) {
+		double off = 0, diag = 0;
+		if (lane < n) {
+			diag = A[lane * n + lane] * A[lane * n + lane];
+			for (int j = lane + 1; j < n; j++) off += A[lane * n + j] * A[lane * n + j];
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			off += __shfl_xor_sync(0xffffffffu, off, o);
+			diag += __shfl_xor_sync(0xffffffffu, diag, o);
+		}
+		if (!(off > 1e-32 * diag)) break;
+		for (int p = 0; p < n - 1; p++) {
+			for (int q = p + 1; q < n; q++) {
+				const double apq = A[p * n + q];
+				if (apq == 0.0) continue;  // uniform across the warp
+				const double app = A[p * n + p], aqq = A[q * n + q];
+				const double theta = (aqq - app) / (2.0 * apq);
+				const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+				const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+				__syncwarp();
+				if (lane < n) {
+					const double akp = A[lane * n + p], akq = A[lane * n + q];
+					A[lane * n + p] = c * akp - sn * akq;
+					A[lane * n + q] = sn * akp + c * akq;
+				}
+				__syncwarp();
+				if (lane < n) {
+					const double apk = A[p * n + lane], aqk = A[q * n + lane];
+					A[p * n + lane] = c * apk - sn * aqk;
+					A[q * n + lane] = sn * apk + c * aqk;
+					const double vpk = V[p * n + lane], vqk = V[q * n + lane];
+					V[p * n + lane] = c * vpk - sn * vqk;
+					V[q * n + lane] = sn * vpk + c * vqk;
+				}
+				__syncwarp();
+			}
+		}
+	}
+	if (lane < n) vals[lane] = A[lane * n + lane];
+	__syncwarp();
+	if (lane == 0) {  // ascending order (Eigen's convention): insertion sort of the indices
+		for (int i = 0; i < n; i++) {
+			int j = i;
+			while (j > 0 && vals[order[j - 1]] > vals[i]) {
+				order[j] = order[j - 1];
+				j--;
+			}
+			order[j] = i;
+		}
+	}
+	__syncwarp();
+	bool good = true;
+	for (int i = lane; i < n * n; i += 32) good = good && (V[i] == V[i]);
+	if (lane < n) good = good && (vals[lane] == vals[lane]);
+	good = __all_sync(0xffffffffu, good);
+	if (good) {
+		if (lane < n) out_vals[(size_t)t * P + lane] = vals[order[lane]];
+		for (int i = lane; i < n * n; i += 32) out_vecs[(size_t)t * P * P + i] = V[order[i / n] * n + i % n];
+	}
+	if (ok_out && lane == 0) ok_out[t] = good ? 1 : 0;
 }
 // staged eigen-systems -> the chains they belong to (update_fisher's tail, :676-711: a NaN result keeps the old system)
 __global__ void k_fisher_commit(const int *__restrict__ idx, const int *__restrict__ ok, int n, int P, const double *__restrict__ vals,
@@ -354,6 +418,20 @@ struct gwat_b200_sampler {
 		long long next_sched = 0, h_counter = 0;
 	} rf[2];
 	int lookahead = 0;
+	// deferred refreshes (fisher_deferred): chains that came due since the last swap-sweep boundary, one staging set, one
+	// pass in flight
+	bool deferred = false;
+	std::vector<int> due;
+	std::vector<char> due_mark;
+	int *g_idx = nullptr, *g_ok = nullptr;
+	double *g_par = nullptr, *g_mat = nullptr, *g_vals = nullptr, *g_vecs = nullptr;
+	int g_inflight = 0;
+	cudaEvent_t ev_g_gathered = nullptr, ev_g_done = nullptr;
+	static constexpr int GNP = 16;
+	int *gh_idx = nullptr;  // pinned [GNP][C]
+	cudaEvent_t gh_ev[GNP] = {};
+	bool gh_used[GNP] = {};
+	long long gh_counter = 0;
 	int nlanes = 1, lane_c0[2] = {0, 0}, lane_n[2] = {0, 0};
 	cudaStream_t st[2] = {nullptr, nullptr}, st_like[2] = {nullptr, nullptr}, st_fisher = nullptr;
 	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -429,7 +507,7 @@ int refresh_schedule(gwat_b200_sampler *s, int ln, long long t, std::vector<int>
 	if (int rc = gwat_internal::fisher_mcmc_dev(ctx, s->method.c_str(), &s->mod, P, s->opt.fisher_deriv_order, n, r.d_par[ds], s->gmst,
 	                                            r.d_mat[ds], sf))
 		return rc;
-	k_fisher_eigen<<<(n + 31) / 32, 32, 0, sf>>>(r.d_mat[ds], r.d_par[ds], n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, r.d_vals[ds],
+	k_fisher_eigen<<<n, 32, 0, sf>>>(r.d_mat[ds], r.d_par[ds], n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, r.d_vals[ds],
 	                                             r.d_vecs[ds], r.d_ok[ds]);
 	SCUDA(ctx, cudaEventRecord(r.ev_done[ds], sf));
 	s->last_launches += 2;
@@ -448,6 +526,56 @@ int refresh_commit(gwat_b200_sampler *s, int ln, long long t)
 	k_fisher_commit<<<n, 64, 0, st>>>(r.d_idx[ds], r.d_ok[ds], n, P, r.d_vals[ds], r.d_vecs[ds], s->d.fvals, s->d.fvecs, s->d.counters);
 	r.n_in_slot[ds] = 0;
 	s->last_launches += 1;
+	return 0;
+}
+
+// One Fisher pass for `list` (chain indices), gathered from the current positions on `st`, computed on the side stream into the
+// group staging set.
+int group_launch(gwat_b200_sampler *s, const std::vector<int> &list, cudaStream_t st)
+{
+	gwat_b200_ctx *ctx = s->ctx;
+	const int n = (int)list.size(), P = s->k.P;
+	const int ps = (int)(s->gh_counter++ % gwat_b200_sampler::GNP);
+	if (s->gh_used[ps]) SCUDA(ctx, cudaEventSynchronize(s->gh_ev[ps]));
+	int *h = s->gh_idx + (size_t)ps * s->k.C;
+	std::memcpy(h, list.data(), sizeof(int) * n);
+	SCUDA(ctx, cudaMemcpyAsync(s->g_idx, h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+	SCUDA(ctx, cudaEventRecord(s->gh_ev[ps], st));
+	s->gh_used[ps] = true;
+	k_gather<<<(n * P + 255) / 256, 256, 0, st>>>(s->d.pos, s->g_idx, n, P, s->g_par);
+	SCUDA(ctx, cudaEventRecord(s->ev_g_gathered, st));
+	cudaStream_t sf = s->st_fisher;
+	SCUDA(ctx, cudaStreamWaitEvent(sf, s->ev_g_gathered, 0));
+	if (int rc = gwat_internal::fisher_mcmc_dev(ctx, s->method.c_str(), &s->mod, P, s->opt.fisher_deriv_order, n, s->g_par, s->gmst, s->g_mat, sf))
+		return rc;
+	k_fisher_eigen<<<n, 32, 0, sf>>>(s->g_mat, s->g_par, n, P, s->pp.pv2, s->alpha_fix ? 1 : 0, s->ppE_Nmod, s->g_vals, s->g_vecs, s->g_ok);
+	SCUDA(ctx, cudaEventRecord(s->ev_g_done, sf));
+	s->g_inflight = n;
+	s->last_launches += 2;
+	return 0;
+}
+
+int group_commit(gwat_b200_sampler *s, cudaStream_t st)
+{
+	if (s->g_inflight == 0) return 0;
+	gwat_b200_ctx *ctx = s->ctx;
+	SCUDA(ctx, cudaStreamWaitEvent(st, s->ev_g_done, 0));
+	k_fisher_commit<<<s->g_inflight, 64, 0, st>>>(s->g_idx, s->g_ok, s->g_inflight, s->k.P, s->g_vals, s->g_vecs, s->d.fvals, s->d.fvecs,
+	                                              s->d.counters);
+	s->g_inflight = 0;
+	s->last_launches += 1;
+	return 0;
+}
+
+// Deferred mode, at a swap-sweep boundary (lanes joined on st[0]): install the pass started at the previous boundary, start
+// one for the chains that came due since.
+int deferred_boundary(gwat_b200_sampler *s)
+{
+	if (int rc = group_commit(s, s->st[0])) return rc;
+	if (s->due.empty()) return 0;
+	if (int rc = group_launch(s, s->due, s->st[0])) return rc;
+	for (int c : s->due) s->due_mark[c] = 0;
+	s->due.clear();
 	return 0;
 }
 
@@ -473,6 +601,8 @@ int swap_sweep(gwat_b200_sampler *s)
 		s->last_launches += 3;
 	}
 	s->sweep += 1;
+	if (s->deferred)
+		if (int rc = deferred_boundary(s)) return rc;
 	if (s->nlanes > 1) {
 		SCUDA(ctx, cudaEventRecord(s->ev_join, st));
 		SCUDA(ctx, cudaStreamWaitEvent(s->st[1], s->ev_join, 0));
@@ -568,7 +698,7 @@ int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	if (rc == 0) {
 		SCUDA(ctx, cudaMemsetAsync(d_vals, 0xff, sizeof(double) * W * P, st));  // NaN where the decomposition fails
 		SCUDA(ctx, cudaMemsetAsync(d_vecs, 0xff, sizeof(double) * W * P * P, st));
-		k_fisher_eigen<<<(W + 31) / 32, 32, 0, st>>>(d_mat, d_par, W, P, pp.pv2, af ? 1 : 0, nm, d_vals, d_vecs, nullptr);
+		k_fisher_eigen<<<W, 32, 0, st>>>(d_mat, d_par, W, P, pp.pv2, af ? 1 : 0, nm, d_vals, d_vecs, nullptr);
 		ctx->launches += 1;
 		if (fisher) SCUDA(ctx, cudaMemcpyAsync(fisher, d_mat, sizeof(double) * W * P * P, cudaMemcpyDeviceToHost, st));
 		if (eigenvalues) SCUDA(ctx, cudaMemcpyAsync(eigenvalues, d_vals, sizeof(double) * W * P, cudaMemcpyDeviceToHost, st));
@@ -611,8 +741,12 @@ void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 		if (s->st_like[i]) cudaStreamDestroy(s->st_like[i]);
 	}
 	if (s->st_fisher) cudaStreamDestroy(s->st_fisher);
-	for (cudaEvent_t e : {s->ev_join, s->ev_t0, s->ev_t1})
+	for (cudaEvent_t e : {s->ev_join, s->ev_t0, s->ev_t1, s->ev_g_gathered, s->ev_g_done})
 		if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : s->gh_ev)
+		if (e) cudaEventDestroy(e);
+	for (void *p : {(void *)s->g_idx, (void *)s->g_ok, (void *)s->g_par, (void *)s->g_mat, (void *)s->g_vals, (void *)s->g_vecs}) cudaFree(p);
+	if (s->gh_idx) cudaFreeHost(s->gh_idx);
 	delete s;
 }
 
@@ -686,14 +820,29 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(dalloc(s->swap_src, (size_t)C));
 	int prio_lo = 0, prio_hi = 0;
 	SC_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-	s->lookahead = std::max(0, std::min(o.fisher_lookahead, 64));
+	s->lookahead = 0;
+	s->deferred = o.fisher_exist && o.fisher_deferred != 0;
+	if (s->deferred) {
+		const size_t n = (size_t)C;
+		SC_TRY(dalloc(s->g_idx, n));
+		SC_TRY(dalloc(s->g_ok, n));
+		SC_TRY(dalloc(s->g_par, n * P));
+		SC_TRY(dalloc(s->g_mat, n * P * P));
+		SC_TRY(dalloc(s->g_vals, n * P));
+		SC_TRY(dalloc(s->g_vecs, n * P * P));
+		SC_TRY(cudaEventCreateWithFlags(&s->ev_g_gathered, cudaEventDisableTiming));
+		SC_TRY(cudaEventCreateWithFlags(&s->ev_g_done, cudaEventDisableTiming));
+		for (int k = 0; k < gwat_b200_sampler::GNP; k++) SC_TRY(cudaEventCreateWithFlags(&s->gh_ev[k], cudaEventDisableTiming));
+		SC_TRY(cudaMallocHost((void **)&s->gh_idx, (size_t)gwat_b200_sampler::GNP * n * sizeof(int)));
+		s->due_mark.assign(C, 0);
+	}
 	for (int i = 0; i < s->nlanes; i++) {
 		// short latency-bound kernels on a high-priority stream, the FP64-bound bin kernel on a low-priority one: the other
 		// lane's setup is then scheduled into the SM slots the bin kernel frees instead of waiting for its last CTA
 		SC_TRY(cudaStreamCreateWithPriority(&s->st[i], cudaStreamNonBlocking, prio_hi));
 		SC_TRY(cudaStreamCreateWithPriority(&s->st_like[i], cudaStreamNonBlocking, prio_lo));
 		SC_TRY(cudaEventCreateWithFlags(&s->ev_lane[i], cudaEventDisableTiming));
-		if (!o.fisher_exist) continue;
+		if (!o.fisher_exist || s->deferred) continue;
 		gwat_b200_sampler::RefreshLane &r = s->rf[i];
 		const size_t n = (size_t)s->lane_n[i];
 		r.ND = s->lookahead + 1;
@@ -746,6 +895,16 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 		if (!(lp[c] > -INFINITY) || !(ll[c] == ll[c]))
 			return bail(gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_create: initial position of chain " + std::to_string(c) +
 			                                                                 " has zero prior or an undefined likelihood"));
+	if (s->deferred) {
+		// every chain starts with the eigen-system of its initial position (the reference computes it at the chain's first
+		// Fisher step, :434-437); the refresh counters then run from zero
+		std::vector<int> all(C);
+		for (int c = 0; c < C; c++) all[c] = c;
+		if (int rc = group_launch(s, all, st)) return bail(rc);
+		if (int rc = group_commit(s, st)) return bail(rc);
+		SC_TRY(cudaStreamSynchronize(st));
+		std::fill(s->h_fisher_ct.begin(), s->h_fisher_ct.end(), 0);
+	}
 #undef SC_TRY
 	lock.unlock();
 	*out = s;
@@ -775,9 +934,15 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 			const int c0 = s->lane_c0[ln], n = s->lane_n[ln];
 			if (n == 0) continue;
 			cudaStream_t st = s->st[ln];
-			if (s->opt.fisher_exist) {
-				// Fisher refreshes run `lookahead` steps ahead of their use, on the side stream (0 = at the step that uses them,
-				// which is the reference's schedule exactly)
+			if (s->opt.fisher_exist && s->deferred) {
+				fisher_schedule(s, ln, step, flagged);
+				for (int c : flagged)
+					if (!s->due_mark[c]) {
+						s->due_mark[c] = 1;
+						s->due.push_back(c);
+					}
+			} else if (s->opt.fisher_exist) {
+				// the reference's schedule: a chain's Fisher matrix is recomputed at the step that first uses it
 				gwat_b200_sampler::RefreshLane &r = s->rf[ln];
 				while (r.next_sched <= step + s->lookahead) {
 					if (int rc = refresh_schedule(s, ln, r.next_sched, flagged)) return rc;

@@ -41,7 +41,7 @@ class Options(C.Structure):
     _fields_ = [("chain_N", C.c_int), ("dimension", C.c_int), ("swp_freq", C.c_int), ("swap_rate", C.c_double),
                 ("history_length", C.c_int), ("history_update", C.c_int), ("fisher_exist", C.c_int),
                 ("fisher_update_number", C.c_int), ("fisher_deriv_order", C.c_int), ("check_stepsize_freq", C.c_int),
-                ("seed", C.c_ulonglong), ("lanes", C.c_int), ("record_cold", C.c_int), ("fisher_lookahead", C.c_int)]
+                ("seed", C.c_ulonglong), ("lanes", C.c_int), ("record_cold", C.c_int), ("fisher_deferred", C.c_int)]
 
 
 def prior_defaults(**kw):

@@ -64,10 +64,12 @@ typedef struct gwat_b200_sampler_options {
 	unsigned long long seed;
 	int lanes;                  /* 1 or 2 concurrent halves */
 	int record_cold;            /* keep the positions of the T=1 chains of every step in a device buffer (gwat_b200_sampler_cold) */
-	int fisher_lookahead;       /* 0: a chain's Fisher matrix is recomputed at the step that first uses it, at the position it has
-	                               then (the reference's schedule).  k > 0: it is computed k steps earlier, at the position the
-	                               chain has then, on a side stream that overlaps the likelihood kernels; same refresh cadence,
-	                               same use, a matrix that is k steps staler out of the ~400 steps it is used for. */
+	int fisher_deferred;        /* 0: a chain's Fisher matrix is recomputed at the step that first needs it, at the position it has
+	                               then (the reference's schedule, :434-437).  1: the chains that come due between two swap sweeps
+	                               are refreshed together at the next sweep, on a side stream that overlaps the likelihood kernels,
+	                               and the new eigen-systems are installed at the sweep after that: same cadence per chain, same
+	                               use, matrices up to 2 swp_freq steps staler out of the ~400 steps each is used for; all chains get
+	                               their first matrix at creation. */
 } gwat_b200_sampler_options;
 
 typedef struct gwat_b200_sampler gwat_b200_sampler;

@@ -147,7 +147,7 @@ def test_lane_split_is_bitwise_invisible(ctx):
     out = []
     for lanes in (1, 2):
         s = smp.Sampler(ctx, wl.method, temps, init, prior, wl.gmst, wl.T_segment, wl.mod, seed=5, lanes=lanes, swp_freq=2,
-                        history_length=20, fisher_update_number=10, record_cold=1, fisher_lookahead=3)
+                        history_length=20, fisher_update_number=10, record_cold=1, fisher_deferred=1)
         s.run(37)
         s.run(23)
         out.append((s.state(), s.counters(), s.cold_chains()))

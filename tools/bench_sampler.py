@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--fisher-update", type=int, default=200)
     ap.add_argument("--history", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--lookahead", type=int, default=0)
+    ap.add_argument("--deferred", type=int, default=0)
     args = ap.parse_args()
     wl = workloads.make(args.config, W=args.chains or None, L=args.bins or None)
     ctx = engine.Context(0)
@@ -58,7 +58,7 @@ def main():
     like_rate = n_like * C_ / (time.perf_counter() - t0)
     s = smp.Sampler(ctx, wl.method, temps, init, prior, wl.gmst, wl.T_segment, wl.mod, seed=1, lanes=args.lanes,
                     fisher_exist=0 if args.no_fisher else 1, fisher_update_number=args.fisher_update, history_length=args.history,
-                    fisher_lookahead=args.lookahead)
+                    fisher_deferred=args.deferred)
     s.run(args.warmup)
     t0 = time.perf_counter()
     s.run(args.steps)
@@ -66,16 +66,22 @@ def main():
     dev_ms = s.last_ms
     ct, widths = s.counters()
     pos, ll, lp = s.state()
+    ctx.loglike_mcmc_batch(wl.method, pos, wl.gmst, wl.T_segment, wl.mod)  # where the ensemble is now: active bins, kernel time
+    final_active, final_kernel_ms = ctx.last_active_bins / (C_ * wl.L), ctx.last_kernel_ms
+    ctx.loglike_mcmc_batch(wl.method, init, wl.gmst, wl.T_segment, wl.mod)
+    init_active, init_kernel_ms = ctx.last_active_bins / (C_ * wl.L), ctx.last_kernel_ms
     line = {"metric": "PTMCMC chain-steps/sec (%s, %d chains = %d ensembles x %d temperatures, %d bins, %d detectors)" % (
                 wl.method, C_, C_ // nt, nt, wl.L, wl.D),
             "value": C_ * args.steps / (dev_ms * 1e-3), "unit": "chain-steps/s", "wall_value": C_ * args.steps / wall,
-            "ms_per_step": dev_ms / args.steps, "steps": args.steps, "lanes": args.lanes, "fisher": not args.no_fisher, "fisher_lookahead": args.lookahead,
+            "ms_per_step": dev_ms / args.steps, "steps": args.steps, "lanes": args.lanes, "fisher": not args.no_fisher, "fisher_deferred": args.deferred,
             "likelihood_only_evals_per_s": like_rate, "fraction_of_likelihood_ceiling": C_ * args.steps / wall / like_rate,
             "launches_per_step": s.last_launches / args.steps,
             "accept_fraction": float(ct["step_accept"].sum() / (ct["step_accept"].sum() + ct["step_reject"].sum())),
             "swap_accept_fraction": float(ct["swap_accept"].sum() / max(1, ct["swap_accept"].sum() + ct["swap_reject"].sum())),
             "fisher_updates": int(ct["fisher_updates"].sum()), "fisher_nan": int(ct["fisher_nan"].sum()),
-            "finite": bool(np.isfinite(ll).all())}
+            "finite": bool(np.isfinite(ll).all()),
+            "active_bin_fraction": {"initial": init_active, "final": final_active},
+            "k_loglike_ms_full_ensemble": {"initial": init_kernel_ms, "final": final_kernel_ms}}
     if args.cpu_sample:
         from oracle import gwat_ref
         if gwat_ref.available():
