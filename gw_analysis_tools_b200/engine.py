@@ -19,7 +19,8 @@ _lib = None
 EXPORTS = [
     "gwat_b200_abi_version", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
     "gwat_b200_ctx_destroy", "gwat_b200_last_error", "gwat_b200_set_network", "gwat_b200_loglike_mcmc_batch",
-    "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_fourier_waveform_batch",
+    "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_loglike_maximized_batch",
+    "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
     "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
@@ -131,6 +132,13 @@ class Context:
         out = np.empty(W)
         self._check(self._lib.gwat_b200_loglike_mcmc_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
                                                            P, W, _p(params), C.c_double(gmst), C.c_double(T_segment), _p(out)))
+        return out
+
+    def loglike_maximized_batch(self, method, sources):
+        """tc/phic-maximised log-likelihoods (the reference's intrinsic samplers), one per source."""
+        arr, W = _src_array(sources)
+        out = np.empty(W)
+        self._check(self._lib.gwat_b200_loglike_maximized_batch(self._h, method.encode(), W, arr, _p(out)))
         return out
 
     def loglike_mcmc_batch_dev(self, method, d_params_ptr, W, P, gmst, T_segment, d_logL_ptr, mod=None, stream=None):

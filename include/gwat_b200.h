@@ -156,6 +156,16 @@ int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *generation_method, i
 
 /* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
 
+/* tc/phic-maximised log-likelihood of the reference's "intrinsic" samplers, summed over the network's detectors:
+ *   maximized_Log_Likelihood_aligned_spin_internal (src/mcmc_gw.cpp:595-652) for the IMRPhenomD family,
+ *   maximized_Log_Likelihood_unaligned_spin_internal (src/mcmc_gw.cpp:660-795) for the IMRPhenomPv2 family,
+ * called as the intrinsic branches of MCMC_likelihood_wrapper do (src/mcmc_gw.cpp:2603-2722): the sources' psi, phiRef,
+ * incl_angle, tc, f_ref are overridden (0, 1, 0, 1, 10 or 20) and the response is the + polarisation (F+ = 1, Fx = 0).
+ * Needs a uniform grid, Simpson's rule and data (the time axis is an FFT of length L; cuFFT replaces FFTW).  Like the
+ * reference's, the value is not normalised: constant (d|d) terms are left out. */
+int gwat_b200_loglike_maximized_batch(gwat_b200_ctx *ctx, const char *generation_method, int W, const gwat_b200_source *sources,
+                                      double *logL);
+
 /*
  * W evaluations of fourier_waveform<double> (src/waveform_generator.cpp:104-294) on the context's grid.
  * Outputs are split real/imag like fourier_waveform_py (src/gwatpy_wrapping.cpp), shape [W*L] row-major; any may be NULL.

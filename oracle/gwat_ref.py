@@ -134,6 +134,17 @@ def loglike_mcmc_batch(method, mod, params, gmst, T_segment, detectors, f, psd, 
     return (out, srcs) if return_sources else out
 
 
+def loglike_maximized_batch(method, sources, detectors, f, psd, data, nthreads=0):
+    """The reference's tc/phic-maximised likelihoods (src/mcmc_gw.cpp:595-795) as its intrinsic samplers call them."""
+    arr, W = _src_array(sources)
+    f, psd = _f64(f), _f64(psd)
+    dre, dim = _f64(data.real), _f64(data.imag)
+    out = np.zeros(W)
+    lib().oracle_ref_loglike_maximized_batch(method.encode(), W, arr, len(detectors), _dets(detectors), _p(f), f.size, _p(psd),
+                                             _p(dre), _p(dim), int(nthreads), _p(out))
+    return out
+
+
 def fisher_numerical_batch(method, sources, detectors, f, psd, dimension, order=4, detector_index=-1,
                            reference_index=0, nthreads=0, fma_build=False):
     arr, S = _src_array(sources)

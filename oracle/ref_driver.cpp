@@ -355,6 +355,60 @@ int oracle_ref_loglike_batch(const char *method, int W, const gwat_b200_source *
 	return 0;
 }
 
+// W x the intrinsic branches of MCMC_likelihood_wrapper (src/mcmc_gw.cpp:2603-2722): coalescence-frame source, then per
+// detector maximized_Log_Likelihood_aligned_spin_internal (PhenomD family: horizon response with theta = phi = psi = 0) or
+// maximized_Log_Likelihood_unaligned_spin_internal (PhenomP family: both polarisations).
+int oracle_ref_loglike_maximized_batch(const char *method, int W, const gwat_b200_source *sources, int D,
+                                       const char *const *detectors, const double *f, int L, const double *psd,
+                                       const double *data_re, const double *data_im, int nthreads, double *logL)
+{
+	std::vector<std::string> dets(D);
+	for (int d = 0; d < D; d++) dets[d] = detectors[d];
+	std::vector<std::vector<std::complex<double>>> data(D, std::vector<std::complex<double>>(L));
+	for (int d = 0; d < D; d++)
+		for (int i = 0; i < L; i++) data[d][i] = std::complex<double>(data_re[(size_t)d * L + i], data_im[(size_t)d * L + i]);
+	if (nthreads <= 0) nthreads = omp_get_max_threads();
+	const std::string m(method);
+	const bool precessing = m.find("IMRPhenomP") != std::string::npos;
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+	for (int w = 0; w < W; w++) {
+		ParamBox b;
+		to_gen_params(sources[w], b);
+		gen_params_base<double> &gp = b.gp;
+		gp.theta = 0;
+		gp.phi = 0;
+		gp.psi = 0;
+		gp.phiRef = 1;
+		gp.f_ref = precessing ? 20 : 10;
+		gp.incl_angle = 0;
+		gp.tc = 1;
+		fftw_outline plan;
+		allocate_FFTW_mem_forward(&plan, L);
+		double ll = 0;
+		double *fp = const_cast<double *>(f);
+		if (!precessing) {
+			std::vector<std::complex<double>> response(L);
+			for (int d = 0; d < D; d++) {
+				fourier_detector_response_horizon(fp, L, response.data(), dets[d], m, &gp);
+				ll += maximized_Log_Likelihood_aligned_spin_internal(data[d].data(), const_cast<double *>(psd) + (size_t)d * L, fp,
+				                                                     response.data(), (size_t)L, &plan);
+			}
+		} else {
+			waveform_polarizations<double> wp;
+			assign_polarizations(m, &wp);
+			wp.allocate_memory(L);
+			fourier_waveform(fp, L, &wp, m, &gp);
+			for (int d = 0; d < D; d++)
+				ll += maximized_Log_Likelihood_unaligned_spin_internal(data[d].data(), const_cast<double *>(psd) + (size_t)d * L, fp, wp.hplus,
+				                                                       wp.hcross, (size_t)L, &plan);
+			wp.deallocate_memory();
+		}
+		deallocate_FFTW_mem(&plan);
+		logL[w] = ll;
+	}
+	return 0;
+}
+
 // W x MCMC_likelihood_wrapper, extrinsic branch (src/mcmc_gw.cpp:2569-2791) with the globals passed explicitly:
 //   MCMC_prep_params (:2492) -> repack_parameters("MCMC_"+method) (src/fisher.cpp:2167) -> tc_ref = T - tc (:2467) ->
 //   create_coherent_GW_detection (:2474) -> sum_d Log_Likelihood_internal (:2476).

@@ -63,6 +63,12 @@ def derived_data(resp):
     return 0.9 * np.exp(0.3j) * resp
 
 
+def maximized_data(gold, gspec):
+    """Data for the maximised-likelihood cases: the response of ONE fixed case per grid (plain IMRPhenomD / IMRPhenomD_NRT),
+    so that every other family is a mismatched template and its phase modifications matter."""
+    return derived_data(gold[("D_bbh" if tuple(gspec) == tuple(GRID_BBH) else "NRT_love") + "/resp"])
+
+
 def grid(spec):
     fmin, df, L = spec
     return fmin + df * np.arange(L, dtype=np.float64)

@@ -20,7 +20,23 @@ from gw_analysis_tools_b200 import workloads  # noqa: E402
 from oracle import gwat_ref as R  # noqa: E402
 
 
+def maximized():
+    """tc/phic-maximised likelihoods of every family case against the case's derived data."""
+    gold = np.load(os.path.join(HERE, "waveforms_v1.npz"))
+    mx = {}
+    for name, method, kw, gspec in cases.CASES:
+        f = cases.grid(gspec)
+        src = cases.source_from_bytes(gold[name + "/src"])
+        data = cases.maximized_data(gold, gspec)
+        psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+        mx[name] = R.loglike_maximized_batch(method, [src], cases.DETECTORS, f, psd, data)[0]
+        print("%-12s %-28s maximised logL %.12e" % (name, method, mx[name]))
+    np.savez_compressed(os.path.join(HERE, "maximized_v1.npz"), **mx)
+
+
 def main():
+    if "--only-maximized" in sys.argv:
+        return maximized()
     out = {}
     for name, method, kw, gspec in cases.CASES:
         f = cases.grid(gspec)
@@ -83,7 +99,8 @@ def main():
     ll = R.loglike_mcmc_batch(wl.method, wl.mod, wl.params, wl.gmst, wl.T_segment, wl.detectors, wl.f, wl.psd, data)
     np.savez_compressed(os.path.join(HERE, "smoke_cfg2.npz"), logL=ll, data=data)
     np.savez_compressed(os.path.join(HERE, "mcmc_v1.npz"), **mo)
-    for fn in ("waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz"):
+    maximized()
+    for fn in ("waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz", "maximized_v1.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
 
 
