@@ -37,7 +37,7 @@ GWAT_HD cplx carrier_bin(const WalkerCoef &w, double f, double sf_hi, double sf_
 	if (Fam::nrt) nrt_bin(c, f, p, logf, amp, phase);
 	phase = phenomd_apply_time_phase(c, f, phase);
 	double sn, cs;
-	sincos(phase, &sn, &cs);
+	fast_sincos(phase, &sn, &cs);
 	if (Fam::nrt) amp *= nrt_taper_factor(c, f);
 	return cplx{amp * cs, -(amp * sn)};
 }
@@ -62,7 +62,7 @@ GWAT_HD cplx project_bin(const DetCoef &dc, cplx hp, cplx hc, double f, bool wit
 	cplx r{dc.Fplus * hp.re + dc.Fcross * hc.re, dc.Fplus * hp.im + dc.Fcross * hc.im};
 	if (with_shift) {
 		double sn, cs;
-		sincos(mul_rn(dc.tshift, f), &sn, &cs);
+		fast_sincos(mul_rn(dc.tshift, f), &sn, &cs);
 		r = cplx{r.re * cs - r.im * sn, r.re * sn + r.im * cs};
 	}
 	return r;

@@ -96,7 +96,7 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	const double epsilon = ((((pc.ecoef[0] * roc3 + pc.ecoef[1] * roc2) + pc.ecoef[2] * roc) + pc.ecoef[3] * logom) + pc.ecoef[4] * oc) -
 	                       pc.epsilon_offset;
 	double s1, c1;
-	sincos(alpha, &s1, &c1);
+	fast_sincos(alpha, &s1, &c1);
 	const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;
 	// sum_m Y_m (d^2_{-m} e^{-i m alpha} +- d^2_m e^{+i m alpha}) with real Y_m, grouped by |m|
 	const double *Y = pc.Y;  // m = -2..2
@@ -168,7 +168,7 @@ GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, doubl
 	}
 	nact += 1.0;
 	double sn, cs;
-	sincos(arg, &sn, &cs);
+	fast_sincos(arg, &sn, &cs);
 	double hh = 0.0, Sre = 0.0, Sim = 0.0;
 #pragma unroll
 	for (int d = 0; d < D; d++) {
@@ -183,7 +183,7 @@ GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, doubl
 			st.z[d] = cplx{zd.re * st.E[d].re - zd.im * st.E[d].im, zd.re * st.E[d].im + zd.im * st.E[d].re};
 		} else {
 			double s_, c_;
-			sincos(mul_rn(dc.tshift, f), &s_, &c_);
+			fast_sincos(mul_rn(dc.tshift, f), &s_, &c_);
 			zd = cplx{c_, -s_};
 		}
 		// t = data * z ;  S += w * conj(G) * t

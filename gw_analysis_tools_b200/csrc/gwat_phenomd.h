@@ -312,7 +312,7 @@ GWAT_HD double phenomd_phase_mr(const DCoef &c, double f, double sixth)
 	double t = add_rn(c.alpha0, mul_rn(c.alpha1, Mf));
 	t = sub_rn(t, mul_rn(c.alpha2, fast_rcp(Mf)));
 	t = add_rn(t, mul_rn(c.alpha3_43, Mf34));
-	t = add_rn(t, mul_rn(c.alpha4, atan(mul_rn(sub_rn(f, c.alpha5fRD), c.inv_fdamp))));
+	t = add_rn(t, mul_rn(c.alpha4, fast_atan(mul_rn(sub_rn(f, c.alpha5fRD), c.inv_fdamp))));
 	double ph = mul_rn(c.inv_eta, t);
 	if (Fam::ppe == PPE_IMR) ph = ppe_phase_terms(c, s2, ph);
 	return ph;

@@ -345,7 +345,7 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 
 	// twist-up: sum over m of exp(-+ i m alpha) d^2 Y
 	double sa, ca;
-	sincos(alpha, &sa, &ca);
+	fast_sincos(alpha, &sa, &ca);
 	// e^{i k alpha}, k = -2..2.  exp(-i alpha) is formed as 1/exp(i alpha) in the reference; |e^{i alpha}| = 1 to rounding.
 	const double inv = 1. / (ca * ca + sa * sa);
 	const cplx e1{ca, sa}, em1{ca * inv, -sa * inv};
@@ -370,7 +370,7 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 	arg = sub_rn(arg, p.phic);
 	arg = add_rn(arg, mul_rn(p.tcorr_2pi, f));
 	double sn, cs;
-	sincos(arg, &sn, &cs);
+	fast_sincos(arg, &sn, &cs);
 	const cplx carrier{amp * cs, -(amp * sn)};
 	const cplx hplus{carrier.re * hpf.re - carrier.im * hpf.im, carrier.re * hpf.im + carrier.im * hpf.re};
 	const cplx hcross{carrier.re * hcf.re - carrier.im * hcf.im, carrier.re * hcf.im + carrier.im * hcf.re};
