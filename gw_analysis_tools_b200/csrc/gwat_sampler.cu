@@ -39,6 +39,7 @@ struct StepConst {
 	int history_update, check_stepsize_freq;
 	int fisher_exist;
 	int record_cold;
+	int chain_offset;  // global index of chain 0 (several GPUs: every rank draws what one GPU would draw for its chains)
 };
 
 struct DevState {
@@ -85,9 +86,9 @@ __global__ void k_propose(DevState d, StepConst k, gwat_b200_prior prior, PriorP
 	double bounds[4];
 	step_boundaries(T, k.fisher_exist != 0, step > k.H, bounds);
 	double alpha, u_acc, u_pick, u_pick2, n0, n1;
-	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u_acc);
-	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_PICK, u_pick, u_pick2);
-	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_NORMAL, n0, n1);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)(k.chain_offset + c), DRAW_TYPE_ACCEPT, alpha, u_acc);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)(k.chain_offset + c), DRAW_PICK, u_pick, u_pick2);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)(k.chain_offset + c), DRAW_NORMAL, n0, n1);
 	const double z = normal_from(n0, n1);
 	const int type = step_type(alpha, bounds);
 	const double *cur = d.pos + (size_t)c * P;
@@ -100,7 +101,7 @@ __global__ void k_propose(DevState d, StepConst k, gwat_b200_prior prior, PriorP
 		int i, j;
 		de_pick(k.H, u_pick, u_pick2, i, j);
 		double beta, unused;
-		uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_DE_SCALE, beta, unused);
+		uniform2(k.seed, (uint64_t)step, (uint32_t)(k.chain_offset + c), DRAW_DE_SCALE, beta, unused);
 		propose_de(cur, prop, P, d.hist + ((size_t)c * k.H + i) * P, d.hist + ((size_t)c * k.H + j) * P, beta, z, w[P + 0]);
 	} else {
 		propose_fisher(cur, prop, P, d.fvals + (size_t)c * P, d.fvecs + (size_t)c * P * P, T, u_pick, z, w[P + 2]);
@@ -116,7 +117,7 @@ __global__ void k_accept(DevState d, StepConst k, long long step, int c0, int n,
 	const int c = c0 + t, P = k.P;
 	const double T = d.temps[c];
 	double alpha, u_acc;
-	uniform2(k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u_acc);
+	uniform2(k.seed, (uint64_t)step, (uint32_t)(k.chain_offset + c), DRAW_TYPE_ACCEPT, alpha, u_acc);
 	const int type = d.info[c] & 0xff, sel = d.info[c] >> 8;
 	double *cur = d.pos + (size_t)c * P;
 	const bool acc = mh_accept(d.ll[c], d.llprop[c], d.lp[c], d.lpprop[c], T, u_acc);
@@ -287,54 +288,29 @@ __global__ void k_fisher_commit(const int *__restrict__ idx, const int *__restri
 // all pairs at once so that the sequential part is one comparison per pair.
 //   kind 0: never swap (equal temperatures), 1: swap iff l1 >= thr, 2: swap iff l1 <= thr, 3: always swap
 __global__ void k_swap_prepare(const double *__restrict__ ll, const double *__restrict__ temps, uint64_t seed, long long sweep, int C,
-                               double *__restrict__ thr, int *__restrict__ kind)
+                               int chain_offset, double *__restrict__ thr, int *__restrict__ kind)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= C - 1) return;
-	const double T1 = temps[i], T2 = temps[i + 1];
 	double alpha, unused;
-	uniform2(seed, (uint64_t)sweep, (uint32_t)i, DRAW_SWAP, alpha, unused);
-	if (T1 == T2) {
-		kind[i] = 0;
-		thr[i] = 0;
-		return;
-	}
-	const double g = 1. / T2 - 1. / T1;  // (l1-l2) * g >= ln(alpha)
-	const double la = log(alpha);        // alpha = 0 -> -inf -> always
-	if (g == 0 || la == -INFINITY) {
-		kind[i] = (la <= 0) ? 3 : 0;
-		thr[i] = 0;
-	} else if (g > 0) {
-		kind[i] = 1;
-		thr[i] = ll[i + 1] + la / g;
-	} else {
-		kind[i] = 2;
-		thr[i] = ll[i + 1] + la / g;
-	}
+	uniform2(seed, (uint64_t)sweep, (uint32_t)(chain_offset + i), DRAW_SWAP, alpha, unused);
+	int kd;
+	double th;
+	swap_threshold(ll[i + 1], temps[i], temps[i + 1], alpha, kd, th);
+	kind[i] = kd;
+	thr[i] = th;
 }
 // src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118)
 __global__ void k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
-                            int *__restrict__ src, long long *__restrict__ counters)
+                            int *__restrict__ src, int *__restrict__ accepted, long long *__restrict__ counters)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
-	double carry = ll[0];
-	int carry_src = 0;
+	swap_scan(ll, thr, kind, C, src, accepted);
 	for (int i = 0; i < C - 1; i++) {
-		const int kd = kind[i];
-		const double th = thr[i];
-		const bool sw = (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
-		if (sw) {
-			src[i] = i + 1;  // slot i receives the untouched state of slot i+1; the carried state moves on to slot i+1
-		} else {
-			src[i] = carry_src;
-			carry = ll[i + 1];
-			carry_src = i + 1;
-		}
-		const int which = sw ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
+		const int which = accepted[i] ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
 		counters[(size_t)i * NCT + which] += 1;
 		counters[(size_t)(i + 1) * NCT + which] += 1;
 	}
-	src[C - 1] = carry_src;
 }
 __global__ void k_swap_apply(const int *__restrict__ src, int C, int P, const double *__restrict__ pos, const double *__restrict__ ll,
                              const double *__restrict__ lp, double *__restrict__ pos2, double *__restrict__ ll2, double *__restrict__ lp2)
@@ -392,6 +368,7 @@ int make_prior_plan(const char *method, const gwat_b200_mod *mod, int dimension,
 
 struct gwat_b200_sampler {
 	gwat_b200_ctx *ctx = nullptr;
+	int device = 0;
 	std::string method;
 	gwat_b200_mod mod;
 	gwat_b200_sampler_options opt;
@@ -405,7 +382,7 @@ struct gwat_b200_sampler {
 	DevState d{};
 	double *pos2 = nullptr, *ll2 = nullptr, *lp2 = nullptr;  // swap double buffers
 	double *swap_thr = nullptr;
-	int *swap_kind = nullptr, *swap_src = nullptr;
+	int *swap_kind = nullptr, *swap_src = nullptr, *swap_acc = nullptr;
 	// Fisher refresh pipeline, per lane: device staging slots (one per step in flight) and a longer ring of pinned index lists
 	struct RefreshLane {
 		int ND = 1, NP = 1;
@@ -472,7 +449,7 @@ void fisher_schedule(gwat_b200_sampler *s, int ln, long long step, std::vector<i
 	for (int c = s->lane_c0[ln]; c < s->lane_c0[ln] + s->lane_n[ln]; c++) {
 		double bounds[4], alpha, u;
 		step_boundaries(s->h_temps[c], true, primed, bounds);
-		uniform2(s->k.seed, (uint64_t)step, (uint32_t)c, DRAW_TYPE_ACCEPT, alpha, u);
+		uniform2(s->k.seed, (uint64_t)step, (uint32_t)(s->k.chain_offset + c), DRAW_TYPE_ACCEPT, alpha, u);
 		if (step_type(alpha, bounds) != STEP_FISHER) continue;
 		if (s->h_fisher_ct[c] == s->opt.fisher_update_number) {
 			flagged.push_back(c);
@@ -592,8 +569,8 @@ int swap_sweep(gwat_b200_sampler *s)
 	double gate, unused;
 	uniform2(s->k.seed, (uint64_t)s->sweep, 0u, DRAW_SWAP_GATE, gate, unused);
 	if (gate < s->opt.swap_rate && C > 1) {  // src/mcmc_sampler.cpp:4646-4654
-		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->swap_thr, s->swap_kind);
-		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->d.counters);
+		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->k.chain_offset, s->swap_thr, s->swap_kind);
+		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc, s->d.counters);
 		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
 		std::swap(s->d.pos, s->pos2);
 		std::swap(s->d.ll, s->ll2);
@@ -715,14 +692,14 @@ int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *method, const gw
 void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 {
 	if (!s) return;
-	cudaSetDevice(s->ctx->device);
+	cudaSetDevice(s->device);  // (a sampler must be destroyed before its context; this at least does not read the context)
 	for (int i = 0; i < 2; i++) {
 		if (s->st[i]) cudaStreamSynchronize(s->st[i]);
 		if (s->st_like[i]) cudaStreamSynchronize(s->st_like[i]);
 	}
 	DevState &d = s->d;
 	void *ptrs[] = {d.pos, d.prop, d.ll, d.lp, d.llprop, d.lpprop, d.temps, d.hist, d.hist_pos, d.fvals, d.fvecs, d.widths, d.counters,
-	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src};
+	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src, s->swap_acc};
 	for (void *p : ptrs) cudaFree(p);
 	if (s->st_fisher) cudaStreamSynchronize(s->st_fisher);
 	for (gwat_b200_sampler::RefreshLane &r : s->rf) {
@@ -762,6 +739,7 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 		return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_create: invalid options");
 	gwat_b200_sampler *s = new gwat_b200_sampler;
 	s->ctx = ctx;
+	s->device = ctx->device;
 	s->method = method ? method : "";
 	if (mod) s->mod = *mod;
 	else gwat_b200_mod_init(&s->mod);
@@ -776,7 +754,7 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	s->gmst = gmst;
 	s->T_segment = T_segment;
 	const int C = o.chain_N, P = o.dimension, H = o.history_length;
-	s->k = StepConst{o.seed, C, P, H, o.history_update, o.check_stepsize_freq, o.fisher_exist, o.record_cold};
+	s->k = StepConst{o.seed, C, P, H, o.history_update, o.check_stepsize_freq, o.fisher_exist, o.record_cold, o.chain_index_offset};
 	s->nlanes = (o.lanes >= 2 && C >= 2) ? 2 : 1;
 	s->lane_c0[0] = 0;
 	s->lane_n[0] = s->nlanes == 2 ? C / 2 : C;
@@ -818,6 +796,7 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(dalloc(d.cold_slot, (size_t)C));
 	SC_TRY(dalloc(s->swap_kind, (size_t)C));
 	SC_TRY(dalloc(s->swap_src, (size_t)C));
+	SC_TRY(dalloc(s->swap_acc, (size_t)C));
 	int prio_lo = 0, prio_hi = 0;
 	SC_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	s->lookahead = 0;
@@ -990,6 +969,41 @@ int gwat_b200_sampler_state(gwat_b200_sampler *s, double *positions, double *log
 	if (positions) SCUDA(ctx, cudaMemcpy(positions, s->d.pos, sizeof(double) * C * P, cudaMemcpyDeviceToHost));
 	if (logL) SCUDA(ctx, cudaMemcpy(logL, s->d.ll, sizeof(double) * C, cudaMemcpyDeviceToHost));
 	if (logP) SCUDA(ctx, cudaMemcpy(logP, s->d.lp, sizeof(double) * C, cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_set_state(gwat_b200_sampler *s, const double *positions, const double *logL, const double *logP)
+{
+	if (!s) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	const int C = s->k.C, P = s->k.P;
+	if (positions) SCUDA(ctx, cudaMemcpy(s->d.pos, positions, sizeof(double) * C * P, cudaMemcpyHostToDevice));
+	if (logL) SCUDA(ctx, cudaMemcpy(s->d.ll, logL, sizeof(double) * C, cudaMemcpyHostToDevice));
+	if (logP) SCUDA(ctx, cudaMemcpy(s->d.lp, logP, sizeof(double) * C, cudaMemcpyHostToDevice));
+	return GWAT_B200_OK;
+}
+
+void gwat_b200_sampler_uniform(unsigned long long seed, unsigned long long step, unsigned chain, unsigned purpose, double *out2)
+{
+	uniform2(seed, step, chain, purpose, out2[0], out2[1]);
+}
+
+int gwat_b200_swap_sweep_host(int C, const double *logL, const double *temps, unsigned long long seed, long long sweep, int *src,
+                              int *accepted)
+{
+	if (C < 1 || !logL || !temps || !src) return GWAT_B200_ERR_ARG;
+	std::vector<double> thr(C);
+	std::vector<int> kind(C), acc(C);
+	for (int i = 0; i < C - 1; i++) {
+		double alpha, unused;
+		uniform2(seed, (uint64_t)sweep, (uint32_t)i, DRAW_SWAP, alpha, unused);
+		swap_threshold(logL[i + 1], temps[i], temps[i + 1], alpha, kind[i], thr[i]);
+	}
+	swap_scan(logL, thr.data(), kind.data(), C, src, acc.data());
+	if (accepted)
+		for (int i = 0; i < C - 1; i++) accepted[i] = acc[i];
 	return GWAT_B200_OK;
 }
 

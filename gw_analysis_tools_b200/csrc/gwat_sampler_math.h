@@ -210,6 +210,46 @@ GWAT_HD int swap_decision(double ll1, double ll2, double T1, double T2, double a
 	return (MH_ratio < alpha) ? 0 : 1;
 }
 
+// The same test as a threshold on ll1 for fixed ll2, T1, T2, alpha (the swap sweep carries ll1 along the ladder, so everything
+// else can be prepared for all pairs at once).  kind 0: never (equal temperatures), 1: swap iff ll1 >= thr, 2: swap iff
+// ll1 <= thr, 3: always.
+GWAT_HD void swap_threshold(double ll2, double T1, double T2, double alpha, int &kind, double &thr)
+{
+	thr = 0;
+	if (T1 == T2) {
+		kind = 0;
+		return;
+	}
+	const double g = 1. / T2 - 1. / T1;  // (ll1 - ll2) * g >= ln(alpha)
+	const double la = log(alpha);        // alpha = 0 -> -inf -> always
+	if (g == 0 || la == -INFINITY) {
+		kind = (la <= 0) ? 3 : 0;
+	} else {
+		kind = g > 0 ? 1 : 2;
+		thr = ll2 + la / g;
+	}
+}
+// chain_swap's sweep (:1086-1118) over C slots: src[i] = slot whose state ends up in slot i; accepted[i] for pair (i, i+1)
+GWAT_HD void swap_scan(const double *ll, const double *thr, const int *kind, int C, int *src, int *accepted)
+{
+	double carry = ll[0];
+	int carry_src = 0;
+	for (int i = 0; i < C - 1; i++) {
+		const int kd = kind[i];
+		const double th = thr[i];
+		const bool sw = (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
+		if (sw) {
+			src[i] = i + 1;  // slot i receives the untouched state of slot i+1; the carried state moves on to slot i+1
+		} else {
+			src[i] = carry_src;
+			carry = ll[i + 1];
+			carry_src = i + 1;
+		}
+		accepted[i] = sw ? 1 : 0;
+	}
+	src[C - 1] = carry_src;
+}
+
 // update_step_widths (:1623-1703): one width, its accept/reject counts since the last check
 GWAT_HD double tuned_width(double width, long long acc, long long rej, double min_target, double max_target)
 {

@@ -77,3 +77,80 @@ def exchange_and_swap(local_positions, local_logl, temps, walkers_per_temp, rank
     idx = torch.as_tensor(src[w0:w0 + nw], device=all_pos.device)
     accepted = int((src != np.arange(src.size)).sum() // 2)
     return all_pos.index_select(0, idx), all_logl.index_select(0, idx), accepted
+
+
+class DistributedSampler:
+    """The device-resident PTMCMC sampler (``sampler.Sampler``) with its chains sharded contiguously over the ranks of a
+    ``torch.distributed`` group -- one process per GPU.  Steps need no communication.  At every swap interval the ranks
+    all-gather logL (8 B per chain) and, when the sweep happens, positions and priors (8 (P+1) B per chain), run the
+    reference's sequential sweep over the WHOLE ladder on the host (``gwat_b200_swap_sweep_host``: the single-GPU sweep's
+    draws and arithmetic) and keep their own slots.  Random draws are functions of the global chain index, so N ranks
+    reproduce the single-GPU run bit for bit (tests/test_sampler_multigpu.py)."""
+
+    DRAW_SWAP_GATE = 5
+
+    def __init__(self, ctx, method, temps, initial_positions, prior, gmst, T_segment, mod=None, group=None, **options):
+        import torch.distributed as dist
+        from . import sampler as smp
+        self._smp = smp
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        temps = np.asarray(temps, dtype=np.float64)
+        init = np.asarray(initial_positions, dtype=np.float64)
+        self.C, self.P = init.shape
+        if self.C % self.world != 0:
+            raise ValueError("DistributedSampler needs the number of chains to be a multiple of the world size")
+        n = self.C // self.world
+        self.lo, self.hi = self.rank * n, (self.rank + 1) * n
+        self.temps = temps
+        self.swp_freq = int(options.get("swp_freq", 5))
+        self.swap_rate = float(options.pop("swap_rate", 1.0 / self.swp_freq))
+        self.seed = int(options.get("seed", 1))
+        self.local = smp.Sampler(ctx, method, temps[self.lo:self.hi], init[self.lo:self.hi], prior, gmst, T_segment, mod,
+                                 swap_rate=0.0, chain_index_offset=self.lo, **options)
+        self.sweep = 0
+        self.since = 0
+        self.swap_accept = np.zeros(self.C, dtype=np.int64)
+        self.swap_reject = np.zeros(self.C, dtype=np.int64)
+
+    def _all_gather(self, local):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return local
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.as_tensor(np.ascontiguousarray(local), device=dev)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return torch.cat(out).cpu().numpy()
+
+    def _sweep(self):
+        gate, _ = self._smp.draw_uniform2(self.seed, self.sweep, 0, self.DRAW_SWAP_GATE)
+        if gate < self.swap_rate and self.C > 1:
+            pos, ll, lp = self.local.state()
+            all_ll = self._all_gather(ll)
+            src, acc = self._smp.swap_sweep_host(all_ll, self.temps, self.seed, self.sweep)
+            if acc.any():
+                all_pos, all_lp = self._all_gather(pos), self._all_gather(lp)
+                mine = src[self.lo:self.hi]
+                self.local.set_state(all_pos[mine], all_ll[mine], all_lp[mine])
+            for which, sel in ((self.swap_accept, acc == 1), (self.swap_reject, acc == 0)):
+                which[:-1] += sel
+                which[1:] += sel
+        self.sweep += 1
+
+    def run(self, n_steps):
+        while n_steps > 0:
+            k = min(n_steps, self.swp_freq - self.since)
+            self.local.run(k)
+            self.since += k
+            n_steps -= k
+            if self.since == self.swp_freq:
+                self._sweep()
+                self.since = 0
+
+    def state(self):
+        """Global (positions, logL, logP), gathered."""
+        pos, ll, lp = self.local.state()
+        return self._all_gather(pos), self._all_gather(ll), self._all_gather(lp)

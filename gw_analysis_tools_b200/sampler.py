@@ -17,7 +17,8 @@ COUNTERS = ["step_accept", "step_reject", "gauss_accept", "gauss_reject", "de_ac
 EXPORTS = [
     "gwat_b200_prior_init", "gwat_b200_sampler_options_init", "gwat_b200_sampler_create", "gwat_b200_sampler_destroy",
     "gwat_b200_sampler_run", "gwat_b200_sampler_state", "gwat_b200_sampler_counters", "gwat_b200_sampler_cold",
-    "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
+    "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_sampler_uniform",
+    "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
 ]
 
 
@@ -41,7 +42,7 @@ class Options(C.Structure):
     _fields_ = [("chain_N", C.c_int), ("dimension", C.c_int), ("swp_freq", C.c_int), ("swap_rate", C.c_double),
                 ("history_length", C.c_int), ("history_update", C.c_int), ("fisher_exist", C.c_int),
                 ("fisher_update_number", C.c_int), ("fisher_deriv_order", C.c_int), ("check_stepsize_freq", C.c_int),
-                ("seed", C.c_ulonglong), ("lanes", C.c_int), ("record_cold", C.c_int), ("fisher_deferred", C.c_int)]
+                ("seed", C.c_ulonglong), ("lanes", C.c_int), ("record_cold", C.c_int), ("fisher_deferred", C.c_int), ("chain_index_offset", C.c_int), ("reserved_", C.c_int)]
 
 
 def prior_defaults(**kw):
@@ -133,6 +134,10 @@ class Sampler:
         self._ctx._check(self._lib.gwat_b200_sampler_state(self._h, _p(pos), _p(ll), _p(lp)))
         return pos, ll, lp
 
+    def set_state(self, positions=None, logL=None, logP=None):
+        a = [None if x is None else _f64(x) for x in (positions, logL, logP)]
+        self._ctx._check(self._lib.gwat_b200_sampler_set_state(self._h, *[_p(x) for x in a]))
+
     def counters(self):
         ct = np.empty((self.C, len(COUNTERS)), dtype=np.int64)
         w = np.empty((self.C, self.P + 3))
@@ -159,6 +164,30 @@ class Sampler:
     @property
     def last_launches(self):
         return self._lib.gwat_b200_sampler_last_launches(self._h)
+
+
+def swap_sweep_host(logL, temps, seed, sweep):
+    """The reference's swap sweep over a whole ladder (host code of the library, the single-GPU sweep's draws and arithmetic):
+    returns (src, accepted) with new_state[i] = old_state[src[i]]."""
+    from .engine import load_library
+    logL, temps = _f64(logL), _f64(temps)
+    n = logL.size
+    src = np.empty(n, dtype=np.int32)
+    acc = np.zeros(max(n - 1, 1), dtype=np.int32)
+    rc = load_library().gwat_b200_swap_sweep_host(n, _p(logL), _p(temps), C.c_ulonglong(seed), C.c_longlong(sweep),
+                                                  src.ctypes.data_as(C.POINTER(C.c_int)), acc.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise GwatB200Error(rc, "swap_sweep_host: bad arguments")
+    return src, acc[:n - 1]
+
+
+def draw_uniform2(seed, step, chain, purpose):
+    from .engine import load_library
+    out = (C.c_double * 2)()
+    lib = load_library()
+    lib.gwat_b200_sampler_uniform.restype = None
+    lib.gwat_b200_sampler_uniform(C.c_ulonglong(seed), C.c_ulonglong(step), C.c_uint(chain), C.c_uint(purpose), out)
+    return out[0], out[1]
 
 
 def prior_for(wl):

@@ -70,6 +70,9 @@ typedef struct gwat_b200_sampler_options {
 	                               and the new eigen-systems are installed at the sweep after that: same cadence per chain, same
 	                               use, matrices up to 2 swp_freq steps staler out of the ~400 steps each is used for; all chains get
 	                               their first matrix at creation. */
+	int chain_index_offset;     /* global index of this sampler's chain 0 when an ensemble is sharded over several GPUs: random draws
+	                               are functions of the GLOBAL chain index, so N samplers reproduce what one would do */
+	int reserved_;
 } gwat_b200_sampler_options;
 
 typedef struct gwat_b200_sampler gwat_b200_sampler;
@@ -82,13 +85,23 @@ void gwat_b200_sampler_options_init(gwat_b200_sampler_options *o); /* the refere
 int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
                              const gwat_b200_sampler_options *options, const gwat_b200_prior *prior, const double *chain_temps,
                              const double *initial_positions, double gmst, double T_segment, gwat_b200_sampler **out);
-void gwat_b200_sampler_destroy(gwat_b200_sampler *s);
+void gwat_b200_sampler_destroy(gwat_b200_sampler *s);   /* before gwat_b200_ctx_destroy of its context */
 
 /* Advance every chain by n_steps (swap sweeps every swp_freq steps).  Returns when the device has finished. */
 int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps);
 
 /* Current state, any pointer may be NULL: positions[chain_N][dimension], logL[chain_N], logP[chain_N] */
 int gwat_b200_sampler_state(gwat_b200_sampler *s, double *positions, double *logL, double *logP);
+/* Overwrite the current state (any pointer may be NULL); histories, widths and Fisher eigen-systems stay with their slots, as
+ * they do in the reference's swaps.  For callers that exchange states between GPUs (below). */
+int gwat_b200_sampler_set_state(gwat_b200_sampler *s, const double *positions, const double *logL, const double *logP);
+/* Several GPUs: create every rank's sampler with swap_rate = 0 and chain_index_offset = its first global chain, run swp_freq
+ * steps, gather logL of all chains, and let every rank compute the reference's swap sweep over the WHOLE ladder with the very
+ * draws and arithmetic the single-GPU sweep uses (host code, no GPU needed): src[i] = global slot whose state moves to slot i.
+ * gwat_b200_sampler_uniform exposes the counter-based draws (purpose 5 = the swap_rate gate of sweep `step`, chain 0). */
+int gwat_b200_swap_sweep_host(int chain_N_total, const double *logL, const double *temps, unsigned long long seed, long long sweep,
+                              int *src, int *accepted /* [chain_N_total - 1] or NULL */);
+void gwat_b200_sampler_uniform(unsigned long long seed, unsigned long long step, unsigned chain, unsigned purpose, double *out2);
 /* counters[chain_N][GWAT_B200_SAMPLER_NCOUNTERS] (see the enum), widths[chain_N][dimension + 3]: Gaussian widths per dimension,
  * then the DE, (unused) and Fisher widths */
 enum {

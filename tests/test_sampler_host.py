@@ -235,3 +235,30 @@ def test_restated_sampler_samples_a_known_target():
     assert np.all(np.abs(cold.mean(axis=0) - mu) < 0.35 * sig)
     assert np.all(np.abs(cold.std(axis=0) / sig - 1) < 0.35)
     assert sum(c["swap"][0] for c in s.ct) > 0
+
+
+def test_host_swap_sweep_matches_restated_sweep():
+    """gwat_b200_swap_sweep_host (the threshold form the device sweep uses) against chain_swap/single_chain_swap as restated."""
+    from gw_analysis_tools_b200 import sampler as smp
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        C_ = int(rng.integers(2, 60))
+        temps = np.tile(np.geomspace(1.0, 40.0, 5), 12)[:C_]
+        if trial % 4 == 0:
+            temps[C_ // 2:] = temps[C_ // 2]  # a run of equal temperatures: never swapped
+        ll = rng.normal(1e4, 6, C_)
+        seed, sweep = int(rng.integers(1, 2**40)), int(rng.integers(0, 1000))
+        src, acc = smp.swap_sweep_host(ll, temps, seed, sweep)
+        s = ref.Sampler.__new__(ref.Sampler)
+        s.C, s.T, s.seed, s.sweep, s.swap_rate = C_, list(temps), seed, sweep, 2.0
+        s.ll, s.lp, s.pos = list(ll), [0.0] * C_, [[float(i)] for i in range(C_)]
+        s.ct = [dict(swap=[0, 0]) for _ in range(C_)]
+        s._swap_sweep()
+        assert [int(p[0]) for p in s.pos] == list(src)
+        assert np.array_equal(np.array(s.ll), ll[src])
+        n_acc = np.array([c["swap"][0] for c in s.ct])
+        want = np.zeros(C_, dtype=int)
+        want[:-1] += acc
+        want[1:] += acc
+        assert np.array_equal(n_acc, want)
+    assert smp.draw_uniform2(5, 7, 3, 4) == ref.uniform2(5, 7, 3, 4)

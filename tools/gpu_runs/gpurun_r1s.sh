@@ -1,0 +1,2 @@
+#!/bin/bash
+python -m pytest tests/test_sampler_multigpu.py tests/test_sampler_gpu.py -m gpu -q 2>&1 | tail -15
