@@ -573,7 +573,7 @@ int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, R
 	plan.nrt = desc.nrt;
 	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
 	plan.gimr = desc.gimr && !plan.ppe;
-	plan.alpha_unit_fix = (desc.theory == THEORY_DCS || desc.theory == THEORY_EDGB);
+	plan.alpha_unit_fix = theory_alpha_units(desc.theory);
 	plan.mcmc = 1;
 	if (mod) plan.mod = *mod;
 	else {

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <string>
 
+#include "gwat_theory.h"
+
 namespace gwat {
 
 enum FamilyId {
@@ -26,7 +28,6 @@ enum FamilyId {
 	FAM_COUNT
 };
 
-enum TheoryId { THEORY_NONE = 0, THEORY_DCS = 1, THEORY_EDGB = 2 };
 
 struct MethodDesc {
 	int family_id;
@@ -88,6 +89,40 @@ inline int parse_method(const char *method_c, MethodDesc &d)
 			d.theory = e.theory;
 			return 0;
 		}
+	}
+	// the remaining theory-mapped methods (assign_mapping, src/ppE_utilities.cpp:158-359): "<theory>_<base model>", with
+	// "_Inspiral"/"_IMR" after the base model for the two generic re-parameterisations
+	struct Theory {
+		const char *prefix;
+		int id;
+		int generic;  // 1: inspiral/IMR chosen by the suffix; 0: inspiral-only ppE
+	};
+	static const Theory theories[] = {
+	    {"EdGB_HO_LO_", THEORY_EDGB_HO_LO, 0}, {"EdGB_HO_", THEORY_EDGB, 0},          {"EdGB_GHOv1_", THEORY_EDGB_GHOV1, 0},
+	    {"EdGB_GHOv2_", THEORY_EDGB_GHOV2, 0}, {"EdGB_GHOv3_", THEORY_EDGB_GHOV3, 0}, {"ExtraDimension_", THEORY_EXTRADIM, 0},
+	    {"BHEvaporation_", THEORY_BHEVAP, 0},  {"TVG_", THEORY_TVG, 0},               {"DipRad_", THEORY_DIPRAD, 0},
+	    {"NonComm_", THEORY_NONCOMM, 0},       {"PNSeries_ppE_", THEORY_PNSERIES, 1}, {"ppEAlt_", THEORY_PPEALT, 1},
+	};
+	for (const Theory &t : theories) {
+		const std::string pre(t.prefix);
+		if (m.compare(0, pre.size(), pre) != 0) continue;
+		std::string rest = m.substr(pre.size());
+		bool ins = true;
+		if (t.generic) {
+			const std::string a = "_Inspiral", b = "_IMR";
+			if (rest.size() > a.size() && rest.compare(rest.size() - a.size(), a.size(), a) == 0) rest.erase(rest.size() - a.size());
+			else if (rest.size() > b.size() && rest.compare(rest.size() - b.size(), b.size(), b) == 0) {
+				rest.erase(rest.size() - b.size());
+				ins = false;
+			} else return -1;
+		}
+		if (rest == "IMRPhenomD") d.family_id = ins ? FAM_D_PPE_INS : FAM_D_PPE_IMR;
+		else if (rest == "IMRPhenomD_NRT") d.family_id = ins ? FAM_D_NRT_PPE_INS : FAM_D_NRT_PPE_IMR;
+		else if (rest == "IMRPhenomPv2") d.family_id = ins ? FAM_P_PPE_INS : FAM_P_PPE_IMR;
+		else return -1;
+		d.theory = t.id;
+		d.ppe = true;
+		return 0;
 	}
 	return -1;
 }

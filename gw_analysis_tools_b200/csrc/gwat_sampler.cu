@@ -359,7 +359,7 @@ int make_prior_plan(const char *method, const gwat_b200_mod *mod, int dimension,
 	pp.tidal_love = tidal_love;
 	pp.dimension = dimension;
 	pp.first_mod = base;
-	alpha_fix = (desc.theory == THEORY_DCS || desc.theory == THEORY_EDGB);
+	alpha_fix = theory_alpha_units(desc.theory);
 	ppE_Nmod = mod ? mod->ppE_Nmod : 0;
 	return 0;
 }

@@ -73,22 +73,109 @@ GWAT_HD double edgb_phase_factor(const SrcQ &s, double m1, double m2)
 	return (-5. / 7168.) * pow_int_seq((m1 * m1 * s2 - m2 * m2 * s1), 2) / (pow_int_seq(s.M, 4) * pow(s.eta, (18. / 5)));
 }
 
-// Replace the walker's (beta, b) by what the theory dictates; betappe[0] on entry is the coupling alpha^2 [s^4].
-// `theory` uses the TheoryId values of gwat_method.h (1 = dCS, 2 = EdGB).
+// Theory ids (gwat_method.h parses the method string into one of these).  "EdGB_HO_<model>" without "_LO" is THEORY_EDGB: in
+// assign_mapping the `if (EdGB_HO)` block is followed by an independent `if (EdGB_HO_LO) ... else if (GHOv1..3) ... else`
+// chain whose final else overwrites the three-term mapping with the plain EdGB one (src/ppE_utilities.cpp:171-221).
+enum TheoryId {
+	THEORY_NONE = 0, THEORY_DCS = 1, THEORY_EDGB = 2, THEORY_EDGB_HO_LO = 3, THEORY_EDGB_GHOV1 = 4, THEORY_EDGB_GHOV2 = 5,
+	THEORY_EDGB_GHOV3 = 6, THEORY_EXTRADIM = 7, THEORY_BHEVAP = 8, THEORY_TVG = 9, THEORY_DIPRAD = 10, THEORY_NONCOMM = 11,
+	THEORY_PNSERIES = 12, THEORY_PPEALT = 13
+};
+// MCMC_prep_params converts sqrt(alpha)[km] -> alpha^2 [s^4] for every method whose name contains dCS or EdGB (src/mcmc_gw.cpp:2560)
+GWAT_HD bool theory_alpha_units(int theory) { return theory >= THEORY_DCS && theory <= THEORY_EDGB_GHOV3; }
+
+// Replace the walker's (beta_i, b_i) by what the theory dictates (prep_source_parameters' theory block,
+// src/waveform_generator.cpp:1383-1410: every beta function sees the INPUT betappe, results are installed afterwards).
 GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 {
-	if (theory == 0) return;
+	if (theory == THEORY_NONE) return;
 	const double etapow = pow(s.eta, 3. / 5);
 	const double root = sqrt(1. - 4 * s.eta);
 	const double m1 = 1. / 2 * (s.chirpmass / etapow + root * s.chirpmass / etapow);
 	const double m2 = 1. / 2 * (s.chirpmass / etapow - root * s.chirpmass / etapow);
 	const double Z = z_from_dl(s.DL / GWAT_MPC_SEC, dz);
 	const double unredshiftedM = s.M / (1. + Z);
-	const double coupling = s.betappe[0];
-	const double factor = theory == 1 ? dcs_phase_factor(s, m1, m2) : edgb_phase_factor(s, m1, m2);
-	s.betappe[0] = 16. * GWAT_PI * coupling / (pow_int_seq(unredshiftedM, 4)) * factor;
-	s.bppe[0] = theory == 1 ? -1 : -7;
-	s.Nmod = 1;
+	const double in0 = s.betappe[0], in1 = s.betappe[1];
+	const double eta = s.eta;
+	double beta[GWAT_B200_MAX_MOD], b[GWAT_B200_MAX_MOD];
+	int n = 1;
+	switch (theory) {
+	case THEORY_DCS:  // dCS_beta (:473-484)
+		beta[0] = 16. * GWAT_PI * in0 / (pow_int_seq(unredshiftedM, 4)) * dcs_phase_factor(s, m1, m2);
+		b[0] = -1;
+		break;
+	case THEORY_EDGB:  // EdGB_beta (:573-583)
+		beta[0] = 16. * GWAT_PI * in0 / (pow_int_seq(unredshiftedM, 4)) * edgb_phase_factor(s, m1, m2);
+		b[0] = -7;
+		break;
+	case THEORY_EDGB_HO_LO: {  // EdGB_HO_0PN_beta (:529-539)
+		const double alphaSq = 16. * GWAT_PI * in0;
+		beta[0] = -5. * alphaSq / pow_int_seq(unredshiftedM, 4) / 7168. / pow(eta, 18. / 5.) * (4 * eta - 1);
+		b[0] = -7;
+		break;
+	}
+	case THEORY_EDGB_GHOV1:  // EdGB_beta + EdGB_GHO_betav1 (:619-630)
+	case THEORY_EDGB_GHOV2:  // (:633-645)
+	case THEORY_EDGB_GHOV3: {  // (:648-661)
+		const double pf = edgb_phase_factor(s, m1, m2);
+		const double lead = 16. * GWAT_PI * in0 / (pow_int_seq(unredshiftedM, 4));
+		beta[0] = lead * pf;
+		if (theory == THEORY_EDGB_GHOV1) beta[1] = lead * in1;
+		else if (theory == THEORY_EDGB_GHOV2) beta[1] = lead * pf * in1;
+		else beta[1] = lead * in1 * pf * (3715. / 756. + 55. * eta / 9.);
+		b[0] = -7;
+		b[1] = -5;
+		n = 2;
+		break;
+	}
+	case THEORY_EXTRADIM: {  // ExtraDimension_beta (:664-678); s.mass1/2 are in seconds
+		const double ten_micrometer = 10.e-6 / GWAT_C_SI;
+		const double T_year = 31557600.;
+		const double m1dot = -2.8e-7 * pow_int_seq(GWAT_MSOL_SEC * (1 + Z) / s.mass1, 2) * in0 / pow_int_seq(ten_micrometer, 2) * GWAT_MSOL_SEC / T_year;
+		const double m2dot = -2.8e-7 * pow_int_seq(GWAT_MSOL_SEC * (1 + Z) / s.mass2, 2) * in0 / pow_int_seq(ten_micrometer, 2) * GWAT_MSOL_SEC / T_year;
+		beta[0] = (m1dot + m2dot) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (pow(eta, 2. / 5.) * (1 - 2 * eta)));
+		b[0] = -13;
+		break;
+	}
+	case THEORY_BHEVAP:  // BHEvaporation_beta (:682-691)
+		beta[0] = (in0) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (pow(eta, 2. / 5.) * (1 - 2 * eta)));
+		b[0] = -13;
+		break;
+	case THEORY_TVG:  // TVG_beta (:695-703)
+		beta[0] = (-25. / 65526.) * (in0 * s.chirpmass / (1 + Z));
+		b[0] = -13;
+		break;
+	case THEORY_DIPRAD:  // DipRad_beta (:707-713)
+		beta[0] = (-3. / 224.) * pow(eta, 2. / 5.) * in0;
+		b[0] = -7;
+		break;
+	case THEORY_NONCOMM:  // NonComm_beta (:717-723)
+		beta[0] = (-75. / 256.) * pow(eta, -4. / 5.) * (2. * eta - 1.) * in0;
+		b[0] = -1;
+		break;
+	case THEORY_PNSERIES:  // PNSeries_beta (:420-435): basis M f instead of Mc f; terms > 0 are relative to the first
+	case THEORY_PPEALT: {  // ppEAlt_beta (:399-414)
+		// calculate_chirpmass(mass1, mass2) (src/util.cpp:1492): the same value as s.chirpmass up to the rounding of its pow calls
+		const double chirp = pow(s.mass1 * s.mass2, 3. / 5) / pow(s.mass1 + s.mass2, 1. / 5);
+		const double total_m = s.mass1 + s.mass2;
+		n = s.Nmod;
+		for (int i = 0; i < n; i++) {
+			b[i] = s.bppe[i];
+			const double conv = pow(total_m / chirp, s.bppe[i] / 3.);
+			if (i == 0 || theory == THEORY_PPEALT) beta[i] = s.betappe[i] * conv;
+			else beta[i] = s.betappe[0] * s.betappe[i] * conv;
+		}
+		break;
+	}
+	default:
+		beta[0] = NAN;
+		b[0] = 0;
+	}
+	s.Nmod = n;
+	for (int i = 0; i < n; i++) {
+		s.betappe[i] = beta[i];
+		s.bppe[i] = b[i];
+	}
 }
 
 }  // namespace gwat

@@ -45,6 +45,24 @@ CASES = [
     ("ppE_NRT_ins", "ppE_IMRPhenomD_NRT_Inspiral", dict(BNS, tidal_love=1, tidal_s=400., Nmod=1, bppe=[-1.], betappe=[0.01]), GRID_BNS),
     ("ppE_NRT_imr", "ppE_IMRPhenomD_NRT_IMR", dict(BNS, tidal_love=1, tidal_s=400., Nmod=1, bppe=[-1.], betappe=[0.01]), GRID_BNS),
 ]
+# The other theory mappings of assign_mapping (src/ppE_utilities.cpp:158-359); couplings chosen for O(0.1-1) rad of dephasing.
+THEORY_CASES = [
+    ("EdGB_HO", "EdGB_HO_IMRPhenomD", dict(BBH_LOW, Nmod=1, bppe=[-7.], betappe=[KM4(3.)]), GRID_BBH),  # == EdGB (reference quirk)
+    ("EdGB_HO_LO", "EdGB_HO_LO_IMRPhenomD", dict(BBH_LOW, Nmod=1, bppe=[-7.], betappe=[KM4(2.)]), GRID_BBH),
+    ("EdGB_GHOv1", "EdGB_GHOv1_IMRPhenomD", dict(BBH_LOW, Nmod=2, bppe=[-7., -5.], betappe=[KM4(3.), -2e-4]), GRID_BBH),
+    ("EdGB_GHOv2", "EdGB_GHOv2_IMRPhenomD", dict(BBH_LOW, Nmod=2, bppe=[-7., -5.], betappe=[KM4(3.), 2.0]), GRID_BBH),
+    ("EdGB_GHOv3", "EdGB_GHOv3_IMRPhenomPv2", dict(PREC, Nmod=2, bppe=[-7., -5.], betappe=[KM4(8.), 1.5]), GRID_BBH),
+    ("ExtraDim", "ExtraDimension_IMRPhenomD", dict(BBH, Nmod=1, bppe=[-13.], betappe=[1e-10]), GRID_BBH),
+    ("BHEvap", "BHEvaporation_IMRPhenomD", dict(BBH, Nmod=1, bppe=[-13.], betappe=[2e-6]), GRID_BBH),
+    ("TVG", "TVG_IMRPhenomPv2", dict(PREC, Nmod=1, bppe=[-13.], betappe=[1e-2]), GRID_BBH),
+    ("DipRad", "DipRad_IMRPhenomD", dict(BBH, Nmod=1, bppe=[-7.], betappe=[1e-3]), GRID_BBH),
+    ("DipRad_NRT", "DipRad_IMRPhenomD_NRT", dict(BNS, tidal_love=1, tidal_s=400., Nmod=1, bppe=[-7.], betappe=[1e-5]), GRID_BNS),
+    ("NonComm", "NonComm_IMRPhenomD", dict(BBH, Nmod=1, bppe=[-1.], betappe=[0.5]), GRID_BBH),
+    ("PNSeries_ins", "PNSeries_ppE_IMRPhenomD_Inspiral", dict(BBH, Nmod=2, bppe=[-7., -5.], betappe=[1e-6, 50.]), GRID_BBH),
+    ("PNSeries_imr", "PNSeries_ppE_IMRPhenomPv2_IMR", dict(PREC, Nmod=2, bppe=[-1., 1.], betappe=[0.1, 0.5]), GRID_BBH),
+    ("ppEAlt_ins", "ppEAlt_IMRPhenomD_Inspiral", dict(BBH, Nmod=2, bppe=[-7., -3.], betappe=[1e-6, 0.02]), GRID_BBH),
+    ("ppEAlt_imr", "ppEAlt_IMRPhenomD_IMR", dict(BBH, Nmod=2, bppe=[-1., 1.], betappe=[0.1, 0.5]), GRID_BBH),
+]
 DETECTORS = ["Hanford", "Livingston", "Virgo"]
 
 # Fisher cases: name, method string as the reference takes it, source kwargs, dimension

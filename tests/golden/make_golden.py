@@ -34,9 +34,39 @@ def maximized():
     np.savez_compressed(os.path.join(HERE, "maximized_v1.npz"), **mx)
 
 
+def theories():
+    """The theory mappings beyond dCS/EdGB: polarisations and the likelihood against derived data."""
+    out = {}
+    gold = np.load(os.path.join(HERE, "waveforms_v1.npz"))
+    for name, method, kw, gspec in cases.THEORY_CASES:
+        f = cases.grid(gspec)
+        src = cases.source(kw)
+        hp, hc = R.fourier_waveform(method, src, f)
+        psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+        # data of a fixed GR case per grid: the template is mismatched, so the likelihood feels the theory's phase
+        ll = R.loglike_batch(method, [src], cases.DETECTORS, f, psd, cases.maximized_data(gold, gspec))[0]
+        gr = R.fourier_waveform(_gr_method(method), cases.source({k: v for k, v in kw.items() if k not in ("Nmod", "bppe", "betappe")}), f)[0]
+        out[name + "/src"] = cases.source_bytes(src)
+        out[name + "/hp"] = hp
+        out[name + "/hc"] = hc
+        out[name + "/logL"] = np.array(ll)
+        dphi = np.abs(np.angle(hp[np.abs(gr) > 0] / gr[np.abs(gr) > 0])).max()
+        print("%-14s %-34s logL %.12e   max dephasing vs GR %.3g rad" % (name, method, ll, dphi))
+    np.savez_compressed(os.path.join(HERE, "theories_v1.npz"), **out)
+
+
+def _gr_method(method):
+    for base in ("IMRPhenomD_NRT", "IMRPhenomPv2", "IMRPhenomD"):
+        if base in method:
+            return base
+    raise ValueError(method)
+
+
 def main():
     if "--only-maximized" in sys.argv:
         return maximized()
+    if "--only-theories" in sys.argv:
+        return theories()
     out = {}
     for name, method, kw, gspec in cases.CASES:
         f = cases.grid(gspec)
@@ -100,7 +130,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "smoke_cfg2.npz"), logL=ll, data=data)
     np.savez_compressed(os.path.join(HERE, "mcmc_v1.npz"), **mo)
     maximized()
-    for fn in ("waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz", "maximized_v1.npz"):
+    theories()
+    for fn in ("theories_v1.npz", "waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz", "maximized_v1.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
 
 
