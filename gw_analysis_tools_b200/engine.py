@@ -23,7 +23,7 @@ EXPORTS = [
     "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
-    "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
+    "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
 
 
@@ -71,6 +71,15 @@ def _src_array(sources):
     if isinstance(sources, C.Array):
         return sources, len(sources)
     return (abi.Source * len(sources))(*sources), len(sources)
+
+
+def gauss_legendre_grid(f_lower, f_upper, n, log10F=True):
+    """(frequencies, weights) of the reference's GAUSSLEG grids (host code of the library)."""
+    f, w = np.empty(n), np.empty(n)
+    rc = load_library().gwat_b200_gauss_legendre_grid(C.c_double(f_lower), C.c_double(f_upper), int(n), int(bool(log10F)), _p(f), _p(w))
+    if rc != 0:
+        raise GwatB200Error(rc, "gauss_legendre_grid: bad arguments")
+    return f, w
 
 
 class Context:

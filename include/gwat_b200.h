@@ -156,6 +156,12 @@ int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *generation_method, i
 
 /* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
 
+/* Gauss-Legendre frequency grid as the reference builds it for "GAUSSLEG" integration (gauleg, src/ortho_basis.cpp:14-48, used as
+ * in src/waveform_util.cpp:3113-3116): n nodes and weights on [f_lower, f_upper], or -- log10F != 0 -- nodes uniform-in-rule over
+ * log10 f, returned as frequencies, with the weights of the log10 f integral (pass the same log10F to gwat_b200_set_network).
+ * Host code; no context needed. */
+int gwat_b200_gauss_legendre_grid(double f_lower, double f_upper, int n, int log10F, double *frequencies, double *weights);
+
 /* tc/phic-maximised log-likelihood of the reference's "intrinsic" samplers, summed over the network's detectors:
  *   maximized_Log_Likelihood_aligned_spin_internal (src/mcmc_gw.cpp:595-652) for the IMRPhenomD family,
  *   maximized_Log_Likelihood_unaligned_spin_internal (src/mcmc_gw.cpp:660-795) for the IMRPhenomPv2 family,

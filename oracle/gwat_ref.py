@@ -165,6 +165,12 @@ def antenna_batch(RA, DEC, psi, gmst, detectors):
     return fp, fc, dt
 
 
+def gauleg_grid(f_lower, f_upper, n, log10F=True):
+    f, w = np.zeros(n), np.zeros(n)
+    lib().oracle_ref_gauleg_grid(C.c_double(f_lower), C.c_double(f_upper), int(n), int(bool(log10F)), _p(f), _p(w))
+    return f, w
+
+
 def populate_noise(f, curve):
     f = _f64(f)
     asd = np.zeros(f.size)

@@ -28,6 +28,7 @@
 #include "detector_util.h"
 #include "mcmc_gw.h"
 #include "fisher.h"
+#include "ortho_basis.h"
 #include "ppE_utilities.h"
 #include "IMRPhenomD.h"
 #include "IMRPhenomP.h"
@@ -508,6 +509,18 @@ int oracle_ref_antenna_batch(int W, const double *RA, const double *DEC, const d
 }
 
 // populate_noise (src/detector_util.cpp:87): amplitude spectral density of a named analytic curve; psd = asd^2.
+// gauleg (src/ortho_basis.cpp:14-48) and the pow(10, .) step of its callers (src/waveform_util.cpp:3113-3116)
+int oracle_ref_gauleg_grid(double f_lower, double f_upper, int n, int log10F, double *freqs, double *weights)
+{
+	if (log10F) {
+		gauleg(log10(f_lower), log10(f_upper), freqs, weights, n);
+		for (int i = 0; i < n; i++) freqs[i] = pow(10, freqs[i]);
+	} else {
+		gauleg(f_lower, f_upper, freqs, weights, n);
+	}
+	return 0;
+}
+
 int oracle_ref_populate_noise(const double *f, const char *curve, double *asd, int L)
 {
 	populate_noise(const_cast<double *>(f), std::string(curve), asd, L);

@@ -5,6 +5,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 from gw_analysis_tools_b200 import abi, engine
@@ -81,3 +82,21 @@ def test_product_does_not_import_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
                 assert not re.search(r'#include\s+"[^"]*(oracle|host_harness)', text), path
                 assert "libgwat_ref" not in text and "libgwat_host_harness" not in text and "dlopen" not in text, path
+
+
+def test_gauss_legendre_grid_matches_reference(oracle):
+    """gwat_b200_gauss_legendre_grid against the reference's gauleg (+ pow(10, .)), and against the rule's defining property."""
+    for lo, hi, n, lg in ((10.0, 2048.0, 1000, True), (20.0, 1024.0, 257, True), (-1.0, 3.0, 16, False), (5.0, 6.0, 1, False)):
+        f, w = engine.gauss_legendre_grid(lo, hi, n, lg)
+        rf, rw = oracle.gauleg_grid(lo, hi, n, lg)
+        assert np.allclose(f, rf, rtol=1e-14, atol=0) and np.allclose(w, rw, rtol=1e-12, atol=0)
+        assert np.all(np.diff(f) > 0) if n > 1 else True
+    x, w = engine.gauss_legendre_grid(0.0, 2.0, 12, False)
+    # exact for polynomials up to degree 2n - 1 -- to the 1e-10 at which the algorithm (and the reference) stops Newton's
+    # iteration: the weights are formed from the derivative at the last-but-one iterate
+    for k in range(0, 24):
+        assert abs((w * x ** k).sum() - 2.0 ** (k + 1) / (k + 1)) <= 1e-9 * 2.0 ** (k + 1)
+    f, w = engine.gauss_legendre_grid(10.0, 1000.0, 64, True)
+    assert abs((w * f * np.log(10.0)).sum() - 990.0) <= 1e-9 * 990.0  # int df = int f ln10 dlog10 f
+    with pytest.raises(engine.GwatB200Error):
+        engine.gauss_legendre_grid(10.0, 5.0, 8, True)
