@@ -52,6 +52,15 @@ def ncu_traffic(config):
         return None
 
 
+def ncu_pipe_pct(config):
+    """FP64-pipe utilisation (sm__inst_executed_pipe_fp64, % of peak sustained active) of k_loglike from the same capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t["cfg%d" % config]["fp64_pipe_active_pct"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def flop_eq_per_bin(method, D):
     a, b = FLOP_EQ[method]
     return a + b * D
@@ -304,7 +313,7 @@ def run_b200(args):
                 "peak_source": "DFMA-chain microbenchmark run in this process (gwat_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "work": "%d flop-eq per active (walker,bin) [SURVEY 8(d)] x %.4g active bins per launch (%.1f%% of W*L)" % (
                     feq, act, 100.0 * act / (W * L)),
-                "kernel_ms": k_ms, "traffic": ncu_traffic(args.config),
+                "kernel_ms": k_ms, "traffic": ncu_traffic(args.config), "fp64_pipe_active_pct_ncu": ncu_pipe_pct(args.config),
                 "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",

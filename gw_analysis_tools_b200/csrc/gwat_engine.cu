@@ -59,7 +59,7 @@ constexpr int kSetupThreads = 32;
 
 __device__ __forceinline__ Tables device_tables()
 {
-	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS}};
+	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS, gwat_md_alphas, gwat_md_boundaries_z, gwat_md_coeffs, GWAT_MD_ALPHAS}};
 }
 
 typedef LikeGrid GridPtrs;

@@ -95,20 +95,21 @@ inline int parse_method(const char *method_c, MethodDesc &d)
 	struct Theory {
 		const char *prefix;
 		int id;
-		int generic;  // 1: inspiral/IMR chosen by the suffix; 0: inspiral-only ppE
+		int generic;  // 1: inspiral/IMR chosen by the suffix; 0: inspiral-only ppE; 2: always the IMR ppE
 	};
 	static const Theory theories[] = {
 	    {"EdGB_HO_LO_", THEORY_EDGB_HO_LO, 0}, {"EdGB_HO_", THEORY_EDGB, 0},          {"EdGB_GHOv1_", THEORY_EDGB_GHOV1, 0},
 	    {"EdGB_GHOv2_", THEORY_EDGB_GHOV2, 0}, {"EdGB_GHOv3_", THEORY_EDGB_GHOV3, 0}, {"ExtraDimension_", THEORY_EXTRADIM, 0},
 	    {"BHEvaporation_", THEORY_BHEVAP, 0},  {"TVG_", THEORY_TVG, 0},               {"DipRad_", THEORY_DIPRAD, 0},
 	    {"NonComm_", THEORY_NONCOMM, 0},       {"PNSeries_ppE_", THEORY_PNSERIES, 1}, {"ppEAlt_", THEORY_PPEALT, 1},
+	    {"ModDispersion_", THEORY_MODDISP, 2},
 	};
 	for (const Theory &t : theories) {
 		const std::string pre(t.prefix);
 		if (m.compare(0, pre.size(), pre) != 0) continue;
 		std::string rest = m.substr(pre.size());
-		bool ins = true;
-		if (t.generic) {
+		bool ins = t.generic != 2;
+		if (t.generic == 1) {
 			const std::string a = "_Inspiral", b = "_IMR";
 			if (rest.size() > a.size() && rest.compare(rest.size() - a.size(), a.size(), a) == 0) rest.erase(rest.size() - a.size());
 			else if (rest.size() > b.size() && rest.compare(rest.size() - b.size(), b.size(), b) == 0) {

@@ -17,6 +17,11 @@ struct DzTable {
 	const double *boundaries;   // [segments + 1]
 	const double (*coeffs)[12];  // [segments][12]
 	int segments;
+	// modified-dispersion distance D_alpha(z) (ModDispersion theory): alphas[n], z boundaries [n][4], coefficients [n][3][17]
+	const double *md_alphas;
+	const double (*md_boundaries_z)[4];
+	const double (*md_coeffs)[3][17];
+	int md_n;
 };
 
 GWAT_HD double pow_int_seq(double base, int power)
@@ -39,6 +44,27 @@ GWAT_HD double z_from_dl(double DL_mpc, const DzTable &t)
 			const double rootx = sqrt(DL_mpc);
 			for (int k = 1; k < 12; k++) sum += c[k] * pow_int_seq(rootx, k);
 			return sum;
+		}
+	}
+	return -1;
+}
+
+// DL_from_Z_MD + cosmology_interpolation_function_MD + dispersion_lookup (src/ppE_utilities.cpp:785-835): Mpc, -1 if alpha or z
+// is outside the tables
+GWAT_HD double dl_from_z_md(double Z, double alpha, const DzTable &t)
+{
+	int idx = -1;
+	for (int i = 0; i < t.md_n; i++)
+		if (fabs(alpha - t.md_alphas[i]) < 1e-10) {
+			idx = i;
+			break;
+		}
+	if (idx < 0) return -1;
+	for (int i = 0; i < 3; i++) {
+		if (Z < t.md_boundaries_z[idx][i + 1]) {
+			double result = 0;
+			for (int j = 0; j < 17; j++) result += t.md_coeffs[idx][i][j] * pow(Z, -3.5 + j * 0.5);
+			return result;
 		}
 	}
 	return -1;
@@ -79,7 +105,7 @@ GWAT_HD double edgb_phase_factor(const SrcQ &s, double m1, double m2)
 enum TheoryId {
 	THEORY_NONE = 0, THEORY_DCS = 1, THEORY_EDGB = 2, THEORY_EDGB_HO_LO = 3, THEORY_EDGB_GHOV1 = 4, THEORY_EDGB_GHOV2 = 5,
 	THEORY_EDGB_GHOV3 = 6, THEORY_EXTRADIM = 7, THEORY_BHEVAP = 8, THEORY_TVG = 9, THEORY_DIPRAD = 10, THEORY_NONCOMM = 11,
-	THEORY_PNSERIES = 12, THEORY_PPEALT = 13
+	THEORY_PNSERIES = 12, THEORY_PPEALT = 13, THEORY_MODDISP = 14
 };
 // MCMC_prep_params converts sqrt(alpha)[km] -> alpha^2 [s^4] for every method whose name contains dCS or EdGB (src/mcmc_gw.cpp:2560)
 GWAT_HD bool theory_alpha_units(int theory) { return theory >= THEORY_DCS && theory <= THEORY_EDGB_GHOV3; }
@@ -165,6 +191,15 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 			if (i == 0 || theory == THEORY_PPEALT) beta[i] = s.betappe[i] * conv;
 			else beta[i] = s.betappe[0] * s.betappe[i] * conv;
 		}
+		break;
+	}
+	case THEORY_MODDISP: {  // ModDispersion_beta (:750-769), arXiv:1110.2720; b = 3 alpha - 3 comes from the caller
+		const double alpha = (s.bppe[0] + 3.) / 3.;
+		const double Dalpha = dl_from_z_md(Z, alpha, dz) * GWAT_MPC_SEC;
+		const double h_planck = 4.135667696e-15;
+		beta[0] = (pow(GWAT_PI, 2. - alpha) / (1. - alpha)) * (Dalpha * in0 / pow(h_planck, 2. - alpha)) *
+		          (pow(s.chirpmass, 1. - alpha) / pow(1 + Z, 1. - alpha));
+		b[0] = s.bppe[0];
 		break;
 	}
 	default:

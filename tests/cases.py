@@ -62,6 +62,11 @@ THEORY_CASES = [
     ("PNSeries_imr", "PNSeries_ppE_IMRPhenomPv2_IMR", dict(PREC, Nmod=2, bppe=[-1., 1.], betappe=[0.1, 0.5]), GRID_BBH),
     ("ppEAlt_ins", "ppEAlt_IMRPhenomD_Inspiral", dict(BBH, Nmod=2, bppe=[-7., -3.], betappe=[1e-6, 0.02]), GRID_BBH),
     ("ppEAlt_imr", "ppEAlt_IMRPhenomD_IMR", dict(BBH, Nmod=2, bppe=[-1., 1.], betappe=[0.1, 0.5]), GRID_BBH),
+    # modified dispersion (arXiv:1110.2720): b = 3 alpha - 3 selects the table of D_alpha(z); betappe[0] = A_alpha
+    ("ModDisp_a0", "ModDispersion_IMRPhenomD", dict(BBH, Nmod=1, bppe=[-3.], betappe=[1e-45]), GRID_BBH),
+    ("ModDisp_a05", "ModDispersion_IMRPhenomD", dict(BBH_LOW, Nmod=1, bppe=[-1.5], betappe=[1e-39]), GRID_BBH),
+    ("ModDisp_a15", "ModDispersion_IMRPhenomPv2", dict(PREC, Nmod=1, bppe=[1.5], betappe=[1e-26]), GRID_BBH),
+    ("ModDisp_a2", "ModDispersion_IMRPhenomD", dict(BBH, Nmod=1, bppe=[3.], betappe=[5e-21]), GRID_BBH),  # linear in f: absorbed by the time shift
 ]
 DETECTORS = ["Hanford", "Livingston", "Virgo"]
 

@@ -304,3 +304,43 @@ def test_odd_length_and_all_bins_above_cutoff(ctx, oracle):
     hp, hc = ctx.fourier_waveform_batch("IMRPhenomD", [heavy])
     assert not hp.any() and not hc.any()
     assert ctx.last_active_bins == 0
+
+
+def test_glq_grid_end_to_end(ctx, oracle):
+    """The library's own Gauss-Legendre grid (log10 f nodes) through the GAUSSLEG likelihood, against the reference fed the same grid."""
+    from gw_analysis_tools_b200 import engine
+    f, w = engine.gauss_legendre_grid(20.0, 1024.0, 300, True)
+    wl = workloads.make(2, W=24, L=1024)
+    psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+    ctx.set_network(wl.detectors, f, psd, None, w, "GAUSSLEG", True)
+    src = ctx.repack_mcmc_batch(wl.method, wl.inj[None, :], wl.gmst, wl.mod)
+    src[0].tc = wl.T_segment - src[0].tc
+    data = ctx.coherent_response_batch(wl.method, src)[0]
+    ctx.set_network(wl.detectors, f, psd, data, w, "GAUSSLEG", True)
+    got = ctx.loglike_mcmc_batch(wl.method, wl.params, wl.gmst, wl.T_segment, wl.mod)
+    want = oracle.loglike_mcmc_batch(wl.method, wl.mod, wl.params, wl.gmst, wl.T_segment, wl.detectors, f, psd, data, weights=w,
+                                     integ="GAUSSLEG", log10F=True)
+    assert (np.abs(got - want) / np.abs(want)).max() <= LL_TOL
+
+
+def test_concurrent_callers_share_a_context(ctx, gold_mcmc):
+    """Thread safety of the C ABI ('Threading'): several host threads submit batches to ONE context at once
+    (ctypes releases the GIL); every call returns exactly what it returns alone."""
+    import threading
+    wl = workloads.make(2, W=64, L=1024)
+    ctx.set_network(wl.detectors, wl.f, wl.psd, gold_mcmc["cfg2/data"])
+    chunks = [wl.params[i::4] for i in range(4)]
+    alone = [ctx.loglike_mcmc_batch(wl.method, c, wl.gmst, wl.T_segment, wl.mod) for c in chunks]
+    results = [[None] * 8 for _ in range(4)]
+
+    def work(k):
+        for it in range(8):
+            results[k][it] = ctx.loglike_mcmc_batch(wl.method, chunks[k], wl.gmst, wl.T_segment, wl.mod)
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(4):
+        for it in range(8):
+            assert np.array_equal(results[k][it], alone[k])

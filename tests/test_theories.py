@@ -1,5 +1,5 @@
 """Theory -> ppE mappings beyond dCS/EdGB (assign_mapping, src/ppE_utilities.cpp:158-359): EdGB_HO (== EdGB, a quirk of the
-reference's if-chain), EdGB_HO_LO, EdGB_GHOv1-3, ExtraDimension, BHEvaporation, TVG, DipRad, NonComm, PNSeries_ppE, ppEAlt.
+reference's if-chain), EdGB_HO_LO, EdGB_GHOv1-3, ExtraDimension, BHEvaporation, TVG, DipRad, NonComm, ModDispersion, PNSeries_ppE, ppEAlt.
 Golden values from the reference's own code (tests/golden/make_golden.py --only-theories); 1e-10 on waveforms, 1e-9 on logL.
 """
 import ctypes as C
@@ -109,11 +109,12 @@ def test_theory_mcmc_vectors_and_fisher(ctx, oracle):
     from oracle import ptmcmc_ref
     # rows/columns of the coupling itself are left out: the stencil steps alpha^2 ~ 1e-20 s^4 by eps = 1e-8 (absolute, as the
     # reference does, src/fisher.cpp:340-543), which overflows on both sides and says nothing about either
-    keep = np.array([i for i in range(13) if i != 11])
+    # ... and so is the row of the generic second parameter: a derivative of ~1e-20 relative size on top of eps = 1e-8
+    # cancellation noise, different on every machine
+    keep = np.arange(11)
     for i in range(2):
         want_f = ptmcmc_ref.fisher_transformations(ref[i], False, True, 2, params[i])[np.ix_(keep, keep)]
         got_f = F[i][np.ix_(keep, keep)]
         dg = np.sqrt(np.abs(np.diag(want_f)))
         nerr = np.abs(got_f - want_f) / np.outer(dg, dg)
-        # the row of the generic second parameter is a small derivative on top of eps = 1e-8 cancellation noise (1e-4 level)
-        assert np.median(nerr) <= 1e-6 and nerr.max() <= 1e-3, (np.median(nerr), nerr.max())
+        assert np.median(nerr) <= 1e-6 and nerr.max() <= 1e-4, (np.median(nerr), nerr.max())

@@ -112,6 +112,15 @@ def main():
     bD0 = bD[:nseg + 1]
     cDZ0 = cDZ[:nseg * ndeg]
 
+    # modified-dispersion distance D_alpha(z) (include/gwat/D_Z_Config_modified_dispersion.h: MD_alphas, MD_boundaries_Z,
+    # MD_COEFF_VEC_ZD; evaluated by DL_from_Z_MD, src/ppE_utilities.cpp:785-822: sum_j c_j z^(-3.5 + j/2))
+    md = strip_comments(open(os.path.join(REF, "include/gwat/D_Z_Config_modified_dispersion.h")).read())
+    md_alphas = numbers(array_body(md, "MD_alphas"))
+    md_bz = numbers(array_body(md, "MD_boundaries_Z"))
+    md_c = numbers(array_body(md, "MD_COEFF_VEC_ZD"))
+    na, md_seg, md_deg = len(md_alphas), 3, 17
+    assert na == 9 and len(md_bz) == na * (md_seg + 1) and len(md_c) == na * md_seg * md_deg, (na, len(md_bz), len(md_c))
+
     r = repr
     with open(OUT, "w") as o:
         o.write("// GENERATED by tools/gen_tables.py from the reference's numerical data tables -- do not edit.\n")
@@ -133,6 +142,21 @@ def main():
         o.write("GWAT_TABLE_QUALIFIER double gwat_dz_coeffs[GWAT_DZ_SEGMENTS][GWAT_DZ_DEGREE] = {\n")
         for i in range(nseg):
             o.write("{" + ",".join(r(x) for x in cDZ0[i * ndeg:(i + 1) * ndeg]) + "},\n")
+        o.write("};\n\n")
+        o.write("// modified-dispersion distance D_alpha(z)/Mpc: alphas, z boundaries per alpha, coefficients of sum_j c_j z^(-3.5 + j/2)\n")
+        o.write("#define GWAT_MD_ALPHAS %d\n#define GWAT_MD_SEGMENTS %d\n#define GWAT_MD_DEGREE %d\n" % (na, md_seg, md_deg))
+        o.write("GWAT_TABLE_QUALIFIER double gwat_md_alphas[GWAT_MD_ALPHAS] = {" + ",".join(r(x) for x in md_alphas) + "};\n")
+        o.write("GWAT_TABLE_QUALIFIER double gwat_md_boundaries_z[GWAT_MD_ALPHAS][GWAT_MD_SEGMENTS + 1] = {\n")
+        for i in range(na):
+            o.write("{" + ",".join(r(x) for x in md_bz[i * (md_seg + 1):(i + 1) * (md_seg + 1)]) + "},\n")
+        o.write("};\n")
+        o.write("GWAT_TABLE_QUALIFIER double gwat_md_coeffs[GWAT_MD_ALPHAS][GWAT_MD_SEGMENTS][GWAT_MD_DEGREE] = {\n")
+        for i in range(na):
+            o.write("{")
+            for k in range(md_seg):
+                base = (i * md_seg + k) * md_deg
+                o.write("{" + ",".join(r(x) for x in md_c[base:base + md_deg]) + "},")
+            o.write("},\n")
         o.write("};\n\n")
         o.write("#define GWAT_NUM_KNOWN_DETECTORS %d\n" % len(rows))
         o.write("// per detector: 9 response-tensor entries (row-major), 3 vertex coordinates [m], geometric factor\n")
