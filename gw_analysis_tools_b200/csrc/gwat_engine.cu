@@ -980,16 +980,15 @@ int gwat_b200_loglike_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const g
 	if (int rc = check_ready(ctx, true)) return rc;
 	if (W < 0 || (W > 0 && (!params || !logL))) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: NULL array");
 	if (W == 0) return GWAT_B200_OK;
-	{
-		std::lock_guard<std::mutex> lock(ctx->mu);
-		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-		if (grow(ctx, ctx->d_params, ctx->cap_params, (size_t)W * dimension)) return GWAT_B200_ERR_CUDA;
-		if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, ctx->stream));
-	}
-	if (int rc = gwat_b200_loglike_mcmc_batch_dev(ctx, method, mod, dimension, W, ctx->d_params, gmst, T_segment, ctx->d_out, nullptr))
-		return rc;
+	if (dimension < 1 || dimension > GWAT_B200_MAX_DIM) return fail(ctx, GWAT_B200_ERR_ARG, "loglike_mcmc_batch: dimension out of range");
+	// one critical section from upload to download: the staging buffers belong to the context, and callers may share it
 	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (grow(ctx, ctx->d_params, ctx->cap_params, (size_t)W * dimension)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, ctx->stream));
+	if (int rc = gwat_internal::loglike_mcmc_lane(ctx, 0, method, mod, dimension, W, ctx->d_params, gmst, T_segment, ctx->d_out, ctx->stream))
+		return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(logL, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
 	return collect_stats(ctx, ctx->stream);
 }
