@@ -3,14 +3,14 @@
 // Data layout in HBM (per context = per GPU):
 //   grid tables      f[L], sf_hi[L], sf_lo[L], logf[L]                      shared by every walker, L2-resident
 //   network tables   wq[D][L] = quadrature coefficient / PSD,  data_re[D][L], data_im[D][L]
-//   per call         params[W][P] -> WalkerCoef[W] (setup kernel) -> partial[W][chunks][2] -> logL[W]
+//   per call         params[W][P] -> WalkerCoef[W] (setup kernel) -> partial[W][units][8 warps][2] -> logL[W]
 // Kernels:
 //   k_setup_mcmc / k_setup_src   one thread per walker: sampling vector or physical record -> WalkerCoef
-//   k_loglike                    grid (bin chunks, walkers); threads stride over consecutive bins (coalesced table reads,
+//   k_loglike                    grid (walkers, bin chunks); threads stride over consecutive bins (coalesced table reads,
 //                                region branches diverge only at the per-walker boundaries); amplitude/phase in FP64,
-//                                detector projection and PSD weighting in registers, warp-shuffle + shared-memory
-//                                reduction to one partial per (walker, chunk)
-//   k_finish                     deterministic sum of the partials -> logL
+//                                detector projection and PSD weighting in registers, per-CTA seed tables for the
+//                                recurrences, warp-shuffle reduction to one partial per (walker, unit, warp)
+//   k_finish                     fixed-order sum of a walker's partials (one warp per walker) -> logL
 //   k_waveform / k_response      the same per-bin code writing polarisations / responses (API parity entry points)
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
@@ -43,8 +43,12 @@ using namespace gwat;
 namespace {
 
 constexpr int kThreads = 256;
-#ifndef GWAT_LOGLIKE_MIN_CTAS
-#define GWAT_LOGLIKE_MIN_CTAS 3
+// Kernel experiments only (never the shipped library): -DGWAT_EXPERIMENT_SLIM compiles 4 of the 11 families and 2 of the 5
+// detector counts so that a variant builds in a minute.
+#ifdef GWAT_EXPERIMENT_SLIM
+#define GWAT_FULL_ONLY(...)
+#else
+#define GWAT_FULL_ONLY(...) __VA_ARGS__
 #endif
 #ifndef GWAT_LOGLIKE_THREADS
 #define GWAT_LOGLIKE_THREADS 256
@@ -154,157 +158,85 @@ __device__ __forceinline__ void load_walker(const WalkerCoef *__restrict__ src, 
 	__syncthreads();
 }
 
+// Resident CTAs per SM the bin kernel is compiled for.  64 registers (4 CTAs, 32 warps/SM) spill a little but hide the
+// FP64 latency better for the PhenomD and PhenomPv2 families (measured: cfg1 -5 %, cfg2 -2 %, cfg4 -6 %); the NRTidal bin is
+// the heaviest and runs best with 80 registers (3 CTAs).
+template <class Fam>
+constexpr int like_min_ctas()
+{
+#ifdef GWAT_LOGLIKE_MIN_CTAS
+	return GWAT_LOGLIKE_MIN_CTAS;
+#else
+	return Fam::nrt ? 3 : 4;
+#endif
+}
+
+// grid (walkers, chunks): a CTA evaluates `units_per_cta` consecutive units of one walker (see gwat_like.h for the cut) and
+// writes one partial sum per (unit, warp):  partial[walker][unit][warp][2] = {sum, active bins}.
 template <class Fam, int D>
-__global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int bins_per_cta,
-                                                     double *__restrict__ partial)
+__global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int unit_bins,
+                                                                              int units_per_cta, int units_total, double *__restrict__ partial)
 {
+	static_assert(kLikeThreads == kUnitThreads && kSeedSlots * (D + 1) <= kLikeThreads, "seed table layout");
 	__shared__ WalkerCoef w;
-	load_walker(coefs + blockIdx.x, w);
-	const int begin = blockIdx.y * bins_per_cta;
-	const int end = min(g.L, begin + bins_per_cta);
-	double acc = 0.0, nact = 0.0;
-	if (w.valid) loglike_run<Fam, D>(w, g, begin + threadIdx.x, end, kLikeThreads, acc, nact);
-	block_sum2<kLikeThreads>(acc, nact);
-	if (threadIdx.x == 0) {
-		double *p = partial + 2 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
-		p[0] = w.valid ? acc : NAN;
-		p[1] = nact;
-	}
-}
-
-// ---- bulk-copy (TMA) staging of the grid tiles ---------------------------------------------------------------------------
-// The likelihood kernel streams 4 + 3 D table values per bin that are shared by every walker.  One elected thread per CTA
-// issues `cp.async.bulk` (UBLKCP) copies of whole 256-bin tiles into a two-stage shared-memory ring and signals an
-// mbarrier; the compute threads read their bin from shared memory (conflict-free: consecutive threads, consecutive
-// doubles) instead of waiting on 13 scattered L2 round trips per bin.
-__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-	             "l"(src), "r"(bytes), "r"(smem_addr(bar))
-	             : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "WAIT_LOOP:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra WAIT_DONE;\n"
-	    "bra WAIT_LOOP;\n"
-	    "WAIT_DONE:\n"
-	    "}\n" ::"r"(smem_addr(bar)),
-	    "r"(parity)
-	    : "memory");
-}
-
-// Table access from a staged shared-memory tile: rows 4.. of the tile are wq[D], dre[D], dim[D].
-template <int TILE, int D>
-struct TileTab {
-	const double *base;  // &tile[stage][4][thread]
-	__device__ __forceinline__ double wq(int d) const { return base[d * TILE]; }
-	__device__ __forceinline__ double dre(int d) const { return base[(D + d) * TILE]; }
-	__device__ __forceinline__ double dim(int d) const { return base[(2 * D + d) * TILE]; }
-};
-
-template <class Fam, int D>
-__global__ void __launch_bounds__(kLikeThreads, GWAT_LOGLIKE_MIN_CTAS) k_loglike_tma(const WalkerCoef *__restrict__ coefs, GridPtrs g,
-                                                                                  int bins_per_cta, double *__restrict__ partial)
-{
-	constexpr int NARR = 4 + 3 * D;
-	constexpr int TILE = kLikeThreads;
-	constexpr unsigned TILE_BYTES = TILE * sizeof(double);
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	double(*tile)[NARR][TILE] = reinterpret_cast<double(*)[NARR][TILE]>(smem_raw);  // [2][NARR][TILE]
-	__shared__ WalkerCoef w;
-	__shared__ __align__(8) unsigned long long bar[2];
-	if (threadIdx.x == 0) {
-		mbar_init(&bar[0], 1);
-		mbar_init(&bar[1], 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	load_walker(coefs + blockIdx.x, w);  // ends with __syncthreads(): the barriers are initialised for everyone
-
-	const int begin = blockIdx.y * bins_per_cta;
-	const int end = min(g.ld, begin + bins_per_cta);
-	int ntiles = (end - begin + TILE - 1) / TILE;
-	const bool uniform = g.uniform != 0;
-	const double fmax = walker_fmax<Fam>(w);
-	if (!w.valid) ntiles = 0;
-	if (uniform && ntiles > 0) {
-		// ascending grid: tiles that start above the model's cutoff contribute exactly zero -- never fetched
-		const double f_begin = g.f[begin];
-		if (f_begin > fmax) ntiles = 0;
-		else {
-			const double span = (fmax - f_begin) / g.df;  // bins of this chunk at or below the cutoff
-			const int live = (int)fmin(span, 2.0e9) / TILE + 1;
-			ntiles = min(ntiles, live);
+	__shared__ CtaSeeds<D> seeds;
+	const int unit0 = blockIdx.y * units_per_cta;
+	const int n_units = min(units_per_cta, units_total - unit0);
+	const int begin = unit0 * unit_bins;
+	double *pout = partial + 2 * kUnitWarps * ((size_t)blockIdx.x * units_total + unit0);
+	if (g.uniform) {
+		// ascending grid: a chunk that starts above the walker's cutoff contributes exactly zero.  Decided from two words of
+		// the coefficient record before anything is staged, so such CTAs cost one L2 round trip.
+		const WalkerCoef &wg = coefs[blockIdx.x];
+		if (wg.valid && g.f[begin] > walker_fmax<Fam>(wg)) {
+			if (threadIdx.x < 2 * kUnitWarps * n_units) pout[threadIdx.x] = 0.0;
+			return;
 		}
 	}
-	const double *src[NARR];
-	src[0] = g.f;
-	src[1] = g.sf_hi;
-	src[2] = g.sf_lo;
-	src[3] = g.logf;
-#pragma unroll
-	for (int d = 0; d < D; d++) {
-		src[4 + d] = g.wq + (size_t)d * g.ld;
-		src[4 + D + d] = g.dre + (size_t)d * g.ld;
-		src[4 + 2 * D + d] = g.dim + (size_t)d * g.ld;
+	load_walker(coefs + blockIdx.x, w);
+	const bool seeded = g.uniform != 0 && w.valid;  // the same for the whole CTA
+	if (seeded) {
+		if (threadIdx.x < kSeedSlots * (D + 1)) cta_seed_slot<D>(w, g, begin, unit_bins, n_units, kLikeThreads, threadIdx.x, seeds);
+		__syncthreads();
 	}
-	auto issue = [&](int t) {
-		const int s_ = t & 1;
-		mbar_expect_tx(&bar[s_], NARR * TILE_BYTES);
-#pragma unroll
-		for (int a = 0; a < NARR; a++) bulk_g2s(&tile[s_][a][0], src[a] + begin + (size_t)t * TILE, TILE_BYTES, &bar[s_]);
-	};
-	if (threadIdx.x == 0) {
-		if (ntiles > 0) issue(0);
-		if (ntiles > 1) issue(1);
-	}
-	double acc = 0.0, nact = 0.0;
-	LikeState<D> st;
-	for (int t = 0; t < ntiles; t++) {
-		const int s_ = t & 1;
-		mbar_wait(&bar[s_], (t >> 1) & 1);
-		// (the asm above is also the compiler barrier that keeps the walker's coefficients in shared memory, not registers)
-		const double f = tile[s_][0][threadIdx.x];
-		if (t == 0 && uniform) like_state_init<D>(w, f, g.df * TILE, f + g.df * TILE * (ntiles - 1), st);
-		const TileTab<TILE, D> tab{&tile[s_][4][threadIdx.x]};
-		like_bin<Fam, D>(w, uniform, st, f, tile[s_][1][threadIdx.x], tile[s_][2][threadIdx.x], tile[s_][3][threadIdx.x], tab, acc, nact);
-		__syncthreads();  // everyone is done with this stage before it is refilled
-		if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
-	}
-	block_sum2<kLikeThreads>(acc, nact);
-	if (threadIdx.x == 0) {
-		double *p = partial + 2 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
-		p[0] = w.valid ? acc : NAN;
-		p[1] = nact;
+	const double fmax = walker_fmax<Fam>(w);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	bool live = w.valid != 0;
+	for (int u = 0; u < n_units; u++) {
+		double acc = 0.0;
+		int nact = 0;
+		const int ub = begin + u * unit_bins;
+		if (live) live = loglike_unit<Fam, D>(w, g, ub + threadIdx.x, min(g.L, ub + unit_bins), kLikeThreads, fmax, acc, nact,
+		                                      seeded ? &seeds : nullptr, u, threadIdx.x);
+		acc = warp_sum(acc);
+		nact = __reduce_add_sync(0xffffffffu, nact);
+		if (lane == 0) {
+			double *p = pout + 2 * (u * kUnitWarps + wid);
+			p[0] = w.valid ? acc : NAN;
+			p[1] = (double)nact;
+		}
 	}
 }
 
-// logL[w] = -1/2 * prefactor * sum_chunks partial        (Log_Likelihood_internal: -0.5*(HH - 2*DH), src/mcmc_gw.cpp:866)
-__global__ void k_finish(const double *__restrict__ partial, int W, int chunks, double prefactor, double *__restrict__ logL,
+// logL[w] = -1/2 * prefactor * sum of the walker's partials   (Log_Likelihood_internal: -0.5*(HH - 2*DH), src/mcmc_gw.cpp:866)
+// One warp per walker: lane l adds entries l, l + 32, ... in order, then the shuffle tree -- a fixed order for a given grid.
+__global__ void k_finish(const double *__restrict__ partial, int W, int entries, double prefactor, double *__restrict__ logL,
                          unsigned long long *__restrict__ active_total)
 {
-	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (w >= W) return;
+	const double *p = partial + 2 * (size_t)w * entries;
 	double s = 0, n = 0;
-	for (int c = 0; c < chunks; c++) {
-		s += partial[2 * ((size_t)w * chunks + c)];
-		n += partial[2 * ((size_t)w * chunks + c) + 1];
+	for (int e = lane; e < entries; e += 32) {
+		s += p[2 * e];
+		n += p[2 * e + 1];
 	}
-	logL[w] = -0.5 * (prefactor * s);
-	if (active_total) atomicAdd(active_total, (unsigned long long)n);
+	s = warp_sum(s);
+	n = warp_sum(n);
+	if (lane == 0) {
+		logL[w] = -0.5 * (prefactor * s);
+		if (active_total) atomicAdd(active_total, (unsigned long long)n);
+	}
 }
 
 template <class Fam>
@@ -598,77 +530,71 @@ int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, R
 		switch ((desc).family_id) {                                                                                          \
 		case FAM_D: { typedef Family<BASE_D, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                              \
 		case FAM_D_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }                  \
-		case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }                       \
-		case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                          \
+		GWAT_FULL_ONLY(case FAM_D_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }) \
+		GWAT_FULL_ONLY(case FAM_D_GIMR: { typedef Family<BASE_D, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }) \
 		case FAM_D_NRT: { typedef Family<BASE_D, PPE_NONE, false, true> Fam; __VA_ARGS__; break; }                           \
-		case FAM_D_NRT_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, true> Fam; __VA_ARGS__; break; }               \
-		case FAM_D_NRT_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, true> Fam; __VA_ARGS__; break; }                    \
+		GWAT_FULL_ONLY(case FAM_D_NRT_PPE_INS: { typedef Family<BASE_D, PPE_INSPIRAL, false, true> Fam; __VA_ARGS__; break; }) \
+		GWAT_FULL_ONLY(case FAM_D_NRT_PPE_IMR: { typedef Family<BASE_D, PPE_IMR, false, true> Fam; __VA_ARGS__; break; }) \
 		case FAM_P: { typedef Family<BASE_P, PPE_NONE, false, false> Fam; __VA_ARGS__; break; }                              \
-		case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }                  \
-		case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }                       \
-		case FAM_P_GIMR: { typedef Family<BASE_P, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }                          \
+		GWAT_FULL_ONLY(case FAM_P_PPE_INS: { typedef Family<BASE_P, PPE_INSPIRAL, false, false> Fam; __VA_ARGS__; break; }) \
+		GWAT_FULL_ONLY(case FAM_P_PPE_IMR: { typedef Family<BASE_P, PPE_IMR, false, false> Fam; __VA_ARGS__; break; }) \
+		GWAT_FULL_ONLY(case FAM_P_GIMR: { typedef Family<BASE_P, PPE_NONE, true, false> Fam; __VA_ARGS__; break; }) \
 		default: return fail(ctx, GWAT_B200_ERR_METHOD, std::string("generation_method not implemented: ") + (desc).base);   \
 		}                                                                                                                    \
 	} while (0)
 
-template <class Fam, int D>
-int launch_loglike_d(gwat_b200_ctx *ctx, const GridPtrs &g, dim3 grid, int bins_per_cta, cudaStream_t st)
-{
-	if (ctx->use_tma) {
-		constexpr size_t smem = (size_t)2 * (4 + 3 * D) * kLikeThreads * sizeof(double);
-		static bool configured[64] = {};
-		if (!configured[ctx->device & 63]) {
-			if (cudaFuncSetAttribute(k_loglike_tma<Fam, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-			configured[ctx->device & 63] = true;
-		}
-		k_loglike_tma<Fam, D><<<grid, kLikeThreads, smem, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial);
-	} else {
-		k_loglike<Fam, D><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, bins_per_cta, ctx->d_partial);
-	}
-	return 0;
-}
+struct LikeCut {
+	int unit_bins, units_total, units_per_cta, chunks;
+};
 
 template <class Fam>
-int launch_loglike(gwat_b200_ctx *ctx, int W, int chunks, int bins_per_cta, cudaStream_t st)
+int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t st)
 {
 	const GridPtrs g = grid_ptrs(ctx);
 	// walkers vary fastest: CTAs in flight together work on the same stretch of the grid tables, so a tile is fetched from
 	// HBM once per pass even when the tables (cfg5: 109 MB) do not fit in L2
-	const dim3 grid(W, chunks);
+	const dim3 grid(W, cut.chunks);
+#define GWAT_LAUNCH_LIKE(DD)                                                                                                      \
+	case DD:                                                                                                                      \
+		k_loglike<Fam, DD><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, cut.unit_bins, cut.units_per_cta, cut.units_total, ctx->d_partial); \
+		return 0;
 	switch (ctx->D) {
-	case 1: return launch_loglike_d<Fam, 1>(ctx, g, grid, bins_per_cta, st);
-	case 2: return launch_loglike_d<Fam, 2>(ctx, g, grid, bins_per_cta, st);
-	case 3: return launch_loglike_d<Fam, 3>(ctx, g, grid, bins_per_cta, st);
-	case 4: return launch_loglike_d<Fam, 4>(ctx, g, grid, bins_per_cta, st);
-	case 5: return launch_loglike_d<Fam, 5>(ctx, g, grid, bins_per_cta, st);
+		GWAT_FULL_ONLY(GWAT_LAUNCH_LIKE(1))
+		GWAT_LAUNCH_LIKE(2)
+		GWAT_LAUNCH_LIKE(3)
+		GWAT_FULL_ONLY(GWAT_LAUNCH_LIKE(4))
+		GWAT_FULL_ONLY(GWAT_LAUNCH_LIKE(5))
 	default: return -1;
 	}
+#undef GWAT_LAUNCH_LIKE
 }
 
-// How the bin axis is cut into CTAs: enough CTAs to fill 148 SMs a few times over, chunks a multiple of the block size.
-void choose_chunks(int W, int L, int &chunks, int &bins_per_cta)
+// The cut of the bin axis into units is a property of the grid (gwat_like.h: unit_bins_for); only the number of consecutive
+// units a CTA evaluates depends on W: runs of up to 64 bins per thread for big ensembles (the per-CTA start-up -- coefficient
+// load, seed table, first table reads -- is worth about one bin per thread), shorter runs when few walkers have to fill
+// 148 SMs.  Results do not depend on that choice.
+LikeCut choose_cut(int W, int L)
 {
-	const long long target_ctas = 148LL * 8;
-	long long want = (target_ctas + W - 1) / W;
-	long long max_chunks = (L + kLikeThreads - 1) / kLikeThreads;
-	if (want < 1) want = 1;
-	if (want > max_chunks) want = max_chunks;
-	long long per = (L + want - 1) / want;
-	per = ((per + kLikeThreads - 1) / kLikeThreads) * kLikeThreads;
-	// keep the per-thread trip count bounded so the tail CTA of a long grid does not dominate
-	const long long cap = 64LL * kLikeThreads;
-	if (per > cap) per = cap;
-	bins_per_cta = (int)per;
-	chunks = (int)((L + per - 1) / per);
+	static const int upc_env = getenv("GWAT_B200_UNITS_PER_CTA") ? atoi(getenv("GWAT_B200_UNITS_PER_CTA")) : 0;  // experiments only
+	LikeCut c;
+	c.unit_bins = unit_bins_for(L);
+	c.units_total = (L + c.unit_bins - 1) / c.unit_bins;
+	int upc = (64 * kUnitThreads) / c.unit_bins;  // 4 for grids up to 2^19 bins, 1 for the longest
+	auto chunks_for = [&](int n) { return (c.units_total + n - 1) / n; };
+	while (upc > 1 && (long long)W * chunks_for(upc) < 148LL * 12) upc /= 2;
+	if (upc_env > 0 && upc_env <= kMaxUnitsPerCta) upc = upc_env;
+	c.units_per_cta = upc;
+	c.chunks = chunks_for(upc);
+	return c;
 }
 
 // The shared tail of every likelihood entry point: coefficients are in ctx->d_coef.
 int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_logL, cudaStream_t st, cudaStream_t st_heavy = nullptr,
                 cudaEvent_t ev_a = nullptr, cudaEvent_t ev_b = nullptr)
 {
-	int chunks, bins_per_cta;
-	choose_chunks(W, ctx->L, chunks, bins_per_cta);
-	if (grow(ctx, ctx->d_partial, ctx->cap_partial, (size_t)2 * W * chunks)) return GWAT_B200_ERR_CUDA;
+	const LikeCut cut = choose_cut(W, ctx->L);
+	const int entries = cut.units_total * kUnitWarps;  // partial sums per walker
+	if (grow(ctx, ctx->d_partial, ctx->cap_partial, (size_t)2 * W * entries)) return GWAT_B200_ERR_CUDA;
 	cudaStream_t sl = st;
 	if (st_heavy && st_heavy != st && ev_a && ev_b) {
 		CUDA_TRY(ctx, cudaEventRecord(ev_a, st));
@@ -677,14 +603,14 @@ int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_log
 	}
 	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), sl));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, sl));
-	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, chunks, bins_per_cta, sl)) return fail(
+	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, cut, sl)) return fail(
 	                               ctx, GWAT_B200_ERR_STATE, "unsupported detector count"));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, sl));
 	if (sl != st) {
 		CUDA_TRY(ctx, cudaEventRecord(ev_b, sl));
 		CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_b, 0));
 	}
-	k_finish<<<(W + 127) / 128, 128, 0, st>>>(ctx->d_partial, W, chunks, ctx->pref_like, d_logL, ctx->d_active);
+	k_finish<<<(W + 3) / 4, 128, 0, st>>>(ctx->d_partial, W, entries, ctx->pref_like, d_logL, ctx->d_active);
 	ctx->launches += 2;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -839,7 +765,6 @@ int gwat_b200_ctx_create(gwat_b200_ctx **out, int device)
 	if (device < 0 || device >= n) return fail(nullptr, GWAT_B200_ERR_ARG, "device ordinal out of range");
 	gwat_b200_ctx *c = new gwat_b200_ctx;
 	c->device = device;
-	if (const char *e = std::getenv("GWAT_B200_TMA")) c->use_tma = (e[0] == '1');
 	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&c->d_active, sizeof(unsigned long long))) != cudaSuccess) {

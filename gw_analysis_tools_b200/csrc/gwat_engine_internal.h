@@ -31,10 +31,6 @@ struct gwat_b200_ctx {
 	int D = 0, L = 0;
 	int ld = 0;  // L padded to a whole number of 256-bin tiles (bulk-copy granularity of the likelihood kernel)
 	bool have_data = false, gaussleg = false, log10F = false, uniform = false;
-	// Bulk-copy (TMA) staging of the grid tiles is implemented (k_loglike_tma) but OFF by default: the tables are 2 MB and
-	// L2-resident, the kernel is FP64-bound, and the staged variant measured 10 % slower (sync + shared-memory footprint);
-	// GWAT_B200_TMA=1 selects it for A/B measurements.
-	bool use_tma = false;
 	double df = 0;
 	gwat::Network net{};
 	double pref_like = 0, pref_fisher = 0;

@@ -150,9 +150,9 @@ GWAT_HD void like_state_init(const WalkerCoef &w, double f0, double step, double
 // advances the recurrences.  wq/dre/dim are the D per-detector values of this bin.
 // `tab` supplies the per-detector table values of this bin lazily -- tab.wq(d), tab.dre(d), tab.dim(d) -- so they are
 // fetched where they are consumed instead of being held in registers across the carrier evaluation.
-template <class Fam, int D, class Tab>
+template <class Fam, int D, class Tab, class Cnt>
 GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, double f, double sf_hi, double sf_lo, double logf,
-                      const Tab &tab, double &acc, double &nact)
+                      const Tab &tab, double &acc, Cnt &nact)
 {
 	double amp, arg;
 	cplx P, Q;
@@ -166,7 +166,7 @@ GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, doubl
 		}
 		return;
 	}
-	nact += 1.0;
+	nact += 1;  // Cnt is an integer type in the kernel: the count stays off the FP64 pipe
 	double sn, cs;
 	fast_sincos(arg, &sn, &cs);
 	double hh = 0.0, Sre = 0.0, Sim = 0.0;
@@ -213,18 +213,102 @@ GWAT_HD double walker_fmax(const WalkerCoef &w)
 	return (Fam::nrt && w.d.nrt_fmerger12 < w.d.fcut) ? w.d.nrt_fmerger12 : w.d.fcut;
 }
 
-// One thread's run of bins read straight from global memory: first, first+stride, ... < end.
-template <class Fam, int D>
-GWAT_HD void loglike_run(const WalkerCoef &w, const LikeGrid &g, int first, int end, int stride, double &acc, double &nact)
+// ---- the cut of the bin axis --------------------------------------------------------------------------------------------
+// A walker's sum over bins is formed in a fixed tree that depends on the grid alone:
+//   unit  = kUnitThreads * unit_steps consecutive bins; inside a unit thread t owns bins t, t + 256, ...; the recurrences are
+//           re-seeded at every unit, so a unit's value does not depend on what was evaluated before it;
+//   per unit one partial sum per warp (shuffle tree), all partials of a walker are added in a fixed order afterwards.
+// How many consecutive units one CTA evaluates is a scheduling decision (long runs for big ensembles, short ones when few
+// walkers must still fill the GPU) and does NOT change a single bit of the result: a walker's logL is the same in any batch.
+constexpr int kUnitThreads = 256;
+constexpr int kUnitWarps = kUnitThreads / 32;
+#ifndef GWAT_UNIT_STEPS
+#define GWAT_UNIT_STEPS 32  // bins per thread and unit on grids of up to 2^20 bins (measured: 16 costs 2 % on cfg2/cfg4, 64 gains 0.5 %)
+#endif
+constexpr int kMaxUnitsPerCta = 64 / GWAT_UNIT_STEPS;
+
+// Per-CTA seeds of the recurrences (uniform grids).  Seeding every thread's state with its own sincos/exp calls costs
+// 2 D + 2 transcendental evaluations per thread and unit -- as much as a whole bin.  Instead the CTA tabulates
+// e^{-i t_d df k} for k = 0..15 and k = 16 j, j = 0..15, once (one evaluation per thread, in parallel) and every thread forms
+// its seed as a product of three table entries:
+//   e^{-i t_d f[unit_begin + t]} = e^{-i t_d f[unit_begin]} * e16[t >> 4] * e1[t & 15]      (3 roundings, < 1e-15)
+// and likewise for the ringdown-amplitude decay.  f[i] = f[unit_begin] + (i - unit_begin) df holds to an ulp of f on a
+// uniform grid; t_d <= 0.14 s rad/Hz, so the phase differs from the directly evaluated one by < 1e-13 rad.
+template <int D>
+struct CtaSeeds {
+	cplx e1[D][16], e16[D][16], step[D], base[kMaxUnitsPerCta][D];
+	double r1[16], r16[16], rstep, rbase[kMaxUnitsPerCta];  // rbase == 0: decay outside double range in that unit -> per-bin exp
+};
+constexpr int kSeedSlots = 33 + kMaxUnitsPerCta;  // 16 + 16 + step + unit bases per detector, and once more for the decay
+
+// Slot j of the CTA's seed table (0 <= j < kSeedSlots * (D + 1)).  The CTA covers units [0, n_units) of unit_bins bins
+// starting at bin `begin`; `stride` is the thread stride of the runs.
+template <int D>
+GWAT_HD void cta_seed_slot(const WalkerCoef &w, const LikeGrid &g, int begin, int unit_bins, int n_units, int stride, int j,
+                           CtaSeeds<D> &sd)
 {
-	if (first >= end) return;
+	const int d = j / kSeedSlots, k = j % kSeedSlots;
+	const int u = k - 33;
+	if (u >= n_units) return;
+	const int ub = begin + (u > 0 ? u : 0) * unit_bins;                  // first bin of unit u
+	const int ue = min_int(g.L, ub + unit_bins) - 1;                     // its last bin
+	const double x = k < 16 ? g.df * k : (k < 32 ? g.df * (16 * (k - 16)) : (k == 32 ? g.df * stride : g.f[ub]));
+	if (d < D) {
+		double sn, cs;
+		fast_sincos(mul_rn(w.det[d].tshift, x), &sn, &cs);
+		const cplx v{cs, -sn};
+		if (k < 16) sd.e1[d][k] = v;
+		else if (k < 32) sd.e16[d][k - 16] = v;
+		else if (k == 32) sd.step[d] = v;
+		else sd.base[u][d] = v;
+		return;
+	}
+	// ringdown decay exp(-mr_rate (f - fRD)); kept within double range, else evaluated per bin
+	if (k < 33) {
+		const double v = exp(-w.d.mr_rate * x);
+		if (k < 16) sd.r1[k] = v;
+		else if (k < 32) sd.r16[k - 16] = v;
+		else sd.rstep = v;
+		return;
+	}
+	const double a0 = -w.d.mr_rate * (x - w.d.fRD), a1 = -w.d.mr_rate * (g.f[ue] - w.d.fRD);
+	sd.rbase[u] = (fabs(a0) < 600.0 && fabs(a1) < 600.0) ? exp(a0) : 0.0;
+}
+
+GWAT_HD cplx cmul(const cplx &a, const cplx &b) { return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+// Seed of the thread whose first bin in unit u is unit_begin + t (t < 256).
+template <int D>
+GWAT_HD void like_state_from_seeds(const CtaSeeds<D> &sd, int u, int t, LikeState<D> &st)
+{
+	const int k1 = t & 15, k16 = t >> 4;
+#pragma unroll
+	for (int d = 0; d < D; d++) {
+		st.z[d] = cmul(cmul(sd.base[u][d], sd.e16[d][k16]), sd.e1[d][k1]);
+		st.E[d] = sd.step[d];
+	}
+	st.decay = (sd.rbase[u] * sd.r16[k16]) * sd.r1[k1];
+	st.decay_step = sd.rbase[u] != 0.0 ? sd.rstep : 1.0;
+}
+
+// One thread's share of one unit, read straight from global memory (L2-resident tables): bins first, first + stride, ...
+// < end.  `seeds` (uniform grids) is the CTA's seed table, `u` the unit's index in it and `t` the thread's offset; without
+// a table the thread seeds its own state.  Returns false once the thread has passed the walker's cutoff on an ascending
+// (uniform) grid: everything after that is exactly zero for it.
+template <class Fam, int D, class Cnt>
+GWAT_HD bool loglike_unit(const WalkerCoef &w, const LikeGrid &g, int first, int end, int stride, double fmax, double &acc,
+                          Cnt &nact, const CtaSeeds<D> *seeds = nullptr, int u = 0, int t = 0)
+{
+	if (first >= end) return true;
 	const bool uniform = g.uniform != 0;
-	const double fmax = walker_fmax<Fam>(w);
 	LikeState<D> st;
 	if (uniform) {
-		const double f0 = g.f[first];
-		if (f0 > fmax) return;  // ascending grid: nothing below the cutoff is left for this thread
-		like_state_init<D>(w, f0, g.df * stride, g.f[min_int(end - 1, g.L - 1)], st);
+		if (seeds) like_state_from_seeds<D>(*seeds, u, t, st);  // (no table read: the cutoff is tested on the first bin below)
+		else {
+			const double f0 = g.f[first];
+			if (f0 > fmax) return false;
+			like_state_init<D>(w, f0, g.df * stride, g.f[min_int(end - 1, g.L - 1)], st);
+		}
 	}
 	for (int i = first; i < end; i += stride) {
 #if defined(__CUDA_ARCH__)
@@ -233,10 +317,19 @@ GWAT_HD void loglike_run(const WalkerCoef &w, const LikeGrid &g, int first, int 
 		asm volatile("" ::: "memory");
 #endif
 		const double f = g.f[i];
-		if (uniform && f > fmax) break;  // ascending grid: the rest is zero too
+		if (uniform && f > fmax) return false;
 		const GlobalTab tab{g.wq + i, g.dre + i, g.dim + i, (size_t)g.ld};
 		like_bin<Fam, D>(w, uniform, st, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], tab, acc, nact);
 	}
+	return true;
+}
+
+// Bins per unit for a grid of L bins: 16 bins per thread, doubled (up to 64) while that would make more than 128 units.
+GWAT_HD int unit_bins_for(int L)
+{
+	int steps = GWAT_UNIT_STEPS;
+	while (steps < 64 && (long long)L > 128LL * steps * kUnitThreads) steps *= 2;
+	return steps * kUnitThreads;
 }
 
 }  // namespace gwat

@@ -40,12 +40,12 @@ GWAT_HD void binary_love(double tidal_s, double mass1, double mass2, double &tid
 	const double b[3][2] = {{-14.40, 14.45}, {31.36, -32.25}, {-22.44, 20.35}};
 	const double cc[3][2] = {{-15.25, 15.37}, {37.33, -43.20}, {-29.93, 35.18}};
 	const double q = mass2 / mass1;
-	const double Q = pow(q, 10. / (3. - n_fit));
+	const double Q = sm::pow(q, 10. / (3. - n_fit));
 	const double F = (1. - Q) / (1. + Q);
 	double num = 1, den = 1;
 	const double qp[2] = {q, q * q};
 	double lp[3];
-	lp[0] = pow(tidal_s, -1. / 5.);
+	lp[0] = sm::pow(tidal_s, -1. / 5.);
 	lp[1] = lp[0] * lp[0];
 	lp[2] = lp[0] * lp[1];
 	for (int i = 0; i < 3; i++)
@@ -61,13 +61,13 @@ GWAT_HD void binary_love(double tidal_s, double mass1, double mass2, double &tid
 // spin-induced quadrupole and octupole moments of a neutron star from its tidal deformability (arXiv:1608.02582 eq. 15)
 GWAT_HD double ns_quad_moment(double lambda)
 {
-	const double l = log(lambda);
-	return exp(0.1940 + 0.09163 * l + 0.04812 * pow(l, 2.) + -0.004283 * pow(l, 3.) + 0.00012450 * pow(l, 4.));
+	const double l = sm::log(lambda);
+	return sm::exp(0.1940 + 0.09163 * l + 0.04812 * pow(l, 2.) + -0.004283 * pow(l, 3.) + 0.00012450 * pow(l, 4.));
 }
 GWAT_HD double ns_oct_moment(double quad)
 {
-	const double l = log(quad);
-	return exp(0.003131 + 2.071 * l + -0.7152 * pow(l, 2.) + 0.2458 * pow(l, 3.) + -0.03309 * pow(l, 4.));
+	const double l = sm::log(quad);
+	return sm::exp(0.003131 + 2.071 * l + -0.7152 * pow(l, 2.) + 0.2458 * pow(l, 3.) + -0.03309 * pow(l, 4.));
 }
 
 // prep_source_parameters' NRT block: tidal deformabilities -> mass-weighted combinations.

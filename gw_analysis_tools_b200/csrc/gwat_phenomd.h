@@ -251,7 +251,7 @@ GWAT_HD double gimr_negative_pn_terms(const DCoef &c, double f, double acc)
 // Extra inspiral-phase terms of the modified families, accumulated onto `ph` in the reference's order.
 // (M f)^(1/6) to a few ulp, for setup-time evaluations where the sixth root only feeds amplitudes or the (M f)^(3/4) term of
 // the merger-ringdown phase (never the leading TaylorF2 term).
-GWAT_HD double sixth_root_approx(double M, double f) { return sqrt(cbrt(M * f)); }
+GWAT_HD double sixth_root_approx(double M, double f) { return sqrt(sm::cbrt(M * f)); }
 
 template <class Fam>
 GWAT_HD double phase_ins_extra(const DCoef &c, double f, double mf_third, double ph)
@@ -386,8 +386,8 @@ struct InsDerivIn {
 GWAT_HD double dphase_ins_df(const InsDerivIn &in, double f)
 {
 	const double x = GWAT_PI * in.M * f;
-	const double u = cbrt(x);
-	const double logx = log(x);
+	const double u = sm::cbrt(x);
+	const double logx = sm::log(x);
 	double c[8];
 	for (int k = 0; k < 8; k++) c[k] = in.c[k];
 	c[5] = in.c[8] + logx * in.c[9];
@@ -405,7 +405,7 @@ GWAT_HD double dphase_ins_df(const InsDerivIn &in, double f)
 	const double K = 3. / (128. * in.eta);
 	const double xm53 = 1. / u5;
 	const double tf2 = K * xm53 * (dP - (5. / 3.) * P) / f;
-	const double Mf13 = cbrt(in.M * f);
+	const double Mf13 = sm::cbrt(in.M * f);
 	const double sig = in.sigma[1] * in.M + in.M * Mf13 * (in.sigma[2] + Mf13 * (in.sigma[3] + Mf13 * in.sigma[4]));
 	return tf2 + sig / in.eta;
 }
@@ -434,7 +434,7 @@ GWAT_HD double ppe_dphase_terms(const SrcQ &s, double f)
 	double acc = 0;
 	for (int i = 0; i < s.Nmod; i++) {
 		const double b3 = s.bppe[i] / 3.;
-		acc += b3 * pow(f, b3 - 1.) * pow(s.chirpmass * GWAT_PI, b3) * s.betappe[i];
+		acc += b3 * sm::pow(f, b3 - 1.) * sm::pow(s.chirpmass * GWAT_PI, b3) * s.betappe[i];
 	}
 	return acc;
 }
@@ -445,13 +445,13 @@ GWAT_HD double dphase_ins_extra(const SrcQ &s, double f)
 	if (Fam::ppe != PPE_NONE) acc += ppe_dphase_terms(s, f);
 	if (Fam::gimr && s.Nmod_phi != 0) {
 		// src/gIMRPhenomD.cpp:168-185
-		const double pimcube = pow(GWAT_PI * s.M, 1. / 3.);
+		const double pimcube = sm::pow(GWAT_PI * s.M, 1. / 3.);
 		for (int i = -4; i < 0; i++) {
 			const int id = find_id(i, s.phii, s.Nmod_phi);
 			if (id == -1) continue;
 			double prod = 1;
 			for (int k = 0; k < 5 - i; k++) prod *= pimcube;
-			acc += 3. / (128. * s.eta) * s.delta_phi[id] * (1. / prod) * (i - 5.) / 3. * pow(f, ((i - 5.) / 3. - 1));
+			acc += 3. / (128. * s.eta) * s.delta_phi[id] * (1. / prod) * (i - 5.) / 3. * sm::pow(f, ((i - 5.) / 3. - 1));
 		}
 	}
 	return acc;
@@ -469,7 +469,7 @@ GWAT_HD void setup_family_extras(const SrcQ &s, DCoef &c)
 	c.n_gimr_neg = 0;
 	if (Fam::ppe != PPE_NONE) {
 		c.Nmod = s.Nmod;
-		c.ppe_scale = cbrt(GWAT_PI * s.chirpmass / s.M);
+		c.ppe_scale = sm::cbrt(GWAT_PI * s.chirpmass / s.M);
 		for (int i = 0; i < s.Nmod && i < GWAT_B200_MAX_MOD; i++) {
 			c.betappe[i] = s.betappe[i];
 			c.bppe[i] = s.bppe[i];

@@ -37,7 +37,7 @@ struct CosSin {
 GWAT_HD CosSin cos_sin(double angle)
 {
 	CosSin r;
-	sincos(angle, &r.s, &r.c);
+	sm::sincos(angle, &r.s, &r.c);
 	return r;
 }
 GWAT_HD void rot_z(const CosSin &a, Vec3 &v)
@@ -85,16 +85,16 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 
 	double J0x, J0y;
 	if (reduced) {
-		J0x = m1_2 * s.chip * cos(s.phip);
-		J0y = m1_2 * s.chip * sin(s.phip);
+		J0x = m1_2 * s.chip * sm::cos(s.phip);
+		J0y = m1_2 * s.chip * sm::sin(s.phip);
 	} else {
 		J0x = m1_2 * s.spin1x + m2_2 * s.spin2x;
 		J0y = m1_2 * s.spin1y + m2_2 * s.spin2y;
 	}
 	const double J0z = L0 + m1_2 * s.spin1z + m2_2 * s.spin2z;
 	const double J0 = sqrt(J0x * J0x + J0y * J0y + J0z * J0z);
-	const double thetaJ = acos(J0z / J0);
-	const double phiJ = atan2(J0y, J0x);
+	const double thetaJ = sm::acos(J0z / J0);
+	const double phiJ = sm::atan2(J0y, J0x);
 	s.phi_aligned = -phiJ;
 
 	const double incl = s.incl_angle, phiRef = s.phiRef;
@@ -104,21 +104,21 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 	Vec3 t = N;
 	rot_z(rJz, t);
 	rot_y(rJy, t);
-	const double kappa = -atan2(t.y, t.x);
+	const double kappa = -sm::atan2(t.y, t.x);
 	const CosSin rK = cos_sin(kappa);
 
 	t = Vec3{0., 0., 1.};
 	rot_z(rJz, t);
 	rot_y(rJy, t);
 	rot_z(rK, t);
-	s.alpha0 = atan2(t.y, t.x);
+	s.alpha0 = sm::atan2(t.y, t.x);
 
 	t = N;
 	rot_z(rJz, t);
 	rot_y(rJy, t);
 	rot_z(rK, t);
 	const double Nx_Jf = t.x, Nz_Jf = t.z;
-	s.thetaJN = acos(Nz_Jf);
+	s.thetaJN = sm::acos(Nz_Jf);
 
 	// polarisation-frame mismatch angle zeta between the (P,Q,N) triad of PhenomP and the LAL wave frame
 	t = Vec3{-ci.c * cp.s, -ci.c * cp.c, ci.s};
@@ -127,7 +127,7 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 	rot_z(rK, t);
 	const double XdotP = t.x * 0. + t.y * -1. + t.z * 0.;
 	const double XdotQ = t.x * Nz_Jf + t.y * 0. + t.z * -Nx_Jf;
-	s.zeta_polariz = atan2(XdotQ, XdotP);
+	s.zeta_polariz = sm::atan2(XdotQ, XdotP);
 }
 
 // Coefficients of the PN expansions of the precession angles alpha(omega), epsilon(omega) (LAL's
@@ -190,7 +190,7 @@ GWAT_HD void euler_angles(const double *a, const double *e, double omega_cbrt, d
 // -2Y_{2m}(theta, 0), m = -2..2: real for zero azimuth
 GWAT_HD void spin_weighted_y2(double theta, double *Y)
 {
-	const double ct = cos(theta), st = sin(theta);
+	const double ct = sm::cos(theta), st = sm::sin(theta);
 	Y[0] = sqrt(5.0 / (64.0 * GWAT_PI)) * (1.0 - ct) * (1.0 - ct);
 	Y[1] = sqrt(5.0 / (16.0 * GWAT_PI)) * st * (1.0 - ct);
 	Y[2] = sqrt(15.0 / (32.0 * GWAT_PI)) * st * st;
@@ -247,7 +247,7 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 	double Y[5];
 	spin_weighted_y2(s.thetaJN, Y);
 	for (int i = 0; i < 5; i++) p.Y[i] = Y[i];
-	p.A0 = s.A0 * pow(s.M, 7. / 6.) / (2. * sqrt(5. / (64. * GWAT_PI)));
+	p.A0 = s.A0 * sm::pow(s.M, 7. / 6.) / (2. * sqrt(5. / (64. * GWAT_PI)));
 	p.SP = s.SP;
 	p.SL = s.SL;
 	p.eta = s.eta;
@@ -257,14 +257,14 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 	euler_angle_coeffs(q, s.chil, s.chip, p.acoef, p.ecoef);
 	// offsets of the angles at f_ref; the reference forms (M f_ref)^(1/3) with pow(x, 1./3.)
 	const PiPowers pi = pi_powers();
-	const double mf_third_ref = pow(s.M * s.f_ref, 1. / 3.);
+	const double mf_third_ref = sm::pow(s.M * s.f_ref, 1. / 3.);
 	const double oc_ref = mf_third_ref * pi.third;
 	double alpha_off, eps_off;
-	euler_angles(p.acoef, p.ecoef, oc_ref, log((oc_ref * oc_ref) * oc_ref), alpha_off, eps_off);
+	euler_angles(p.acoef, p.ecoef, oc_ref, sm::log((oc_ref * oc_ref) * oc_ref), alpha_off, eps_off);
 	p.alpha_const = s.alpha0 - alpha_off;
 	p.epsilon_offset = eps_off;
-	p.c2z = cos(2. * s.zeta_polariz);
-	p.s2z = sin(2. * s.zeta_polariz);
+	p.c2z = sm::cos(2. * s.zeta_polariz);
+	p.s2z = sm::sin(2. * s.zeta_polariz);
 	p.phic = 2 * s.phi_aligned;
 	p.tc = 2 * GWAT_PI * s.tc;
 	p.f_ref = s.f_ref;
@@ -286,7 +286,7 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 				// the samples straddle fRD > f2p: merger-ringdown phase, where the sixth root only enters through (Mf)^(3/4);
 				// below f1p (never for physical parameters) the exact root is used
 				const double root = f < c.f1p ? sixth_root_direct(c.M, f) : sixth_root_approx(c.M, f);
-				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, log(f), a_unused, ph);
+				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, sm::log(f), a_unused, ph);
 				xs[j] = f;
 				ys[j] = -ph;
 			}
@@ -398,7 +398,7 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 		w.cfac = 0;
 		w.pfac = 0;
 	} else {
-		const double ci = cos(s.incl_angle);
+		const double ci = sm::cos(s.incl_angle);
 		w.cfac = ci;
 		w.pfac = .5 * (1. + ci * ci);
 	}

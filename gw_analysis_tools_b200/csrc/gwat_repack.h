@@ -64,12 +64,12 @@ GWAT_HD void source_defaults(gwat_b200_source &s)
 // calculate_mass1 / calculate_mass2 (src/util.cpp:1516-1540)
 GWAT_HD double mass1_of(double chirpmass, double eta)
 {
-	const double etapow = pow(eta, 3. / 5);
+	const double etapow = sm::pow(eta, 3. / 5);
 	return 1. / 2 * (chirpmass / etapow + sqrt(1. - 4 * eta) * chirpmass / etapow);
 }
 GWAT_HD double mass2_of(double chirpmass, double eta)
 {
-	const double etapow = pow(eta, 3. / 5);
+	const double etapow = sm::pow(eta, 3. / 5);
 	return 1. / 2 * (chirpmass / etapow - sqrt(1. - 4 * eta) * chirpmass / etapow);
 }
 
@@ -78,7 +78,7 @@ GWAT_HD double clamped_acos(double x)
 	// "Fishers don't necessarily respect the bounds of acos" (src/fisher.cpp:2190-2213)
 	if (x > 1) return 0;
 	if (x < -1) return GWAT_PI;
-	return acos(x);
+	return sm::acos(x);
 }
 
 // The modification tails shared by both parameterisations (src/fisher.cpp:2399-2505)
@@ -87,10 +87,10 @@ GWAT_HD void repack_tails(const double *v, const RepackPlan &plan, gwat_b200_sou
 	const int dim = plan.dimension;
 	if (plan.nrt && !plan.pv2) {
 		if (s.tidal_love) {
-			s.tidal_s = exp(v[11]);
+			s.tidal_s = sm::exp(v[11]);
 		} else {
-			s.tidal1 = exp(v[11]);
-			s.tidal2 = exp(v[12]);
+			s.tidal1 = sm::exp(v[11]);
+			s.tidal2 = sm::exp(v[12]);
 		}
 	}
 	if (plan.ppe) {
@@ -153,24 +153,24 @@ GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, dou
 		v[base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
 	}
 	// repack_parameters, "MCMC_" branch, sky_average = false
-	s.mass1 = mass1_of(exp(v[7]), v[8]);
-	s.mass2 = mass2_of(exp(v[7]), v[8]);
-	s.Luminosity_Distance = exp(v[6]);
+	s.mass1 = mass1_of(sm::exp(v[7]), v[8]);
+	s.mass2 = mass2_of(sm::exp(v[7]), v[8]);
+	s.Luminosity_Distance = sm::exp(v[6]);
 	s.RA = v[0];
-	s.DEC = asin(v[1]);
+	s.DEC = sm::asin(v[1]);
 	s.psi = v[2];
-	s.incl_angle = acos(v[3]);
+	s.incl_angle = sm::acos(v[3]);
 	s.phiRef = v[4];
 	s.tc = v[5];
 	if (plan.pv2) {
 		const double th1 = clamped_acos(v[11]), th2 = clamped_acos(v[12]);
 		// transform_sph_cart (src/util.cpp:1909-1914)
-		s.spin1[0] = v[9] * sin(th1) * cos(v[13]);
-		s.spin1[1] = v[9] * sin(th1) * sin(v[13]);
-		s.spin1[2] = v[9] * cos(th1);
-		s.spin2[0] = v[10] * sin(th2) * cos(v[14]);
-		s.spin2[1] = v[10] * sin(th2) * sin(v[14]);
-		s.spin2[2] = v[10] * cos(th2);
+		s.spin1[0] = v[9] * sm::sin(th1) * sm::cos(v[13]);
+		s.spin1[1] = v[9] * sm::sin(th1) * sm::sin(v[13]);
+		s.spin1[2] = v[9] * sm::cos(th1);
+		s.spin2[0] = v[10] * sm::sin(th2) * sm::cos(v[14]);
+		s.spin2[1] = v[10] * sm::sin(th2) * sm::sin(v[14]);
+		s.spin2[2] = v[10] * sm::cos(th2);
 	} else {
 		s.spin1[2] = v[9];
 		s.spin2[2] = v[10];
@@ -185,12 +185,12 @@ GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, dou
 GWAT_HD void cart_to_sph(const double *c, double *sph)
 {
 	sph[0] = sqrt(c[0] * c[0] + c[2] * c[2] + c[1] * c[1]);
-	sph[1] = acos(c[2] / sph[0]);
-	sph[2] = atan2(c[1], c[0]);
+	sph[1] = sm::acos(c[2] / sph[0]);
+	sph[2] = sm::atan2(c[1], c[0]);
 	if (sph[2] < 0) sph[2] += 2 * GWAT_PI;
 }
 
-GWAT_HD double chirpmass_from(double m1, double m2) { return pow(m1 * m2, 3. / 5) / pow(m1 + m2, 1. / 5); }
+GWAT_HD double chirpmass_from(double m1, double m2) { return sm::pow(m1 * m2, 3. / 5) / sm::pow(m1 + m2, 1. / 5); }
 GWAT_HD double eta_from(double m1, double m2) { return (m1 * m2) / ((m1 + m2) * (m1 + m2)); }
 
 // unpack_parameters, non-sky-averaged branches (src/fisher.cpp:1843-1966, 2038-2160).  `logf[i]` != 0 marks the
@@ -205,10 +205,10 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 	v[5] = in.tc;
 	v[8] = eta_from(in.mass1, in.mass2);
 	if (plan.mcmc) {
-		v[1] = sin(in.DEC);
-		v[3] = cos(in.incl_angle);
-		v[6] = log(in.Luminosity_Distance);
-		v[7] = log(chirpmass_from(in.mass1, in.mass2));
+		v[1] = sm::sin(in.DEC);
+		v[3] = sm::cos(in.incl_angle);
+		v[6] = sm::log(in.Luminosity_Distance);
+		v[7] = sm::log(chirpmass_from(in.mass1, in.mass2));
 	} else {
 		logfac[6] = 1;
 		logfac[7] = 1;
@@ -224,8 +224,8 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 			cart_to_sph(in.spin2, s2);
 			v[9] = s1[0];
 			v[10] = s2[0];
-			v[11] = cos(s1[1]);
-			v[12] = cos(s2[1]);
+			v[11] = sm::cos(s1[1]);
+			v[12] = sm::cos(s2[1]);
 			v[13] = s1[2];
 			v[14] = s2[2];
 		} else {
@@ -241,11 +241,11 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 	if (plan.nrt && !plan.pv2) {
 		if (in.tidal_love) {
 			logfac[11] = plan.mcmc ? 0 : 1;
-			v[11] = log(in.tidal_s);
+			v[11] = sm::log(in.tidal_s);
 		} else {
 			logfac[11] = logfac[12] = plan.mcmc ? 0 : 1;
-			v[11] = log(in.tidal1);
-			v[12] = log(in.tidal2);
+			v[11] = sm::log(in.tidal1);
+			v[12] = sm::log(in.tidal2);
 		}
 	}
 	if (plan.ppe) {
@@ -300,11 +300,11 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 	s.phiRef = v[4];
 	s.tc = v[5];
 	if (plan.mcmc) {
-		s.mass1 = mass1_of(exp(v[7]), v[8]);
-		s.mass2 = mass2_of(exp(v[7]), v[8]);
-		s.Luminosity_Distance = exp(v[6]);
-		s.DEC = asin(v[1]);
-		s.incl_angle = acos(v[3]);
+		s.mass1 = mass1_of(sm::exp(v[7]), v[8]);
+		s.mass2 = mass2_of(sm::exp(v[7]), v[8]);
+		s.Luminosity_Distance = sm::exp(v[6]);
+		s.DEC = sm::asin(v[1]);
+		s.incl_angle = sm::acos(v[3]);
 	} else {
 		s.mass1 = mass1_of(v[7], v[8]);
 		s.mass2 = mass2_of(v[7], v[8]);
@@ -315,12 +315,12 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 	if (plan.pv2) {
 		if (plan.mcmc) {
 			const double th1 = clamped_acos(v[11]), th2 = clamped_acos(v[12]);
-			s.spin1[0] = v[9] * sin(th1) * cos(v[13]);
-			s.spin1[1] = v[9] * sin(th1) * sin(v[13]);
-			s.spin1[2] = v[9] * cos(th1);
-			s.spin2[0] = v[10] * sin(th2) * cos(v[14]);
-			s.spin2[1] = v[10] * sin(th2) * sin(v[14]);
-			s.spin2[2] = v[10] * cos(th2);
+			s.spin1[0] = v[9] * sm::sin(th1) * sm::cos(v[13]);
+			s.spin1[1] = v[9] * sm::sin(th1) * sm::sin(v[13]);
+			s.spin1[2] = v[9] * sm::cos(th1);
+			s.spin2[0] = v[10] * sm::sin(th2) * sm::cos(v[14]);
+			s.spin2[1] = v[10] * sm::sin(th2) * sm::sin(v[14]);
+			s.spin2[2] = v[10] * sm::cos(th2);
 		} else {
 			s.spin1[2] = v[9];
 			s.spin2[2] = v[10];

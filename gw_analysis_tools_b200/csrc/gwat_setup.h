@@ -15,13 +15,13 @@
 namespace gwat {
 
 // ---- populate_source_parameters --------------------------------------------------------------------------------------
-GWAT_HD double chirpmass_of(double m1, double m2) { return pow(m1 * m2, 3. / 5) / pow(m1 + m2, 1. / 5); }
+GWAT_HD double chirpmass_of(double m1, double m2) { return sm::pow(m1 * m2, 3. / 5) / sm::pow(m1 + m2, 1. / 5); }
 GWAT_HD double eta_of(double m1, double m2) { return (m1 * m2) / ((m1 + m2) * (m1 + m2)); }
 // A0_from_DL (src/util.cpp:1271-1279)
 GWAT_HD double a0_from_dl(double chirpmass, double DL, bool sky_average)
 {
 	const double pref = sky_average ? sqrt(GWAT_PI / 30) : sqrt(GWAT_PI * 40. / 192.);
-	return pref * chirpmass * chirpmass / DL * pow(GWAT_PI * chirpmass, -7. / 6);
+	return pref * chirpmass * chirpmass / DL * sm::pow(GWAT_PI * chirpmass, -7. / 6);
 }
 
 GWAT_HD void populate_source(const gwat_b200_source &in, SrcQ &s)
@@ -74,9 +74,9 @@ GWAT_HD SkyTrig sky_trig(double ra, double dec, double psi, double gmst)
 {
 	SkyTrig t;
 	const double gha = gmst - ra;
-	sincos(gha, &t.singha, &t.cosgha);
-	sincos(dec, &t.sindec, &t.cosdec);
-	sincos(psi, &t.sinpsi, &t.cospsi);
+	sm::sincos(gha, &t.singha, &t.cosgha);
+	sm::sincos(dec, &t.sindec, &t.cosdec);
+	sm::sincos(psi, &t.sinpsi, &t.cospsi);
 	return t;
 }
 
@@ -182,8 +182,8 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		c.sM_hi = r.hi;
 		c.sM_lo = r.lo;
 	}
-	c.logM = log(M);
-	c.logpiM = log(GWAT_PI * M);
+	c.logM = sm::log(M);
+	c.logpiM = sm::log(GWAT_PI * M);
 	c.pichirp = GWAT_PI * s.chirpmass;
 	c.fRD = s.fRD;
 	c.fdamp = s.fdamp;
@@ -191,7 +191,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.inv_eta = 1. / eta;
 
 	// ---- amplitude -----------------------------------------------------------------------------------------------------
-	c.A0 = s.A0 * pow(M, 7. / 6.);
+	c.A0 = s.A0 * sm::pow(M, 7. / 6.);
 	c.ains[0] = camp[0];
 	c.ains[1] = camp[1] * pi.third;
 	c.ains[2] = camp[2] * pi.two3;
@@ -215,13 +215,13 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		// d/df of the inspiral amplitude at f1
 		double dA1 = 0;
 		{
-			const double u = cbrt(GWAT_PI * M * s.f1);
+			const double u = sm::cbrt(GWAT_PI * M * s.f1);
 			double uk = 1;
 			for (int k = 0; k < 7; k++) {
 				dA1 += camp[k] * uk * (k / 3.);
 				uk *= u;
 			}
-			const double m13 = cbrt(M * s.f1);
+			const double m13 = sm::cbrt(M * s.f1);
 			const double m73 = m13 * m13 * m13 * m13 * m13 * m13 * m13;
 			dA1 += lam.rho[0] * m73 * (7. / 3.) + lam.rho[1] * m73 * m13 * (8. / 3.) + lam.rho[2] * m73 * m13 * m13 * 3.;
 			dA1 /= s.f1;
@@ -231,7 +231,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		{
 			const double df = s.f3 - s.fRD;
 			const double den = df * df + c.mr_w2;
-			dA3 = -c.mr_num * exp(-c.mr_rate * df) * (c.mr_rate * den + 2 * df) / (den * den);
+			dA3 = -c.mr_num * sm::exp(-c.mr_rate * df) * (c.mr_rate * den + 2 * df) / (den * den);
 		}
 		const double x1 = M * s.f1, x3 = M * s.f3, x2 = M * ((s.f1 + s.f3) / 2.);
 		const double s1 = dA1 / M, s3 = dA3 / M;  // slopes with respect to x
@@ -289,7 +289,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	din.eta = eta;
 	lam.beta[0] = lam.beta[1] = lam.alpha[0] = lam.alpha[1] = 0;
 	const double f1p = s.f1_phase, f2p = s.f2_phase;
-	const double log_f1p = log(f1p), log_f2p = log(f2p);
+	const double log_f1p = sm::log(f1p), log_f2p = sm::log(f2p);
 	auto sync_int_mr = [&]() {
 		c.beta0 = lam.beta[0];
 		c.beta1 = lam.beta[1];
@@ -338,7 +338,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		if (s.shift_phase) {
 			f_ref = s.f_ref;
 			double a_unused, phi_shift;
-			phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f_ref, sixth_root_direct(M, f_ref), log(f_ref), a_unused,
+			phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f_ref, sixth_root_direct(M, f_ref), sm::log(f_ref), a_unused,
 			                                                         phi_shift);
 			phic = 2 * s.phiRef + phi_shift;
 		} else {

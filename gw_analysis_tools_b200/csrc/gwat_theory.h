@@ -63,7 +63,7 @@ GWAT_HD double dl_from_z_md(double Z, double alpha, const DzTable &t)
 	for (int i = 0; i < 3; i++) {
 		if (Z < t.md_boundaries_z[idx][i + 1]) {
 			double result = 0;
-			for (int j = 0; j < 17; j++) result += t.md_coeffs[idx][i][j] * pow(Z, -3.5 + j * 0.5);
+			for (int j = 0; j < 17; j++) result += t.md_coeffs[idx][i][j] * sm::pow(Z, -3.5 + j * 0.5);
 			return result;
 		}
 	}
@@ -82,8 +82,8 @@ GWAT_HD double dcs_phase_factor(const SrcQ &s, double m1, double m2)
 	if (s.NSflag1) s1 = 0;  // neutron stars carry no scalar charge
 	if (s.NSflag2) s2 = 0;
 	double g = 0;
-	g += (-5. / 8192.) / (pow(eta, 14. / 5.)) * pow((m1 * s2 - m2 * s1), 2.) / (m * m);
-	g += (15075. / 114688.) / (pow(eta, 14. / 5.)) * (m2 * m2 * chi1 * chi1 - 350. / 201. * m1 * m2 * chi1 * chi2 + m1 * m1 * chi2 * chi2) / (m * m);
+	g += (-5. / 8192.) / (sm::pow(eta, 14. / 5.)) * pow((m1 * s2 - m2 * s1), 2.) / (m * m);
+	g += (15075. / 114688.) / (sm::pow(eta, 14. / 5.)) * (m2 * m2 * chi1 * chi1 - 350. / 201. * m1 * m2 * chi1 * chi2 + m1 * m1 * chi2 * chi2) / (m * m);
 	return g;
 }
 
@@ -96,7 +96,7 @@ GWAT_HD double edgb_phase_factor(const SrcQ &s, double m1, double m2)
 	double s2 = fabs(chi2) < 1e-10 ? 0 : temp2 / (chi2 * chi2);
 	if (s.NSflag1) s1 = 0;
 	if (s.NSflag2) s2 = 0;
-	return (-5. / 7168.) * pow_int_seq((m1 * m1 * s2 - m2 * m2 * s1), 2) / (pow_int_seq(s.M, 4) * pow(s.eta, (18. / 5)));
+	return (-5. / 7168.) * pow_int_seq((m1 * m1 * s2 - m2 * m2 * s1), 2) / (pow_int_seq(s.M, 4) * sm::pow(s.eta, (18. / 5)));
 }
 
 // Theory ids (gwat_method.h parses the method string into one of these).  "EdGB_HO_<model>" without "_LO" is THEORY_EDGB: in
@@ -115,7 +115,7 @@ GWAT_HD bool theory_alpha_units(int theory) { return theory >= THEORY_DCS && the
 GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 {
 	if (theory == THEORY_NONE) return;
-	const double etapow = pow(s.eta, 3. / 5);
+	const double etapow = sm::pow(s.eta, 3. / 5);
 	const double root = sqrt(1. - 4 * s.eta);
 	const double m1 = 1. / 2 * (s.chirpmass / etapow + root * s.chirpmass / etapow);
 	const double m2 = 1. / 2 * (s.chirpmass / etapow - root * s.chirpmass / etapow);
@@ -136,7 +136,7 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 		break;
 	case THEORY_EDGB_HO_LO: {  // EdGB_HO_0PN_beta (:529-539)
 		const double alphaSq = 16. * GWAT_PI * in0;
-		beta[0] = -5. * alphaSq / pow_int_seq(unredshiftedM, 4) / 7168. / pow(eta, 18. / 5.) * (4 * eta - 1);
+		beta[0] = -5. * alphaSq / pow_int_seq(unredshiftedM, 4) / 7168. / sm::pow(eta, 18. / 5.) * (4 * eta - 1);
 		b[0] = -7;
 		break;
 	}
@@ -159,12 +159,12 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 		const double T_year = 31557600.;
 		const double m1dot = -2.8e-7 * pow_int_seq(GWAT_MSOL_SEC * (1 + Z) / s.mass1, 2) * in0 / pow_int_seq(ten_micrometer, 2) * GWAT_MSOL_SEC / T_year;
 		const double m2dot = -2.8e-7 * pow_int_seq(GWAT_MSOL_SEC * (1 + Z) / s.mass2, 2) * in0 / pow_int_seq(ten_micrometer, 2) * GWAT_MSOL_SEC / T_year;
-		beta[0] = (m1dot + m2dot) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (pow(eta, 2. / 5.) * (1 - 2 * eta)));
+		beta[0] = (m1dot + m2dot) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (sm::pow(eta, 2. / 5.) * (1 - 2 * eta)));
 		b[0] = -13;
 		break;
 	}
 	case THEORY_BHEVAP:  // BHEvaporation_beta (:682-691)
-		beta[0] = (in0) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (pow(eta, 2. / 5.) * (1 - 2 * eta)));
+		beta[0] = (in0) * (25. / 851968.) * ((3. - 26. * eta + 34. * eta * eta) / (sm::pow(eta, 2. / 5.) * (1 - 2 * eta)));
 		b[0] = -13;
 		break;
 	case THEORY_TVG:  // TVG_beta (:695-703)
@@ -172,22 +172,22 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 		b[0] = -13;
 		break;
 	case THEORY_DIPRAD:  // DipRad_beta (:707-713)
-		beta[0] = (-3. / 224.) * pow(eta, 2. / 5.) * in0;
+		beta[0] = (-3. / 224.) * sm::pow(eta, 2. / 5.) * in0;
 		b[0] = -7;
 		break;
 	case THEORY_NONCOMM:  // NonComm_beta (:717-723)
-		beta[0] = (-75. / 256.) * pow(eta, -4. / 5.) * (2. * eta - 1.) * in0;
+		beta[0] = (-75. / 256.) * sm::pow(eta, -4. / 5.) * (2. * eta - 1.) * in0;
 		b[0] = -1;
 		break;
 	case THEORY_PNSERIES:  // PNSeries_beta (:420-435): basis M f instead of Mc f; terms > 0 are relative to the first
 	case THEORY_PPEALT: {  // ppEAlt_beta (:399-414)
 		// calculate_chirpmass(mass1, mass2) (src/util.cpp:1492): the same value as s.chirpmass up to the rounding of its pow calls
-		const double chirp = pow(s.mass1 * s.mass2, 3. / 5) / pow(s.mass1 + s.mass2, 1. / 5);
+		const double chirp = sm::pow(s.mass1 * s.mass2, 3. / 5) / sm::pow(s.mass1 + s.mass2, 1. / 5);
 		const double total_m = s.mass1 + s.mass2;
 		n = s.Nmod;
 		for (int i = 0; i < n; i++) {
 			b[i] = s.bppe[i];
-			const double conv = pow(total_m / chirp, s.bppe[i] / 3.);
+			const double conv = sm::pow(total_m / chirp, s.bppe[i] / 3.);
 			if (i == 0 || theory == THEORY_PPEALT) beta[i] = s.betappe[i] * conv;
 			else beta[i] = s.betappe[0] * s.betappe[i] * conv;
 		}
@@ -197,8 +197,8 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 		const double alpha = (s.bppe[0] + 3.) / 3.;
 		const double Dalpha = dl_from_z_md(Z, alpha, dz) * GWAT_MPC_SEC;
 		const double h_planck = 4.135667696e-15;
-		beta[0] = (pow(GWAT_PI, 2. - alpha) / (1. - alpha)) * (Dalpha * in0 / pow(h_planck, 2. - alpha)) *
-		          (pow(s.chirpmass, 1. - alpha) / pow(1 + Z, 1. - alpha));
+		beta[0] = (sm::pow(GWAT_PI, 2. - alpha) / (1. - alpha)) * (Dalpha * in0 / sm::pow(h_planck, 2. - alpha)) *
+		          (sm::pow(s.chirpmass, 1. - alpha) / sm::pow(1 + Z, 1. - alpha));
 		b[0] = s.bppe[0];
 		break;
 	}

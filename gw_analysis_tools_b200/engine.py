@@ -23,6 +23,7 @@ EXPORTS = [
     "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
+    "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
     "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
 
@@ -51,6 +52,10 @@ def load_library():
         lib.gwat_b200_last_kernel_ms.argtypes = [C.c_void_p]
         lib.gwat_b200_ctx_destroy.argtypes = [C.c_void_p]
         lib.gwat_b200_ctx_destroy.restype = None
+        lib.gwat_b200_queue_destroy.argtypes = [C.c_void_p]
+        lib.gwat_b200_queue_destroy.restype = None
+        lib.gwat_b200_queue_loglike.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
+        lib.gwat_b200_queue_loglike.restype = C.c_double
         if lib.gwat_b200_abi_version() != abi.ABI_VERSION:
             raise ImportError("gwat_b200 ABI mismatch")
         _lib = lib
@@ -225,3 +230,44 @@ class Context:
     @property
     def last_active_bins(self):
         return int(self._lib.gwat_b200_last_active_bins(self._h))
+
+
+class LikelihoodQueue:
+    """One-chain-per-call likelihood with the reference callback's shape; concurrent calls are merged into batched launches
+    (``gwat_b200_queue_*``).  ``loglike`` blocks and may be called from many threads (ctypes releases the GIL)."""
+
+    def __init__(self, ctx, method, dimension, gmst, T_segment, mod=None, max_batch=4096, expected_callers=16, max_wait_us=200.0):
+        self._lib = ctx._lib
+        self._ctx = ctx  # keeps the context alive
+        self._h = C.c_void_p()
+        rc = self._lib.gwat_b200_queue_create(C.byref(self._h), ctx._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                              int(dimension), C.c_double(gmst), C.c_double(T_segment), int(max_batch),
+                                              int(expected_callers), C.c_double(max_wait_us))
+        if rc != 0:
+            raise GwatB200Error(rc, "queue_create: bad arguments")
+        self.dimension = int(dimension)
+
+    def loglike(self, param):
+        param = _f64(param)
+        assert param.shape == (self.dimension,)
+        status = C.c_int()
+        v = self._lib.gwat_b200_queue_loglike(self._h, _p(param), C.byref(status))
+        if status.value != 0:
+            raise GwatB200Error(status.value, self._lib.gwat_b200_last_error(self._ctx._h).decode())
+        return v
+
+    def stats(self):
+        calls, batches, largest = C.c_longlong(), C.c_longlong(), C.c_int()
+        self._lib.gwat_b200_queue_stats(self._h, C.byref(calls), C.byref(batches), C.byref(largest))
+        return calls.value, batches.value, largest.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gwat_b200_queue_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -157,6 +157,27 @@ int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *generation_
 int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *generation_method, int W, const gwat_b200_source *sources,
                             double *logL);
 
+/*
+ * One-chain-per-call front of gwat_b200_loglike_mcmc_batch: keeps the shape of the reference's likelihood callback
+ *   double ll(double *param, int *status, int model_status, mcmc_data_interface *interface, void *parameters)
+ * (include/gwat/mcmc_sampler_internals.h:169-171, bound to MCMC_likelihood_wrapper, src/mcmc_gw.cpp:2569), which the
+ * samplers call concurrently from the workers of a thread pool, one chain per call (src/mcmc_sampler.cpp:347-447).
+ * Calls that are in flight at the same moment are merged into ONE batched launch: the first caller waits until
+ * `expected_callers` calls have joined (the pool's thread count), the batch holds `max_batch` vectors, or `max_wait_us`
+ * microseconds have passed, then evaluates the whole group; every caller gets its own chain's value back.  Grouping never
+ * changes a value.  The queue replaces the file-static globals mcmc_generation_method, mcmc_mod_struct, mcmc_gmst
+ * (include/gwat/mcmc_gw.h:22-46) for the calls made through it; the network comes from `ctx` (gwat_b200_set_network).
+ */
+typedef struct gwat_b200_queue gwat_b200_queue;
+int gwat_b200_queue_create(gwat_b200_queue **queue, gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                           int dimension, double gmst, double T_segment, int max_batch, int expected_callers, double max_wait_us);
+void gwat_b200_queue_destroy(gwat_b200_queue *queue);
+/* Blocking; safe to call from any number of threads.  Returns the chain's log-likelihood, or NaN when the point is
+ * unphysical or the batched call failed (`*status`, may be NULL, then holds the gwat_b200_status; 0 on success). */
+double gwat_b200_queue_loglike(gwat_b200_queue *queue, const double *param, int *status);
+/* How many one-chain calls were served, in how many batched launches, and the largest group so far (any may be NULL). */
+int gwat_b200_queue_stats(gwat_b200_queue *queue, long long *calls, long long *batches, int *largest_batch);
+
 /* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
 
 /* Gauss-Legendre frequency grid as the reference builds it for "GAUSSLEG" integration (gauleg, src/ortho_basis.cpp:14-48, used as

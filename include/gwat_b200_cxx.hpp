@@ -213,6 +213,35 @@ inline double MCMC_likelihood_extrinsic(Engine &e, bool /*save_waveform*/, GenPa
 	return ll;
 }
 
+// The samplers' likelihood callback, one chain per call from many pool threads
+//   std::function<double(double *param, int *status, int model_status, mcmc_data_interface *interface, void *parameters)>
+// (include/gwat/mcmc_sampler_internals.h:169-171; MCMC_likelihood_wrapper, src/mcmc_gw.cpp:2569).  `CallbackQueue` owns a
+// gwat_b200_queue that merges the calls in flight into batched launches; bind it where the reference binds its wrapper:
+//   gwat_b200::CallbackQueue q(engine, mcmc_generation_method, mod, dimension, mcmc_gmst, T, numThreads);
+//   sampler.ll = [&q](double *p, int *, int, mcmc_data_interface *, void *) { return q(p); };
+// The callback's `status` / `model_status` arguments are INPUTS in the reference (which dimensions an RJMCMC model has
+// switched on); the fixed-dimension samplers on this path ignore them, and so does this.  Unphysical points and failed
+// launches return NaN, which mcmc_step rejects (src/mcmc_sampler_internals.cpp:101-103).
+class CallbackQueue {
+public:
+	CallbackQueue(Engine &e, const std::string &generation_method, const gwat_b200_mod *mod, int dimension, double gmst, double T_segment,
+	              int pool_threads, int max_batch = 4096, double max_wait_us = 200.0)
+	{
+		if (e.ok())
+			gwat_b200_queue_create(&q_, e.ctx(), generation_method.c_str(), mod, dimension, gmst, T_segment, max_batch, pool_threads, max_wait_us);
+	}
+	~CallbackQueue() { gwat_b200_queue_destroy(q_); }
+	CallbackQueue(const CallbackQueue &) = delete;
+	CallbackQueue &operator=(const CallbackQueue &) = delete;
+	bool ok() const { return q_ != nullptr; }
+	// `rc` (optional) receives the gwat_b200_status of the batched launch that served this call.
+	double operator()(const double *param, int *rc = nullptr) const { return gwat_b200_queue_loglike(q_, param, rc); }
+	gwat_b200_queue *handle() const { return q_; }
+
+private:
+	gwat_b200_queue *q_ = nullptr;
+};
+
 // fisher_numerical(frequency, length, generation_method, detector, reference_detector, output, dimension, parameters, order,
 //                  amp_tapes = NULL, phase_tapes = NULL, noise)     -- `noise` (the PSD) is required here.
 template <class GenParams>

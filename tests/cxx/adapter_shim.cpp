@@ -3,7 +3,10 @@
 // extern "C" functions so that tests/test_cxx_adapter.py can compare them with the oracle.  The flat gwat_b200_source
 // coming from Python is only the transport for the test inputs: it is unpacked into the C++ struct first.
 #include <complex>
+#include <atomic>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dropin_types.hpp"
@@ -137,5 +140,40 @@ int cxa_fisher_numerical(const gwat_b200_source *src, const char *method, const 
 	gwat_b200::fisher_numerical(e, f, L, std::string(method), std::string(detector), std::string(detector), rows.data(), dimension,
 	                            &u.g, order, (int *)nullptr, (int *)nullptr, psd);
 	return e.ok() ? 1 : 0;
+}
+
+// The reference's sampler shape: `threads` pool workers pull chains off a shared counter and call the likelihood callback
+// one chain at a time (src/mcmc_sampler.cpp:347-447).  The callback is a gwat_b200::CallbackQueue bound the way
+// INTEGRATION.md shows.  stats[0..2] = calls, batched launches, largest group.
+int cxa_pool_loglike(const char *method, const gwat_b200_mod *mod, int dimension, int W, const double *params, double gmst,
+                     double T_segment, const char *detectors_csv, double *f, double *psd, const double *data_re, const double *data_im,
+                     int L, int threads, double *logL, long long *stats)
+{
+	std::vector<std::string> dets = split_names(detectors_csv);
+	const int D = (int)dets.size();
+	gwat_b200::Engine e(0);
+	if (!e.ok()) return 0;
+	std::vector<std::vector<std::complex<double>>> data(D, std::vector<std::complex<double>>(L));
+	std::vector<std::complex<double> *> dptr(D);
+	std::vector<double *> fptr(D), pptr(D);
+	for (int d = 0; d < D; d++) {
+		for (int i = 0; i < L; i++) data[d][i] = std::complex<double>(data_re[(size_t)d * L + i], data_im[(size_t)d * L + i]);
+		dptr[d] = data[d].data(); fptr[d] = f; pptr[d] = psd + (size_t)d * L;
+	}
+	if (e.set_network(dets.data(), D, L, fptr.data(), pptr.data(), dptr.data(), nullptr, "SIMPSONS", false) != 0) return 0;
+	gwat_b200::CallbackQueue q(e, std::string(method), mod, dimension, gmst, T_segment, threads);
+	if (!q.ok()) return 0;
+	std::function<double(double *, int *, int, void *, void *)> ll = [&q](double *p, int *, int, void *, void *) { return q(p); };
+	std::atomic<int> next(0);
+	auto worker = [&]() {
+		for (int w = next++; w < W; w = next++) logL[w] = ll(const_cast<double *>(params) + (size_t)w * dimension, nullptr, 0, nullptr, nullptr);
+	};
+	std::vector<std::thread> pool;
+	for (int t = 0; t < threads; t++) pool.emplace_back(worker);
+	for (auto &t : pool) t.join();
+	int largest = 0;
+	gwat_b200_queue_stats(q.handle(), &stats[0], &stats[1], &largest);
+	stats[2] = largest;
+	return 1;
 }
 }

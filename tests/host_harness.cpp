@@ -259,12 +259,16 @@ double loglike_t(int theory, const gwat_b200_source *src, const Network &net, co
 	lg.ld = lg.L;
 	lg.uniform = uniform ? 1 : 0;
 	lg.df = df;
+	// the kernel's cut: units of `bins_per_cta` bins (<= 0: the library's own unit size for this grid), 256 "threads" per
+	// unit, per-thread seeds (the device's per-CTA seed tables are the same numbers to rounding)
+	if (bins_per_cta <= 0) bins_per_cta = unit_bins_for(lg.L);
+	const double fmax = walker_fmax<Fam>(w);
 	double total = 0, nact = 0;
 	for (int begin = 0; begin < lg.L; begin += bins_per_cta) {
 		const int end = std::min(lg.L, begin + bins_per_cta);
 		for (int tid = 0; tid < 256; tid++) {
 			double acc = 0;
-			loglike_run<Fam, D>(w, lg, begin + tid, end, 256, acc, nact);
+			loglike_unit<Fam, D>(w, lg, begin + tid, end, 256, fmax, acc, nact);
 			total += acc;
 		}
 	}

@@ -109,6 +109,32 @@ def test_unknown_method_is_rejected(hh):
         assert hh.hh_fourier_waveform(bad.encode(), C.byref(src), _p(f), f.size, *[_p(x) for x in o]) == -2
 
 
+LL_TOL = 1e-9  # BASELINE.json: log-likelihood relative error
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_fused_likelihood_vs_golden(hh, gold_wf, case):
+    """gwat_like.h -- the fused per-bin likelihood algebra and the fixed summation tree of k_loglike (units of bins, 256
+    threads per unit) -- compiled as C++, against the reference's stored logL; and the value must not depend on the unit size
+    beyond rounding."""
+    name, method, kw, gspec = case
+    f = cases.grid(gspec)
+    src = cases.source_from_bytes(gold_wf[name + "/src"])
+    psd = np.ascontiguousarray(np.tile(workloads.aligo_analytic_psd(f), (3, 1)))
+    data = cases.derived_data(gold_wf[name + "/resp"])
+    dre, dim = np.ascontiguousarray(data.real), np.ascontiguousarray(data.imag)
+    dets = (C.c_char_p * 3)(*[d.encode() for d in cases.DETECTORS])
+    ref = float(gold_wf[name + "/logL"])
+    got = []
+    for unit in (0, 256, 4096):
+        out = np.zeros(1)
+        rc = hh.hh_loglike(method.encode(), 1, C.byref(src), 3, dets, _p(f), f.size, _p(psd), _p(dre), _p(dim), None, 0, 0, unit, _p(out))
+        assert rc == 0
+        assert abs(out[0] - ref) <= LL_TOL * abs(ref), (unit, out[0], ref)
+        got.append(out[0])
+    assert max(got) - min(got) <= 1e-12 * abs(ref)
+
+
 def test_grid_tables_reproduce_glibc_pow():
     """f^(fl(1/6)) * M^(fl(1/6)) in double-double, rounded once, equals glibc's pow(M*f, 1./6.) to <= 1 ulp."""
     rng = np.random.default_rng(3)
