@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(
 		int nact = 0;
 		const int ub = begin + u * unit_bins;
 		if (live) live = loglike_unit<Fam, D>(w, g, ub + threadIdx.x, min(g.L, ub + unit_bins), kLikeThreads, fmax, acc, nact,
-		                                      seeded ? &seeds : nullptr, u, threadIdx.x);
+		                                      &seeds, u, threadIdx.x);
 		acc = warp_sum(acc);
 		nact = __reduce_add_sync(0xffffffffu, nact);
 		if (lane == 0) {
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(
 
 // logL[w] = -1/2 * prefactor * sum of the walker's partials   (Log_Likelihood_internal: -0.5*(HH - 2*DH), src/mcmc_gw.cpp:866)
 // One warp per walker: lane l adds entries l, l + 32, ... in order, then the shuffle tree -- a fixed order for a given grid.
-__global__ void k_finish(const double *__restrict__ partial, int W, int entries, double prefactor, double *__restrict__ logL,
+// snr_mode: the partials are sums of |r|^2 / S alone (data replaced by zeros) and the output is sqrt(prefactor * sum).
+__global__ void k_finish(const double *__restrict__ partial, int W, int entries, double prefactor, int snr_mode, double *__restrict__ logL,
                          unsigned long long *__restrict__ active_total)
 {
 	const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -234,7 +235,7 @@ __global__ void k_finish(const double *__restrict__ partial, int W, int entries,
 	s = warp_sum(s);
 	n = warp_sum(n);
 	if (lane == 0) {
-		logL[w] = -0.5 * (prefactor * s);
+		logL[w] = snr_mode ? sqrt(prefactor * s) : -0.5 * (prefactor * s);
 		if (active_total) atomicAdd(active_total, (unsigned long long)n);
 	}
 }
@@ -479,7 +480,7 @@ int grow(gwat_b200_ctx *c, T *&ptr, size_t &cap, size_t need)
 	return 0;
 }
 
-GridPtrs grid_ptrs(const gwat_b200_ctx *c)
+GridPtrs grid_ptrs(const gwat_b200_ctx *c, const double *zero_data = nullptr)
 {
 	GridPtrs g;
 	const size_t L = c->ld, DL = (size_t)c->D * c->ld;
@@ -489,8 +490,8 @@ GridPtrs grid_ptrs(const gwat_b200_ctx *c)
 	g.logf = c->d_grid + 3 * L;
 	g.ld = c->ld;
 	g.wq = c->d_net;
-	g.dre = c->d_net + DL;
-	g.dim = c->d_net + 2 * DL;
+	g.dre = zero_data ? zero_data : c->d_net + DL;  // zero_data: D*ld zeros standing in for the strain (SNR: <h|h> alone)
+	g.dim = zero_data ? zero_data : c->d_net + 2 * DL;
 	g.L = c->L;
 	g.uniform = c->uniform ? 1 : 0;
 	g.df = c->df;
@@ -548,9 +549,9 @@ struct LikeCut {
 };
 
 template <class Fam>
-int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t st)
+int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t st, const double *zero_data)
 {
-	const GridPtrs g = grid_ptrs(ctx);
+	const GridPtrs g = grid_ptrs(ctx, zero_data);
 	// walkers vary fastest: CTAs in flight together work on the same stretch of the grid tables, so a tile is fetched from
 	// HBM once per pass even when the tables (cfg5: 109 MB) do not fit in L2
 	const dim3 grid(W, cut.chunks);
@@ -589,9 +590,23 @@ LikeCut choose_cut(int W, int L)
 }
 
 // The shared tail of every likelihood entry point: coefficients are in ctx->d_coef.
+// snr_mode: the strain is replaced by zeros and the output is sqrt(<h|h>) instead of -1/2 (<h|h> - 2 <d|h>).
 int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_logL, cudaStream_t st, cudaStream_t st_heavy = nullptr,
-                cudaEvent_t ev_a = nullptr, cudaEvent_t ev_b = nullptr)
+                cudaEvent_t ev_a = nullptr, cudaEvent_t ev_b = nullptr, bool snr_mode = false)
 {
+	const double *zero_data = nullptr;
+	if (snr_mode) {
+		const size_t n = (size_t)ctx->D * ctx->ld;
+		if (ctx->cap_zero < n) {
+			if (ctx->d_zero) cudaFree(ctx->d_zero);
+			ctx->d_zero = nullptr;
+			ctx->cap_zero = 0;
+			CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_zero, sizeof(double) * n));
+			CUDA_TRY(ctx, cudaMemset(ctx->d_zero, 0, sizeof(double) * n));
+			ctx->cap_zero = n;
+		}
+		zero_data = ctx->d_zero;
+	}
 	const LikeCut cut = choose_cut(W, ctx->L);
 	const int entries = cut.units_total * kUnitWarps;  // partial sums per walker
 	if (grow(ctx, ctx->d_partial, ctx->cap_partial, (size_t)2 * W * entries)) return GWAT_B200_ERR_CUDA;
@@ -603,14 +618,14 @@ int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_log
 	}
 	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), sl));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, sl));
-	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, cut, sl)) return fail(
+	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, cut, sl, zero_data)) return fail(
 	                               ctx, GWAT_B200_ERR_STATE, "unsupported detector count"));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, sl));
 	if (sl != st) {
 		CUDA_TRY(ctx, cudaEventRecord(ev_b, sl));
 		CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_b, 0));
 	}
-	k_finish<<<(W + 3) / 4, 128, 0, st>>>(ctx->d_partial, W, entries, ctx->pref_like, d_logL, ctx->d_active);
+	k_finish<<<(W + 3) / 4, 128, 0, st>>>(ctx->d_partial, W, entries, ctx->pref_like, snr_mode ? 1 : 0, d_logL, ctx->d_active);
 	ctx->launches += 2;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -789,6 +804,7 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 	cudaFree(c->d_out);
 	cudaFree(c->d_src);
 	cudaFree(c->d_active);
+	cudaFree(c->d_zero);
 	cudaFree(c->d_deriv);
 	cudaFree(c->d_scale);
 	cudaFree(c->d_fisher);
@@ -932,6 +948,23 @@ int gwat_b200_loglike_batch(gwat_b200_ctx *ctx, const char *method, int W, const
 	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	if (int rc = run_loglike(ctx, desc, W, ctx->d_out, ctx->stream)) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(logL, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+	return collect_stats(ctx, ctx->stream);
+}
+
+int gwat_b200_snr_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *sources, double *snr)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && (!sources || !snr))) return fail(ctx, GWAT_B200_ERR_ARG, "snr_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (int rc = setup_from_sources(ctx, desc, W, sources, ctx->stream)) return rc;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	if (int rc = run_loglike(ctx, desc, W, ctx->d_out, ctx->stream, nullptr, nullptr, nullptr, true)) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(snr, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
 	return collect_stats(ctx, ctx->stream);
 }
 

@@ -19,6 +19,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -305,6 +306,42 @@ int fourier_waveform_batch_py(double *frequencies, int length, int W, void **par
 	const int rc = gwat_b200_fourier_waveform_batch(S.ctx, generation_method, W, src.data(), wf_plus_real, wf_plus_imaginary,
 	                                                wf_cross_real, wf_cross_imaginary);
 	return report(S, rc) == 0 ? 1 : 0;
+}
+
+// ---- noise curves and SNR (src/gwatpy_wrapping.cpp:59-69, 886-889) ----------------------------------------------------------
+// The tabulated curves are read from $GWAT_B200_NOISE_DIR (the directory GWAT installs as GWAT_SHARE_DIR/noise_data; in its
+// source tree data/noise_data/currently_supported).  integration_time only matters for the LISA confusion noise: unused.
+void populate_noise_py(double *frequencies, char *detector, double *noise_root, int length, double integration_time)
+{
+	(void)integration_time;
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	const int rc = gwat_b200_populate_noise(frequencies, detector, std::getenv("GWAT_B200_NOISE_DIR"), length, noise_root);
+	if (rc != 0) {
+		S.last_error = std::string("populate_noise: curve '") + (detector ? detector : "(null)") +
+		               "' unknown, unreadable (set GWAT_B200_NOISE_DIR) or evaluated outside its table";
+		std::fprintf(stderr, "gwat_b200: %s\n", S.last_error.c_str());
+	}
+}
+
+// calculate_snr(sensitivity_curve, detector, generation_method, params, frequencies, length, integration_method, weights,
+// log10_freq), src/waveform_util.cpp:290-344: sqrt(4 int |response|^2 / S) with S = populate_noise(curve)^2.
+double calculate_snr_py(char *sensitivity_curve, char *detector, char *generation_method, void *params, double *frequencies, int length,
+                        char *integration_method, double *weights, bool log10_freq)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	std::vector<double> psd(length > 0 ? length : 0);
+	if (gwat_b200_populate_noise(frequencies, sensitivity_curve, std::getenv("GWAT_B200_NOISE_DIR"), length, psd.data()) != 0) {
+		S.last_error = "calculate_snr: noise curve unavailable";
+		return NaN;
+	}
+	for (double &v : psd) v *= v;
+	const char *dets[1] = {detector};
+	if (ensure_network(S, 1, dets, length, frequencies, psd.data(), nullptr, nullptr, weights, integration_method, log10_freq)) return NaN;
+	double snr = NaN;
+	if (report(S, gwat_b200_snr_batch(S.ctx, generation_method, 1, &static_cast<GenParams *>(params)->s, &snr)) != 0) return NaN;
+	return snr;
 }
 
 // ---- likelihoods (src/gwatpy_wrapping.cpp:96-241) ---------------------------------------------------------------------------

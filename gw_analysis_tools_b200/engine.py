@@ -23,6 +23,7 @@ EXPORTS = [
     "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
+    "gwat_b200_snr_batch", "gwat_b200_populate_noise",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
     "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
@@ -85,6 +86,17 @@ def gauss_legendre_grid(f_lower, f_upper, n, log10F=True):
     if rc != 0:
         raise GwatB200Error(rc, "gauss_legendre_grid: bad arguments")
     return f, w
+
+
+def populate_noise(frequencies, curve, noise_data_dir=None):
+    """sqrt(S_n(f)) of a named GWAT noise curve (host code of the library; tabulated curves are read from ``noise_data_dir``)."""
+    f = _f64(frequencies)
+    out = np.empty(f.size)
+    rc = load_library().gwat_b200_populate_noise(_p(f), curve.encode(), noise_data_dir.encode() if noise_data_dir else None, int(f.size),
+                                                 _p(out))
+    if rc != 0:
+        raise GwatB200Error(rc, "populate_noise(%r): unknown curve, unreadable file or frequency outside the table" % curve)
+    return out
 
 
 class Context:
@@ -160,6 +172,13 @@ class Context:
         self._check(self._lib.gwat_b200_loglike_mcmc_batch_dev(
             self._h, method.encode(), C.byref(mod) if mod is not None else None, int(P), int(W), C.c_void_p(d_params_ptr),
             C.c_double(gmst), C.c_double(T_segment), C.c_void_p(d_logL_ptr), C.c_void_p(stream or 0)))
+
+    def snr_batch(self, method, sources):
+        """Network matched-filter SNR of each source (one-detector network: the reference's calculate_snr)."""
+        arr, W = _src_array(sources)
+        out = np.empty(W)
+        self._check(self._lib.gwat_b200_snr_batch(self._h, method.encode(), W, arr, _p(out)))
+        return out
 
     def loglike_batch(self, method, sources):
         arr, W = _src_array(sources)

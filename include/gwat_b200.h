@@ -178,6 +178,28 @@ double gwat_b200_queue_loglike(gwat_b200_queue *queue, const double *param, int 
 /* How many one-chain calls were served, in how many batched launches, and the largest group so far (any may be NULL). */
 int gwat_b200_queue_stats(gwat_b200_queue *queue, long long *calls, long long *batches, int *largest_batch);
 
+/*
+ * Matched-filter signal-to-noise ratios of W templates in the context's network,
+ *   snr[w] = sqrt( sum_d 4 int |r_d(f)|^2 / S_d(f) df ),
+ * by the network's quadrature rule.  With a one-detector network this is calculate_snr(sensitivity_curve, detector,
+ * generation_method, params, frequencies, length, integration_method, weights, log10_freq) of the reference
+ * (src/waveform_util.cpp:290-344 -> calculate_snr_internal :479-510) with psd = populate_noise(curve)^2.  Data, if the
+ * network has any, are ignored.  Same kernels as the likelihood.
+ */
+int gwat_b200_snr_batch(gwat_b200_ctx *ctx, const char *generation_method, int W, const gwat_b200_source *sources, double *snr);
+
+/*
+ * populate_noise (src/detector_util.cpp:87-282): amplitude spectral density sqrt(S_n) of a named noise curve at the given
+ * frequencies.  Analytic models "aLIGO_analytic", "Hanford_O1_fitted"; tabulated curves ("AdLIGODesign", "AdLIGOAPlus",
+ * "CE1", "CE2", "AdVIRGOPlus2_opt", "KAGRA_opt", "ET-D", "AdLIGOVoyager", ... and their "_smoothed" variants) are read from
+ * the reference's two-column CSV files in `noise_data_dir` (GWAT installs them as GWAT_SHARE_DIR/noise_data; in its source
+ * tree: data/noise_data/currently_supported) and interpolated linearly like gsl_interp_linear.  Frequencies outside a
+ * table give NaN and GWAT_B200_ERR_ARG (GSL aborts there); LISA curves are GWAT_B200_ERR_UNSUPPORTED.  Host code, run once
+ * per analysis before gwat_b200_set_network; noise_data_dir may be NULL for the analytic models.
+ */
+int gwat_b200_populate_noise(const double *frequencies, const char *curve, const char *noise_data_dir, int length,
+                             double *noise_root);
+
 /* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
 
 /* Gauss-Legendre frequency grid as the reference builds it for "GAUSSLEG" integration (gauleg, src/ortho_basis.cpp:14-48, used as

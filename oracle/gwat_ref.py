@@ -178,6 +178,13 @@ def populate_noise(f, curve):
     return asd
 
 
+def calculate_snr(curve, detector, method, src, f, weights=None, integ="SIMPSONS", log10F=False):
+    f, w = _f64(f), _f64(weights)
+    fn = lib().oracle_ref_calculate_snr
+    fn.restype = C.c_double
+    return fn(curve.encode(), detector.encode(), method.encode(), C.byref(src), _p(f), f.size, integ.encode(), _p(w), int(bool(log10F)))
+
+
 def phenomd_intermediates(src):
     out = np.zeros(11)
     lib().oracle_ref_phenomd_intermediates(C.byref(src), _p(out))

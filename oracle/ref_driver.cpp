@@ -527,6 +527,16 @@ int oracle_ref_populate_noise(const double *f, const char *curve, double *asd, i
 	return 0;
 }
 
+// calculate_snr (src/waveform_util.cpp:290-344): SNR of one template in one detector against a named noise curve.
+double oracle_ref_calculate_snr(const char *curve, const char *detector, const char *method, const gwat_b200_source *src,
+                                const double *f, int L, const char *integration_method, const double *weights, int log10F)
+{
+	ParamBox b;
+	to_gen_params(*src, b);
+	return calculate_snr(std::string(curve), std::string(detector), std::string(method), &b.gp, const_cast<double *>(f), L,
+	                     std::string(integration_method), const_cast<double *>(weights), log10F != 0);
+}
+
 // Intermediate per-walker quantities of IMRPhenomD's setup, for unit-testing the GPU setup kernel
 // (src/IMRPhenomD.cpp:414-466).  out[0..] = M, eta, chirpmass, chi_pn, A0, fRD, fdamp, f1, f3, f1_phase, f2_phase
 int oracle_ref_phenomd_intermediates(const gwat_b200_source *src, double *out)
