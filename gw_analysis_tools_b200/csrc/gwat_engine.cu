@@ -580,7 +580,7 @@ LikeCut choose_cut(int W, int L)
 	LikeCut c;
 	c.unit_bins = unit_bins_for(L);
 	c.units_total = (L + c.unit_bins - 1) / c.unit_bins;
-	int upc = (64 * kUnitThreads) / c.unit_bins;  // 4 for grids up to 2^19 bins, 1 for the longest
+	int upc = (64 * kUnitThreads) / c.unit_bins;  // 2 for grids up to 2^20 bins, 1 for longer ones
 	auto chunks_for = [&](int n) { return (c.units_total + n - 1) / n; };
 	while (upc > 1 && (long long)W * chunks_for(upc) < 148LL * 12) upc /= 2;
 	if (upc_env > 0 && upc_env <= kMaxUnitsPerCta) upc = upc_env;
