@@ -23,7 +23,7 @@ EXPORTS = [
     "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
-    "gwat_b200_snr_batch", "gwat_b200_populate_noise",
+    "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
     "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
@@ -172,6 +172,21 @@ class Context:
         self._check(self._lib.gwat_b200_loglike_mcmc_batch_dev(
             self._h, method.encode(), C.byref(mod) if mod is not None else None, int(P), int(W), C.c_void_p(d_params_ptr),
             C.c_double(gmst), C.c_double(T_segment), C.c_void_p(d_logL_ptr), C.c_void_p(stream or 0)))
+
+    def losc_prepare(self, data_files, psd_file, trigger_time, post_merger_duration):
+        """(frequencies[L], psd[D][L], data[D][L]) from LOSC strain text files and a LOSC PSD file (the reference's allocate_LOSC_data)."""
+        D = len(data_files)
+        names = (C.c_char_p * D)(*[str(p).encode() for p in data_files])
+        n = C.c_int(0)
+        rc = self._lib.gwat_b200_losc_prepare(self._h, D, names, str(psd_file).encode(), C.c_double(trigger_time),
+                                              C.c_double(post_merger_duration), 0, C.byref(n), None, None, None, None)
+        if n.value <= 0:
+            self._check(rc)
+        L = n.value
+        f, psd, dre, dim = np.empty(L), np.empty((D, L)), np.empty((D, L)), np.empty((D, L))
+        self._check(self._lib.gwat_b200_losc_prepare(self._h, D, names, str(psd_file).encode(), C.c_double(trigger_time),
+                                                     C.c_double(post_merger_duration), L, C.byref(n), _p(f), _p(psd), _p(dre), _p(dim)))
+        return f, psd, dre + 1j * dim
 
     def snr_batch(self, method, sources):
         """Network matched-filter SNR of each source (one-detector network: the reference's calculate_snr)."""

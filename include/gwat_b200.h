@@ -200,6 +200,22 @@ int gwat_b200_snr_batch(gwat_b200_ctx *ctx, const char *generation_method, int W
 int gwat_b200_populate_noise(const double *frequencies, const char *curve, const char *noise_data_dir, int length,
                              double *noise_root);
 
+/*
+ * LOSC/GWOSC text files -> the inputs of gwat_b200_set_network: allocate_LOSC_data (src/io_util.cpp:523-661).
+ *   data_files[D]          one strain text file per detector (read_LOSC_data_file, :403-464: three header lines -- sampling rate
+ *                          on the second, GPS start and duration on the third -- then the samples)
+ *   psd_file               header line, then rows "f S_1 ... S_D" (read_LOSC_PSD_file, :466-500); its spacing df fixes the
+ *                          observation time T_obs = 1/df, its range the bins that are kept
+ *   trigger_time (GPS), post_merger_duration (s): the segment is (trigger - (T_obs - post), trigger + post]
+ *   capacity               rows the output arrays can hold; *length returns the rows of the PSD file (call with capacity 0 to ask)
+ *   frequencies[length], psd[D*length], data_re/im[D*length]   detector-major, as gwat_b200_set_network takes them
+ * The segment is Tukey-windowed (alpha = 0.8/T_obs), transformed (batched cuFFT, forward, as the reference's FFTW plan) and
+ * multiplied by dt on the GPU.  Unlike the reference, missing files and a trigger outside the file are error codes.
+ */
+int gwat_b200_losc_prepare(gwat_b200_ctx *ctx, int num_detectors, const char *const *data_files, const char *psd_file,
+                           double trigger_time, double post_merger_duration, int capacity, int *length, double *frequencies,
+                           double *psd, double *data_re, double *data_im);
+
 /* ---- waveforms and detector responses ---------------------------------------------------------------------------- */
 
 /* Gauss-Legendre frequency grid as the reference builds it for "GAUSSLEG" integration (gauleg, src/ortho_basis.cpp:14-48, used as

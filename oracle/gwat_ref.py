@@ -178,6 +178,16 @@ def populate_noise(f, curve):
     return asd
 
 
+def losc(data_files, psd_file, trigger_time, post_merger_duration, psd_length, data_file_length):
+    """allocate_LOSC_data: (frequencies[L], psd[D][L], data[D][L])."""
+    D = len(data_files)
+    names = (C.c_char_p * D)(*[str(p).encode() for p in data_files])
+    f, psd, dre, dim = np.zeros(psd_length), np.zeros((D, psd_length)), np.zeros((D, psd_length)), np.zeros((D, psd_length))
+    lib().oracle_ref_losc(D, names, str(psd_file).encode(), C.c_double(trigger_time), C.c_double(post_merger_duration), int(psd_length),
+                          int(data_file_length), _p(f), _p(psd), _p(dre), _p(dim))
+    return f, psd, dre + 1j * dim
+
+
 def calculate_snr(curve, detector, method, src, f, weights=None, integ="SIMPSONS", log10F=False):
     f, w = _f64(f), _f64(weights)
     fn = lib().oracle_ref_calculate_snr

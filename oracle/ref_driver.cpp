@@ -26,6 +26,7 @@
 #include "waveform_generator.h"
 #include "waveform_util.h"
 #include "detector_util.h"
+#include "io_util.h"
 #include "mcmc_gw.h"
 #include "fisher.h"
 #include "ortho_basis.h"
@@ -524,6 +525,29 @@ int oracle_ref_gauleg_grid(double f_lower, double f_upper, int n, int log10F, do
 int oracle_ref_populate_noise(const double *f, const char *curve, double *asd, int L)
 {
 	populate_noise(const_cast<double *>(f), std::string(curve), asd, L);
+	return 0;
+}
+
+// allocate_LOSC_data (src/io_util.cpp:523-661).  Outputs detector-major [D][psd_length]; freqs[psd_length].
+int oracle_ref_losc(int D, const char *const *data_files, const char *psd_file, double trigger_time, double post_merger_duration,
+                    int psd_length, int data_file_length, double *freqs, double *psds, double *data_re, double *data_im)
+{
+	std::vector<std::string> files(D);
+	for (int d = 0; d < D; d++) files[d] = data_files[d];
+	std::vector<std::vector<std::complex<double>>> data(D, std::vector<std::complex<double>>(psd_length));
+	std::vector<std::vector<double>> p(D, std::vector<double>(psd_length)), f(D, std::vector<double>(psd_length));
+	std::vector<std::complex<double> *> dptr(D);
+	std::vector<double *> pptr(D), fptr(D);
+	for (int d = 0; d < D; d++) { dptr[d] = data[d].data(); pptr[d] = p[d].data(); fptr[d] = f[d].data(); }
+	allocate_LOSC_data(files.data(), std::string(psd_file), D, psd_length, data_file_length, trigger_time, post_merger_duration,
+	                   dptr.data(), pptr.data(), fptr.data());
+	for (int d = 0; d < D; d++)
+		for (int i = 0; i < psd_length; i++) {
+			psds[(size_t)d * psd_length + i] = p[d][i];
+			data_re[(size_t)d * psd_length + i] = data[d][i].real();
+			data_im[(size_t)d * psd_length + i] = data[d][i].imag();
+		}
+	for (int i = 0; i < psd_length; i++) freqs[i] = f[0][i];
 	return 0;
 }
 
