@@ -130,3 +130,19 @@ extern "C" int gwat_b200_populate_noise(const double *frequencies, const char *c
 	}
 	return rc;
 }
+
+// gps_to_GMST_radian (src/util.cpp:1793-1846): Greenwich mean sidereal time of a GPS time by the USNO approximation the
+// reference uses (GPS -> Julian date without leap seconds, GMST = 6.697374558 + 0.06570982441908 D0 + 1.00273790935 H +
+// 0.000026 tau^2 hours, reduced modulo 24), in radians.  It is how callers obtain the `gmst` every likelihood call takes.
+extern "C" double gwat_b200_gps_to_gmst_radian(double gps_time)
+{
+	const double J2000 = 2451545;
+	const double JD = J2000 + (gps_time - 630763213.) / (86400.);
+	const double JD0 = std::floor(JD) + .5;
+	const double H = (JD - JD0) * 24;
+	const double D0 = JD0 - J2000, Dd = JD - J2000;
+	const double tau = Dd / 36525.;
+	const double unscaled = 6.697374558 + 0.06570982441908 * D0 + 1.00273790935 * H + 0.000026 * tau * tau;
+	const double hours = ((int)std::floor(unscaled) % 24);
+	return (hours + (unscaled - std::floor(unscaled))) * M_PI / 12.;
+}

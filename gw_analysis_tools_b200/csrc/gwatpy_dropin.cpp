@@ -294,6 +294,23 @@ int fourier_detector_response_py(double *frequencies, int length, double *respon
 	return report(S, rc) == 0 ? 1 : 0;
 }
 
+// fourier_waveform_full_py (src/gwatpy_wrapping.cpp:492-546): all six polarisation arrays.  The models on this path are GR
+// or phase-modified GR -- plus and cross only (assign_polarizations) -- so the vector x/y and scalar b/l outputs are zero.
+int fourier_waveform_full_py(double *frequencies, int length, double *wf_plus_real, double *wf_plus_imaginary, double *wf_cross_real,
+                             double *wf_cross_imaginary, double *wf_x_real, double *wf_x_imaginary, double *wf_y_real,
+                             double *wf_y_imaginary, double *wf_b_real, double *wf_b_imaginary, double *wf_l_real,
+                             double *wf_l_imaginary, char *generation_method, void *parameters)
+{
+	const int st = fourier_waveform_py(frequencies, length, wf_plus_real, wf_plus_imaginary, wf_cross_real, wf_cross_imaginary,
+	                                   generation_method, parameters);
+	double *extra[8] = {wf_x_real, wf_x_imaginary, wf_y_real, wf_y_imaginary, wf_b_real, wf_b_imaginary, wf_l_real, wf_l_imaginary};
+	for (double *a : extra)
+		if (a) std::memset(a, 0, sizeof(double) * (size_t)(length > 0 ? length : 0));
+	return st;
+}
+
+double gps_to_GMST_radian_py(double gps) { return gwat_b200_gps_to_gmst_radian(gps); }
+
 // batched versions (new): W parameter objects at once, outputs [W][length]
 int fourier_waveform_batch_py(double *frequencies, int length, int W, void **parameters, char *generation_method,
                               double *wf_plus_real, double *wf_plus_imaginary, double *wf_cross_real, double *wf_cross_imaginary)

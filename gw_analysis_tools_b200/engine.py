@@ -23,7 +23,7 @@ EXPORTS = [
     "gwat_b200_fourier_waveform_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
-    "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare",
+    "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare", "gwat_b200_gps_to_gmst_radian",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
     "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
@@ -53,6 +53,8 @@ def load_library():
         lib.gwat_b200_last_kernel_ms.argtypes = [C.c_void_p]
         lib.gwat_b200_ctx_destroy.argtypes = [C.c_void_p]
         lib.gwat_b200_ctx_destroy.restype = None
+        lib.gwat_b200_gps_to_gmst_radian.argtypes = [C.c_double]
+        lib.gwat_b200_gps_to_gmst_radian.restype = C.c_double
         lib.gwat_b200_queue_destroy.argtypes = [C.c_void_p]
         lib.gwat_b200_queue_destroy.restype = None
         lib.gwat_b200_queue_loglike.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
@@ -86,6 +88,11 @@ def gauss_legendre_grid(f_lower, f_upper, n, log10F=True):
     if rc != 0:
         raise GwatB200Error(rc, "gauss_legendre_grid: bad arguments")
     return f, w
+
+
+def gps_to_gmst_radian(gps_time):
+    """Greenwich mean sidereal time (rad) of a GPS time, by the reference's formula."""
+    return load_library().gwat_b200_gps_to_gmst_radian(float(gps_time))
 
 
 def populate_noise(frequencies, curve, noise_data_dir=None):

@@ -285,6 +285,9 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_metho
 int gwat_b200_antenna_batch(gwat_b200_ctx *ctx, int W, const double *RA, const double *DEC, const double *psi,
                             double gmst, double *Fplus, double *Fcross, double *dtoa);
 
+/* gps_to_GMST_radian (src/util.cpp:1793-1846): the `gmst` argument of the likelihood calls from a GPS time.  Host code. */
+double gwat_b200_gps_to_gmst_radian(double gps_time);
+
 /* ---- introspection used by bench.py / the tests ------------------------------------------------------------------ */
 
 /* Measured FP64 FMA issue peak of ctx's GPU in TFLOP/s (a DFMA-chain microbenchmark; the roofline denominator of the

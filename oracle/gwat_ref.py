@@ -178,6 +178,13 @@ def populate_noise(f, curve):
     return asd
 
 
+def gps_to_gmst_radian(gps):
+    fn = lib().oracle_ref_gps_to_gmst_radian
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_double]
+    return fn(float(gps))
+
+
 def losc(data_files, psd_file, trigger_time, post_merger_duration, psd_length, data_file_length):
     """allocate_LOSC_data: (frequencies[L], psd[D][L], data[D][L])."""
     D = len(data_files)

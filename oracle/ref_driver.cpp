@@ -551,6 +551,8 @@ int oracle_ref_losc(int D, const char *const *data_files, const char *psd_file, 
 	return 0;
 }
 
+double oracle_ref_gps_to_gmst_radian(double gps) { return gps_to_GMST_radian(gps); }
+
 // calculate_snr (src/waveform_util.cpp:290-344): SNR of one template in one detector against a named noise curve.
 double oracle_ref_calculate_snr(const char *curve, const char *detector, const char *method, const gwat_b200_source *src,
                                 const double *f, int L, const char *integration_method, const double *weights, int log10F)

@@ -20,7 +20,8 @@ ON_PATH_SYMBOLS = ["gen_params_base_py", "gen_params_base_py_destructor", "MCMC_
                    "MCMC_likelihood_extrinsic_py", "MCMC_likelihood_extrinsic_pyv2", "repack_parameters_py", "DTOA_DETECTOR_py",
                    "detector_response_equatorial_py", "calculate_chirpmass_py", "calculate_eta_py", "calculate_mass1_py",
                    "calculate_mass2_py", "calculate_chirpmass_vectorized_py", "calculate_eta_vectorized_py",
-                   "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py"]
+                   "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py",
+                   "fourier_waveform_full_py", "populate_noise_py", "calculate_snr_py", "gps_to_GMST_radian_py"]
 
 
 def _lib():
@@ -30,6 +31,9 @@ def _lib():
     lib.MCMC_likelihood_extrinsic_py.restype = C.c_double
     lib.MCMC_likelihood_extrinsic_pyv2.restype = C.c_double
     lib.DTOA_DETECTOR_py.restype = C.c_double
+    lib.calculate_snr_py.restype = C.c_double
+    lib.gps_to_GMST_radian_py.restype = C.c_double
+    lib.populate_noise_py.restype = None
     return lib
 
 
@@ -129,3 +133,26 @@ def test_gwatpy_likelihood_v2_and_batch(oracle):
     assert rc == 0
     assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-9
     lib.MCMC_modification_struct_py_destructor(C.c_void_p(mod))
+
+
+@pytest.mark.gpu
+def test_gwatpy_noise_snr_and_full_polarisations(oracle):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "waveforms_v1.npz"))
+    lib = _lib()
+    name, method, kw, gspec = [c for c in cases.CASES if c[0] == "P_full"][0]
+    f = cases.grid(gspec)
+    L = f.size
+    gp = _gen_params(lib, kw)
+    asd = np.zeros(L)
+    lib.populate_noise_py(_p(f), b"Hanford_O1_fitted", _p(asd), L, C.c_double(48.0))
+    assert np.allclose(asd, oracle.populate_noise(f, "Hanford_O1_fitted"), rtol=1e-14, atol=0)
+    snr = lib.calculate_snr_py(b"Hanford_O1_fitted", b"Virgo", method.encode(), C.c_void_p(gp), _p(f), L, b"SIMPSONS", None, C.c_bool(False))
+    want = oracle.calculate_snr("Hanford_O1_fitted", "Virgo", method, cases.source(kw), f)
+    assert abs(snr - want) <= 1e-9 * want
+    o = [np.full(L, 7.0) for _ in range(12)]
+    assert lib.fourier_waveform_full_py(_p(f), L, *[_p(x) for x in o], method.encode(), C.c_void_p(gp)) == 1
+    assert np.abs(o[0] + 1j * o[1] - gold[name + "/hp"]).max() <= 1e-10 * np.abs(gold[name + "/hp"]).max()
+    assert np.abs(o[2] + 1j * o[3] - gold[name + "/hc"]).max() <= 1e-10 * np.abs(gold[name + "/hc"]).max()
+    assert all(not x.any() for x in o[4:])  # no vector / scalar polarisations in these models
+    assert lib.gps_to_GMST_radian_py(C.c_double(1126259462.4)) == oracle.gps_to_gmst_radian(1126259462.4)
+    lib.gen_params_base_py_destructor(C.c_void_p(gp))

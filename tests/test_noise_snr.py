@@ -35,6 +35,12 @@ def test_analytic_curves_golden_and_oracle(oracle):
     assert np.allclose(engine.populate_noise(f, "aLIGO_analytic") ** 2, workloads.aligo_analytic_psd(f), rtol=1e-14, atol=0)
 
 
+def test_gps_to_gmst_vs_reference(oracle):
+    for gps in (1126259462.4, 1187008882.4, 630763213.0, 1e9 + 0.5, 1.4e9, 815000000.25):
+        assert engine.gps_to_gmst_radian(gps) == oracle.gps_to_gmst_radian(gps)
+    assert engine.gps_to_gmst_radian(1126259462.4) == 2.4568247373045096  # value of the reference build, GW150914's GPS time
+
+
 def test_unknown_and_unsupported_curves():
     f = np.array([30.0, 40.0])
     for name, code in (("LISA", abi.ERR_UNSUPPORTED), ("LISA_SADC_CONF", abi.ERR_UNSUPPORTED), ("NoSuchCurve", abi.ERR_ARG),
