@@ -23,36 +23,66 @@ struct BinGrid {
 };
 
 
-// The (2,2) carrier h = A exp(-i phi) of the IMRPhenomD families, time and phase shifts applied.
+// The (2,2) carrier h = A exp(-i phi) of the IMRPhenomD families before the time and phase shifts: amplitude (NRT: already
+// tapered) and phase.
 template <class Fam>
-GWAT_HD cplx carrier_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf)
+GWAT_HD void carrier_parts(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, PolParts &pp)
 {
 	const DCoef &c = w.d;
-	if (f > c.fcut) return cplx{0.0, 0.0};
 	// NRT: the Planck taper multiplies everything above 1.2 f_merger by exactly zero (src/IMRPhenomD_NRT.cpp:582-585, 745)
-	if (Fam::nrt && f > c.nrt_fmerger12) return cplx{0.0, 0.0};
+	pp.zero = f > c.fcut || (Fam::nrt && f > c.nrt_fmerger12);
+	if (pp.zero) return;
 	double amp, phase;
 	MfPowers p;
 	phenomd_bin<Fam>(c, f, bin_sixth_root(c, sf_hi, sf_lo), logf, amp, phase, p);
-	if (Fam::nrt) nrt_bin(c, f, p, logf, amp, phase);
-	phase = phenomd_apply_time_phase(c, f, phase);
-	double sn, cs;
-	fast_sincos(phase, &sn, &cs);
-	if (Fam::nrt) amp *= nrt_taper_factor(c, f);
-	return cplx{amp * cs, -(amp * sn)};
+	if (Fam::nrt) {
+		nrt_bin(c, f, p, logf, amp, phase);
+		amp *= nrt_taper_factor(c, f);
+	}
+	pp.amp = amp;
+	pp.phase = phase;
 }
 
-// fourier_waveform semantics for the IMRPhenomD families.
+// Polarisations of one bin in two steps (all families): the parts that do not involve the coalescence time, and the finish
+// with the coefficient `tc` of (f - f_ref) -- w.d.tc / w.p.tc unless the caller re-times the point (Fisher stencil).
+template <class Fam>
+GWAT_HD void polarization_parts(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, PolParts &pp)
+{
+	if (Fam::base == BASE_P) phenomp_polarization_parts<Fam>(w, f, sf_hi, sf_lo, logf, pp);
+	else carrier_parts<Fam>(w, f, sf_hi, sf_lo, logf, pp);
+}
+template <class Fam>
+GWAT_HD double walker_time_coefficient(const WalkerCoef &w)
+{
+	return Fam::base == BASE_P ? w.p.tc : w.d.tc;
+}
+template <class Fam>
+GWAT_HD void polarizations_finish(const WalkerCoef &w, const PolParts &pp, double tc, double f, cplx &hp, cplx &hc)
+{
+	if (Fam::base == BASE_P) {
+		phenomp_polarizations_finish<Fam>(w, pp, tc, f, hp, hc);
+		return;
+	}
+	if (pp.zero) {
+		hp = cplx{0.0, 0.0};
+		hc = cplx{0.0, 0.0};
+		return;
+	}
+	// waveform[j] = amp exp(-i phase); h+ = (1+cos^2 i)/2 h, hx = -i cos(i) h
+	double sn, cs;
+	fast_sincos(phenomd_apply_time_phase(w.d, tc, f, pp.phase), &sn, &cs);
+	const cplx h{pp.amp * cs, -(pp.amp * sn)};
+	hp = cplx{h.re * w.pfac, h.im * w.pfac};
+	hc = cplx{h.im * w.cfac, -h.re * w.cfac};
+}
+
+// fourier_waveform semantics.
 template <class Fam>
 GWAT_HD void polarizations_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, cplx &hp, cplx &hc)
 {
-	if (Fam::base == BASE_P) {
-		phenomp_polarizations_bin<Fam>(w, f, sf_hi, sf_lo, logf, hp, hc);
-		return;
-	}
-	const cplx h = carrier_bin<Fam>(w, f, sf_hi, sf_lo, logf);
-	hp = cplx{h.re * w.pfac, h.im * w.pfac};
-	hc = cplx{h.im * w.cfac, -h.re * w.cfac};
+	PolParts pp;
+	polarization_parts<Fam>(w, f, sf_hi, sf_lo, logf, pp);
+	polarizations_finish<Fam>(w, pp, walker_time_coefficient<Fam>(w), f, hp, hc);
 }
 
 // Response of detector d including the arrival-time phase (create_coherent_GW_detection_reuse_WF semantics);
@@ -60,7 +90,7 @@ GWAT_HD void polarizations_bin(const WalkerCoef &w, double f, double sf_hi, doub
 GWAT_HD cplx project_bin(const DetCoef &dc, cplx hp, cplx hc, double f, bool with_shift)
 {
 	cplx r{dc.Fplus * hp.re + dc.Fcross * hc.re, dc.Fplus * hp.im + dc.Fcross * hc.im};
-	if (with_shift) {
+	if (with_shift && dc.tshift != 0.0) {  // (a zero shift multiplies by exactly 1: the reference detector, and most stencil points)
 		double sn, cs;
 		fast_sincos(mul_rn(dc.tshift, f), &sn, &cs);
 		r = cplx{r.re * cs - r.im * sn, r.re * sn + r.im * cs};

@@ -289,22 +289,29 @@ struct FisherPlan {
 	double det_row[5][13], ref_row[13];
 };
 
+// One thread per (source, parameter, stencil point): the perturbed source's coefficient block with the antenna patterns of
+// all detectors of the pass, and per detector the two quantities through which the detector enters the response besides
+// F+/Fx -- the arrival-time phase (+-eps points) or the re-timed carrier (+-2 eps points):
+//   tshift[d]   -2 pi DTOA(reference, d) for k < 2, else 0                    (:403-408, 425-430)
+//   tcoef[d]    coefficient of (f - f_ref) with t_c - DTOA for k >= 2         (:436-438, 451-453)  [reference quirk, kept]
+// Everything else of a response is the same for all detectors, so the carrier is evaluated once per stencil point
+// (k_fisher_deriv) instead of once per detector as the reference does.
 template <class Fam>
 __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__restrict__ src, int S, FisherPlan fp,
-                                                     WalkerCoef *__restrict__ coefs, double *__restrict__ scale,
-                                                     int *__restrict__ eta_bc)
+                                                     WalkerCoef *__restrict__ coefs, double *__restrict__ tcoef,
+                                                     double *__restrict__ scale, int *__restrict__ eta_bc)
 {
 	const int dim = fp.rp.dimension;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= fp.nd * S * dim * fp.npts) return;
-	const int k = t % fp.npts, i = (t / fp.npts) % dim, sidx = (t / (fp.npts * dim)) % S, d = t / (fp.npts * dim * S);
+	if (t >= S * dim * fp.npts) return;
+	const int k = t % fp.npts, i = (t / fp.npts) % dim, sidx = t / (fp.npts * dim);
 	const double epsilon = 1e-8;
 	const gwat_b200_source orig = src[sidx];
 	double v[GWAT_B200_MAX_DIM];
 	int logfac[GWAT_B200_MAX_DIM];
 	unpack_fisher(orig, fp.rp, v, logfac);
 	const bool bc = (i == 8 && v[8] > .25 - epsilon);  // eta at its upper boundary: one-sided difference (:369-383)
-	if (k == 0 && d == 0) {
+	if (k == 0) {
 		scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
 		eta_bc[(size_t)sidx * dim + i] = bc ? 1 : 0;
 	}
@@ -314,71 +321,135 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	else v[i] = base + step;
 	gwat_b200_source sp;
 	repack_fisher_point(v, orig, fp.rp, sp);
-	double tshift = 0;
-	if (!fp.det_is_ref[d]) {
-		const double dtoa = dtoa_between(fp.ref_row + 9, fp.det_row[d] + 9, sp.RA, sp.DEC, sp.gmst);
-		if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;  // +-eps: phase factor on the response (:403-408, 425-430)
-		else sp.tc -= dtoa;                          // +-2eps: shift of tc instead (:436-438, 451-453)  [reference quirk, kept]
-	}
 	Network net;
-	net.D = 1;
-	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[d][j];
+	net.D = fp.nd;
+	for (int d = 0; d < fp.nd; d++)
+		for (int j = 0; j < 13; j++) net.row[d][j] = fp.det_row[d][j];
 	WalkerCoef wc;
 	walker_setup<Fam>(sp, net, device_tables(), fp.theory, wc);
-	wc.det[0].tshift = tshift;
-	wc.valid = coef_is_finite(wc, 1, Fam::base == BASE_P) ? 1 : 0;
+	for (int d = 0; d < fp.nd; d++) {
+		double tshift = 0, tc_seconds = sp.tc;
+		if (!fp.det_is_ref[d]) {
+			const double dtoa = dtoa_between(fp.ref_row + 9, fp.det_row[d] + 9, sp.RA, sp.DEC, sp.gmst);
+			if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;
+			else tc_seconds = sp.tc - dtoa;
+		}
+		wc.det[d].tshift = tshift;
+		tcoef[(size_t)t * fp.nd + d] =
+		    Fam::base == BASE_P ? phenomp_time_coefficient(tc_seconds) : phenomd_time_coefficient(tc_seconds, wc.d.tc_shift);
+	}
+	wc.valid = coef_is_finite(wc, fp.nd, Fam::base == BASE_P) ? 1 : 0;
 	coefs[t] = wc;
 }
 
-// deriv[s][i][bin] = stencil combination of the responses, times the log-parameter factor (:462-484, 548-554)
+// deriv[d][s][i][bin] = stencil combination of the responses, times the log-parameter factor (:462-484, 548-554).
+// grid (bin tiles, sources x parameters): the time-independent parts of the 2 or 4 stencil points are evaluated once per bin
+// -- once for ALL points when the parameter is RA, DEC or psi, which only move the antenna patterns and arrival times --
+// and finished per detector.
 template <class Fam>
-__global__ void __launch_bounds__(kThreads) k_fisher_deriv(const WalkerCoef *__restrict__ coefs, GridPtrs g, int npts,
-                                                          const double *__restrict__ scale, const int *__restrict__ eta_bc,
-                                                          double *__restrict__ dre, double *__restrict__ dim_)
+__global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *__restrict__ coefs, const double *__restrict__ tcoef,
+                                                          GridPtrs g, int npts, int nd, int dim, const double *__restrict__ scale,
+                                                          const int *__restrict__ eta_bc, double *__restrict__ dre, double *__restrict__ dim_,
+                                                          int *__restrict__ bin_limit)
 {
 	__shared__ WalkerCoef w[4];
+	__shared__ double tc_s[4][5];
+	if (g.uniform) {
+		// ascending grid: a tile that starts above the cutoff of every stencil point is exactly zero -- decided from a few words
+		// of the coefficient records before anything is staged (about half of the tiles of a BBH population end here)
+		const WalkerCoef *wg = coefs + (size_t)blockIdx.y * npts;
+		const double f0 = g.f[blockIdx.x * kThreads];
+		bool dead = true;
+		for (int k = 0; k < npts; k++) dead = dead && wg[k].valid && f0 > walker_fmax<Fam>(wg[k]);
+		if (dead) {
+			const int bin = blockIdx.x * kThreads + threadIdx.x;
+			if (bin < g.L)
+				for (int d = 0; d < nd; d++) {
+					const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+					dre[o] = 0.0;
+					dim_[o] = 0.0;
+				}
+			return;
+		}
+	}
 	{
-		const double *sp = reinterpret_cast<const double *>(coefs + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * npts);
+		const double *sp = reinterpret_cast<const double *>(coefs + (size_t)blockIdx.y * npts);
 		double *dp = reinterpret_cast<double *>(&w[0]);
 		for (int i = threadIdx.x; i < (int)(npts * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
+		if (threadIdx.x < npts * nd) tc_s[threadIdx.x / nd][threadIdx.x % nd] = tcoef[(size_t)blockIdx.y * npts * nd + threadIdx.x];
 		__syncthreads();
 	}
-	const int bin = blockIdx.x * kThreads + threadIdx.x;
-	if (bin >= g.L) return;
+	const int bin_raw = blockIdx.x * kThreads + threadIdx.x;
+	const bool in_grid = bin_raw < g.L;
+	const int bin = in_grid ? bin_raw : g.L - 1;  // (tail threads shadow the last bin and store nothing: no early return before the barrier below)
 	const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
-	cplx r[4];
-	for (int k = 0; k < npts; k++) {
-		if (!w[k].valid) {
-			r[k] = cplx{NAN, NAN};
-			continue;
+	// parameters 0..2 are RA, DEC (or sin DEC) and psi in every parameterisation (src/fisher.cpp:46-66): the intrinsic part of
+	// the source, and with it everything in PolParts, is bit-identical at all stencil points
+	const bool shared_parts = (int)(blockIdx.y % dim) < 3;
+	PolParts pp[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
+		if (k >= npts) continue;
+		if (k > 0 && shared_parts) pp[k] = pp[0];
+		else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
+	}
+	// Bins above every stencil point's cutoff have exactly zero responses: nothing to evaluate, and k_fisher_assemble need not
+	// read them -- the highest live bin of each source is recorded (one atomic per CTA).  Invalid points (NaN) keep every bin.
+	bool live = false;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (k < npts) live = live || !w[k].valid || !pp[k].zero;
+	const int any_live = __syncthreads_or(live && in_grid);
+	if (threadIdx.x == 0 && any_live) atomicMax(&bin_limit[blockIdx.y / dim], min(g.L, (int)(blockIdx.x + 1) * kThreads));
+	if (!in_grid) return;
+	if (!live) {
+		for (int d = 0; d < nd; d++) {
+			const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+			dre[o] = 0.0;
+			dim_[o] = 0.0;
 		}
-		cplx hp, hc;
-		polarizations_bin<Fam>(w[k], f, hi, lo, lg, hp, hc);
-		r[k] = project_bin(w[k].det[0], hp, hc, f, true);
+		return;
 	}
 	const double epsilon = 1e-8;
 	const bool bc = eta_bc[blockIdx.y] != 0;
-	cplx d;
-	if (npts == 2) {
-		const double den = bc ? epsilon : 2. * epsilon;
-		d = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
-	} else {
-		const double den = bc ? 6. * epsilon : 12. * epsilon;
-		d = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
-		         (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
-	}
 	const double sc = scale[blockIdx.y];
-	const size_t o = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.L + bin;
-	dre[o] = d.re * sc;
-	dim_[o] = d.im * sc;
+	for (int d = 0; d < nd; d++) {
+		cplx r[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (k >= npts) continue;
+			if (!w[k].valid) {
+				r[k] = cplx{NAN, NAN};
+				continue;
+			}
+			// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8 instead
+			// of 12 finishes for three detectors -- measured 11 % slower: 40 more live registers)
+			cplx hp, hc;
+			polarizations_finish<Fam>(w[k], pp[k], tc_s[k][d], f, hp, hc);
+			r[k] = project_bin(w[k].det[d], hp, hc, f, true);
+		}
+		cplx dv;
+		if (npts == 2) {
+			const double den = bc ? epsilon : 2. * epsilon;
+			dv = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
+		} else {
+			const double den = bc ? 6. * epsilon : 12. * epsilon;
+			dv = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
+			          (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
+		}
+		const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+		dre[o] = dv.re * sc;
+		dim_[o] = dv.im * sc;
+	}
 }
 
 // F_jk = sum_d prefactor * sum_bins coef_d * Re(d_j conj(d_k)) / S_d   (calculate_fisher_elements, src/fisher.cpp:2704-2781, and the
 // detector loop of the callers: one partial Fisher per detector, added in detector order)
 __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__restrict__ dre, const double *__restrict__ dim_,
                                                              const double *__restrict__ wq, int ld, int L, int dim, int ns, int nd,
-                                                             double prefactor, double *__restrict__ out)
+                                                             double prefactor, const int *__restrict__ bin_limit, double *__restrict__ out)
 {
+	const int Llive = bin_limit[blockIdx.y];  // derivatives are exactly zero from here on (k_fisher_deriv)
 	// blockIdx.x enumerates the pairs j >= k, blockIdx.y the source
 	int j = 0, k = blockIdx.x;
 	while (k > j) {
@@ -392,7 +463,7 @@ __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__re
 		const double *akr = dre + (sbase + k) * L, *aki = dim_ + (sbase + k) * L;
 		const double *w = wq + (size_t)d * ld;
 		double acc = 0, unused = 0;
-		for (int i = threadIdx.x; i < L; i += kThreads) acc += w[i] * (ajr[i] * akr[i] + aji[i] * aki[i]);
+		for (int i = threadIdx.x; i < Llive; i += kThreads) acc += w[i] * (ajr[i] * akr[i] + aji[i] * aki[i]);
 		block_sum2(acc, unused);
 		if (threadIdx.x == 0) {
 			const double val = prefactor * acc;
@@ -680,7 +751,9 @@ int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim, int nd)
 int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts, int nd)
 {
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts * nd)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_tcoef, ctx->cap_tcoef, (size_t)chunk * dim * npts * nd)) return GWAT_B200_ERR_CUDA;
+	if (grow(ctx, ctx->d_binlim, ctx->cap_binlim, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L * nd)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
@@ -702,15 +775,16 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 		std::memcpy(fp.det_row[d], ctx->net.row[d0 + d], sizeof(fp.det_row[d]));
 		fp.det_is_ref[d] = (std::memcmp(fp.det_row[d], fp.ref_row, sizeof(fp.ref_row)) == 0) ? 1 : 0;
 	}
-	const int nthreads = nd * ns * dim * fp.npts;
-	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef,
+	const int nthreads = ns * dim * fp.npts;
+	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef, ctx->d_tcoef,
 	                                                                                        ctx->d_scale, ctx->d_bc));
-	const dim3 gd((L + kThreads - 1) / kThreads, ns * dim, nd);
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_binlim, 0, sizeof(int) * ns, st));
+	const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
 	double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L * nd;
-	GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, ctx->d_scale, ctx->d_bc,
-	                                                                         dre, dim_));
+	GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, ctx->d_tcoef, g, fp.npts, nd, dim, ctx->d_scale,
+	                                                                         ctx->d_bc, dre, dim_, ctx->d_binlim));
 	k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d0 * ctx->ld, ctx->ld, L, dim, ns, nd,
-	                                                          ctx->pref_fisher, ctx->d_fisher);
+	                                                          ctx->pref_fisher, ctx->d_binlim, ctx->d_fisher);
 	ctx->launches += 3;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -805,6 +879,8 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 	cudaFree(c->d_src);
 	cudaFree(c->d_active);
 	cudaFree(c->d_zero);
+	cudaFree(c->d_tcoef);
+	cudaFree(c->d_binlim);
 	cudaFree(c->d_deriv);
 	cudaFree(c->d_scale);
 	cudaFree(c->d_fisher);

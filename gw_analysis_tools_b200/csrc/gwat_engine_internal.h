@@ -47,9 +47,11 @@ struct gwat_b200_ctx {
 	unsigned long long *d_active = nullptr;
 	double *d_zero = nullptr;  // D*ld zeros: the strain seen by gwat_b200_snr_batch
 	size_t cap_zero = 0;
-	size_t cap_deriv = 0, cap_scale = 0, cap_fisher = 0, cap_bc = 0;
-	double *d_deriv = nullptr, *d_scale = nullptr, *d_fisher = nullptr;
+	size_t cap_deriv = 0, cap_scale = 0, cap_fisher = 0, cap_bc = 0, cap_tcoef = 0;
+	double *d_deriv = nullptr, *d_scale = nullptr, *d_fisher = nullptr, *d_tcoef = nullptr;
 	int *d_bc = nullptr;
+	int *d_binlim = nullptr;  // per source: bins from here on have exactly zero derivatives (Fisher passes)
+	size_t cap_binlim = 0;
 	// two more sets of likelihood scratch for callers that keep several batches in flight on their own streams (the
 	// ensemble sampler); swapped in by LaneSwap while the caller holds `mu`
 	LikeLane extra[2];

@@ -95,6 +95,7 @@ struct DCoef {
 	double alpha0, alpha1, alpha2, alpha3_43, alpha4, alpha5fRD;
 	// time and phase reference
 	double tc, f_ref, phic;
+	double tc_shift;  // tc = 2 pi t_c + tc_shift (kept so that a stencil point can be re-timed per detector, see k_fisher_setup)
 	// ppE / gIMR extras (used only by the families that have them)
 	int Nmod;
 	double betappe[GWAT_B200_MAX_MOD], bppe[GWAT_B200_MAX_MOD];

@@ -366,11 +366,18 @@ GWAT_HD void phenomd_bin(const DCoef &c, double f, double sixth, double logf, do
 	phenomd_bin<Fam>(c, f, sixth, logf, amp, phase, p);
 }
 
+// The coefficient of (f - f_ref) in the carrier phase: 2 pi t_c plus the shift that puts the peak at t_c
+// (src/IMRPhenomD.cpp:452-466); for IMRPhenomPv2 the shift is applied separately (src/IMRPhenomP.cpp:354-362).
+// One definition so that every caller rounds it the same way.
+GWAT_HD double phenomd_time_coefficient(double tc_seconds, double tc_shift) { return 2 * GWAT_PI * tc_seconds + tc_shift; }
+GWAT_HD double phenomp_time_coefficient(double tc_seconds) { return 2 * GWAT_PI * tc_seconds; }
+
 // phase -= tc (f - f_ref) + phic     (src/IMRPhenomD.cpp:497), unfused like the reference
-GWAT_HD double phenomd_apply_time_phase(const DCoef &c, double f, double phase)
+GWAT_HD double phenomd_apply_time_phase(const DCoef &c, double tc, double f, double phase)
 {
-	return sub_rn(phase, add_rn(mul_rn(c.tc, sub_rn(f, c.f_ref)), c.phic));
+	return sub_rn(phase, add_rn(mul_rn(tc, sub_rn(f, c.f_ref)), c.phic));
 }
+GWAT_HD double phenomd_apply_time_phase(const DCoef &c, double f, double phase) { return phenomd_apply_time_phase(c, c.tc, f, phase); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // per-walker setup

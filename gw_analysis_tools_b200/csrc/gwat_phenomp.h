@@ -266,7 +266,7 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 	p.c2z = sm::cos(2. * s.zeta_polariz);
 	p.s2z = sm::sin(2. * s.zeta_polariz);
 	p.phic = 2 * s.phi_aligned;
-	p.tc = 2 * GWAT_PI * s.tc;
+	p.tc = phenomp_time_coefficient(s.tc);
 	p.f_ref = s.f_ref;
 	double t_corr = 0;
 	if (s.shift_time) {
@@ -297,17 +297,22 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 }
 
 // One bin of IMRPhenomPv2: both polarisations, rotated by 2 zeta (fourier_waveform semantics).
+// What a bin's polarisations are made of before the coalescence time enters: carrier amplitude and phase, and (PhenomPv2)
+// the twist factors.  The Fisher stencil evaluates this once per stencil point and finishes it per detector, because the
+// reference re-times some stencil points per detector (src/fisher.cpp:436-453) and nothing else depends on the detector.
+struct PolParts {
+	double amp, phase;
+	cplx hpf, hcf;
+	bool zero;  // above the model's cutoff: the polarisations are exactly zero
+};
+
 template <class Fam>
-GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, cplx &hp,
-                                       cplx &hc)
+GWAT_HD void phenomp_polarization_parts(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, PolParts &pp)
 {
 	const DCoef &c = w.d;
 	const PCoef &p = w.p;
-	if (f > c.fcut) {
-		hp = cplx{0.0, 0.0};
-		hc = cplx{0.0, 0.0};
-		return;
-	}
+	pp.zero = f > c.fcut;
+	if (pp.zero) return;
 	const double sixth = bin_sixth_root(c, sf_hi, sf_lo);
 	MfPowers mp;
 	mf_powers(c.M, f, sixth, mp);
@@ -364,9 +369,26 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 		hcf.re += -(T2m.im - Tm2m.im);
 		hcf.im += (T2m.re - Tm2m.re);
 	}
-	phase = add_rn(phase, mul_rn(2., epsilon));
+	pp.amp = amp;
+	pp.phase = add_rn(phase, mul_rn(2., epsilon));
+	pp.hpf = hpf;
+	pp.hcf = hcf;
+}
+
+// `tc`: the coefficient of (f - f_ref), p.tc unless a caller re-times the point.
+template <class Fam>
+GWAT_HD void phenomp_polarizations_finish(const WalkerCoef &w, const PolParts &pp, double tc, double f, cplx &hp, cplx &hc)
+{
+	const PCoef &p = w.p;
+	if (pp.zero) {
+		hp = cplx{0.0, 0.0};
+		hc = cplx{0.0, 0.0};
+		return;
+	}
+	const double amp = pp.amp;
+	const cplx hpf = pp.hpf, hcf = pp.hcf;
 	// exp(-i (phase - tc (f - f_ref) - phic + 2 pi t_corr f))       (src/IMRPhenomP.cpp:354-362)
-	double arg = sub_rn(phase, mul_rn(p.tc, sub_rn(f, p.f_ref)));
+	double arg = sub_rn(pp.phase, mul_rn(tc, sub_rn(f, p.f_ref)));
 	arg = sub_rn(arg, p.phic);
 	arg = add_rn(arg, mul_rn(p.tcorr_2pi, f));
 	double sn, cs;
@@ -376,6 +398,15 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 	const cplx hcross{carrier.re * hcf.re - carrier.im * hcf.im, carrier.re * hcf.im + carrier.im * hcf.re};
 	hp = cplx{p.c2z * hplus.re + p.s2z * hcross.re, p.c2z * hplus.im + p.s2z * hcross.im};
 	hc = cplx{p.c2z * hcross.re - p.s2z * hplus.re, p.c2z * hcross.im - p.s2z * hplus.im};
+}
+
+template <class Fam>
+GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, cplx &hp,
+                                       cplx &hc)
+{
+	PolParts pp;
+	phenomp_polarization_parts<Fam>(w, f, sf_hi, sf_lo, logf, pp);
+	phenomp_polarizations_finish<Fam>(w, pp, w.p.tc, f, hp, hc);
 }
 
 // ---- one walker, start to finish (all families) ---------------------------------------------------------------------

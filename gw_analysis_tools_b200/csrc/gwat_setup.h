@@ -350,7 +350,8 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 			tc_shift = dphase_mr_df(lam, M, eta, s.fRD, s.fdamp, s.f3) + dphase_imr_extra<Fam>(s, s.f3) +
 			           (-lam.alpha[1] + alpha1_fit) * M / eta;
 		}
-		c.tc = 2 * GWAT_PI * s.tc + tc_shift;
+		c.tc_shift = tc_shift;
+		c.tc = phenomd_time_coefficient(s.tc, tc_shift);
 		c.f_ref = f_ref;
 		c.phic = phic;
 	}

@@ -40,9 +40,18 @@ def main():
     line = {"metric": "order-4 numerical Fisher matrices/sec (%s, dim %d, 3 detectors summed, %d bins)" % (args.method, args.dim, args.bins),
             "value": args.sources / dt, "unit": "Fisher/s", "sources": args.sources, "seconds": dt,
             "device_ms": ctx.last_kernel_ms, "finite": bool(np.all(np.isfinite(F)))}
+    bad = np.flatnonzero(~np.all(np.isfinite(F.reshape(args.sources, -1)), axis=1))
+    line["nonfinite_sources"] = int(bad.size)
     try:
         from oracle import gwat_ref
-        if gwat_ref.available():
+        if gwat_ref.available() and bad.size:
+            # sources whose Fisher matrix is not finite: does the reference agree?  (checked on up to 32 of them)
+            chk = bad[:32]
+            R = gwat_ref.fisher_numerical_batch(args.method, [srcs[int(i)] for i in chk], dets, f, psd, args.dim, order=4,
+                                                detector_index=-1, reference_index=0)
+            line["nonfinite_checked"] = int(chk.size)
+            line["nonfinite_in_reference_too"] = int(np.sum(~np.all(np.isfinite(R.reshape(chk.size, -1)), axis=1)))
+        if gwat_ref.available() and args.cpu_sample > 0:
             n = min(args.cpu_sample, args.sources)
             threads = max(1, len(os.sched_getaffinity(0)))
             t0 = time.perf_counter()
