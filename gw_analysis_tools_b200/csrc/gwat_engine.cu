@@ -257,6 +257,30 @@ __global__ void __launch_bounds__(kThreads) k_waveform(const WalkerCoef *__restr
 	if (hc_im) hc_im[k] = hc.im;
 }
 
+// Amplitude and phase of the (2,2) carrier of the IMRPhenomD families, as the reference's fourier_amplitude / fourier_phase
+// return them (IMRPhenomD::construct_amplitude / construct_phase, src/IMRPhenomD.cpp:604-740): amplitude A0 M^(7/6) x shape,
+// zero above 0.2/M; phase phi(f) - tc (f - f_ref) - phic at EVERY frequency (construct_phase applies no cutoff; it returns
+// the negative, and fourier_phase negates that again: src/waveform_generator.cpp:704-707).
+template <class Fam>
+__global__ void __launch_bounds__(kThreads) k_amp_phase(const WalkerCoef *__restrict__ coefs, GridPtrs g, double *amp_out, double *phase_out)
+{
+	__shared__ WalkerCoef w;
+	load_walker(coefs + blockIdx.y, w);
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= g.L) return;
+	double amp = NAN, phase = NAN;
+	if (w.valid) {
+		const double f = g.f[i];
+		MfPowers p;
+		phenomd_bin<Fam>(w.d, f, bin_sixth_root(w.d, g.sf_hi[i], g.sf_lo[i]), g.logf[i], amp, phase, p);
+		if (f > w.d.fcut) amp = 0.0;
+		phase = phenomd_apply_time_phase(w.d, f, phase);
+	}
+	const size_t k = (size_t)blockIdx.y * g.L + i;
+	if (amp_out) amp_out[k] = amp;
+	if (phase_out) phase_out[k] = phase;
+}
+
 // responses of detectors [d0, d0+nd) of the network; out shape [W][nd][L]
 template <class Fam>
 __global__ void __launch_bounds__(kThreads) k_response(const WalkerCoef *__restrict__ coefs, GridPtrs g, int d0, int nd,
@@ -1068,6 +1092,41 @@ int gwat_b200_fourier_waveform_batch(gwat_b200_ctx *ctx, const char *method, int
 	double *host[4] = {hplus_re, hplus_im, hcross_re, hcross_im};
 	for (int k = 0; k < 4; k++)
 		if (host[k]) CUDA_TRY(ctx, cudaMemcpyAsync(host[k], o + k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_fourier_amplitude_phase_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwat_b200_source *sources,
+                                            double *amplitude, double *phase)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && !sources)) return fail(ctx, GWAT_B200_ERR_ARG, "fourier_amplitude_phase_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	if (desc.pv2 || desc.nrt)
+		return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fourier_amplitude/phase: IMRPhenomD, ppE_IMRPhenomD_* and gIMRPhenomD only");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (int rc = setup_from_sources(ctx, desc, W, sources, st)) return rc;
+	const size_t n = (size_t)W * ctx->L;
+	if (grow(ctx, ctx->d_out, ctx->cap_out, 2 * n)) return GWAT_B200_ERR_CUDA;
+	double *o = ctx->d_out;
+	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const GridPtrs g = grid_ptrs(ctx);
+	switch (desc.family_id) {
+	case FAM_D: k_amp_phase<Family<BASE_D, PPE_NONE, false, false>><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n); break;
+	case FAM_D_PPE_INS: k_amp_phase<Family<BASE_D, PPE_INSPIRAL, false, false>><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n); break;
+	GWAT_FULL_ONLY(case FAM_D_PPE_IMR: k_amp_phase<Family<BASE_D, PPE_IMR, false, false>><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n); break;)
+	GWAT_FULL_ONLY(case FAM_D_GIMR: k_amp_phase<Family<BASE_D, PPE_NONE, true, false>><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n); break;)
+	default: return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fourier_amplitude/phase: family not supported");
+	}
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	if (amplitude) CUDA_TRY(ctx, cudaMemcpyAsync(amplitude, o, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	if (phase) CUDA_TRY(ctx, cudaMemcpyAsync(phase, o + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	return GWAT_B200_OK;
 }

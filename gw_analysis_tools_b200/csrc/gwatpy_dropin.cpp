@@ -325,6 +325,86 @@ int fourier_waveform_batch_py(double *frequencies, int length, int W, void **par
 	return report(S, rc) == 0 ? 1 : 0;
 }
 
+// ---- the plain-C waveform API (include/gwat/waveform_generator_C.h, src/waveform_generator_C.cpp) -----------------------------
+// Argument ORDER follows the definitions in src/waveform_generator_C.cpp:8-33 (phiRef, tc, f_ref) -- the header lists
+// (tc, f_ref, phiRef), but the compiled symbol is what callers bind to.  Every other gen_params member keeps its default.
+namespace {
+gwat_b200_source c_api_source(double mass1, double mass2, double DL, double s1x, double s1y, double s1z, double s2x, double s2y,
+                              double s2z, double incl_angle, double theta, double phi)
+{
+	gwat_b200_source s;
+	gwat_b200_source_init(&s);
+	s.mass1 = mass1;
+	s.mass2 = mass2;
+	s.Luminosity_Distance = DL;
+	s.spin1[0] = s1x; s.spin1[1] = s1y; s.spin1[2] = s1z;
+	s.spin2[0] = s2x; s.spin2[1] = s2y; s.spin2[2] = s2z;
+	s.incl_angle = incl_angle;
+	s.theta = theta;
+	s.phi = phi;
+	s.NSflag1 = s.NSflag2 = 0;
+	s.sky_average = 0;
+	return s;
+}
+void c_api_ppe(gwat_b200_source &s, const double *beta, const double *b, int Nmod)
+{
+	s.Nmod = Nmod < 0 ? 0 : (Nmod > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : Nmod);
+	for (int i = 0; i < s.Nmod; i++) {
+		if (beta) s.betappe[i] = beta[i];
+		if (b) s.bppe[i] = b[i];
+	}
+}
+}  // namespace
+
+int fourier_waveformC(double *frequencies, int length, double *waveform_plus_real, double *waveform_plus_imag,
+                      double *waveform_cross_real, double *waveform_cross_imag, char *generation_method, double mass1, double mass2,
+                      double DL, double spin1x, double spin1y, double spin1z, double spin2x, double spin2y, double spin2z,
+                      double phiRef, double tc, double f_ref, double *ppE_beta, double *ppE_b, int Nmod, double incl_angle,
+                      double theta, double phi)
+{
+	gwat_b200_source s = c_api_source(mass1, mass2, DL, spin1x, spin1y, spin1z, spin2x, spin2y, spin2z, incl_angle, theta, phi);
+	s.tc = tc;
+	s.phiRef = phiRef;
+	s.f_ref = f_ref;
+	c_api_ppe(s, ppE_beta, ppE_b, Nmod);
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
+	const int rc = gwat_b200_fourier_waveform_batch(S.ctx, generation_method, 1, &s, waveform_plus_real, waveform_plus_imag,
+	                                                waveform_cross_real, waveform_cross_imag);
+	return report(S, rc) == 0 ? 1 : 0;
+}
+
+int fourier_amplitudeC(double *frequencies, int length, double *amplitude, char *generation_method, double mass1, double mass2,
+                       double DL, double spin1x, double spin1y, double spin1z, double spin2x, double spin2y, double spin2z,
+                       double incl_angle, double theta, double phi)
+{
+	gwat_b200_source s = c_api_source(mass1, mass2, DL, spin1x, spin1y, spin1z, spin2x, spin2y, spin2z, incl_angle, theta, phi);
+	// the amplitude does not involve the time/phase reference (construct_amplitude never evaluates it); keep the record's
+	// phase fields out of the way so that an unset f_ref = 0 cannot invalidate the coefficient block
+	s.shift_time = 0;
+	s.shift_phase = 0;
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
+	return report(S, gwat_b200_fourier_amplitude_phase_batch(S.ctx, generation_method, 1, &s, amplitude, nullptr)) == 0 ? 1 : 0;
+}
+
+int fourier_phaseC(double *frequencies, int length, double *phase, char *generation_method, double mass1, double mass2, double DL,
+                   double spin1x, double spin1y, double spin1z, double spin2x, double spin2y, double spin2z, double tc, double f_ref,
+                   double phiRef, double *ppE_beta, double *ppE_b, int Nmod, double incl_angle, double theta, double phi)
+{
+	gwat_b200_source s = c_api_source(mass1, mass2, DL, spin1x, spin1y, spin1z, spin2x, spin2y, spin2z, incl_angle, theta, phi);
+	s.tc = tc;
+	s.phiRef = phiRef;
+	s.f_ref = f_ref;
+	c_api_ppe(s, ppE_beta, ppE_b, Nmod);
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
+	return report(S, gwat_b200_fourier_amplitude_phase_batch(S.ctx, generation_method, 1, &s, nullptr, phase)) == 0 ? 1 : 0;
+}
+
 // ---- noise curves and SNR (src/gwatpy_wrapping.cpp:59-69, 886-889) ----------------------------------------------------------
 // The tabulated curves are read from $GWAT_B200_NOISE_DIR (the directory GWAT installs as GWAT_SHARE_DIR/noise_data; in its
 // source tree data/noise_data/currently_supported).  integration_time only matters for the LISA confusion noise: unused.

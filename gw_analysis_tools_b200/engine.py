@@ -20,7 +20,7 @@ EXPORTS = [
     "gwat_b200_abi_version", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
     "gwat_b200_ctx_destroy", "gwat_b200_last_error", "gwat_b200_set_network", "gwat_b200_loglike_mcmc_batch",
     "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_loglike_maximized_batch",
-    "gwat_b200_fourier_waveform_batch",
+    "gwat_b200_fourier_waveform_batch", "gwat_b200_fourier_amplitude_phase_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
     "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare", "gwat_b200_gps_to_gmst_radian",
@@ -214,6 +214,13 @@ class Context:
         o = [np.empty((W, self.L)) for _ in range(4)]
         self._check(self._lib.gwat_b200_fourier_waveform_batch(self._h, method.encode(), W, arr, *[_p(x) for x in o]))
         return o[0] + 1j * o[1], o[2] + 1j * o[3]
+
+    def fourier_amplitude_phase_batch(self, method, sources):
+        """(amplitude[W][L], phase[W][L]) of the IMRPhenomD-family carrier: the reference's fourier_amplitude / fourier_phase."""
+        arr, W = _src_array(sources)
+        a, p = np.empty((W, self.L)), np.empty((W, self.L))
+        self._check(self._lib.gwat_b200_fourier_amplitude_phase_batch(self._h, method.encode(), W, arr, _p(a), _p(p)))
+        return a, p
 
     def coherent_response_batch(self, method, sources):
         arr, W = _src_array(sources)

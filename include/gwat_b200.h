@@ -243,6 +243,17 @@ int gwat_b200_fourier_waveform_batch(gwat_b200_ctx *ctx, const char *generation_
                                      double *hcross_re, double *hcross_im);
 
 /*
+ * W evaluations of fourier_amplitude<double> and fourier_phase<double> (src/waveform_generator.cpp:537-670, 672-814) for the
+ * IMRPhenomD family (IMRPhenomD, ppE_IMRPhenomD_Inspiral/_IMR and the theories mapped onto them, gIMRPhenomD):
+ * IMRPhenomD::construct_amplitude / construct_phase (src/IMRPhenomD.cpp:604-740).  amplitude/phase shape [W*L]; either may
+ * be NULL.  The amplitude is zero above 0.2/M; the phase, like the reference's, has no cutoff.  For the theory-mapped
+ * methods (dCS_, EdGB_ ...) the phase carries the mapped ppE term exactly as fourier_waveform does; the reference's deprecated
+ * four-argument fourier_phase silently returns the GR phase there.  Other families: GWAT_B200_ERR_UNSUPPORTED.
+ */
+int gwat_b200_fourier_amplitude_phase_batch(gwat_b200_ctx *ctx, const char *generation_method, int W,
+                                            const gwat_b200_source *sources, double *amplitude, double *phase);
+
+/*
  * W evaluations of create_coherent_GW_detection_reuse_WF (src/waveform_util.cpp:153-184): responses of all D detectors
  * of the network including the inter-detector time-of-arrival phase.  resp_re/im shape [W*D*L].
  */

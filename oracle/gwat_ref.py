@@ -178,6 +178,13 @@ def populate_noise(f, curve):
     return asd
 
 
+def fourier_amplitude_phase(method, src, f):
+    f = _f64(f)
+    a, p = np.zeros(f.size), np.zeros(f.size)
+    lib().oracle_ref_fourier_amplitude_phase(method.encode(), C.byref(src), _p(f), f.size, _p(a), _p(p))
+    return a, p
+
+
 def gps_to_gmst_radian(gps):
     fn = lib().oracle_ref_gps_to_gmst_radian
     fn.restype = C.c_double

@@ -551,6 +551,19 @@ int oracle_ref_losc(int D, const char *const *data_files, const char *psd_file, 
 	return 0;
 }
 
+// fourier_amplitude<double> / fourier_phase<double> (src/waveform_generator.cpp:537-670, 672-814)
+int oracle_ref_fourier_amplitude_phase(const char *method, const gwat_b200_source *src, const double *f, int L, double *amplitude,
+                                       double *phase)
+{
+	ParamBox b;
+	to_gen_params(*src, b);
+	if (amplitude) fourier_amplitude(const_cast<double *>(f), L, amplitude, std::string(method), &b.gp);
+	ParamBox b2;
+	to_gen_params(*src, b2);
+	if (phase) fourier_phase(const_cast<double *>(f), L, phase, std::string(method), &b2.gp);
+	return 0;
+}
+
 double oracle_ref_gps_to_gmst_radian(double gps) { return gps_to_GMST_radian(gps); }
 
 // calculate_snr (src/waveform_util.cpp:290-344): SNR of one template in one detector against a named noise curve.

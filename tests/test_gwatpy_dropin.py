@@ -21,7 +21,8 @@ ON_PATH_SYMBOLS = ["gen_params_base_py", "gen_params_base_py_destructor", "MCMC_
                    "detector_response_equatorial_py", "calculate_chirpmass_py", "calculate_eta_py", "calculate_mass1_py",
                    "calculate_mass2_py", "calculate_chirpmass_vectorized_py", "calculate_eta_vectorized_py",
                    "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py",
-                   "fourier_waveform_full_py", "populate_noise_py", "calculate_snr_py", "gps_to_GMST_radian_py"]
+                   "fourier_waveform_full_py", "populate_noise_py", "calculate_snr_py", "gps_to_GMST_radian_py",
+                   "fourier_waveformC", "fourier_amplitudeC", "fourier_phaseC"]
 
 
 def _lib():
@@ -66,7 +67,7 @@ def test_symbol_names_exist_in_reference_header_when_available():
     hdr = "/root/reference/include/gwat/gwatpy_wrapping.h"
     if not os.path.exists(hdr):
         pytest.skip("reference not mounted")
-    text = open(hdr).read()
+    text = open(hdr).read() + open("/root/reference/include/gwat/waveform_generator_C.h").read()
     for name in ON_PATH_SYMBOLS:
         if name == "MCMC_likelihood_extrinsic_batch_py":
             continue  # the one new entry point
@@ -156,3 +157,67 @@ def test_gwatpy_noise_snr_and_full_polarisations(oracle):
     assert all(not x.any() for x in o[4:])  # no vector / scalar polarisations in these models
     assert lib.gps_to_GMST_radian_py(C.c_double(1126259462.4)) == oracle.gps_to_gmst_radian(1126259462.4)
     lib.gen_params_base_py_destructor(C.c_void_p(gp))
+
+
+AMP_PHASE_CASES = [c for c in cases.CASES if c[0] in ("D_bbh", "D_low", "D_q8", "D_noshift", "ppE_ins", "ppE_imr", "gIMR", "gIMR_log")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", AMP_PHASE_CASES, ids=[c[0] for c in AMP_PHASE_CASES])
+def test_fourier_amplitude_and_phase_vs_reference(ctx, oracle, case):
+    """gwat_b200_fourier_amplitude_phase_batch against the reference's fourier_amplitude / fourier_phase (IMRPhenomD family)."""
+    name, method, kw, gspec = case
+    f = cases.grid(gspec)
+    src = cases.source(kw)
+    ctx.set_network(["Hanford"], f, np.ones((1, f.size)))
+    a, p = ctx.fourier_amplitude_phase_batch(method, [src, src])
+    ra, rp = oracle.fourier_amplitude_phase(method, src, f)
+    assert np.array_equal(a[0], a[1]) and np.array_equal(p[0], p[1])
+    assert np.abs(a[0] - ra).max() <= 1e-10 * ra.max()
+    assert np.array_equal(a[0] == 0, ra == 0)  # same cutoff bin
+    # phases reach 1e4..1e5 rad: 1e-10 relative to the largest, i.e. <= 1e-5 rad absolute would be loose; ask for 1e-9 rad
+    assert np.abs(p[0] - rp).max() <= 1e-9
+
+
+@pytest.mark.gpu
+def test_plain_c_waveform_api(oracle):
+    """fourier_waveformC / fourier_amplitudeC / fourier_phaseC with the argument order of src/waveform_generator_C.cpp."""
+    lib = _lib()
+    f = cases.grid(cases.GRID_BBH)
+    L = f.size
+    kw = dict(cases.BBH)
+    src = cases.source(dict(kw, psi=0.0, RA=0.0, DEC=0.0, gmst=0.0))
+    d = C.c_double
+    s1, s2 = kw["spin1"], kw["spin2"]
+    o = [np.zeros(L) for _ in range(4)]
+    assert lib.fourier_waveformC(_p(f), L, *[_p(x) for x in o], b"IMRPhenomD", d(kw["mass1"]), d(kw["mass2"]), d(kw["Luminosity_Distance"]),
+                                 d(s1[0]), d(s1[1]), d(s1[2]), d(s2[0]), d(s2[1]), d(s2[2]), d(kw["phiRef"]), d(kw["tc"]), d(kw["f_ref"]),
+                                 None, None, 0, d(kw["incl_angle"]), d(0.0), d(0.0)) == 1
+    hp, hc = oracle.fourier_waveform("IMRPhenomD", src, f)
+    assert np.abs(o[0] + 1j * o[1] - hp).max() <= 1e-10 * np.abs(hp).max()
+    assert np.abs(o[2] + 1j * o[3] - hc).max() <= 1e-10 * np.abs(hc).max()
+    ra, rp = oracle.fourier_amplitude_phase("IMRPhenomD", src, f)
+    a, p = np.zeros(L), np.zeros(L)
+    assert lib.fourier_amplitudeC(_p(f), L, _p(a), b"IMRPhenomD", d(kw["mass1"]), d(kw["mass2"]), d(kw["Luminosity_Distance"]),
+                                  d(s1[0]), d(s1[1]), d(s1[2]), d(s2[0]), d(s2[1]), d(s2[2]), d(kw["incl_angle"]), d(0.0), d(0.0)) == 1
+    assert lib.fourier_phaseC(_p(f), L, _p(p), b"IMRPhenomD", d(kw["mass1"]), d(kw["mass2"]), d(kw["Luminosity_Distance"]),
+                              d(s1[0]), d(s1[1]), d(s1[2]), d(s2[0]), d(s2[1]), d(s2[2]), d(kw["tc"]), d(kw["f_ref"]), d(kw["phiRef"]),
+                              None, None, 0, d(kw["incl_angle"]), d(0.0), d(0.0)) == 1
+    assert np.abs(a - ra).max() <= 1e-10 * ra.max()
+    assert np.abs(p - rp).max() <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["dCS", "EdGB", "D_bbh"])
+def test_amplitude_and_phase_are_the_waveforms_carrier(ctx, name):
+    """h+ = (1 + cos^2 i)/2 A exp(-i phase) with the amplitude and phase this entry point returns -- also for the theory-mapped
+    methods, where the reference's deprecated fourier_phase silently drops the mapped ppE term (its dCS phase equals the GR one)."""
+    _, method, kw, gspec = [c for c in cases.CASES if c[0] == name][0]
+    f = cases.grid(gspec)
+    src = cases.source(kw)
+    ctx.set_network(["Hanford"], f, np.ones((1, f.size)))
+    a, p = ctx.fourier_amplitude_phase_batch(method, [src])
+    hp, hc = ctx.fourier_waveform_batch(method, [src])
+    ci = np.cos(kw["incl_angle"])
+    want = 0.5 * (1 + ci * ci) * a[0] * np.exp(-1j * p[0])
+    assert np.abs(want - hp[0]).max() <= 1e-10 * np.abs(hp[0]).max()
