@@ -85,6 +85,32 @@ GWAT_HD void polarizations_bin(const WalkerCoef &w, double f, double sf_hi, doub
 	polarizations_finish<Fam>(w, pp, walker_time_coefficient<Fam>(w), f, hp, hc);
 }
 
+// fourier_amplitude / fourier_phase values of one bin for the IMRPhenomD families (construct_amplitude / construct_phase,
+// src/IMRPhenomD.cpp:604-740): amplitude zero above 0.2/M, phase -(phi - tc (f - f_ref) - phic) with no cutoff.
+template <class Fam>
+GWAT_HD void amplitude_phase_bin(const WalkerCoef &w, double f, double sf_hi, double sf_lo, double logf, double &amp, double &phase)
+{
+	MfPowers p;
+	phenomd_bin<Fam>(w.d, f, bin_sixth_root(w.d, sf_hi, sf_lo), logf, amp, phase, p);
+	if (f > w.d.fcut) amp = 0.0;
+	phase = -phenomd_apply_time_phase(w.d, f, phase);
+}
+
+// One bin of the sky-averaged derivative (calculate_derivatives, src/fisher.cpp:183-338): central differences of amplitude
+// and phase; order 2 forms dA + i A dphi, order 4 dA - i A dphi (as the reference has it; the Fisher matrix does not
+// depend on that sign).  a[k], ph[k]: the stencil points (+eps, -eps, +2eps, -2eps); amp0: the unperturbed amplitude.
+GWAT_HD cplx sky_derivative_bin(int npts, const double *a, const double *ph, double amp0)
+{
+	const double epsilon = 1e-8;
+	if (npts == 2) {
+		const double da = (a[0] - a[1]) / (2 * epsilon), dp = (ph[0] - ph[1]) / (2 * epsilon);
+		return cplx{da, dp * amp0};
+	}
+	const double da = (((-a[2] + 8. * a[0]) - 8. * a[1]) + a[3]) / (12. * epsilon);
+	const double dp = (((-ph[2] + 8. * ph[0]) - 8. * ph[1]) + ph[3]) / (12. * epsilon);
+	return cplx{da, -(dp * amp0)};
+}
+
 // Response of detector d including the arrival-time phase (create_coherent_GW_detection_reuse_WF semantics);
 // with_shift = false gives fourier_detector_response semantics.
 GWAT_HD cplx project_bin(const DetCoef &dc, cplx hp, cplx hc, double f, bool with_shift)

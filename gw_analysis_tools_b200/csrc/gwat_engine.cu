@@ -467,6 +467,71 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 	}
 }
 
+// ---- sky-averaged Fisher (calculate_derivatives, src/fisher.cpp:183-338) ---------------------------------------------------
+// IMRPhenomD in the 7-parameter set ln A0, phic, tc, ln Mc, ln eta, chi_s, chi_a: derivatives of amplitude and phase instead
+// of the detector response.  One coefficient block per (source, parameter, stencil point) plus one for the unperturbed
+// source (the reference multiplies the phase derivative by the UNPERTURBED amplitude, :187-190, 303-320).
+template <class Fam>
+__global__ void __launch_bounds__(128) k_fisher_setup_sky(const gwat_b200_source *__restrict__ src, int S, FisherPlan fp,
+                                                         WalkerCoef *__restrict__ coefs, double *__restrict__ scale)
+{
+	const int dim = fp.rp.dimension, nblk = fp.npts + 1;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= S * dim * nblk) return;
+	const int k = t % nblk, i = (t / nblk) % dim, sidx = t / (nblk * dim);
+	const double epsilon = 1e-8;
+	const gwat_b200_source orig = src[sidx];
+	gwat_b200_source sp = orig;
+	if (k < fp.npts) {
+		double v[GWAT_B200_MAX_DIM];
+		int logfac[GWAT_B200_MAX_DIM];
+		unpack_fisher(orig, fp.rp, v, logfac);
+		if (k == 0) scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
+		v[i] += (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
+		repack_fisher_point(v, orig, fp.rp, sp);
+	}
+	Network net;
+	net.D = 1;
+	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[0][j];
+	WalkerCoef wc;
+	walker_setup<Fam>(sp, net, device_tables(), fp.theory, wc, true);
+	wc.valid = coef_is_finite(wc, 1, false) ? 1 : 0;
+	coefs[t] = wc;
+}
+
+template <class Fam>
+__global__ void __launch_bounds__(kThreads) k_fisher_deriv_sky(const WalkerCoef *__restrict__ coefs, GridPtrs g, int npts, int dim,
+                                                              const double *__restrict__ scale, double *__restrict__ dre,
+                                                              double *__restrict__ dim_, int *__restrict__ bin_limit)
+{
+	__shared__ WalkerCoef w[5];
+	{
+		const double *sp = reinterpret_cast<const double *>(coefs + (size_t)blockIdx.y * (npts + 1));
+		double *dp = reinterpret_cast<double *>(&w[0]);
+		for (int i = threadIdx.x; i < (int)((npts + 1) * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
+		__syncthreads();
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&bin_limit[blockIdx.y / dim], g.L);  // the phase has no cutoff: every bin counts
+	const int bin = blockIdx.x * kThreads + threadIdx.x;
+	if (bin >= g.L) return;
+	const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
+	cplx dv{NAN, NAN};
+	bool ok = w[npts].valid != 0;
+	for (int k = 0; k < npts; k++) ok = ok && w[k].valid;
+	if (ok) {
+		double a[4], ph[4], a0, p0;
+		amplitude_phase_bin<Fam>(w[npts], f, hi, lo, lg, a0, p0);
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (k < npts) amplitude_phase_bin<Fam>(w[k], f, hi, lo, lg, a[k], ph[k]);
+		dv = sky_derivative_bin(npts, a, ph, a0);
+	}
+	const double sc = scale[blockIdx.y];
+	const size_t o = (size_t)blockIdx.y * g.L + bin;
+	dre[o] = dv.re * sc;
+	dim_[o] = dv.im * sc;
+}
+
 // F_jk = sum_d prefactor * sum_bins coef_d * Re(d_j conj(d_k)) / S_d   (calculate_fisher_elements, src/fisher.cpp:2704-2781, and the
 // detector loop of the callers: one partial Fisher per detector, added in detector order)
 __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__restrict__ dre, const double *__restrict__ dim_,
@@ -809,6 +874,28 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 	                                                                         ctx->d_bc, dre, dim_, ctx->d_binlim));
 	k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d0 * ctx->ld, ctx->ld, L, dim, ns, nd,
 	                                                          ctx->pref_fisher, ctx->d_binlim, ctx->d_fisher);
+	ctx->launches += 3;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return 0;
+}
+
+// Sky-averaged pass: ctx->d_src[0..ns) -> ctx->d_fisher[ns][7][7] for the PSD of detector `det`.
+int fisher_chunk_sky(gwat_b200_ctx *ctx, FisherPlan &fp, int ns, int chunk, int det, cudaStream_t st)
+{
+	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
+	const int L = ctx->L, dim = fp.rp.dimension;
+	const GridPtrs g = grid_ptrs(ctx);
+	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
+	fp.nd = 1;
+	std::memcpy(fp.det_row[0], ctx->net.row[det], sizeof(fp.det_row[0]));
+	const int nthreads = ns * dim * (fp.npts + 1);
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_binlim, 0, sizeof(int) * ns, st));
+	k_fisher_setup_sky<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef, ctx->d_scale);
+	double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L;
+	k_fisher_deriv_sky<Fam><<<dim3((L + kThreads - 1) / kThreads, ns * dim), kThreads, 0, st>>>(ctx->d_coef, g, fp.npts, dim, ctx->d_scale,
+	                                                                                           dre, dim_, ctx->d_binlim);
+	k_fisher_assemble<<<dim3(dim * (dim + 1) / 2, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)det * ctx->ld, ctx->ld, L, dim, ns, 1,
+	                                                                    ctx->pref_fisher, ctx->d_binlim, ctx->d_fisher);
 	ctx->launches += 3;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -1248,7 +1335,42 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	MethodDesc desc;
 	if (parse_method(method, desc) != 0)
 		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
-	if (sources[0].sky_average) return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers are outside this path");
+	bool any_sky = false, all_sky = true;
+	for (int i = 0; i < S; i++) {
+		any_sky = any_sky || sources[i].sky_average != 0;
+		all_sky = all_sky && sources[i].sky_average != 0;
+	}
+	if (any_sky) {
+		// sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): IMRPhenomD, 7 parameters, one detector's PSD
+		if (!all_sky) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: sky-averaged and pointed sources in one batch");
+		if (desc.family_id != FAM_D || desc.theory != THEORY_NONE || desc.mcmc || dimension != 7)
+			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers are built for IMRPhenomD, dimension 7");
+		if (detector_index < 0) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: a sky-averaged Fisher needs one detector's PSD");
+		FisherPlan fp;
+		std::memset(&fp, 0, sizeof(fp));
+		fp.rp.dimension = 7;
+		fp.rp.sky = 1;
+		fp.npts = order == 4 ? 4 : 2;
+		fp.theory = THEORY_NONE;
+		std::lock_guard<std::mutex> lock(ctx->mu);
+		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+		cudaStream_t st = ctx->stream;
+		const int chunk = fisher_chunk_size(ctx, S, 7, 1);
+		if (int rc = fisher_reserve(ctx, chunk, 7, fp.npts + 1, 1)) return rc;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+		for (int s0 = 0; s0 < S; s0 += chunk) {
+			const int ns = std::min(chunk, S - s0);
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, sources + s0, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, st));
+			if (int rc = fisher_chunk_sky(ctx, fp, ns, chunk, detector_index, st)) return rc;
+			CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * 49, ctx->d_fisher, sizeof(double) * ns * 49, cudaMemcpyDeviceToHost, st));
+		}
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		float ms = 0;
+		CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		ctx->last_ms = ms;
+		return GWAT_B200_OK;
+	}
 	// the modification layout is taken from the first source (all sources of a batch share it, as they share the method)
 	gwat_b200_mod mod;
 	gwat_b200_mod_init(&mod);

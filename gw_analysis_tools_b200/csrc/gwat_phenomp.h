@@ -411,7 +411,8 @@ GWAT_HD void phenomp_polarizations_bin(const WalkerCoef &w, double f, double sf_
 
 // ---- one walker, start to finish (all families) ---------------------------------------------------------------------
 template <class Fam>
-GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const Tables &t, int theory, WalkerCoef &w)
+GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const Tables &t, int theory, WalkerCoef &w,
+                          bool allow_sky_average = false)
 {
 	SrcQ s;
 	populate_source(src, s);
@@ -446,7 +447,9 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 	}
 	// options of the reference that are outside this path are refused loudly (NaN), never silently approximated:
 	// horizon/equatorial-orientation inputs, sky-averaged amplitudes, and the wall-clock-seeded tidal_love_error draw
-	if (src.horizon_coord || src.equatorial_orientation || src.sky_average || (Fam::nrt && src.tidal_love_error)) w.d.A0 = NAN;
+	// (sky-averaged amplitudes are accepted only from the sky-averaged Fisher path, which uses amplitude and phase alone)
+	if (src.horizon_coord || src.equatorial_orientation || (src.sky_average && !allow_sky_average) || (Fam::nrt && src.tidal_love_error))
+		w.d.A0 = NAN;
 	w.valid = 1;
 }
 

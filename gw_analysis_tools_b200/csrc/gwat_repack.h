@@ -23,6 +23,7 @@ struct RepackPlan {
 	int gimr;           // last (phi+sigma+beta+alpha) entries are fractional deviations
 	int alpha_unit_fix; // dCS/EdGB: entry [base] is sqrt(alpha) in km -> alpha^2 in s^4 (src/mcmc_gw.cpp:2560-2565)
 	int mcmc;           // "MCMC_" parameterisation (sin DEC, cos iota, ln DL, ln Mc); else the physical one
+	int sky;            // sky-averaged IMRPhenomD set: ln A0, phic, tc, ln Mc, ln eta, chi_s, chi_a (src/fisher.cpp:40, 2015-2032)
 	gwat_b200_mod mod;
 };
 
@@ -195,10 +196,28 @@ GWAT_HD double eta_from(double m1, double m2) { return (m1 * m2) / ((m1 + m2) * 
 
 // unpack_parameters, non-sky-averaged branches (src/fisher.cpp:1843-1966, 2038-2160).  `logf[i]` != 0 marks the
 // parameters whose derivative is multiplied by the parameter itself afterwards (d/d ln x).
+// A0_from_DL / DL_from_A0 (src/util.cpp:1269-1295): the same expression both ways round, in seconds
+GWAT_HD double a0_dl_conversion(double chirpmass_sec, double other, bool sky_average)
+{
+	const double pref = sky_average ? sqrt(GWAT_PI / 30) : sqrt(GWAT_PI * 40. / 192.);
+	return pref * chirpmass_sec * chirpmass_sec / other * sm::pow(GWAT_PI * chirpmass_sec, -7. / 6);
+}
+
 GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, double *v, int *logfac)
 {
 	const int dim = plan.dimension;
 	for (int i = 0; i < dim; i++) logfac[i] = 0;
+	if (plan.sky) {  // src/fisher.cpp:2015-2032
+		logfac[0] = logfac[3] = logfac[4] = 1;
+		v[3] = chirpmass_from(in.mass1, in.mass2);
+		v[0] = a0_dl_conversion(v[3] * GWAT_MSOL_SEC, in.Luminosity_Distance * GWAT_MPC_SEC, in.sky_average != 0);
+		v[1] = in.phiRef;
+		v[2] = in.tc;
+		v[4] = eta_from(in.mass1, in.mass2);
+		v[5] = (in.spin1[2] + in.spin2[2]) / 2.;
+		v[6] = (in.spin1[2] - in.spin2[2]) / 2.;
+		return;
+	}
 	v[0] = in.RA;
 	v[2] = in.psi;
 	v[4] = in.phiRef;
@@ -295,6 +314,16 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		}
 	}
 	// repack_parameters
+	if (plan.sky) {  // src/fisher.cpp:2379-2393
+		s.mass1 = mass1_of(v[3], v[4]);
+		s.mass2 = mass2_of(v[3], v[4]);
+		s.Luminosity_Distance = a0_dl_conversion(v[3] * GWAT_MSOL_SEC, v[0], s.sky_average != 0) / GWAT_MPC_SEC;
+		s.tc = v[2];
+		s.phiRef = v[1];
+		s.spin1[2] = v[5] + v[6];
+		s.spin2[2] = v[5] - v[6];
+		return;
+	}
 	s.RA = v[0];
 	s.psi = v[2];
 	s.phiRef = v[4];

@@ -278,6 +278,9 @@ int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *ge
  *   reference_index      the detector tc refers to (the reference's reference_detector)
  *   fisher[S*dim*dim]    out, row-major per source
  * With detector_index < 0 the matrices of all detectors are summed (MCMC_fisher_wrapper, src/mcmc_gw.cpp:2298-2312).
+ * Sources with sky_average set take the sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): "IMRPhenomD",
+ * dimension 7 (ln A0, phic, tc, ln chirpmass, ln eta, chi_s, chi_a), derivatives of amplitude and phase, detector_index >= 0
+ * naming the PSD; all sources of a batch must agree on the flag.
  */
 int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *generation_method, int detector_index,
                                      int reference_index, int dimension, int order, int S,

@@ -169,6 +169,49 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 	const int npts = order == 4 ? 4 : 2;
 	const size_t L = g.f.size();
 	const double eps = 1e-8;
+	if (src->sky_average) {
+		// sky-averaged branch (src/fisher.cpp:183-338): amplitude / phase derivatives in the 7-parameter set
+		if (Fam::base != BASE_D || Fam::nrt || dim != 7) return -5;
+		plan.sky = 1;
+		double v0s[GWAT_B200_MAX_DIM];
+		int logf_[GWAT_B200_MAX_DIM];
+		unpack_fisher(*src, plan, v0s, logf_);
+		Network net;
+		net.D = 1;
+		std::memcpy(net.row[0], det_row, sizeof(double) * 13);
+		WalkerCoef w0;
+		walker_setup<Fam>(*src, net, host_tables(), theory, w0, true);
+		std::vector<std::vector<cplx>> deriv(dim, std::vector<cplx>(L));
+		for (int i = 0; i < dim; i++) {
+			WalkerCoef wk[4];
+			for (int k = 0; k < npts; k++) {
+				double v[GWAT_B200_MAX_DIM];
+				for (int j = 0; j < dim; j++) v[j] = v0s[j];
+				v[i] = v0s[i] + ((k == 0) ? eps : (k == 1) ? -eps : (k == 2) ? 2 * eps : -2 * eps);
+				gwat_b200_source sp;
+				repack_fisher_point(v, *src, plan, sp);
+				walker_setup<Fam>(sp, net, host_tables(), theory, wk[k], true);
+			}
+			const double sc = logf_[i] ? v0s[i] : 1.0;
+			for (size_t b = 0; b < L; b++) {
+				double a[4], ph[4], a0, p0;
+				amplitude_phase_bin<Fam>(w0, g.f[b], g.hi[b], g.lo[b], g.lg[b], a0, p0);
+				for (int k = 0; k < npts; k++) amplitude_phase_bin<Fam>(wk[k], g.f[b], g.hi[b], g.lo[b], g.lg[b], a[k], ph[k]);
+				const cplx d = sky_derivative_bin(npts, a, ph, a0);
+				deriv[i][b] = cplx{d.re * sc, d.im * sc};
+			}
+		}
+		const double pref = quadrature_prefactor((int)L, false, g.f.data(), true);
+		for (int j = 0; j < dim; j++)
+			for (int k = 0; k <= j; k++) {
+				double acc = 0;
+				for (size_t b = 0; b < L; b++)
+					acc += quadrature_coefficient((int)b, (int)L, false, false, nullptr, g.f.data()) *
+					       ((deriv[j][b].re * deriv[k][b].re + deriv[j][b].im * deriv[k][b].im) / psd[b]);
+				out[j * dim + k] = out[k * dim + j] = pref * acc;
+			}
+		return 0;
+	}
 	double v0[GWAT_B200_MAX_DIM];
 	int logfac[GWAT_B200_MAX_DIM];
 	unpack_fisher(*src, plan, v0, logfac);
