@@ -1,10 +1,10 @@
 #!/bin/bash
 # ncu --set full of the Fisher derivative and assembly kernels (cfg3 shape), and a sky-averaged Fisher throughput line
 O=gpurun_out/r2s; mkdir -p $O /tmp/prof
-ncu --set full --clock-control none --import-source on -k regex:k_fisher_deriv -s 2 -c 1 -o /tmp/prof/fisher_deriv -f python tools/bench_fisher.py --sources 2048 --bins 4096 --cpu-sample 0 > $O/ncu_deriv.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_fisher_deriv -s 0 -c 1 -o /tmp/prof/fisher_deriv -f python tools/bench_fisher.py --sources 2048 --bins 4096 --cpu-sample 0 > $O/ncu_deriv.log 2>&1
 ncu -i /tmp/prof/fisher_deriv.ncu-rep --page raw --csv > $O/fisher_deriv_raw.csv 2>/dev/null
 ncu -i /tmp/prof/fisher_deriv.ncu-rep --page details --csv > $O/fisher_deriv_details.csv 2>/dev/null
-ncu --set full --clock-control none -k regex:k_fisher_assemble -s 2 -c 1 -o /tmp/prof/fisher_asm -f python tools/bench_fisher.py --sources 2048 --bins 4096 --cpu-sample 0 > $O/ncu_asm.log 2>&1
+ncu --set full --clock-control none -k regex:k_fisher_assemble -s 0 -c 1 -o /tmp/prof/fisher_asm -f python tools/bench_fisher.py --sources 2048 --bins 4096 --cpu-sample 0 > $O/ncu_asm.log 2>&1
 ncu -i /tmp/prof/fisher_asm.ncu-rep --page raw --csv > $O/fisher_assemble_raw.csv 2>/dev/null
 python - <<'PY'
 import time, json, numpy as np, sys
