@@ -56,6 +56,8 @@ constexpr int kThreads = 256;
 constexpr int kLikeThreads = GWAT_LOGLIKE_THREADS;
 // one warp per CTA: the per-walker setup is a long dependent FP64 chain, so it is spread over as many SMs as possible
 constexpr int kSetupThreads = 32;
+// bin tiles (of kThreads bins) one CTA of the Fisher derivative kernel evaluates with one staging of its coefficient blocks
+constexpr int kFisherTilesPerCta = 4;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -378,21 +380,31 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 {
 	__shared__ WalkerCoef w[4];
 	__shared__ double tc_s[4][5];
+	const int ntiles = (g.L + kThreads - 1) / kThreads;
+	const int tile0 = blockIdx.x * kFisherTilesPerCta, tile1 = min(ntiles, tile0 + kFisherTilesPerCta);
+	auto zero_tile = [&](int t) {
+		const int bin = t * kThreads + threadIdx.x;
+		if (bin < g.L)
+			for (int d = 0; d < nd; d++) {
+				const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+				dre[o] = 0.0;
+				dim_[o] = 0.0;
+			}
+	};
+	// ascending grid: a tile that starts above the cutoff of every stencil point is exactly zero -- decided from a few words
+	// of the coefficient records before anything is staged (about half of the tiles of a BBH population end here)
+	double fmax_all = INFINITY;
 	if (g.uniform) {
-		// ascending grid: a tile that starts above the cutoff of every stencil point is exactly zero -- decided from a few words
-		// of the coefficient records before anything is staged (about half of the tiles of a BBH population end here)
 		const WalkerCoef *wg = coefs + (size_t)blockIdx.y * npts;
-		const double f0 = g.f[blockIdx.x * kThreads];
-		bool dead = true;
-		for (int k = 0; k < npts; k++) dead = dead && wg[k].valid && f0 > walker_fmax<Fam>(wg[k]);
-		if (dead) {
-			const int bin = blockIdx.x * kThreads + threadIdx.x;
-			if (bin < g.L)
-				for (int d = 0; d < nd; d++) {
-					const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
-					dre[o] = 0.0;
-					dim_[o] = 0.0;
-				}
+		bool all_valid = true;
+		double fm = 0.0;
+		for (int k = 0; k < npts; k++) {
+			all_valid = all_valid && wg[k].valid;
+			fm = fmax(fm, walker_fmax<Fam>(wg[k]));
+		}
+		if (all_valid) fmax_all = fm;
+		if (g.f[tile0 * kThreads] > fmax_all) {
+			for (int t = tile0; t < tile1; t++) zero_tile(t);
 			return;
 		}
 	}
@@ -403,67 +415,74 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 		if (threadIdx.x < npts * nd) tc_s[threadIdx.x / nd][threadIdx.x % nd] = tcoef[(size_t)blockIdx.y * npts * nd + threadIdx.x];
 		__syncthreads();
 	}
-	const int bin_raw = blockIdx.x * kThreads + threadIdx.x;
-	const bool in_grid = bin_raw < g.L;
-	const int bin = in_grid ? bin_raw : g.L - 1;  // (tail threads shadow the last bin and store nothing: no early return before the barrier below)
-	const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
 	// parameters 0..2 are RA, DEC (or sin DEC) and psi in every parameterisation (src/fisher.cpp:46-66): the intrinsic part of
 	// the source, and with it everything in PolParts, is bit-identical at all stencil points
 	const bool shared_parts = (int)(blockIdx.y % dim) < 3;
-	PolParts pp[4];
-#pragma unroll
-	for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
-		if (k >= npts) continue;
-		if (k > 0 && shared_parts) pp[k] = pp[0];
-		else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
-	}
-	// Bins above every stencil point's cutoff have exactly zero responses: nothing to evaluate, and k_fisher_assemble need not
-	// read them -- the highest live bin of each source is recorded (one atomic per CTA).  Invalid points (NaN) keep every bin.
-	bool live = false;
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		if (k < npts) live = live || !w[k].valid || !pp[k].zero;
-	const int any_live = __syncthreads_or(live && in_grid);
-	if (threadIdx.x == 0 && any_live) atomicMax(&bin_limit[blockIdx.y / dim], min(g.L, (int)(blockIdx.x + 1) * kThreads));
-	if (!in_grid) return;
-	if (!live) {
-		for (int d = 0; d < nd; d++) {
-			const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
-			dre[o] = 0.0;
-			dim_[o] = 0.0;
-		}
-		return;
-	}
 	const double epsilon = 1e-8;
 	const bool bc = eta_bc[blockIdx.y] != 0;
 	const double sc = scale[blockIdx.y];
-	for (int d = 0; d < nd; d++) {
-		cplx r[4];
+	// several tiles per CTA: the 4 coefficient blocks (5.7 KB) are staged once for 1024 bins instead of once per 256
+	for (int t = tile0; t < tile1; t++) {
+		if (g.f[t * kThreads] > fmax_all) {  // (the same for the whole CTA)
+			zero_tile(t);
+			continue;
+		}
+		const int bin_raw = t * kThreads + threadIdx.x;
+		const bool in_grid = bin_raw < g.L;
+		const int bin = in_grid ? bin_raw : g.L - 1;  // (tail threads shadow the last bin and store nothing: everyone reaches the barrier below)
+		const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
+		PolParts pp[4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) {
+		for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
 			if (k >= npts) continue;
-			if (!w[k].valid) {
-				r[k] = cplx{NAN, NAN};
-				continue;
+			if (k > 0 && shared_parts) pp[k] = pp[0];
+			else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
+		}
+		// Bins above every stencil point's cutoff have exactly zero responses: nothing to evaluate, and k_fisher_assemble need
+		// not read them -- the highest live bin of each source is recorded (one atomic per tile).  Invalid points (NaN) keep every bin.
+		bool live = false;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (k < npts) live = live || !w[k].valid || !pp[k].zero;
+		const int any_live = __syncthreads_or(live && in_grid);
+		if (threadIdx.x == 0 && any_live) atomicMax(&bin_limit[blockIdx.y / dim], min(g.L, (t + 1) * kThreads));
+		if (!in_grid) continue;
+		if (!live) {
+			for (int d = 0; d < nd; d++) {
+				const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+				dre[o] = 0.0;
+				dim_[o] = 0.0;
 			}
-			// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8 instead
-			// of 12 finishes for three detectors -- measured 11 % slower: 40 more live registers)
-			cplx hp, hc;
-			polarizations_finish<Fam>(w[k], pp[k], tc_s[k][d], f, hp, hc);
-			r[k] = project_bin(w[k].det[d], hp, hc, f, true);
+			continue;
 		}
-		cplx dv;
-		if (npts == 2) {
-			const double den = bc ? epsilon : 2. * epsilon;
-			dv = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
-		} else {
-			const double den = bc ? 6. * epsilon : 12. * epsilon;
-			dv = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
-			          (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
+		for (int d = 0; d < nd; d++) {
+			cplx r[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				if (k >= npts) continue;
+				if (!w[k].valid) {
+					r[k] = cplx{NAN, NAN};
+					continue;
+				}
+				// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8
+				// instead of 12 finishes for three detectors -- measured 11 % slower: 40 more live registers)
+				cplx hp, hc;
+				polarizations_finish<Fam>(w[k], pp[k], tc_s[k][d], f, hp, hc);
+				r[k] = project_bin(w[k].det[d], hp, hc, f, true);
+			}
+			cplx dv;
+			if (npts == 2) {
+				const double den = bc ? epsilon : 2. * epsilon;
+				dv = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
+			} else {
+				const double den = bc ? 6. * epsilon : 12. * epsilon;
+				dv = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
+				          (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
+			}
+			const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+			dre[o] = dv.re * sc;
+			dim_[o] = dv.im * sc;
 		}
-		const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
-		dre[o] = dv.re * sc;
-		dim_[o] = dv.im * sc;
 	}
 }
 
@@ -868,7 +887,8 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef, ctx->d_tcoef,
 	                                                                                        ctx->d_scale, ctx->d_bc));
 	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_binlim, 0, sizeof(int) * ns, st));
-	const dim3 gd((L + kThreads - 1) / kThreads, ns * dim);
+	const int ntiles = (L + kThreads - 1) / kThreads;
+	const dim3 gd((ntiles + kFisherTilesPerCta - 1) / kFisherTilesPerCta, ns * dim);
 	double *dre = ctx->d_deriv, *dim_ = ctx->d_deriv + (size_t)chunk * dim * L * nd;
 	GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, ctx->d_tcoef, g, fp.npts, nd, dim, ctx->d_scale,
 	                                                                         ctx->d_bc, dre, dim_, ctx->d_binlim));
