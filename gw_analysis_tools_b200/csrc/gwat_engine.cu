@@ -812,9 +812,12 @@ int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_log
 
 int collect_stats(gwat_b200_ctx *ctx, cudaStream_t st)
 {
-	unsigned long long act = 0;
-	CUDA_TRY(ctx, cudaMemcpyAsync(&act, ctx->d_active, sizeof(act), cudaMemcpyDeviceToHost, st));
+	// the active-bin count lands in a pinned word of the context: an asynchronous copy behind the caller's own result copy, one
+	// synchronisation for both (a pageable destination would make this copy a second, blocking round trip)
+	if (!ctx->h_active) CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->h_active, sizeof(unsigned long long), cudaHostAllocDefault));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_active, ctx->d_active, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	const unsigned long long act = *ctx->h_active;
 	float ms = 0;
 	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = ms;
@@ -1010,6 +1013,7 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 	cudaFree(c->d_src);
 	cudaFree(c->d_active);
 	cudaFree(c->d_zero);
+	if (c->h_active) cudaFreeHost(c->h_active);
 	cudaFree(c->d_tcoef);
 	cudaFree(c->d_binlim);
 	cudaFree(c->d_deriv);

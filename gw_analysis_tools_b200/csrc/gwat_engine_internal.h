@@ -45,6 +45,7 @@ struct gwat_b200_ctx {
 	double *d_out = nullptr;
 	gwat_b200_source *d_src = nullptr;
 	unsigned long long *d_active = nullptr;
+	unsigned long long *h_active = nullptr;  // pinned host word the active-bin count is copied into
 	double *d_zero = nullptr;  // D*ld zeros: the strain seen by gwat_b200_snr_batch
 	size_t cap_zero = 0;
 	size_t cap_deriv = 0, cap_scale = 0, cap_fisher = 0, cap_bc = 0, cap_tcoef = 0;
