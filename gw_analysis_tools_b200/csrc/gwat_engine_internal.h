@@ -29,7 +29,7 @@ struct gwat_b200_ctx {
 	std::mutex mu;
 	// network
 	int D = 0, L = 0;
-	int ld = 0;  // L padded to a whole number of 256-bin tiles (bulk-copy granularity of the likelihood kernel)
+	int ld = 0;  // L padded to a whole number of 256-bin tiles: leading dimension of the per-detector tables
 	bool have_data = false, gaussleg = false, log10F = false, uniform = false;
 	double df = 0;
 	gwat::Network net{};
