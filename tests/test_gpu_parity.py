@@ -344,3 +344,20 @@ def test_concurrent_callers_share_a_context(ctx, gold_mcmc):
     for k in range(4):
         for it in range(8):
             assert np.array_equal(results[k][it], alone[k])
+
+
+@pytest.mark.parametrize("cfg,L", [(1, 8192), (2, 16384), (4, 3000), (5, 70000)])
+def test_value_does_not_depend_on_the_batch(ctx, cfg, L):
+    """The fixed summation tree: a walker's logL is bit-identical alone, in a small group and in a large batch,
+    whatever run length per CTA the launcher picks for the ensemble size."""
+    wl = workloads.make(cfg, W=600, L=L)
+    ctx.set_network(wl.detectors, wl.f, wl.psd)
+    src = ctx.repack_mcmc_batch(wl.method, wl.inj[None, :], wl.gmst, wl.mod)
+    src[0].tc = wl.T_segment - src[0].tc
+    ctx.set_network(wl.detectors, wl.f, wl.psd, ctx.coherent_response_batch(wl.method, src)[0])
+    full = ctx.loglike_mcmc_batch(wl.method, wl.params, wl.gmst, wl.T_segment, wl.mod)
+    assert np.all(np.isfinite(full))
+    for i in (0, 17, 599):
+        assert ctx.loglike_mcmc_batch(wl.method, wl.params[i:i + 1], wl.gmst, wl.T_segment, wl.mod)[0] == full[i]
+    part = np.concatenate([ctx.loglike_mcmc_batch(wl.method, wl.params[a:a + 37], wl.gmst, wl.T_segment, wl.mod) for a in range(0, 600, 37)])
+    assert np.array_equal(part, full)
