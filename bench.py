@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Benchmark of the hot path: log-likelihood evaluations per second (waveform + response + inner product).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|2|4|5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|2|3|4|5] [--masses heavy|light]
+                    [--scaling weak|strong] [--workload likelihood|sampler]
 
 Workload (default): BASELINE.json configs[1] -- IMRPhenomPv2 precessing BBH, 3 detectors (H1/L1/V1), a parallel-tempered
 ensemble of 8 temperatures x 512 walkers = 4096 walkers per GPU on 16384 frequency bins; synthetic, seeded inputs
@@ -17,7 +18,13 @@ JSON line keys (see the task contract):
              beside it as `hbm`.
   cpu_baseline  the reference's own CPU code (oracle/_ref, the reference sources compiled unmodified) on all host threads
              over a bounded sample of the same walkers.
+  sustained  the same two timed loops repeated for >= 1 s each (the K-step region of the short configs is ~10 ms)
+  extra      (N=1 default run) the other lines north_star names, measured in the same process, each with value / e2e /
+             roofline / cpu_baseline: the (10,8) Msun mass set, configs 1, 4, 5 and config 3 (10^5 Fisher matrices)
 `--impl reference` times that CPU implementation alone, with the same config/metric/unit.
+`--config 3` makes the Fisher batch the main line (unit Fisher/s); `--scaling strong` splits the config's ensemble over
+the GPUs instead of giving each its own; `--workload sampler` times device-resident PTMCMC steps with the PT-swap
+exchange over NCCL (tools/bench_sampler.py).
 """
 import argparse
 import json
@@ -42,21 +49,12 @@ UNIT = "evals/s"
 FLOP_EQ = {"IMRPhenomD": (270, 90), "IMRPhenomPv2": (670, 90), "IMRPhenomD_NRT": (530, 90), "dCS_IMRPhenomD": (320, 90)}
 
 
-def ncu_traffic(config):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_loglike launch of this workload, from the committed
-    `ncu --set full` capture (profiles/traffic.json names the capture); None when no capture exists for the config."""
+def ncu_value(key, field):
+    """A per-launch figure from the committed `ncu --set full` captures (profiles/traffic.json names each capture):
+    dram__bytes_read.sum + dram__bytes_write.sum (`*_dram_bytes`) or sm__inst_executed_pipe_fp64 in % of peak sustained
+    active (`fp64_pipe_active_pct`).  None when no capture exists for that workload."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t["cfg%d" % config]["k_loglike_dram_bytes"]
-    except (OSError, ValueError, KeyError):
-        return None
-
-
-def ncu_pipe_pct(config):
-    """FP64-pipe utilisation (sm__inst_executed_pipe_fp64, % of peak sustained active) of k_loglike from the same capture."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t["cfg%d" % config]["fp64_pipe_active_pct"]
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key][field]
     except (OSError, ValueError, KeyError):
         return None
 
@@ -185,6 +183,21 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def pin_rank_cores(local, world):
+    """Give every rank of a multi-GPU run its own, disjoint share of the host cores (eight ranks on the
+    same 32 cores made the host-buffer path's max-over-ranks time a scheduler lottery).  Returns the cores kept."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cores) < world:
+            return cores
+        share = len(cores) // world
+        mine = cores[local * share:(local + 1) * share]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return []
+
+
 def cpu_reference_rate(wl, sample, nthreads=0, repeats=1):
     """evals/s of the reference's CPU path (oracle/_ref) on `sample` walkers of the workload, all host threads."""
     from oracle import gwat_ref
@@ -200,13 +213,236 @@ def cpu_reference_rate(wl, sample, nthreads=0, repeats=1):
     return sample / best, nthreads, best
 
 
-def workload_config(wl, n_gpus):
-    return {"workload": "%s: %s, %d detectors (%s), %d walkers/GPU x %d bins, MCMC sampling dim %d" %
-                        (wl.name, wl.method, wl.D, "/".join(wl.detectors), wl.W, wl.L, wl.P),
-            "method": wl.method, "walkers_per_gpu": wl.W, "bins": wl.L, "detectors": wl.D, "dimension": wl.P,
-            "parallelism": "walkers sharded over %d GPU(s), no data-path collective" % n_gpus,
+def workload_config(wl, n_gpus, scaling="weak", masses="heavy"):
+    par = ("walkers sharded over %d GPU(s), no data-path collective" % n_gpus if scaling == "weak" else
+           "the config's ensemble split over %d GPU(s) (%d walkers each), no data-path collective" % (n_gpus, wl.W))
+    return {"workload": "%s: %s, %d detectors (%s), %d walkers/GPU x %d bins, MCMC sampling dim %d, %s masses" %
+                        (wl.name, wl.method, wl.D, "/".join(wl.detectors), wl.W, wl.L, wl.P, masses),
+            "method": wl.method, "walkers_per_gpu": wl.W, "bins": wl.L, "detectors": wl.D, "dimension": wl.P, "masses": masses,
+            "parallelism": par,
             "l2": "L2 flushed (256 MiB device memset) between timed steps; a fresh walker set every step"}
 
+
+LIGHT = {1: (10.0, 8.0), 2: (10.0, 8.0), 4: (10.0, 8.0)}   # the low-mass set, every bin below 0.2/M active
+
+
+def make_workload(config, masses, W=None, L=None, seed=None):
+    m = LIGHT.get(config) if masses == "light" else None
+    return workloads.make(config, W=W, L=L, masses=m, seed=seed)
+
+
+def peaks_file():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the likelihood path (configs 1, 2, 4, 5)
+# ---------------------------------------------------------------------------------------------------------------------------
+
+class LikelihoodBench:
+    """One workload resident on one GPU: pinned host walker sets, device copies, and the two timed call paths."""
+
+    def __init__(self, ctx, wl, rank, stream, flush, nsets=4):
+        import torch
+        self.torch = torch
+        self.ctx, self.wl, self.stream, self.flush = ctx, wl, stream, flush
+        make_injection(ctx, wl)
+        rng = np.random.default_rng(7 + rank)
+        self.host_sets = []
+        for _ in range(nsets):   # a few distinct walker sets so that consecutive steps do not repeat the same parameter points
+            p = wl.params.copy()
+            p[:, [0, 2, 4]] += 1e-3 * rng.standard_normal((wl.W, 3))
+            self.host_sets.append(torch.from_numpy(p).pin_memory())
+        self.dev_sets = [h.cuda(non_blocking=True) for h in self.host_sets]
+        self.d_out = torch.empty(wl.W, dtype=torch.float64, device="cuda")
+        self.h_out = torch.empty(wl.W, dtype=torch.float64).pin_memory()
+        self.nsets = nsets
+        torch.cuda.synchronize()
+
+    def step_resident(self, k):
+        wl = self.wl
+        self.ctx.loglike_mcmc_batch_dev(wl.method, self.dev_sets[k % self.nsets].data_ptr(), wl.W, wl.P, wl.gmst, wl.T_segment,
+                                        self.d_out.data_ptr(), wl.mod, self.stream.cuda_stream)
+
+    def step_e2e(self, k):
+        wl, ctx = self.wl, self.ctx
+        h = self.host_sets[k % self.nsets]
+        rc = ctx._lib.gwat_b200_loglike_mcmc_batch(ctx._h, wl.method.encode(), _mod_ref(wl.mod), wl.P, wl.W, _ptr(h.data_ptr()),
+                                                   _dbl(wl.gmst), _dbl(wl.T_segment), _ptr(self.h_out.data_ptr()))
+        ctx._check(rc)
+
+    def warm(self, n):
+        # the two call paths share the context's lane-0 scratch: never in flight together (include/gwat_b200.h)
+        for k in range(n):
+            self.step_resident(k)
+        self.torch.cuda.synchronize()
+        for k in range(n):
+            self.step_e2e(k)
+        self.torch.cuda.synchronize()
+
+    def time_resident(self, steps):
+        """CUDA events on the launching stream around every step, L2 flushed before each; returns seconds (sum over steps)."""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(self.stream):
+            for k in range(steps):
+                self.flush.zero_()
+                ev[k][0].record(self.stream)
+                self.step_resident(k)
+                ev[k][1].record(self.stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+
+    def time_e2e(self, steps):
+        """Host-buffer C-ABI call (H2D + kernels + D2H + sync inside), wall clock; also the per-launch k_loglike time."""
+        kernel_ms, active = [], []
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            self.step_e2e(k)
+            kernel_ms.append(self.ctx.last_kernel_ms)
+            active.append(self.ctx.last_active_bins)
+        self.torch.cuda.synchronize()
+        return time.perf_counter() - t0, float(np.mean(kernel_ms)), float(np.mean(active))
+
+    def roofline(self, k_ms, act, fp64_peak, config_key):
+        wl = self.wl
+        feq = flop_eq_per_bin(wl.method, wl.D)
+        achieved_tf = act * feq / (k_ms * 1e-3) / 1e12
+        alg_bytes = wl.L * (8 + 24 * wl.D) + wl.W * 8 * (wl.P + 1)
+        peaks = peaks_file()
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        return {"bound": "fp64", "kernel": "k_loglike", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+                "peak_source": "DFMA-chain microbenchmark run in this process (gwat_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "work": "%d flop-eq per active (walker,bin) on the reference's schedule [SURVEY 8(d)] x %.4g active bins per launch (%.1f%% of W*L)" % (
+                    feq, act, 100.0 * act / (wl.W * wl.L)),
+                "kernel_ms": k_ms, "traffic": ncu_value(config_key, "k_loglike_dram_bytes"),
+                "fp64_pipe_active_pct_ncu": ncu_value(config_key, "fp64_pipe_active_pct"),
+                "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                        "algorithmic_bytes": alg_bytes}}
+
+    def cpu_baseline(self, sample):
+        from oracle import gwat_ref
+        wl = self.wl
+        if not gwat_ref.available():
+            return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built on this box"}
+        sample = min(wl.W, sample)
+        rate, cores, secs = cpu_reference_rate(wl, sample)
+        rate1, _, _ = cpu_reference_rate(wl, max(4, sample // 16), nthreads=1)
+        return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "single_thread_value": rate1,
+                "sample": "%d of the %d walkers of this workload, one pass, %.2f s wall, OpenMP over walkers" % (sample, wl.W, secs)}
+
+    def brief(self, steps, warmup, fp64_peak, config_key, cpu_sample):
+        """value / e2e / roofline / cpu_baseline of this workload in one dict (used for the extra lines of the default run)."""
+        self.warm(warmup)
+        t_res = self.time_resident(steps)
+        t_e2e, k_ms, act = self.time_e2e(steps)
+        wl = self.wl
+        out = {"config": workload_config(wl, 1, masses=config_key.split("_")[-1] if "_" in config_key else "heavy"),
+               "value": wl.W * steps / t_res, "unit": UNIT, "steps": steps, "ms_per_step": t_res / steps * 1e3,
+               "e2e": {"value": wl.W * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": wl.W * wl.P * 8,
+                       "d2h_bytes_per_step": wl.W * 8 + 8, "ms_per_step": t_e2e / steps * 1e3},
+               "roofline": self.roofline(k_ms, act, fp64_peak, config_key)}
+        if cpu_sample:
+            try:
+                out["cpu_baseline"] = self.cpu_baseline(cpu_sample)
+            except Exception as exc:
+                out["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (exc,)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# config 3: batched Fisher matrices
+# ---------------------------------------------------------------------------------------------------------------------------
+
+FISHER_METRIC = "order-4 numerical Fisher matrices/sec (IMRPhenomD, 11 parameters, 3 detectors summed, 4096 bins)"
+FISHER_DETS = ["Hanford", "Livingston", "Virgo"]
+
+
+def fisher_grid(L=4096):
+    f = 20.0 + 0.25 * np.arange(L)
+    return f, np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+
+
+def fisher_flop_eq(srcs, f, D=3, dim=11):
+    """SURVEY 8(d), reference schedule: per source D*4*dim*L_active*(270+65) for the stencil evaluations, D*dim*L*10 for
+    combining the points, D*dim(dim+1)/2*L*10 for the assembly.  L_active = bins at or below 0.2/M."""
+    total = 0.0
+    L = f.size
+    for s in srcs:
+        fcut = 0.2 / ((s.mass1 + s.mass2) * workloads.MSOL_SEC)
+        la = int(np.searchsorted(f, fcut, side="right"))
+        total += D * 4 * dim * la * 335.0 + D * dim * L * 10.0 + D * (dim * (dim + 1) // 2) * L * 10.0
+    return total
+
+
+def fisher_measure(ctx, S, steps, warmup, fp64_peak, cpu_sample, seed_offset=0):
+    """Fisher/s through the host-buffer C ABI (the only entry point a GWAT user has for Fishers: sources in host memory,
+    matrices back in host memory), device time from the library's events, roofline on the reference-schedule count."""
+    f, psd = fisher_grid()
+    ctx.set_network(FISHER_DETS, f, psd)
+    sets = [workloads.fisher_sources(S, seed=workloads.SEED0 + 3 + 17 * k + seed_offset) for k in range(2)]
+    arrs = [(workloads.abi.Source * S)(*s) for s in sets]
+    for k in range(max(1, min(warmup, 3))):
+        ctx.fisher_numerical_batch("IMRPhenomD", arrs[k % 2], 11, order=4)
+    dev_ms, t0 = [], time.perf_counter()
+    for k in range(steps):
+        F = ctx.fisher_numerical_batch("IMRPhenomD", arrs[k % 2], 11, order=4)
+        dev_ms.append(ctx.last_kernel_ms)
+    t_e2e = time.perf_counter() - t0
+    t_dev = sum(dev_ms) * 1e-3
+    work = 0.5 * (fisher_flop_eq(sets[0], f) + fisher_flop_eq(sets[1], f)) if steps > 1 else fisher_flop_eq(sets[0], f)
+    achieved = work * steps / t_dev / 1e12
+    nonfinite = int(np.sum(~np.all(np.isfinite(F.reshape(S, -1)), axis=1)))
+    out = {"metric": FISHER_METRIC, "value": S * steps / t_dev, "unit": "Fisher/s", "steps": steps, "sources_per_step": S,
+           "ms_per_step": t_dev / steps * 1e3,
+           "value_note": "device time of the whole pass (chunk loop incl. the H2D of the sources and the D2H of the matrices, CUDA events inside the library)",
+           "e2e": {"value": S * steps / t_e2e, "unit": "Fisher/s", "h2d_bytes_per_step": S * C_sizeof_source(),
+                   "d2h_bytes_per_step": S * 121 * 8, "ms_per_step": t_e2e / steps * 1e3},
+           "equivalent_response_evals_per_s": S * steps / t_dev * 132,
+           "roofline": {"bound": "fp64", "kernel": "k_fisher_deriv (+ k_fisher_setup, k_fisher_assemble: whole pass)", "achieved": achieved,
+                        "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                        "work": "reference schedule [SURVEY 8(d)]: %.4g flop-eq per source on average (3 det x 44 stencil responses x L_active x 335 + combine + assembly)" % (work / S),
+                        "fp64_pipe_active_pct_ncu": ncu_value("cfg3", "fp64_pipe_active_pct"),
+                        "traffic": ncu_value("cfg3", "k_fisher_dram_bytes_per_source"),
+                        "peak_source": "DFMA-chain microbenchmark run in this process"},
+           "nonfinite_sources": nonfinite}
+    if cpu_sample:
+        try:
+            from oracle import gwat_ref
+            if gwat_ref.available():
+                n = min(cpu_sample, S)
+                nt = host_threads()
+                t0 = time.perf_counter()
+                R = gwat_ref.fisher_numerical_batch("IMRPhenomD", sets[(steps - 1) % 2][:n], FISHER_DETS, f, psd, 11, order=4,
+                                                    detector_index=-1, reference_index=0, nthreads=nt)
+                dtc = time.perf_counter() - t0
+                ok = np.all(np.isfinite(R.reshape(n, -1)), axis=1)
+                dg = np.sqrt(np.abs(np.einsum("sii->si", R[ok])))
+                nerr = np.abs(F[:n][ok] - R[ok]) / (dg[:, :, None] * dg[:, None, :])
+                out["cpu_baseline"] = {"value": n / dtc, "unit": "Fisher/s", "cores": nt, "kind": "reference",
+                                       "sample": "%d of the %d sources, fisher_numerical per detector and summed, %.2f s wall, OpenMP over sources" % (n, S, dtc)}
+                out["parity_on_sample"] = {"normalised_error_median": float(np.median(nerr)), "normalised_error_max": float(nerr.max()),
+                                           "measure": "|dF_ij|/sqrt(F_ii F_jj) vs the reference on the CPU sample"}
+        except Exception as exc:
+            out["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (exc,)}
+    return out
+
+
+def C_sizeof_source():
+    import ctypes
+    return ctypes.sizeof(workloads.abi.Source)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------------------------
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -216,13 +452,35 @@ def run_reference(args):
     if not gwat_ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgwat_ref.so not built (needs /root/reference at build time)"}))
         return 0
-    wl = workloads.make(args.config, W=args.walkers, L=args.bins)
+    nthreads = host_threads()
+    if args.config == 3:
+        f, psd = fisher_grid()
+        n = min(args.fisher_sources, max(nthreads * 4, 64))
+        srcs = workloads.fisher_sources(n)
+        for _ in range(min(args.warmup, 1)):
+            gwat_ref.fisher_numerical_batch("IMRPhenomD", srcs[:nthreads], FISHER_DETS, f, psd, 11, order=4, nthreads=nthreads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            gwat_ref.fisher_numerical_batch("IMRPhenomD", srcs, FISHER_DETS, f, psd, 11, order=4, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        value = n * args.steps / dt
+        desc = "%d of the %d sources per step, %d OpenMP threads over sources" % (n, args.fisher_sources, nthreads)
+        line = {"impl": "reference", "metric": FISHER_METRIC, "value": value, "unit": "Fisher/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": fisher_config(args.fisher_sources, args.gpus),
+                "cpu_baseline": {"value": value, "unit": "Fisher/s", "cores": nthreads, "kind": "reference", "sample": desc},
+                "e2e": {"value": value, "unit": "Fisher/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    W_local = args.walkers
+    wl = make_workload(args.config, args.masses, W=W_local, L=args.bins)
+    if args.scaling == "strong" and args.gpus > 1:
+        wl.params = wl.params[:wl.W // args.gpus]
     # the data the GPU arm uses comes from the product; here the oracle makes the same injection itself
     _, src = gwat_ref.loglike_mcmc_batch(wl.method, wl.mod, wl.inj[None, :], wl.gmst, wl.T_segment, wl.detectors, wl.f, wl.psd,
                                          None, return_sources=True)
     wl.data = gwat_ref.coherent_response(wl.method, src[0], wl.detectors, wl.f)
-    nthreads = host_threads()
-    sample = min(wl.W, args.cpu_sample)
+    sample = min(wl.W, args.cpu_sample if args.config != 5 else min(args.cpu_sample, 4 * nthreads))
     for _ in range(args.warmup):
         cpu_reference_rate(wl, min(sample, 4 * nthreads), nthreads)
     t0 = time.perf_counter()
@@ -236,14 +494,26 @@ def run_reference(args):
     desc = "%d of the %d walkers per step, %d OpenMP threads over walkers (one chain per thread, as the reference's pool)" % (
         sample, wl.W, nthreads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, args.gpus),
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, args.gpus, args.scaling, args.masses),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
+
+def fisher_config(S, n_gpus):
+    return {"workload": "cfg3_IMRPhenomD_Fisher: %d sources/GPU (m in U(3,100) Msun, testing/fisher_comparison.cpp draw), 11 parameters, order-4 stencil, "
+                        "3 detectors (Hanford/Livingston/Virgo) summed, 4096 bins from 20 Hz at df = 1/4 Hz" % S,
+            "method": "IMRPhenomD", "sources_per_gpu": S, "bins": 4096, "detectors": 3, "dimension": 11, "order": 4,
+            "parallelism": "sources sharded over %d GPU(s), no collective" % n_gpus,
+            "l2": "inputs larger than L2: the derivative buffer of one pass is 2 GiB; two alternating source sets"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------------------------------
 
 def run_b200(args):
     import torch
@@ -257,87 +527,104 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cores = pin_rank_cores(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
-
-    # every rank owns its own ensemble (weak scaling): same grid/injection, different walker draws
-    wl = workloads.make(args.config, W=args.walkers, L=args.bins, seed=workloads.SEED0 + args.config + 1000 * rank)
     ctx = engine.Context(local)
-    make_injection(ctx, wl)
-    W, P, D, L = wl.W, wl.P, wl.D, wl.L
-
-    # a few distinct walker sets so that consecutive steps do not repeat the same parameter points
-    nsets = 4
-    rng = np.random.default_rng(7 + rank)
-    host_sets = []
-    for s in range(nsets):
-        p = wl.params.copy()
-        p[:, [0, 2, 4]] += 1e-3 * rng.standard_normal((W, 3))
-        host_sets.append(torch.from_numpy(p).pin_memory())
-    dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
-    d_out = torch.empty(W, dtype=torch.float64, device="cuda")
-    h_out = torch.empty(W, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.Stream()   # non-default: the C ABI treats a NULL stream as "the context's own"
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    # a non-default stream: the C ABI treats a NULL stream as "the context's own", and torch's default stream handle is 0
-    stream = torch.cuda.Stream()
-    torch.cuda.synchronize()
 
-    def step_resident(k):
-        ctx.loglike_mcmc_batch_dev(wl.method, dev_sets[k % nsets].data_ptr(), W, P, wl.gmst, wl.T_segment, d_out.data_ptr(),
-                                   wl.mod, stream.cuda_stream)
+    def reduce_max(vals):
+        if world == 1:
+            return vals, [vals]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        per_rank = [[float(x) for x in a] for a in allv]
+        return [max(col) for col in zip(*per_rank)], per_rank
 
-    def step_e2e(k):
-        h = host_sets[k % nsets]
-        rc = ctx._lib.gwat_b200_loglike_mcmc_batch(ctx._h, wl.method.encode(), _mod_ref(wl.mod), P, W,
-                                                   _ptr(h.data_ptr()), _dbl(wl.gmst), _dbl(wl.T_segment), _ptr(h_out.data_ptr()))
-        ctx._check(rc)
+    if args.workload == "sampler":
+        from tools import bench_sampler
+        return bench_sampler.run_under_bench(args, ctx, world, rank, local, dist if world > 1 else None, ClockSampler)
 
-    for k in range(args.warmup):
-        step_resident(k)
-        step_e2e(k)
-    torch.cuda.synchronize()
+    # ---- config 3: Fisher batches ---------------------------------------------------------------------------------------
+    if args.config == 3:
+        S = args.fisher_sources if args.scaling == "weak" else args.fisher_sources // world
+        fp64_peak = ctx.measure_fp64_peak()
+        launches0 = ctx.launch_count
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        res = fisher_measure(ctx, S, args.steps, args.warmup, fp64_peak, 0 if (world > 1 or args.no_cpu_baseline) else args.fisher_cpu_sample,
+                             seed_offset=1000 * rank)
+        clocks = sampler.stop()
+        (t_dev, t_e2e), per_rank = reduce_max([res["ms_per_step"], res["e2e"]["ms_per_step"]])
+        if rank != 0:
+            if world > 1:
+                dist.destroy_process_group()
+            return 0
+        line = {"metric": FISHER_METRIC, "value": n_gpus * S / (t_dev * 1e-3), "unit": "Fisher/s", "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_dev, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": fisher_config(S, n_gpus),
+                "e2e": dict(res["e2e"], value=n_gpus * S / (t_e2e * 1e-3), ms_per_step=t_e2e),
+                "gpu_launches": int(ctx.launch_count - launches0), "clocks": clocks, "roofline": res["roofline"],
+                "equivalent_response_evals_per_s": n_gpus * S / (t_dev * 1e-3) * 132, "nonfinite_sources": res["nonfinite_sources"]}
+        for k in ("cpu_baseline", "parity_on_sample"):
+            if k in res:
+                line[k] = res[k]
+        print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- likelihood configs ---------------------------------------------------------------------------------------------
+    # weak scaling: every rank owns its own ensemble of the config's size (same grid/injection, different walker draws);
+    # strong scaling: the config's ONE ensemble is split over the ranks (whole temperature rungs per rank)
+    wl = make_workload(args.config, args.masses, W=args.walkers, L=args.bins,
+                       seed=workloads.SEED0 + args.config + (1000 * rank if args.scaling == "weak" else 0))
+    W_total = wl.W * (n_gpus if args.scaling == "weak" else 1)
+    if args.scaling == "strong" and world > 1:
+        per = wl.W // world
+        wl.params = wl.params[rank * per:(rank + 1) * per].copy()
+    lb = LikelihoodBench(ctx, wl, rank, stream, flush)
+    W, P, D, L = wl.W, wl.P, wl.D, wl.L
+    lb.warm(args.warmup)
     fp64_peak = ctx.measure_fp64_peak()
     launches0 = ctx.launch_count
 
-    # ---- resident-input timing: CUDA events on the launching stream, L2 flushed between steps ----------------------------
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, active = [], []
-    with torch.cuda.stream(stream):
-        for k in range(args.steps):
-            flush.zero_()
-            ev[k][0].record(stream)
-            step_resident(k)
-            ev[k][1].record(stream)
-    torch.cuda.synchronize()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    t_resident = sum(step_ms) * 1e-3
+    t_resident = lb.time_resident(args.steps)
     launches_resident = ctx.launch_count - launches0
-
-    # ---- end-to-end timing through the host-buffer entry point (H2D + kernels + D2H inside the timed region) ----------
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_e2e(k)
-        kernel_ms.append(ctx.last_kernel_ms)
-        active.append(ctx.last_active_bins)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+    t_e2e, k_ms, act = lb.time_e2e(args.steps)
     clocks = sampler.stop()
     launches_total = ctx.launch_count - launches0
-    logl_checksum = float(np.nansum(h_out.numpy()))
+    logl_checksum = float(np.nansum(lb.h_out.numpy()))
 
+    # ---- sustained figure: the same two loops for >= 1 s each (weak #9: the K-step region is ~10 ms) ---------------------
+    sustained = None
+    if not args.no_extras:
+        n_sus = int(min(20000, max(args.steps, np.ceil(args.sustain_seconds / max(t_resident / args.steps, 1e-6)))))
+        if world > 1:
+            dist.barrier()
+        s2 = ClockSampler(local)
+        s2.start()
+        ts_res = lb.time_resident(n_sus)
+        ts_e2e, _, _ = lb.time_e2e(n_sus)
+        c2 = s2.stop()
+        sustained = [ts_res, ts_e2e, n_sus, c2]
+
+    (t_resident, t_e2e, ts_res, ts_e2e), per_rank = reduce_max([t_resident, t_e2e, sustained[0] if sustained else 0.0,
+                                                                 sustained[1] if sustained else 0.0])
     if world > 1:
-        tt = torch.tensor([t_resident, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_resident, t_e2e = float(tt[0]), float(tt[1])
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -345,54 +632,52 @@ def run_b200(args):
         return 0
 
     K = args.steps
-    value = n_gpus * W * K / t_resident
-    e2e_value = n_gpus * W * K / t_e2e
-    k_ms = float(np.mean(kernel_ms))
-    act = float(np.mean(active))
-    feq = flop_eq_per_bin(wl.method, D)
-    achieved_tf = act * feq / (k_ms * 1e-3) / 1e12
-    alg_bytes = L * (8 + 24 * D) + W * 8 * (P + 1)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except (OSError, ValueError):
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {"bound": "fp64", "kernel": "k_loglike", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
-                "peak_source": "DFMA-chain microbenchmark run in this process (gwat_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "work": "%d flop-eq per active (walker,bin) [SURVEY 8(d)] x %.4g active bins per launch (%.1f%% of W*L)" % (
-                    feq, act, 100.0 * act / (W * L)),
-                "kernel_ms": k_ms, "traffic": ncu_traffic(args.config), "fp64_pipe_active_pct_ncu": ncu_pipe_pct(args.config),
-                "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                        "algorithmic_bytes": alg_bytes}}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": args.warmup,
-            "ms_per_step": t_resident / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_gpus),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * P * 8, "d2h_bytes_per_step": W * 8 + 8,
-                    "ms_per_step": t_e2e / K * 1e3},
+    key = "cfg%d" % args.config + ("_light" if args.masses == "light" else "")
+    line = {"metric": METRIC, "value": W_total * K / t_resident, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": args.warmup,
+            "ms_per_step": t_resident / K * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_gpus, args.scaling, args.masses),
+            "e2e": {"value": W_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": W * P * 8, "d2h_bytes_per_step": W * 8 + 8,
+                    "ms_per_step": t_e2e / K * 1e3, "per_rank_ms_per_step": [r[1] / K * 1e3 for r in per_rank],
+                    "host_cores_per_rank": len(cores)},
             "gpu_launches": int(launches_total), "gpu_launches_per_step": launches_resident / K,
-            "clocks": clocks, "roofline": roofline, "logL_checksum": logl_checksum}
+            "clocks": clocks, "roofline": lb.roofline(k_ms, act, fp64_peak, key), "logL_checksum": logl_checksum}
+    if sustained:
+        n_sus, c2 = sustained[2], sustained[3]
+        line["sustained"] = {"steps": n_sus, "seconds_resident": ts_res, "seconds_e2e": ts_e2e, "value": W_total * n_sus / ts_res,
+                             "e2e_value": W_total * n_sus / ts_e2e, "unit": UNIT, "clocks": c2,
+                             "note": "the same two timed loops run for >= %.1f s each (L2 flushed between steps)" % args.sustain_seconds}
 
     # ---- CPU baseline: the reference's own code on the host cores of this box, bounded sample (N=1 only) ----------------
     if n_gpus == 1 and not args.no_cpu_baseline:
         try:
-            from oracle import gwat_ref
-            if gwat_ref.available():
-                sample = min(W, args.cpu_sample)
-                rate, cores, secs = cpu_reference_rate(wl, sample)
-                rate1, _, _ = cpu_reference_rate(wl, max(8, sample // 16), nthreads=1)
-                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "single_thread_value": rate1,
-                                        "sample": "%d of the %d walkers of this workload, one pass, %.2f s wall, OpenMP over walkers" % (
-                                            sample, W, secs)}
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                                        "sample": "oracle/_ref not built on this box"}
+            line["cpu_baseline"] = lb.cpu_baseline(args.cpu_sample)
         except Exception as exc:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+
+    # ---- the other lines north_star names, measured in the same process (N=1 default run only) --------------------------
+    if n_gpus == 1 and not args.no_extras and args.walkers is None and args.bins is None:
+        extras = {}
+        del lb
+        torch.cuda.empty_cache()
+
+        def extra_like(cfg, masses, steps, cpu_sample):
+            w2 = make_workload(cfg, masses)
+            b2 = LikelihoodBench(ctx, w2, 0, stream, flush, nsets=2)
+            return b2.brief(steps, 3, fp64_peak, "cfg%d" % cfg + ("_light" if masses == "light" else ""),
+                            0 if args.no_cpu_baseline else cpu_sample)
+        try:
+            other = "light" if args.masses == "heavy" else "heavy"
+            if args.config in LIGHT:
+                extras["%s_masses" % other] = extra_like(args.config, other, 10, 256)
+            for cfg, steps, cs in ((1, 20, 512), (2, 10, 512), (4, 10, 512), (5, 3, 32)):
+                if cfg != args.config:
+                    extras["cfg%d" % cfg] = extra_like(cfg, "heavy", steps, cs)
+            if args.config != 3:
+                extras["cfg3"] = fisher_measure(ctx, args.fisher_sources, 2, 1, fp64_peak, 0 if args.no_cpu_baseline else args.fisher_cpu_sample)
+                extras["cfg3"]["config"] = fisher_config(args.fisher_sources, 1)
+        except Exception as exc:
+            extras["error"] = repr(exc)
+        line["extra"] = extras
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -421,14 +706,26 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--masses", default="heavy", choices=["heavy", "light"],
+                    help="heavy: (36,29) Msun, ~30%% of the bins below 0.2/M; light: (10,8) Msun, every bin active (configs 1, 2, 4)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's ensemble per GPU; strong: the config's ensemble split over the GPUs")
+    ap.add_argument("--workload", default="likelihood", choices=["likelihood", "sampler"],
+                    help="sampler: device-resident PTMCMC steps, chains sharded over the GPUs, PT swap over NCCL")
     ap.add_argument("--walkers", type=int, default=None, help="walkers per GPU (default: the config's)")
     ap.add_argument("--bins", type=int, default=None, help="frequency bins (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="walkers in the CPU-baseline sample")
+    ap.add_argument("--fisher-sources", type=int, default=100000, help="config 3: sources per GPU and step")
+    ap.add_argument("--fisher-cpu-sample", type=int, default=256)
+    ap.add_argument("--sustain-seconds", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained figure and the other configs' lines")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.config == 3 and args.steps > 20 and "--steps" not in sys.argv:
+        args.steps = 5
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

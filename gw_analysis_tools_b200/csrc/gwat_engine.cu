@@ -58,6 +58,8 @@ constexpr int kLikeThreads = GWAT_LOGLIKE_THREADS;
 constexpr int kSetupThreads = 32;
 // bin tiles (of kThreads bins) one CTA of the Fisher derivative kernel evaluates with one staging of its coefficient blocks
 constexpr int kFisherTilesPerCta = 4;
+// detectors one Fisher pass handles (sizes FisherPlan and the kernels' staging arrays)
+constexpr int kFisherMaxDetectors = 5;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -247,12 +249,12 @@ __global__ void __launch_bounds__(kThreads) k_waveform(const WalkerCoef *__restr
                                                       double *hp_im, double *hc_re, double *hc_im)
 {
 	__shared__ WalkerCoef w;
-	load_walker(coefs + blockIdx.y, w);
-	const int i = blockIdx.x * kThreads + threadIdx.x;
+	load_walker(coefs + blockIdx.x, w);
+	const int i = blockIdx.y * kThreads + threadIdx.x;
 	if (i >= g.L) return;
 	cplx hp{NAN, NAN}, hc{NAN, NAN};
 	if (w.valid) polarizations_bin<Fam>(w, g.f[i], g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
-	const size_t k = (size_t)blockIdx.y * g.L + i;
+	const size_t k = (size_t)blockIdx.x * g.L + i;
 	if (hp_re) hp_re[k] = hp.re;
 	if (hp_im) hp_im[k] = hp.im;
 	if (hc_re) hc_re[k] = hc.re;
@@ -267,8 +269,8 @@ template <class Fam>
 __global__ void __launch_bounds__(kThreads) k_amp_phase(const WalkerCoef *__restrict__ coefs, GridPtrs g, double *amp_out, double *phase_out)
 {
 	__shared__ WalkerCoef w;
-	load_walker(coefs + blockIdx.y, w);
-	const int i = blockIdx.x * kThreads + threadIdx.x;
+	load_walker(coefs + blockIdx.x, w);
+	const int i = blockIdx.y * kThreads + threadIdx.x;
 	if (i >= g.L) return;
 	double amp = NAN, phase = NAN;
 	if (w.valid) {
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_amp_phase(const WalkerCoef *__rest
 		if (f > w.d.fcut) amp = 0.0;
 		phase = phenomd_apply_time_phase(w.d, f, phase);
 	}
-	const size_t k = (size_t)blockIdx.y * g.L + i;
+	const size_t k = (size_t)blockIdx.x * g.L + i;
 	if (amp_out) amp_out[k] = amp;
 	if (phase_out) phase_out[k] = phase;
 }
@@ -289,15 +291,15 @@ __global__ void __launch_bounds__(kThreads) k_response(const WalkerCoef *__restr
                                                       int with_shift, double *re, double *im)
 {
 	__shared__ WalkerCoef w;
-	load_walker(coefs + blockIdx.y, w);
-	const int i = blockIdx.x * kThreads + threadIdx.x;
+	load_walker(coefs + blockIdx.x, w);
+	const int i = blockIdx.y * kThreads + threadIdx.x;
 	if (i >= g.L) return;
 	cplx hp{NAN, NAN}, hc{NAN, NAN};
 	const double f = g.f[i];
 	if (w.valid) polarizations_bin<Fam>(w, f, g.sf_hi[i], g.sf_lo[i], g.logf[i], hp, hc);
 	for (int d = 0; d < nd; d++) {
 		const cplx r = project_bin(w.det[d0 + d], hp, hc, f, with_shift != 0);
-		const size_t k = ((size_t)blockIdx.y * nd + d) * g.L + i;
+		const size_t k = ((size_t)blockIdx.x * nd + d) * g.L + i;
 		re[k] = r.re;
 		im[k] = r.im;
 	}
@@ -311,8 +313,8 @@ struct FisherPlan {
 	int npts;       // 2 or 4 stencil points per parameter
 	int theory;
 	int nd;               // detectors handled by one pass (1..5)
-	int det_is_ref[5];    // detector == reference detector: no arrival-time handling at all
-	double det_row[5][13], ref_row[13];
+	int det_is_ref[kFisherMaxDetectors];    // detector == reference detector: no arrival-time handling at all
+	double det_row[kFisherMaxDetectors][13], ref_row[13];
 };
 
 // One thread per (source, parameter, stencil point): the perturbed source's coefficient block with the antenna patterns of
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
                                                           int *__restrict__ bin_limit)
 {
 	__shared__ WalkerCoef w[4];
-	__shared__ double tc_s[4][5];
+	__shared__ double tc_s[4][kFisherMaxDetectors];
 	const int ntiles = (g.L + kThreads - 1) / kThreads;
 	const int tile0 = blockIdx.x * kFisherTilesPerCta, tile1 = min(ntiles, tile0 + kFisherTilesPerCta);
 	auto zero_tile = [&](int t) {
@@ -877,6 +879,10 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
                  int reference_index, cudaStream_t st)
 {
 	const int L = ctx->L, dim = fp.rp.dimension, nd = d1 - d0;
+	// FisherPlan::det_row and the kernels' staging arrays hold kFisherMaxDetectors detectors per pass (as the likelihood
+	// kernels are instantiated for 1..5): larger networks are refused, never truncated
+	if (nd < 1 || nd > kFisherMaxDetectors)
+		return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher: at most 5 detectors per pass (pass detector_index >= 0 for larger networks)");
 	const GridPtrs g = grid_ptrs(ctx);
 	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
 	const int npairs = dim * (dim + 1) / 2;
@@ -1195,7 +1201,7 @@ int gwat_b200_fourier_waveform_batch(gwat_b200_ctx *ctx, const char *method, int
 	const size_t n = (size_t)W * ctx->L;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, 4 * n)) return GWAT_B200_ERR_CUDA;
 	double *o = ctx->d_out;
-	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const dim3 grid(W, (ctx->L + kThreads - 1) / kThreads);  // walkers on x: no 65535 limit on the batch
 	const GridPtrs g = grid_ptrs(ctx);
 	GWAT_DISPATCH_FAMILY(desc, k_waveform<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n, o + 2 * n, o + 3 * n));
 	ctx->launches += 1;
@@ -1225,7 +1231,7 @@ int gwat_b200_fourier_amplitude_phase_batch(gwat_b200_ctx *ctx, const char *meth
 	const size_t n = (size_t)W * ctx->L;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, 2 * n)) return GWAT_B200_ERR_CUDA;
 	double *o = ctx->d_out;
-	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const dim3 grid(W, (ctx->L + kThreads - 1) / kThreads);  // walkers on x: no 65535 limit on the batch
 	const GridPtrs g = grid_ptrs(ctx);
 	switch (desc.family_id) {
 	case FAM_D: k_amp_phase<Family<BASE_D, PPE_NONE, false, false>><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n); break;
@@ -1255,7 +1261,7 @@ static int response_common(gwat_b200_ctx *ctx, const char *method, int d0, int n
 	const size_t n = (size_t)W * nd * ctx->L;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, 2 * n)) return GWAT_B200_ERR_CUDA;
 	double *o = ctx->d_out;
-	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const dim3 grid(W, (ctx->L + kThreads - 1) / kThreads);  // walkers on x: no 65535 limit on the batch
 	const GridPtrs g = grid_ptrs(ctx);
 	GWAT_DISPATCH_FAMILY(desc, k_response<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, d0, nd, with_shift, o, o + n));
 	ctx->launches += 1;
@@ -1532,7 +1538,7 @@ int polarizations_dev(gwat_b200_ctx *ctx, const char *method, int W, const gwat_
 	const size_t n = (size_t)W * ctx->L;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, 4 * n)) return GWAT_B200_ERR_CUDA;
 	double *o = ctx->d_out;
-	const dim3 grid((ctx->L + kThreads - 1) / kThreads, W);
+	const dim3 grid(W, (ctx->L + kThreads - 1) / kThreads);  // walkers on x: no 65535 limit on the batch
 	const GridPtrs g = grid_ptrs(ctx);
 	GWAT_DISPATCH_FAMILY(desc, k_waveform<Fam><<<grid, kThreads, 0, st>>>(ctx->d_coef, g, o, o + n, o + 2 * n, o + 3 * n));
 	ctx->launches += 1;

@@ -183,7 +183,8 @@ extern "C" int gwat_b200_loglike_maximized_batch(gwat_b200_ctx *ctx, const char 
 		s.equatorial_orientation = 0;
 	}
 	const size_t per_walker = (size_t)D * npol * L * sizeof(cufftDoubleComplex);
-	const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, ((size_t)1 << 30) / per_walker));
+	// walkers per pass: a 1 GiB FFT buffer, and gridDim.y of k_max_fill (65535)
+	const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)W, 65535), ((size_t)1 << 30) / per_walker));
 	Scratch sc;
 	MCUDA(ctx, cudaMalloc((void **)&sc.buf, (size_t)chunk * per_walker));
 	MCUDA(ctx, cudaMalloc((void **)&sc.norms, (size_t)chunk * D * 3 * sizeof(double)));

@@ -51,14 +51,36 @@ Session &session()
 	return s;
 }
 
+// Identity of an input array for the network cache: its address, its length and a word-wise FNV-1a over 64 evenly spaced
+// samples plus both ends.  A caller that overwrites an array in place between calls (same address, same length) with values
+// that differ only between the samples must call gwat_b200_gwatpy_invalidate_network(); the reference's wrappers have no such
+// cache because they re-read everything on every call, which is exactly the cost this avoids (cfg5: 100 MB per call).
+uint64_t fnv_word(uint64_t h, uint64_t w)
+{
+	h ^= w;
+	h *= 1099511628211ULL;
+	return h;
+}
 uint64_t fnv(uint64_t h, const void *p, size_t n)
 {
 	const unsigned char *b = static_cast<const unsigned char *>(p);
-	for (size_t i = 0; i < n; i++) {
-		h ^= b[i];
-		h *= 1099511628211ULL;
-	}
+	for (size_t i = 0; i < n; i++) h = fnv_word(h, b[i]);
 	return h;
+}
+uint64_t array_key(uint64_t h, const double *a, size_t n)
+{
+	h = fnv_word(h, (uint64_t)(uintptr_t)a);
+	h = fnv_word(h, (uint64_t)n);
+	if (!a || n == 0) return h;
+	const size_t step = n > 64 ? n / 64 : 1;
+	for (size_t i = 0; i < n; i += step) {
+		uint64_t w;
+		std::memcpy(&w, a + i, sizeof(w));
+		h = fnv_word(h, w);
+	}
+	uint64_t w;
+	std::memcpy(&w, a + (n - 1), sizeof(w));
+	return fnv_word(h, w);
 }
 
 const char *detector_from_letter(char c)
@@ -95,12 +117,12 @@ int ensure_network(Session &S, int D, const char *const *dets, int L, const doub
 	key = fnv(key, &D, sizeof(D));
 	key = fnv(key, &L, sizeof(L));
 	for (int d = 0; d < D; d++) key = fnv(key, dets[d], std::strlen(dets[d]));
-	key = fnv(key, f, sizeof(double) * L);
-	key = fnv(key, psd, sizeof(double) * (size_t)D * L);
-	if (dre) key = fnv(key, dre, sizeof(double) * (size_t)D * L);
-	if (dim) key = fnv(key, dim, sizeof(double) * (size_t)D * L);
+	key = array_key(key, f, (size_t)L);
+	key = array_key(key, psd, (size_t)D * L);
+	key = array_key(key, dre, dre ? (size_t)D * L : 0);
+	key = array_key(key, dim, dim ? (size_t)D * L : 0);
 	const bool gl = integ && std::string(integ) == "GAUSSLEG";
-	if (gl && weights) key = fnv(key, weights, sizeof(double) * L);
+	key = array_key(key, (gl && weights) ? weights : nullptr, (gl && weights) ? (size_t)L : 0);
 	key = fnv(key, integ ? integ : "", integ ? std::strlen(integ) : 0);
 	key = fnv(key, &log10F, sizeof(log10F));
 	if (key == S.net_key) return 0;
@@ -182,6 +204,11 @@ void *gen_params_base_py(double mass1, double mass2, double *spin1, double *spin
 {
 	(void)LISA_alpha0;
 	(void)LISA_phi0;
+	for (int n : {Nmod_phi, Nmod_sigma, Nmod_beta, Nmod_alpha, Nmod})
+		if (n > GWAT_B200_MAX_MOD) {  // never evaluated with terms silently dropped
+			std::fprintf(stderr, "gwat_b200: gen_params_base_py: more than %d modifications of one kind are not supported\n", GWAT_B200_MAX_MOD);
+			return nullptr;
+		}
 	GenParams *p = new GenParams;
 	gwat_b200_source &s = p->s;
 	gwat_b200_source_init(&s);
@@ -213,7 +240,7 @@ void *gen_params_base_py(double mass1, double mass2, double *spin1, double *spin
 	s.shift_time = shift_time;
 	s.shift_phase = shift_phase;
 	s.sky_average = sky_average;
-	auto clampn = [](int n) { return n < 0 ? 0 : (n > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : n); };
+	auto clampn = [](int n) { return n < 0 ? 0 : n; };
 	s.Nmod_phi = clampn(Nmod_phi);
 	s.Nmod_sigma = clampn(Nmod_sigma);
 	s.Nmod_beta = clampn(Nmod_beta);
@@ -251,9 +278,14 @@ void *MCMC_modification_struct_py(int ppE_Nmod, double *bppe, int gIMR_Nmod_phi,
                                   int *gIMR_sigmai, int gIMR_Nmod_beta, int *gIMR_betai, int gIMR_Nmod_alpha, int *gIMR_alphai,
                                   bool NSflag1, bool NSflag2)
 {
+	for (int n : {ppE_Nmod, gIMR_Nmod_phi, gIMR_Nmod_sigma, gIMR_Nmod_beta, gIMR_Nmod_alpha})
+		if (n > GWAT_B200_MAX_MOD) {
+			std::fprintf(stderr, "gwat_b200: MCMC_modification_struct_py: more than %d modifications of one kind are not supported\n", GWAT_B200_MAX_MOD);
+			return nullptr;
+		}
 	ModStruct *m = new ModStruct;
 	gwat_b200_mod_init(&m->m);
-	auto clampn = [](int n) { return n < 0 ? 0 : (n > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : n); };
+	auto clampn = [](int n) { return n < 0 ? 0 : n; };
 	m->m.ppE_Nmod = clampn(ppE_Nmod);
 	for (int i = 0; i < m->m.ppE_Nmod; i++) m->m.bppe[i] = bppe[i];
 	m->m.gIMR_Nmod_phi = clampn(gIMR_Nmod_phi);
@@ -346,13 +378,16 @@ gwat_b200_source c_api_source(double mass1, double mass2, double DL, double s1x,
 	s.sky_average = 0;
 	return s;
 }
-void c_api_ppe(gwat_b200_source &s, const double *beta, const double *b, int Nmod)
+// false: more ppE terms than the flat record holds -> the caller returns status 0, nothing is evaluated
+bool c_api_ppe(gwat_b200_source &s, const double *beta, const double *b, int Nmod)
 {
-	s.Nmod = Nmod < 0 ? 0 : (Nmod > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : Nmod);
+	if (Nmod > GWAT_B200_MAX_MOD) return false;
+	s.Nmod = Nmod < 0 ? 0 : Nmod;
 	for (int i = 0; i < s.Nmod; i++) {
 		if (beta) s.betappe[i] = beta[i];
 		if (b) s.bppe[i] = b[i];
 	}
+	return true;
 }
 }  // namespace
 
@@ -366,7 +401,7 @@ int fourier_waveformC(double *frequencies, int length, double *waveform_plus_rea
 	s.tc = tc;
 	s.phiRef = phiRef;
 	s.f_ref = f_ref;
-	c_api_ppe(s, ppE_beta, ppE_b, Nmod);
+	if (!c_api_ppe(s, ppE_beta, ppE_b, Nmod)) return 0;
 	Session &S = session();
 	std::lock_guard<std::mutex> lock(S.mu);
 	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
@@ -398,7 +433,7 @@ int fourier_phaseC(double *frequencies, int length, double *phase, char *generat
 	s.tc = tc;
 	s.phiRef = phiRef;
 	s.f_ref = f_ref;
-	c_api_ppe(s, ppE_beta, ppE_b, Nmod);
+	if (!c_api_ppe(s, ppE_beta, ppE_b, Nmod)) return 0;
 	Session &S = session();
 	std::lock_guard<std::mutex> lock(S.mu);
 	if (ensure_grid_only(S, "Hanford", length, frequencies)) return 0;
@@ -596,6 +631,15 @@ int calculate_mass2_vectorized_py(double *chirpmass, double *eta, double *out, i
 {
 	for (int i = 0; i < length; i++) calculate_mass2_py(chirpmass[i], eta[i], out + i);
 	return 0;
+}
+
+// Forget the cached network: the next call re-uploads its arrays.  Needed only by callers that overwrite their frequency /
+// PSD / data arrays IN PLACE between calls (the cache key samples each array, see array_key).
+void gwat_b200_gwatpy_invalidate_network(void)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	S.net_key = 0;
 }
 
 // Why the last call failed ("" if it did not).

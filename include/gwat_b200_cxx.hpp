@@ -30,11 +30,12 @@
 
 namespace gwat_b200 {
 
-// gen_params_base<double>-like  ->  flat record (field for field; pointer members copied into the fixed arrays)
+// gen_params_base<double>-like  ->  flat record (field for field; pointer members copied into the fixed arrays).
+// Returns false -- and the caller reports failure (status 0 / NaN) -- when the source carries more modifications than the
+// flat record holds (GWAT_B200_MAX_MOD per kind): nothing is ever evaluated with terms silently dropped.
 template <class GenParams>
-inline gwat_b200_source flatten(const GenParams &g)
+inline bool flatten(const GenParams &g, gwat_b200_source &s)
 {
-	gwat_b200_source s;
 	gwat_b200_source_init(&s);
 	s.mass1 = g.mass1;
 	s.mass2 = g.mass2;
@@ -59,6 +60,8 @@ inline gwat_b200_source flatten(const GenParams &g)
 	s.delta_tidal_weighted = g.delta_tidal_weighted;
 	s.diss_tidal1 = g.diss_tidal1;
 	s.diss_tidal2 = g.diss_tidal2;
+	s.diss_tidal_s = g.diss_tidal_s;
+	s.diss_tidal_a = g.diss_tidal_a;
 	s.diss_tidal_weighted = g.diss_tidal_weighted;
 	s.chip = g.chip;
 	s.phip = g.phip;
@@ -75,7 +78,10 @@ inline gwat_b200_source flatten(const GenParams &g)
 	s.horizon_coord = g.horizon_coord;
 	if (g.equatorial_orientation) { s.theta_l = g.theta_l; s.phi_l = g.phi_l; }
 	if (g.horizon_coord) { s.theta = g.theta; s.phi = g.phi; }
-	auto clampn = [](int n) { return n < 0 ? 0 : (n > GWAT_B200_MAX_MOD ? GWAT_B200_MAX_MOD : n); };
+	const int counts[5] = {g.Nmod, g.Nmod_phi, g.Nmod_sigma, g.Nmod_beta, g.Nmod_alpha};
+	for (int n : counts)
+		if (n > GWAT_B200_MAX_MOD) return false;
+	auto clampn = [](int n) { return n < 0 ? 0 : n; };
 	s.Nmod = clampn(g.Nmod);
 	for (int i = 0; i < s.Nmod; i++) {
 		if (g.betappe) s.betappe[i] = g.betappe[i];
@@ -89,7 +95,7 @@ inline gwat_b200_source flatten(const GenParams &g)
 	for (int i = 0; i < s.Nmod_sigma; i++) { s.sigmai[i] = g.sigmai[i]; s.delta_sigma[i] = g.delta_sigma[i]; }
 	for (int i = 0; i < s.Nmod_beta; i++) { s.betai[i] = g.betai[i]; s.delta_beta[i] = g.delta_beta[i]; }
 	for (int i = 0; i < s.Nmod_alpha; i++) { s.alphai[i] = g.alphai[i]; s.delta_alpha[i] = g.delta_alpha[i]; }
-	return s;
+	return true;
 }
 
 // RAII handle on a context.  One per thread group that submits work; the uploaded network persists between calls.
@@ -148,8 +154,8 @@ template <class GenParams>
 inline int fourier_waveform(Engine &e, double *frequencies, int length, std::complex<double> *hplus, std::complex<double> *hcross,
                             const std::string &generation_method, GenParams *parameters)
 {
-	if (!e.ok() || detail::grid_only(e, "Hanford", frequencies, length) != 0) return 0;
-	const gwat_b200_source s = flatten(*parameters);
+	gwat_b200_source s;
+	if (!e.ok() || !flatten(*parameters, s) || detail::grid_only(e, "Hanford", frequencies, length) != 0) return 0;
 	std::vector<double> b((size_t)4 * length);
 	if (gwat_b200_fourier_waveform_batch(e.ctx(), generation_method.c_str(), 1, &s, &b[0], &b[length], &b[2 * (size_t)length],
 	                                     &b[3 * (size_t)length]) != 0)
@@ -166,8 +172,8 @@ template <class GenParams>
 inline int fourier_detector_response(Engine &e, double *frequencies, int length, std::complex<double> *response,
                                      const std::string &detector, const std::string &generation_method, GenParams *parameters)
 {
-	if (!e.ok() || detail::grid_only(e, detector, frequencies, length) != 0) return 0;
-	const gwat_b200_source s = flatten(*parameters);
+	gwat_b200_source s;
+	if (!e.ok() || !flatten(*parameters, s) || detail::grid_only(e, detector, frequencies, length) != 0) return 0;
 	std::vector<double> re(length), im(length);
 	if (gwat_b200_fourier_detector_response_batch(e.ctx(), generation_method.c_str(), detector.c_str(), 1, &s, re.data(), im.data()) != 0)
 		return 0;
@@ -182,8 +188,8 @@ inline void create_coherent_GW_detection(Engine &e, std::string *detectors, int 
                                          std::complex<double> **responses)
 {
 	const int L = lengths[0];
-	if (!e.ok() || e.set_network(detectors, detector_N, L, frequencies, nullptr, nullptr, nullptr, "SIMPSONS", false) != 0) return;
-	const gwat_b200_source s = flatten(*gen_params);
+	gwat_b200_source s;
+	if (!e.ok() || !flatten(*gen_params, s) || e.set_network(detectors, detector_N, L, frequencies, nullptr, nullptr, nullptr, "SIMPSONS", false) != 0) return;
 	std::vector<double> re((size_t)detector_N * L), im((size_t)detector_N * L);
 	if (gwat_b200_coherent_response_batch(e.ctx(), generation_method.c_str(), 1, &s, re.data(), im.data()) != 0) return;
 	for (int d = 0; d < detector_N; d++)
@@ -205,7 +211,8 @@ inline double MCMC_likelihood_extrinsic(Engine &e, bool /*save_waveform*/, GenPa
 	if (!e.ok()) return nan;
 	const int L = data_length[0];
 	if (reload && e.set_network(detectors, num_detectors, L, frequencies, psd, data, weights, integration_method, log10F) != 0) return nan;
-	gwat_b200_source s = flatten(*parameters);
+	gwat_b200_source s;
+	if (!flatten(*parameters, s)) return nan;
 	const double T = T_segment > 0 ? T_segment : 1. / (frequencies[0][1] - frequencies[0][0]);
 	s.tc = T - s.tc;  // tc_ref (src/mcmc_gw.cpp:2467,2473)
 	double ll = nan;
@@ -254,8 +261,8 @@ inline void fisher_numerical(Engine &e, double *frequency, int length, const std
 	const int D = detector == reference_detector ? 1 : 2;
 	double *f2[2] = {frequency, frequency};
 	double *p2[2] = {noise, noise};
-	if (e.set_network(dets, D, length, f2, p2, nullptr, nullptr, "SIMPSONS", false) != 0) return;
-	const gwat_b200_source s = flatten(*parameters);
+	gwat_b200_source s;
+	if (!flatten(*parameters, s) || e.set_network(dets, D, length, f2, p2, nullptr, nullptr, "SIMPSONS", false) != 0) return;
 	std::vector<double> flat((size_t)dimension * dimension);
 	if (gwat_b200_fisher_numerical_batch(e.ctx(), generation_method.c_str(), D - 1, 0, dimension, order, 1, &s, flat.data()) != 0) return;
 	for (int i = 0; i < dimension; i++)

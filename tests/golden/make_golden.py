@@ -62,7 +62,30 @@ def _gr_method(method):
     raise ValueError(method)
 
 
+def fisher_noise():
+    """The self-difference yardstick of every Fisher golden matrix (tests/fisher_noise.py): largest normalised difference among
+    the FMA-contracted build and four re-evaluations on inputs moved by parts in 1e14."""
+    import fisher_noise as FN
+    f = cases.grid(cases.FISHER_GRID)
+    psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+    out = {}
+    for name, method, kw, dim in cases.FISHER_CASES:
+        src = cases.source(kw)
+        row = []
+        for order in (2, 4):
+            for d, det in list(enumerate(cases.DETECTORS[:2])) + [(-1, "sum")]:
+                if d < 0 and order == 2:
+                    continue
+                v = FN.reference_self_difference(R, method, [src], cases.DETECTORS, f, psd, dim, order, detector_index=d, nthreads=1)[0]
+                out["%s/o%d/%s" % (name, order, det)] = np.array(v)
+                row.append("%.1e" % v)
+        print("%-10s self-difference %s" % (name, " ".join(row)))
+    np.savez_compressed(os.path.join(HERE, "fisher_noise_v2.npz"), **out)
+
+
 def main():
+    if "--only-fisher-noise" in sys.argv:
+        return fisher_noise()
     if "--only-maximized" in sys.argv:
         return maximized()
     if "--only-theories" in sys.argv:
@@ -131,7 +154,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mcmc_v1.npz"), **mo)
     maximized()
     theories()
-    for fn in ("theories_v1.npz", "waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz", "maximized_v1.npz"):
+    fisher_noise()
+    for fn in ("fisher_noise_v2.npz", "theories_v1.npz", "waveforms_v1.npz", "fisher_v1.npz", "mcmc_v1.npz", "smoke_cfg2.npz", "maximized_v1.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
 
 
