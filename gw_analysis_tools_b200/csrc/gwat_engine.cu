@@ -370,6 +370,60 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	coefs[t] = wc;
 }
 
+// One bin of the stencil of one (source, parameter): the derivative of every detector's response with respect to the parameter,
+// times the log-parameter factor (:462-484, 548-554), handed to store(d, value) detector by detector.
+//   w[k], tc_s[k * tcs_stride + d]   the coefficient blocks and per-detector time coefficients of the npts stencil points
+//   shared_parts                     the intrinsic part of the source is bit-identical at all points (RA, DEC, psi)
+// Returns false when every point is exactly zero at this bin (above all cutoffs); zeros are stored then.
+template <class Fam, class Store>
+__device__ __forceinline__ bool fisher_deriv_bin(const WalkerCoef *w, const double *tc_s, int tcs_stride, int npts, int nd, bool shared_parts,
+                                                 bool bc, double sc, double f, double hi, double lo, double lg, const Store &store)
+{
+	const double epsilon = 1e-8;
+	PolParts pp[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
+		if (k >= npts) continue;
+		if (k > 0 && shared_parts) pp[k] = pp[0];
+		else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
+	}
+	bool live = false;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (k < npts) live = live || !w[k].valid || !pp[k].zero;
+	if (!live) {
+		for (int d = 0; d < nd; d++) store(d, cplx{0.0, 0.0});
+		return false;
+	}
+	for (int d = 0; d < nd; d++) {
+		cplx r[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (k >= npts) continue;
+			if (!w[k].valid) {
+				r[k] = cplx{NAN, NAN};
+				continue;
+			}
+			// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8
+			// instead of 12 finishes for three detectors -- measured 11 % slower: 40 more live registers)
+			cplx hp, hc;
+			polarizations_finish<Fam>(w[k], pp[k], tc_s[k * tcs_stride + d], f, hp, hc);
+			r[k] = project_bin(w[k].det[d], hp, hc, f, true);
+		}
+		cplx dv;
+		if (npts == 2) {
+			const double den = bc ? epsilon : 2. * epsilon;
+			dv = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
+		} else {
+			const double den = bc ? 6. * epsilon : 12. * epsilon;
+			dv = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
+			          (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
+		}
+		store(d, cplx{dv.re * sc, dv.im * sc});
+	}
+	return true;
+}
+
 // deriv[d][s][i][bin] = stencil combination of the responses, times the log-parameter factor (:462-484, 548-554).
 // grid (bin tiles, sources x parameters): the time-independent parts of the 2 or 4 stencil points are evaluated once per bin
 // -- once for ALL points when the parameter is RA, DEC or psi, which only move the antenna patterns and arrival times --
@@ -420,7 +474,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 	// parameters 0..2 are RA, DEC (or sin DEC) and psi in every parameterisation (src/fisher.cpp:46-66): the intrinsic part of
 	// the source, and with it everything in PolParts, is bit-identical at all stencil points
 	const bool shared_parts = (int)(blockIdx.y % dim) < 3;
-	const double epsilon = 1e-8;
 	const bool bc = eta_bc[blockIdx.y] != 0;
 	const double sc = scale[blockIdx.y];
 	// several tiles per CTA: the 4 coefficient blocks (5.7 KB) are staged once for 1024 bins instead of once per 256
@@ -433,58 +486,133 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 		const bool in_grid = bin_raw < g.L;
 		const int bin = in_grid ? bin_raw : g.L - 1;  // (tail threads shadow the last bin and store nothing: everyone reaches the barrier below)
 		const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
-		PolParts pp[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
-			if (k >= npts) continue;
-			if (k > 0 && shared_parts) pp[k] = pp[0];
-			else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
-		}
+		auto store = [&](int d, const cplx &dv) {
+			if (!in_grid) return;
+			const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
+			dre[o] = dv.re;
+			dim_[o] = dv.im;
+		};
 		// Bins above every stencil point's cutoff have exactly zero responses: nothing to evaluate, and k_fisher_assemble need
 		// not read them -- the highest live bin of each source is recorded (one atomic per tile).  Invalid points (NaN) keep every bin.
-		bool live = false;
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if (k < npts) live = live || !w[k].valid || !pp[k].zero;
+		const bool live = fisher_deriv_bin<Fam>(w, &tc_s[0][0], kFisherMaxDetectors, npts, nd, shared_parts, bc, sc, f, hi, lo, lg, store);
 		const int any_live = __syncthreads_or(live && in_grid);
 		if (threadIdx.x == 0 && any_live) atomicMax(&bin_limit[blockIdx.y / dim], min(g.L, (t + 1) * kThreads));
-		if (!in_grid) continue;
-		if (!live) {
-			for (int d = 0; d < nd; d++) {
-				const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
-				dre[o] = 0.0;
-				dim_[o] = 0.0;
-			}
-			continue;
+	}
+}
+
+// ---- fused stencil + assembly -------------------------------------------------------------------------------------------------
+// One CTA per source, one WARP per parameter: the dim x npts coefficient blocks of the source are staged in shared memory
+// once (dim 11, order 4: 62 KB), then the CTA walks the live part of the grid in tiles of 32 bins.  Per tile every warp
+// evaluates its parameter's derivative of all detector responses (lane = bin; exactly the arithmetic of k_fisher_deriv) and
+// parks sqrt(w_d) x (Re, Im) in a [detector, Re/Im, bin][parameter] tile; after a barrier the whole CTA adds the tile's
+// contribution to the dim (dim + 1) / 2 inner products F_jk = sum w_d Re(d_j conj d_k) (calculate_fisher_elements,
+// src/fisher.cpp:2704-2781), each thread keeping ONE running sum in a register over all tiles.  The derivative rows never go
+// to HBM (the unfused path writes and re-reads 2 D dim L 8 B = 2.2 MB per source), nothing is atomic, and a source's matrix
+// does not depend on the batch it is evaluated in: the order of every sum is a function of (dim, D, L) alone.
+constexpr int kFusedTileBins = 32;
+
+struct FusedLayout {
+	int rows_p;      // dim rounded up to even: row stride of the derivative tile
+	int K;           // nd * 2 * kFusedTileBins values per parameter and tile
+	int npairs, slices;
+	size_t off_tc, off_z, off_red, bytes;
+};
+__host__ __device__ inline FusedLayout fused_layout(int dim, int npts, int nd)
+{
+	FusedLayout l;
+	l.rows_p = (dim + 1) & ~1;
+	l.K = nd * 2 * kFusedTileBins;
+	l.npairs = dim * (dim + 1) / 2;
+	l.slices = (dim * 32) / l.npairs;  // >= 2 for every dim <= 32
+	size_t o = (size_t)dim * npts * sizeof(WalkerCoef);
+	l.off_tc = o;
+	o += sizeof(double) * (size_t)dim * npts * nd;
+	l.off_z = o;
+	o += sizeof(double) * (size_t)l.K * l.rows_p;
+	l.off_red = o;
+	o += sizeof(double) * (size_t)l.slices * l.npairs;
+	l.bytes = o;
+	return l;
+}
+
+template <class Fam, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCoef *__restrict__ coefs, const double *__restrict__ tcoef, GridPtrs g,
+                                                                  const double *__restrict__ wq, int npts, int nd, int dim,
+                                                                  const double *__restrict__ scale, const int *__restrict__ eta_bc,
+                                                                  double prefactor, double *__restrict__ out)
+{
+	extern __shared__ __align__(16) unsigned char fused_smem[];
+	const FusedLayout lay = fused_layout(dim, npts, nd);
+	WalkerCoef *w_all = reinterpret_cast<WalkerCoef *>(fused_smem);
+	double *tc_all = reinterpret_cast<double *>(fused_smem + lay.off_tc);
+	double *Z = reinterpret_cast<double *>(fused_smem + lay.off_z);
+	double *red = reinterpret_cast<double *>(fused_smem + lay.off_red);
+	const int s = blockIdx.x, lane = threadIdx.x & 31, param = threadIdx.x >> 5;
+	{
+		const double *sp = reinterpret_cast<const double *>(coefs + (size_t)s * dim * npts);
+		double *dp = reinterpret_cast<double *>(w_all);
+		for (int i = threadIdx.x; i < (int)(dim * npts * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
+		for (int i = threadIdx.x; i < dim * npts * nd; i += blockDim.x) tc_all[i] = tcoef[(size_t)s * dim * npts * nd + i];
+		if (lay.rows_p != dim)
+			for (int i = threadIdx.x; i < lay.K; i += blockDim.x) Z[i * lay.rows_p + dim] = 0.0;  // the padding row
+		__syncthreads();
+	}
+	// the live part of an ascending grid ends at the highest cutoff of any stencil point (all points valid), else it is all of it
+	double fmax_all = INFINITY;
+	if (g.uniform) {
+		bool all_valid = true;
+		double fm = 0.0;
+		for (int k = 0; k < dim * npts; k++) {
+			all_valid = all_valid && w_all[k].valid;
+			fm = fmax(fm, walker_fmax<Fam>(w_all[k]));
 		}
-		for (int d = 0; d < nd; d++) {
-			cplx r[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				if (k >= npts) continue;
-				if (!w[k].valid) {
-					r[k] = cplx{NAN, NAN};
-					continue;
-				}
-				// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8
-				// instead of 12 finishes for three detectors -- measured 11 % slower: 40 more live registers)
-				cplx hp, hc;
-				polarizations_finish<Fam>(w[k], pp[k], tc_s[k][d], f, hp, hc);
-				r[k] = project_bin(w[k].det[d], hp, hc, f, true);
-			}
-			cplx dv;
-			if (npts == 2) {
-				const double den = bc ? epsilon : 2. * epsilon;
-				dv = cplx{(r[0].re - r[1].re) / den, (r[0].im - r[1].im) / den};
-			} else {
-				const double den = bc ? 6. * epsilon : 12. * epsilon;
-				dv = cplx{(((-r[2].re + 8. * r[0].re) - 8. * r[1].re) + r[3].re) / den,
-				          (((-r[2].im + 8. * r[0].im) - 8. * r[1].im) + r[3].im) / den};
-			}
-			const size_t o = ((size_t)d * gridDim.y + blockIdx.y) * g.L + bin;
-			dre[o] = dv.re * sc;
-			dim_[o] = dv.im * sc;
+		if (all_valid) fmax_all = fm;
+	}
+	const WalkerCoef *w = w_all + param * npts;
+	const double *tc_s = tc_all + param * npts * nd;
+	const bool shared_parts = param < 3;  // RA, DEC (or sin DEC), psi: see k_fisher_deriv
+	const bool bc = eta_bc[(size_t)s * dim + param] != 0;
+	const double sc = scale[(size_t)s * dim + param];
+	// inner-product ownership: thread -> (pair, slice); the threads of a warp hold consecutive pairs of one slice, so the
+	// reads of a k-row are broadcasts out of one or two 128-byte lines
+	const int gp = threadIdx.x % lay.npairs, gs = threadIdx.x / lay.npairs;
+	int pj = 0, pk = gp;
+	while (pk > pj) {
+		pk -= pj + 1;
+		pj++;
+	}
+	double acc = 0.0;
+	const int ntiles = (g.L + kFusedTileBins - 1) / kFusedTileBins;
+	for (int t = 0; t < ntiles; t++) {
+		const int bin0 = t * kFusedTileBins;
+		if (g.f[bin0] > fmax_all) break;  // (the same for the whole CTA)
+		const int bin_raw = bin0 + lane;
+		const bool in_grid = bin_raw < g.L;
+		const int bin = in_grid ? bin_raw : g.L - 1;
+		const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
+		auto store = [&](int d, const cplx &dv) {
+			// sqrt(w) on both factors of the product: w >= 0 (quadrature coefficient / PSD); bins of the last tile beyond L weigh 0
+			const double rw = in_grid ? sqrt(wq[(size_t)d * g.ld + bin]) : 0.0;
+			Z[((d * 2 + 0) * kFusedTileBins + lane) * lay.rows_p + param] = in_grid ? rw * dv.re : 0.0;
+			Z[((d * 2 + 1) * kFusedTileBins + lane) * lay.rows_p + param] = in_grid ? rw * dv.im : 0.0;
+		};
+		fisher_deriv_bin<Fam>(w, tc_s, nd, npts, nd, shared_parts, bc, sc, f, hi, lo, lg, store);
+		__syncthreads();
+		if (gs < lay.slices) {
+			const double *zj = Z + pj, *zk = Z + pk;
+			for (int k = gs; k < lay.K; k += lay.slices) acc = fma(zj[k * lay.rows_p], zk[k * lay.rows_p], acc);
 		}
+		__syncthreads();
+	}
+	if (gs < lay.slices) red[gs * lay.npairs + gp] = acc;
+	__syncthreads();
+	if (threadIdx.x < lay.npairs) {
+		double total = 0.0;
+		for (int q = 0; q < lay.slices; q++) total += red[q * lay.npairs + threadIdx.x];
+		total *= prefactor;
+		double *o = out + (size_t)s * dim * dim;
+		o[pj * dim + pk] = total;
+		o[pk * dim + pj] = total;
 	}
 }
 
@@ -853,32 +981,63 @@ int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const 
 }
 
 // ---- Fisher passes shared by the host-source entry point and the sampler's device-parameter entry point ------------------
-int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim, int nd)
+// The fused kernel (one CTA per source, one warp per parameter) is used whenever its shared-memory footprint fits; otherwise
+// (dimension > 16) the stencil and the assembly run as two kernels with the derivative rows in HBM.
+bool fisher_fused_fits(int dim, int npts, int nd)
 {
+	return dim <= 16 && fused_layout(dim, npts, nd).bytes <= (size_t)227 * 1024;
+}
+
+int fisher_chunk_size(const gwat_b200_ctx *ctx, int S, int dim, int npts, int nd, bool fused)
+{
+	if (fused) {
+		// sources per pass: bounded by 1 GiB of coefficient blocks (cfg3: 17 k sources)
+		const size_t per_source = (size_t)dim * npts * sizeof(WalkerCoef);
+		return (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)1024 << 20) / per_source));
+	}
 	// sources per pass: bounded by a 2 GiB derivative buffer
 	const size_t per_source = (size_t)dim * ctx->L * 16 * nd;
 	const size_t by_memory = ((size_t)2048 << 20) / per_source, by_grid = 65535 / (size_t)dim;  // gridDim.y = sources * dim
 	return (int)std::max<size_t>(1, std::min<size_t>((size_t)S, std::min(by_memory, by_grid)));
 }
 
-int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts, int nd)
+int fisher_reserve(gwat_b200_ctx *ctx, int chunk, int dim, int npts, int nd, bool fused)
 {
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)chunk * dim * npts)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_tcoef, ctx->cap_tcoef, (size_t)chunk * dim * npts * nd)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_binlim, ctx->cap_binlim, (size_t)chunk)) return GWAT_B200_ERR_CUDA;
-	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L * nd)) return GWAT_B200_ERR_CUDA;
+	if (!fused && grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * ctx->L * nd)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_scale, ctx->cap_scale, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_bc, ctx->cap_bc, (size_t)chunk * dim)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_fisher, ctx->cap_fisher, (size_t)chunk * dim * dim)) return GWAT_B200_ERR_CUDA;
 	return 0;
 }
 
-// ctx->d_src[0..ns) -> ctx->d_fisher[ns][dim][dim], detectors d0..d1-1 summed; one launch of each kernel for all detectors
+template <class Fam>
+int launch_fisher_fused(gwat_b200_ctx *ctx, const FisherPlan &fp, int ns, const GridPtrs &g, const double *wq, double *d_out, cudaStream_t st)
+{
+	const int dim = fp.rp.dimension;
+	const FusedLayout lay = fused_layout(dim, fp.npts, fp.nd);
+#define GWAT_FUSED_LAUNCH(MAXW, MINB)                                                                                                    \
+	do {                                                                                                                                   \
+		auto kern = k_fisher_fused<Fam, MAXW, MINB>;                                                                                         \
+		CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));                              \
+		kern<<<ns, dim * 32, lay.bytes, st>>>(ctx->d_coef, ctx->d_tcoef, g, wq, fp.npts, fp.nd, dim, ctx->d_scale, ctx->d_bc, ctx->pref_fisher, d_out); \
+	} while (0)
+	if (dim <= 12) GWAT_FUSED_LAUNCH(12, 2);
+	else GWAT_FUSED_LAUNCH(16, 1);
+#undef GWAT_FUSED_LAUNCH
+	return 0;
+}
+
+// d_src[0..ns) -> d_out[ns][dim][dim], detectors d0..d1-1 summed; one launch of each kernel for all detectors
 int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int ns, int chunk, int d0, int d1,
-                 int reference_index, cudaStream_t st)
+                 int reference_index, cudaStream_t st, const gwat_b200_source *d_src = nullptr, double *d_out = nullptr)
 {
 	const int L = ctx->L, dim = fp.rp.dimension, nd = d1 - d0;
+	if (!d_src) d_src = ctx->d_src;
+	if (!d_out) d_out = ctx->d_fisher;
 	// FisherPlan::det_row and the kernels' staging arrays hold kFisherMaxDetectors detectors per pass (as the likelihood
 	// kernels are instantiated for 1..5): larger networks are refused, never truncated
 	if (nd < 1 || nd > kFisherMaxDetectors)
@@ -893,8 +1052,16 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 		fp.det_is_ref[d] = (std::memcmp(fp.det_row[d], fp.ref_row, sizeof(fp.ref_row)) == 0) ? 1 : 0;
 	}
 	const int nthreads = ns * dim * fp.npts;
-	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(ctx->d_src, ns, fp, ctx->d_coef, ctx->d_tcoef,
+	GWAT_DISPATCH_FAMILY(desc, k_fisher_setup<Fam><<<(nthreads + 127) / 128, 128, 0, st>>>(d_src, ns, fp, ctx->d_coef, ctx->d_tcoef,
 	                                                                                        ctx->d_scale, ctx->d_bc));
+	static const bool no_fused = getenv("GWAT_B200_FISHER_UNFUSED") != nullptr;  // experiments / A-B tests only
+	if (!no_fused && fisher_fused_fits(dim, fp.npts, nd)) {
+		GWAT_DISPATCH_FAMILY(desc, if (int rc = launch_fisher_fused<Fam>(ctx, fp, ns, g, wq_fisher_all + (size_t)d0 * ctx->ld, d_out, st)) return rc);
+		ctx->launches += 2;
+		CUDA_TRY(ctx, cudaGetLastError());
+		return 0;
+	}
+	if (grow(ctx, ctx->d_deriv, ctx->cap_deriv, (size_t)2 * chunk * dim * L * nd)) return GWAT_B200_ERR_CUDA;
 	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_binlim, 0, sizeof(int) * ns, st));
 	const int ntiles = (L + kThreads - 1) / kThreads;
 	const dim3 gd((ntiles + kFisherTilesPerCta - 1) / kFisherTilesPerCta, ns * dim);
@@ -902,7 +1069,7 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 	GWAT_DISPATCH_FAMILY(desc, k_fisher_deriv<Fam><<<gd, kThreads, 0, st>>>(ctx->d_coef, ctx->d_tcoef, g, fp.npts, nd, dim, ctx->d_scale,
 	                                                                         ctx->d_bc, dre, dim_, ctx->d_binlim));
 	k_fisher_assemble<<<dim3(npairs, ns), kThreads, 0, st>>>(dre, dim_, wq_fisher_all + (size_t)d0 * ctx->ld, ctx->ld, L, dim, ns, nd,
-	                                                          ctx->pref_fisher, ctx->d_binlim, ctx->d_fisher);
+	                                                          ctx->pref_fisher, ctx->d_binlim, d_out);
 	ctx->launches += 3;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -1037,6 +1204,17 @@ void gwat_b200_ctx_destroy(gwat_b200_ctx *c)
 		if (l.ev_a) cudaEventDestroy(l.ev_a);
 		if (l.ev_b) cudaEventDestroy(l.ev_b);
 	}
+	for (auto &fs : c->fstage) {
+		if (fs.h_src) cudaFreeHost(fs.h_src);
+		if (fs.h_out) cudaFreeHost(fs.h_out);
+		cudaFree(fs.d_src);
+		cudaFree(fs.d_out);
+		if (fs.ev_in) cudaEventDestroy(fs.ev_in);
+		if (fs.ev_done) cudaEventDestroy(fs.ev_done);
+		if (fs.ev_out) cudaEventDestroy(fs.ev_out);
+	}
+	if (c->copy_in) cudaStreamDestroy(c->copy_in);
+	if (c->copy_out) cudaStreamDestroy(c->copy_out);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -1385,8 +1563,8 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 		std::lock_guard<std::mutex> lock(ctx->mu);
 		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 		cudaStream_t st = ctx->stream;
-		const int chunk = fisher_chunk_size(ctx, S, 7, 1);
-		if (int rc = fisher_reserve(ctx, chunk, 7, fp.npts + 1, 1)) return rc;
+		const int chunk = fisher_chunk_size(ctx, S, 7, fp.npts + 1, 1, false);
+		if (int rc = fisher_reserve(ctx, chunk, 7, fp.npts + 1, 1, false)) return rc;
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 		for (int s0 = 0; s0 < S; s0 += chunk) {
 			const int ns = std::min(chunk, S - s0);
@@ -1437,21 +1615,79 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	const int L = ctx->L, dim = dimension;
 	const int d0 = detector_index < 0 ? 0 : detector_index;
 	const int d1 = detector_index < 0 ? ctx->D : detector_index + 1;
-	const int chunk = fisher_chunk_size(ctx, S, dim, d1 - d0);
-	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, d1 - d0)) return rc;
+	const bool fused = fisher_fused_fits(dim, fp.npts, d1 - d0) && getenv("GWAT_B200_FISHER_UNFUSED") == nullptr;
+	// passes of at most `chunk` sources; at least four passes for big batches so that the copies have kernels to hide behind
+	int chunk = fisher_chunk_size(ctx, S, dim, fp.npts, d1 - d0, fused);
+	if (S >= 4096) chunk = std::min(chunk, (S + 3) / 4);
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, d1 - d0, fused)) return rc;
+	// The caller's arrays are pageable: a cudaMemcpyAsync on them is staged by the driver and the D2H one blocks the host
+	// until the pass has finished, so the next pass cannot even be enqueued (measured in round 1: 1 ms of idle GPU per 3.4 ms
+	// pass).  Two pinned staging sets and two device source/result sets: pass k+1's sources travel and pass k-1's matrices
+	// return while pass k computes.
+	if (!ctx->copy_in) {
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+		for (auto &fs : ctx->fstage) {
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&fs.ev_in, cudaEventDisableTiming));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&fs.ev_done, cudaEventDisableTiming));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&fs.ev_out, cudaEventDisableTiming));
+		}
+	}
+	const size_t out_per = (size_t)dim * dim;
+	for (auto &fs : ctx->fstage) {
+		if (fs.cap_src < (size_t)chunk) {
+			if (fs.h_src) cudaFreeHost(fs.h_src);
+			if (fs.d_src) cudaFree(fs.d_src);
+			fs.h_src = nullptr;
+			fs.d_src = nullptr;
+			fs.cap_src = 0;
+			CUDA_TRY(ctx, cudaHostAlloc((void **)&fs.h_src, sizeof(gwat_b200_source) * chunk, cudaHostAllocDefault));
+			CUDA_TRY(ctx, cudaMalloc((void **)&fs.d_src, sizeof(gwat_b200_source) * chunk));
+			fs.cap_src = chunk;
+		}
+		if (fs.cap_out < (size_t)chunk * out_per) {
+			if (fs.h_out) cudaFreeHost(fs.h_out);
+			if (fs.d_out) cudaFree(fs.d_out);
+			fs.h_out = nullptr;
+			fs.d_out = nullptr;
+			fs.cap_out = 0;
+			CUDA_TRY(ctx, cudaHostAlloc((void **)&fs.h_out, sizeof(double) * chunk * out_per, cudaHostAllocDefault));
+			CUDA_TRY(ctx, cudaMalloc((void **)&fs.d_out, sizeof(double) * chunk * out_per));
+			fs.cap_out = (size_t)chunk * out_per;
+		}
+	}
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-	for (int s0 = 0; s0 < S; s0 += chunk) {
-		const int ns = std::min(chunk, S - s0);
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, sources + s0, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, st));
-		if (int rc = fisher_chunk(ctx, desc, fp, ns, chunk, d0, d1, reference_index, st)) return rc;
-		CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * dim * dim, ctx->d_fisher, sizeof(double) * ns * dim * dim,
-		                              cudaMemcpyDeviceToHost, st));
+	const int npass = (S + chunk - 1) / chunk;
+	auto drain = [&](int pass) -> int {  // pass's matrices: pinned staging -> the caller's array
+		auto &fs = ctx->fstage[pass & 1];
+		const int s0 = pass * chunk, ns = std::min(chunk, S - s0);
+		CUDA_TRY(ctx, cudaEventSynchronize(fs.ev_out));
+		std::memcpy(fisher + (size_t)s0 * out_per, fs.h_out, sizeof(double) * ns * out_per);
+		return 0;
+	};
+	for (int pass = 0; pass < npass; pass++) {
+		auto &fs = ctx->fstage[pass & 1];
+		const int s0 = pass * chunk, ns = std::min(chunk, S - s0);
+		if (pass >= 2)
+			if (int rc = drain(pass - 2)) return rc;  // (also: the set's previous H2D and kernels are long done)
+		std::memcpy(fs.h_src, sources + s0, sizeof(gwat_b200_source) * ns);
+		CUDA_TRY(ctx, cudaMemcpyAsync(fs.d_src, fs.h_src, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, ctx->copy_in));
+		CUDA_TRY(ctx, cudaEventRecord(fs.ev_in, ctx->copy_in));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(st, fs.ev_in, 0));
+		if (int rc = fisher_chunk(ctx, desc, fp, ns, chunk, d0, d1, reference_index, st, fs.d_src, fs.d_out)) return rc;
+		CUDA_TRY(ctx, cudaEventRecord(fs.ev_done, st));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, fs.ev_done, 0));
+		CUDA_TRY(ctx, cudaMemcpyAsync(fs.h_out, fs.d_out, sizeof(double) * ns * out_per, cudaMemcpyDeviceToHost, ctx->copy_out));
+		CUDA_TRY(ctx, cudaEventRecord(fs.ev_out, ctx->copy_out));
 	}
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+	for (int pass = std::max(0, npass - 2); pass < npass; pass++)
+		if (int rc = drain(pass)) return rc;
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	float ms = 0;
 	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = ms;
+	(void)L;
 	return GWAT_B200_OK;
 }
 
@@ -1566,8 +1802,9 @@ int fisher_mcmc_dev(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod 
 	fp.npts = order == 4 ? 4 : 2;
 	fp.theory = desc.theory;
 	const int dim = dimension;
-	const int chunk = fisher_chunk_size(ctx, S, dim, ctx->D);
-	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, ctx->D)) return rc;
+	const bool fused = fisher_fused_fits(dim, fp.npts, ctx->D) && getenv("GWAT_B200_FISHER_UNFUSED") == nullptr;
+	const int chunk = fisher_chunk_size(ctx, S, dim, fp.npts, ctx->D, fused);
+	if (int rc = fisher_reserve(ctx, chunk, dim, fp.npts, ctx->D, fused)) return rc;
 	for (int s0 = 0; s0 < S; s0 += chunk) {
 		const int ns = std::min(chunk, S - s0);
 		k_repack_only<<<(ns + 127) / 128, 128, 0, st>>>(d_params + (size_t)s0 * dim, ns, rp, gmst, ctx->d_src);

@@ -53,6 +53,15 @@ struct gwat_b200_ctx {
 	int *d_bc = nullptr;
 	int *d_binlim = nullptr;  // per source: bins from here on have exactly zero derivatives (Fisher passes)
 	size_t cap_binlim = 0;
+	// Fisher batches through host buffers: two pinned staging sets and two device source/result sets, so that the copies of
+	// pass k+1 and k-1 overlap the kernels of pass k (the caller's arrays are pageable)
+	struct FisherStage {
+		gwat_b200_source *h_src = nullptr, *d_src = nullptr;
+		double *h_out = nullptr, *d_out = nullptr;
+		size_t cap_src = 0, cap_out = 0;
+		cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+	} fstage[2];
+	cudaStream_t copy_in = nullptr, copy_out = nullptr;
 	// two more sets of likelihood scratch for callers that keep several batches in flight on their own streams (the
 	// ensemble sampler); swapped in by LaneSwap while the caller holds `mu`
 	LikeLane extra[2];

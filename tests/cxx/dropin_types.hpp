@@ -17,7 +17,7 @@ struct test_gen_params {
 	double tidal1 = -1, tidal2 = -1, tidal_s = -1, tidal_a = -1, tidal_weighted = -1;
 	bool tidal_love = true, tidal_love_error = false;
 	double delta_tidal_weighted = -1;
-	double diss_tidal1 = -1, diss_tidal2 = -1, diss_tidal_weighted = -1;
+	double diss_tidal1 = -1, diss_tidal2 = -1, diss_tidal_s = -1, diss_tidal_a = -1, diss_tidal_weighted = -1;
 	double psi = 0, incl_angle;
 	bool equatorial_orientation = false;
 	double theta_l, phi_l;
