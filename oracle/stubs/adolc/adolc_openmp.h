@@ -4,4 +4,8 @@
 #include "adolc/adouble.h"
 #include "adolc/taping.h"
 #include "adolc/drivers/drivers.h"
+// real ADOL-C: `firstprivate(ADOLC_OpenMP_Handler)`, a clause for `#pragma omp parallel`; nothing to privatise without taping
+#ifndef ADOLC_OPENMP
+#define ADOLC_OPENMP
+#endif
 #endif

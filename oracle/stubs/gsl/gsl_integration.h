@@ -10,4 +10,6 @@ inline gsl_integration_workspace *gsl_integration_workspace_alloc(size_t n) { gs
 inline void gsl_integration_workspace_free(gsl_integration_workspace *w) { delete w; }
 inline int gsl_integration_qag(const gsl_function *, double, double, double, double, size_t, int, gsl_integration_workspace *, double *, double *)
 { std::fprintf(stderr, "oracle stub: gsl_integration_qag called (off-path)\n"); std::abort(); return -1; }
+inline int gsl_integration_qags(const gsl_function *, double, double, double, double, size_t, gsl_integration_workspace *, double *, double *)
+{ std::fprintf(stderr, "oracle stub: gsl_integration_qags called (off-path)\n"); std::abort(); return -1; }
 #endif

@@ -39,18 +39,22 @@ def perturbed(src, rng, rel=REL):
 
 
 def reference_self_difference(oracle, method, srcs, dets, f, psd, dim, order, detector_index=-1, reference_index=0, nthreads=0,
-                              runs=PERTURBED_RUNS, seed=1, with_fma=True):
-    """Per source: max_ij normalised difference between the reference and `runs` re-evaluations of itself (see module doc)."""
+                              runs=PERTURBED_RUNS, seed=1, with_fma=True, with_median=False):
+    """Per source: max_ij normalised difference between the reference and `runs` re-evaluations of itself (see module doc);
+    with_median: also the largest median_ij among those re-evaluations."""
     import os
     srcs = list(srcs)
     kw = dict(order=order, detector_index=detector_index, reference_index=reference_index, nthreads=nthreads)
     base = oracle.fisher_numerical_batch(method, srcs, dets, f, psd, dim, **kw)
     rng = np.random.default_rng(seed)
     worst = np.zeros(len(srcs))
+    worst_median = np.zeros(len(srcs))
     others = [oracle.fisher_numerical_batch(method, [perturbed(s, rng) for s in srcs], dets, f, psd, dim, **kw) for _ in range(runs)]
     if with_fma and os.path.exists(oracle.LIB_PATH_FMA):
         others.append(oracle.fisher_numerical_batch(method, srcs, dets, f, psd, dim, fma_build=True, **kw))
     for o in others:
         e = normalised_error(o, base).reshape(len(srcs), -1)
-        worst = np.fmax(worst, np.where(np.isfinite(e), e, 0.0).max(axis=1))
-    return worst
+        e = np.where(np.isfinite(e), e, 0.0)
+        worst = np.fmax(worst, e.max(axis=1))
+        worst_median = np.fmax(worst_median, np.median(e, axis=1))
+    return (worst, worst_median) if with_median else worst

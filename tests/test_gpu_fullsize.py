@@ -114,8 +114,8 @@ def test_fisher_bench_population(ctx, oracle):
     Measure: e_ij = |dF_ij| / sqrt(F_ii F_jj).  The eps = 1e-8 stencil amplifies rounding by 1e8, so the reference differs from
     ITSELF when its arithmetic is perturbed; the yardstick is measured here, per source, by running the reference again on
     inputs moved by parts in 1e14 (far below the stencil step, far above nothing: a different rounding sequence, the same
-    mathematics).  The GPU must agree with the reference to within kFactor x that self-difference (plus the 1e-6 of
-    BASELINE.json where the reference is quieter than that)."""
+    mathematics).  The GPU must agree with the reference to within FACTOR x that self-difference, for the largest entry and
+    for the median entry of every matrix (or to BASELINE.json's 1e-6 where the reference is quieter than that)."""
     import fisher_noise
     S = 64
     srcs = workloads.fisher_sources(S)
@@ -126,14 +126,15 @@ def test_fisher_bench_population(ctx, oracle):
     got = ctx.fisher_numerical_batch("IMRPhenomD", srcs, 11, order=4)
     ref = oracle.fisher_numerical_batch("IMRPhenomD", srcs, dets, f, psd, 11, order=4, detector_index=-1, reference_index=0,
                                         nthreads=_threads())
-    floor = fisher_noise.reference_self_difference(oracle, "IMRPhenomD", srcs, dets, f, psd, 11, 4, nthreads=_threads())
+    floor, floor_med = fisher_noise.reference_self_difference(oracle, "IMRPhenomD", srcs, dets, f, psd, 11, 4, nthreads=_threads(),
+                                                              with_median=True)
     finite = np.all(np.isfinite(ref.reshape(S, -1)), axis=1)
     assert finite.sum() >= S - 2
     assert np.array_equal(np.all(np.isfinite(got.reshape(S, -1)), axis=1), finite)  # NaN where, and only where, the reference has NaN
     worst = 0.0
     for i in np.flatnonzero(finite):
         e = fisher_noise.normalised_error(got[i], ref[i])
-        assert np.median(e) <= 1e-6, (i, np.median(e))
+        assert np.median(e) <= max(1e-6, fisher_noise.FACTOR * floor_med[i]), (i, np.median(e), floor_med[i])
         bound = max(1e-6, fisher_noise.FACTOR * floor[i])
         worst = max(worst, e.max() / bound)
         assert e.max() <= bound, (i, e.max(), floor[i])
