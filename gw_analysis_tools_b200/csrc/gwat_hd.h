@@ -65,6 +65,13 @@ GWAT_HD double fma_rn(double a, double b, double c)
 // of that footprint is CUDA's libm inlined at every call site (pow ~300 instructions, log/exp/sincos/cbrt/acos/atan2
 // 80-150 each, ~150 call sites).  Setup code calls them through these out-of-line copies instead: one body per function,
 // resident in the instruction cache after its first use.  The per-bin code keeps its inlined fast_* versions.
+// For the same reason loops of the setup code whose bodies are large are kept rolled (GWAT_SETUP_LOOP before the `for`): the
+// body is fetched once and then runs out of the instruction cache.  -DGWAT_SETUP_UNROLLED restores full unrolling (A/B runs).
+#if defined(__CUDACC__) && !defined(GWAT_SETUP_UNROLLED)
+#define GWAT_SETUP_LOOP _Pragma("unroll 1")
+#else
+#define GWAT_SETUP_LOOP
+#endif
 namespace sm {
 GWAT_HD_NOINLINE double pow(double a, double b) { return ::pow(a, b); }
 GWAT_HD_NOINLINE double log(double a) { return ::log(a); }

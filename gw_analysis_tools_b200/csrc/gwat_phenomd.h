@@ -105,15 +105,19 @@ GWAT_HD double phenomd_fit_element(const double (*fit)[11], int i, double eta, d
 }
 GWAT_HD void phenomd_fit(const double (*fit)[11], double eta, double chi_pn, Lambda &l)
 {
-	for (int i = 0; i < 3; i++) l.rho[i] = phenomd_fit_element(fit, i, eta, chi_pn);
-	l.v2 = phenomd_fit_element(fit, 3, eta, chi_pn);
-	for (int i = 0; i < 3; i++) l.gamma[i] = phenomd_fit_element(fit, i + 4, eta, chi_pn);
+	// one rolled loop over the 19 table rows (setup code is fetch-bound: gwat_hd.h); v[] is then dealt out
+	double v[19];
+	GWAT_SETUP_LOOP
+	for (int i = 0; i < 19; i++) v[i] = phenomd_fit_element(fit, i, eta, chi_pn);
+	for (int i = 0; i < 3; i++) l.rho[i] = v[i];
+	l.v2 = v[3];
+	for (int i = 0; i < 3; i++) l.gamma[i] = v[i + 4];
 	l.sigma[0] = 0;
-	for (int i = 0; i < 4; i++) l.sigma[i + 1] = phenomd_fit_element(fit, i + 7, eta, chi_pn);
+	for (int i = 0; i < 4; i++) l.sigma[i + 1] = v[i + 7];
 	l.beta[0] = 0;
-	for (int i = 0; i < 3; i++) l.beta[i + 1] = phenomd_fit_element(fit, i + 11, eta, chi_pn);
+	for (int i = 0; i < 3; i++) l.beta[i + 1] = v[i + 11];
 	l.alpha[0] = 0;
-	for (int i = 0; i < 5; i++) l.alpha[i + 1] = phenomd_fit_element(fit, i + 14, eta, chi_pn);
+	for (int i = 0; i < 5; i++) l.alpha[i + 1] = v[i + 14];
 }
 
 // TaylorF2 3PN amplitude coefficients (reference: assign_pn_amplitude_coeff, src/IMRPhenomD.cpp:955-986).

@@ -205,6 +205,7 @@ GWAT_HD double natural_spline_deriv(const double *xa, const double *ya, int n, d
 	double c[16], g[16], diag[16], off[16], gam[16], alp[16], z[16];
 	const int N = n - 2;
 	for (int i = 0; i < n; i++) c[i] = 0;
+	GWAT_SETUP_LOOP
 	for (int i = 0; i < N; i++) {
 		const double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
 		const double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
@@ -215,15 +216,19 @@ GWAT_HD double natural_spline_deriv(const double *xa, const double *ya, int n, d
 	}
 	alp[0] = diag[0];
 	gam[0] = off[0] / alp[0];
+	GWAT_SETUP_LOOP
 	for (int i = 1; i < N - 1; i++) {
 		alp[i] = sub_rn(diag[i], mul_rn(off[i - 1], gam[i - 1]));
 		gam[i] = off[i] / alp[i];
 	}
 	alp[N - 1] = sub_rn(diag[N - 1], mul_rn(off[N - 2], gam[N - 2]));
 	z[0] = g[0];
+	GWAT_SETUP_LOOP
 	for (int i = 1; i < N; i++) z[i] = sub_rn(g[i], mul_rn(gam[i - 1], z[i - 1]));
+	GWAT_SETUP_LOOP
 	for (int i = 0; i < N; i++) z[i] = z[i] / alp[i];
 	c[N] = z[N - 1];
+	GWAT_SETUP_LOOP
 	for (int i = N - 2; i >= 0; i--) c[i + 1] = sub_rn(z[i], mul_rn(gam[i], c[i + 2]));
 	// interval by bisection, like gsl_interp_bsearch
 	int lo = 0, hi = n - 1;
@@ -279,14 +284,18 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 			t_corr = 0;  // the reference bails out with 0 as well (:567-572)
 		} else {
 			double xs[10], ys[10];
-#pragma unroll
+			// (a rolled loop: the setup kernels are bound by instruction fetch, see gwat_hd.h; ten inlined copies of the carrier
+			// evaluation were a quarter of the kernel's code)
+			GWAT_SETUP_LOOP
 			for (int j = 0; j < n; j++) {
 				const double f = start + j * step;
 				double a_unused, ph;
 				// the samples straddle fRD > f2p: merger-ringdown phase, where the sixth root only enters through (Mf)^(3/4);
 				// below f1p (never for physical parameters) the exact root is used
 				const double root = f < c.f1p ? sixth_root_direct(c.M, f) : sixth_root_approx(c.M, f);
-				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, sm::log(f), a_unused, ph);
+				// ln f feeds the inspiral and intermediate phases only: not evaluated for a merger-ringdown sample
+				const double lg = f > c.f2p ? 0.0 : sm::log(f);
+				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, lg, a_unused, ph);
 				xs[j] = f;
 				ys[j] = -ph;
 			}

@@ -15,10 +15,13 @@
 // The host never reads device results inside gwat_b200_sampler_run: the step types are pure functions of (seed, step,
 // chain), so the host replays them to know which chains refresh their Fisher matrix at which step.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is opened at run time (see nccl_api)
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,7 +68,7 @@ __global__ void k_init(DevState d, StepConst k, gwat_b200_prior prior, PriorPlan
 	for (int i = 0; i < P; i++) {
 		d.hist[((size_t)c * k.H) * P + i] = d.pos[(size_t)c * P + i];
 		d.widths[(size_t)c * (P + 3) + i] = .05;  // allocate_sampler_mem, src/mcmc_sampler_internals.cpp:1998-2004
-		d.fvals[(size_t)c * P + i] = 0;
+		d.fvals[(size_t)c * P + i] = 1;  // (what assign_initial_pos leaves when the first matrix is not finite, :3193-3207)
 		for (int j = 0; j < P; j++) d.fvecs[((size_t)c * P + i) * P + j] = (i == j) ? 1.0 : 0.0;
 		for (int j = 0; j < 4; j++) d.gauss_ct[((size_t)c * P + i) * 4 + j] = 0;
 	}
@@ -325,6 +328,44 @@ __global__ void k_swap_apply(const int *__restrict__ src, int C, int P, const do
 	}
 }
 
+// Sharded ladder: one record per chain, [position | logL | logP], what the swap may move
+__global__ void k_swap_pack(int C, int P, const double *__restrict__ pos, const double *__restrict__ ll, const double *__restrict__ lp,
+                            double *__restrict__ rec)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x, R = P + 2;
+	if (t >= C * R) return;
+	const int c = t / R, i = t % R;
+	rec[t] = i < P ? pos[(size_t)c * P + i] : (i == P ? ll[c] : lp[c]);
+}
+__global__ void k_swap_global_ll(int Ct, int P, const double *__restrict__ rec, double *__restrict__ g_ll)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < Ct) g_ll[c] = rec[(size_t)c * (P + 2) + P];
+}
+// the sweep over the WHOLE ladder (every rank computes the same src[]); swap counters only for this rank's chains [c0, c0 + C)
+__global__ void k_swap_scan_global(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int Ct,
+                                   int c0, int C, int *__restrict__ src, int *__restrict__ accepted, long long *__restrict__ counters)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	swap_scan(ll, thr, kind, Ct, src, accepted);
+	for (int i = 0; i < Ct - 1; i++) {
+		const int which = accepted[i] ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
+		if (i >= c0 && i < c0 + C) counters[(size_t)(i - c0) * NCT + which] += 1;
+		if (i + 1 >= c0 && i + 1 < c0 + C) counters[(size_t)(i + 1 - c0) * NCT + which] += 1;
+	}
+}
+__global__ void k_swap_take(const int *__restrict__ src, int c0, int C, int P, const double *__restrict__ rec, double *__restrict__ pos,
+                            double *__restrict__ ll, double *__restrict__ lp)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x, R = P + 2;
+	if (t >= C * R) return;
+	const int c = t / R, i = t % R;
+	const double v = rec[(size_t)src[c0 + c] * R + i];
+	if (i < P) pos[(size_t)c * P + i] = v;
+	else if (i == P) ll[c] = v;
+	else lp[c] = v;
+}
+
 __global__ void k_prior(const double *__restrict__ params, int W, gwat_b200_prior prior, PriorPlan pp, double *__restrict__ out)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,6 +405,44 @@ int make_prior_plan(const char *method, const gwat_b200_mod *mod, int dimension,
 	return 0;
 }
 
+}  // namespace
+
+// ---- NCCL, loaded on demand --------------------------------------------------------------------------------------------------
+// Only the sharded sampler needs it, so the library does not link it: libnccl.so.2 is opened the first time a sampler is
+// attached to a group of ranks (a process that already loaded NCCL -- e.g. through torch.distributed -- gets that copy).
+namespace {
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	std::string error;
+};
+NcclApi &nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char *names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char *n : names) {
+			api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+			if (api.handle) break;
+		}
+		if (!api.handle) {
+			api.error = std::string("NCCL not found: ") + (dlerror() ? dlerror() : "libnccl.so.2 could not be opened");
+			return;
+		}
+		api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+		api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+		api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+		api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+		if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) api.error = "NCCL: missing symbols";
+	});
+	return api;
+}
 }  // namespace
 
 struct gwat_b200_sampler {
@@ -421,6 +500,19 @@ struct gwat_b200_sampler {
 	long long cold_cap = 0;
 	double last_ms = 0;
 	long long last_launches = 0;
+	// Sharded ladder (gwat_b200_sampler_attach_ranks): this sampler owns chains [rank * C, (rank + 1) * C) of a ladder of
+	// n_ranks * C chains; the swap sweep all-gathers every rank's (position, logL, logP) records over NCCL and every rank runs
+	// the same sweep over the whole ladder
+	ncclComm_t comm = nullptr;
+	int rank = 0, n_ranks = 1;
+	double *x_send = nullptr, *x_recv = nullptr;  // [C][P + 2] and [n_ranks * C][P + 2]
+	double *g_ll = nullptr, *g_temps = nullptr, *g_thr = nullptr;
+	int *g_kind = nullptr, *g_src = nullptr, *g_acc = nullptr;
+	static constexpr int NSW = 64;                  // swap sweeps of a run whose exchange is timed
+	cudaEvent_t ev_sw0[NSW] = {}, ev_sw1[NSW] = {};
+	int n_sw_timed = 0;
+	double last_swap_ms = 0;
+	long long last_sweeps = 0;
 };
 
 namespace {
@@ -568,7 +660,25 @@ int swap_sweep(gwat_b200_sampler *s)
 	}
 	double gate, unused;
 	uniform2(s->k.seed, (uint64_t)s->sweep, 0u, DRAW_SWAP_GATE, gate, unused);
-	if (gate < s->opt.swap_rate && C > 1) {  // src/mcmc_sampler.cpp:4646-4654
+	if (s->comm && gate < s->opt.swap_rate) {
+		// The one exchange of the path: all-gather of 8 (P + 2) bytes per chain over NVLink, on the sampler's stream;
+		// then the reference's sequential sweep (src/mcmc_sampler_internals.cpp:1086-1184) over the gathered ladder, computed by
+		// every rank from the same logL and the same counter-based draws, and each rank takes the records that land in its slots.
+		const int Ct = C * s->n_ranks, R = P + 2, c0 = s->rank * C;
+		const bool timed = s->n_sw_timed < gwat_b200_sampler::NSW;
+		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw0[s->n_sw_timed], st));
+		k_swap_pack<<<(C * R + 255) / 256, 256, 0, st>>>(C, P, s->d.pos, s->d.ll, s->d.lp, s->x_send);
+		const ncclResult_t nr = nccl_api().AllGather(s->x_send, s->x_recv, (size_t)C * R, ncclDouble, s->comm, st);
+		if (nr != ncclSuccess)
+			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr));
+		k_swap_global_ll<<<(Ct + 255) / 256, 256, 0, st>>>(Ct, P, s->x_recv, s->g_ll);
+		k_swap_prepare<<<(Ct + 255) / 256, 256, 0, st>>>(s->g_ll, s->g_temps, s->k.seed, s->sweep, Ct, 0, s->g_thr, s->g_kind);
+		k_swap_scan_global<<<1, 32, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, c0, C, s->g_src, s->g_acc, s->d.counters);
+		k_swap_take<<<(C * R + 255) / 256, 256, 0, st>>>(s->g_src, c0, C, P, s->x_recv, s->d.pos, s->d.ll, s->d.lp);
+		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw1[s->n_sw_timed++], st));
+		s->last_launches += 6;
+		s->last_sweeps += 1;
+	} else if (!s->comm && gate < s->opt.swap_rate && C > 1) {  // src/mcmc_sampler.cpp:4646-4654
 		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->k.chain_offset, s->swap_thr, s->swap_kind);
 		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc, s->d.counters);
 		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
@@ -724,6 +834,14 @@ void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 		if (e) cudaEventDestroy(e);
 	for (void *p : {(void *)s->g_idx, (void *)s->g_ok, (void *)s->g_par, (void *)s->g_mat, (void *)s->g_vals, (void *)s->g_vecs}) cudaFree(p);
 	if (s->gh_idx) cudaFreeHost(s->gh_idx);
+	for (void *p : {(void *)s->x_send, (void *)s->x_recv, (void *)s->g_ll, (void *)s->g_temps, (void *)s->g_thr, (void *)s->g_kind, (void *)s->g_src,
+	                (void *)s->g_acc})
+		cudaFree(p);
+	for (int i = 0; i < gwat_b200_sampler::NSW; i++) {
+		if (s->ev_sw0[i]) cudaEventDestroy(s->ev_sw0[i]);
+		if (s->ev_sw1[i]) cudaEventDestroy(s->ev_sw1[i]);
+	}
+	if (s->comm) nccl_api().CommDestroy(s->comm);
 	delete s;
 }
 
@@ -801,7 +919,8 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	s->lookahead = 0;
 	s->deferred = o.fisher_exist && o.fisher_deferred != 0;
-	if (s->deferred) {
+	if (o.fisher_exist) {
+		// the group staging set: every chain's first matrix (below), and the deferred passes
 		const size_t n = (size_t)C;
 		SC_TRY(dalloc(s->g_idx, n));
 		SC_TRY(dalloc(s->g_ok, n));
@@ -874,9 +993,9 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 		if (!(lp[c] > -INFINITY) || !(ll[c] == ll[c]))
 			return bail(gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_create: initial position of chain " + std::to_string(c) +
 			                                                                 " has zero prior or an undefined likelihood"));
-	if (s->deferred) {
-		// every chain starts with the eigen-system of its initial position (the reference computes it at the chain's first
-		// Fisher step, :434-437); the refresh counters then run from zero
+	if (o.fisher_exist) {
+		// every chain starts with the eigen-system of its initial position and a refresh counter of zero, as assign_initial_pos
+		// leaves them (src/mcmc_sampler_internals.cpp:3182-3212)
 		std::vector<int> all(C);
 		for (int c = 0; c < C; c++) all[c] = c;
 		if (int rc = group_launch(s, all, st)) return bail(rc);
@@ -900,6 +1019,9 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 	const int P = s->k.P;
 	const long long launches0 = ctx->launches;
 	s->last_launches = 0;
+	s->n_sw_timed = 0;
+	s->last_sweeps = 0;
+	s->last_swap_ms = 0;
 	SCUDA(ctx, cudaEventRecord(s->ev_t0, s->st[0]));
 	if (s->nlanes > 1) {
 		SCUDA(ctx, cudaEventRecord(s->ev_join, s->st[0]));
@@ -956,6 +1078,12 @@ int gwat_b200_sampler_run(gwat_b200_sampler *s, int n_steps)
 	SCUDA(ctx, cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
 	s->last_ms = ms;
 	s->last_launches += ctx->launches - launches0;
+	for (int i = 0; i < s->n_sw_timed; i++) {
+		float t = 0;
+		SCUDA(ctx, cudaEventElapsedTime(&t, s->ev_sw0[i], s->ev_sw1[i]));
+		s->last_swap_ms += t;
+	}
+	if (s->n_sw_timed > 0) s->last_swap_ms /= s->n_sw_timed;
 	return GWAT_B200_OK;
 }
 
@@ -1046,6 +1174,73 @@ int gwat_b200_sampler_cold(gwat_b200_sampler *s, long long first_step, int n, do
 		SCUDA(ctx, cudaMemcpy(out, s->d.cold + (size_t)first_step * row, sizeof(double) * n * row, cudaMemcpyDeviceToHost));
 	return GWAT_B200_OK;
 }
+
+int gwat_b200_nccl_unique_id(unsigned char *id128)
+{
+	if (!id128) return GWAT_B200_ERR_ARG;
+	NcclApi &api = nccl_api();
+	if (!api.error.empty()) return gwat_internal::set_error(nullptr, GWAT_B200_ERR_UNSUPPORTED, api.error);
+	static_assert(sizeof(ncclUniqueId) == GWAT_B200_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+	ncclUniqueId id;
+	const ncclResult_t r = api.GetUniqueId(&id);
+	if (r != ncclSuccess) return gwat_internal::set_error(nullptr, GWAT_B200_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+	std::memcpy(id128, &id, sizeof(id));
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_attach_ranks(gwat_b200_sampler *s, const unsigned char *id128, int rank, int n_ranks)
+{
+	if (!s || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	if (s->comm) return gwat_internal::set_error(ctx, GWAT_B200_ERR_STATE, "sampler_attach_ranks: already attached");
+	if (s->step != 0) return gwat_internal::set_error(ctx, GWAT_B200_ERR_STATE, "sampler_attach_ranks: attach before the first step");
+	if (s->k.chain_offset != rank * s->k.C)
+		return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_attach_ranks: options.chain_index_offset must be rank * chain_N (equal shards)");
+	NcclApi &api = nccl_api();
+	if (!api.error.empty()) return gwat_internal::set_error(ctx, GWAT_B200_ERR_UNSUPPORTED, api.error);
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	ncclUniqueId id;
+	std::memcpy(&id, id128, sizeof(id));
+	ncclComm_t comm = nullptr;
+	ncclResult_t r = api.CommInitRank(&comm, n_ranks, id, rank);
+	if (r != ncclSuccess) return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+	const int C = s->k.C, P = s->k.P, Ct = C * n_ranks, R = P + 2;
+	cudaStream_t st = s->st[0];
+	auto fail_here = [&](const std::string &m) {
+		api.CommDestroy(comm);
+		return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, m);
+	};
+#define AT_TRY(expr)                                                                                  \
+	do {                                                                                                \
+		cudaError_t e_ = (expr);                                                                          \
+		if (e_ != cudaSuccess) return fail_here(std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+	} while (0)
+	AT_TRY(dalloc(s->x_send, (size_t)C * R));
+	AT_TRY(dalloc(s->x_recv, (size_t)Ct * R));
+	AT_TRY(dalloc(s->g_ll, (size_t)Ct));
+	AT_TRY(dalloc(s->g_temps, (size_t)Ct));
+	AT_TRY(dalloc(s->g_thr, (size_t)Ct));
+	AT_TRY(dalloc(s->g_kind, (size_t)Ct));
+	AT_TRY(dalloc(s->g_src, (size_t)Ct));
+	AT_TRY(dalloc(s->g_acc, (size_t)Ct));
+	for (int i = 0; i < gwat_b200_sampler::NSW; i++) {
+		AT_TRY(cudaEventCreate(&s->ev_sw0[i]));
+		AT_TRY(cudaEventCreate(&s->ev_sw1[i]));
+	}
+	// the whole ladder's temperatures, once
+	r = api.AllGather(s->d.temps, s->g_temps, (size_t)C, ncclDouble, comm, st);
+	if (r != ncclSuccess) return fail_here(std::string("ncclAllGather(temperatures): ") + api.GetErrorString(r));
+	AT_TRY(cudaStreamSynchronize(st));
+#undef AT_TRY
+	s->comm = comm;
+	s->rank = rank;
+	s->n_ranks = n_ranks;
+	return GWAT_B200_OK;
+}
+
+double gwat_b200_sampler_last_swap_ms(const gwat_b200_sampler *s) { return s ? s->last_swap_ms : 0; }
+long long gwat_b200_sampler_last_sweeps(const gwat_b200_sampler *s) { return s ? s->last_sweeps : 0; }
 
 double gwat_b200_sampler_last_ms(const gwat_b200_sampler *s) { return s ? s->last_ms : 0; }
 long long gwat_b200_sampler_last_launches(const gwat_b200_sampler *s) { return s ? s->last_launches : 0; }

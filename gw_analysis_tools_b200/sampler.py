@@ -19,7 +19,20 @@ EXPORTS = [
     "gwat_b200_sampler_run", "gwat_b200_sampler_state", "gwat_b200_sampler_counters", "gwat_b200_sampler_cold",
     "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_sampler_uniform",
     "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
+    "gwat_b200_nccl_unique_id", "gwat_b200_sampler_attach_ranks", "gwat_b200_sampler_last_swap_ms", "gwat_b200_sampler_last_sweeps",
 ]
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id():
+    """128 opaque bytes identifying a new group of ranks (rank 0 calls this and hands them to the others)."""
+    from .engine import load_library
+    buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES)()
+    lib = load_library()
+    rc = lib.gwat_b200_nccl_unique_id(buf)
+    if rc != 0:
+        raise GwatB200Error(rc, lib.gwat_b200_last_error(None).decode())
+    return bytes(buf)
 
 
 class Prior(C.Structure):
@@ -156,6 +169,24 @@ class Sampler:
         out = np.empty((n, nc.value, self.P))
         self._ctx._check(self._lib.gwat_b200_sampler_cold(self._h, C.c_longlong(first_step), int(n), _p(out), C.byref(nc)))
         return out
+
+    def attach_ranks(self, unique_id, rank, n_ranks):
+        """Join a ladder sharded over ``n_ranks`` processes (one per GPU): this sampler must have been created with its own
+        equal share of the chains and ``chain_index_offset = rank * chain_N``.  The swap sweeps then exchange over NCCL."""
+        buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._ctx._check(self._lib.gwat_b200_sampler_attach_ranks(self._h, buf, int(rank), int(n_ranks)))
+
+    @property
+    def last_swap_ms(self):
+        self._lib.gwat_b200_sampler_last_swap_ms.restype = C.c_double
+        self._lib.gwat_b200_sampler_last_swap_ms.argtypes = [C.c_void_p]
+        return self._lib.gwat_b200_sampler_last_swap_ms(self._h)
+
+    @property
+    def last_sweeps(self):
+        self._lib.gwat_b200_sampler_last_sweeps.restype = C.c_longlong
+        self._lib.gwat_b200_sampler_last_sweeps.argtypes = [C.c_void_p]
+        return self._lib.gwat_b200_sampler_last_sweeps(self._h)
 
     @property
     def last_ms(self):

@@ -102,6 +102,28 @@ int gwat_b200_sampler_set_state(gwat_b200_sampler *s, const double *positions, c
 int gwat_b200_swap_sweep_host(int chain_N_total, const double *logL, const double *temps, unsigned long long seed, long long sweep,
                               int *src, int *accepted /* [chain_N_total - 1] or NULL */);
 void gwat_b200_sampler_uniform(unsigned long long seed, unsigned long long step, unsigned chain, unsigned purpose, double *out2);
+/*
+ * One ladder sharded over the GPUs of a box, one process (rank) per GPU -- the split BASELINE.json's north_star names: "only the
+ * PT swap step exchanges per-walker log-likelihoods and positions via NCCL allgather over NVLink".
+ *   rank 0:     gwat_b200_nccl_unique_id(id), then hands the 128 bytes to the other ranks (MPI_Bcast, torch.distributed, a file ...)
+ *   every rank: gwat_b200_sampler_create(...) with its own chain_N chains (equal on all ranks), their temperatures and
+ *               options.chain_index_offset = rank * chain_N, then gwat_b200_sampler_attach_ranks(s, id, rank, n_ranks)
+ *   every rank: gwat_b200_sampler_run(s, n) with the same n.
+ * At every swap sweep the ranks ncclAllGather one record [position | logL | logP] per chain (8 (dimension + 2) bytes) on the
+ * sampler's stream, every rank runs the reference's sequential sweep (chain_swap / single_chain_swap,
+ * src/mcmc_sampler_internals.cpp:1086-1184) over the WHOLE ladder from the same gathered logL and the same counter-based draws,
+ * and keeps the records that land in its own slots.  Nothing goes through the host.  Because every draw is a function of the
+ * global chain index, n_ranks samplers reproduce bit for bit what one sampler with all the chains does.
+ * NCCL is loaded with dlopen("libnccl.so.2") at the first of these calls; without it they return GWAT_B200_ERR_UNSUPPORTED.
+ */
+#define GWAT_B200_NCCL_UNIQUE_ID_BYTES 128
+int gwat_b200_nccl_unique_id(unsigned char *id128);
+int gwat_b200_sampler_attach_ranks(gwat_b200_sampler *s, const unsigned char *id128, int rank, int n_ranks);
+/* mean device time of the swap exchange (pack, all-gather, sweep, take) over the first 64 sweeps of the last run, in ms, and the
+ * number of sweeps that run performed */
+double gwat_b200_sampler_last_swap_ms(const gwat_b200_sampler *s);
+long long gwat_b200_sampler_last_sweeps(const gwat_b200_sampler *s);
+
 /* counters[chain_N][GWAT_B200_SAMPLER_NCOUNTERS] (see the enum), widths[chain_N][dimension + 3]: Gaussian widths per dimension,
  * then the DE, (unused) and Fisher widths */
 enum {

@@ -247,13 +247,21 @@ class Sampler:
         self.hist_pos = [0] * C
         for c in range(C):
             self.hist[c][0] = list(self.pos[c])
-        self.fvals = [[0.] * P for _ in range(C)]
+        self.fvals = [[1.] * P for _ in range(C)]
         self.fvecs = [np.eye(P) for _ in range(C)]
         self.fisher_ct = [fisher_update_number] * C  # :2011
         self.gauss_ct = [[[0, 0, 0, 0] for _ in range(P)] for _ in range(C)]
         self.type_last = [[0, 0, 0, 0] for _ in range(C)]
         self.ct = [dict(step=[0, 0], gauss=[0, 0], de=[0, 0], fisher=[0, 0], swap=[0, 0], fisher_updates=0) for _ in range(C)]
         self.pending = None
+        if self.fisher_exist:
+            # assign_initial_pos (:3182-3212): every chain's matrix at its initial position; update_fisher resets the counter
+            for c in range(C):
+                vals, vecs = self.fisher_fn(c, np.array(self.pos[c]))
+                if not (np.isnan(vals).any() or np.isnan(vecs).any()):
+                    self.fvals[c], self.fvecs[c] = list(vals), np.array(vecs)
+                    self.ct[c]["fisher_updates"] += 1
+                self.fisher_ct[c] = 0
 
     # -- proposals (one chain) --
     def _propose(self, c, s):

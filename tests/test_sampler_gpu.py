@@ -139,6 +139,94 @@ def test_trajectories_match_restated_reference(ctx, oracle, cfg, fisher, lanes):
     assert ct["swap_accept"].sum() > 0
 
 
+@pytest.mark.parametrize("cfg,fisher,lanes", [(1, False, 1), (1, True, 2), (2, True, 2), (4, True, 1), (5, True, 2)])
+def test_trajectories_match_reference_steps(ctx, oracle, cfg, fisher, lanes):
+    """Step for step against the reference's OWN compiled sampler (oracle/_ref: src/mcmc_sampler_internals.cpp,
+    src/mcmc_sampler.cpp, src/standardPriorLibrary.cpp, unmodified), run by its own loop PTMCMC_MH_step_incremental on its own
+    likelihood and priors, and fed -- through the scripted gsl_rng stand-in -- the counter-based draws the device uses, in the
+    order the reference's code asks for them (oracle/ref_sampler.py).  Positions after every step (and after every swap sweep),
+    likelihoods, priors, acceptance/swap counters and tuned widths must agree.
+
+    Fisher jumps: the eigenvectors of a numerically differentiated, nearly degenerate matrix are not reproducible between two
+    evaluations, so the reference's Eigen stand-in is told to return, for every refresh, the eigen-system the device holds after
+    that step (its refresh schedule, its use of the system and everything else are the reference's own); the matrices themselves
+    are pinned to the compiled reference in test_mcmc_fisher_vs_oracle."""
+    from oracle import ref_sampler as rs
+    if not hasattr(oracle.lib(), "oracle_sampler_create"):
+        pytest.skip("oracle/_ref was built without the sampler translation units")
+    wl = _inject(ctx, workloads.make(cfg, W=64, L=1024 if cfg != 5 else 8192))
+    C = 12
+    temps = _ladder(3, 4, 20.0)
+    init = _start(wl, C)
+    prior = smp.prior_for(wl)
+    kw = dict(swp_freq=3, history_length=12, history_update=2, fisher_update_number=4, check_stepsize_freq=5)
+    seed = 177 + cfg
+    n_rounds = 14
+    n_steps = n_rounds * kw["swp_freq"]
+    g = smp.Sampler(ctx, wl.method, temps, init, prior, wl.gmst, wl.T_segment, wl.mod, seed=seed, fisher_exist=int(fisher), lanes=lanes, **kw)
+    fisher_hist = {-1: g.fisher_state()}
+    pos0, ll0, lp0 = g.state()
+    traj, lls, lps = [], [], []
+    for step in range(n_steps):
+        g.run(1)
+        p, l, q = g.state()
+        traj.append(p)
+        lls.append(l)
+        lps.append(q)
+        if fisher:
+            fisher_hist[step] = g.fisher_state()
+    R = rs.RefSampler(wl, temps, init, prior, seed, n_rounds, smp.draw_uniform2, ref.normal_from, fisher_exist=fisher,
+                      initial_fisher=(lambda c: (fisher_hist[-1][0][c], fisher_hist[-1][1][c])) if fisher else None, **kw)
+    kinds, refreshes = R.script(lambda s, c: (fisher_hist[s][0][c], fisher_hist[s][1][c]))
+    R.run()
+    res = R.results()
+    R.close()
+    d = res["diag"]
+    assert d["rng_underflow"] == 0 and d["uniforms_left"] == 0 and d["normals_left"] == 0 and d["fisher_script_underflow"] == 0, d
+    out = res["output"]
+    assert np.allclose(res["ll"][:, 0], ll0, rtol=1e-9) and np.allclose(res["lp"][:, 0], lp0, rtol=1e-13)
+    for s in range(n_steps):
+        assert np.allclose(out[:, s + 1], traj[s], rtol=1e-9, atol=1e-12), "diverged at step %d" % s
+        if (s + 1) % kw["swp_freq"] != 0:  # (the reference logs ll/lp before the swap of a round's last step)
+            assert np.allclose(res["ll"][:, s + 1], lls[s], rtol=1e-9)
+            assert np.allclose(res["lp"][:, s + 1], lps[s], rtol=1e-9, atol=1e-9)
+    ct, widths = g.counters()
+    rc = res["counters"]
+    for name in ("step_accept", "step_reject", "swap_accept", "swap_reject", "gauss_accept", "gauss_reject", "de_accept", "de_reject",
+                 "fisher_accept", "fisher_reject"):
+        assert np.array_equal(ct[name], rc[name]), name
+    P = wl.P
+    assert np.allclose(widths[:, :P + 1], res["widths"][:, :P + 1], rtol=1e-14) and np.allclose(widths[:, P + 2], res["widths"][:, P + 2], rtol=1e-14)
+    assert (ct["step_accept"] + ct["step_reject"] == n_steps).all() and ct["swap_accept"].sum() > 0
+    if fisher:
+        assert ct["de_accept"].sum() + ct["de_reject"].sum() > 0 and ct["fisher_accept"].sum() + ct["fisher_reject"].sum() > 0
+        # the device refreshed exactly when the reference did: once per chain at creation, then at the scheduled steps
+        assert (ct["fisher_updates"] + ct["fisher_nan"]).sum() == C + len(refreshes)
+    g.close()
+
+
+def test_log_prior_batch_vs_reference(ctx, oracle):
+    """The device priors against the reference's compiled classes (src/standardPriorLibrary.cpp) for the four BASELINE families."""
+    from oracle import ref_sampler as rs
+    if not hasattr(oracle.lib(), "oracle_ref_log_prior_batch"):
+        pytest.skip("oracle/_ref was built without the sampler translation units")
+    for cfg in (1, 2, 4, 5):
+        wl = workloads.make(cfg, W=512, L=1024 if cfg != 5 else 4096)
+        ctx.set_network(wl.detectors, wl.f, wl.psd)
+        prior = smp.prior_for(wl)
+        rng = np.random.default_rng(100 + cfg)
+        params = wl.params.copy()
+        k = rng.integers(0, wl.P, 170)
+        params[np.arange(170), k] += rng.choice([-1, 1], 170) * 10.0
+        got = smp.log_prior_batch(ctx, wl.method, params, prior, wl.mod)
+        base = (15 if "Pv2" in wl.method else 11) + (1 if "NRT" in wl.method else 0)
+        want = rs.log_prior_batch(wl.method, params, prior, wl.P - base)
+        assert np.array_equal(np.isneginf(got), np.isneginf(want))
+        fin = ~np.isneginf(want)
+        assert 100 < fin.sum() < 512
+        assert np.allclose(got[fin], want[fin], rtol=1e-13, atol=1e-13)
+
+
 def test_lane_split_is_bitwise_invisible(ctx):
     wl = _inject(ctx, workloads.make(2, W=64, L=2048))
     temps = _ladder(4, 8)

@@ -1,5 +1,6 @@
-"""Two GPUs: the sharded sampler (ensemble.DistributedSampler, NCCL all-gathers at the swap sweeps only) reproduces the
-single-GPU device sampler bit for bit.  Skipped on boxes with fewer than two GPUs."""
+"""Two GPUs: the sharded sampler reproduces the single-GPU device sampler bit for bit -- both the exchange inside the library
+(gwat_b200_sampler_attach_ranks: ncclAllGather + device sweep, no host round trip) and the Python-level one
+(ensemble.DistributedSampler over torch.distributed).  Skipped on boxes with fewer than two GPUs."""
 import os
 import subprocess
 import sys
@@ -16,7 +17,8 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def test_two_ranks_reproduce_one(tmp_path):
+@pytest.mark.parametrize("mode", ["cabi", "python"])
+def test_two_ranks_reproduce_one(tmp_path, mode):
     if _gpus() < 2:
         pytest.skip("needs two GPUs")
     from gw_analysis_tools_b200 import engine, workloads
@@ -25,7 +27,7 @@ def test_two_ranks_reproduce_one(tmp_path):
     out = str(tmp_path / "two.npz")
     worker = os.path.join(ROOT, "tests", "mgpu_sampler_worker.py")
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                    "--master-port", "29533", worker, out, str(steps)], check=True, timeout=600)
+                    "--master-port", "29533" if mode == "python" else "29534", worker, out, str(steps), mode], check=True, timeout=600)
     two = np.load(out)
     # the same run on one GPU, swaps done by the device sweep
     ctx = engine.Context(0)
@@ -45,5 +47,7 @@ def test_two_ranks_reproduce_one(tmp_path):
     assert np.array_equal(two["pos"], pos) and np.array_equal(two["ll"], ll) and np.array_equal(two["lp"], lp)
     assert np.array_equal(two["swap_accept"], ct["swap_accept"]) and np.array_equal(two["swap_reject"], ct["swap_reject"])
     assert ct["swap_accept"].sum() > 0
+    if mode == "cabi":
+        assert int(two["sweeps"]) > 0 and float(two["swap_ms"]) > 0
     s.close()  # before its context
     ctx.close()

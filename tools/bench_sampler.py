@@ -22,6 +22,97 @@ from gw_analysis_tools_b200 import sampler as smp  # noqa: E402
 N_TEMPS = {1: 8, 2: 8, 4: 16, 5: 8}
 
 
+def run_under_bench(args, ctx, world, rank, local, dist, ClockSampler):
+    """`bench.py --workload sampler [--gpus N] [--scaling strong|weak]`: device-resident PTMCMC steps on the config's ensemble.
+
+    strong (what north_star describes): the config's ONE ladder (cfg2: 8 temperatures x 512 ensembles = 4096 chains) is cut into
+    N contiguous blocks of chains, one per rank; every swap sweep all-gathers (position, logL, logP) over NCCL inside the library
+    (gwat_b200_sampler_attach_ranks) and every rank runs the reference's sweep over the whole ladder.  weak: every rank owns a
+    ladder of the config's size and joins the same exchange (N x 4096 chains).  One "step" = one MH step of every chain.
+    value = chain-steps/s from the device time of gwat_b200_sampler_run (CUDA events on the sampler's stream), max over ranks;
+    e2e = the same from wall clock around the call, including a device->host read of the cold chains' state every `steps`."""
+    import torch
+    cfg = args.config if args.config in N_TEMPS else 2
+    wl = workloads.make(cfg, W=args.walkers, L=args.bins)
+    ctx.set_network(wl.detectors, wl.f, wl.psd)
+    src = ctx.repack_mcmc_batch(wl.method, wl.inj[None, :], wl.gmst, wl.mod)
+    src[0].tc = wl.T_segment - src[0].tc
+    wl.data = ctx.coherent_response_batch(wl.method, src)[0]
+    ctx.set_network(wl.detectors, wl.f, wl.psd, wl.data)
+    nt = N_TEMPS[cfg]
+    strong = args.scaling == "strong"
+    C_total = wl.W if strong else wl.W * world
+    C_loc = C_total // world
+    ladder = np.tile(np.geomspace(1.0, 100.0, nt), C_total // nt)
+    rng = np.random.default_rng(11)
+    reps = -(-C_total // wl.W)
+    base = np.concatenate([wl.params] * reps)[:C_total]
+    init_all = wl.inj[None, :] + 0.2 * (base - wl.inj[None, :])
+    if reps > 1:
+        init_all[:, [0, 2, 4]] += 1e-3 * rng.standard_normal((C_total, 3))
+    lo = rank * C_loc
+    prior = smp.prior_for(wl)
+    fisher = 1
+    s = smp.Sampler(ctx, wl.method, ladder[lo:lo + C_loc], init_all[lo:lo + C_loc], prior, wl.gmst, wl.T_segment, wl.mod, seed=1, lanes=2,
+                    fisher_exist=fisher, fisher_update_number=200, history_length=1000, fisher_deferred=1, chain_index_offset=lo)
+    if world > 1:
+        ids = [smp.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        s.attach_ranks(ids[0], rank, world)
+    s.run(max(args.warmup, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    s.run(args.steps)
+    pos, ll, lp = s.state()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms, swap_ms, sweeps, launches = s.last_ms, s.last_swap_ms, s.last_sweeps, s.last_launches
+    if world > 1:
+        t = torch.tensor([dev_ms, wall, swap_ms], dtype=torch.float64, device="cuda")
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        per_rank = [[float(x) for x in a] for a in allv]
+        dev_ms, wall, swap_ms = (max(col) for col in zip(*per_rank))
+    else:
+        per_rank = [[dev_ms, wall, swap_ms]]
+    ct, _ = s.counters()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    P = wl.P
+    line = {"metric": "PTMCMC chain-steps/sec (proposal + prior + waveform/response/inner-product likelihood + MH accept; PT swap sweep every %d steps)" % s.options.swp_freq,
+            "value": C_total * args.steps / (dev_ms * 1e-3), "unit": "chain-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 10),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s sampler: %s, %d detectors, %d chains in all (%d ensembles x %d temperatures), %d per GPU, %d bins, Gaussian + differential-evolution + Fisher proposals" % (
+                           wl.name, wl.method, wl.D, C_total, C_total // nt, nt, C_loc, wl.L),
+                       "method": wl.method, "chains_total": C_total, "chains_per_gpu": C_loc, "bins": wl.L, "detectors": wl.D, "dimension": P,
+                       "parallelism": ("one ladder sharded over %d GPU(s)" % world if strong else "one ladder of %d x the config's chains over %d GPU(s)" % (world, world)) +
+                                      "; swap sweep = ncclAllGather of (position, logL, logP) per chain inside the library" if world > 1 else "single GPU, swap sweep on the device",
+                       "l2": "a fresh proposal set every step (the chains move); inputs stay resident: this is the sampler, not a copy benchmark"},
+            "e2e": {"value": C_total * args.steps / wall, "unit": "chain-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": C_loc * (P + 2) * 8 / args.steps, "ms_per_step": wall / args.steps * 1e3,
+                    "note": "wall clock around gwat_b200_sampler_run + one device->host read of the ensemble state per call"},
+            "swap_exchange": {"ms_per_sweep": swap_ms, "sweeps": int(sweeps), "bytes_per_rank_per_sweep": C_loc * (P + 2) * 8,
+                              "bytes_gathered_per_sweep": C_total * (P + 2) * 8,
+                              "share_of_step_time": swap_ms * sweeps / dev_ms if dev_ms > 0 else None,
+                              "what": "pack + ncclAllGather + threshold/sequential sweep over the whole ladder + take, CUDA events on the sampler's stream" if world > 1 else "device sweep, no exchange"},
+            "per_rank": {"device_ms": [r[0] for r in per_rank], "wall_s": [r[1] for r in per_rank], "swap_ms_per_sweep": [r[2] for r in per_rank]},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "accept_fraction": float(ct["step_accept"].sum() / max(1, ct["step_accept"].sum() + ct["step_reject"].sum())),
+            "swap_accept_fraction": float(ct["swap_accept"].sum() / max(1, ct["swap_accept"].sum() + ct["swap_reject"].sum())),
+            "finite": bool(np.isfinite(ll).all())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=2)
