@@ -527,7 +527,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    cores = pin_rank_cores(local, world)
+    # (measured on a 2-GPU box: splitting the 32 host threads into two halves made one rank's host-buffer path 8 % SLOWER than
+    # leaving the scheduler alone -- the halves are hyperthread siblings -- so pinning is opt-in)
+    cores = pin_rank_cores(local, world) if args.pin_cores else sorted(os.sched_getaffinity(0))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -719,6 +721,7 @@ def main():
     ap.add_argument("--fisher-sources", type=int, default=100000, help="config 3: sources per GPU and step")
     ap.add_argument("--fisher-cpu-sample", type=int, default=256)
     ap.add_argument("--sustain-seconds", type=float, default=1.0)
+    ap.add_argument("--pin-cores", action="store_true", help="give every rank a disjoint share of the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained figure and the other configs' lines")
     args = ap.parse_args()

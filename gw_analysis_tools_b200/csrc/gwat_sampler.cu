@@ -303,17 +303,26 @@ __global__ void k_swap_prepare(const double *__restrict__ ll, const double *__re
 	kind[i] = kd;
 	thr[i] = th;
 }
-// src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118)
+// src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118).  One thread: the
+// sweep is a chain of dependent decisions (4 instructions per pair); everything that is not -- thresholds before, counters and
+// the moves after -- runs in parallel kernels around it.
 __global__ void k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
-                            int *__restrict__ src, int *__restrict__ accepted, long long *__restrict__ counters)
+                            int *__restrict__ src, int *__restrict__ accepted)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	swap_scan(ll, thr, kind, C, src, accepted);
-	for (int i = 0; i < C - 1; i++) {
-		const int which = accepted[i] ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
-		counters[(size_t)i * NCT + which] += 1;
-		counters[(size_t)(i + 1) * NCT + which] += 1;
-	}
+}
+// swap counters of the chains [c0, c0 + C) of a ladder of Ct chains: chain g took part in the pairs (g-1, g) and (g, g+1)
+__global__ void k_swap_count(const int *__restrict__ accepted, int Ct, int c0, int C, long long *__restrict__ counters)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C) return;
+	const int g = c0 + c;
+	long long acc = 0, rej = 0;
+	if (g > 0) (accepted[g - 1] ? acc : rej) += 1;
+	if (g < Ct - 1) (accepted[g] ? acc : rej) += 1;
+	counters[(size_t)c * NCT + GWAT_B200_CT_SWAP_ACCEPT] += acc;
+	counters[(size_t)c * NCT + GWAT_B200_CT_SWAP_REJECT] += rej;
 }
 __global__ void k_swap_apply(const int *__restrict__ src, int C, int P, const double *__restrict__ pos, const double *__restrict__ ll,
                              const double *__restrict__ lp, double *__restrict__ pos2, double *__restrict__ ll2, double *__restrict__ lp2)
@@ -341,18 +350,6 @@ __global__ void k_swap_global_ll(int Ct, int P, const double *__restrict__ rec, 
 {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c < Ct) g_ll[c] = rec[(size_t)c * (P + 2) + P];
-}
-// the sweep over the WHOLE ladder (every rank computes the same src[]); swap counters only for this rank's chains [c0, c0 + C)
-__global__ void k_swap_scan_global(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int Ct,
-                                   int c0, int C, int *__restrict__ src, int *__restrict__ accepted, long long *__restrict__ counters)
-{
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
-	swap_scan(ll, thr, kind, Ct, src, accepted);
-	for (int i = 0; i < Ct - 1; i++) {
-		const int which = accepted[i] ? GWAT_B200_CT_SWAP_ACCEPT : GWAT_B200_CT_SWAP_REJECT;
-		if (i >= c0 && i < c0 + C) counters[(size_t)(i - c0) * NCT + which] += 1;
-		if (i + 1 >= c0 && i + 1 < c0 + C) counters[(size_t)(i + 1 - c0) * NCT + which] += 1;
-	}
 }
 __global__ void k_swap_take(const int *__restrict__ src, int c0, int C, int P, const double *__restrict__ rec, double *__restrict__ pos,
                             double *__restrict__ ll, double *__restrict__ lp)
@@ -673,19 +670,25 @@ int swap_sweep(gwat_b200_sampler *s)
 			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr));
 		k_swap_global_ll<<<(Ct + 255) / 256, 256, 0, st>>>(Ct, P, s->x_recv, s->g_ll);
 		k_swap_prepare<<<(Ct + 255) / 256, 256, 0, st>>>(s->g_ll, s->g_temps, s->k.seed, s->sweep, Ct, 0, s->g_thr, s->g_kind);
-		k_swap_scan_global<<<1, 32, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, c0, C, s->g_src, s->g_acc, s->d.counters);
+		k_swap_scan<<<1, 32, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, s->g_src, s->g_acc);  // the WHOLE ladder, the same on every rank
+		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->g_acc, Ct, c0, C, s->d.counters);
 		k_swap_take<<<(C * R + 255) / 256, 256, 0, st>>>(s->g_src, c0, C, P, s->x_recv, s->d.pos, s->d.ll, s->d.lp);
 		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw1[s->n_sw_timed++], st));
-		s->last_launches += 6;
+		s->last_launches += 7;
 		s->last_sweeps += 1;
 	} else if (!s->comm && gate < s->opt.swap_rate && C > 1) {  // src/mcmc_sampler.cpp:4646-4654
+		const bool timed = s->n_sw_timed < gwat_b200_sampler::NSW;
+		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw0[s->n_sw_timed], st));
 		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->k.chain_offset, s->swap_thr, s->swap_kind);
-		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc, s->d.counters);
+		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc);
+		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->swap_acc, C, 0, C, s->d.counters);
 		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
 		std::swap(s->d.pos, s->pos2);
 		std::swap(s->d.ll, s->ll2);
 		std::swap(s->d.lp, s->lp2);
-		s->last_launches += 3;
+		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw1[s->n_sw_timed++], st));
+		s->last_launches += 4;
+		s->last_sweeps += 1;
 	}
 	s->sweep += 1;
 	if (s->deferred)
@@ -979,6 +982,10 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 	SC_TRY(cudaEventCreate(&s->ev_t0));
 	SC_TRY(cudaEventCreate(&s->ev_t1));
+	for (int i = 0; i < gwat_b200_sampler::NSW; i++) {
+		SC_TRY(cudaEventCreate(&s->ev_sw0[i]));
+		SC_TRY(cudaEventCreate(&s->ev_sw1[i]));
+	}
 	cudaStream_t st = s->st[0];
 	SC_TRY(cudaMemcpyAsync(d.pos, initial_positions, sizeof(double) * C * P, cudaMemcpyHostToDevice, st));
 	SC_TRY(cudaMemcpyAsync(d.temps, chain_temps, sizeof(double) * C, cudaMemcpyHostToDevice, st));
@@ -1224,10 +1231,6 @@ int gwat_b200_sampler_attach_ranks(gwat_b200_sampler *s, const unsigned char *id
 	AT_TRY(dalloc(s->g_kind, (size_t)Ct));
 	AT_TRY(dalloc(s->g_src, (size_t)Ct));
 	AT_TRY(dalloc(s->g_acc, (size_t)Ct));
-	for (int i = 0; i < gwat_b200_sampler::NSW; i++) {
-		AT_TRY(cudaEventCreate(&s->ev_sw0[i]));
-		AT_TRY(cudaEventCreate(&s->ev_sw1[i]));
-	}
 	// the whole ladder's temperatures, once
 	r = api.AllGather(s->d.temps, s->g_temps, (size_t)C, ncclDouble, comm, st);
 	if (r != ncclSuccess) return fail_here(std::string("ncclAllGather(temperatures): ") + api.GetErrorString(r));

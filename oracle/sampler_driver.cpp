@@ -8,7 +8,7 @@
 //   src/standardPriorLibrary.cpp     logPriorStandard_{D,P,D_NRT,P_NRT}[_mod]::eval
 //   src/mcmc_gw.cpp, src/fisher.cpp  the likelihood of every proposal (through oracle_ref_loglike_mcmc_batch of ref_driver.cpp)
 //
-// Third-party pieces the reference's sampler needs and this image lacks are stand-ins under oracle/stubs:
+// Third-party pieces the reference's sampler needs and this image lacks are stand-ins under standins/:
 //   gsl_rng        scripted: every uniform / normal the reference draws is played back from per-chain queues that the harness
 //                  fills with the CUDA sampler's counter-based draws, in the order the reference consumes them
 //   Eigen          a Jacobi SelfAdjointEigenSolver; a test that follows the device's eigen-system step by step installs it through

@@ -1,6 +1,6 @@
 """tc/phic-maximised likelihoods: gwat_b200_loglike_maximized_batch against golden values produced by the
 reference's own maximized_Log_Likelihood_{aligned,unaligned}_spin_internal (oracle/_ref; the FFT there is the textbook
-transform of oracle/stubs/fftw3.h, cuFFT here), and against the oracle itself on fresh draws.  Tolerance: 1e-9 relative,
+transform of standins/fftw3.h, cuFFT here), and against the oracle itself on fresh draws.  Tolerance: 1e-9 relative,
 the log-likelihood tolerance of BASELINE.json.
 """
 import os

@@ -101,7 +101,7 @@ def run_under_bench(args, ctx, world, rank, local, dist, ClockSampler):
             "swap_exchange": {"ms_per_sweep": swap_ms, "sweeps": int(sweeps), "bytes_per_rank_per_sweep": C_loc * (P + 2) * 8,
                               "bytes_gathered_per_sweep": C_total * (P + 2) * 8,
                               "share_of_step_time": swap_ms * sweeps / dev_ms if dev_ms > 0 else None,
-                              "what": "pack + ncclAllGather + threshold/sequential sweep over the whole ladder + take, CUDA events on the sampler's stream" if world > 1 else "device sweep, no exchange"},
+                              "what": "pack + ncclAllGather + threshold/sequential sweep over the whole ladder + take, CUDA events on the sampler's stream" if world > 1 else "thresholds + sequential sweep + counters + moves on the device, no exchange"},
             "per_rank": {"device_ms": [r[0] for r in per_rank], "wall_s": [r[1] for r in per_rank], "swap_ms_per_sweep": [r[2] for r in per_rank]},
             "gpu_launches": int(launches), "clocks": clocks,
             "accept_fraction": float(ct["step_accept"].sum() / max(1, ct["step_accept"].sum() + ct["step_reject"].sum())),
