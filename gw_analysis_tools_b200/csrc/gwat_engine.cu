@@ -716,6 +716,24 @@ __global__ void __launch_bounds__(kThreads) k_fisher_assemble(const double *__re
 	}
 }
 
+// Log_Likelihood_internal for a response the caller supplies (src/mcmc_gw.cpp:801-868): sum_i w_i (|r_i|^2 - 2 Re(d_i conj r_i)) with
+// w_i = quadrature coefficient / S_i.  One CTA, fixed order: thread t adds bins t, t + 1024, ...; then the block tree.
+__global__ void __launch_bounds__(1024) k_inner_product(int L, const double *__restrict__ w, const double *__restrict__ dre,
+                                                        const double *__restrict__ dim, const double *__restrict__ rre,
+                                                        const double *__restrict__ rim, double *__restrict__ out)
+{
+	double hh = 0, dh = 0;
+	for (int i = threadIdx.x; i < L; i += 1024) {
+		hh += w[i] * (rre[i] * rre[i] + rim[i] * rim[i]);
+		dh += w[i] * (dre[i] * rre[i] + dim[i] * rim[i]);
+	}
+	block_sum2<1024>(hh, dh);
+	if (threadIdx.x == 0) {
+		out[0] = hh;
+		out[1] = dh;
+	}
+}
+
 __global__ void k_antenna(int W, const double *RA, const double *DEC, const double *psi, double gmst, Network net,
                           double *Fp, double *Fc, double *dt)
 {
@@ -1688,6 +1706,48 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = ms;
 	(void)L;
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_method_info(const char *generation_method, int *ppe_like, int *gimr, int *alpha_units, int *pv2, int *nrt)
+{
+	MethodDesc desc;
+	if (parse_method(generation_method, desc) != 0) return GWAT_B200_ERR_METHOD;
+	if (ppe_like) *ppe_like = (desc.ppe || desc.theory != THEORY_NONE) ? 1 : 0;
+	if (gimr) *gimr = (desc.gimr && !(desc.ppe || desc.theory != THEORY_NONE)) ? 1 : 0;
+	if (alpha_units) *alpha_units = theory_alpha_units(desc.theory) ? 1 : 0;
+	if (pv2) *pv2 = desc.pv2 ? 1 : 0;
+	if (nrt) *nrt = desc.nrt ? 1 : 0;
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_log_likelihood_internal(gwat_b200_ctx *ctx, int L, const double *frequencies, const double *psd, const double *data_re,
+                                      const double *data_im, const double *weights, const char *integration_method, int log10F,
+                                      const double *response_re, const double *response_im, double *logL)
+{
+	if (!ctx || L < 4 || !frequencies || !psd || !data_re || !data_im || !response_re || !response_im || !logL) return GWAT_B200_ERR_ARG;
+	const std::string integ = integration_method ? integration_method : "SIMPSONS";
+	const bool gl = integ == "GAUSSLEG";
+	if (!gl && integ != "SIMPSONS") return fail(ctx, GWAT_B200_ERR_ARG, "log_likelihood_internal: integration_method must be SIMPSONS or GAUSSLEG");
+	if (gl && !weights) return fail(ctx, GWAT_B200_ERR_ARG, "log_likelihood_internal: GAUSSLEG needs weights");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	std::vector<double> w(L);
+	for (int i = 0; i < L; i++) w[i] = quadrature_coefficient(i, L, gl, log10F != 0, weights, frequencies) / psd[i];
+	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)5 * L + 2)) return GWAT_B200_ERR_CUDA;
+	double *d = ctx->d_out;
+	const double *host[5] = {w.data(), data_re, data_im, response_re, response_im};
+	for (int k = 0; k < 5; k++) CUDA_TRY(ctx, cudaMemcpyAsync(d + (size_t)k * L, host[k], sizeof(double) * L, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (w is a local buffer)
+	k_inner_product<<<1, 1024, 0, st>>>(L, d, d + L, d + 2 * (size_t)L, d + 3 * (size_t)L, d + 4 * (size_t)L, d + 5 * (size_t)L);
+	ctx->launches += 1;
+	CUDA_TRY(ctx, cudaGetLastError());
+	double sums[2];
+	CUDA_TRY(ctx, cudaMemcpyAsync(sums, d + 5 * (size_t)L, sizeof(sums), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	const double pref = quadrature_prefactor(L, gl, frequencies, false);
+	*logL = -0.5 * (pref * sums[0] - 2.0 * (pref * sums[1]));
 	return GWAT_B200_OK;
 }
 

@@ -131,6 +131,37 @@ __global__ void __launch_bounds__(kT) k_max_reduce(const cufftDoubleComplex *__r
 	if (threadIdx.x == 0) out[w] = total;
 }
 
+// ---- match (src/waveform_util.cpp:41-89) ------------------------------------------------------------------------------------
+// in[i] = conj(d1[i]) d2[i] / S[i];  norms: 4 Simpson sums of |d1|^2 / S and |d2|^2 / S (data_snr, :108-127)
+__global__ void __launch_bounds__(kT) k_match_fill(int L, const double *__restrict__ a_re, const double *__restrict__ a_im,
+                                                  const double *__restrict__ b_re, const double *__restrict__ b_im,
+                                                  const double *__restrict__ psd, cufftDoubleComplex *__restrict__ in,
+                                                  double *__restrict__ norms)
+{
+	double n1 = 0, n2 = 0;
+	for (int i = threadIdx.x; i < L; i += kT) {
+		const double ar = a_re[i], ai = a_im[i], br = b_re[i], bi = b_im[i], s = psd[i];
+		// conj(a) * b
+		in[i] = cufftDoubleComplex{(ar * br + ai * bi) / s, (ar * bi - ai * br) / s};
+		const double coef = (i == 0 || i == L - 1) ? 1.0 : ((i % 2 == 0) ? 2.0 : 4.0);
+		n1 += coef * (4. * (ar * ar + ai * ai) / s);
+		n2 += coef * (4. * (br * br + bi * bi) / s);
+	}
+	n1 = block_reduce(n1, false);
+	n2 = block_reduce(n2, false);
+	if (threadIdx.x == 0) {
+		norms[0] = n1;
+		norms[1] = n2;
+	}
+}
+__global__ void __launch_bounds__(kT) k_match_max(int L, const cufftDoubleComplex *__restrict__ G, double *__restrict__ out)
+{
+	double best = -INFINITY;
+	for (int i = threadIdx.x; i < L; i += kT) best = fmax(best, sqrt(G[i].x * G[i].x + G[i].y * G[i].y));
+	best = block_reduce(best, true);
+	if (threadIdx.x == 0) out[2] = best;
+}
+
 #define MCUDA(ctx, expr)                                                                                         \
 	do {                                                                                                           \
 		cudaError_t e_ = (expr);                                                                                     \
@@ -220,5 +251,52 @@ extern "C" int gwat_b200_loglike_maximized_batch(gwat_b200_ctx *ctx, const char 
 		MCUDA(ctx, cudaMemcpyAsync(logL + w0, sc.out, sizeof(double) * nw, cudaMemcpyDeviceToHost, st));
 		MCUDA(ctx, cudaStreamSynchronize(st));
 	}
+	return GWAT_B200_OK;
+}
+
+// match(data1, data2, SN, frequencies, length) of the reference (src/waveform_util.cpp:41-89; gwatpy: match_py): the overlap of two
+// frequency-domain series maximised over a relative time shift, 4 max_t |IFFT(conj(d1) d2 / S)| df / (||d1|| ||d2||), with the norms
+// from data_snr (Simpson's rule, delta_f = f[1] - f[0]).  The inverse transform is cuFFT's (FFTW_BACKWARD in the reference).
+extern "C" int gwat_b200_match(gwat_b200_ctx *ctx, int L, const double *frequencies, const double *psd, const double *data1_re,
+                               const double *data1_im, const double *data2_re, const double *data2_im, double *match)
+{
+	if (!ctx || L < 4 || !frequencies || !psd || !data1_re || !data1_im || !data2_re || !data2_im || !match) return GWAT_B200_ERR_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	MCUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	double *d = nullptr;
+	cufftDoubleComplex *buf = nullptr;
+	MCUDA(ctx, cudaMalloc((void **)&d, sizeof(double) * ((size_t)5 * L + 4)));
+	MCUDA(ctx, cudaMalloc((void **)&buf, sizeof(cufftDoubleComplex) * (size_t)L));
+	auto cleanup = [&]() {
+		cudaFree(d);
+		cudaFree(buf);
+	};
+	const double *host[5] = {data1_re, data1_im, data2_re, data2_im, psd};
+	for (int k = 0; k < 5; k++)
+		if (cudaMemcpyAsync(d + (size_t)k * L, host[k], sizeof(double) * L, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+			cleanup();
+			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, "match: upload failed");
+		}
+	double *norms = d + (size_t)5 * L;
+	k_match_fill<<<1, kT, 0, st>>>(L, d, d + L, d + 2 * (size_t)L, d + 3 * (size_t)L, d + 4 * (size_t)L, buf, norms);
+	cufftHandle plan;
+	if (cufftPlan1d(&plan, L, CUFFT_Z2Z, 1) != CUFFT_SUCCESS || cufftSetStream(plan, st) != CUFFT_SUCCESS) {
+		cleanup();
+		return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, "match: cufftPlan1d failed");
+	}
+	const bool ok = cufftExecZ2Z(plan, buf, buf, CUFFT_INVERSE) == CUFFT_SUCCESS;
+	k_match_max<<<1, kT, 0, st>>>(L, buf, norms);
+	ctx->launches += 2;
+	double h[3] = {0, 0, 0};
+	const cudaError_t e1 = cudaMemcpyAsync(h, norms, sizeof(h), cudaMemcpyDeviceToHost, st);
+	const cudaError_t e2 = cudaStreamSynchronize(st);
+	cufftDestroy(plan);
+	cleanup();
+	if (!ok || e1 != cudaSuccess || e2 != cudaSuccess) return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, "match: transform failed");
+	const double delta_f = frequencies[1] - frequencies[0];
+	// simpsons_sum(delta_f, ...) = delta_f / 3 * sum coef_i g_i   (include/gwat/util.h:843-856)
+	const double n1 = sqrt(delta_f / 3. * h[0]), n2 = sqrt(delta_f / 3. * h[1]);
+	*match = 4. * (h[2] * delta_f) / (n1 * n2);
 	return GWAT_B200_OK;
 }

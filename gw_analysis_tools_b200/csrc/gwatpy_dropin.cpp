@@ -37,6 +37,11 @@ struct GenParams {  // what gen_params_base_py returns
 struct ModStruct {  // what MCMC_modification_struct_py returns
 	gwat_b200_mod m;
 };
+struct DataInterface {  // what mcmc_data_interface_py returns: the fields of mcmc_data_interface (include/gwat/mcmc_sampler_internals.h:20-30)
+	int min_dim, chain_id, max_dim, nested_model_number, chain_number;
+	double RJ_step_width;
+	bool burn_phase;
+};
 
 // One process-wide context; the uploaded network is cached and only re-uploaded when the caller's arrays change.
 struct Session {
@@ -554,6 +559,135 @@ void repack_parameters_py(double *parameters, void *gen_param, char *generation_
 	g->s.shift_phase = keep.shift_phase;
 	g->s.sky_average = keep.sky_average;
 	g->s.gmst = keep.gmst;
+}
+
+// ---- sampler-side helpers gwatpy exposes (src/gwatpy_wrapping.cpp:244-372) -------------------------------------------------
+void *mcmc_data_interface_py(int min_dim, int max_dim, int chain_id, int nested_model_number, int chain_number, double RJ_step_width,
+                             bool burn_phase)
+{
+	(void)RJ_step_width;
+	DataInterface *d = new DataInterface;
+	d->min_dim = min_dim;
+	d->max_dim = max_dim;
+	d->chain_id = chain_id;
+	d->nested_model_number = nested_model_number;
+	d->chain_number = chain_number;
+	d->RJ_step_width = chain_number;  // as the reference has it (src/gwatpy_wrapping.cpp:260)
+	d->burn_phase = burn_phase;
+	return d;
+}
+void mcmc_data_interface_destructor_py(void *d) { delete static_cast<DataInterface *>(d); }
+// read-back for tests and ctypes users (the reference's struct is plain data that Python cannot see either)
+void mcmc_data_interface_get_py(void *p, int *ints5, double *RJ_step_width, bool *burn_phase)
+{
+	const DataInterface *d = static_cast<DataInterface *>(p);
+	ints5[0] = d->min_dim;
+	ints5[1] = d->max_dim;
+	ints5[2] = d->chain_id;
+	ints5[3] = d->nested_model_number;
+	ints5[4] = d->chain_number;
+	*RJ_step_width = d->RJ_step_width;
+	*burn_phase = d->burn_phase;
+}
+
+// MCMC_prep_params (src/mcmc_gw.cpp:2492-2568): the flags every sampler likelihood call sets on the gen_params object, the copy
+// of the sampling vector into temp_params, the modification layout, and the dCS/EdGB unit change of the coupling.  Returns the
+// generation method in a string the caller owns (new char[], as the reference's wrapper does).  The reference's wrapper runs in a
+// translation unit whose static mcmc_gmst is never set, so gmst becomes 0 unless save_gmst (src/gwatpy_wrapping.cpp:357-381).
+char *MCMC_prep_params_py(double *param, double *temp_params, void *gen_params, int dimension, char *generation_method, void *mod_struct,
+                          bool save_gmst)
+{
+	GenParams *g = static_cast<GenParams *>(gen_params);
+	const gwat_b200_mod &m = static_cast<ModStruct *>(mod_struct)->m;
+	gwat_b200_source &s = g->s;
+	const double gmst = s.gmst;
+	s.sky_average = 0;
+	s.tidal_love = m.tidal_love;
+	s.tidal_love_error = m.tidal_love_error;
+	s.f_ref = 20;
+	s.shift_time = 1;
+	s.shift_phase = 1;
+	s.gmst = save_gmst ? gmst : 0.0;
+	s.equatorial_orientation = 0;
+	s.horizon_coord = 0;
+	s.NSflag1 = m.NSflag1;
+	s.NSflag2 = m.NSflag2;
+	for (int i = 0; i < dimension; i++) temp_params[i] = param[i];
+	int ppe_like = 0, gimr = 0, alpha_units = 0;
+	std::string method(generation_method ? generation_method : "");
+	std::string bare = method;
+	if (bare.compare(0, 5, "MCMC_") == 0) bare.erase(0, 5);
+	if (gwat_b200_method_info(bare.c_str(), &ppe_like, &gimr, &alpha_units, nullptr, nullptr) == 0) {
+		int base = dimension;
+		if (ppe_like) {
+			s.Nmod = m.ppE_Nmod;
+			for (int i = 0; i < m.ppE_Nmod; i++) s.bppe[i] = m.bppe[i];
+			base = dimension - m.ppE_Nmod;
+		} else if (gimr) {
+			s.Nmod_phi = m.gIMR_Nmod_phi;
+			s.Nmod_sigma = m.gIMR_Nmod_sigma;
+			s.Nmod_beta = m.gIMR_Nmod_beta;
+			s.Nmod_alpha = m.gIMR_Nmod_alpha;
+			for (int i = 0; i < GWAT_B200_MAX_MOD; i++) {
+				s.phii[i] = m.gIMR_phii[i];
+				s.sigmai[i] = m.gIMR_sigmai[i];
+				s.betai[i] = m.gIMR_betai[i];
+				s.alphai[i] = m.gIMR_alphai[i];
+			}
+			base = dimension - m.gIMR_Nmod_phi - m.gIMR_Nmod_sigma - m.gIMR_Nmod_beta - m.gIMR_Nmod_alpha;
+		}
+		if (alpha_units && base >= 0 && base < dimension) {
+			const double x = temp_params[base] / (299792458. / 1000.);  // pow_int(sqrt(alpha)[km] / (c/1000), 4):
+			temp_params[base] = ((x * x) * x) * x;                       // a sequential product (src/util.cpp:1585-1597)
+		}
+	}
+	char *out = new char[method.size() + 1];
+	std::memcpy(out, method.c_str(), method.size() + 1);
+	return out;
+}
+
+// pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476): the gIMR modifications that are switched on in an RJMCMC status vector.
+void pack_local_mod_structure_py(void *interface, double *param, int *status, char *waveform_extended, void *full_struct, void *local_struct)
+{
+	(void)param;
+	const DataInterface *di = static_cast<DataInterface *>(interface);
+	const gwat_b200_mod &full = static_cast<ModStruct *>(full_struct)->m;
+	gwat_b200_mod &loc = static_cast<ModStruct *>(local_struct)->m;
+	if (!waveform_extended || std::string(waveform_extended).find("gIMR") == std::string::npos) return;
+	const int b_phi = full.gIMR_Nmod_phi + di->min_dim, b_sigma = full.gIMR_Nmod_sigma + b_phi, b_beta = full.gIMR_Nmod_beta + b_sigma,
+	          b_alpha = full.gIMR_Nmod_alpha + b_beta;
+	int dimct = 0;
+	for (int i = 0; i < di->max_dim; i++) {
+		if (status[i] == 1) dimct++;
+		if (i >= di->min_dim && status[i] == 1) {
+			if (i < b_phi) loc.gIMR_Nmod_phi++;
+			else if (i < b_sigma) loc.gIMR_Nmod_sigma++;
+			else if (i < b_beta) loc.gIMR_Nmod_beta++;
+			else if (i < b_alpha) loc.gIMR_Nmod_alpha++;
+		}
+	}
+	if (dimct == di->min_dim) return;
+	int c_phi = 0, c_sigma = 0, c_beta = 0, c_alpha = 0;
+	for (int i = di->min_dim; i < di->max_dim; i++) {
+		if (status[i] != 1) continue;
+		if (i < b_phi) { if (c_phi < GWAT_B200_MAX_MOD) loc.gIMR_phii[c_phi++] = full.gIMR_phii[i - b_phi + full.gIMR_Nmod_phi]; }
+		else if (i < b_sigma) { if (c_sigma < GWAT_B200_MAX_MOD) loc.gIMR_sigmai[c_sigma++] = full.gIMR_sigmai[i - b_sigma + full.gIMR_Nmod_sigma]; }
+		else if (i < b_beta) { if (c_beta < GWAT_B200_MAX_MOD) loc.gIMR_betai[c_beta++] = full.gIMR_betai[i - b_beta + full.gIMR_Nmod_beta]; }
+		else if (i < b_alpha) { if (c_alpha < GWAT_B200_MAX_MOD) loc.gIMR_alphai[c_alpha++] = full.gIMR_alphai[i - b_alpha + full.gIMR_Nmod_alpha]; }
+	}
+}
+// read-back of a modification struct (tests / ctypes users)
+void MCMC_modification_struct_get_py(void *m, gwat_b200_mod *out) { *out = static_cast<ModStruct *>(m)->m; }
+
+// match_py (src/gwatpy_wrapping.cpp:43-57 -> match, src/waveform_util.cpp:41-89)
+double match_py(double *data1_real, double *data1_imag, double *data2_real, double *data2_imag, double *SN, double *frequencies, int length)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	if (ensure_ctx(S)) return NaN;
+	double out = NaN;
+	if (report(S, gwat_b200_match(S.ctx, length, frequencies, SN, data1_real, data1_imag, data2_real, data2_imag, &out))) return NaN;
+	return out;
 }
 
 // ---- detector helpers ---------------------------------------------------------------------------------------------------

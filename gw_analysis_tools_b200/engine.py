@@ -25,7 +25,7 @@ EXPORTS = [
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
     "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare", "gwat_b200_gps_to_gmst_radian",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
-    "gwat_b200_gauss_legendre_grid", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
+    "gwat_b200_gauss_legendre_grid", "gwat_b200_log_likelihood_internal", "gwat_b200_match", "gwat_b200_method_info", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
 
 
@@ -242,6 +242,25 @@ class Context:
                                                                int(reference_index), int(dimension), int(order), S, arr,
                                                                _p(out)))
         return out
+
+    def log_likelihood_internal(self, data, psd, frequencies, response, weights=None, integration_method="SIMPSONS", log10F=False):
+        """The reference's Log_Likelihood_internal for one detector and a response held in host memory."""
+        f, psd, w = _f64(frequencies), _f64(psd), _f64(weights)
+        dre, dim = _f64(np.asarray(data).real), _f64(np.asarray(data).imag)
+        rre, rim = _f64(np.asarray(response).real), _f64(np.asarray(response).imag)
+        out = C.c_double()
+        self._check(self._lib.gwat_b200_log_likelihood_internal(self._h, int(f.size), _p(f), _p(psd), _p(dre), _p(dim), _p(w),
+                                                                integration_method.encode(), int(bool(log10F)), _p(rre), _p(rim), C.byref(out)))
+        return out.value
+
+    def match(self, data1, data2, psd, frequencies):
+        """The reference's match(): overlap of two frequency series maximised over a relative time shift."""
+        f, psd = _f64(frequencies), _f64(psd)
+        a, b = np.asarray(data1), np.asarray(data2)
+        out = C.c_double()
+        self._check(self._lib.gwat_b200_match(self._h, int(f.size), _p(f), _p(psd), _p(_f64(a.real)), _p(_f64(a.imag)), _p(_f64(b.real)),
+                                              _p(_f64(b.imag)), C.byref(out)))
+        return out.value
 
     # ---- helpers ---------------------------------------------------------------------------------------------------
     def repack_mcmc_batch(self, method, params, gmst, mod=None):

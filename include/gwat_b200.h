@@ -304,6 +304,36 @@ double gwat_b200_gps_to_gmst_radian(double gps_time);
 
 /* ---- introspection used by bench.py / the tests ------------------------------------------------------------------ */
 
+/*
+ * Log_Likelihood_internal (include/gwat/mcmc_gw.h:276-284, src/mcmc_gw.cpp:801-868) for ONE detector and a response the caller
+ * already holds in host memory: -1/2 ((r|r) - 2 (d|r)) with the reference's quadrature (SIMPSONS: 1,4,2,...,4,1 by index parity
+ * and delta_f from the middle of the array; GAUSSLEG: weights, times f ln 10 when log10F).  Exists for callers that built the
+ * response themselves (fourier_detector_response); the batched likelihoods above never materialise responses.  Does not use
+ * or change the network set on the context.
+ */
+int gwat_b200_log_likelihood_internal(gwat_b200_ctx *ctx, int L, const double *frequencies, const double *psd, const double *data_re,
+                                      const double *data_im, const double *weights, const char *integration_method, int log10F,
+                                      const double *response_re, const double *response_im, double *logL);
+
+/*
+ * match(data1, data2, SN, frequencies, length) (include/gwat/waveform_util.h, src/waveform_util.cpp:41-89; gwatpy's match_py):
+ * 4 max_t |IFFT(conj(d1) d2 / S)| delta_f / (||d1|| ||d2||), norms by Simpson's rule with delta_f = f[1] - f[0].  `psd` is S(f)
+ * (the reference's argument `SN` is used as a power spectral density).  Uniform grid; one batched cuFFT where the reference
+ * plans one FFTW transform per call.  Does not use or change the network set on the context.
+ */
+int gwat_b200_match(gwat_b200_ctx *ctx, int L, const double *frequencies, const double *psd, const double *data1_re, const double *data1_im,
+                    const double *data2_re, const double *data2_im, double *match);
+
+/*
+ * How a generation_method string is read (the reference re-derives this with std::string::find in check_mod /
+ * check_theory_support, src/ppE_utilities.cpp:65-134, and in MCMC_prep_params, src/mcmc_gw.cpp:2517-2565):
+ *   ppe_like     the trailing sampling dimensions are ppE betas (ppE_* and every theory-mapped method)
+ *   gimr         they are gIMR fractional deviations
+ *   alpha_units  the first of them is sqrt(alpha) in km and is converted to alpha^2 in s^4 (dCS / EdGB family)
+ * Returns GWAT_B200_ERR_METHOD for a string this library does not implement.  Any pointer may be NULL.
+ */
+int gwat_b200_method_info(const char *generation_method, int *ppe_like, int *gimr, int *alpha_units, int *pv2, int *nrt);
+
 /* Measured FP64 FMA issue peak of ctx's GPU in TFLOP/s (a DFMA-chain microbenchmark; the roofline denominator of the
  * FP64-bound kernels -- the driver-written MEASURED_PEAKS.json carries no FP64 figure). */
 int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops);

@@ -213,3 +213,33 @@ def phenomd_intermediates(src):
     out = np.zeros(11)
     lib().oracle_ref_phenomd_intermediates(C.byref(src), _p(out))
     return dict(zip(["M", "eta", "chirpmass", "chi_pn", "A0", "fRD", "fdamp", "f1", "f3", "f1_phase", "f2_phase"], out))
+
+
+def match(data1, data2, psd, f):
+    """match() of the reference (src/waveform_util.cpp:41-89)."""
+    f, psd = _f64(f), _f64(psd)
+    a, b = np.asarray(data1), np.asarray(data2)
+    fn = lib().oracle_ref_match
+    fn.restype = C.c_double
+    return fn(_p(_f64(a.real)), _p(_f64(a.imag)), _p(_f64(b.real)), _p(_f64(b.imag)), _p(psd), _p(f), f.size)
+
+
+def mcmc_prep_params(method, mod, param, src):
+    """MCMC_prep_params (src/mcmc_gw.cpp:2492-2568): returns (temp_params, the source with the flags and layout it set)."""
+    param = _f64(param)
+    temp = np.zeros_like(param)
+    out = abi.Source()
+    m = mod if mod is not None else abi.mod_defaults()
+    lib().oracle_ref_mcmc_prep_params(method.encode(), C.byref(m), param.size, _p(param), C.byref(src), _p(temp), C.byref(out))
+    return temp, out
+
+
+def pack_local_mod_structure(min_dim, max_dim, status, waveform_extended, full_mod):
+    """pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476): (counts[4], indices[4][MAX_MOD]) of the local structure."""
+    status = np.ascontiguousarray(status, dtype=np.int32)
+    counts = np.zeros(4, dtype=np.int32)
+    idx = np.zeros((4, 8), dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    lib().oracle_ref_pack_local_mod_structure(int(min_dim), int(max_dim), status.ctypes.data_as(ip), waveform_extended.encode(),
+                                              C.byref(full_mod), counts.ctypes.data_as(ip), idx.ctypes.data_as(ip))
+    return counts, idx

@@ -576,6 +576,75 @@ double oracle_ref_calculate_snr(const char *curve, const char *detector, const c
 	                     std::string(integration_method), const_cast<double *>(weights), log10F != 0);
 }
 
+// match (src/waveform_util.cpp:41-89): overlap maximised over a relative time shift (FFTW_BACKWARD = the stand-in's DFT here).
+double oracle_ref_match(const double *a_re, const double *a_im, const double *b_re, const double *b_im, const double *psd, const double *f,
+                        int L)
+{
+	std::vector<std::complex<double>> a(L), b(L);
+	for (int i = 0; i < L; i++) {
+		a[i] = std::complex<double>(a_re[i], a_im[i]);
+		b[i] = std::complex<double>(b_re[i], b_im[i]);
+	}
+	return match(a.data(), b.data(), const_cast<double *>(psd), const_cast<double *>(f), L);
+}
+
+// MCMC_prep_params (src/mcmc_gw.cpp:2492-2568) on a source that arrives with the fields `src` carries: returns temp_params, the
+// flags it set on the gen_params object (as a gwat_b200_source) and the modification layout it attached.
+int oracle_ref_mcmc_prep_params(const char *method, const gwat_b200_mod *mod, int dimension, const double *param, const gwat_b200_source *src,
+                                double *temp_params, gwat_b200_source *out)
+{
+	ParamBox b;
+	to_gen_params(*src, b);
+	ModBox mb;
+	to_mod_struct(mod, mb);
+	gen_params_base<double> gp = b.gp;
+	std::string local = MCMC_prep_params(const_cast<double *>(param), temp_params, &gp, dimension, std::string(method), &mb.m);
+	gwat_b200_source s = *src;
+	s.sky_average = gp.sky_average;
+	s.tidal_love = gp.tidal_love;
+	s.tidal_love_error = gp.tidal_love_error;
+	s.f_ref = gp.f_ref;
+	s.shift_time = gp.shift_time;
+	s.shift_phase = gp.shift_phase;
+	s.gmst = gp.gmst;
+	s.NSflag1 = gp.NSflag1;
+	s.NSflag2 = gp.NSflag2;
+	s.Nmod = gp.Nmod;
+	s.Nmod_phi = gp.Nmod_phi;
+	s.Nmod_sigma = gp.Nmod_sigma;
+	s.Nmod_beta = gp.Nmod_beta;
+	s.Nmod_alpha = gp.Nmod_alpha;
+	if (check_mod(local) && (local.find("ppE") != std::string::npos || check_theory_support(local)))
+		for (int i = 0; i < gp.Nmod && i < GWAT_B200_MAX_MOD; i++) s.bppe[i] = gp.bppe[i];
+	*out = s;
+	free_prepped(gp, local, mb.m);
+	return (int)local.size();
+}
+
+// pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476); counts[4] and idx[4][GWAT_B200_MAX_MOD] receive the local structure.
+int oracle_ref_pack_local_mod_structure(int min_dim, int max_dim, const int *status, const char *waveform_extended, const gwat_b200_mod *full,
+                                        int *counts, int *idx)
+{
+	mcmc_data_interface iface;
+	iface.min_dim = min_dim;
+	iface.max_dim = max_dim;
+	ModBox fb;
+	to_mod_struct(full, fb);
+	MCMC_modification_struct loc;
+	loc.gIMR_Nmod_phi = loc.gIMR_Nmod_sigma = loc.gIMR_Nmod_beta = loc.gIMR_Nmod_alpha = 0;
+	loc.gIMR_phii = loc.gIMR_sigmai = loc.gIMR_betai = loc.gIMR_alphai = NULL;
+	pack_local_mod_structure(&iface, (double *)NULL, const_cast<int *>(status), std::string(waveform_extended), (void *)NULL, &fb.m, &loc);
+	counts[0] = loc.gIMR_Nmod_phi;
+	counts[1] = loc.gIMR_Nmod_sigma;
+	counts[2] = loc.gIMR_Nmod_beta;
+	counts[3] = loc.gIMR_Nmod_alpha;
+	int *arrs[4] = {loc.gIMR_phii, loc.gIMR_sigmai, loc.gIMR_betai, loc.gIMR_alphai};
+	for (int k = 0; k < 4; k++)
+		for (int i = 0; i < GWAT_B200_MAX_MOD; i++) idx[k * GWAT_B200_MAX_MOD + i] = (arrs[k] && i < counts[k]) ? arrs[k][i] : 0;
+	for (int k = 0; k < 4; k++) delete[] arrs[k];
+	return 0;
+}
+
 // Intermediate per-walker quantities of IMRPhenomD's setup, for unit-testing the GPU setup kernel
 // (src/IMRPhenomD.cpp:414-466).  out[0..] = M, eta, chirpmass, chi_pn, A0, fRD, fdamp, f1, f3, f1_phase, f2_phase
 int oracle_ref_phenomd_intermediates(const gwat_b200_source *src, double *out)

@@ -27,7 +27,7 @@ def test_header_compiles_against_stand_in():
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include", "gwat")), reason="reference headers not on this box")
 def test_header_compiles_against_reference_gen_params():
-    stubs = os.path.join(ROOT, "oracle", "stubs")
+    stubs = os.path.join(ROOT, "standins")
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-DGWAT_CXX_REAL_HEADERS", "-I" + stubs, "-I" + os.path.join(stubs, "gwatcfg"),
                     "-I" + os.path.join(REF, "include", "gwat"), "-I" + os.path.join(REF, "include")] + INCS + [SHIM], check=True)
 

@@ -22,7 +22,8 @@ ON_PATH_SYMBOLS = ["gen_params_base_py", "gen_params_base_py_destructor", "MCMC_
                    "calculate_mass2_py", "calculate_chirpmass_vectorized_py", "calculate_eta_vectorized_py",
                    "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py",
                    "fourier_waveform_full_py", "populate_noise_py", "calculate_snr_py", "gps_to_GMST_radian_py",
-                   "fourier_waveformC", "fourier_amplitudeC", "fourier_phaseC"]
+                   "fourier_waveformC", "fourier_amplitudeC", "fourier_phaseC", "MCMC_prep_params_py", "mcmc_data_interface_py",
+                   "pack_local_mod_structure_py", "match_py"]
 
 
 def _lib():
@@ -221,3 +222,121 @@ def test_amplitude_and_phase_are_the_waveforms_carrier(ctx, name):
     ci = np.cos(kw["incl_angle"])
     want = 0.5 * (1 + ci * ci) * a[0] * np.exp(-1j * p[0])
     assert np.abs(want - hp[0]).max() <= 1e-10 * np.abs(hp[0]).max()
+
+
+# ---- the sampler-side helpers (src/gwatpy_wrapping.cpp:244-381): host code, checked against the compiled reference ----------
+def _mod_struct(lib, m):
+    ia = lambda a: (C.c_int * 8)(*a)
+    return lib.MCMC_modification_struct_py(m.ppE_Nmod, (C.c_double * 8)(*m.bppe), m.gIMR_Nmod_phi, ia(m.gIMR_phii), m.gIMR_Nmod_sigma,
+                                           ia(m.gIMR_sigmai), m.gIMR_Nmod_beta, ia(m.gIMR_betai), m.gIMR_Nmod_alpha, ia(m.gIMR_alphai),
+                                           C.c_bool(bool(m.NSflag1)), C.c_bool(bool(m.NSflag2)))
+
+
+def test_mcmc_data_interface_py_fields():
+    lib = _lib()
+    lib.mcmc_data_interface_py.restype = C.c_void_p
+    h = lib.mcmc_data_interface_py(11, 15, 3, 2, 7, C.c_double(0.25), C.c_bool(True))
+    ints, rj, burn = (C.c_int * 5)(), C.c_double(), C.c_bool()
+    lib.mcmc_data_interface_get_py(C.c_void_p(h), ints, C.byref(rj), C.byref(burn))
+    assert list(ints) == [11, 15, 3, 2, 7]
+    assert rj.value == 7.0  # the reference stores chain_number there (src/gwatpy_wrapping.cpp:260)
+    assert burn.value is True
+    lib.mcmc_data_interface_destructor_py(C.c_void_p(h))
+
+
+PREP_CASES = [("IMRPhenomD", 11, {}), ("IMRPhenomPv2", 15, {}), ("dCS_IMRPhenomD", 12, dict(ppE_Nmod=1, bppe=[-1.0])),
+              ("EdGB_IMRPhenomPv2", 16, dict(ppE_Nmod=1, bppe=[-7.0])), ("ppE_IMRPhenomD_Inspiral", 13, dict(ppE_Nmod=2, bppe=[-3.0, 1.0])),
+              ("gIMRPhenomD", 14, dict(gIMR_Nmod_phi=2, gIMR_phii=[3, 4], gIMR_Nmod_beta=1, gIMR_betai=[2])),
+              ("IMRPhenomD_NRT", 13, dict(NSflag1=1, NSflag2=1))]
+
+
+@pytest.mark.parametrize("method,dim,modkw", PREP_CASES, ids=[c[0] for c in PREP_CASES])
+def test_mcmc_prep_params_py_vs_reference(oracle, method, dim, modkw):
+    lib = _lib()
+    lib.MCMC_prep_params_py.restype = C.c_void_p
+    mod = abi.mod_defaults(**modkw)
+    rng = np.random.default_rng(dim)
+    param = rng.uniform(0.1, 60.0, dim)
+    kw = dict(cases.CASES[0][2])
+    kw["gmst"] = 1.234
+    src = abi.source_defaults(**kw)
+    for save in (False, True):
+        temp_ref, out_ref = oracle.mcmc_prep_params(method, mod, param, src)
+        gp = _gen_params(lib, kw)
+        mh = _mod_struct(lib, mod)
+        temp = np.zeros(dim)
+        sp = lib.MCMC_prep_params_py(_p(param.copy()), _p(temp), C.c_void_p(gp), dim, method.encode(), C.c_void_p(mh), C.c_bool(save))
+        assert C.string_at(sp).decode() == method
+        assert np.array_equal(temp, temp_ref)  # bit for bit, the dCS / EdGB unit change included
+        got = abi.Source()
+        lib.gen_params_base_get_flat_py(C.c_void_p(gp), C.byref(got))
+        # (the oracle's translation unit has mcmc_gmst = 0 as well: gmst is 0 unless saved)
+        assert got.gmst == (1.234 if save else out_ref.gmst)
+        for fld in ("sky_average", "tidal_love", "tidal_love_error", "f_ref", "shift_time", "shift_phase", "NSflag1", "NSflag2", "Nmod", "Nmod_phi",
+                    "Nmod_sigma", "Nmod_beta", "Nmod_alpha"):
+            assert getattr(got, fld) == getattr(out_ref, fld), fld
+        assert list(got.bppe)[:got.Nmod] == list(out_ref.bppe)[:out_ref.Nmod]
+        lib.gen_params_base_py_destructor(C.c_void_p(gp))
+        lib.MCMC_modification_struct_py_destructor(C.c_void_p(mh))
+
+
+def test_pack_local_mod_structure_py_vs_reference(oracle):
+    lib = _lib()
+    lib.mcmc_data_interface_py.restype = C.c_void_p
+    full = abi.mod_defaults(gIMR_Nmod_phi=3, gIMR_phii=[2, 3, 4], gIMR_Nmod_sigma=2, gIMR_sigmai=[2, 4], gIMR_Nmod_beta=2, gIMR_betai=[2, 3],
+                            gIMR_Nmod_alpha=1, gIMR_alphai=[4])
+    min_dim, max_dim = 11, 19
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        status = np.ones(max_dim, dtype=np.int32)
+        status[min_dim:] = rng.integers(0, 2, max_dim - min_dim)
+        if trial == 0:
+            status[min_dim:] = 0  # the base model: nothing switched on
+        counts_ref, idx_ref = oracle.pack_local_mod_structure(min_dim, max_dim, status, "gIMRPhenomD", full)
+        iface = lib.mcmc_data_interface_py(min_dim, max_dim, 0, 0, 1, C.c_double(0), C.c_bool(False))
+        fh = _mod_struct(lib, full)
+        lh = lib.MCMC_modification_struct_py(0, None, 0, None, 0, None, 0, None, 0, None, C.c_bool(False), C.c_bool(False))
+        lib.pack_local_mod_structure_py(C.c_void_p(iface), None, status.ctypes.data_as(_ip), b"gIMRPhenomD", C.c_void_p(fh), C.c_void_p(lh))
+        loc = abi.Mod()
+        lib.MCMC_modification_struct_get_py(C.c_void_p(lh), C.byref(loc))
+        counts = [loc.gIMR_Nmod_phi, loc.gIMR_Nmod_sigma, loc.gIMR_Nmod_beta, loc.gIMR_Nmod_alpha]
+        assert counts == list(counts_ref)
+        for k, arr in enumerate((loc.gIMR_phii, loc.gIMR_sigmai, loc.gIMR_betai, loc.gIMR_alphai)):
+            assert list(arr)[:counts[k]] == list(idx_ref[k][:counts[k]])
+        for h, d in ((fh, lib.MCMC_modification_struct_py_destructor), (lh, lib.MCMC_modification_struct_py_destructor),
+                     (iface, lib.mcmc_data_interface_destructor_py)):
+            d(C.c_void_p(h))
+
+
+@pytest.mark.gpu
+def test_match_py_and_log_likelihood_internal_vs_reference(ctx, oracle):
+    lib = _lib()
+    lib.match_py.restype = C.c_double
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "waveforms_v1.npz"))
+    name, method, kw, gspec = [c for c in cases.CASES if c[0] == "D_bbh"][0]
+    f = cases.grid(gspec)
+    L = f.size
+    psd = oracle.populate_noise(f, "aLIGO_analytic") ** 2
+    h1 = gold[name + "/hp"]
+    kw2 = dict(kw)
+    kw2["mass1"] = kw["mass1"] * 1.01
+    h2 = oracle.fourier_waveform(method, abi.source_defaults(**kw2), f)[0]
+    for a, b in ((h1, h1), (h1, h2), (h2, h1 * np.exp(2j * np.pi * f * 0.01))):
+        ref = oracle.match(a, b, psd, f)
+        got = lib.match_py(_p(np.ascontiguousarray(a.real)), _p(np.ascontiguousarray(a.imag)), _p(np.ascontiguousarray(b.real)),
+                           _p(np.ascontiguousarray(b.imag)), _p(psd), _p(f), L)
+        assert abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
+        assert abs(ctx.match(a, b, psd, f) - ref) <= 1e-10 * abs(ref)
+    # Log_Likelihood_internal for a response held by the caller: Simpson (odd and even length) and Gauss-Legendre
+    resp = gold[name + "/single_L"] if name + "/single_L" in gold else h2
+    data = 0.9 * np.exp(0.3j) * resp + 0.05 * h2
+    for n in (L, L - 1):
+        ref = oracle.log_likelihood_internal(data[:n], psd[:n], f[:n], None, resp[:n])
+        got = ctx.log_likelihood_internal(data[:n], psd[:n], f[:n], resp[:n])
+        assert abs(got - ref) <= 1e-11 * abs(ref), (got, ref)
+    fg, wg = oracle.gauleg_grid(f[0], f[-1], 512)
+    rg = oracle.fourier_waveform(method, abi.source_defaults(**kw), fg)[0]
+    pg = oracle.populate_noise(fg, "aLIGO_analytic") ** 2
+    ref = oracle.log_likelihood_internal(0.8 * rg, pg, fg, wg, rg, log10F=True, integ="GAUSSLEG")
+    got = ctx.log_likelihood_internal(0.8 * rg, pg, fg, rg, weights=wg, integration_method="GAUSSLEG", log10F=True)
+    assert abs(got - ref) <= 1e-11 * abs(ref), (got, ref)
