@@ -37,6 +37,7 @@ namespace hosttab {  // the same generated tables for host-side use (detector ro
 #include "gwat_grid.h"
 #include "gwat_method.h"
 #include "gwat_repack.h"
+#include "gwat_setup_coop.h"
 
 using namespace gwat;
 
@@ -54,8 +55,6 @@ constexpr int kThreads = 256;
 #define GWAT_LOGLIKE_THREADS 256
 #endif
 constexpr int kLikeThreads = GWAT_LOGLIKE_THREADS;
-// one warp per CTA: the per-walker setup is a long dependent FP64 chain, so it is spread over as many SMs as possible
-constexpr int kSetupThreads = 32;
 // bin tiles (of kThreads bins) one CTA of the Fisher derivative kernel evaluates with one staging of its coefficient blocks
 constexpr int kFisherTilesPerCta = 4;
 // detectors one Fisher pass handles (sizes FisherPlan and the kernels' staging arrays)
@@ -71,6 +70,7 @@ __device__ __forceinline__ Tables device_tables()
 }
 
 typedef LikeGrid GridPtrs;
+
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -121,35 +121,80 @@ __device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool 
 // kernels
 // ---------------------------------------------------------------------------------------------------------------------
 
-template <class Fam>
-__global__ void __launch_bounds__(kSetupThreads) k_setup_mcmc(const double *__restrict__ params, int W, RepackPlan plan, Network net,
-                                                   int theory, double gmst, double T_segment, WalkerCoef *__restrict__ out,
-                                                   gwat_b200_source *__restrict__ src_out)
-{
-	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= W) return;
-	gwat_b200_source s;
-	repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, T_segment, s);
-	if (src_out) src_out[w] = s;
-	if (out) {
-		WalkerCoef wc;
-		walker_setup<Fam>(s, net, device_tables(), theory, wc);
-		wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
-		out[w] = wc;
-	}
-}
+// Per-walker setup, cooperative (gwat_setup_coop.h): one CTA sets up kSetupWalkers walkers, lane = walker, warp = role; the
+// finished records leave with coalesced stores.  params != NULL: sampling vectors (repack_mcmc_walker), else physical records.
+constexpr int kSetupWalkers = 32;
+static_assert(sizeof(SetupRec) * kSetupWalkers <= 48 * 1024, "static shared memory");
 
+// kernel experiments only (-DGWAT_SETUP_PROFILE): clock64 stamps of lane 0 of every role of block 0
+#ifdef GWAT_SETUP_PROFILE
+__device__ long long g_setup_stamp[4][16];
+#define GWAT_KSTAMP(i)                                                                    \
+	do {                                                                                    \
+		if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_setup_stamp[threadIdx.x >> 5][i] = clock64(); \
+	} while (0)
+#else
+#define GWAT_KSTAMP(i)
+#endif
 template <class Fam>
-__global__ void __launch_bounds__(kSetupThreads) k_setup_src(const gwat_b200_source *__restrict__ src, int W, Network net, int theory,
-                                                  WalkerCoef *__restrict__ out)
+__global__ void __launch_bounds__(kSetupWalkers * setup_roles<Fam>()) k_setup(const double *__restrict__ params, const gwat_b200_source *__restrict__ src_in, int W,
+                                                                              RepackPlan plan, Network net, int theory, double gmst, double T_segment,
+                                                                              WalkerCoef *__restrict__ out, unsigned long long *__restrict__ active_zero)
 {
-	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= W) return;
-	const gwat_b200_source s = src[w];
-	WalkerCoef wc;
-	walker_setup<Fam>(s, net, device_tables(), theory, wc);
-	wc.valid = coef_is_finite(wc, net.D, Fam::base == BASE_P) ? 1 : 0;
-	out[w] = wc;
+	constexpr bool kP = Fam::base == BASE_P;
+	__shared__ SetupRec recs[kSetupWalkers];
+	if (active_zero && blockIdx.x == 0 && threadIdx.x == 0) *active_zero = 0;  // the pass's active-bin counter (k_finish / k_loglike add to it)
+	const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+	const int w = blockIdx.x * kSetupWalkers + lane;
+	const bool active = w < W;
+	SetupRec &r = recs[lane];
+	const Tables t = device_tables();
+	gwat_b200_source s;
+	SetupCarry k;
+	GWAT_KSTAMP(0);
+	if (active) {
+		// (ONE copy of the repack for all roles: the kernel is bound by instruction fetch, and a copy per role -- each keeping only
+		// what its role reads -- was measured 70 % slower: four code streams per SM instead of one shared one)
+		if (params) repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, T_segment, s);
+		else s = src_in[w];
+		setup_step1<Fam>(role, s, net, t, theory, k, r);
+		GWAT_KSTAMP(1);
+	}
+	GWAT_KSTAMP(2);
+	if (role <= ROLE_AMP) {
+		// fRD, fdamp go from the amplitude role to the phase role: a barrier of these two warps alone (the twist role is the longest
+		// of step 1 and nobody needs it before step 3)
+		asm volatile("bar.sync 1, 64;" ::: "memory");
+		GWAT_KSTAMP(3);
+		if (active) setup_step2<Fam>(role, t, k, r);
+	}
+	GWAT_KSTAMP(4);
+	__syncthreads();
+	GWAT_KSTAMP(5);
+	if (active) setup_step3<Fam>(role, net, r);
+	GWAT_KSTAMP(6);
+	if (kP) {
+		__syncthreads();
+		GWAT_KSTAMP(7);
+		if (active) setup_step4<Fam>(role, s.shift_time != 0, r);
+		__syncthreads();
+	}
+	GWAT_KSTAMP(8);
+	if (active && role == ROLE_PHASE) {
+		if (r.refused) r.w.d.A0 = NAN;
+		r.w.valid = coef_is_finite(r.w, net.D, kP) ? 1 : 0;
+	}
+	__syncthreads();
+	GWAT_KSTAMP(9);
+	if (out) {
+		const int n = min(kSetupWalkers, W - blockIdx.x * kSetupWalkers);
+		double *o = reinterpret_cast<double *>(out + (size_t)blockIdx.x * kSetupWalkers);
+		for (int j = threadIdx.x; j < n * kCoefWords; j += blockDim.x) {
+			const int l = j / kCoefWords;
+			o[j] = reinterpret_cast<const double *>(&recs[l].w)[j - l * kCoefWords];
+		}
+	}
+	GWAT_KSTAMP(10);
 }
 
 // Stage one walker's coefficient block in shared memory.
@@ -177,13 +222,24 @@ constexpr int like_min_ctas()
 
 // grid (walkers, chunks): a CTA evaluates `units_per_cta` consecutive units of one walker (see gwat_like.h for the cut) and
 // writes one partial sum per (unit, warp):  partial[walker][unit][warp][2] = {sum, active bins}.
+// When one CTA holds all units of its walker (fin.logL != NULL: every BASELINE grid up to 16384 bins) it also finishes the walker:
+// the same fixed-order sum as k_finish -- lane l adds partials l, l + 32, ... in order, then the shuffle tree -- over the partials
+// in shared memory, so logL has the same bits whichever kernel forms it, and the third launch of the pass disappears.
+struct LikeFinish {
+	double *logL;  // NULL: partials go to `partial` and k_finish adds them
+	unsigned long long *active_total;
+	double prefactor;
+	int snr_mode;
+};
 template <class Fam, int D>
 __global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(const WalkerCoef *__restrict__ coefs, GridPtrs g, int unit_bins,
-                                                                              int units_per_cta, int units_total, double *__restrict__ partial)
+                                                                              int units_per_cta, int units_total, double *__restrict__ partial,
+                                                                              LikeFinish fin)
 {
 	static_assert(kLikeThreads == kUnitThreads && kSeedSlots * (D + 1) <= kLikeThreads, "seed table layout");
 	__shared__ WalkerCoef w;
 	__shared__ CtaSeeds<D> seeds;
+	__shared__ double fin_part[2 * kUnitWarps * kMaxUnitsPerCta];
 	const int unit0 = blockIdx.y * units_per_cta;
 	const int n_units = min(units_per_cta, units_total - unit0);
 	const int begin = unit0 * unit_bins;
@@ -193,7 +249,9 @@ __global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(
 		// the coefficient record before anything is staged, so such CTAs cost one L2 round trip.
 		const WalkerCoef &wg = coefs[blockIdx.x];
 		if (wg.valid && g.f[begin] > walker_fmax<Fam>(wg)) {
-			if (threadIdx.x < 2 * kUnitWarps * n_units) pout[threadIdx.x] = 0.0;
+			if (fin.logL) {
+				if (threadIdx.x == 0) fin.logL[blockIdx.x] = fin.snr_mode ? sqrt(fin.prefactor * 0.0) : -0.5 * (fin.prefactor * 0.0);
+			} else if (threadIdx.x < 2 * kUnitWarps * n_units) pout[threadIdx.x] = 0.0;
 			return;
 		}
 	}
@@ -215,9 +273,26 @@ __global__ void __launch_bounds__(kLikeThreads, like_min_ctas<Fam>()) k_loglike(
 		acc = warp_sum(acc);
 		nact = __reduce_add_sync(0xffffffffu, nact);
 		if (lane == 0) {
-			double *p = pout + 2 * (u * kUnitWarps + wid);
+			double *p = (fin.logL ? fin_part : pout) + 2 * (u * kUnitWarps + wid);
 			p[0] = w.valid ? acc : NAN;
 			p[1] = (double)nact;
+		}
+	}
+	if (fin.logL) {
+		__syncthreads();
+		if (wid == 0) {
+			const int entries = n_units * kUnitWarps;
+			double s = 0, n = 0;
+			for (int e = lane; e < entries; e += 32) {
+				s += fin_part[2 * e];
+				n += fin_part[2 * e + 1];
+			}
+			s = warp_sum(s);
+			n = warp_sum(n);
+			if (lane == 0) {
+				fin.logL[blockIdx.x] = fin.snr_mode ? sqrt(fin.prefactor * s) : -0.5 * (fin.prefactor * s);
+				if (fin.active_total) atomicAdd(fin.active_total, (unsigned long long)n);
+			}
 		}
 	}
 }
@@ -876,7 +951,7 @@ struct LikeCut {
 };
 
 template <class Fam>
-int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t st, const double *zero_data)
+int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t st, const double *zero_data, const LikeFinish &fin)
 {
 	const GridPtrs g = grid_ptrs(ctx, zero_data);
 	// walkers vary fastest: CTAs in flight together work on the same stretch of the grid tables, so a tile is fetched from
@@ -884,7 +959,7 @@ int launch_loglike(gwat_b200_ctx *ctx, int W, const LikeCut &cut, cudaStream_t s
 	const dim3 grid(W, cut.chunks);
 #define GWAT_LAUNCH_LIKE(DD)                                                                                                      \
 	case DD:                                                                                                                      \
-		k_loglike<Fam, DD><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, cut.unit_bins, cut.units_per_cta, cut.units_total, ctx->d_partial); \
+		k_loglike<Fam, DD><<<grid, kLikeThreads, 0, st>>>(ctx->d_coef, g, cut.unit_bins, cut.units_per_cta, cut.units_total, ctx->d_partial, fin); \
 		return 0;
 	switch (ctx->D) {
 		GWAT_FULL_ONLY(GWAT_LAUNCH_LIKE(1))
@@ -943,17 +1018,21 @@ int run_loglike(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, double *d_log
 		CUDA_TRY(ctx, cudaStreamWaitEvent(st_heavy, ev_a, 0));
 		sl = st_heavy;
 	}
-	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_active, 0, sizeof(unsigned long long), sl));
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, sl));
-	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, cut, sl, zero_data)) return fail(
+	// (the pass's active-bin counter was zeroed by k_setup, which every path runs first on `st`)
+	const bool fused = cut.chunks == 1;  // one CTA per walker: it finishes the walker itself
+	const LikeFinish fin{fused ? d_logL : nullptr, ctx->d_active, ctx->pref_like, snr_mode ? 1 : 0};
+	// CUDA events around the bin kernel cost ~3 us each on the stream (measured: cfg1 0.158 -> 0.148 ms per call without them): only on
+	// request (gwat_b200_set_kernel_timing; bench.py's resident loop asks for them, the roofline needs the kernel's own duration)
+	if (ctx->kernel_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, sl));
+	GWAT_DISPATCH_FAMILY(desc, if (launch_loglike<Fam>(ctx, W, cut, sl, zero_data, fin)) return fail(
 	                               ctx, GWAT_B200_ERR_STATE, "unsupported detector count"));
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, sl));
+	if (ctx->kernel_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, sl));
 	if (sl != st) {
 		CUDA_TRY(ctx, cudaEventRecord(ev_b, sl));
 		CUDA_TRY(ctx, cudaStreamWaitEvent(st, ev_b, 0));
 	}
-	k_finish<<<(W + 3) / 4, 128, 0, st>>>(ctx->d_partial, W, entries, ctx->pref_like, snr_mode ? 1 : 0, d_logL, ctx->d_active);
-	ctx->launches += 2;
+	if (!fused) k_finish<<<(W + 3) / 4, 128, 0, st>>>(ctx->d_partial, W, entries, ctx->pref_like, snr_mode ? 1 : 0, d_logL, ctx->d_active);
+	ctx->launches += fused ? 1 : 2;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
 }
@@ -967,7 +1046,7 @@ int collect_stats(gwat_b200_ctx *ctx, cudaStream_t st)
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	const unsigned long long act = *ctx->h_active;
 	float ms = 0;
-	CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	if (ctx->kernel_timing) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = ms;
 	ctx->last_active = (long long)act;
 	return 0;
@@ -984,7 +1063,8 @@ int check_ready(gwat_b200_ctx *ctx, bool need_data)
 template <class Fam>
 void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st)
 {
-	k_setup_src<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_src, W, ctx->net, theory, ctx->d_coef);
+	k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(nullptr, d_src, W, RepackPlan{}, ctx->net, theory, 0.0, 0.0,
+	                                                                                                 ctx->d_coef, ctx->d_active);
 }
 
 int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st)
@@ -1511,14 +1591,12 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	if (grow(ctx, ctx->d_params, ctx->cap_params, (size_t)W * dimension)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * W * dimension, cudaMemcpyHostToDevice, st));
-	// T_segment = 0 and the sign flip below leave tc as sampled: this entry point mirrors repack_parameters alone
-	typedef Family<BASE_D, PPE_NONE, false, false> AnyFam;
-	k_setup_mcmc<AnyFam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(ctx->d_params, W, plan, ctx->net, 0, gmst, 0.0, nullptr, ctx->d_src);
+	// tc is left as sampled: this entry point mirrors repack_parameters alone
+	k_repack_only<<<(W + 127) / 128, 128, 0, st>>>(ctx->d_params, W, plan, gmst, ctx->d_src);
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	CUDA_TRY(ctx, cudaMemcpyAsync(sources, ctx->d_src, sizeof(gwat_b200_source) * W, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
-	for (int w = 0; w < W; w++) sources[w].tc = -sources[w].tc;
 	return GWAT_B200_OK;
 }
 
@@ -1778,6 +1856,21 @@ int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops)
 	return GWAT_B200_OK;
 }
 
+#ifdef GWAT_SETUP_PROFILE
+int gwat_b200_debug_setup_stamps(long long *out64)
+{
+	return cudaMemcpyFromSymbol(out64, g_setup_stamp, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+int gwat_b200_set_kernel_timing(gwat_b200_ctx *c, int on)
+{
+	if (!c) return GWAT_B200_ERR_ARG;
+	std::lock_guard<std::mutex> lock(c->mu);
+	c->kernel_timing = on != 0;
+	return GWAT_B200_OK;
+}
+
 long long gwat_b200_launch_count(const gwat_b200_ctx *c) { return c ? c->launches : 0; }
 double gwat_b200_last_kernel_ms(const gwat_b200_ctx *c) { return c ? c->last_ms : 0.0; }
 long long gwat_b200_last_active_bins(const gwat_b200_ctx *c) { return c ? c->last_active : 0; }
@@ -1817,8 +1910,8 @@ int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gw
 	cudaEvent_t ev_a = lane > 0 ? ctx->extra[lane - 1].ev_a : nullptr, ev_b = lane > 0 ? ctx->extra[lane - 1].ev_b : nullptr;
 	LaneSwap swap(ctx, lane);
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
-	GWAT_DISPATCH_FAMILY(desc, k_setup_mcmc<Fam><<<(W + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, st>>>(d_params, W, plan, ctx->net, desc.theory, gmst, T_segment,
-	                                                                              ctx->d_coef, nullptr));
+	GWAT_DISPATCH_FAMILY(desc, k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(
+	                               d_params, nullptr, W, plan, ctx->net, desc.theory, gmst, T_segment, ctx->d_coef, ctx->d_active));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return run_loglike(ctx, desc, W, d_logL, st, st_heavy, ev_a, ev_b);

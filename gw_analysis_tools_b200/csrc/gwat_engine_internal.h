@@ -67,6 +67,7 @@ struct gwat_b200_ctx {
 	LikeLane extra[2];
 	// introspection
 	long long launches = 0;
+	bool kernel_timing = false;  // CUDA events around k_loglike (gwat_b200_set_kernel_timing)
 	double last_ms = 0;
 	long long last_active = 0;
 };

@@ -103,23 +103,6 @@ GWAT_HD double phenomd_fit_element(const double (*fit)[11], int i, double eta, d
 	return p[0] + p[1] * eta + xi * (p[2] + p[3] * eta + p[4] * eta * eta) + xi2 * (p[5] + p[6] * eta + p[7] * eta * eta) +
 	       xi3 * (p[8] + p[9] * eta + p[10] * eta * eta);
 }
-GWAT_HD void phenomd_fit(const double (*fit)[11], double eta, double chi_pn, Lambda &l)
-{
-	// one rolled loop over the 19 table rows (setup code is fetch-bound: gwat_hd.h); v[] is then dealt out
-	double v[19];
-	GWAT_SETUP_LOOP
-	for (int i = 0; i < 19; i++) v[i] = phenomd_fit_element(fit, i, eta, chi_pn);
-	for (int i = 0; i < 3; i++) l.rho[i] = v[i];
-	l.v2 = v[3];
-	for (int i = 0; i < 3; i++) l.gamma[i] = v[i + 4];
-	l.sigma[0] = 0;
-	for (int i = 0; i < 4; i++) l.sigma[i + 1] = v[i + 7];
-	l.beta[0] = 0;
-	for (int i = 0; i < 3; i++) l.beta[i + 1] = v[i + 11];
-	l.alpha[0] = 0;
-	for (int i = 0; i < 5; i++) l.alpha[i + 1] = v[i + 14];
-}
-
 // TaylorF2 3PN amplitude coefficients (reference: assign_pn_amplitude_coeff, src/IMRPhenomD.cpp:955-986).
 GWAT_HD void pn_amplitude_coeffs(const SrcQ &s, double *a)
 {

@@ -54,7 +54,8 @@ GWAT_HD void rot_y(const CosSin &a, Vec3 &v)
 }
 
 // Source-frame spins -> the PhenomP parameters.  `reduced` selects the (chi_p, phi_p) input convention.
-GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
+// First the spin projections (chi_l, chi_p, S_perp, S_L: all the carrier's remnant needs), then the frame angles.
+GWAT_HD void phenompv2_spin_projection(SrcQ &s, bool reduced)
 {
 	const double chi1_l = s.spin1z, chi2_l = s.spin2z;
 	const double q = s.mass1 / s.mass2;
@@ -74,6 +75,10 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 	const double m1 = q / (1 + q), m2 = 1. / (1 + q);
 	s.SP = s.chip * m1 * m1;
 	s.SL = chi1_l * m1 * m1 + chi2_l * m2 * m2;
+}
+GWAT_HD void phenompv2_frame_angles(SrcQ &s, bool reduced)
+{
+	const double m1_2 = s.mass1 * s.mass1, m2_2 = s.mass2 * s.mass2;
 
 	// L at f_ref (the reference fills the inspiral power table at f_ref: src/IMRPhenomP.cpp:1117-1123)
 	const PiPowers pi = pi_powers();
@@ -128,6 +133,12 @@ GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
 	const double XdotP = t.x * 0. + t.y * -1. + t.z * 0.;
 	const double XdotQ = t.x * Nz_Jf + t.y * 0. + t.z * -Nx_Jf;
 	s.zeta_polariz = sm::atan2(XdotQ, XdotP);
+}
+
+GWAT_HD void phenompv2_param_transform(SrcQ &s, bool reduced)
+{
+	phenompv2_spin_projection(s, reduced);
+	phenompv2_frame_angles(s, reduced);
 }
 
 // Coefficients of the PN expansions of the precession angles alpha(omega), epsilon(omega) (LAL's
@@ -243,12 +254,12 @@ GWAT_HD double natural_spline_deriv(const double *xa, const double *ya, int n, d
 	return add_rn(b_i, mul_rn(delx, add_rn(mul_rn(2.0, c[lo]), mul_rn(mul_rn(3.0, d_i), delx))));
 }
 
-// Per-walker setup of the twist-up on top of a finished carrier block `w.d`.
-template <class Fam>
-GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
+// Per-walker setup of the twist-up.  Everything but the time shift is independent of the carrier block (phenomp_setup_angles);
+// the time shift (calculate_time_shift) is the slope at fRD of the natural spline through kTimeShiftSamples samples of -phase on
+// [0.8, 1.2] fRD of the FINISHED carrier block: phenomp_time_shift_sample gives sample j, phenomp_time_shift_finish the slope.
+constexpr int kTimeShiftSamples = 10;
+GWAT_HD void phenomp_setup_angles(const SrcQ &s, PCoef &p)
 {
-	PCoef &p = w.p;
-	const DCoef &c = w.d;
 	double Y[5];
 	spin_weighted_y2(s.thetaJN, Y);
 	for (int i = 0; i < 5; i++) p.Y[i] = Y[i];
@@ -273,36 +284,47 @@ GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
 	p.phic = 2 * s.phi_aligned;
 	p.tc = phenomp_time_coefficient(s.tc);
 	p.f_ref = s.f_ref;
-	double t_corr = 0;
+}
+// x_j and y_j = -phase(x_j); false when the window is degenerate (the reference bails out with 0 as well, :567-572)
+template <class Fam>
+GWAT_HD bool phenomp_time_shift_sample(const DCoef &c, int j, double &x, double &y)
+{
+	const double f_final = c.fRD;
+	const double start = .8 * f_final, stop = 1.2 * f_final;
+	const double step = (stop - start) / (kTimeShiftSamples - 1);
+	if (!(step > 0)) return false;
+	const double f = start + j * step;
+	double a_unused, ph;
+	// the samples straddle fRD > f2p: merger-ringdown phase, where the sixth root only enters through (Mf)^(3/4);
+	// below f1p (never for physical parameters) the exact root is used
+	const double root = f < c.f1p ? sixth_root_direct(c.M, f) : sixth_root_approx(c.M, f);
+	// ln f feeds the inspiral and intermediate phases only: not evaluated for a merger-ringdown sample
+	const double lg = f > c.f2p ? 0.0 : sm::log(f);
+	phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, lg, a_unused, ph);
+	x = f;
+	y = -ph;
+	return true;
+}
+GWAT_HD double phenomp_time_shift_finish(const DCoef &c, const double *xs, const double *ys)
+{
+	return 2 * GWAT_PI * (natural_spline_deriv(xs, ys, kTimeShiftSamples, c.fRD) / (2. * GWAT_PI));
+}
+template <class Fam>
+GWAT_HD void phenomp_setup(const SrcQ &s, WalkerCoef &w)
+{
+	PCoef &p = w.p;
+	const DCoef &c = w.d;
+	phenomp_setup_angles(s, p);
+	p.tcorr_2pi = 2 * GWAT_PI * 0.0;
 	if (s.shift_time) {
-		// calculate_time_shift: slope at fRD of the natural spline through 10 samples of -phase on [0.8, 1.2] fRD
-		const int n = 10;
-		const double f_final = c.fRD;
-		const double start = .8 * f_final, stop = 1.2 * f_final;
-		const double step = (stop - start) / (n - 1);
-		if (!(step > 0)) {
-			t_corr = 0;  // the reference bails out with 0 as well (:567-572)
-		} else {
-			double xs[10], ys[10];
-			// (a rolled loop: the setup kernels are bound by instruction fetch, see gwat_hd.h; ten inlined copies of the carrier
-			// evaluation were a quarter of the kernel's code)
-			GWAT_SETUP_LOOP
-			for (int j = 0; j < n; j++) {
-				const double f = start + j * step;
-				double a_unused, ph;
-				// the samples straddle fRD > f2p: merger-ringdown phase, where the sixth root only enters through (Mf)^(3/4);
-				// below f1p (never for physical parameters) the exact root is used
-				const double root = f < c.f1p ? sixth_root_direct(c.M, f) : sixth_root_approx(c.M, f);
-				// ln f feeds the inspiral and intermediate phases only: not evaluated for a merger-ringdown sample
-				const double lg = f > c.f2p ? 0.0 : sm::log(f);
-				phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f, root, lg, a_unused, ph);
-				xs[j] = f;
-				ys[j] = -ph;
-			}
-			t_corr = natural_spline_deriv(xs, ys, n, f_final) / (2. * GWAT_PI);
-		}
+		double xs[kTimeShiftSamples], ys[kTimeShiftSamples];
+		bool ok = true;
+		// (a rolled loop: the setup kernels are bound by instruction fetch, see gwat_hd.h; ten inlined copies of the carrier
+		// evaluation were a quarter of the kernel's code)
+		GWAT_SETUP_LOOP
+		for (int j = 0; j < kTimeShiftSamples; j++) ok = phenomp_time_shift_sample<Fam>(c, j, xs[j], ys[j]) && ok;
+		if (ok) p.tcorr_2pi = phenomp_time_shift_finish(c, xs, ys);
 	}
-	p.tcorr_2pi = 2 * GWAT_PI * t_corr;
 }
 
 // One bin of IMRPhenomPv2: both polarisations, rotated by 2 zeta (fourier_waveform semantics).

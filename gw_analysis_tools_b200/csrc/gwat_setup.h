@@ -135,41 +135,40 @@ GWAT_HD void detector_setup(const Network &net, double ra, double dec, double ps
 }
 
 // ---- IMRPhenomD carrier setup ----------------------------------------------------------------------------------------
+// The setup is written as four stages so that the cooperative setup kernel (k_setup, gwat_engine.cu) can give them to different
+// warps of a CTA; phenomd_setup below runs them one after the other on one thread (Fisher stencil points, host harness) with the
+// very same arithmetic, so both give the same bits.
+//   remnant : ringdown / damping frequency (QNM spline)                         <- s
+//   common  : region boundaries, mass scalings                                   <- s, fRD, fdamp, f3
+//   amp     : rows 0-6 of the fit, PN amplitude coefficients, f3, the collocation of the intermediate amplitude
+//   phase   : rows 7-18 of the fit, PN phase coefficients, modifications, C1 matching, reference phase and time
+// Ownership of DCoef: `amp` fills the contiguous block A0 .. mr_w2, `common` + `phase` everything else.
+
+// ringdown and damping frequency: spline(QNM table, a_final) / (1 - E_rad) / M      (calc_fring / calc_fdamp)
 template <class Fam>
-GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)[5], int qnm_n, DCoef &c)
+GWAT_HD void phenomd_setup_remnant(SrcQ &s, const double (*qnm)[5], int qnm_n)
 {
-	const double M = s.M, eta = s.eta;
-	const PiPowers pi = pi_powers();
-
-	Lambda lam;
-	phenomd_fit(fit, eta, s.chi_pn, lam);
-	double cph[12], camp[7];
-	pn_amplitude_coeffs(s, camp);
-	pn_phase_coeffs(s, cph);
-	if (Fam::nrt) {
-		nrt_moments(s);
-		nrt_adjust_pn_phase(s, cph);
-	}
-	const double c8_gr = cph[8];
-	const double alpha1_fit = lam.alpha[1];  // the reference re-evaluates fit element 14 for the time shift (:456)
-	apply_gimr<Fam>(s, lam, cph);
-
-	// ringdown and damping frequency: spline(QNM table, a_final) / (1 - E_rad) / M      (calc_fring / calc_fdamp)
 	const double a_final = remnant_spin<Fam>(s);
-	const double erad = erad_rational_0815(eta, s.spin1z, s.spin2z);
-	s.fRD = (qnm_eval(qnm, qnm_n, a_final, 1) / (1.0 - erad)) / M;
-	s.fdamp = (qnm_eval(qnm, qnm_n, a_final, 3) / (1.0 - erad)) / M;
-	s.f1_phase = 0.018 / M;
-	s.f2_phase = s.fRD / 2.;
-	s.f1 = 0.014 / M;
-	{  // fpeak (:1312-1326)
-		const double g2 = lam.gamma[1], g3 = lam.gamma[2];
-		double pk;
-		if (g2 > 1) pk = s.fRD + (s.fdamp * (-1.) * g3) / g2;
-		else pk = s.fRD + s.fdamp * g3 * (sqrt(1 - g2 * g2) - 1) / g2;
-		s.f3 = sqrt(pk * pk);
-	}
+	const double erad = erad_rational_0815(s.eta, s.spin1z, s.spin2z);
+	s.fRD = (qnm_eval(qnm, qnm_n, a_final, 1) / (1.0 - erad)) / s.M;
+	s.fdamp = (qnm_eval(qnm, qnm_n, a_final, 3) / (1.0 - erad)) / s.M;
+}
 
+// fpeak (:1312-1326) and the fixed region boundaries; needs gamma[1], gamma[2], fRD, fdamp
+GWAT_HD void phenomd_setup_boundaries(SrcQ &s, double g2, double g3)
+{
+	s.f1_phase = 0.018 / s.M;
+	s.f2_phase = s.fRD / 2.;
+	s.f1 = 0.014 / s.M;
+	double pk;
+	if (g2 > 1) pk = s.fRD + (s.fdamp * (-1.) * g3) / g2;
+	else pk = s.fRD + s.fdamp * g3 * (sqrt(1 - g2 * g2) - 1) / g2;
+	s.f3 = sqrt(pk * pk);
+}
+
+GWAT_HD void phenomd_setup_common(const SrcQ &s, DCoef &c)
+{
+	const double M = s.M;
 	c.fcut = .2 / M;
 	c.f1a = s.f1;
 	c.f3a = s.f3;
@@ -188,9 +187,24 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.fRD = s.fRD;
 	c.fdamp = s.fdamp;
 	c.inv_fdamp = 1. / s.fdamp;
-	c.inv_eta = 1. / eta;
+	c.inv_eta = 1. / s.eta;
+}
 
-	// ---- amplitude -----------------------------------------------------------------------------------------------------
+// Rows [first, first + count) of the fit table into v (one rolled loop: setup code is fetch-bound, gwat_hd.h)
+GWAT_HD void phenomd_fit_rows(const double (*fit)[11], double eta, double chi_pn, int first, int count, double *v)
+{
+	GWAT_SETUP_LOOP
+	for (int i = 0; i < count; i++) v[i] = phenomd_fit_element(fit, first + i, eta, chi_pn);
+}
+
+// The amplitude block of DCoef (A0 .. mr_w2).  Needs s.fRD, s.fdamp, s.f1, s.f3 and c.M (phenomd_setup_common); `lam` brings rho,
+// v2, gamma.
+GWAT_HD void phenomd_setup_amp(const SrcQ &s, const Lambda &lam, DCoef &c)
+{
+	const double M = s.M;
+	const PiPowers pi = pi_powers();
+	double camp[7];
+	pn_amplitude_coeffs(s, camp);
 	c.A0 = s.A0 * sm::pow(M, 7. / 6.);
 	c.ains[0] = camp[0];
 	c.ains[1] = camp[1] * pi.third;
@@ -203,60 +217,91 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	c.mr_num = lam.gamma[0] * lam.gamma[2] * s.fdamp / M;
 	c.mr_rate = lam.gamma[1] / (lam.gamma[2] * s.fdamp);
 	c.mr_w2 = (lam.gamma[2] * s.fdamp) * (lam.gamma[2] * s.fdamp);
+	// Collocation of the intermediate amplitude: value+slope at f1, value at the midpoint, value+slope at f3
+	// (amp_connection_coeffs, :1679-1702; the reference expands the solution into closed-form monomial
+	// coefficients, here it stays in Newton divided-difference form in x = M f).
+	MfPowers p1;
+	mf_powers(M, s.f1, sixth_root_approx(M, s.f1), p1);  // amplitude only
+	const double v1 = phenomd_amp_ins(c, p1);
+	const double v2 = lam.v2;
+	const double v3 = phenomd_amp_mr(c, s.f3);
+	// d/df of the inspiral amplitude at f1
+	double dA1 = 0;
 	{
-		// Collocation of the intermediate amplitude: value+slope at f1, value at the midpoint, value+slope at f3
-		// (amp_connection_coeffs, :1679-1702; the reference expands the solution into closed-form monomial
-		// coefficients, here it stays in Newton divided-difference form in x = M f).
-		MfPowers p1;
-		mf_powers(M, s.f1, sixth_root_approx(M, s.f1), p1);  // amplitude only
-		const double v1 = phenomd_amp_ins(c, p1);
-		const double v2 = lam.v2;
-		const double v3 = phenomd_amp_mr(c, s.f3);
-		// d/df of the inspiral amplitude at f1
-		double dA1 = 0;
-		{
-			const double u = sm::cbrt(GWAT_PI * M * s.f1);
-			double uk = 1;
-			for (int k = 0; k < 7; k++) {
-				dA1 += camp[k] * uk * (k / 3.);
-				uk *= u;
-			}
-			const double m13 = sm::cbrt(M * s.f1);
-			const double m73 = m13 * m13 * m13 * m13 * m13 * m13 * m13;
-			dA1 += lam.rho[0] * m73 * (7. / 3.) + lam.rho[1] * m73 * m13 * (8. / 3.) + lam.rho[2] * m73 * m13 * m13 * 3.;
-			dA1 /= s.f1;
+		const double u = sm::cbrt(GWAT_PI * M * s.f1);
+		double uk = 1;
+		for (int k = 0; k < 7; k++) {
+			dA1 += camp[k] * uk * (k / 3.);
+			uk *= u;
 		}
-		// d/df of the merger-ringdown amplitude at f3
-		double dA3;
-		{
-			const double df = s.f3 - s.fRD;
-			const double den = df * df + c.mr_w2;
-			dA3 = -c.mr_num * sm::exp(-c.mr_rate * df) * (c.mr_rate * den + 2 * df) / (den * den);
-		}
-		const double x1 = M * s.f1, x3 = M * s.f3, x2 = M * ((s.f1 + s.f3) / 2.);
-		const double s1 = dA1 / M, s3 = dA3 / M;  // slopes with respect to x
-		// divided differences on [x1,x1,x2,x3,x3]
-		const double f01 = s1;
-		const double f12 = (v2 - v1) / (x2 - x1);
-		const double f23 = (v3 - v2) / (x3 - x2);
-		const double f34 = s3;
-		const double f012 = (f12 - f01) / (x2 - x1);
-		const double f123 = (f23 - f12) / (x3 - x1);
-		const double f234 = (f34 - f23) / (x3 - x2);
-		const double f0123 = (f123 - f012) / (x3 - x1);
-		const double f1234 = (f234 - f123) / (x3 - x1);
-		const double f01234 = (f1234 - f0123) / (x3 - x1);
-		c.ix1 = x1;
-		c.ix2 = x2;
-		c.ix3 = x3;
-		c.ic[0] = v1;
-		c.ic[1] = f01;
-		c.ic[2] = f012;
-		c.ic[3] = f0123;
-		c.ic[4] = f01234;
+		const double m13 = sm::cbrt(M * s.f1);
+		const double m73 = m13 * m13 * m13 * m13 * m13 * m13 * m13;
+		dA1 += lam.rho[0] * m73 * (7. / 3.) + lam.rho[1] * m73 * m13 * (8. / 3.) + lam.rho[2] * m73 * m13 * m13 * 3.;
+		dA1 /= s.f1;
 	}
+	// d/df of the merger-ringdown amplitude at f3
+	double dA3;
+	{
+		const double df = s.f3 - s.fRD;
+		const double den = df * df + c.mr_w2;
+		dA3 = -c.mr_num * sm::exp(-c.mr_rate * df) * (c.mr_rate * den + 2 * df) / (den * den);
+	}
+	const double x1 = M * s.f1, x3 = M * s.f3, x2 = M * ((s.f1 + s.f3) / 2.);
+	const double s1 = dA1 / M, s3 = dA3 / M;  // slopes with respect to x
+	// divided differences on [x1,x1,x2,x3,x3]
+	const double f01 = s1;
+	const double f12 = (v2 - v1) / (x2 - x1);
+	const double f23 = (v3 - v2) / (x3 - x2);
+	const double f34 = s3;
+	const double f012 = (f12 - f01) / (x2 - x1);
+	const double f123 = (f23 - f12) / (x3 - x1);
+	const double f234 = (f34 - f23) / (x3 - x2);
+	const double f0123 = (f123 - f012) / (x3 - x1);
+	const double f1234 = (f234 - f123) / (x3 - x1);
+	const double f01234 = (f1234 - f0123) / (x3 - x1);
+	c.ix1 = x1;
+	c.ix2 = x2;
+	c.ix3 = x3;
+	c.ic[0] = v1;
+	c.ic[1] = f01;
+	c.ic[2] = f012;
+	c.ic[3] = f0123;
+	c.ic[4] = f01234;
+}
 
-	// ---- phase ---------------------------------------------------------------------------------------------------------
+// What the phase stage computes before it needs the remnant: fit rows 7-18, PN phase coefficients, NRT moments, gIMR rescalings.
+struct PhasePrep {
+	double cph[12];
+	double c8_gr, alpha1_fit;
+};
+template <class Fam>
+GWAT_HD void phenomd_setup_phase_prep(SrcQ &s, const double (*fit)[11], Lambda &lam, PhasePrep &pp)
+{
+	double v[12];
+	phenomd_fit_rows(fit, s.eta, s.chi_pn, 7, 12, v);
+	lam.sigma[0] = 0;
+	for (int i = 0; i < 4; i++) lam.sigma[i + 1] = v[i];
+	lam.beta[0] = 0;
+	for (int i = 0; i < 3; i++) lam.beta[i + 1] = v[i + 4];
+	lam.alpha[0] = 0;
+	for (int i = 0; i < 5; i++) lam.alpha[i + 1] = v[i + 7];
+	pn_phase_coeffs(s, pp.cph);
+	if (Fam::nrt) {
+		nrt_moments(s);
+		nrt_adjust_pn_phase(s, pp.cph);
+	}
+	pp.c8_gr = pp.cph[8];
+	pp.alpha1_fit = lam.alpha[1];  // the reference re-evaluates fit element 14 for the time shift (:456)
+	apply_gimr<Fam>(s, lam, pp.cph);
+}
+
+// The phase side of DCoef.  Needs the common block of c, s.fRD, s.fdamp, s.f3 and lam.sigma/beta/alpha.
+template <class Fam>
+GWAT_HD void phenomd_setup_phase(SrcQ &s, Lambda &lam, const PhasePrep &pp, DCoef &c)
+{
+	const double M = s.M, eta = s.eta;
+	const PiPowers pi = pi_powers();
+	const double *cph = pp.cph;
 	c.k1 = cph[1] * pi.third;
 	c.k2 = cph[2] * pi.two3;
 	c.k3 = (cph[3] * GWAT_PI) * M;
@@ -283,7 +328,7 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 	// found in sequence, each with the not-yet-known ones at zero.
 	InsDerivIn din;
 	for (int k = 0; k < 12; k++) din.c[k] = cph[k];
-	din.c8_gr = c8_gr;
+	din.c8_gr = pp.c8_gr;
 	for (int k = 0; k < 5; k++) din.sigma[k] = lam.sigma[k];
 	din.M = M;
 	din.eta = eta;
@@ -337,9 +382,16 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		double f_ref, phic;
 		if (s.shift_phase) {
 			f_ref = s.f_ref;
-			double a_unused, phi_shift;
-			phenomd_bin<Family<BASE_D, Fam::ppe, Fam::gimr, false>>(c, f_ref, sixth_root_direct(M, f_ref), sm::log(f_ref), a_unused,
-			                                                         phi_shift);
+			// (the phase alone: the amplitude block may belong to another warp, see the note at the top)
+			const double root = sixth_root_direct(M, f_ref), lg = sm::log(f_ref);
+			typedef Family<BASE_D, Fam::ppe, Fam::gimr, false> Plain;
+			double phi_shift;
+			if (f_ref < c.f1p) {
+				MfPowers p;
+				mf_powers(M, f_ref, root, p);
+				phi_shift = phenomd_phase_ins<Plain>(c, f_ref, p, lg);
+			} else if (f_ref > c.f2p) phi_shift = phenomd_phase_mr<Plain>(c, f_ref, root);
+			else phi_shift = phenomd_phase_int<Plain>(c, f_ref, lg, root);
 			phic = 2 * s.phiRef + phi_shift;
 		} else {
 			f_ref = 0;
@@ -348,13 +400,34 @@ GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)
 		double tc_shift = 0;
 		if (s.shift_time) {
 			tc_shift = dphase_mr_df(lam, M, eta, s.fRD, s.fdamp, s.f3) + dphase_imr_extra<Fam>(s, s.f3) +
-			           (-lam.alpha[1] + alpha1_fit) * M / eta;
+			           (-lam.alpha[1] + pp.alpha1_fit) * M / eta;
 		}
 		c.tc_shift = tc_shift;
 		c.tc = phenomd_time_coefficient(s.tc, tc_shift);
 		c.f_ref = f_ref;
 		c.phic = phic;
 	}
+}
+
+// The four stages on one thread.
+template <class Fam>
+GWAT_HD void phenomd_setup(SrcQ &s, const double (*fit)[11], const double (*qnm)[5], int qnm_n, DCoef &c)
+{
+	Lambda lam;
+	{
+		double v[7];
+		phenomd_fit_rows(fit, s.eta, s.chi_pn, 0, 7, v);
+		for (int i = 0; i < 3; i++) lam.rho[i] = v[i];
+		lam.v2 = v[3];
+		for (int i = 0; i < 3; i++) lam.gamma[i] = v[i + 4];
+	}
+	PhasePrep pp;
+	phenomd_setup_phase_prep<Fam>(s, fit, lam, pp);
+	phenomd_setup_remnant<Fam>(s, qnm, qnm_n);
+	phenomd_setup_boundaries(s, lam.gamma[1], lam.gamma[2]);
+	phenomd_setup_common(s, c);
+	phenomd_setup_amp(s, lam, c);
+	phenomd_setup_phase<Fam>(s, lam, pp, c);
 }
 
 // ---- one walker, start to finish --------------------------------------------------------------------------------------

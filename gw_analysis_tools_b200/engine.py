@@ -25,7 +25,7 @@ EXPORTS = [
     "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
     "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare", "gwat_b200_gps_to_gmst_radian",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
-    "gwat_b200_gauss_legendre_grid", "gwat_b200_log_likelihood_internal", "gwat_b200_match", "gwat_b200_method_info", "gwat_b200_measure_fp64_peak", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
+    "gwat_b200_gauss_legendre_grid", "gwat_b200_log_likelihood_internal", "gwat_b200_match", "gwat_b200_method_info", "gwat_b200_measure_fp64_peak", "gwat_b200_set_kernel_timing", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
 ]
 
 
@@ -289,6 +289,10 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.gwat_b200_launch_count(self._h))
+
+    def set_kernel_timing(self, on):
+        """Record CUDA events around the hot likelihood kernel of every call (off by default: they cost ~6 us per call)."""
+        self._check(self._lib.gwat_b200_set_kernel_timing(self._h, int(bool(on))))
 
     @property
     def last_kernel_ms(self):

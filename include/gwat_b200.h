@@ -339,7 +339,10 @@ int gwat_b200_method_info(const char *generation_method, int *ppe_like, int *gim
 int gwat_b200_measure_fp64_peak(gwat_b200_ctx *ctx, double *tflops);
 /* Number of kernels this library has launched on ctx since creation (for the bench's gpu_launches). */
 long long gwat_b200_launch_count(const gwat_b200_ctx *ctx);
-/* Device-time (ms, CUDA events on the context's stream) of the hot kernel launches of the last *_batch call. */
+/* Device-time (ms, CUDA events on the context's stream) of the hot kernel launches of the last *_batch call.  For the
+ * likelihood entry points the events are recorded only after gwat_b200_set_kernel_timing(ctx, 1) (two events cost ~6 us per
+ * call on the stream, 4 % of a 1024-walker pass); otherwise 0.  Fisher batches always report it. */
+int gwat_b200_set_kernel_timing(gwat_b200_ctx *ctx, int on);
 double gwat_b200_last_kernel_ms(const gwat_b200_ctx *ctx);
 /* Active (walker,bin) pairs (f below the model's cutoff) evaluated by the last likelihood call. */
 long long gwat_b200_last_active_bins(const gwat_b200_ctx *ctx);

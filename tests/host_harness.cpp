@@ -13,6 +13,7 @@
 #include "../gw_analysis_tools_b200/csrc/gwat_grid.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_method.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_repack.h"
+#include "../gw_analysis_tools_b200/csrc/gwat_setup_coop.h"
 
 using namespace gwat;
 
@@ -145,6 +146,55 @@ extern "C" int hh_debug_dcoef(const gwat_b200_source *src, double *out)
 	walker_setup<Fam>(*src, net, host_tables(), theory, w);
 	std::memcpy(out, &w.d, sizeof(DCoef));
 	return (int)(sizeof(DCoef) / sizeof(double));
+}
+
+// The cooperative setup kernel's dataflow on the host (gwat_setup_coop.h): the steps run role by role on SEPARATE carry
+// structures, everything a role does not write itself is poisoned with NaN bit patterns beforehand, and the record is merged
+// exactly as k_setup merges it.  out_coop / out_seq receive the WalkerCoef words of this flow and of walker_setup: the test
+// wants them identical bit for bit.
+template <class Fam>
+int setup_coop_t(int theory, const gwat_b200_source *src, const Network &net, double *out_coop, double *out_seq)
+{
+	const Tables t = host_tables();
+	constexpr int kRoles = setup_roles<Fam>();
+	SetupRec r;
+	std::memset(&r, 0xff, sizeof(r));
+	SetupCarry k[4];
+	std::memset(k, 0xff, sizeof(k));
+	// the kernel's roles run concurrently between barriers; any order must do -- run them backwards
+	for (int role = kRoles - 1; role >= 0; role--) setup_step1<Fam>(role, *src, net, t, theory, k[role], r);
+	for (int role = kRoles - 1; role >= 0; role--) setup_step2<Fam>(role, t, k[role], r);
+	for (int role = kRoles - 1; role >= 0; role--) setup_step3<Fam>(role, net, r);
+	for (int role = kRoles - 1; role >= 0; role--) setup_step4<Fam>(role, src->shift_time != 0, r);
+	if (r.refused) r.w.d.A0 = NAN;
+	r.w.valid = 1;
+	std::memcpy(out_coop, &r.w, sizeof(WalkerCoef));
+	WalkerCoef w;
+	std::memset(&w, 0xff, sizeof(w));
+	walker_setup<Fam>(*src, net, t, theory, w);
+	w.pad_ = 0;
+	std::memcpy(out_seq, &w, sizeof(WalkerCoef));
+	return (int)(sizeof(WalkerCoef) / sizeof(double));
+}
+extern "C" int hh_setup_coop(const char *method, const gwat_b200_source *src, int D, const char *const *dets, double *out_coop, double *out_seq)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0) return -1;
+	Network net;
+	if (make_network(D, dets, net) != 0) return -3;
+	int n = 0;
+	DISPATCH_FAMILY(desc, n = setup_coop_t<Fam>(desc.theory, src, net, out_coop, out_seq));
+	return n;
+}
+// which words of WalkerCoef each family defines (the others stay poisoned in both flows): offsets for the test
+extern "C" void hh_walkercoef_layout(int *out)
+{
+	out[0] = (int)(offsetof(WalkerCoef, d) / 8);
+	out[1] = (int)(offsetof(WalkerCoef, p) / 8);
+	out[2] = (int)(offsetof(WalkerCoef, pfac) / 8);
+	out[3] = (int)(offsetof(WalkerCoef, det) / 8);
+	out[4] = (int)(offsetof(WalkerCoef, valid) / 8);
+	out[5] = (int)(sizeof(DetCoef) / 8);
 }
 
 // Fisher matrix of one source on the host, through the same GWAT_HD pieces the Fisher kernels use (unpack/repack of the

@@ -74,6 +74,36 @@ def test_waveform_and_response_vs_golden(hh, gold_wf, case):
         assert _relerr(re[1] + 1j * im[1], gold_wf[name + "/single_L"]) <= WF_TOL
 
 
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_cooperative_setup_dataflow_is_bit_identical(hh, gold_wf, case):
+    """k_setup's roles and steps (gwat_setup_coop.h) run on the host, role by role on separate carry structures with everything
+    a role does not own poisoned: the merged coefficient record equals walker_setup's bit for bit."""
+    name, method, kw, gspec = case
+    src = cases.source_from_bytes(gold_wf[name + "/src"])
+    layout = (C.c_int * 6)()
+    hh.hh_walkercoef_layout(layout)
+    o_d, o_p, o_fac, o_det, o_valid, det_words = list(layout)
+    dets = ["Hanford", "Livingston", "Virgo"]
+    arr = (C.c_char_p * 3)(*[d.encode() for d in dets])
+    a, b = np.zeros(512, dtype=np.uint64), np.zeros(512, dtype=np.uint64)
+    n = hh.hh_setup_coop(method.encode(), C.byref(src), 3, arr, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    assert n > 0, n
+    a, b = a[:n], b[:n]
+    poison = np.uint64(0xffffffffffffffff)
+    # words the sequential flow defines must be defined identically by the cooperative one; detectors beyond D stay untouched
+    defined = b != poison
+    defined[o_det + 3 * det_words:o_valid] = False
+    assert defined[o_d:o_d + 20].all()  # (the poison pattern is not a value any field takes)
+    # (an int field shares its word with 4 bytes of padding, which stay poisoned in the sequential flow: compare the int alone)
+    half = np.uint64(0xffffffff)
+    int_words = defined & ((b >> np.uint64(32)) == half)
+    full = defined & ~int_words
+    assert np.array_equal(a[full], b[full]), np.nonzero(full & (a != b))[0]
+    assert np.array_equal(a[int_words] & half, b[int_words] & half), np.nonzero(int_words & ((a & half) != (b & half)))[0]
+    # and the cooperative flow leaves nothing undefined that the per-bin code of this family reads
+    assert not (a[full] == poison).any()
+
+
 def test_modified_families_differ_from_gr(gold_wf):
     """The modification terms are really exercised: each modified case is far (>> tolerance) from its GR counterpart."""
     for name, base in [("ppE_ins", "D_bbh"), ("ppE_imr", "D_bbh"), ("gIMR", "D_bbh"), ("gIMR_log", "D_bbh"), ("dCS", "D_bbh"),

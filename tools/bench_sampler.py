@@ -157,6 +157,7 @@ def main():
     dev_ms = s.last_ms
     ct, widths = s.counters()
     pos, ll, lp = s.state()
+    ctx.set_kernel_timing(True)
     ctx.loglike_mcmc_batch(wl.method, pos, wl.gmst, wl.T_segment, wl.mod)  # where the ensemble is now: active bins, kernel time
     final_active, final_kernel_ms = ctx.last_active_bins / (C_ * wl.L), ctx.last_kernel_ms
     ctx.loglike_mcmc_batch(wl.method, init, wl.gmst, wl.T_segment, wl.mod)
