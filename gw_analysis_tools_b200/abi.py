@@ -46,7 +46,8 @@ class Source(C.Structure):
         ("NSflag1", C.c_int), ("NSflag2", C.c_int),
         ("dep_postmerger", C.c_int),
         ("equatorial_orientation", C.c_int), ("horizon_coord", C.c_int),
-        ("reserved_", C.c_int * 2),
+        ("cosmology", C.c_int),
+        ("reserved_", C.c_int),
     ]
 
 

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <cctype>
 #include <string>
 #include <vector>
 
@@ -66,7 +67,7 @@ constexpr int kFisherMaxDetectors = 5;
 
 __device__ __forceinline__ Tables device_tables()
 {
-	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS, gwat_md_alphas, gwat_md_boundaries_z, gwat_md_coeffs, GWAT_MD_ALPHAS}};
+	return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS, GWAT_NUM_COSMOLOGIES, gwat_md_alphas, gwat_md_boundaries_z, gwat_md_coeffs, GWAT_MD_ALPHAS}};
 }
 
 typedef LikeGrid GridPtrs;
@@ -1238,6 +1239,17 @@ int gwat_b200_abi_version(void) { return GWAT_B200_ABI_VERSION; }
 void gwat_b200_source_init(gwat_b200_source *src)
 {
 	if (src) source_defaults(*src);
+}
+
+int gwat_b200_cosmology_index(const char *name)
+{
+	if (!name) return -1;
+	static const char *const names[GWAT_NUM_COSMOLOGIES] = GWAT_COSMOLOGY_NAMES;
+	std::string up(name);
+	for (char &ch : up) ch = (char)std::toupper((unsigned char)ch);
+	for (int i = 0; i < GWAT_NUM_COSMOLOGIES; i++)
+		if (up == names[i]) return i;
+	return -1;
 }
 
 void gwat_b200_mod_init(gwat_b200_mod *mod)

@@ -50,6 +50,7 @@ struct SrcQ {
 	double tidal1, tidal2, tidal_weighted, delta_tidal_weighted, diss_tidal_weighted;
 	double quad1, quad2, oct1, oct2;
 	// ppE / gIMR
+	int cosmology;  // index into the reference's cosmos[] (theory mappings: Z_from_DL)
 	int Nmod;
 	double betappe[GWAT_B200_MAX_MOD], bppe[GWAT_B200_MAX_MOD];
 	int Nmod_phi, Nmod_sigma, Nmod_beta, Nmod_alpha;

@@ -59,7 +59,8 @@ GWAT_HD void source_defaults(gwat_b200_source &s)
 	s.dep_postmerger = 0;
 	s.equatorial_orientation = 0;
 	s.horizon_coord = 0;
-	s.reserved_[0] = s.reserved_[1] = 0;
+	s.cosmology = 0;  // "PLANCK15"
+	s.reserved_ = 0;
 }
 
 // calculate_mass1 / calculate_mass2 (src/util.cpp:1516-1540)

@@ -58,6 +58,7 @@ GWAT_HD void populate_source(const gwat_b200_source &in, SrcQ &s)
 	s.chip = in.chip;
 	s.phip = in.phip;
 	s.q = 0;
+	s.cosmology = in.cosmology;
 	s.Nmod = 0;
 	s.Nmod_phi = s.Nmod_sigma = s.Nmod_beta = s.Nmod_alpha = 0;
 	s.tidal1 = s.tidal2 = s.tidal_weighted = s.delta_tidal_weighted = s.diss_tidal_weighted = -1;

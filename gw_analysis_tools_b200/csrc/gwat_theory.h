@@ -5,7 +5,7 @@
 //   prep_source_parameters, theory block src/waveform_generator.cpp:1383-1410
 //   dCS_beta / dCS_phase_factor          src/ppE_utilities.cpp:473-524
 //   EdGB_beta / EdGB_phase_factor        src/ppE_utilities.cpp:573-617
-//   Z_from_DL, cosmology_interpolation_function   src/util.cpp:356-382, 502-512 (PLANCK15, the gen_params default)
+//   Z_from_DL, cosmology_interpolation_function   src/util.cpp:356-382, 502-512 (all six cosmologies of include/gwat/D_Z_Config.h)
 #ifndef GWAT_THEORY_H
 #define GWAT_THEORY_H
 
@@ -14,9 +14,10 @@
 namespace gwat {
 
 struct DzTable {
-	const double *boundaries;   // [segments + 1]
-	const double (*coeffs)[12];  // [segments][12]
+	const double (*boundaries)[4];   // [cosmology][segments + 1]
+	const double (*coeffs)[3][12];   // [cosmology][segments][12]
 	int segments;
+	int n_cosmologies;
 	// modified-dispersion distance D_alpha(z) (ModDispersion theory): alphas[n], z boundaries [n][4], coefficients [n][3][17]
 	const double *md_alphas;
 	const double (*md_boundaries_z)[4];
@@ -35,11 +36,14 @@ GWAT_HD double pow_int_seq(double base, int power)
 }
 
 // redshift from luminosity distance in Mpc: piecewise series in half-integer powers of D_L
-GWAT_HD double z_from_dl(double DL_mpc, const DzTable &t)
+// (cosmology = index into the reference's cosmos[]: PLANCK15, PLANCK13, WMAP9, WMAP7, WMAP5, TESTING_COSMOLOGY; -1 as the
+// reference returns it for a name it does not know)
+GWAT_HD double z_from_dl(double DL_mpc, int cosmology, const DzTable &t)
 {
+	if (cosmology < 0 || cosmology >= t.n_cosmologies) return -1;
 	for (int i = 0; i < t.segments; i++) {
-		if (DL_mpc < t.boundaries[i + 1]) {
-			const double *c = t.coeffs[i];
+		if (DL_mpc < t.boundaries[cosmology][i + 1]) {
+			const double *c = t.coeffs[cosmology][i];
 			double sum = c[0];
 			const double rootx = sqrt(DL_mpc);
 			for (int k = 1; k < 12; k++) sum += c[k] * pow_int_seq(rootx, k);
@@ -119,7 +123,7 @@ GWAT_HD void apply_theory(int theory, const DzTable &dz, SrcQ &s)
 	const double root = sqrt(1. - 4 * s.eta);
 	const double m1 = 1. / 2 * (s.chirpmass / etapow + root * s.chirpmass / etapow);
 	const double m2 = 1. / 2 * (s.chirpmass / etapow - root * s.chirpmass / etapow);
-	const double Z = z_from_dl(s.DL / GWAT_MPC_SEC, dz);
+	const double Z = z_from_dl(s.DL / GWAT_MPC_SEC, s.cosmology, dz);
 	const double unredshiftedM = s.M / (1. + Z);
 	const double in0 = s.betappe[0], in1 = s.betappe[1];
 	const double eta = s.eta;

@@ -237,6 +237,12 @@ void *gen_params_base_py(double mass1, double mass2, double *spin1, double *spin
 	s.theta = theta;
 	s.phi = phi;
 	p->cosmology = cosmology ? cosmology : "PLANCK15";
+	s.cosmology = gwat_b200_cosmology_index(p->cosmology.c_str());
+	if (s.cosmology < 0) {
+		std::fprintf(stderr, "gwat_b200: gen_params_base_py: unknown cosmology '%s'\n", p->cosmology.c_str());
+		delete p;
+		return nullptr;
+	}
 	s.equatorial_orientation = equatorial_orientation;
 	s.horizon_coord = horizon_coord;
 	s.NSflag1 = NSflag1;

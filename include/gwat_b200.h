@@ -71,7 +71,10 @@ typedef struct gwat_b200_source {
 	int NSflag1, NSflag2;
 	int dep_postmerger;
 	int equatorial_orientation, horizon_coord;
-	int reserved_[2];
+	int cosmology;                   /* gen_params::cosmology as its index in the reference's cosmos[] (include/gwat/D_Z_Config.h:13):
+	                                    0 PLANCK15 (the default), 1 PLANCK13, 2 WMAP9, 3 WMAP7, 4 WMAP5, 5 TESTING_COSMOLOGY;
+	                                    gwat_b200_cosmology_index() maps the name.  Read by the theory mappings only (Z_from_DL) */
+	int reserved_;
 } gwat_b200_source;
 
 /*
@@ -100,6 +103,8 @@ int gwat_b200_abi_version(void);
 /* Fill a source / modification record with the reference's member defaults (include/gwat/util.h:125-285,
  * include/gwat/mcmc_gw.h:52-67). */
 void gwat_b200_source_init(gwat_b200_source *src);
+/* Index of a cosmology name as Z_from_DL reads it (case-insensitive, src/util.cpp:356-365); -1 for a name the reference does not know. */
+int gwat_b200_cosmology_index(const char *name);
 void gwat_b200_mod_init(gwat_b200_mod *mod);
 
 /* One context per GPU and per submitting thread group.  Owns the device copies of the frequency grid, PSDs, data and

@@ -76,6 +76,8 @@ inline bool flatten(const GenParams &g, gwat_b200_source &s)
 	s.dep_postmerger = g.dep_postmerger;
 	s.equatorial_orientation = g.equatorial_orientation;
 	s.horizon_coord = g.horizon_coord;
+	s.cosmology = gwat_b200_cosmology_index(std::string(g.cosmology).c_str());
+	if (s.cosmology < 0) return false;  // (the reference prints "Invalid Cosmology" and carries on with z = -1)
 	if (g.equatorial_orientation) { s.theta_l = g.theta_l; s.phi_l = g.phi_l; }
 	if (g.horizon_coord) { s.theta = g.theta; s.phi = g.phi; }
 	const int counts[5] = {g.Nmod, g.Nmod_phi, g.Nmod_sigma, g.Nmod_beta, g.Nmod_alpha};

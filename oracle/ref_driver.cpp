@@ -60,6 +60,10 @@ void to_gen_params(const gwat_b200_source &s, ParamBox &b)
 		g.spin1[i] = s.spin1[i];
 		g.spin2[i] = s.spin2[i];
 	}
+	{
+		static const char *const names[6] = {"PLANCK15", "PLANCK13", "WMAP9", "WMAP7", "WMAP5", "TESTING_COSMOLOGY"};  // cosmos[], D_Z_Config.h:13
+		g.cosmology = names[(s.cosmology >= 0 && s.cosmology < 6) ? s.cosmology : 0];
+	}
 	g.tc = s.tc;
 	g.phiRef = s.phiRef;
 	g.f_ref = s.f_ref;

@@ -10,7 +10,9 @@
 typedef gen_params_base<double> test_gen_params;
 #else
 #include <cstddef>
+#include <string>
 struct test_gen_params {
+	std::string cosmology = "PLANCK15";
 	double mass1, mass2, Luminosity_Distance;
 	double spin1[3], spin2[3];
 	double tc = 0;

@@ -19,7 +19,7 @@ using namespace gwat;
 
 namespace {
 
-Tables host_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS, gwat_md_alphas, gwat_md_boundaries_z, gwat_md_coeffs, GWAT_MD_ALPHAS}}; }
+Tables host_tables() { return Tables{gwat_phenomd_fit, gwat_qnm_knots, GWAT_QNM_N, DzTable{gwat_dz_boundaries, gwat_dz_coeffs, GWAT_DZ_SEGMENTS, GWAT_NUM_COSMOLOGIES, gwat_md_alphas, gwat_md_boundaries_z, gwat_md_coeffs, GWAT_MD_ALPHAS}}; }
 
 struct Grid {
 	std::vector<double> f, hi, lo, lg;

@@ -118,3 +118,54 @@ def test_theory_mcmc_vectors_and_fisher(ctx, oracle):
         dg = np.sqrt(np.abs(np.diag(want_f)))
         nerr = np.abs(got_f - want_f) / np.outer(dg, dg)
         assert np.median(nerr) <= 1e-6 and nerr.max() <= 1e-4, (np.median(nerr), nerr.max())
+
+
+# ---- cosmologies of Z_from_DL other than the default (include/gwat/D_Z_Config.h: cosmos[]) ----------------------------------
+COSMO_METHODS = ["dCS_IMRPhenomD", "EdGB_IMRPhenomD", "ModDispersion_IMRPhenomD", "ExtraDimension_IMRPhenomD"]
+
+
+def _cosmo_source(gold, method, index):
+    name = [c[0] for c in (cases.THEORY_CASES + cases.CASES) if c[1] == method][0]
+    g = gold if name + "/src" in gold else np.load(os.path.join(GOLD, "waveforms_v1.npz"))
+    src = cases.source_from_bytes(g[name + "/src"])
+    src.cosmology = index
+    src.Luminosity_Distance = 2500.0  # z ~ 0.4-0.45: the cosmologies differ in the third digit of z
+    return src, [c for c in (cases.THEORY_CASES + cases.CASES) if c[0] == name][0][3]
+
+
+@pytest.mark.parametrize("index", [1, 2, 3, 4, 5], ids=["PLANCK13", "WMAP9", "WMAP7", "WMAP5", "TESTING_COSMOLOGY"])
+def test_cosmologies_host_math_vs_reference(hh, oracle, gold, index):
+    for method in COSMO_METHODS:
+        src, gspec = _cosmo_source(gold, method, index)
+        f = cases.grid(gspec)
+        o = [np.zeros(f.size) for _ in range(4)]
+        assert hh.hh_fourier_waveform(method.encode(), C.byref(src), _p(f), f.size, *[_p(x) for x in o]) == 0
+        hp, hc = oracle.fourier_waveform(method, src, f)
+        assert _relerr(o[0] + 1j * o[1], hp) <= 1e-10, method
+        src0, _ = _cosmo_source(gold, method, 0)
+        hp0, _ = oracle.fourier_waveform(method, src0, f)
+        if index != 5:  # (TESTING_COSMOLOGY carries PLANCK15's numbers)
+            assert _relerr(hp0, hp) > 1e-6, method  # the cosmology is really read
+
+
+def test_cosmology_names():
+    from gw_analysis_tools_b200 import engine
+    lib = engine.load_library()
+    for i, n in enumerate(["PLANCK15", "PLANCK13", "WMAP9", "WMAP7", "WMAP5", "TESTING_COSMOLOGY"]):
+        assert lib.gwat_b200_cosmology_index(n.encode()) == i
+        assert lib.gwat_b200_cosmology_index(n.lower().encode()) == i  # Z_from_DL upper-cases the name
+    assert lib.gwat_b200_cosmology_index(b"EINSTEIN_DE_SITTER") == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("index", [1, 2, 4], ids=["PLANCK13", "WMAP9", "WMAP5"])
+def test_cosmologies_cuda_vs_reference(ctx, oracle, gold, index):
+    for method in COSMO_METHODS:
+        src, gspec = _cosmo_source(gold, method, index)
+        f = cases.grid(gspec)
+        psd = np.tile(workloads.aligo_analytic_psd(f), (3, 1))
+        ctx.set_network(cases.DETECTORS, f, psd)
+        hp, hc = ctx.fourier_waveform_batch(method, [src])
+        rp, rc = oracle.fourier_waveform(method, src, f)
+        assert _relerr(hp[0], rp) <= 1e-10, method
+        assert _relerr(hc[0], rc) <= 1e-10, method

@@ -101,16 +101,16 @@ def main():
         assert len(D) == 9 and len(loc) == 3
         rows.append((name, D, loc, gf))
 
-    # redshift(luminosity distance) piecewise half-power series of the default cosmology PLANCK15
-    # (include/gwat/D_Z_Config.h: boundaries_D[0], COEFF_VEC_DZ[0]; evaluated by Z_from_DL, src/util.cpp:356-382)
+    # redshift(luminosity distance) piecewise half-power series, all cosmologies of the reference
+    # (include/gwat/D_Z_Config.h: cosmos, boundaries_D, COEFF_VEC_DZ; evaluated by Z_from_DL, src/util.cpp:356-382)
     dz = strip_comments(open(os.path.join(REF, "include/gwat/D_Z_Config.h")).read())
     bD = numbers(array_body(dz, "boundaries_D"))
     cDZ = numbers(array_body(dz, "COEFF_VEC_DZ"))
     ncos = int(re.search(r"num_cosmologies\s*=\s*(\d+)", dz).group(1))
     nseg, ndeg = 3, 12
     assert len(bD) == ncos * (nseg + 1) and len(cDZ) == ncos * nseg * ndeg, (len(bD), len(cDZ))
-    bD0 = bD[:nseg + 1]
-    cDZ0 = cDZ[:nseg * ndeg]
+    cosmo_names = re.findall(r'"([A-Z0-9_]+)"', re.search(r"cosmos\[\d+\]\s*=\s*\{([^}]*)\}", dz).group(1))
+    assert len(cosmo_names) == ncos and cosmo_names[0] == "PLANCK15", cosmo_names
 
     # modified-dispersion distance D_alpha(z) (include/gwat/D_Z_Config_modified_dispersion.h: MD_alphas, MD_boundaries_Z,
     # MD_COEFF_VEC_ZD; evaluated by DL_from_Z_MD, src/ppE_utilities.cpp:785-822: sum_j c_j z^(-3.5 + j/2))
@@ -136,12 +136,21 @@ def main():
         for i in range(19):
             o.write("{" + ",".join(r(x) for x in lam[i * 11:(i + 1) * 11]) + "},\n")
         o.write("};\n\n")
-        o.write("// PLANCK15 z(D_L/Mpc): segment boundaries and, per segment, coefficients of sum_k c_k (sqrt D_L)^k\n")
-        o.write("#define GWAT_DZ_SEGMENTS %d\n#define GWAT_DZ_DEGREE %d\n" % (nseg, ndeg))
-        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_boundaries[GWAT_DZ_SEGMENTS + 1] = {" + ",".join(r(x) for x in bD0) + "};\n")
-        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_coeffs[GWAT_DZ_SEGMENTS][GWAT_DZ_DEGREE] = {\n")
-        for i in range(nseg):
-            o.write("{" + ",".join(r(x) for x in cDZ0[i * ndeg:(i + 1) * ndeg]) + "},\n")
+        o.write("// z(D_L/Mpc) per cosmology (index = position in the reference's cosmos[]: " + ", ".join(cosmo_names) + "):\n")
+        o.write("// segment boundaries and, per segment, coefficients of sum_k c_k (sqrt D_L)^k\n")
+        o.write("#define GWAT_NUM_COSMOLOGIES %d\n#define GWAT_DZ_SEGMENTS %d\n#define GWAT_DZ_DEGREE %d\n" % (ncos, nseg, ndeg))
+        o.write("#define GWAT_COSMOLOGY_NAMES {" + ",".join('"%s"' % n for n in cosmo_names) + "}\n")
+        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_boundaries[GWAT_NUM_COSMOLOGIES][GWAT_DZ_SEGMENTS + 1] = {\n")
+        for c in range(ncos):
+            o.write("{" + ",".join(r(x) for x in bD[c * (nseg + 1):(c + 1) * (nseg + 1)]) + "},\n")
+        o.write("};\n")
+        o.write("GWAT_TABLE_QUALIFIER double gwat_dz_coeffs[GWAT_NUM_COSMOLOGIES][GWAT_DZ_SEGMENTS][GWAT_DZ_DEGREE] = {\n")
+        for c in range(ncos):
+            o.write("{")
+            for i in range(nseg):
+                base = (c * nseg + i) * ndeg
+                o.write("{" + ",".join(r(x) for x in cDZ[base:base + ndeg]) + "},")
+            o.write("},\n")
         o.write("};\n\n")
         o.write("// modified-dispersion distance D_alpha(z)/Mpc: alphas, z boundaries per alpha, coefficients of sum_j c_j z^(-3.5 + j/2)\n")
         o.write("#define GWAT_MD_ALPHAS %d\n#define GWAT_MD_SEGMENTS %d\n#define GWAT_MD_DEGREE %d\n" % (na, md_seg, md_deg))
