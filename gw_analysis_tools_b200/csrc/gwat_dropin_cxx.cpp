@@ -247,7 +247,17 @@ int fourier_detector_response<double>(double *frequencies, int length, std::comp
 	gwat_b200::Engine *e = engine_locked(S);
 	if (!e) return 0;
 	S.net_key = 0;
-	return gwat_b200::fourier_detector_response(*e, frequencies, length, response, detector, generation_method, parameters);
+	const int st = gwat_b200::fourier_detector_response(*e, frequencies, length, response, detector, generation_method, parameters);
+	if (parameters->equatorial_orientation && !parameters->horizon_coord) {
+		// the reference derives incl_angle and psi from (theta_l, phi_l) IN the caller's object (transform_orientation_coords,
+		// src/waveform_util.cpp:947-949); callers read them back afterwards
+		gwat_b200_source s;
+		if (gwat_b200::flatten(*parameters, s) && gwat_b200_transform_orientation_coords(generation_method.c_str(), 1, &s) == 0) {
+			parameters->incl_angle = s.incl_angle;
+			parameters->psi = s.psi;
+		}
+	}
+	return st;
 }
 
 template <>

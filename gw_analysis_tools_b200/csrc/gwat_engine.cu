@@ -39,6 +39,7 @@ namespace hosttab {  // the same generated tables for host-side use (detector ro
 #include "gwat_method.h"
 #include "gwat_repack.h"
 #include "gwat_setup_coop.h"
+#include "gwat_orient.h"
 
 using namespace gwat;
 
@@ -427,6 +428,7 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	repack_fisher_point(v, orig, fp.rp, sp);
 	Network net;
 	net.D = fp.nd;
+	net.horizon_mode = 0;
 	for (int d = 0; d < fp.nd; d++)
 		for (int j = 0; j < 13; j++) net.row[d][j] = fp.det_row[d][j];
 	WalkerCoef wc;
@@ -711,12 +713,18 @@ __global__ void __launch_bounds__(128) k_fisher_setup_sky(const gwat_b200_source
 		double v[GWAT_B200_MAX_DIM];
 		int logfac[GWAT_B200_MAX_DIM];
 		unpack_fisher(orig, fp.rp, v, logfac);
-		if (k == 0) scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
-		v[i] += (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
+		// The reference keeps the "eta at its boundary" rule of the 11-parameter set -- parameter 8 above 1/4 - eps gets a one-sided
+		// difference -- in this branch too (src/fisher.cpp:218-232, 303-316), where parameter 8 is the second modification: the
+		// +eps / +2 eps points stay at the value and the quotient loses its factor 2 (folded into `scale`, exact).
+		const bool one_sided = i == 8 && v[i] > .25 - epsilon;
+		if (k == 0) scale[(size_t)sidx * dim + i] = (logfac[i] ? v[i] : 1.0) * (one_sided ? 2.0 : 1.0);
+		const double step = (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
+		if (!(one_sided && step > 0)) v[i] += step;
 		repack_fisher_point(v, orig, fp.rp, sp);
 	}
 	Network net;
 	net.D = 1;
+	net.horizon_mode = 0;
 	for (int j = 0; j < 13; j++) net.row[0][j] = fp.det_row[0][j];
 	WalkerCoef wc;
 	walker_setup<Fam>(sp, net, device_tables(), fp.theory, wc, true);
@@ -1062,18 +1070,36 @@ int check_ready(gwat_b200_ctx *ctx, bool need_data)
 }
 
 template <class Fam>
-void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st)
+void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st, const Network &net)
 {
-	k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(nullptr, d_src, W, RepackPlan{}, ctx->net, theory, 0.0, 0.0,
+	k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(nullptr, d_src, W, RepackPlan{}, net, theory, 0.0, 0.0,
 	                                                                                                 ctx->d_coef, ctx->d_active);
 }
 
-int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st)
+// single_detector: the semantics of the reference's one-detector entry points (fourier_detector_response, calculate_snr), which
+// honour equatorial_orientation (incl_angle and psi derived from theta_l, phi_l: gwat_orient.h) and horizon_coord; the coherent
+// network response and the likelihoods read incl_angle / psi / RA / DEC as given, as create_coherent_GW_detection does.
+int setup_from_sources(gwat_b200_ctx *ctx, const MethodDesc &desc, int W, const gwat_b200_source *h_src, cudaStream_t st,
+                       bool single_detector = false)
 {
 	if (grow(ctx, ctx->d_src, ctx->cap_src, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
+	Network net = ctx->net;
+	std::vector<gwat_b200_source> oriented;
+	if (single_detector) {
+		net.horizon_mode = 1;
+		bool any = false;
+		for (int w = 0; w < W && !any; w++) any = h_src[w].equatorial_orientation != 0;
+		if (any) {
+			oriented.assign(h_src, h_src + W);
+			for (gwat_b200_source &s : oriented)
+				if (s.equatorial_orientation) transform_orientation_coords(s, desc.pv2 != 0);
+			h_src = oriented.data();
+		}
+	}
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, h_src, sizeof(gwat_b200_source) * W, cudaMemcpyHostToDevice, st));
-	GWAT_DISPATCH_FAMILY(desc, launch_setup_src<Fam>(ctx, W, ctx->d_src, desc.theory, st));
+	if (!oriented.empty()) CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (the staging vector is local)
+	GWAT_DISPATCH_FAMILY(desc, launch_setup_src<Fam>(ctx, W, ctx->d_src, desc.theory, st, net));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -1175,9 +1201,9 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 }
 
 // Sky-averaged pass: ctx->d_src[0..ns) -> ctx->d_fisher[ns][7][7] for the PSD of detector `det`.
+template <class Fam>
 int fisher_chunk_sky(gwat_b200_ctx *ctx, FisherPlan &fp, int ns, int chunk, int det, cudaStream_t st)
 {
-	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
 	const int L = ctx->L, dim = fp.rp.dimension;
 	const GridPtrs g = grid_ptrs(ctx);
 	const double *wq_fisher_all = ctx->d_net + 3 * (size_t)ctx->D * ctx->ld;
@@ -1239,6 +1265,15 @@ int gwat_b200_abi_version(void) { return GWAT_B200_ABI_VERSION; }
 void gwat_b200_source_init(gwat_b200_source *src)
 {
 	if (src) source_defaults(*src);
+}
+
+int gwat_b200_transform_orientation_coords(const char *generation_method, int n, gwat_b200_source *sources)
+{
+	MethodDesc desc;
+	if (!sources || n < 0) return GWAT_B200_ERR_ARG;
+	if (parse_method(generation_method, desc) != 0) return GWAT_B200_ERR_METHOD;
+	for (int i = 0; i < n; i++) transform_orientation_coords(sources[i], desc.pv2 != 0);
+	return GWAT_B200_OK;
 }
 
 int gwat_b200_cosmology_index(const char *name)
@@ -1466,7 +1501,8 @@ int gwat_b200_snr_batch(gwat_b200_ctx *ctx, const char *method, int W, const gwa
 		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	if (int rc = setup_from_sources(ctx, desc, W, sources, ctx->stream)) return rc;
+	// calculate_snr (src/waveform_util.cpp:290-344) is a one-detector routine: orientation / horizon conventions as fourier_detector_response
+	if (int rc = setup_from_sources(ctx, desc, W, sources, ctx->stream, ctx->D == 1)) return rc;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, (size_t)W)) return GWAT_B200_ERR_CUDA;
 	if (int rc = run_loglike(ctx, desc, W, ctx->d_out, ctx->stream, nullptr, nullptr, nullptr, true)) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(snr, ctx->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1536,6 +1572,7 @@ int gwat_b200_fourier_amplitude_phase_batch(gwat_b200_ctx *ctx, const char *meth
 	return GWAT_B200_OK;
 }
 
+// with_shift == 0 is the one-detector entry point (fourier_detector_response)
 static int response_common(gwat_b200_ctx *ctx, const char *method, int d0, int nd, int with_shift, int W,
                            const gwat_b200_source *sources, double *re, double *im)
 {
@@ -1545,7 +1582,7 @@ static int response_common(gwat_b200_ctx *ctx, const char *method, int d0, int n
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
-	if (int rc = setup_from_sources(ctx, desc, W, sources, st)) return rc;
+	if (int rc = setup_from_sources(ctx, desc, W, sources, st, with_shift == 0)) return rc;
 	const size_t n = (size_t)W * nd * ctx->L;
 	if (grow(ctx, ctx->d_out, ctx->cap_out, 2 * n)) return GWAT_B200_ERR_CUDA;
 	double *o = ctx->d_out;
@@ -1657,28 +1694,47 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 		all_sky = all_sky && sources[i].sky_average != 0;
 	}
 	if (any_sky) {
-		// sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): IMRPhenomD, 7 parameters, one detector's PSD
+		// sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): the IMRPhenomD carrier in the 7-parameter set, followed by
+		// the ppE betas (ppE_IMRPhenomD_*, and the theories mapped onto them) or the gIMR deviations; one detector's PSD
 		if (!all_sky) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: sky-averaged and pointed sources in one batch");
-		if (desc.family_id != FAM_D || desc.theory != THEORY_NONE || desc.mcmc || dimension != 7)
-			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers are built for IMRPhenomD, dimension 7");
+		const bool ppe = desc.ppe || desc.theory != THEORY_NONE, gimr = desc.gimr && !ppe;
+		int mods = 0;
+		if (ppe) mods = sources[0].Nmod;
+		else if (gimr) mods = sources[0].Nmod_phi + sources[0].Nmod_sigma + sources[0].Nmod_beta + sources[0].Nmod_alpha;
+		if (desc.pv2 || desc.mcmc)
+			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers exist for the IMRPhenomD family only (as in the reference)");
+		if (desc.nrt)
+			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED,
+			            "fisher_numerical_batch: the reference's sky-averaged NRT layout puts ln(tidal) on top of ln(eta) (src/fisher.cpp:2061-2078); not built");
+		if (mods < 0 || mods > GWAT_B200_MAX_MOD || dimension != 7 + mods)
+			return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: a sky-averaged Fisher has 7 parameters plus the sources' modifications");
 		if (detector_index < 0) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: a sky-averaged Fisher needs one detector's PSD");
 		FisherPlan fp;
 		std::memset(&fp, 0, sizeof(fp));
-		fp.rp.dimension = 7;
+		fp.rp.dimension = dimension;
 		fp.rp.sky = 1;
+		fp.rp.ppe = ppe;
+		fp.rp.gimr = gimr;
 		fp.npts = order == 4 ? 4 : 2;
-		fp.theory = THEORY_NONE;
+		fp.theory = desc.theory;
+		const int dd = dimension * dimension;
 		std::lock_guard<std::mutex> lock(ctx->mu);
 		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 		cudaStream_t st = ctx->stream;
-		const int chunk = fisher_chunk_size(ctx, S, 7, fp.npts + 1, 1, false);
-		if (int rc = fisher_reserve(ctx, chunk, 7, fp.npts + 1, 1, false)) return rc;
+		const int chunk = fisher_chunk_size(ctx, S, dimension, fp.npts + 1, 1, false);
+		if (int rc = fisher_reserve(ctx, chunk, dimension, fp.npts + 1, 1, false)) return rc;
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 		for (int s0 = 0; s0 < S; s0 += chunk) {
 			const int ns = std::min(chunk, S - s0);
 			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, sources + s0, sizeof(gwat_b200_source) * ns, cudaMemcpyHostToDevice, st));
-			if (int rc = fisher_chunk_sky(ctx, fp, ns, chunk, detector_index, st)) return rc;
-			CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * 49, ctx->d_fisher, sizeof(double) * ns * 49, cudaMemcpyDeviceToHost, st));
+			switch (desc.family_id) {
+			case FAM_D: if (int rc = fisher_chunk_sky<Family<BASE_D, PPE_NONE, false, false>>(ctx, fp, ns, chunk, detector_index, st)) return rc; break;
+			case FAM_D_PPE_INS: if (int rc = fisher_chunk_sky<Family<BASE_D, PPE_INSPIRAL, false, false>>(ctx, fp, ns, chunk, detector_index, st)) return rc; break;
+			GWAT_FULL_ONLY(case FAM_D_PPE_IMR: if (int rc = fisher_chunk_sky<Family<BASE_D, PPE_IMR, false, false>>(ctx, fp, ns, chunk, detector_index, st)) return rc; break;)
+			GWAT_FULL_ONLY(case FAM_D_GIMR: if (int rc = fisher_chunk_sky<Family<BASE_D, PPE_NONE, true, false>>(ctx, fp, ns, chunk, detector_index, st)) return rc; break;)
+			default: return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fisher: family not built");
+			}
+			CUDA_TRY(ctx, cudaMemcpyAsync(fisher + (size_t)s0 * dd, ctx->d_fisher, sizeof(double) * ns * dd, cudaMemcpyDeviceToHost, st));
 		}
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
 		CUDA_TRY(ctx, cudaStreamSynchronize(st));

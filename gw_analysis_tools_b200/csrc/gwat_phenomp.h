@@ -465,7 +465,7 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 		w.cfac = ci;
 		w.pfac = .5 * (1. + ci * ci);
 	}
-	detector_setup(net, src.RA, src.DEC, src.psi, src.gmst, w.det);
+	detector_setup_source(net, src, w.det);
 	for (int d = 0; d < net.D; d++) {
 		DetCoef &dc = w.det[d];
 		if (Fam::base == BASE_P) {
@@ -477,9 +477,10 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 		}
 	}
 	// options of the reference that are outside this path are refused loudly (NaN), never silently approximated:
-	// horizon/equatorial-orientation inputs, sky-averaged amplitudes, and the wall-clock-seeded tidal_love_error draw
-	// (sky-averaged amplitudes are accepted only from the sky-averaged Fisher path, which uses amplitude and phase alone)
-	if (src.horizon_coord || src.equatorial_orientation || (src.sky_average && !allow_sky_average) || (Fam::nrt && src.tidal_love_error))
+	// sky-averaged amplitudes and the wall-clock-seeded tidal_love_error draw
+	// (sky-averaged amplitudes are accepted only from the sky-averaged Fisher path, which uses amplitude and phase alone).
+	// equatorial_orientation / horizon_coord are handled where the reference handles them (gwat_orient.h) and ignored elsewhere.
+	if ((src.sky_average && !allow_sky_average) || (Fam::nrt && src.tidal_love_error))
 		w.d.A0 = NAN;
 	w.valid = 1;
 }

@@ -23,7 +23,7 @@ struct RepackPlan {
 	int gimr;           // last (phi+sigma+beta+alpha) entries are fractional deviations
 	int alpha_unit_fix; // dCS/EdGB: entry [base] is sqrt(alpha) in km -> alpha^2 in s^4 (src/mcmc_gw.cpp:2560-2565)
 	int mcmc;           // "MCMC_" parameterisation (sin DEC, cos iota, ln DL, ln Mc); else the physical one
-	int sky;            // sky-averaged IMRPhenomD set: ln A0, phic, tc, ln Mc, ln eta, chi_s, chi_a (src/fisher.cpp:40, 2015-2032)
+	int sky;            // sky-averaged IMRPhenomD set: ln A0, phic, tc, ln Mc, ln eta, chi_s, chi_a (src/fisher.cpp:40, 2015-2032), then the modifications
 	gwat_b200_mod mod;
 };
 
@@ -204,6 +204,22 @@ GWAT_HD double a0_dl_conversion(double chirpmass_sec, double other, bool sky_ave
 	return pref * chirpmass_sec * chirpmass_sec / other * sm::pow(GWAT_PI * chirpmass_sec, -7. / 6);
 }
 
+// the modification parameters at the end of the vector (src/fisher.cpp:2082-2160)
+GWAT_HD void unpack_fisher_mods(const gwat_b200_source &in, const RepackPlan &plan, double *v)
+{
+	const int dim = plan.dimension;
+	if (plan.ppe) {
+		const int base = dim - in.Nmod;
+		for (int i = 0; i < in.Nmod; i++) v[base + i] = in.betappe[i];
+	} else if (plan.gimr) {
+		int at = dim - (in.Nmod_phi + in.Nmod_sigma + in.Nmod_beta + in.Nmod_alpha);
+		for (int i = 0; i < in.Nmod_phi; i++) v[at++] = in.delta_phi[i];
+		for (int i = 0; i < in.Nmod_sigma; i++) v[at++] = in.delta_sigma[i];
+		for (int i = 0; i < in.Nmod_beta; i++) v[at++] = in.delta_beta[i];
+		for (int i = 0; i < in.Nmod_alpha; i++) v[at++] = in.delta_alpha[i];
+	}
+}
+
 GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, double *v, int *logfac)
 {
 	const int dim = plan.dimension;
@@ -217,6 +233,7 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 		v[4] = eta_from(in.mass1, in.mass2);
 		v[5] = (in.spin1[2] + in.spin2[2]) / 2.;
 		v[6] = (in.spin1[2] - in.spin2[2]) / 2.;
+		unpack_fisher_mods(in, plan, v);  // ppE betas / gIMR deviations behind the seven (:2082-2160)
 		return;
 	}
 	v[0] = in.RA;
@@ -268,16 +285,7 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 			v[12] = sm::log(in.tidal2);
 		}
 	}
-	if (plan.ppe) {
-		const int base = dim - in.Nmod;
-		for (int i = 0; i < in.Nmod; i++) v[base + i] = in.betappe[i];
-	} else if (plan.gimr) {
-		int at = dim - (in.Nmod_phi + in.Nmod_sigma + in.Nmod_beta + in.Nmod_alpha);
-		for (int i = 0; i < in.Nmod_phi; i++) v[at++] = in.delta_phi[i];
-		for (int i = 0; i < in.Nmod_sigma; i++) v[at++] = in.delta_sigma[i];
-		for (int i = 0; i < in.Nmod_beta; i++) v[at++] = in.delta_beta[i];
-		for (int i = 0; i < in.Nmod_alpha; i++) v[at++] = in.delta_alpha[i];
-	}
+	unpack_fisher_mods(in, plan, v);
 }
 
 // One stencil point: repack_non_parameter_options + repack_parameters (src/fisher.cpp:2513-2572, 2167-2507) starting
@@ -323,6 +331,7 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		s.phiRef = v[1];
 		s.spin1[2] = v[5] + v[6];
 		s.spin2[2] = v[5] - v[6];
+		repack_tails(v, plan, s);  // (never with plan.nrt: the reference's sky-averaged NRT layout collides with ln eta, refused upstream)
 		return;
 	}
 	s.RA = v[0];

@@ -121,6 +121,7 @@ GWAT_HD double dtoa_between(const double *loc1, const double *loc2, double ra, d
 // The detector network as the kernels see it: rows of the generated detector table (tensor, location, factor).
 struct Network {
 	int D;
+	int horizon_mode;  // 1: a source with horizon_coord set gets the horizon-frame patterns (the single-detector response path only)
 	double row[GWAT_B200_MAX_DETECTORS][13];
 };
 
@@ -133,6 +134,31 @@ GWAT_HD void detector_setup(const Network &net, double ra, double dec, double ps
 		// tc = -DTOA; tc *= 2*M_PI;   (src/waveform_util.cpp:173-174)
 		out[d].tshift = (-dtoa) * (2 * GWAT_PI);
 	}
+}
+
+// Antenna patterns in the detector's horizon frame   (right_interferometer; the geometric factor as fourier_detector_response_horizon applies it)
+GWAT_HD void horizon_patterns(double theta, double phi, double psi, double geometric_factor, double &Fplus, double &Fcross)
+{
+	const double ct = cos(theta);
+	const double fp = (1. / 2) * (1 + ct * ct) * cos(2. * phi);
+	const double fc = ct * sin(2. * phi);
+	const double c2psi = cos(2. * psi), s2psi = sin(2. * psi);
+	Fplus = (fp * c2psi - fc * s2psi) * geometric_factor;
+	Fcross = (fp * s2psi + fc * c2psi) * geometric_factor;
+}
+
+// The detector constants of one source: equatorial sky position, or -- on the single-detector response path, for a source with
+// horizon_coord set -- the detector's own frame (fourier_detector_response_horizon, src/waveform_util.cpp:684-720: no time shift).
+GWAT_HD void detector_setup_source(const Network &net, const gwat_b200_source &src, DetCoef *out)
+{
+	if (net.horizon_mode && src.horizon_coord) {
+		for (int d = 0; d < net.D; d++) {
+			horizon_patterns(src.theta, src.phi, src.psi, net.row[d][12], out[d].Fplus, out[d].Fcross);
+			out[d].tshift = 0.0;
+		}
+		return;
+	}
+	detector_setup(net, src.RA, src.DEC, src.psi, src.gmst, out);
 }
 
 // ---- IMRPhenomD carrier setup ----------------------------------------------------------------------------------------

@@ -78,7 +78,7 @@ GWAT_HD void setup_step1(int role, const gwat_b200_source &s, const Network &net
 		r.fRD = q.fRD;
 		r.fdamp = q.fdamp;
 	} else if (role == ROLE_DETECTOR) {
-		detector_setup(net, s.RA, s.DEC, s.psi, s.gmst, r.w.det);
+		detector_setup_source(net, s, r.w.det);
 		if (!kP) {
 			const double ci = sm::cos(s.incl_angle);
 			r.w.cfac = ci;
@@ -89,7 +89,7 @@ GWAT_HD void setup_step1(int role, const gwat_b200_source &s, const Network &net
 		}
 		r.w.pad_ = 0;
 		// options of the reference that are outside this path are refused loudly (NaN), never silently approximated (walker_setup)
-		r.refused = (s.horizon_coord || s.equatorial_orientation || s.sky_average || (Fam::nrt && s.tidal_love_error)) ? 1 : 0;
+		r.refused = (s.sky_average || (Fam::nrt && s.tidal_love_error)) ? 1 : 0;
 	} else {
 		populate_source(s, q);
 		phenompv2_param_transform(q, (s.chip + 1) > 1e-10);

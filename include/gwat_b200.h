@@ -33,7 +33,7 @@ typedef enum gwat_b200_status {
 	GWAT_B200_ERR_METHOD = -2,    /* generation_method string not supported by this library */
 	GWAT_B200_ERR_CUDA = -3,      /* CUDA runtime error (message in gwat_b200_last_error) */
 	GWAT_B200_ERR_STATE = -4,     /* network/grid not set, or context built for another shape */
-	GWAT_B200_ERR_UNSUPPORTED = -5 /* valid GWAT option that is outside this library's path (LISA, horizon coords, autodiff ...) */
+	GWAT_B200_ERR_UNSUPPORTED = -5 /* valid GWAT option that is outside this library's path (LISA, autodiff ...) */
 } gwat_b200_status;
 
 /*
@@ -49,8 +49,8 @@ typedef struct gwat_b200_source {
 	double tc, phiRef, f_ref;
 	double psi, incl_angle;
 	double RA, DEC, gmst;
-	double theta, phi;               /* horizon coordinates (accepted, only used when horizon_coord != 0 -> unsupported) */
-	double theta_l, phi_l;           /* equatorial orientation of L (equatorial_orientation != 0 -> unsupported) */
+	double theta, phi;               /* sky position in the detector's horizon frame, read when horizon_coord != 0 by the one-detector response */
+	double theta_l, phi_l;           /* equatorial direction of L, read when equatorial_orientation != 0 by the one-detector entry points */
 	double tidal1, tidal2, tidal_s, tidal_a, tidal_weighted, delta_tidal_weighted;
 	double diss_tidal1, diss_tidal2, diss_tidal_s, diss_tidal_a, diss_tidal_weighted;
 	double chip, phip;               /* reduced PhenomPv2 parameterisation, used when chip != -1 */
@@ -103,6 +103,11 @@ int gwat_b200_abi_version(void);
 /* Fill a source / modification record with the reference's member defaults (include/gwat/util.h:125-285,
  * include/gwat/mcmc_gw.h:52-67). */
 void gwat_b200_source_init(gwat_b200_source *src);
+/* transform_orientation_coords (src/waveform_util.cpp:1535-1595) for terrestrial detectors, in place: incl_angle and psi of every
+ * source from the equatorial direction of L (theta_l, phi_l); for IMRPhenomPv2 methods psi follows the direction of J.  The
+ * one-detector entry points below apply it themselves to sources with equatorial_orientation set (on a copy: the reference
+ * overwrites the caller's object); it is exported for callers that want the derived angles. */
+int gwat_b200_transform_orientation_coords(const char *generation_method, int n, gwat_b200_source *sources);
 /* Index of a cosmology name as Z_from_DL reads it (case-insensitive, src/util.cpp:356-365); -1 for a name the reference does not know. */
 int gwat_b200_cosmology_index(const char *name);
 void gwat_b200_mod_init(gwat_b200_mod *mod);
@@ -266,8 +271,12 @@ int gwat_b200_coherent_response_batch(gwat_b200_ctx *ctx, const char *generation
                                       const gwat_b200_source *sources, double *resp_re, double *resp_im);
 
 /*
- * W evaluations of fourier_detector_response<double> (src/waveform_util.cpp:1070-1088, equatorial branch :936-985) for
- * ONE named detector, no time-of-arrival shift.  resp_re/im shape [W*L].
+ * W evaluations of fourier_detector_response<double> (src/waveform_util.cpp:1070-1088) for ONE named detector, no
+ * time-of-arrival shift.  resp_re/im shape [W*L].  Per source, as the reference's wrapper does: horizon_coord != 0 -> the
+ * detector-frame patterns of (theta, phi, psi) (fourier_detector_response_horizon, :684-720); else the equatorial branch
+ * (:936-985), where equatorial_orientation != 0 first derives incl_angle and psi from (theta_l, phi_l)
+ * (transform_orientation_coords).  The coherent response above and the likelihoods read incl_angle / psi / RA / DEC as given,
+ * as create_coherent_GW_detection does.
  */
 int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *generation_method, const char *detector,
                                               int W, const gwat_b200_source *sources, double *resp_re,

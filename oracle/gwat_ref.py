@@ -243,3 +243,10 @@ def pack_local_mod_structure(min_dim, max_dim, status, waveform_extended, full_m
     lib().oracle_ref_pack_local_mod_structure(int(min_dim), int(max_dim), status.ctypes.data_as(ip), waveform_extended.encode(),
                                               C.byref(full_mod), counts.ctypes.data_as(ip), idx.ctypes.data_as(ip))
     return counts, idx
+
+
+def transform_orientation_coords(method, detector, src):
+    """transform_orientation_coords (src/waveform_util.cpp:1535-1595): the (incl_angle, psi) it derives from (theta_l, phi_l)."""
+    incl, psi = C.c_double(), C.c_double()
+    lib().oracle_ref_transform_orientation_coords(method.encode(), detector.encode(), C.byref(src), C.byref(incl), C.byref(psi))
+    return incl.value, psi.value

@@ -580,6 +580,17 @@ double oracle_ref_calculate_snr(const char *curve, const char *detector, const c
 	                     std::string(integration_method), const_cast<double *>(weights), log10F != 0);
 }
 
+// transform_orientation_coords (src/waveform_util.cpp:1535-1595) for a named (terrestrial) detector: incl_angle and psi it derives
+int oracle_ref_transform_orientation_coords(const char *method, const char *detector, const gwat_b200_source *src, double *incl_angle, double *psi)
+{
+	ParamBox b;
+	to_gen_params(*src, b);
+	transform_orientation_coords(&b.gp, std::string(method), std::string(detector));
+	*incl_angle = b.gp.incl_angle;
+	*psi = b.gp.psi;
+	return 0;
+}
+
 // match (src/waveform_util.cpp:41-89): overlap maximised over a relative time shift (FFTW_BACKWARD = the stand-in's DFT here).
 double oracle_ref_match(const double *a_re, const double *a_im, const double *b_re, const double *b_im, const double *psd, const double *f,
                         int L)

@@ -14,6 +14,7 @@
 #include "../gw_analysis_tools_b200/csrc/gwat_method.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_repack.h"
 #include "../gw_analysis_tools_b200/csrc/gwat_setup_coop.h"
+#include "../gw_analysis_tools_b200/csrc/gwat_orient.h"
 
 using namespace gwat;
 
@@ -68,6 +69,7 @@ void response_t(int theory, const gwat_b200_source *src, const Network &net, con
 int make_network(int D, const char *const *dets, Network &net)
 {
 	net.D = D;
+	net.horizon_mode = 0;
 	for (int d = 0; d < D; d++) {
 		const int id = detector_index(dets[d]);
 		if (id < 0) return -1;
@@ -101,7 +103,7 @@ int hh_fourier_waveform(const char *method, const gwat_b200_source *src, const d
 {
 	MethodDesc desc;
 	if (parse_method(method, desc) != 0) return -2;
-	Network net;
+	Network net{};
 	net.D = 0;
 	const Grid g = make_grid(f, L);
 	DISPATCH_FAMILY(desc, waveform_t<Fam>(desc.theory, src, net, g, hp_re, hp_im, hc_re, hc_im));
@@ -113,7 +115,7 @@ int hh_coherent_response(const char *method, const gwat_b200_source *src, int D,
 {
 	MethodDesc desc;
 	if (parse_method(method, desc) != 0) return -2;
-	Network net;
+	Network net{};
 	if (make_network(D, dets, net) != 0) return -1;
 	const Grid g = make_grid(f, L);
 	DISPATCH_FAMILY(desc, response_t<Fam>(desc.theory, src, net, g, with_shift != 0, re, im));
@@ -125,7 +127,7 @@ int hh_phenomd_setup_probe(const gwat_b200_source *src, double *out)
 {
 	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
 	const int theory = 0;
-	Network net;
+	Network net{};
 	net.D = 0;
 	WalkerCoef w;
 	walker_setup<Fam>(*src, net, host_tables(), theory, w);
@@ -140,7 +142,7 @@ extern "C" int hh_debug_dcoef(const gwat_b200_source *src, double *out)
 {
 	typedef Family<BASE_D, PPE_NONE, false, false> Fam;
 	const int theory = 0;
-	Network net;
+	Network net{};
 	net.D = 0;
 	WalkerCoef w;
 	walker_setup<Fam>(*src, net, host_tables(), theory, w);
@@ -180,12 +182,21 @@ extern "C" int hh_setup_coop(const char *method, const gwat_b200_source *src, in
 {
 	MethodDesc desc;
 	if (parse_method(method, desc) != 0) return -1;
-	Network net;
+	Network net{};
 	if (make_network(D, dets, net) != 0) return -3;
 	int n = 0;
 	DISPATCH_FAMILY(desc, n = setup_coop_t<Fam>(desc.theory, src, net, out_coop, out_seq));
 	return n;
 }
+// transform_orientation_coords of gwat_orient.h, in place
+extern "C" int hh_transform_orientation(const char *method, gwat_b200_source *src)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0) return -1;
+	transform_orientation_coords(*src, desc.pv2 != 0);
+	return 0;
+}
+
 // which words of WalkerCoef each family defines (the others stay poisoned in both flows): offsets for the test
 extern "C" void hh_walkercoef_layout(int *out)
 {
@@ -221,12 +232,12 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 	const double eps = 1e-8;
 	if (src->sky_average) {
 		// sky-averaged branch (src/fisher.cpp:183-338): amplitude / phase derivatives in the 7-parameter set
-		if (Fam::base != BASE_D || Fam::nrt || dim != 7) return -5;
+		if (Fam::base != BASE_D || Fam::nrt) return -5;
 		plan.sky = 1;
 		double v0s[GWAT_B200_MAX_DIM];
 		int logf_[GWAT_B200_MAX_DIM];
 		unpack_fisher(*src, plan, v0s, logf_);
-		Network net;
+		Network net{};
 		net.D = 1;
 		std::memcpy(net.row[0], det_row, sizeof(double) * 13);
 		WalkerCoef w0;
@@ -237,12 +248,13 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 			for (int k = 0; k < npts; k++) {
 				double v[GWAT_B200_MAX_DIM];
 				for (int j = 0; j < dim; j++) v[j] = v0s[j];
-				v[i] = v0s[i] + ((k == 0) ? eps : (k == 1) ? -eps : (k == 2) ? 2 * eps : -2 * eps);
+				const double step = (k == 0) ? eps : (k == 1) ? -eps : (k == 2) ? 2 * eps : -2 * eps;
+				if (!(step > 0 && i == 8 && v0s[8] > .25 - eps)) v[i] = v0s[i] + step;  // (the one-sided rule of parameter 8, :218-232)
 				gwat_b200_source sp;
 				repack_fisher_point(v, *src, plan, sp);
 				walker_setup<Fam>(sp, net, host_tables(), theory, wk[k], true);
 			}
-			const double sc = logf_[i] ? v0s[i] : 1.0;
+			const double sc = (logf_[i] ? v0s[i] : 1.0) * ((i == 8 && v0s[8] > .25 - eps) ? 2.0 : 1.0);
 			for (size_t b = 0; b < L; b++) {
 				double a[4], ph[4], a0, p0;
 				amplitude_phase_bin<Fam>(w0, g.f[b], g.hi[b], g.lo[b], g.lg[b], a0, p0);
@@ -282,7 +294,7 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 				if (k < 2) tshift = (-2 * GWAT_PI) * dtoa;
 				else sp.tc -= dtoa;
 			}
-			Network net;
+			Network net{};
 			net.D = 1;
 			std::memcpy(net.row[0], det_row, sizeof(double) * 13);
 			WalkerCoef w;
@@ -374,7 +386,7 @@ extern "C" int hh_loglike(const char *method, int W, const gwat_b200_source *src
 {
 	MethodDesc desc;
 	if (parse_method(method, desc) != 0) return -2;
-	Network net;
+	Network net{};
 	if (make_network(D, dets, net) != 0) return -1;
 	if (D != 2 && D != 3) return -3;
 	const Grid g = make_grid(f, L);

@@ -11,6 +11,7 @@ import os
 import numpy as np
 import pytest
 
+import fisher_noise
 from gw_analysis_tools_b200 import abi, engine
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -79,9 +80,83 @@ def test_sky_averaged_fisher_argument_errors(ctx):
     ctx.set_network(["Hanford"], f, psd[None, :])
     pointed = abi.source_defaults(mass1=30., mass2=20., Luminosity_Distance=400., f_ref=20.0)
     for kwargs, code in ((dict(method="IMRPhenomD", sources=srcs + [pointed], dimension=7, detector_index=0), abi.ERR_ARG),
-                         (dict(method="IMRPhenomD", sources=srcs, dimension=11, detector_index=0), abi.ERR_UNSUPPORTED),
+                         (dict(method="IMRPhenomD", sources=srcs, dimension=11, detector_index=0), abi.ERR_ARG),
                          (dict(method="IMRPhenomPv2", sources=srcs, dimension=7, detector_index=0), abi.ERR_UNSUPPORTED),
                          (dict(method="IMRPhenomD", sources=srcs, dimension=7, detector_index=-1), abi.ERR_ARG)):
         with pytest.raises(engine.GwatB200Error) as e:
             ctx.fisher_numerical_batch(kwargs["method"], kwargs["sources"], kwargs["dimension"], order=4, detector_index=kwargs["detector_index"])
         assert e.value.code == code
+
+
+# ---- the modified families behind the seven parameters (ppE, the theories mapped onto ppE, gIMR) --------------
+def mod_cases():
+    f, psd, srcs = setup_case()
+    out = []
+    for method, kw in (("ppE_IMRPhenomD_Inspiral", dict(Nmod=2, bppe=[-3.0, 1.0], betappe=[0.02, 0.3])),  # (beta_2 > 1/4 - eps: the one-sided rule)
+                       ("ppE_IMRPhenomD_IMR", dict(Nmod=1, bppe=[-1.0], betappe=[0.01])),
+                       ("dCS_IMRPhenomD", dict(Nmod=1, bppe=[-1.0], betappe=[1e-20])),
+                       ("gIMRPhenomD", dict(Nmod_phi=1, phii=[4], delta_phi=[0.05], Nmod_beta=1, betai=[2], delta_beta=[0.02]))):
+        ss = []
+        for s in srcs[:3]:
+            t = abi.Source()
+            C.memmove(C.addressof(t), C.addressof(s), C.sizeof(s))
+            for k, v in kw.items():
+                if isinstance(v, list):
+                    for i, x in enumerate(v):
+                        getattr(t, k)[i] = x
+                else:
+                    setattr(t, k, v)
+            ss.append(t)
+        mods = kw.get("Nmod", 0) + kw.get("Nmod_phi", 0) + kw.get("Nmod_beta", 0)
+        out.append((method, 7 + mods, ss))
+    return f, psd, out
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_sky_averaged_modified_families_math_vs_reference(oracle, order):
+    hh = C.CDLL(os.path.join(ROOT, "tests", "_build", "libgwat_host_harness.so"))
+    f, psd, cs = mod_cases()
+    for method, dim, srcs in cs:
+        ref = oracle.fisher_numerical_batch(method, srcs, ["Hanford"], f, psd[None, :], dim, order=order, detector_index=0)
+        got = np.zeros_like(ref)
+        for i, s in enumerate(srcs):
+            assert hh.hh_fisher_numerical(method.encode(), b"Hanford", b"Hanford", dim, order, C.byref(s), f.ctypes.data_as(_dp), f.size,
+                                          psd.ctypes.data_as(_dp), got[i].ctypes.data_as(_dp)) == 0, method
+        if method == "dCS_IMRPhenomD":
+            # ln A0 +- 1e-8 makes the luminosity distance negative (A0 ~ 1e-21), and the theory mapping takes its redshift: the reference's
+            # own matrix is NaN in that row and column.  Same pattern here; the finite block agrees.
+            assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(ref[:, 0, :]).all() and np.isfinite(ref[:, 1:, 1:]).all()
+            ref, got = ref[:, 1:, 1:], got[:, 1:, 1:]
+        assert np.all(np.isfinite(ref)), method
+        # yardstick: the reference against itself on inputs moved by parts in 1e14 (tests/fisher_noise.py)
+        floor = fisher_noise.reference_self_difference(oracle, method, srcs, ["Hanford"], f, psd[None, :], dim, order, detector_index=0)
+        err = normalised(got, ref).reshape(len(srcs), -1).max(axis=1)
+        assert np.all(err <= np.maximum(NORM_TOL, fisher_noise.FACTOR * floor)), (method, err, floor)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [2, 4])
+def test_sky_averaged_modified_families_vs_reference(ctx, oracle, order):
+    f, psd, cs = mod_cases()
+    ctx.set_network(["Hanford"], f, psd[None, :])
+    for method, dim, srcs in cs:
+        ref = oracle.fisher_numerical_batch(method, srcs, ["Hanford"], f, psd[None, :], dim, order=order, detector_index=0)
+        got = ctx.fisher_numerical_batch(method, srcs, dim, order=order, detector_index=0)
+        assert got.shape == ref.shape, method
+        if method == "dCS_IMRPhenomD":
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            ref, got = ref[:, 1:, 1:], got[:, 1:, 1:]
+        assert np.all(np.isfinite(got)), method
+        floor = fisher_noise.reference_self_difference(oracle, method, srcs, ["Hanford"], f, psd[None, :], dim, order, detector_index=0)
+        err = normalised(got, ref).reshape(len(srcs), -1).max(axis=1)
+        assert np.all(err <= np.maximum(NORM_TOL_GPU, fisher_noise.FACTOR * floor)), (method, err, floor)
+        assert np.median(normalised(got, ref)) <= 1e-5, method
+
+
+@pytest.mark.gpu
+def test_sky_averaged_nrt_is_refused_with_the_reason(ctx):
+    f, psd, srcs = setup_case()
+    ctx.set_network(["Hanford"], f, psd[None, :])
+    with pytest.raises(engine.GwatB200Error) as e:
+        ctx.fisher_numerical_batch("IMRPhenomD_NRT", srcs, 8, order=4, detector_index=0)
+    assert e.value.code == abi.ERR_UNSUPPORTED and "ln(eta)" in str(e.value)

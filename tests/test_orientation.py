@@ -1,0 +1,106 @@
+"""equatorial_orientation and horizon_coord: the one-detector entry points honour them as the reference's
+fourier_detector_response / calculate_snr do (gwat_orient.h), the coherent response and the likelihoods read incl_angle, psi, RA,
+DEC as given, as create_coherent_GW_detection_reuse_WF does."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from gw_analysis_tools_b200 import abi, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def hh():
+    return C.CDLL(os.path.join(ROOT, "tests", "_build", "libgwat_host_harness.so"))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "waveforms_v1.npz"))
+
+
+def _sources(gold, name, n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        s = cases.source_from_bytes(gold[name + "/src"])
+        s.equatorial_orientation = 1
+        s.theta_l = rng.uniform(0.2, np.pi - 0.2)
+        s.phi_l = rng.uniform(0, 2 * np.pi)
+        s.RA = rng.uniform(0, 2 * np.pi)
+        s.DEC = rng.uniform(-1.2, 1.2)
+        s.incl_angle = 9.0  # garbage on purpose: the transform must replace both
+        s.psi = 9.0
+        if name.startswith("P_"):
+            s.chip = rng.uniform(0.05, 0.8)  # PhenomPv2_JSF_from_params reads the reduced parameters
+            s.phip = rng.uniform(0, 2 * np.pi)
+        out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("name,method", [("D_bbh", "IMRPhenomD"), ("P_full", "IMRPhenomPv2"), ("NRT_love", "IMRPhenomD_NRT")])
+def test_transform_orientation_coords_vs_reference(hh, oracle, gold, name, method):
+    for s in _sources(gold, name, 16, 3):
+        incl_ref, psi_ref = oracle.transform_orientation_coords(method, "Hanford", s)
+        t = abi.Source()
+        C.memmove(C.addressof(t), C.addressof(s), C.sizeof(s))
+        assert hh.hh_transform_orientation(method.encode(), C.byref(t)) == 0
+        assert abs(t.incl_angle - incl_ref) <= 1e-13 * max(1.0, abs(incl_ref))
+        assert abs(t.psi - psi_ref) <= 1e-12 * max(1.0, abs(psi_ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,method", [("D_bbh", "IMRPhenomD"), ("P_full", "IMRPhenomPv2")])
+def test_one_detector_response_with_equatorial_orientation(ctx, oracle, gold, name, method):
+    gspec = [c for c in cases.CASES if c[0] == name][0][3]
+    f = cases.grid(gspec)
+    ctx.set_network(["Hanford", "Virgo"], f, np.tile(workloads.aligo_analytic_psd(f), (2, 1)))
+    srcs = _sources(gold, name, 6, 11)
+    got = ctx.fourier_detector_response_batch(method, "Virgo", srcs)
+    for k, s in enumerate(srcs):
+        ref = oracle.fourier_detector_response(method, "Virgo", s, f)
+        assert np.abs(got[k] - ref).max() <= 1e-10 * np.abs(ref).max(), k
+    # the coherent response does not look at the flag: garbage incl_angle / psi are used as given, as in the reference
+    coh = ctx.coherent_response_batch(method, srcs[:2])
+    for k in range(2):
+        ref = oracle.coherent_response(method, srcs[k], ["Hanford", "Virgo"], f)
+        assert np.abs(coh[k] - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_one_detector_response_in_horizon_coordinates(ctx, oracle, gold):
+    name, method = "D_bbh", "IMRPhenomD"
+    gspec = [c for c in cases.CASES if c[0] == name][0][3]
+    f = cases.grid(gspec)
+    ctx.set_network(["Livingston", "ET1"], f, np.tile(workloads.aligo_analytic_psd(f), (2, 1)))
+    rng = np.random.default_rng(5)
+    srcs = []
+    for _ in range(4):
+        s = cases.source_from_bytes(gold[name + "/src"])
+        s.horizon_coord = 1
+        s.theta, s.phi, s.psi = rng.uniform(0.1, 3.0), rng.uniform(0, 6.28), rng.uniform(0, 3.14)
+        srcs.append(s)
+    srcs.append(cases.source_from_bytes(gold[name + "/src"]))  # a batch may mix both conventions
+    for det in ("Livingston", "ET1"):
+        got = ctx.fourier_detector_response_batch(method, det, srcs)
+        for k, s in enumerate(srcs):
+            ref = oracle.fourier_detector_response(method, det, s, f)
+            assert np.abs(got[k] - ref).max() <= 1e-10 * np.abs(ref).max(), (det, k)
+
+
+@pytest.mark.gpu
+def test_snr_with_equatorial_orientation(ctx, oracle, gold):
+    name, method = "D_bbh", "IMRPhenomD"
+    f = cases.grid([c for c in cases.CASES if c[0] == name][0][3])
+    psd = oracle.populate_noise(f, "aLIGO_analytic") ** 2
+    ctx.set_network(["Hanford"], f, psd[None, :])
+    srcs = _sources(gold, name, 4, 21)
+    got = ctx.snr_batch(method, srcs)
+    for k, s in enumerate(srcs):
+        ref = oracle.calculate_snr("aLIGO_analytic", "Hanford", method, s, f)
+        assert abs(got[k] - ref) <= 1e-9 * ref, k
