@@ -143,6 +143,25 @@ int gwat_b200_sampler_cold(gwat_b200_sampler *s, long long first_step, int n, do
 double gwat_b200_sampler_last_ms(const gwat_b200_sampler *s);
 long long gwat_b200_sampler_last_launches(const gwat_b200_sampler *s);
 
+/*
+ * Chain output (host code, csrc/gwat_chain_io.cpp): the data dump and the thinned, flattened sample file of the reference's
+ * mcmc_sampler_output (create_data_dump src/mcmc_io_util.cpp:643-990, write_flat_thin_output :555-642, count_indep_samples :521-552)
+ * with the same dataset paths, shapes and thinning rule.  The reference writes HDF5; HDF5 is not available where this library is
+ * built, so the datasets go into a flat self-describing container (layout at the top of gwat_chain_io.cpp: magic, then per record
+ * the HDF5-style path, dtype 0 = float64 / 1 = int32, rank, dims, row-major payload).
+ *   positions [n_chains][steps][dimension]; logl_logp [n_chains][steps][2] or NULL; trim_lengths [n_chains] or NULL;
+ *   ac_values [n_cold][dimension] autocorrelation lengths (NULL: dataset omitted; the autocorrelation tools themselves are outside
+ *   this path).
+ */
+typedef struct gwat_b200_dump gwat_b200_dump;
+int gwat_b200_dump_create(const char *path, gwat_b200_dump **out);
+int gwat_b200_dump_write(gwat_b200_dump *d, const char *dataset_path, int dtype, int rank, const long long *dims, const void *data);
+int gwat_b200_dump_close(gwat_b200_dump *d);
+int gwat_b200_write_data_dump(const char *path, int n_chains, int dimension, long long steps, const int *chain_ids, const double *temperatures,
+                              const double *positions, const double *logl_logp, const int *trim_lengths, int n_cold, const int *ac_values);
+int gwat_b200_write_flat_thin_output(const char *path, int n_cold, int dimension, long long steps, const double *positions,
+                                     const int *trim_lengths, const int *ac_values, long long *n_rows);
+
 /* Building blocks, exposed for tests and for callers that keep their own sampler loop:
  * log prior of W sampling vectors (host arrays) with the standard prior of the method's family */
 int gwat_b200_log_prior_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension, int W,
