@@ -20,6 +20,8 @@ EXPORTS = [
     "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_sampler_uniform",
     "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
     "gwat_b200_nccl_unique_id", "gwat_b200_sampler_attach_ranks", "gwat_b200_sampler_last_swap_ms", "gwat_b200_sampler_last_sweeps",
+    # chain output (bound in chain_io.py)
+    "gwat_b200_dump_create", "gwat_b200_dump_write", "gwat_b200_dump_close", "gwat_b200_write_data_dump", "gwat_b200_write_flat_thin_output",
 ]
 NCCL_UNIQUE_ID_BYTES = 128
 
