@@ -1182,6 +1182,110 @@ int gwat_b200_sampler_cold(gwat_b200_sampler *s, long long first_step, int n, do
 	return GWAT_B200_OK;
 }
 
+// ---- dynamic temperature allocation (arXiv:1501.05823) --------------------------------------------------------------------------
+// update_temperatures_full_ensemble, linear-swapping branch (src/mcmc_sampler_internals.cpp:3371-3413): chains at T = 1 and at the
+// hottest temperature of an ensemble stay put, the others move so that neighbouring swap acceptances even out.
+//   A[i] = 1 / 0: the last swap attempt between chains i - 1 and i was accepted / rejected (chain_swap, :1095-1112); A[0] is never written.
+int gwat_b200_update_temperatures(int chain_N, double *chain_temps, const double *A, int t0, int nu, int t)
+{
+	if (chain_N < 1 || !chain_temps || !A || nu == 0) return GWAT_B200_ERR_ARG;
+	const double thresh = 1e-10;  // DOUBLE_COMP_THRESH (include/gwat/util.h)
+	std::vector<double> old_temps(chain_N, 0.0);
+	double max_temp = 0;
+	int ensemble_chain_number = 0;
+	bool search = true;
+	for (int i = 0; i < chain_N - 1; i++) {
+		old_temps[i] = chain_temps[i];
+		if (i != 0 && std::fabs(chain_temps[i] - 1) < thresh) {
+			max_temp = chain_temps[i - 1];
+			if (search) {
+				ensemble_chain_number = i;
+				search = false;
+			}
+		}
+	}
+	if (max_temp < thresh) {
+		max_temp = chain_temps[chain_N - 1];
+		ensemble_chain_number = chain_N;
+	}
+	(void)ensemble_chain_number;  // (only read by a branch the loop bounds below never reach, :3405-3408)
+	const double kappa = (1. / nu) * (double)(t0) / (t + t0);  // PT_dynamical_timescale (:3224-3230)
+	for (int i = 1; i < chain_N - 1; i++) {
+		if (!(std::fabs(chain_temps[i] - 1) < thresh || std::fabs(chain_temps[i] - max_temp) < thresh)) {
+			const double power = kappa * (A[i] - A[i + 1]);
+			chain_temps[i] = chain_temps[i - 1] + (old_temps[i] - old_temps[i - 1]) * std::exp(power);
+		}
+	}
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_set_temperatures(gwat_b200_sampler *s, const double *chain_temps)
+{
+	if (!s || !chain_temps) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	if (s->comm) return gwat_internal::set_error(ctx, GWAT_B200_ERR_UNSUPPORTED, "sampler_set_temperatures: not for a sampler sharded over ranks");
+	const int C = s->k.C;
+	for (int c = 0; c < C; c++)
+		if ((chain_temps[c] == 1.0) != (s->h_temps[c] == 1.0) || !(chain_temps[c] >= 1.0))
+			return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "sampler_set_temperatures: the T = 1 chains must stay the T = 1 chains, and T >= 1");
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	SCUDA(ctx, cudaMemcpy(s->d.temps, chain_temps, sizeof(double) * C, cudaMemcpyHostToDevice));
+	s->h_temps.assign(chain_temps, chain_temps + C);
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_temperatures(gwat_b200_sampler *s, double *chain_temps)
+{
+	if (!s || !chain_temps) return GWAT_B200_ERR_ARG;
+	std::memcpy(chain_temps, s->h_temps.data(), sizeof(double) * s->h_temps.size());
+	return GWAT_B200_OK;
+}
+
+int gwat_b200_sampler_last_swap_accepts(gwat_b200_sampler *s, int *accepted)
+{
+	if (!s || !accepted) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	if (s->comm) return gwat_internal::set_error(ctx, GWAT_B200_ERR_UNSUPPORTED, "sampler_last_swap_accepts: not for a sampler sharded over ranks");
+	if (s->k.C < 2) return GWAT_B200_OK;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	SCUDA(ctx, cudaSetDevice(ctx->device));
+	SCUDA(ctx, cudaMemcpy(accepted, s->swap_acc, sizeof(int) * (s->k.C - 1), cudaMemcpyDeviceToHost));
+	return GWAT_B200_OK;
+}
+
+// dynamic_temperature_full_ensemble_internal with linear swapping (src/mcmc_sampler.cpp:453-545): blocks of swp_freq steps, one
+// sweep over the whole ladder after each (the reference switches its probabilistic gate off and calls chain_swap itself; here
+// the gate is held open for the duration), then the temperature update with t = steps taken so far.
+int gwat_b200_sampler_dynamic_temperatures(gwat_b200_sampler *s, int N_steps, int nu, int t0, long long *sweeps_done)
+{
+	if (!s || N_steps < 0 || nu == 0) return GWAT_B200_ERR_ARG;
+	gwat_b200_ctx *ctx = s->ctx;
+	if (s->comm) return gwat_internal::set_error(ctx, GWAT_B200_ERR_UNSUPPORTED, "sampler_dynamic_temperatures: not for a sampler sharded over ranks");
+	if (s->since_swap != 0) return gwat_internal::set_error(ctx, GWAT_B200_ERR_STATE, "sampler_dynamic_temperatures: start at a swap boundary (steps run so far must be a multiple of swp_freq)");
+	const int C = s->k.C, steps = s->opt.swp_freq;
+	const double swap_rate_saved = s->opt.swap_rate;
+	s->opt.swap_rate = 2.0;  // every sweep happens
+	std::vector<double> A(C + 1, 0.0), temps(C);
+	std::vector<int> acc(C > 1 ? C - 1 : 1, 0);
+	int t = 0, rc = GWAT_B200_OK;
+	long long n = 0;
+	while (t < N_steps - steps && rc == GWAT_B200_OK) {
+		rc = gwat_b200_sampler_run(s, steps);
+		t += steps;
+		if (rc == GWAT_B200_OK) rc = gwat_b200_sampler_last_swap_accepts(s, acc.data());
+		if (rc != GWAT_B200_OK) break;
+		for (int i = 0; i + 1 < C; i++) A[i + 1] = acc[i] ? 1.0 : 0.0;
+		temps = s->h_temps;
+		gwat_b200_update_temperatures(C, temps.data(), A.data(), t0, nu, t);
+		rc = gwat_b200_sampler_set_temperatures(s, temps.data());
+		n++;
+	}
+	s->opt.swap_rate = swap_rate_saved;
+	if (sweeps_done) *sweeps_done = n;
+	return rc;
+}
+
 int gwat_b200_nccl_unique_id(unsigned char *id128)
 {
 	if (!id128) return GWAT_B200_ERR_ARG;

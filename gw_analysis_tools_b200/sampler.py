@@ -20,6 +20,8 @@ EXPORTS = [
     "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_sampler_uniform",
     "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
     "gwat_b200_nccl_unique_id", "gwat_b200_sampler_attach_ranks", "gwat_b200_sampler_last_swap_ms", "gwat_b200_sampler_last_sweeps",
+    "gwat_b200_update_temperatures", "gwat_b200_sampler_set_temperatures", "gwat_b200_sampler_temperatures",
+    "gwat_b200_sampler_last_swap_accepts", "gwat_b200_sampler_dynamic_temperatures",
     # chain output (bound in chain_io.py)
     "gwat_b200_dump_create", "gwat_b200_dump_write", "gwat_b200_dump_close", "gwat_b200_write_data_dump", "gwat_b200_write_flat_thin_output",
 ]
@@ -172,6 +174,28 @@ class Sampler:
         self._ctx._check(self._lib.gwat_b200_sampler_cold(self._h, C.c_longlong(first_step), int(n), _p(out), C.byref(nc)))
         return out
 
+    # ---- dynamic temperature allocation (arXiv:1501.05823; src/mcmc_sampler.cpp:453-545) ----
+    def temperatures(self):
+        out = np.empty(self.C)
+        self._ctx._check(self._lib.gwat_b200_sampler_temperatures(self._h, _p(out)))
+        return out
+
+    def set_temperatures(self, temps):
+        t = np.ascontiguousarray(temps, dtype=np.float64)
+        self._ctx._check(self._lib.gwat_b200_sampler_set_temperatures(self._h, _p(t)))
+
+    def last_swap_accepts(self):
+        out = np.zeros(max(self.C - 1, 1), dtype=np.int32)
+        self._ctx._check(self._lib.gwat_b200_sampler_last_swap_accepts(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out[:self.C - 1]
+
+    def dynamic_temperatures(self, n_steps, nu=10, t0=1000):
+        """Tune the ladder for n_steps steps (blocks of swp_freq steps, a sweep and a temperature update after each); returns the sweeps done."""
+        n = C.c_longlong()
+        self._ctx._check(self._lib.gwat_b200_sampler_dynamic_temperatures(self._h, int(n_steps), int(nu), int(t0), C.byref(n)))
+        self.steps += n.value * self.options.swp_freq
+        return n.value
+
     def attach_ranks(self, unique_id, rank, n_ranks):
         """Join a ladder sharded over ``n_ranks`` processes (one per GPU): this sampler must have been created with its own
         equal share of the chains and ``chain_index_offset = rank * chain_N``.  The swap sweeps then exchange over NCCL."""
@@ -197,6 +221,18 @@ class Sampler:
     @property
     def last_launches(self):
         return self._lib.gwat_b200_sampler_last_launches(self._h)
+
+
+def update_temperatures(chain_temps, A, t0, nu, t):
+    """update_temperatures_full_ensemble with linear swapping (src/mcmc_sampler_internals.cpp:3371-3413): the new ladder."""
+    from .engine import load_library
+    temps = np.array(chain_temps, dtype=np.float64)
+    a = np.zeros(temps.size + 1)
+    a[:len(A)] = A
+    rc = load_library().gwat_b200_update_temperatures(int(temps.size), _p(temps), _p(a), int(t0), int(nu), int(t))
+    if rc != 0:
+        raise ValueError("gwat_b200_update_temperatures: %d" % rc)
+    return temps
 
 
 def swap_sweep_host(logL, temps, seed, sweep):

@@ -144,6 +144,23 @@ double gwat_b200_sampler_last_ms(const gwat_b200_sampler *s);
 long long gwat_b200_sampler_last_launches(const gwat_b200_sampler *s);
 
 /*
+ * Dynamic temperature allocation (arXiv:1501.05823; dynamic_temperature_full_ensemble_internal src/mcmc_sampler.cpp:453-545 with
+ * linear swapping, update_temperatures_full_ensemble src/mcmc_sampler_internals.cpp:3371-3413, PT_dynamical_timescale :3224-3230).
+ *   gwat_b200_update_temperatures       the update rule alone (host arithmetic): A[i] = 1 / 0 says whether the last swap attempt
+ *                                       between chains i-1 and i was accepted; chains at T = 1 and at the ensemble's hottest
+ *                                       temperature stay where they are
+ *   gwat_b200_sampler_dynamic_temperatures  blocks of swp_freq steps on the device, a sweep after each, the update on the host
+ *                                       (C doubles back and forth per block), until N_steps - swp_freq steps are done
+ *   gwat_b200_sampler_set_temperatures / _temperatures / _last_swap_accepts   the pieces, for callers with their own schedule
+ * Single-rank samplers only.
+ */
+int gwat_b200_update_temperatures(int chain_N, double *chain_temps, const double *A /* [chain_N + 1] */, int t0, int nu, int t);
+int gwat_b200_sampler_set_temperatures(gwat_b200_sampler *s, const double *chain_temps);
+int gwat_b200_sampler_temperatures(gwat_b200_sampler *s, double *chain_temps);
+int gwat_b200_sampler_last_swap_accepts(gwat_b200_sampler *s, int *accepted /* [chain_N - 1] */);
+int gwat_b200_sampler_dynamic_temperatures(gwat_b200_sampler *s, int N_steps, int nu, int t0, long long *sweeps_done);
+
+/*
  * Chain output (host code, csrc/gwat_chain_io.cpp): the data dump and the thinned, flattened sample file of the reference's
  * mcmc_sampler_output (create_data_dump src/mcmc_io_util.cpp:643-990, write_flat_thin_output :555-642, count_indep_samples :521-552)
  * with the same dataset paths, shapes and thinning rule.  The reference writes HDF5; HDF5 is not available where this library is

@@ -205,3 +205,12 @@ class RefSampler:
                 "fvals": fvals, "fvecs": fvecs, "chain_pos": pos,
                 "diag": {"rng_underflow": int(diag[0]), "uniforms_left": int(diag[1]), "normals_left": int(diag[2]),
                          "fisher_script_underflow": int(diag[3]), "ll_calls": int(diag[4]), "fisher_calls": int(diag[5])}}
+
+
+def update_temperatures(chain_temps, A, t0, nu, t):
+    """update_temperatures_full_ensemble of the reference (linear swapping, src/mcmc_sampler_internals.cpp:3371-3413)."""
+    temps = np.array(chain_temps, dtype=np.float64)
+    a = np.zeros(temps.size + 1, dtype=np.int32)
+    a[:len(A)] = A
+    gwat_ref.lib().oracle_ref_update_temperatures(int(temps.size), _p(temps), a.ctypes.data_as(C.POINTER(C.c_int)), int(t0), int(nu), int(t))
+    return temps

@@ -356,4 +356,17 @@ void oracle_sampler_destroy(void *h)
 	delete r;
 }
 
+// update_temperatures_full_ensemble (src/mcmc_sampler_internals.cpp:3312-3413) with linear swapping, on a sampler struct that
+// carries nothing but the ladder and the swap indicators A.
+int oracle_ref_update_temperatures(int chain_N, double *chain_temps, int *A, int t0, int nu, int t)
+{
+	sampler s;
+	s.chain_N = chain_N;
+	s.chain_temps = chain_temps;
+	s.A = A;
+	s.linear_swapping = true;
+	update_temperatures_full_ensemble(&s, t0, nu, t);
+	return 0;
+}
+
 }  // extern "C"
