@@ -415,9 +415,9 @@ def fisher_measure(ctx, S, steps, warmup, fp64_peak, cpu_sample, seed_offset=0):
            "e2e": {"value": S * steps / t_e2e, "unit": "Fisher/s", "h2d_bytes_per_step": S * C_sizeof_source(),
                    "d2h_bytes_per_step": S * 121 * 8, "ms_per_step": t_e2e / steps * 1e3},
            "equivalent_response_evals_per_s": S * steps / t_dev * 132,
-           "roofline": {"bound": "fp64", "kernel": "k_fisher_deriv (+ k_fisher_setup, k_fisher_assemble: whole pass)", "achieved": achieved,
+           "roofline": {"bound": "fp64", "kernel": "k_fisher_fused (+ k_fisher_setup: whole pass)", "achieved": achieved,
                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                        "work": "reference schedule [SURVEY 8(d)]: %.4g flop-eq per source on average (3 det x 44 stencil responses x L_active x 335 + combine + assembly)" % (work / S),
+                        "work": "reference schedule [SURVEY 8(d)]: %.4g flop-eq per source on average (3 det x 44 stencil responses x L_active x 335 + combine + assembly); per source in HBM: the 11 x 4 coefficient blocks (61.6 kB) the fused kernel stages, see traffic" % (work / S),
                         "fp64_pipe_active_pct_ncu": ncu_value("cfg3", "fp64_pipe_active_pct"),
                         "traffic": ncu_value("cfg3", "k_fisher_dram_bytes_per_source"),
                         "peak_source": "DFMA-chain microbenchmark run in this process"},

@@ -590,23 +590,25 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 constexpr int kFusedTileBins = 32;
 
 struct FusedLayout {
-	int rows_p;      // dim rounded up to even: row stride of the derivative tile
 	int K;           // nd * 2 * kFusedTileBins values per parameter and tile
+	int Kp;          // row stride of the derivative tile Z[parameter][k]: K + 1, odd -- lanes store consecutive k (no bank conflict), and the
+	                 // threads of a warp that read the same k of different parameters hit different banks (the first layout, Z[k][parameter]
+	                 // with 12 doubles per k, stored with an 8-way conflict: 113 M conflicts per 5000 sources, short-scoreboard 2.1 per issue)
 	int npairs, slices;
 	size_t off_tc, off_z, off_red, bytes;
 };
 __host__ __device__ inline FusedLayout fused_layout(int dim, int npts, int nd)
 {
 	FusedLayout l;
-	l.rows_p = (dim + 1) & ~1;
 	l.K = nd * 2 * kFusedTileBins;
+	l.Kp = l.K + 1;
 	l.npairs = dim * (dim + 1) / 2;
 	l.slices = (dim * 32) / l.npairs;  // >= 2 for every dim <= 32
 	size_t o = (size_t)dim * npts * sizeof(WalkerCoef);
 	l.off_tc = o;
 	o += sizeof(double) * (size_t)dim * npts * nd;
 	l.off_z = o;
-	o += sizeof(double) * (size_t)l.K * l.rows_p;
+	o += sizeof(double) * 2 * (size_t)l.Kp * dim;  // two tiles: the products of tile t overlap the derivatives of tile t + 1
 	l.off_red = o;
 	o += sizeof(double) * (size_t)l.slices * l.npairs;
 	l.bytes = o;
@@ -631,8 +633,6 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 		double *dp = reinterpret_cast<double *>(w_all);
 		for (int i = threadIdx.x; i < (int)(dim * npts * sizeof(WalkerCoef) / sizeof(double)); i += blockDim.x) dp[i] = sp[i];
 		for (int i = threadIdx.x; i < dim * npts * nd; i += blockDim.x) tc_all[i] = tcoef[(size_t)s * dim * npts * nd + i];
-		if (lay.rows_p != dim)
-			for (int i = threadIdx.x; i < lay.K; i += blockDim.x) Z[i * lay.rows_p + dim] = 0.0;  // the padding row
 		__syncthreads();
 	}
 	// the live part of an ascending grid ends at the highest cutoff of any stencil point (all points valid), else it is all of it
@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 	}
 	double acc = 0.0;
 	const int ntiles = (g.L + kFusedTileBins - 1) / kFusedTileBins;
+	const size_t tile_words = (size_t)lay.Kp * dim;
 	for (int t = 0; t < ntiles; t++) {
 		const int bin0 = t * kFusedTileBins;
 		if (g.f[bin0] > fmax_all) break;  // (the same for the whole CTA)
@@ -668,19 +669,22 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 		const bool in_grid = bin_raw < g.L;
 		const int bin = in_grid ? bin_raw : g.L - 1;
 		const double f = g.f[bin], hi = g.sf_hi[bin], lo = g.sf_lo[bin], lg = g.logf[bin];
+		double *Zt = Z + (t & 1) * tile_words;
+		double *zrow = Zt + (size_t)param * lay.Kp;
 		auto store = [&](int d, const cplx &dv) {
 			// sqrt(w) on both factors of the product: w >= 0 (quadrature coefficient / PSD); bins of the last tile beyond L weigh 0
 			const double rw = in_grid ? sqrt(wq[(size_t)d * g.ld + bin]) : 0.0;
-			Z[((d * 2 + 0) * kFusedTileBins + lane) * lay.rows_p + param] = in_grid ? rw * dv.re : 0.0;
-			Z[((d * 2 + 1) * kFusedTileBins + lane) * lay.rows_p + param] = in_grid ? rw * dv.im : 0.0;
+			zrow[(d * 2 + 0) * kFusedTileBins + lane] = in_grid ? rw * dv.re : 0.0;
+			zrow[(d * 2 + 1) * kFusedTileBins + lane] = in_grid ? rw * dv.im : 0.0;
 		};
 		fisher_deriv_bin<Fam>(w, tc_s, nd, npts, nd, shared_parts, bc, sc, f, hi, lo, lg, store);
+		// one barrier per tile: the next tile's derivatives go to the other buffer, and nobody writes THIS buffer again before every
+		// thread has passed the next barrier, i.e. has finished the products below
 		__syncthreads();
 		if (gs < lay.slices) {
-			const double *zj = Z + pj, *zk = Z + pk;
-			for (int k = gs; k < lay.K; k += lay.slices) acc = fma(zj[k * lay.rows_p], zk[k * lay.rows_p], acc);
+			const double *zj = Zt + (size_t)pj * lay.Kp, *zk = Zt + (size_t)pk * lay.Kp;
+			for (int k = gs; k < lay.K; k += lay.slices) acc = fma(zj[k], zk[k], acc);
 		}
-		__syncthreads();
 	}
 	if (gs < lay.slices) red[gs * lay.npairs + gp] = acc;
 	__syncthreads();
