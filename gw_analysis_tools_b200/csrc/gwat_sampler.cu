@@ -306,11 +306,58 @@ __global__ void k_swap_prepare(const double *__restrict__ ll, const double *__re
 // src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118).  One thread: the
 // sweep is a chain of dependent decisions (4 instructions per pair); everything that is not -- thresholds before, counters and
 // the moves after -- runs in parallel kernels around it.
-__global__ void k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
-                            int *__restrict__ src, int *__restrict__ accepted)
+// The sequential part of the sweep (swap_scan, gwat_sampler_math.h): one thread walks the ladder, because whether pair (i, i+1) swaps
+// depends on what pair (i-1, i) did.  Everything that does NOT depend on the carried state -- thresholds, kinds, the next chain's
+// logL -- is staged in shared memory by the whole CTA in coalesced chunks, and the results leave the same way, so the walking
+// thread's dependent chain is a compare and a select per pair out of shared memory instead of three L2 round trips and two
+// stores (measured before: 0.3 ms per 4096 chains, 6 ms per 32768 -- 44 % of the step time of an 8-GPU ladder).
+constexpr int kScanChunk = 1536, kScanThreads = 512;  // 28 B of shared memory per pair: 42 KB
+__global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
+                                                           int *__restrict__ src, int *__restrict__ accepted)
 {
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
-	swap_scan(ll, thr, kind, C, src, accepted);
+	__shared__ double s_thr[kScanChunk], s_ll[kScanChunk];
+	__shared__ int s_kind[kScanChunk], s_src[kScanChunk], s_acc[kScanChunk];
+	__shared__ double s_carry;
+	__shared__ int s_carry_src;
+	if (blockIdx.x != 0) return;
+	if (threadIdx.x == 0) {
+		s_carry = ll[0];
+		s_carry_src = 0;
+	}
+	const int pairs = C - 1;
+	for (int base = 0; base < pairs; base += kScanChunk) {
+		const int n = min(kScanChunk, pairs - base);
+		for (int j = threadIdx.x; j < n; j += kScanThreads) {
+			s_thr[j] = thr[base + j];
+			s_kind[j] = kind[base + j];
+			s_ll[j] = ll[base + j + 1];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double carry = s_carry;
+			int carry_src = s_carry_src;
+			for (int j = 0; j < n; j++) {  // the very decisions of swap_scan
+				const int kd = s_kind[j];
+				const double th = s_thr[j];
+				const bool sw = (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
+				s_src[j] = sw ? base + j + 1 : carry_src;
+				s_acc[j] = sw ? 1 : 0;
+				if (!sw) {
+					carry = s_ll[j];
+					carry_src = base + j + 1;
+				}
+			}
+			s_carry = carry;
+			s_carry_src = carry_src;
+		}
+		__syncthreads();
+		for (int j = threadIdx.x; j < n; j += kScanThreads) {
+			src[base + j] = s_src[j];
+			accepted[base + j] = s_acc[j];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) src[C - 1] = s_carry_src;
 }
 // swap counters of the chains [c0, c0 + C) of a ladder of Ct chains: chain g took part in the pairs (g-1, g) and (g, g+1)
 __global__ void k_swap_count(const int *__restrict__ accepted, int Ct, int c0, int C, long long *__restrict__ counters)
@@ -670,7 +717,7 @@ int swap_sweep(gwat_b200_sampler *s)
 			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr));
 		k_swap_global_ll<<<(Ct + 255) / 256, 256, 0, st>>>(Ct, P, s->x_recv, s->g_ll);
 		k_swap_prepare<<<(Ct + 255) / 256, 256, 0, st>>>(s->g_ll, s->g_temps, s->k.seed, s->sweep, Ct, 0, s->g_thr, s->g_kind);
-		k_swap_scan<<<1, 32, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, s->g_src, s->g_acc);  // the WHOLE ladder, the same on every rank
+		k_swap_scan<<<1, kScanThreads, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, s->g_src, s->g_acc);  // the WHOLE ladder, the same on every rank
 		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->g_acc, Ct, c0, C, s->d.counters);
 		k_swap_take<<<(C * R + 255) / 256, 256, 0, st>>>(s->g_src, c0, C, P, s->x_recv, s->d.pos, s->d.ll, s->d.lp);
 		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw1[s->n_sw_timed++], st));
@@ -680,7 +727,7 @@ int swap_sweep(gwat_b200_sampler *s)
 		const bool timed = s->n_sw_timed < gwat_b200_sampler::NSW;
 		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw0[s->n_sw_timed], st));
 		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->k.chain_offset, s->swap_thr, s->swap_kind);
-		k_swap_scan<<<1, 32, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc);
+		k_swap_scan<<<1, kScanThreads, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc);
 		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->swap_acc, C, 0, C, s->d.counters);
 		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
 		std::swap(s->d.pos, s->pos2);
