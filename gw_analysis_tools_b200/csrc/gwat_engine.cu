@@ -13,6 +13,7 @@
 //   k_finish                     fixed-order sum of a walker's partials (one warp per walker) -> logL
 //   k_waveform / k_response      the same per-bin code writing polarisations / responses (API parity entry points)
 // There is no CPU fallback anywhere in this file.
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -126,7 +127,8 @@ __device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool 
 // Per-walker setup, cooperative (gwat_setup_coop.h): one CTA sets up kSetupWalkers walkers, lane = walker, warp = role; the
 // finished records leave with coalesced stores.  params != NULL: sampling vectors (repack_mcmc_walker), else physical records.
 constexpr int kSetupWalkers = 32;
-static_assert(sizeof(SetupRec) * kSetupWalkers <= 48 * 1024, "static shared memory");
+constexpr size_t kSetupSmemBytes = sizeof(SetupRec) * kSetupWalkers;  // 49.6 KB: dynamic shared memory, opted in once per instantiation (setup_smem_opt_in)
+static_assert(kSetupSmemBytes <= 96 * 1024, "shared memory of k_setup");
 
 // kernel experiments only (-DGWAT_SETUP_PROFILE): clock64 stamps of lane 0 of every role of block 0
 #ifdef GWAT_SETUP_PROFILE
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(kSetupWalkers * setup_roles<Fam>()) k_setup(co
                                                                               WalkerCoef *__restrict__ out, unsigned long long *__restrict__ active_zero)
 {
 	constexpr bool kP = Fam::base == BASE_P;
-	__shared__ SetupRec recs[kSetupWalkers];
+	extern __shared__ __align__(16) unsigned char setup_smem[];
+	SetupRec *recs = reinterpret_cast<SetupRec *>(setup_smem);
 	if (active_zero && blockIdx.x == 0 && threadIdx.x == 0) *active_zero = 0;  // the pass's active-bin counter (k_finish / k_loglike add to it)
 	const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
 	const int w = blockIdx.x * kSetupWalkers + lane;
@@ -1073,11 +1076,30 @@ int check_ready(gwat_b200_ctx *ctx, bool need_data)
 	return 0;
 }
 
+// k_setup's records take more than the 48 KB a kernel gets without asking: opt in once per instantiation and device.
+template <class Fam>
+void setup_smem_opt_in()
+{
+	static std::atomic<bool> done[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (done[dev].load(std::memory_order_acquire)) return;
+	cudaFuncSetAttribute(k_setup<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSetupSmemBytes);
+	done[dev].store(true, std::memory_order_release);
+}
+template <class Fam>
+void launch_setup(int W, cudaStream_t st, const double *d_params, const gwat_b200_source *d_src, const RepackPlan &plan, const Network &net, int theory,
+                  double gmst, double T_segment, WalkerCoef *d_coef, unsigned long long *d_active)
+{
+	setup_smem_opt_in<Fam>();
+	k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), kSetupSmemBytes, st>>>(d_params, d_src, W, plan, net, theory, gmst,
+	                                                                                                            T_segment, d_coef, d_active);
+}
 template <class Fam>
 void launch_setup_src(gwat_b200_ctx *ctx, int W, const gwat_b200_source *d_src, int theory, cudaStream_t st, const Network &net)
 {
-	k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(nullptr, d_src, W, RepackPlan{}, net, theory, 0.0, 0.0,
-	                                                                                                 ctx->d_coef, ctx->d_active);
+	launch_setup<Fam>(W, st, nullptr, d_src, RepackPlan{}, net, theory, 0.0, 0.0, ctx->d_coef, ctx->d_active);
 }
 
 // single_detector: the semantics of the reference's one-detector entry points (fourier_detector_response, calculate_snr), which
@@ -1982,8 +2004,7 @@ int loglike_mcmc_lane(gwat_b200_ctx *ctx, int lane, const char *method, const gw
 	cudaEvent_t ev_a = lane > 0 ? ctx->extra[lane - 1].ev_a : nullptr, ev_b = lane > 0 ? ctx->extra[lane - 1].ev_b : nullptr;
 	LaneSwap swap(ctx, lane);
 	if (grow(ctx, ctx->d_coef, ctx->cap_walkers, (size_t)W)) return GWAT_B200_ERR_CUDA;
-	GWAT_DISPATCH_FAMILY(desc, k_setup<Fam><<<(W + kSetupWalkers - 1) / kSetupWalkers, kSetupWalkers * setup_roles<Fam>(), 0, st>>>(
-	                               d_params, nullptr, W, plan, ctx->net, desc.theory, gmst, T_segment, ctx->d_coef, ctx->d_active));
+	GWAT_DISPATCH_FAMILY(desc, launch_setup<Fam>(W, st, d_params, nullptr, plan, ctx->net, desc.theory, gmst, T_segment, ctx->d_coef, ctx->d_active));
 	ctx->launches += 1;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return run_loglike(ctx, desc, W, d_logL, st, st_heavy, ev_a, ev_b);

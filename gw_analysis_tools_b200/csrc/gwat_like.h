@@ -43,7 +43,10 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	if (Fam::nrt && f > c.nrt_fmerger12) return false;
 	const double sixth = bin_sixth_root(c, sf_hi, sf_lo);
 	MfPowers p;
-	const bool full = f < c.f1p || f < c.f1a || Fam::base == BASE_P || Fam::nrt;
+	// The full table of powers (with its exact division for the leading TaylorF2 term) only where the inspiral forms are
+	// evaluated and for NRTidal; above both inspiral boundaries the carrier needs (M f), its sixth root and -- IMRPhenomPv2 --
+	// the two powers of the twist-up.
+	const bool full = f < c.f1p || f < c.f1a || Fam::nrt;
 	if (full) {
 		// mf_powers with the quotient shared: 1/(Mf)^(7/6) = (Mf)^(1/2) / (Mf)^(5/3) -- amplitude side only
 		mf_powers(c.M, f, sixth, p);
@@ -51,6 +54,10 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 		p.Mf = mul_rn(c.M, f);
 		p.sixth = sixth;
 		p.seven6 = mul_rn(mul_rn(sixth, c.M), f);
+		if (Fam::base == BASE_P) {
+			p.third = mul_rn(sixth, sixth);
+			p.two3 = mul_rn(p.third, p.third);
+		}
 	}
 	double shape;
 	if (f < c.f1a) shape = phenomd_amp_ins(c, p);
@@ -84,12 +91,15 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	const double roc = fast_rcp(oc);
 	const double x2 = x * x, eta = pc.eta;
 	const double Lorb = (eta * (1.0 + pc.lc1 * x + pc.lc2 * x2)) * roc;
-	const double sb = pc.SP * fast_rcp(Lorb + pc.SL);  // tan(beta)
-	const double cb = fast_rsqrt(1.0 + sb * sb);       // cos(beta)
-	const double sinb = fabs(sb) * cb;                  // 2 cos(beta/2) sin(beta/2) with the reference's positive half-angle roots
-	const double c2h = 0.5 * (1.0 + cb), s2h = 0.5 * (1.0 - cb);  // cos^2(beta/2), sin^2(beta/2)
-	// Wigner d^2_{m,2}: a_m, m = -2..2  (= s^4, 2 c s^3, sqrt6 s^2 c^2, 2 c^3 s, c^4 in half-angle terms)
-	const double a0 = s2h * s2h, a1 = sinb * s2h, a2 = 2.44948974278317788 * (s2h * c2h), a3 = sinb * c2h, a4 = c2h * c2h;
+	// tan(beta) = SP / (Lorb + SL); the reference takes cos(beta) = 1/sqrt(1 + tan^2) > 0 and positive half-angle roots, i.e.
+	// cos(beta) = |u| / sqrt(u^2 + SP^2), sin(beta) = |SP| / sqrt(u^2 + SP^2) with u = Lorb + SL: one reciprocal root, no division
+	const double u = Lorb + pc.SL;
+	const double rn = fast_rsqrt(u * u + pc.SP2);
+	const double cb = fabs(u) * rn, sinb = fabs(pc.SP) * rn;
+	// Wigner d^2_{m,2}(beta), m = -2..2, is (s^4, 2 c s^3, sqrt6 s^2 c^2, 2 c^3 s, c^4) in the half angle.  The sums over +-m that
+	// the polarisations need are polynomials in cos(beta), sin(beta) themselves:
+	//   d_2 - d_-2 = cos b,   d_2 + d_-2 = (1 + cos^2 b)/2,   d_1 + d_-1 = sin b,   d_1 - d_-1 = sin b cos b,   2 d_0 = (sqrt6/2) sin^2 b
+	const double sc = sinb * cb, e2 = fma(cb, cb, 1.0), sb2 = sinb * sinb;
 	const double roc2 = roc * roc, roc3 = roc2 * roc;
 	const double logom = add_rn(c.logpiM, logf);
 	const double alpha = ((((pc.acoef[0] * roc3 + pc.acoef[1] * roc2) + pc.acoef[2] * roc) + pc.acoef[3] * logom) + pc.acoef[4] * oc) +
@@ -99,16 +109,10 @@ GWAT_HD bool carrier_terms(const WalkerCoef &w, double f, double sf_hi, double s
 	double s1, c1;
 	fast_sincos(alpha, &s1, &c1);
 	const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;
-	// sum_m Y_m (d^2_{-m} e^{-i m alpha} +- d^2_m e^{+i m alpha}) with real Y_m, grouped by |m|
-	const double *Y = pc.Y;  // m = -2..2
-	const double Pm2 = a4 + a0, Pm1 = a1 - a3, P0 = 2.0 * a2, Pp1 = a3 - a1, Pp2 = a0 + a4;
-	const double Nm2 = a0 - a4, Nm1 = a1 + a3, Np1 = a3 + a1, Np2 = a4 - a0;
-	const double A1 = Y[3] * Pp1 + Y[1] * Pm1, A2 = Y[4] * Pp2 + Y[0] * Pm2;   // cos coefficients of Re(P)
-	const double B1 = Y[3] * Np1 - Y[1] * Nm1, B2 = Y[4] * Np2 - Y[0] * Nm2;   // sin coefficients of Im(P)
-	const double C1 = Y[3] * Pp1 - Y[1] * Pm1, C2 = Y[4] * Pp2 - Y[0] * Pm2;   // sin coefficients of Re(Q)
-	const double D1 = Y[3] * Np1 + Y[1] * Nm1, D2 = Y[4] * Np2 + Y[0] * Nm2;   // cos coefficients of -Im(Q)
-	P = cplx{Y[2] * P0 + c1 * A1 + c2 * A2, s1 * B1 + s2 * B2};
-	Q = cplx{s1 * C1 + s2 * C2, -(c1 * D1 + c2 * D2)};
+	// sum_m Y_m (d^2_{-m} e^{-i m alpha} +- d^2_m e^{+i m alpha}) with real Y_m, grouped by |m| (pc.tw: the +- m sums of Y_m)
+	const double *tw = pc.tw;
+	P = cplx{tw[2] * sb2 + tw[0] * (c1 * sc) + tw[5] * (c2 * e2), tw[0] * (s1 * sinb) + tw[3] * (s2 * cb)};
+	Q = cplx{tw[1] * (s1 * sc) + tw[6] * (s2 * e2), -(tw[1] * (c1 * sinb) + tw[4] * (c2 * cb))};
 	phase = add_rn(phase, mul_rn(2., epsilon));
 	double a = sub_rn(phase, mul_rn(pc.tc, sub_rn(f, pc.f_ref)));
 	a = sub_rn(a, pc.phic);
@@ -190,8 +194,9 @@ GWAT_HD void like_bin(const WalkerCoef &w, bool uniform, LikeState<D> &st, doubl
 #pragma unroll
 	for (int d = 0; d < D; d++) {
 		const DetCoef &dc = w.det[d];
-		// G = ga P + gb Q
-		const double Gre = dc.ga * P.re + dc.gb * Q.re, Gim = dc.ga * P.im + dc.gb * Q.im;
+		// G = ga P + gb Q   (IMRPhenomD families: P = 1, Q = -i, so G = ga - i gb is a walker constant)
+		const double Gre = Fam::base == BASE_D ? dc.ga : dc.ga * P.re + dc.gb * Q.re;
+		const double Gim = Fam::base == BASE_D ? -dc.gb : dc.ga * P.im + dc.gb * Q.im;
 		const double wq = tab.wq(d);
 		hh += wq * (Gre * Gre + Gim * Gim);
 		cplx zd;

@@ -134,6 +134,9 @@ struct PCoef {
 	double alpha_const;    // alpha0 - alpha_offset
 	double epsilon_offset;
 	double Y[5];  // -2Y_{2m}(thetaJN, 0), m = -2..2 (real at zero azimuth)
+	// the same harmonics in the combinations the fused likelihood uses (gwat_like.h: carrier_terms):
+	//   tw = { Y1 - Y-1, Y1 + Y-1, (sqrt6 / 2) Y0, Y2 + Y-2, Y2 - Y-2, (Y2 + Y-2) / 2, (Y2 - Y-2) / 2 },  SP2 = SP^2
+	double tw[7], SP2;
 	double c2z, s2z;        // polarisation rotation by 2 zeta (src/waveform_generator.cpp:257-266)
 	double phic, tc, f_ref, tcorr_2pi;
 };

@@ -263,6 +263,14 @@ GWAT_HD void phenomp_setup_angles(const SrcQ &s, PCoef &p)
 	double Y[5];
 	spin_weighted_y2(s.thetaJN, Y);
 	for (int i = 0; i < 5; i++) p.Y[i] = Y[i];
+	p.tw[0] = Y[3] - Y[1];
+	p.tw[1] = Y[3] + Y[1];
+	p.tw[2] = (0.5 * 2.44948974278317788) * Y[2];
+	p.tw[3] = Y[4] + Y[0];
+	p.tw[4] = Y[4] - Y[0];
+	p.tw[5] = 0.5 * p.tw[3];
+	p.tw[6] = 0.5 * p.tw[4];
+	p.SP2 = s.SP * s.SP;
 	p.A0 = s.A0 * sm::pow(s.M, 7. / 6.) / (2. * sqrt(5. / (64. * GWAT_PI)));
 	p.SP = s.SP;
 	p.SL = s.SL;
