@@ -19,6 +19,7 @@
 #include <nccl.h>  // types and prototypes only: the library is opened at run time (see nccl_api)
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -303,23 +304,35 @@ __global__ void k_swap_prepare(const double *__restrict__ ll, const double *__re
 	kind[i] = kd;
 	thr[i] = th;
 }
-// src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118).  One thread: the
-// sweep is a chain of dependent decisions (4 instructions per pair); everything that is not -- thresholds before, counters and
-// the moves after -- runs in parallel kernels around it.
-// The sequential part of the sweep (swap_scan, gwat_sampler_math.h): one thread walks the ladder, because whether pair (i, i+1) swaps
-// depends on what pair (i-1, i) did.  Everything that does NOT depend on the carried state -- thresholds, kinds, the next chain's
-// logL -- is staged in shared memory by the whole CTA in coalesced chunks, and the results leave the same way, so the walking
-// thread's dependent chain is a compare and a select per pair out of shared memory instead of three L2 round trips and two
-// stores (measured before: 0.3 ms per 4096 chains, 6 ms per 32768 -- 44 % of the step time of an 8-GPU ladder).
-constexpr int kScanChunk = 1536, kScanThreads = 512;  // 28 B of shared memory per pair: 42 KB
-__global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
-                                                           int *__restrict__ src, int *__restrict__ accepted)
+// src[i] = which slot's state ends up in slot i (chain_swap's sweep, src/mcmc_sampler_internals.cpp:1086-1118).
+//
+// The sweep is sequential as the reference writes it -- whether pair (i, i+1) swaps depends on what pair (i-1, i) did -- but the
+// dependence has a simple shape.  A state that the sweep carries upwards from slot s (logL = ll[s]) keeps moving while it passes
+// the thresholds of the pairs s, s+1, ...; the first pair e(s) it fails ends its RUN, slot e(s) receives it, and the next run
+// starts at slot e(s) + 1 with that slot's own state.  So with nxt[s] = e(s) + 1 (computed for every slot at once, a couple of
+// comparisons each: runs are short) the slots where runs start are the orbit of slot 0 under nxt, and
+//   accepted[j] = (slot j+1 does not start a run),   src[j] = j + 1 for accepted pairs,   src[nxt[s] - 1] = s for every start s
+// (the last run ends at the top slot: nxt = C).  The orbit is marked by pointer doubling: after round k the starts with orbit
+// index < 2^k are marked and jump = nxt^(2^k), ceil(log2 C) + 1 rounds in all.  The comparisons are the very ones of swap_scan
+// (gwat_sampler_math.h) on the same values, so the decisions are identical; a run longer than kRunCap pairs (practically only
+// adversarial inputs) makes the CTA fall back to the staged sequential walk below.
+// One CTA; the jump and mark arrays live in shared memory (16-bit / 8-bit) up to kScanSmemSlots slots, else in global scratch (L2).
+// Measured before (one thread walking the ladder out of staged shared memory): 0.15 ms per 4096 chains, 1.2 ms per 32768.
+constexpr int kScanChunk = 1536, kScanThreads = 1024, kRunCap = 256;
+constexpr int kScanSmemSlots = 36000;  // 5 B per slot (two 16-bit jump arrays, byte marks): 176 KB of dynamic shared memory next to the 42 KB of the fallback's staging
+__device__ __forceinline__ bool swap_passes(int kd, double th, double carry)
+{
+	return (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
+}
+// The sequential walk (fallback): one thread walks the ladder; everything that does not depend on the carried state is staged in
+// shared memory by the whole CTA in coalesced chunks, and the results leave the same way.
+__device__ void swap_scan_staged(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C, int *__restrict__ src,
+                                 int *__restrict__ accepted)
 {
 	__shared__ double s_thr[kScanChunk], s_ll[kScanChunk];
 	__shared__ int s_kind[kScanChunk], s_src[kScanChunk], s_acc[kScanChunk];
 	__shared__ double s_carry;
 	__shared__ int s_carry_src;
-	if (blockIdx.x != 0) return;
 	if (threadIdx.x == 0) {
 		s_carry = ll[0];
 		s_carry_src = 0;
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__rest
 	const int pairs = C - 1;
 	for (int base = 0; base < pairs; base += kScanChunk) {
 		const int n = min(kScanChunk, pairs - base);
-		for (int j = threadIdx.x; j < n; j += kScanThreads) {
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
 			s_thr[j] = thr[base + j];
 			s_kind[j] = kind[base + j];
 			s_ll[j] = ll[base + j + 1];
@@ -337,9 +350,7 @@ __global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__rest
 			double carry = s_carry;
 			int carry_src = s_carry_src;
 			for (int j = 0; j < n; j++) {  // the very decisions of swap_scan
-				const int kd = s_kind[j];
-				const double th = s_thr[j];
-				const bool sw = (kd == 3) || (kd == 1 && carry >= th) || (kd == 2 && carry <= th);
+				const bool sw = swap_passes(s_kind[j], s_thr[j], carry);
 				s_src[j] = sw ? base + j + 1 : carry_src;
 				s_acc[j] = sw ? 1 : 0;
 				if (!sw) {
@@ -351,13 +362,98 @@ __global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__rest
 			s_carry_src = carry_src;
 		}
 		__syncthreads();
-		for (int j = threadIdx.x; j < n; j += kScanThreads) {
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
 			src[base + j] = s_src[j];
 			accepted[base + j] = s_acc[j];
 		}
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) src[C - 1] = s_carry_src;
+}
+// Rounds of pointer doubling over the slots [0, C): ja = nxt on entry, mk[0] = 1.  Idx/Mark: 16-bit jumps and byte marks in shared
+// memory for ladders below 2^16 slots, ints in global scratch otherwise.
+template <class Idx, class Mark>
+__device__ __forceinline__ void swap_mark_starts(Idx *ja, Idx *jb, Mark *mk, int C)
+{
+	for (int span = 1; span < 2 * C; span *= 2) {
+		// marks first (stores into mk), then the jumps as a pass of loads that nothing in between can alias
+		for (int s = threadIdx.x; s < C; s += blockDim.x) {
+			if (mk[s]) {
+				const int t = ja[s];
+				if (t < C) mk[t] = 1;
+			}
+		}
+		{
+			const Idx *__restrict__ a = ja;
+			Idx *__restrict__ o = jb;
+#pragma unroll 8
+			for (int s = threadIdx.x; s < C; s += blockDim.x) {
+				const int t = a[s];
+				o[s] = t < C ? a[t] : (Idx)C;
+			}
+		}
+		__syncthreads();
+		Idx *sw = ja;
+		ja = jb;
+		jb = sw;
+	}
+}
+// work: 4 C ints of global scratch (nxt, and the jump/mark arrays of ladders too long for shared memory); force_sequential: tests only
+__global__ void __launch_bounds__(kScanThreads) k_swap_scan(const double *__restrict__ ll, const double *__restrict__ thr, const int *__restrict__ kind, int C,
+                                                           int *__restrict__ src, int *__restrict__ accepted, int *__restrict__ work, int force_sequential)
+{
+	extern __shared__ unsigned char scan_smem[];
+	__shared__ int s_slow;
+	if (blockIdx.x != 0) return;
+	const bool in_smem = C <= kScanSmemSlots;
+	int *nxt = work;
+	unsigned short *ja16 = reinterpret_cast<unsigned short *>(scan_smem), *jb16 = ja16 + C;
+	unsigned char *mk8 = reinterpret_cast<unsigned char *>(jb16 + C);
+	int *ja32 = work + C, *jb32 = ja32 + C, *mk32 = jb32 + C;
+	const int pairs = C - 1;
+	if (threadIdx.x == 0) s_slow = force_sequential;
+	__syncthreads();
+	// runs: nxt[s] = 1 + the first pair at or after s that the state of slot s does not pass
+	for (int s = threadIdx.x; s < C; s += blockDim.x) {
+		const double carry = ll[s];
+		int j = s;
+		while (j < pairs && j - s < kRunCap && swap_passes(kind[j], thr[j], carry)) j++;
+		if (j < pairs && j - s >= kRunCap) s_slow = 1;
+		nxt[s] = j + 1;
+		if (in_smem) {
+			ja16[s] = (unsigned short)(j + 1);
+			mk8[s] = s == 0 ? 1 : 0;
+		} else {
+			ja32[s] = j + 1;
+			mk32[s] = s == 0 ? 1 : 0;
+		}
+	}
+	__syncthreads();
+	if (s_slow) {
+		swap_scan_staged(ll, thr, kind, C, src, accepted);
+		return;
+	}
+	// the starts of the runs: the orbit of slot 0 under nxt, by pointer doubling
+	if (in_smem) swap_mark_starts(ja16, jb16, mk8, C);
+	else swap_mark_starts(ja32, jb32, mk32, C);
+	for (int j = threadIdx.x; j < pairs; j += blockDim.x) {
+		const int acc = (in_smem ? (int)mk8[j + 1] : mk32[j + 1]) ? 0 : 1;
+		accepted[j] = acc;
+		if (acc) src[j] = j + 1;
+	}
+	for (int s = threadIdx.x; s < C; s += blockDim.x)
+		if (in_smem ? (int)mk8[s] : mk32[s]) src[nxt[s] - 1] = s;
+}
+inline size_t scan_smem_bytes(int C) { return C <= kScanSmemSlots ? (size_t)C * 5 : 0; }
+inline void scan_smem_opt_in()
+{
+	static std::atomic<bool> done[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (done[dev].load(std::memory_order_acquire)) return;
+	cudaFuncSetAttribute(k_swap_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kScanSmemSlots));
+	done[dev].store(true, std::memory_order_release);
 }
 // swap counters of the chains [c0, c0 + C) of a ladder of Ct chains: chain g took part in the pairs (g-1, g) and (g, g+1)
 __global__ void k_swap_count(const int *__restrict__ accepted, int Ct, int c0, int C, long long *__restrict__ counters)
@@ -505,7 +601,7 @@ struct gwat_b200_sampler {
 	DevState d{};
 	double *pos2 = nullptr, *ll2 = nullptr, *lp2 = nullptr;  // swap double buffers
 	double *swap_thr = nullptr;
-	int *swap_kind = nullptr, *swap_src = nullptr, *swap_acc = nullptr;
+	int *swap_kind = nullptr, *swap_src = nullptr, *swap_acc = nullptr, *swap_work = nullptr;  // swap_work: 4 C ints, k_swap_scan's arrays when the ladder is too long for shared memory
 	// Fisher refresh pipeline, per lane: device staging slots (one per step in flight) and a longer ring of pinned index lists
 	struct RefreshLane {
 		int ND = 1, NP = 1;
@@ -551,7 +647,7 @@ struct gwat_b200_sampler {
 	int rank = 0, n_ranks = 1;
 	double *x_send = nullptr, *x_recv = nullptr;  // [C][P + 2] and [n_ranks * C][P + 2]
 	double *g_ll = nullptr, *g_temps = nullptr, *g_thr = nullptr;
-	int *g_kind = nullptr, *g_src = nullptr, *g_acc = nullptr;
+	int *g_kind = nullptr, *g_src = nullptr, *g_acc = nullptr, *g_work = nullptr;
 	static constexpr int NSW = 64;                  // swap sweeps of a run whose exchange is timed
 	cudaEvent_t ev_sw0[NSW] = {}, ev_sw1[NSW] = {};
 	int n_sw_timed = 0;
@@ -717,7 +813,8 @@ int swap_sweep(gwat_b200_sampler *s)
 			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr));
 		k_swap_global_ll<<<(Ct + 255) / 256, 256, 0, st>>>(Ct, P, s->x_recv, s->g_ll);
 		k_swap_prepare<<<(Ct + 255) / 256, 256, 0, st>>>(s->g_ll, s->g_temps, s->k.seed, s->sweep, Ct, 0, s->g_thr, s->g_kind);
-		k_swap_scan<<<1, kScanThreads, 0, st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, s->g_src, s->g_acc);  // the WHOLE ladder, the same on every rank
+		scan_smem_opt_in();
+		k_swap_scan<<<1, kScanThreads, scan_smem_bytes(Ct), st>>>(s->g_ll, s->g_thr, s->g_kind, Ct, s->g_src, s->g_acc, s->g_work, 0);  // the WHOLE ladder, the same on every rank
 		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->g_acc, Ct, c0, C, s->d.counters);
 		k_swap_take<<<(C * R + 255) / 256, 256, 0, st>>>(s->g_src, c0, C, P, s->x_recv, s->d.pos, s->d.ll, s->d.lp);
 		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw1[s->n_sw_timed++], st));
@@ -727,7 +824,8 @@ int swap_sweep(gwat_b200_sampler *s)
 		const bool timed = s->n_sw_timed < gwat_b200_sampler::NSW;
 		if (timed) SCUDA(ctx, cudaEventRecord(s->ev_sw0[s->n_sw_timed], st));
 		k_swap_prepare<<<(C + 255) / 256, 256, 0, st>>>(s->d.ll, s->d.temps, s->k.seed, s->sweep, C, s->k.chain_offset, s->swap_thr, s->swap_kind);
-		k_swap_scan<<<1, kScanThreads, 0, st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc);
+		scan_smem_opt_in();
+		k_swap_scan<<<1, kScanThreads, scan_smem_bytes(C), st>>>(s->d.ll, s->swap_thr, s->swap_kind, C, s->swap_src, s->swap_acc, s->swap_work, 0);
 		k_swap_count<<<(C + 255) / 256, 256, 0, st>>>(s->swap_acc, C, 0, C, s->d.counters);
 		k_swap_apply<<<(C * P + 255) / 256, 256, 0, st>>>(s->swap_src, C, P, s->d.pos, s->d.ll, s->d.lp, s->pos2, s->ll2, s->lp2);
 		std::swap(s->d.pos, s->pos2);
@@ -859,7 +957,7 @@ void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 	}
 	DevState &d = s->d;
 	void *ptrs[] = {d.pos, d.prop, d.ll, d.lp, d.llprop, d.lpprop, d.temps, d.hist, d.hist_pos, d.fvals, d.fvecs, d.widths, d.counters,
-	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src, s->swap_acc};
+	                d.gauss_ct, d.type_last, d.info, d.cold_slot, d.cold, s->pos2, s->ll2, s->lp2, s->swap_thr, s->swap_kind, s->swap_src, s->swap_acc, s->swap_work};
 	for (void *p : ptrs) cudaFree(p);
 	if (s->st_fisher) cudaStreamSynchronize(s->st_fisher);
 	for (gwat_b200_sampler::RefreshLane &r : s->rf) {
@@ -885,7 +983,7 @@ void gwat_b200_sampler_destroy(gwat_b200_sampler *s)
 	for (void *p : {(void *)s->g_idx, (void *)s->g_ok, (void *)s->g_par, (void *)s->g_mat, (void *)s->g_vals, (void *)s->g_vecs}) cudaFree(p);
 	if (s->gh_idx) cudaFreeHost(s->gh_idx);
 	for (void *p : {(void *)s->x_send, (void *)s->x_recv, (void *)s->g_ll, (void *)s->g_temps, (void *)s->g_thr, (void *)s->g_kind, (void *)s->g_src,
-	                (void *)s->g_acc})
+	                (void *)s->g_acc, (void *)s->g_work})
 		cudaFree(p);
 	for (int i = 0; i < gwat_b200_sampler::NSW; i++) {
 		if (s->ev_sw0[i]) cudaEventDestroy(s->ev_sw0[i]);
@@ -965,6 +1063,7 @@ int gwat_b200_sampler_create(gwat_b200_ctx *ctx, const char *method, const gwat_
 	SC_TRY(dalloc(s->swap_kind, (size_t)C));
 	SC_TRY(dalloc(s->swap_src, (size_t)C));
 	SC_TRY(dalloc(s->swap_acc, (size_t)C));
+	SC_TRY(dalloc(s->swap_work, (size_t)4 * C));
 	int prio_lo = 0, prio_hi = 0;
 	SC_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	s->lookahead = 0;
@@ -1189,6 +1288,49 @@ int gwat_b200_swap_sweep_host(int C, const double *logL, const double *temps, un
 	return GWAT_B200_OK;
 }
 
+// The device sweep on caller-supplied inputs (thresholds + k_swap_scan), for tests against gwat_b200_swap_sweep_host: mode 0 = as the
+// sampler runs it, 1 = the sequential fallback forced.
+int gwat_b200_swap_sweep_device(gwat_b200_ctx *ctx, int C, const double *logL, const double *temps, unsigned long long seed, long long sweep,
+                                int mode, int *src, int *accepted)
+{
+	if (!ctx || C < 2 || !logL || !temps || !src) return GWAT_B200_ERR_ARG;
+	double *d_ll = nullptr, *d_t = nullptr, *d_thr = nullptr;
+	int *d_kind = nullptr, *d_src = nullptr, *d_acc = nullptr, *d_work = nullptr;
+	auto release = [&]() {
+		for (void *p : {(void *)d_ll, (void *)d_t, (void *)d_thr, (void *)d_kind, (void *)d_src, (void *)d_acc, (void *)d_work}) cudaFree(p);
+	};
+#define SW_TRY(x)                                                                   \
+	do {                                                                            \
+		cudaError_t e_ = (x);                                                       \
+		if (e_ != cudaSuccess) {                                                    \
+			release();                                                              \
+			return gwat_internal::set_error(ctx, GWAT_B200_ERR_CUDA, std::string("swap_sweep_device: ") + cudaGetErrorString(e_)); \
+		}                                                                           \
+	} while (0)
+	SW_TRY(cudaSetDevice(ctx->device));
+	SW_TRY(cudaMalloc((void **)&d_ll, sizeof(double) * C));
+	SW_TRY(cudaMalloc((void **)&d_t, sizeof(double) * C));
+	SW_TRY(cudaMalloc((void **)&d_thr, sizeof(double) * C));
+	SW_TRY(cudaMalloc((void **)&d_kind, sizeof(int) * C));
+	SW_TRY(cudaMalloc((void **)&d_src, sizeof(int) * C));
+	SW_TRY(cudaMalloc((void **)&d_acc, sizeof(int) * C));
+	SW_TRY(cudaMalloc((void **)&d_work, sizeof(int) * 4 * (size_t)C));
+	SW_TRY(cudaMemcpy(d_ll, logL, sizeof(double) * C, cudaMemcpyHostToDevice));
+	SW_TRY(cudaMemcpy(d_t, temps, sizeof(double) * C, cudaMemcpyHostToDevice));
+	SW_TRY(cudaMemset(d_src, 0xff, sizeof(int) * C));
+	SW_TRY(cudaMemset(d_acc, 0xff, sizeof(int) * C));
+	k_swap_prepare<<<(C + 255) / 256, 256>>>(d_ll, d_t, seed, sweep, C, 0, d_thr, d_kind);
+	scan_smem_opt_in();
+	k_swap_scan<<<1, kScanThreads, scan_smem_bytes(C)>>>(d_ll, d_thr, d_kind, C, d_src, d_acc, d_work, mode);
+	SW_TRY(cudaGetLastError());
+	SW_TRY(cudaDeviceSynchronize());
+	SW_TRY(cudaMemcpy(src, d_src, sizeof(int) * C, cudaMemcpyDeviceToHost));
+	if (accepted) SW_TRY(cudaMemcpy(accepted, d_acc, sizeof(int) * (C - 1), cudaMemcpyDeviceToHost));
+#undef SW_TRY
+	release();
+	return GWAT_B200_OK;
+}
+
 int gwat_b200_sampler_counters(gwat_b200_sampler *s, long long *counters, double *widths)
 {
 	if (!s) return GWAT_B200_ERR_ARG;
@@ -1382,6 +1524,7 @@ int gwat_b200_sampler_attach_ranks(gwat_b200_sampler *s, const unsigned char *id
 	AT_TRY(dalloc(s->g_kind, (size_t)Ct));
 	AT_TRY(dalloc(s->g_src, (size_t)Ct));
 	AT_TRY(dalloc(s->g_acc, (size_t)Ct));
+	AT_TRY(dalloc(s->g_work, (size_t)4 * Ct));
 	// the whole ladder's temperatures, once
 	r = api.AllGather(s->d.temps, s->g_temps, (size_t)C, ncclDouble, comm, st);
 	if (r != ncclSuccess) return fail_here(std::string("ncclAllGather(temperatures): ") + api.GetErrorString(r));

@@ -17,7 +17,7 @@ COUNTERS = ["step_accept", "step_reject", "gauss_accept", "gauss_reject", "de_ac
 EXPORTS = [
     "gwat_b200_prior_init", "gwat_b200_sampler_options_init", "gwat_b200_sampler_create", "gwat_b200_sampler_destroy",
     "gwat_b200_sampler_run", "gwat_b200_sampler_state", "gwat_b200_sampler_counters", "gwat_b200_sampler_cold",
-    "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_sampler_uniform",
+    "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_swap_sweep_device", "gwat_b200_sampler_uniform",
     "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
     "gwat_b200_nccl_unique_id", "gwat_b200_sampler_attach_ranks", "gwat_b200_sampler_last_swap_ms", "gwat_b200_sampler_last_sweeps",
     "gwat_b200_update_temperatures", "gwat_b200_sampler_set_temperatures", "gwat_b200_sampler_temperatures",
@@ -247,6 +247,22 @@ def swap_sweep_host(logL, temps, seed, sweep):
                                                   src.ctypes.data_as(C.POINTER(C.c_int)), acc.ctypes.data_as(C.POINTER(C.c_int)))
     if rc != 0:
         raise GwatB200Error(rc, "swap_sweep_host: bad arguments")
+    return src, acc[:n - 1]
+
+
+def swap_sweep_device(ctx, logL, temps, seed, sweep, mode=0):
+    """The sweep as the device sampler computes it (thresholds in parallel, run starts by pointer doubling; mode 1: the sequential
+    fallback) on the given ladder: (src, accepted), identical to swap_sweep_host's."""
+    from .engine import load_library
+    logL, temps = _f64(logL), _f64(temps)
+    n = logL.size
+    src = np.empty(n, dtype=np.int32)
+    acc = np.zeros(max(n - 1, 1), dtype=np.int32)
+    lib = load_library()
+    rc = lib.gwat_b200_swap_sweep_device(ctx._h, n, _p(logL), _p(temps), C.c_ulonglong(seed), C.c_longlong(sweep), int(mode),
+                                         src.ctypes.data_as(C.POINTER(C.c_int)), acc.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise GwatB200Error(rc, lib.gwat_b200_last_error(ctx._h).decode())
     return src, acc[:n - 1]
 
 

@@ -102,6 +102,12 @@ int gwat_b200_sampler_set_state(gwat_b200_sampler *s, const double *positions, c
 int gwat_b200_swap_sweep_host(int chain_N_total, const double *logL, const double *temps, unsigned long long seed, long long sweep,
                               int *src, int *accepted /* [chain_N_total - 1] or NULL */);
 void gwat_b200_sampler_uniform(unsigned long long seed, unsigned long long step, unsigned chain, unsigned purpose, double *out2);
+/* The same sweep (chain_swap, src/mcmc_sampler_internals.cpp:1086-1184) computed the way the sampler computes it on the device --
+ * thresholds for all pairs at once, the starts of the carried runs by pointer doubling -- on caller-supplied inputs; mode 0: as the
+ * sampler runs it, mode 1: its sequential fallback.  Exists so that tests can hold the device sweep against the host one on
+ * adversarial ladders; identical decisions for any input. */
+int gwat_b200_swap_sweep_device(gwat_b200_ctx *ctx, int chain_N_total, const double *logL, const double *temps, unsigned long long seed,
+                                long long sweep, int mode, int *src, int *accepted /* [chain_N_total - 1] or NULL */);
 /*
  * One ladder sharded over the GPUs of a box, one process (rank) per GPU -- the split BASELINE.json's north_star names: "only the
  * PT swap step exchanges per-walker log-likelihoods and positions via NCCL allgather over NVLink".

@@ -289,3 +289,47 @@ def test_bad_arguments_fail_loudly(ctx):
         smp.Sampler(ctx, wl.method, np.ones(4), bad, prior, wl.gmst, wl.T_segment)
     with pytest.raises(smp.GwatB200Error):
         smp.Sampler(ctx, wl.method, np.ones(4), init[:, :10], prior, wl.gmst, wl.T_segment)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,ens", [(2, 1), (3, 1), (17, 1), (4096, 8), (32768, 8), (36000, 8), (36001, 1), (100003, 7)])
+def test_device_swap_sweep_equals_host_sweep(n, ens):
+    """The run/pointer-doubling form of chain_swap's sweep (src/mcmc_sampler_internals.cpp:1086-1184) that the sampler runs on the
+    device makes the very decisions of the sequential one: random ladders (ensembles of `ens` rungs laid end to end), for the
+    shared-memory and the global-scratch sizes, and with the sequential fallback forced."""
+    from gw_analysis_tools_b200 import sampler as smp
+    from gw_analysis_tools_b200.engine import Context
+    rng = np.random.default_rng(n + ens)
+    ctx = Context(0)
+    temps = np.tile(np.geomspace(1.0, 50.0, ens), n // ens + 1)[:n] if ens > 1 else np.geomspace(1.0, 1e3, n)
+    for trial, scale in enumerate([1.0, 30.0, 1e-3]):
+        ll = 1e4 + scale * rng.standard_normal(n)
+        src_h, acc_h = smp.swap_sweep_host(ll, temps, 1234 + trial, 7 + trial)
+        for mode in (0, 1):
+            src_d, acc_d = smp.swap_sweep_device(ctx, ll, temps, 1234 + trial, 7 + trial, mode)
+            assert np.array_equal(src_d, src_h) and np.array_equal(acc_d, acc_h)
+        assert sorted(src_h.tolist()) == list(range(n))  # a permutation
+
+
+@pytest.mark.gpu
+def test_device_swap_sweep_long_runs_fall_back():
+    """A state far below every other on a single ladder of increasing temperatures is carried to the top: one run of n - 1 pairs,
+    longer than the parallel scan follows -- the CTA falls back to the sequential walk and still agrees."""
+    from gw_analysis_tools_b200 import sampler as smp
+    from gw_analysis_tools_b200.engine import Context
+    ctx = Context(0)
+    for n in (300, 5000, 40000):
+        temps = np.geomspace(1.0, 1e6, n)
+        ll = 1e4 + np.random.default_rng(n).standard_normal(n)
+        ll[0] = -1e12
+        src_h, acc_h = smp.swap_sweep_host(ll, temps, 99, 3)
+        assert acc_h.sum() == n - 1 and src_h[n - 1] == 0
+        src_d, acc_d = smp.swap_sweep_device(ctx, ll, temps, 99, 3, 0)
+        assert np.array_equal(src_d, src_h) and np.array_equal(acc_d, acc_h)
+        # ... and a ladder whose runs stop just short of / just past the cap
+        ll2 = ll.copy()
+        ll2[0] = 1e4
+        ll2[n // 2] = -1e12
+        src_h, acc_h = smp.swap_sweep_host(ll2, temps, 99, 3)
+        src_d, acc_d = smp.swap_sweep_device(ctx, ll2, temps, 99, 3, 0)
+        assert np.array_equal(src_d, src_h) and np.array_equal(acc_d, acc_h)
