@@ -60,11 +60,14 @@ def run_under_bench(args, ctx, world, rank, local, dist, ClockSampler):
         dist.broadcast_object_list(ids, src=0)
         s.attach_ranks(ids[0], rank, world)
     s.run(max(args.warmup, 10))
+    # the clock sampler starts BEFORE the barrier: NVML start-up takes 10-20 ms and differs between ranks, and a rank that enters
+    # the timed call late makes every other rank wait for it at the first swap exchange (seen as 1.5-2 ms "per sweep" on 8 GPUs)
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     t0 = time.perf_counter()
     s.run(args.steps)
     pos, ll, lp = s.state()
@@ -77,8 +80,10 @@ def run_under_bench(args, ctx, world, rank, local, dist, ClockSampler):
         dist.all_gather(allv, t)
         per_rank = [[float(x) for x in a] for a in allv]
         dev_ms, wall, swap_ms = (max(col) for col in zip(*per_rank))
+        swap_ms_min = min(r[2] for r in per_rank)
     else:
         per_rank = [[dev_ms, wall, swap_ms]]
+        swap_ms_min = swap_ms
     ct, _ = s.counters()
     if rank != 0:
         if world > 1:
@@ -98,10 +103,12 @@ def run_under_bench(args, ctx, world, rank, local, dist, ClockSampler):
             "e2e": {"value": C_total * args.steps / wall, "unit": "chain-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": C_loc * (P + 2) * 8 / args.steps, "ms_per_step": wall / args.steps * 1e3,
                     "note": "wall clock around gwat_b200_sampler_run + one device->host read of the ensemble state per call"},
-            "swap_exchange": {"ms_per_sweep": swap_ms, "sweeps": int(sweeps), "bytes_per_rank_per_sweep": C_loc * (P + 2) * 8,
+            "swap_exchange": {"ms_per_sweep": swap_ms, "ms_per_sweep_last_arriving_rank": swap_ms_min, "sweeps": int(sweeps), "bytes_per_rank_per_sweep": C_loc * (P + 2) * 8,
                               "bytes_gathered_per_sweep": C_total * (P + 2) * 8,
                               "share_of_step_time": swap_ms * sweeps / dev_ms if dev_ms > 0 else None,
-                              "what": "pack + ncclAllGather + threshold/sequential sweep over the whole ladder + take, CUDA events on the sampler's stream" if world > 1 else "thresholds + sequential sweep + counters + moves on the device, no exchange"},
+                              "what": ("pack + ncclAllGather + thresholds + run/pointer-doubling sweep over the whole ladder + take, CUDA events on the sampler's stream; "
+                                       "ms_per_sweep = max over ranks and includes waiting for the slowest rank to reach the collective, the rank that arrives last "
+                                       "waits for nobody: its time is the exchange itself") if world > 1 else "thresholds + run/pointer-doubling sweep + counters + moves on the device, no exchange"},
             "per_rank": {"device_ms": [r[0] for r in per_rank], "wall_s": [r[1] for r in per_rank], "swap_ms_per_sweep": [r[2] for r in per_rank]},
             "gpu_launches": int(launches), "clocks": clocks,
             "accept_fraction": float(ct["step_accept"].sum() / max(1, ct["step_accept"].sum() + ct["step_reject"].sum())),
