@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	const bool bc = (i == 8 && v[8] > .25 - epsilon);  // eta at its upper boundary: one-sided difference (:369-383)
 	if (k == 0) {
 		scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
-		eta_bc[(size_t)sidx * dim + i] = bc ? 1 : 0;
+		// bit 0: one-sided difference; bit 1: the stencil points of RA, DEC, psi do NOT share their intrinsic part -- IMRPhenomPv2 with
+		// equatorial_orientation, where the sky position moves theta_JN through the derived inclination
+		eta_bc[(size_t)sidx * dim + i] = (bc ? 1 : 0) | ((Fam::base == BASE_P && orig.equatorial_orientation) ? 2 : 0);
 	}
 	const double step = (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
 	const double base = v[i];
@@ -429,6 +431,8 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 	else v[i] = base + step;
 	gwat_b200_source sp;
 	repack_fisher_point(v, orig, fp.rp, sp);
+	// fourier_detector_response_equatorial derives incl_angle and psi from (theta_l, phi_l) at every stencil point (src/waveform_util.cpp:947-949)
+	if (sp.equatorial_orientation) transform_orientation_coords(sp, Fam::base == BASE_P);
 	Network net;
 	net.D = fp.nd;
 	net.horizon_mode = 0;
@@ -554,8 +558,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_fisher_deriv(const WalkerCoef *
 	}
 	// parameters 0..2 are RA, DEC (or sin DEC) and psi in every parameterisation (src/fisher.cpp:46-66): the intrinsic part of
 	// the source, and with it everything in PolParts, is bit-identical at all stencil points
-	const bool shared_parts = (int)(blockIdx.y % dim) < 3;
-	const bool bc = eta_bc[blockIdx.y] != 0;
+	const bool shared_parts = (int)(blockIdx.y % dim) < 3 && (eta_bc[blockIdx.y] & 2) == 0;
+	const bool bc = (eta_bc[blockIdx.y] & 1) != 0;
 	const double sc = scale[blockIdx.y];
 	// several tiles per CTA: the 4 coefficient blocks (5.7 KB) are staged once for 1024 bins instead of once per 256
 	for (int t = tile0; t < tile1; t++) {
@@ -651,8 +655,8 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 	}
 	const WalkerCoef *w = w_all + param * npts;
 	const double *tc_s = tc_all + param * npts * nd;
-	const bool shared_parts = param < 3;  // RA, DEC (or sin DEC), psi: see k_fisher_deriv
-	const bool bc = eta_bc[(size_t)s * dim + param] != 0;
+	const bool shared_parts = param < 3 && (eta_bc[(size_t)s * dim + param] & 2) == 0;  // RA, DEC (or sin DEC), psi: see k_fisher_deriv
+	const bool bc = (eta_bc[(size_t)s * dim + param] & 1) != 0;
 	const double sc = scale[(size_t)s * dim + param];
 	// inner-product ownership: thread -> (pair, slice); the threads of a warp hold consecutive pairs of one slice, so the
 	// reads of a k-row are broadcasts out of one or two 128-byte lines
@@ -1769,6 +1773,10 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 		ctx->last_ms = ms;
 		return GWAT_B200_OK;
 	}
+	for (int i = 0; i < S; i++)
+		if (sources[i].horizon_coord)
+			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED,
+			            "fisher_numerical_batch: horizon_coord sources (the parameter set holds RA and DEC, which a detector-frame response does not read)");
 	// the modification layout is taken from the first source (all sources of a batch share it, as they share the method)
 	gwat_b200_mod mod;
 	gwat_b200_mod_init(&mod);

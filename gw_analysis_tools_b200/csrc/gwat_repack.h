@@ -237,20 +237,23 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 		return;
 	}
 	v[0] = in.RA;
-	v[2] = in.psi;
+	// equatorial_orientation: the direction of L (theta_l, phi_l) takes the place of (psi, iota) (src/fisher.cpp:1851-1858,1887-1894,
+	// 1916-1923,1944-1951); incl_angle and psi of a stencil point are then derived by transform_orientation_coords (gwat_orient.h)
+	const bool eq = in.equatorial_orientation != 0;
+	v[2] = eq ? in.theta_l : in.psi;
 	v[4] = in.phiRef;
 	v[5] = in.tc;
 	v[8] = eta_from(in.mass1, in.mass2);
 	if (plan.mcmc) {
 		v[1] = sm::sin(in.DEC);
-		v[3] = sm::cos(in.incl_angle);
+		v[3] = eq ? in.phi_l : sm::cos(in.incl_angle);
 		v[6] = sm::log(in.Luminosity_Distance);
 		v[7] = sm::log(chirpmass_from(in.mass1, in.mass2));
 	} else {
 		logfac[6] = 1;
 		logfac[7] = 1;
 		v[1] = in.DEC;
-		v[3] = in.incl_angle;
+		v[3] = eq ? in.phi_l : in.incl_angle;
 		v[6] = in.Luminosity_Distance;
 		v[7] = chirpmass_from(in.mass1, in.mass2);
 	}
@@ -335,7 +338,12 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		return;
 	}
 	s.RA = v[0];
-	s.psi = v[2];
+	const bool eq = s.equatorial_orientation != 0;  // (src/fisher.cpp:2180-2187, 2242-2249, 2268-2275, 2293-2300)
+	if (eq) {
+		s.theta_l = v[2];
+		s.phi_l = v[3];
+	} else
+		s.psi = v[2];
 	s.phiRef = v[4];
 	s.tc = v[5];
 	if (plan.mcmc) {
@@ -343,13 +351,13 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		s.mass2 = mass2_of(sm::exp(v[7]), v[8]);
 		s.Luminosity_Distance = sm::exp(v[6]);
 		s.DEC = sm::asin(v[1]);
-		s.incl_angle = sm::acos(v[3]);
+		if (!eq) s.incl_angle = sm::acos(v[3]);
 	} else {
 		s.mass1 = mass1_of(v[7], v[8]);
 		s.mass2 = mass2_of(v[7], v[8]);
 		s.Luminosity_Distance = v[6];
 		s.DEC = v[1];
-		s.incl_angle = v[3];
+		if (!eq) s.incl_angle = v[3];
 	}
 	if (plan.pv2) {
 		if (plan.mcmc) {

@@ -288,6 +288,7 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 			if (!(step > 0 && bc)) v[i] = v0[i] + step;
 			gwat_b200_source sp;
 			repack_fisher_point(v, *src, plan, sp);
+			if (sp.equatorial_orientation) transform_orientation_coords(sp, Fam::base == BASE_P);
 			double tshift = 0;
 			if (!same) {
 				const double dtoa = dtoa_between(ref_row + 9, det_row + 9, sp.RA, sp.DEC, sp.gmst);

@@ -104,3 +104,81 @@ def test_snr_with_equatorial_orientation(ctx, oracle, gold):
     for k, s in enumerate(srcs):
         ref = oracle.calculate_snr("aLIGO_analytic", "Hanford", method, s, f)
         assert abs(got[k] - ref) <= 1e-9 * ref, k
+
+
+# ---- Fisher matrices with the direction of L as parameters (src/fisher.cpp:1851-1858, 2180-2187): theta_l and phi_l take the
+# slots of psi and iota, and every stencil point derives incl_angle and psi again (src/waveform_util.cpp:947-949)
+FISHER_EQ_CASES = [c for c in cases.FISHER_CASES if c[0] in ("F_D", "F_D_mcmc", "F_P_mcmc", "F_P_red")]
+
+
+def _fisher_eq_source(name, seed):
+    gold_fisher = np.load(os.path.join(GOLD, "fisher_v1.npz"))
+    rng = np.random.default_rng(seed)
+    s = cases.source_from_bytes(gold_fisher[name + "/src"])
+    s.equatorial_orientation = 1
+    s.theta_l = rng.uniform(0.3, 2.8)
+    s.phi_l = rng.uniform(0, 2 * np.pi)
+    s.incl_angle = 9.0  # garbage on purpose: neither may be read
+    s.psi = 9.0
+    return s
+
+
+def _fisher_eq_check(got, oracle, method, src, f, psd2, dim, order, di):
+    import fisher_noise
+    ref = oracle.fisher_numerical_batch(method, [src], cases.DETECTORS[:2], f, psd2, dim, order=order, detector_index=di)[0]
+    floor = fisher_noise.reference_self_difference(oracle, method, [src], cases.DETECTORS[:2], f, psd2, dim, order,
+                                                   detector_index=di, runs=2)[0]
+    nerr = fisher_noise.normalised_error(got, ref)
+    assert np.all(np.isfinite(got))
+    assert np.median(nerr) <= 1e-6, (method, order, di, np.median(nerr))
+    assert nerr.max() <= max(1e-6, fisher_noise.FACTOR * floor), (method, order, di, nerr.max(), floor)
+    # the orientation rows are really those of (theta_l, phi_l): the same source with the flag off gives another matrix
+    plain = abi.Source()
+    C.memmove(C.addressof(plain), C.addressof(src), C.sizeof(src))
+    plain.equatorial_orientation = 0
+    plain.incl_angle, plain.psi = 0.7, 0.4
+    other = oracle.fisher_numerical_batch(method, [plain], cases.DETECTORS[:2], f, psd2, dim, order=order, detector_index=di)[0]
+    assert fisher_noise.normalised_error(other, ref).max() > 1e-2
+
+
+@pytest.mark.parametrize("case", FISHER_EQ_CASES, ids=[c[0] for c in FISHER_EQ_CASES])
+def test_fisher_with_equatorial_orientation_host_math(hh, oracle, case):
+    name, method, kw, dim = case
+    f = cases.grid(cases.FISHER_GRID)
+    psd = workloads.aligo_analytic_psd(f)
+    src = _fisher_eq_source(name, 7)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for order, di in ((2, 0), (4, 1)):
+        out = np.zeros((dim, dim))
+        assert hh.hh_fisher_numerical(method.encode(), cases.DETECTORS[di].encode(), cases.DETECTORS[0].encode(), dim, order, C.byref(src),
+                                      p(f), f.size, p(psd), p(out)) == 0
+        _fisher_eq_check(out, oracle, method, src, f, np.tile(psd, (2, 1)), dim, order, di)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FISHER_EQ_CASES, ids=[c[0] for c in FISHER_EQ_CASES])
+def test_fisher_with_equatorial_orientation(ctx, oracle, case):
+    name, method, kw, dim = case
+    f = cases.grid(cases.FISHER_GRID)
+    psd2 = np.tile(workloads.aligo_analytic_psd(f), (2, 1))
+    ctx.set_network(cases.DETECTORS[:2], f, psd2)
+    src = _fisher_eq_source(name, 7)
+    for order, di in ((2, 0), (4, 1), (4, -1)):
+        got = ctx.fisher_numerical_batch(method, [src], dim, order=order, detector_index=di)[0]
+        _fisher_eq_check(got, oracle, method, src, f, psd2, dim, order, di)
+    # a batch may mix both conventions (the flag is per source)
+    plain = cases.source_from_bytes(np.load(os.path.join(GOLD, "fisher_v1.npz"))[name + "/src"])
+    both = ctx.fisher_numerical_batch(method, [src, plain, src], dim, order=4, detector_index=1)
+    alone = ctx.fisher_numerical_batch(method, [plain], dim, order=4, detector_index=1)[0]
+    assert np.array_equal(both[1], alone) and np.array_equal(both[0], both[2])
+
+
+@pytest.mark.gpu
+def test_fisher_refuses_horizon_coordinates(ctx):
+    f = cases.grid(cases.FISHER_GRID)
+    ctx.set_network(cases.DETECTORS[:2], f, np.tile(workloads.aligo_analytic_psd(f), (2, 1)))
+    s = _fisher_eq_source("F_D", 1)
+    s.equatorial_orientation = 0
+    s.horizon_coord = 1
+    with pytest.raises(Exception, match="horizon_coord"):
+        ctx.fisher_numerical_batch("IMRPhenomD", [s], 11)
