@@ -389,6 +389,9 @@ void gwat_b200_dropin_bind_mcmc(std::complex<double> **data, double **noise, dou
 	session().net_key = 0;
 }
 
+// mcmc_intrinsic of this unit (PTMCMC_method_specific_prep sets the reference's copy from the dimension, src/mcmc_gw.cpp:1880-1985):
+// the wrappers then take the tc/phic-maximised likelihood and the sky-averaged Fisher of the 4 (+ modifications) / 8 parameter sets
+void gwat_b200_dropin_set_intrinsic(int intrinsic) { mcmc_intrinsic = intrinsic != 0; }
 void gwat_b200_dropin_set_segment_duration(double T) { session().T_override = T; }
 void gwat_b200_dropin_invalidate(void) { session().net_key = 0; }
 const char *gwat_b200_dropin_last_error(void)
@@ -405,7 +408,7 @@ double MCMC_likelihood_wrapper(double *param, mcmc_data_interface *interface, vo
 {
 	MCMC_user_param *user_param = (MCMC_user_param *)parameters;
 	const int dimension = interface->max_dim;
-	if (mcmc_intrinsic || !mcmc_data || !same_length(mcmc_data_length, mcmc_num_detectors)) return kNaN;  // the maximised branches: gwat_b200_loglike_maximized_batch
+	if (!mcmc_data || !same_length(mcmc_data_length, mcmc_num_detectors)) return kNaN;
 	Session &S = session();
 	std::lock_guard<std::mutex> lock(S.mu);
 	gwat_b200::Engine *e = engine_locked(S);
@@ -418,8 +421,14 @@ double MCMC_likelihood_wrapper(double *param, mcmc_data_interface *interface, vo
 	bool ok;
 	to_mod(mcmc_mod_struct, mod, ok);
 	if (!ok) return kNaN;
-	const double T = segment_duration(S, mcmc_frequencies, mcmc_num_detectors);
 	double ll = kNaN;
+	if (mcmc_intrinsic) {
+		// the tc/phic-maximised branches (src/mcmc_gw.cpp:2611-2722): the intrinsic sampling set, repacked with sky_average, through the
+		// batched cuFFT likelihood (GAUSSLEG grids have no time axis: the C ABI refuses them, and so does this call)
+		if (gwat_b200_loglike_maximized_mcmc_batch(e->ctx(), mcmc_generation_method.c_str(), &mod, dimension, 1, param, mcmc_gmst, &ll) != 0) return kNaN;
+		return ll;
+	}
+	const double T = segment_duration(S, mcmc_frequencies, mcmc_num_detectors);
 	if (gwat_b200_loglike_mcmc_batch(e->ctx(), mcmc_generation_method.c_str(), &mod, dimension, 1, param, mcmc_gmst, T, &ll) != 0) return kNaN;
 	return ll;
 }
@@ -443,6 +452,14 @@ void MCMC_fisher_wrapper(double *param, double **output, mcmc_data_interface *in
 	to_mod(mcmc_mod_struct, mod, ok);
 	if (!ok) return;
 	std::vector<double> F((size_t)dimension * dimension), vals(dimension), vecs((size_t)dimension * dimension);
+	if (mcmc_intrinsic) {  // sky-averaged records: amplitude / phase derivatives per detector PSD, intrinsic transformations (:2163-2179)
+		if (gwat_b200_mcmc_fisher_intrinsic_batch(e->ctx(), mcmc_generation_method.c_str(), &mod, dimension, mcmc_deriv_order, 1, param, mcmc_gmst,
+		                                          F.data()) != 0)
+			return;
+		for (int j = 0; j < dimension; j++)
+			for (int k = 0; k < dimension; k++) output[j][k] = F[(size_t)j * dimension + k];
+		return;
+	}
 	// sum over detectors of fisher_numerical("MCMC_" + method) + MCMC_fisher_transformations (:2298-2316)
 	if (gwat_b200_mcmc_fisher_batch(e->ctx(), mcmc_generation_method.c_str(), &mod, dimension, mcmc_deriv_order, 1, param, mcmc_gmst, F.data(),
 	                                vals.data(), vecs.data()) != 0)

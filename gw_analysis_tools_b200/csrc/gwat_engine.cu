@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(128) k_fisher_setup(const gwat_b200_source *__
 		scale[(size_t)sidx * dim + i] = logfac[i] ? v[i] : 1.0;
 		// bit 0: one-sided difference; bit 1: the stencil points of RA, DEC, psi do NOT share their intrinsic part -- IMRPhenomPv2 with
 		// equatorial_orientation, where the sky position moves theta_JN through the derived inclination
-		eta_bc[(size_t)sidx * dim + i] = (bc ? 1 : 0) | ((Fam::base == BASE_P && orig.equatorial_orientation) ? 2 : 0);
+		// ... and the intrinsic set (fp.rp.sky), whose first parameters are ln Mc, eta, a1
+		eta_bc[(size_t)sidx * dim + i] = (bc ? 1 : 0) | (((Fam::base == BASE_P && orig.equatorial_orientation) || fp.rp.sky) ? 2 : 0);
 	}
 	const double step = (k == 0) ? epsilon : (k == 1) ? -epsilon : (k == 2) ? 2 * epsilon : -2 * epsilon;
 	const double base = v[i];
@@ -920,7 +921,9 @@ GridPtrs grid_ptrs(const gwat_b200_ctx *c, const double *zero_data = nullptr)
 	return g;
 }
 
-int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, RepackPlan &plan)
+// intrinsic: the sets of the reference's tc/phic-maximised runs (PTMCMC_method_specific_prep, src/mcmc_gw.cpp:1880-1985): ln Mc, eta and the
+// spins (4 for the IMRPhenomD family, + 1 or 2 tidal parameters for NRT; 8 for IMRPhenomPv2), then the modifications
+int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, RepackPlan &plan, bool intrinsic = false)
 {
 	std::memset(&plan, 0, sizeof(plan));
 	plan.dimension = dimension;
@@ -937,7 +940,8 @@ int make_plan(const MethodDesc &desc, const gwat_b200_mod *mod, int dimension, R
 	}
 	if (dimension < 1 || dimension > GWAT_B200_MAX_DIM) return -1;
 	if (plan.mod.ppE_Nmod < 0 || plan.mod.ppE_Nmod > GWAT_B200_MAX_MOD) return -1;
-	int base = desc.pv2 ? 15 : 11;
+	int base = intrinsic ? (desc.pv2 ? 8 : 4) : (desc.pv2 ? 15 : 11);
+	plan.sky = intrinsic ? 1 : 0;
 	if (desc.nrt && !desc.pv2) base += plan.mod.tidal_love ? 1 : 2;
 	int mods = 0;
 	if (plan.ppe) mods = plan.mod.ppE_Nmod;
@@ -1278,7 +1282,7 @@ __global__ void k_repack_only(const double *__restrict__ params, int W, RepackPl
 	if (w >= W) return;
 	gwat_b200_source s;
 	repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, 0.0, s);
-	s.tc = -s.tc;
+	if (!plan.sky) s.tc = -s.tc;
 	out[w] = s;
 }
 
@@ -1652,8 +1656,20 @@ int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *me
 	return response_common(ctx, method, d0, 1, 0, W, sources, resp_re, resp_im);
 }
 
+static int repack_mcmc_any(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W, const double *params, double gmst,
+                           gwat_b200_source *sources, bool intrinsic);
 int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
                                 const double *params, double gmst, gwat_b200_source *sources)
+{
+	return repack_mcmc_any(ctx, method, mod, dimension, W, params, gmst, sources, false);
+}
+int gwat_b200_repack_mcmc_intrinsic_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                                          const double *params, double gmst, gwat_b200_source *sources)
+{
+	return repack_mcmc_any(ctx, method, mod, dimension, W, params, gmst, sources, true);
+}
+static int repack_mcmc_any(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W, const double *params, double gmst,
+                           gwat_b200_source *sources, bool intrinsic)
 {
 	if (!ctx) return GWAT_B200_ERR_ARG;
 	if (W < 0 || (W > 0 && (!params || !sources))) return fail(ctx, GWAT_B200_ERR_ARG, "repack_mcmc_batch: NULL array");
@@ -1662,7 +1678,7 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	if (parse_method(method, desc) != 0 || desc.mcmc)
 		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
 	RepackPlan plan;
-	if (make_plan(desc, mod, dimension, plan) != 0)
+	if (make_plan(desc, mod, dimension, plan, intrinsic) != 0)
 		return fail(ctx, GWAT_B200_ERR_ARG, "repack_mcmc_batch: dimension does not match the method and modification struct");
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1676,6 +1692,55 @@ int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gw
 	CUDA_TRY(ctx, cudaGetLastError());
 	CUDA_TRY(ctx, cudaMemcpyAsync(sources, ctx->d_src, sizeof(gwat_b200_source) * W, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return GWAT_B200_OK;
+}
+
+// MCMC_fisher_wrapper in an intrinsic run (src/mcmc_gw.cpp:2229-2330): per detector fisher_numerical("MCMC_" + method) of the record
+// MCMC_prep_params + repack_parameters build (sky_average: the amplitude / phase branch, one detector's PSD each), summed, then the
+// intrinsic branch of MCMC_fisher_transformations (:2163-2179: the prior terms REPLACE the diagonal entries of eta and the spins)
+// and the dCS / EdGB unit factor (:2182-2193).
+int gwat_b200_mcmc_fisher_intrinsic_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int order, int W,
+                                          const double *params, double gmst, double *fisher)
+{
+	if (int rc = check_ready(ctx, false)) return rc;
+	if (W < 0 || (W > 0 && (!params || !fisher))) return fail(ctx, GWAT_B200_ERR_ARG, "mcmc_fisher_intrinsic_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc)
+		return fail(ctx, GWAT_B200_ERR_METHOD, std::string("unknown generation_method: ") + (method ? method : "(null)"));
+	std::vector<gwat_b200_source> src((size_t)W);
+	if (int rc = gwat_b200_repack_mcmc_intrinsic_batch(ctx, method, mod, dimension, W, params, gmst, src.data())) return rc;
+	const std::string m = std::string("MCMC_") + method;
+	const size_t dd = (size_t)dimension * dimension;
+	std::vector<double> part((size_t)W * dd);
+	std::fill(fisher, fisher + (size_t)W * dd, 0.0);
+	const int D = ctx->D;
+	for (int d = 0; d < D; d++) {
+		if (int rc = gwat_b200_fisher_numerical_batch(ctx, m.c_str(), d, 0, dimension, order, W, src.data(), part.data())) return rc;
+		for (size_t i = 0; i < (size_t)W * dd; i++) fisher[i] += part[i];
+	}
+	const bool alpha_fix = theory_alpha_units(desc.theory);
+	for (int w = 0; w < W; w++) {
+		double *F = fisher + (size_t)w * dd;
+		F[1 * dimension + 1] = 1. / (.25);
+		F[2 * dimension + 2] = 1. / (4);
+		F[3 * dimension + 3] = 1. / (4);
+		if (desc.pv2) {
+			F[4 * dimension + 4] = 1. / (4);
+			F[5 * dimension + 5] = 1. / (4);
+			F[6 * dimension + 6] = 1. / (4 * GWAT_PI * GWAT_PI);
+			F[7 * dimension + 7] = 1. / (4 * GWAT_PI * GWAT_PI);
+		}
+		if (alpha_fix) {
+			const int base = dimension - src[w].Nmod;
+			double factor = 4 * std::pow(src[w].betappe[0], 3. / 4.);  // temp_params[base]: alpha^2 in s^4 after the unit change
+			factor *= 1000 / GWAT_C_SI;
+			for (int i = 0; i < dimension; i++) {
+				F[base * dimension + i] *= factor;
+				F[i * dimension + base] *= factor;
+			}
+		}
+	}
 	return GWAT_B200_OK;
 }
 
@@ -1723,7 +1788,11 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 		any_sky = any_sky || sources[i].sky_average != 0;
 		all_sky = all_sky && sources[i].sky_average != 0;
 	}
-	if (any_sky) {
+	// A sky-averaged IMRPhenomPv2 record is not differentiated through amplitude and phase (the reference's test is for "IMRPhenomD",
+	// src/fisher.cpp:183): its "MCMC_" set -- the 8 intrinsic parameters, everything else at the constants of repack_parameters
+	// (:2308-2352) -- takes the response branch below.
+	const bool pv2_intrinsic = any_sky && all_sky && desc.pv2 && desc.mcmc;
+	if (any_sky && !pv2_intrinsic) {
 		// sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): the IMRPhenomD carrier in the 7-parameter set, followed by
 		// the ppE betas (ppE_IMRPhenomD_*, and the theories mapped onto them) or the gIMR deviations; one detector's PSD
 		if (!all_sky) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: sky-averaged and pointed sources in one batch");
@@ -1731,18 +1800,27 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 		int mods = 0;
 		if (ppe) mods = sources[0].Nmod;
 		else if (gimr) mods = sources[0].Nmod_phi + sources[0].Nmod_sigma + sources[0].Nmod_beta + sources[0].Nmod_alpha;
-		if (desc.pv2 || desc.mcmc)
-			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED, "fisher_numerical_batch: sky-averaged Fishers exist for the IMRPhenomD family only (as in the reference)");
+		if (desc.pv2)
+			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED,
+			            "fisher_numerical_batch: sky-averaged Fishers of amplitude and phase exist for the IMRPhenomD family only (the reference prints "
+			            "\"not supported\" for the physical IMRPhenomPv2 set, src/fisher.cpp:1993; pass \"MCMC_IMRPhenomPv2\" and dimension 8 for the intrinsic set)");
 		if (desc.nrt)
 			return fail(ctx, GWAT_B200_ERR_UNSUPPORTED,
-			            "fisher_numerical_batch: the reference's sky-averaged NRT layout puts ln(tidal) on top of ln(eta) (src/fisher.cpp:2061-2078); not built");
-		if (mods < 0 || mods > GWAT_B200_MAX_MOD || dimension != 7 + mods)
-			return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: a sky-averaged Fisher has 7 parameters plus the sources' modifications");
+			            desc.mcmc ? "fisher_numerical_batch: sky-averaged NRT Fishers: the reference's construct_phase reads the NRTidal spin/quadrupole "
+			                        "coefficients before anything has set them (they are assigned in construct_waveform only, src/IMRPhenomD_NRT.cpp:596-608); not built"
+			                      : "fisher_numerical_batch: the reference's sky-averaged NRT layout puts ln(tidal) on top of ln(eta) (src/fisher.cpp:2061-2078); not built");
+		// "MCMC_" + method: the intrinsic set ln Mc, eta, chi1, chi2 (src/fisher.cpp:2000-2013) instead of the seven
+		const int nbase = desc.mcmc ? 4 : 7;
+		if (mods < 0 || mods > GWAT_B200_MAX_MOD || dimension != nbase + mods)
+			return fail(ctx, GWAT_B200_ERR_ARG,
+			            desc.mcmc ? "fisher_numerical_batch: a sky-averaged MCMC_ Fisher has 4 parameters plus the sources' modifications"
+			                      : "fisher_numerical_batch: a sky-averaged Fisher has 7 parameters plus the sources' modifications");
 		if (detector_index < 0) return fail(ctx, GWAT_B200_ERR_ARG, "fisher_numerical_batch: a sky-averaged Fisher needs one detector's PSD");
 		FisherPlan fp;
 		std::memset(&fp, 0, sizeof(fp));
 		fp.rp.dimension = dimension;
 		fp.rp.sky = 1;
+		fp.rp.mcmc = desc.mcmc;
 		fp.rp.ppe = ppe;
 		fp.rp.gimr = gimr;
 		fp.npts = order == 4 ? 4 : 2;
@@ -1795,9 +1873,10 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *method, int
 	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
 	plan.gimr = desc.gimr && !plan.ppe;
 	plan.mcmc = desc.mcmc;
+	plan.sky = pv2_intrinsic ? 1 : 0;
 	plan.mod = mod;
 	{
-		int base = desc.pv2 ? (desc.mcmc ? 15 : 13) : 11;
+		int base = pv2_intrinsic ? 8 : desc.pv2 ? (desc.mcmc ? 15 : 13) : 11;
 		if (desc.nrt && !desc.pv2) base += mod.tidal_love ? 1 : 2;
 		int mods = 0;
 		if (plan.ppe) mods = mod.ppE_Nmod;

@@ -254,6 +254,19 @@ extern "C" int gwat_b200_loglike_maximized_batch(gwat_b200_ctx *ctx, const char 
 	return GWAT_B200_OK;
 }
 
+// The intrinsic branch of MCMC_likelihood_wrapper (src/mcmc_gw.cpp:2569-2722) for W sampling vectors of the intrinsic sets:
+// MCMC_prep_params with mcmc_intrinsic -> repack_parameters("MCMC_" + method, sky_average) -> the maximised likelihood above.
+extern "C" int gwat_b200_loglike_maximized_mcmc_batch(gwat_b200_ctx *ctx, const char *method, const gwat_b200_mod *mod, int dimension, int W,
+                                                      const double *params, double gmst, double *logL)
+{
+	if (!ctx) return GWAT_B200_ERR_ARG;
+	if (W < 0 || (W > 0 && (!params || !logL))) return gwat_internal::set_error(ctx, GWAT_B200_ERR_ARG, "loglike_maximized_mcmc_batch: NULL array");
+	if (W == 0) return GWAT_B200_OK;
+	std::vector<gwat_b200_source> src((size_t)W);
+	if (int rc = gwat_b200_repack_mcmc_intrinsic_batch(ctx, method, mod, dimension, W, params, gmst, src.data())) return rc;
+	return gwat_b200_loglike_maximized_batch(ctx, method, W, src.data(), logL);
+}
+
 // match(data1, data2, SN, frequencies, length) of the reference (src/waveform_util.cpp:41-89; gwatpy: match_py): the overlap of two
 // frequency-domain series maximised over a relative time shift, 4 max_t |IFFT(conj(d1) d2 / S)| df / (||d1|| ||d2||), with the norms
 // from data_snr (Simpson's rule, delta_f = f[1] - f[0]).  The inverse transform is cuFFT's (FFTW_BACKWARD in the reference).

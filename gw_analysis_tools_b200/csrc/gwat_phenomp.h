@@ -484,12 +484,12 @@ GWAT_HD void walker_setup(const gwat_b200_source &src, const Network &net, const
 			dc.gb = dc.Fcross * w.cfac;
 		}
 	}
-	// options of the reference that are outside this path are refused loudly (NaN), never silently approximated:
-	// sky-averaged amplitudes and the wall-clock-seeded tidal_love_error draw
-	// (sky-averaged amplitudes are accepted only from the sky-averaged Fisher path, which uses amplitude and phase alone).
+	// an option of the reference that is outside this path is refused loudly (NaN), never silently approximated: the wall-clock-seeded
+	// tidal_love_error draw.  sky_average changes the amplitude prefactor A0 and nothing else in the reference's waveform path
+	// (populate_source_parameters, src/util.cpp:1024-1025) -- the records of the intrinsic samplers carry it (src/mcmc_gw.cpp:2494).
 	// equatorial_orientation / horizon_coord are handled where the reference handles them (gwat_orient.h) and ignored elsewhere.
-	if ((src.sky_average && !allow_sky_average) || (Fam::nrt && src.tidal_love_error))
-		w.d.A0 = NAN;
+	(void)allow_sky_average;
+	if (Fam::nrt && src.tidal_love_error) w.d.A0 = NAN;
 	w.valid = 1;
 }
 

@@ -24,6 +24,9 @@ struct RepackPlan {
 	int alpha_unit_fix; // dCS/EdGB: entry [base] is sqrt(alpha) in km -> alpha^2 in s^4 (src/mcmc_gw.cpp:2560-2565)
 	int mcmc;           // "MCMC_" parameterisation (sin DEC, cos iota, ln DL, ln Mc); else the physical one
 	int sky;            // sky-averaged IMRPhenomD set: ln A0, phic, tc, ln Mc, ln eta, chi_s, chi_a (src/fisher.cpp:40, 2015-2032), then the modifications
+	                    // sky && mcmc: the INTRINSIC sampling sets of the reference's tc/phic-maximised runs ("MCMC_" + method with
+	                    // sky_average): ln Mc, eta, chi1, chi2 [, ln tidal_s | ln tidal1, ln tidal2] (src/fisher.cpp:2000-2013, 2061-2078)
+	                    // or, IMRPhenomPv2, ln Mc, eta, a1, a2, cos tilt1, cos tilt2, phi1, phi2 (:1968-1990), then the modifications
 	gwat_b200_mod mod;
 };
 
@@ -88,11 +91,12 @@ GWAT_HD void repack_tails(const double *v, const RepackPlan &plan, gwat_b200_sou
 {
 	const int dim = plan.dimension;
 	if (plan.nrt && !plan.pv2) {
+		const int at = (plan.sky && plan.mcmc) ? 4 : 11;  // the intrinsic set keeps them behind chi2 (src/fisher.cpp:2420-2431)
 		if (s.tidal_love) {
-			s.tidal_s = sm::exp(v[11]);
+			s.tidal_s = sm::exp(v[at]);
 		} else {
-			s.tidal1 = sm::exp(v[11]);
-			s.tidal2 = sm::exp(v[12]);
+			s.tidal1 = sm::exp(v[at]);
+			s.tidal2 = sm::exp(v[at + 1]);
 		}
 	}
 	if (plan.ppe) {
@@ -133,13 +137,45 @@ GWAT_HD void apply_mod_options(const RepackPlan &plan, gwat_b200_source &s)
 	}
 }
 
+// repack_parameters, "MCMC_" branches with sky_average = true (src/fisher.cpp:2308-2376): the physical part of the intrinsic sets.
+// Everything the set does not hold is a constant of the reference's choosing (the maximised likelihoods override most of them).
+GWAT_HD void repack_intrinsic_physical(const double *v, bool pv2, gwat_b200_source &s)
+{
+	s.mass1 = mass1_of(sm::exp(v[0]), v[1]);
+	s.mass2 = mass2_of(sm::exp(v[0]), v[1]);
+	if (pv2) {
+		const double th1 = clamped_acos(v[4]), th2 = clamped_acos(v[5]);
+		// transform_sph_cart (src/util.cpp:1909-1914)
+		s.spin1[0] = v[2] * sm::sin(th1) * sm::cos(v[6]);
+		s.spin1[1] = v[2] * sm::sin(th1) * sm::sin(v[6]);
+		s.spin1[2] = v[2] * sm::cos(th1);
+		s.spin2[0] = v[3] * sm::sin(th2) * sm::cos(v[7]);
+		s.spin2[1] = v[3] * sm::sin(th2) * sm::sin(v[7]);
+		s.spin2[2] = v[3] * sm::cos(th2);
+		s.tc = 0;
+		s.phiRef = 0;
+		s.RA = 0;
+		s.DEC = 0;
+		s.psi = 0;
+		s.incl_angle = GWAT_PI / 4.;
+		s.Luminosity_Distance = 100;
+	} else {
+		s.Luminosity_Distance = 1000;
+		s.spin1[2] = v[2];
+		s.spin2[2] = v[3];
+		s.phiRef = 0;
+		s.tc = 0;
+		s.incl_angle = 0;
+	}
+}
+
 // One walker of MCMC_likelihood_wrapper's parameter handling: param[dimension] -> record with tc = T_segment - tc.
 GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, double gmst, double T_segment,
                                 gwat_b200_source &s)
 {
 	source_defaults(s);
 	// MCMC_prep_params
-	s.sky_average = 0;
+	s.sky_average = plan.sky ? 1 : 0;  // mcmc_intrinsic (src/mcmc_gw.cpp:2494)
 	s.f_ref = 20;
 	s.shift_time = 1;
 	s.shift_phase = 1;
@@ -153,6 +189,11 @@ GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, dou
 		const int base = plan.dimension - plan.mod.ppE_Nmod;
 		const double x = v[base] / (GWAT_C_SI / 1000.);
 		v[base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
+	}
+	if (plan.sky) {  // the intrinsic sets: no T_segment (the maximised likelihoods set tc themselves, src/mcmc_gw.cpp:2613-2619)
+		repack_intrinsic_physical(v, plan.pv2 != 0, s);
+		repack_tails(v, plan, s);
+		return;
 	}
 	// repack_parameters, "MCMC_" branch, sky_average = false
 	s.mass1 = mass1_of(sm::exp(v[7]), v[8]);
@@ -224,6 +265,33 @@ GWAT_HD void unpack_fisher(const gwat_b200_source &in, const RepackPlan &plan, d
 {
 	const int dim = plan.dimension;
 	for (int i = 0; i < dim; i++) logfac[i] = 0;
+	if (plan.sky && plan.mcmc) {  // the intrinsic sets (src/fisher.cpp:1968-1990, 2000-2013, 2061-2078): no logarithmic factors
+		v[0] = sm::log(chirpmass_from(in.mass1, in.mass2));
+		v[1] = eta_from(in.mass1, in.mass2);
+		if (plan.pv2) {
+			double s1[3], s2[3];
+			cart_to_sph(in.spin1, s1);
+			cart_to_sph(in.spin2, s2);
+			v[2] = s1[0];
+			v[3] = s2[0];
+			v[4] = sm::cos(s1[1]);
+			v[5] = sm::cos(s2[1]);
+			v[6] = s1[2];
+			v[7] = s2[2];
+		} else {
+			v[2] = in.spin1[2];
+			v[3] = in.spin2[2];
+			if (plan.nrt) {
+				if (in.tidal_love) v[4] = sm::log(in.tidal_s);
+				else {
+					v[4] = sm::log(in.tidal1);
+					v[5] = sm::log(in.tidal2);
+				}
+			}
+		}
+		unpack_fisher_mods(in, plan, v);
+		return;
+	}
 	if (plan.sky) {  // src/fisher.cpp:2015-2032
 		logfac[0] = logfac[3] = logfac[4] = 1;
 		v[3] = chirpmass_from(in.mass1, in.mass2);
@@ -326,6 +394,11 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		}
 	}
 	// repack_parameters
+	if (plan.sky && plan.mcmc) {  // src/fisher.cpp:2308-2376
+		repack_intrinsic_physical(v, plan.pv2 != 0, s);
+		repack_tails(v, plan, s);
+		return;
+	}
 	if (plan.sky) {  // src/fisher.cpp:2379-2393
 		s.mass1 = mass1_of(v[3], v[4]);
 		s.mass2 = mass2_of(v[3], v[4]);

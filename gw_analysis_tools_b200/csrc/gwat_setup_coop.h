@@ -89,7 +89,7 @@ GWAT_HD void setup_step1(int role, const gwat_b200_source &s, const Network &net
 		}
 		r.w.pad_ = 0;
 		// options of the reference that are outside this path are refused loudly (NaN), never silently approximated (walker_setup)
-		r.refused = (s.sky_average || (Fam::nrt && s.tidal_love_error)) ? 1 : 0;
+		r.refused = (Fam::nrt && s.tidal_love_error) ? 1 : 0;
 	} else {
 		populate_source(s, q);
 		phenompv2_param_transform(q, (s.chip + 1) > 1e-10);

@@ -19,10 +19,10 @@ _lib = None
 EXPORTS = [
     "gwat_b200_abi_version", "gwat_b200_cosmology_index", "gwat_b200_transform_orientation_coords", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
     "gwat_b200_ctx_destroy", "gwat_b200_last_error", "gwat_b200_set_network", "gwat_b200_loglike_mcmc_batch",
-    "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_loglike_maximized_batch",
+    "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_loglike_maximized_batch", "gwat_b200_loglike_maximized_mcmc_batch",
     "gwat_b200_fourier_waveform_batch", "gwat_b200_fourier_amplitude_phase_batch",
     "gwat_b200_coherent_response_batch", "gwat_b200_fourier_detector_response_batch",
-    "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_antenna_batch",
+    "gwat_b200_fisher_numerical_batch", "gwat_b200_repack_mcmc_batch", "gwat_b200_repack_mcmc_intrinsic_batch", "gwat_b200_antenna_batch",
     "gwat_b200_snr_batch", "gwat_b200_populate_noise", "gwat_b200_losc_prepare", "gwat_b200_gps_to_gmst_radian",
     "gwat_b200_queue_create", "gwat_b200_queue_destroy", "gwat_b200_queue_loglike", "gwat_b200_queue_stats",
     "gwat_b200_gauss_legendre_grid", "gwat_b200_log_likelihood_internal", "gwat_b200_match", "gwat_b200_method_info", "gwat_b200_measure_fp64_peak", "gwat_b200_set_kernel_timing", "gwat_b200_launch_count", "gwat_b200_last_kernel_ms", "gwat_b200_last_active_bins",
@@ -269,6 +269,24 @@ class Context:
         out = (abi.Source * W)()
         self._check(self._lib.gwat_b200_repack_mcmc_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
                                                           P, W, _p(params), C.c_double(gmst), out))
+        return out
+
+    def repack_mcmc_intrinsic_batch(self, method, params, gmst, mod=None):
+        """Sampling vectors of the intrinsic sets (ln Mc, eta, spins [, tidal] [, modifications]) -> physical records."""
+        params = _f64(params)
+        W, P = params.shape
+        out = (abi.Source * W)()
+        self._check(self._lib.gwat_b200_repack_mcmc_intrinsic_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                                                    P, W, _p(params), C.c_double(gmst), out))
+        return out
+
+    def loglike_maximized_mcmc_batch(self, method, params, gmst, mod=None):
+        """The intrinsic branch of MCMC_likelihood_wrapper for W sampling vectors: tc/phic-maximised log-likelihoods."""
+        params = _f64(params)
+        W, P = params.shape
+        out = np.empty(W)
+        self._check(self._lib.gwat_b200_loglike_maximized_mcmc_batch(self._h, method.encode(), C.byref(mod) if mod is not None else None,
+                                                                     P, W, _p(params), C.c_double(gmst), _p(out)))
         return out
 
     def antenna_batch(self, RA, DEC, psi, gmst):

@@ -18,7 +18,7 @@ EXPORTS = [
     "gwat_b200_prior_init", "gwat_b200_sampler_options_init", "gwat_b200_sampler_create", "gwat_b200_sampler_destroy",
     "gwat_b200_sampler_run", "gwat_b200_sampler_state", "gwat_b200_sampler_counters", "gwat_b200_sampler_cold",
     "gwat_b200_sampler_fisher_state", "gwat_b200_sampler_set_state", "gwat_b200_swap_sweep_host", "gwat_b200_swap_sweep_device", "gwat_b200_sampler_uniform",
-    "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch",
+    "gwat_b200_sampler_last_ms", "gwat_b200_sampler_last_launches", "gwat_b200_log_prior_batch", "gwat_b200_mcmc_fisher_batch", "gwat_b200_mcmc_fisher_intrinsic_batch",
     "gwat_b200_nccl_unique_id", "gwat_b200_sampler_attach_ranks", "gwat_b200_sampler_last_swap_ms", "gwat_b200_sampler_last_sweeps",
     "gwat_b200_update_temperatures", "gwat_b200_sampler_set_temperatures", "gwat_b200_sampler_temperatures",
     "gwat_b200_sampler_last_swap_accepts", "gwat_b200_sampler_dynamic_temperatures",
@@ -106,6 +106,16 @@ def mcmc_fisher_batch(ctx, method, params, gmst, order=4, mod=None):
     ctx._check(ctx._lib.gwat_b200_mcmc_fisher_batch(ctx._h, method.encode(), C.byref(mod) if mod is not None else None, P, int(order), W,
                                                     _p(params), C.c_double(gmst), _p(F), _p(vals), _p(vecs)))
     return F, vals, vecs
+
+
+def mcmc_fisher_intrinsic_batch(ctx, method, params, gmst, order=4, mod=None):
+    """``MCMC_fisher_wrapper`` of an intrinsic run (ln Mc, eta, chi1, chi2 [, modifications]): sum over detectors + transformations."""
+    params = _f64(params)
+    W, P = params.shape
+    F = np.empty((W, P, P))
+    ctx._check(ctx._lib.gwat_b200_mcmc_fisher_intrinsic_batch(ctx._h, method.encode(), C.byref(mod) if mod is not None else None, P, int(order), W,
+                                                              _p(params), C.c_double(gmst), _p(F)))
+    return F
 
 
 class Sampler:

@@ -244,6 +244,14 @@ int gwat_b200_gauss_legendre_grid(double f_lower, double f_upper, int n, int log
 int gwat_b200_loglike_maximized_batch(gwat_b200_ctx *ctx, const char *generation_method, int W, const gwat_b200_source *sources,
                                       double *logL);
 
+/* The same for W sampling vectors of the reference's INTRINSIC sets, as the intrinsic branch of MCMC_likelihood_wrapper evaluates
+ * one of them (src/mcmc_gw.cpp:2569-2722): MCMC_prep_params with mcmc_intrinsic (sky_average = true, :2494), then
+ * repack_parameters("MCMC_" + method) (src/fisher.cpp:2308-2376, 2420-2431).  The sets (PTMCMC_method_specific_prep,
+ * src/mcmc_gw.cpp:1880-1985): ln chirpmass, eta, chi1, chi2 for the IMRPhenomD family (+ ln tidal_s, or ln tidal1, ln tidal2, for
+ * IMRPhenomD_NRT); ln chirpmass, eta, a1, a2, cos tilt1, cos tilt2, phi1, phi2 for IMRPhenomPv2; then the modifications. */
+int gwat_b200_loglike_maximized_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension,
+                                           int W, const double *params, double gmst, double *logL);
+
 /*
  * W evaluations of fourier_waveform<double> (src/waveform_generator.cpp:104-294) on the context's grid.
  * Outputs are split real/imag like fourier_waveform_py (src/gwatpy_wrapping.cpp), shape [W*L] row-major; any may be NULL.
@@ -294,7 +302,11 @@ int gwat_b200_fourier_detector_response_batch(gwat_b200_ctx *ctx, const char *ge
  * With detector_index < 0 the matrices of all detectors are summed (MCMC_fisher_wrapper, src/mcmc_gw.cpp:2298-2312).
  * Sources with sky_average set take the sky-averaged branch of calculate_derivatives (src/fisher.cpp:183-338): "IMRPhenomD",
  * dimension 7 (ln A0, phic, tc, ln chirpmass, ln eta, chi_s, chi_a), derivatives of amplitude and phase, detector_index >= 0
- * naming the PSD; all sources of a batch must agree on the flag.
+ * naming the PSD; all sources of a batch must agree on the flag.  "MCMC_" + method with sky-averaged sources: the INTRINSIC sets of the
+ * tc/phic-maximised samplers -- ln chirpmass, eta, chi1, chi2 (+ modifications) through the same amplitude / phase branch
+ * (src/fisher.cpp:2000-2013, 2360-2376); "MCMC_IMRPhenomPv2", dimension 8 (ln chirpmass, eta, a1, a2, cos tilt1, cos tilt2, phi1, phi2)
+ * through the response branch with the extrinsic members at the reference's constants (:1968-1990, 2308-2352; detector_index as for
+ * pointed sources).  gwat_b200_repack_mcmc_intrinsic_batch makes such records from sampling vectors.
  */
 int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *generation_method, int detector_index,
                                      int reference_index, int dimension, int order, int S,
@@ -306,6 +318,10 @@ int gwat_b200_fisher_numerical_batch(gwat_b200_ctx *ctx, const char *generation_
  * change of MCMC_prep_params (src/mcmc_gw.cpp:2560-2565): sampling vectors -> physical records. */
 int gwat_b200_repack_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
                                 int dimension, int W, const double *params, double gmst, gwat_b200_source *sources);
+/* ... and for the intrinsic sets (see gwat_b200_loglike_maximized_mcmc_batch): sky_average = 1 in the records, the members the set
+ * does not hold at the constants of the reference (D_L = 1000 Mpc, or 100 Mpc and iota = pi/4 for IMRPhenomPv2; src/fisher.cpp:2308-2376). */
+int gwat_b200_repack_mcmc_intrinsic_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
+                                          int dimension, int W, const double *params, double gmst, gwat_b200_source *sources);
 
 /* Antenna patterns and time-of-arrival differences for W sky positions:
  * detector_response_functions_equatorial (src/detector_util.cpp:1037) and DTOA_DETECTOR (:677) for every detector of the

@@ -194,6 +194,12 @@ int gwat_b200_log_prior_batch(gwat_b200_ctx *ctx, const char *generation_method,
 int gwat_b200_mcmc_fisher_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension,
                                 int order, int W, const double *params, double gmst, double *fisher, double *eigenvalues,
                                 double *eigenvectors);
+/* MCMC_fisher_wrapper of an INTRINSIC run (mcmc_intrinsic: the sets of gwat_b200_loglike_maximized_mcmc_batch; src/mcmc_gw.cpp:2229-2330):
+ * sum over the network's detectors of fisher_numerical("MCMC_" + method) on the sky-averaged record, then the intrinsic branch of
+ * MCMC_fisher_transformations (:2163-2179) and the dCS / EdGB unit factor.  IMRPhenomD family (with ppE / gIMR modifications) and
+ * IMRPhenomPv2; the NRT sets are refused with the reason (see gwat_b200_fisher_numerical_batch).  fisher[W][dim][dim]. */
+int gwat_b200_mcmc_fisher_intrinsic_batch(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod, int dimension,
+                                          int order, int W, const double *params, double gmst, double *fisher);
 
 #ifdef __cplusplus
 }

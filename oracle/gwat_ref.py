@@ -234,6 +234,16 @@ def mcmc_prep_params(method, mod, param, src):
     return temp, out
 
 
+def repack_mcmc_intrinsic(method, mod, params, gmst):
+    """MCMC_prep_params (mcmc_intrinsic) + repack_parameters("MCMC_" + method) for the intrinsic sampling sets (src/fisher.cpp:2308-2376)."""
+    params = _f64(params)
+    W, P = params.shape
+    out = (abi.Source * W)()
+    m = mod if mod is not None else abi.mod_defaults()
+    lib().oracle_ref_repack_mcmc_intrinsic(method.encode(), C.byref(m), P, W, _p(params), C.c_double(gmst), out)
+    return out
+
+
 def pack_local_mod_structure(min_dim, max_dim, status, waveform_extended, full_mod):
     """pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476): (counts[4], indices[4][MAX_MOD]) of the local structure."""
     status = np.ascontiguousarray(status, dtype=np.int32)

@@ -636,6 +636,28 @@ int oracle_ref_mcmc_prep_params(const char *method, const gwat_b200_mod *mod, in
 	return (int)local.size();
 }
 
+// The parameter handling of MCMC_likelihood_wrapper / MCMC_fisher_wrapper in an INTRINSIC run (src/mcmc_gw.cpp:2576-2581, 2236-2241):
+// MCMC_prep_params with mcmc_intrinsic set (sky_average = true, :2494; the flag is a static of the reference's translation unit, so it
+// is applied here on the object MCMC_prep_params returns) -> repack_parameters("MCMC_" + method) (src/fisher.cpp:2308-2376, 2420-2431).
+int oracle_ref_repack_mcmc_intrinsic(const char *method, const gwat_b200_mod *mod, int dimension, int W, const double *params, double gmst,
+                                     gwat_b200_source *sources_out)
+{
+	ModBox mb;
+	to_mod_struct(mod, mb);
+	const std::string m(method);
+	for (int w = 0; w < W; w++) {
+		std::vector<double> temp(dimension);
+		gen_params_base<double> gp;
+		std::string local_gen = MCMC_prep_params(const_cast<double *>(params) + (size_t)w * dimension, temp.data(), &gp, dimension, m, &mb.m);
+		gp.sky_average = true;
+		gp.gmst = gmst;
+		repack_parameters(temp.data(), &gp, "MCMC_" + m, dimension, (gen_params_base<double> *)NULL);
+		from_gen_params(gp, sources_out[w]);
+		free_prepped(gp, local_gen, mb.m);
+	}
+	return 0;
+}
+
 // pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476); counts[4] and idx[4][GWAT_B200_MAX_MOD] receive the local structure.
 int oracle_ref_pack_local_mod_structure(int min_dim, int max_dim, const int *status, const char *waveform_extended, const gwat_b200_mod *full,
                                         int *counts, int *idx)

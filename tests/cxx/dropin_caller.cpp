@@ -24,6 +24,8 @@ extern "C" void gwat_b200_dropin_bind_mcmc(std::complex<double> **data, double *
                                            std::string *detectors, int num_detectors, const char *generation_method,
                                            MCMC_modification_struct *mod_struct, double gmst, int deriv_order) __attribute__((weak));
 
+extern "C" void gwat_b200_dropin_set_intrinsic(int intrinsic) __attribute__((weak));
+
 static void put(const char *name, double v) { std::printf("%s %.17g\n", name, v); }
 static void put(const std::string &name, int i, double v) { std::printf("%s[%d] %.17g\n", name.c_str(), i, v); }
 
@@ -188,6 +190,75 @@ int main()
 		put("fisher_sum_offdiag_7_8", F[7][8]);
 		deallocate_2D_array(F, dim, dim);
 		deallocate_2D_array(Ft, dim, dim);
+	}
+
+	// ---- an INTRINSIC run (ln Mc, eta, chi1, chi2): the wrappers' maximised likelihood and sky-averaged Fisher ------------------
+	{
+		const int dim = 4;
+		double chirp = calculate_chirpmass(36.4, 29.3), eta = calculate_eta(36.4, 29.3);
+		double param[dim] = {std::log(chirp * 1.0003), eta, .3, .2};
+		MCMC_modification_struct mod;
+		double temp[dim];
+		// the chain of reference calls MCMC_likelihood_wrapper stands for when mcmc_intrinsic is set (src/mcmc_gw.cpp:2576-2640, with
+		// mcmc_save_waveform: one response for all detectors); the flag is a static of the reference's own translation unit, so its
+		// one effect on the record -- sky_average (:2494) -- is applied here
+		gen_params_base<double> g;
+		std::string local = MCMC_prep_params(param, temp, &g, dim, "IMRPhenomD", &mod);
+		g.sky_average = true;
+		g.gmst = 2.1;
+		repack_parameters(temp, &g, "MCMC_" + std::string("IMRPhenomD"), dim, (gen_params_base<double> *)NULL);
+		gen_params_base<double> gl = g;
+		gl.theta = 0;
+		gl.phi = 0;
+		gl.psi = 0;
+		gl.phiRef = 1;
+		gl.f_ref = 10;
+		gl.incl_angle = 0;
+		gl.tc = 1;
+		{
+			fftw_outline plan;
+			allocate_FFTW_mem_forward(&plan, L);
+			std::vector<std::complex<double>> response(L);
+			fourier_detector_response_horizon(freq[0], L, response.data(), detectors[0], local, &gl);
+			double ll = 0;
+			for (int d = 0; d < D; d++) ll += maximized_Log_Likelihood_aligned_spin_internal(data[d], psd[d], freq[d], response.data(), (size_t)L, &plan);
+			deallocate_FFTW_mem(&plan);
+			put("intrinsic_callback_chain", ll);
+		}
+		double **F = allocate_2D_array(dim, dim), **Ft = allocate_2D_array(dim, dim);
+		for (int i = 0; i < dim; i++)
+			for (int j = 0; j < dim; j++) F[i][j] = 0;
+		for (int d = 0; d < D; d++) {
+			fisher_numerical(freq[d], L, "MCMC_IMRPhenomD", detectors[d], detectors[0], Ft, dim, &g, 4, NULL, NULL, psd[d]);
+			for (int i = 0; i < dim; i++)
+				for (int j = 0; j < dim; j++) F[i][j] += Ft[i][j];
+		}
+		{
+			mcmc_data_interface iface2;
+			iface2.min_dim = iface2.max_dim = dim;
+			MCMC_fisher_transformations(temp, F, dim, "IMRPhenomD", true, &iface2, &mod, NULL);
+		}
+		for (int i = 0; i < dim; i++) put("intrinsic_fisher_sum_diag", i, F[i][i]);
+		put("intrinsic_fisher_sum_offdiag_0_1", F[0][1]);
+		deallocate_2D_array(F, dim, dim);
+		deallocate_2D_array(Ft, dim, dim);
+		if (gwat_b200_dropin_bind_mcmc && gwat_b200_dropin_set_intrinsic) {
+			gwat_b200_dropin_bind_mcmc(data, psd, freq, lengths, detectors, D, "IMRPhenomD", &mod, 2.1, 4);
+			gwat_b200_dropin_set_intrinsic(1);
+			mcmc_data_interface iface;
+			iface.min_dim = iface.max_dim = dim;
+			iface.chain_id = 0;
+			iface.chain_number = 1;
+			iface.nested_model_number = 0;
+			MCMC_user_param up;
+			put("MCMC_likelihood_wrapper_intrinsic", MCMC_likelihood_wrapper(param, &iface, (void *)&up));
+			double **Fw = allocate_2D_array(dim, dim);
+			MCMC_fisher_wrapper(param, Fw, &iface, (void *)&up);
+			for (int i = 0; i < dim; i++) put("MCMC_fisher_wrapper_intrinsic_diag", i, Fw[i][i]);
+			put("MCMC_fisher_wrapper_intrinsic_offdiag_0_1", Fw[0][1]);
+			deallocate_2D_array(Fw, dim, dim);
+			gwat_b200_dropin_set_intrinsic(0);
+		}
 	}
 
 	// ---- fisher_numerical, physical parameterisation, one detector --------------------------------------------------------

@@ -197,6 +197,27 @@ extern "C" int hh_transform_orientation(const char *method, gwat_b200_source *sr
 	return 0;
 }
 
+// sampling vector of an intrinsic set -> physical record (repack_mcmc_walker with plan.sky), as k_repack_only runs it
+extern "C" int hh_repack_mcmc_intrinsic(const char *method, const gwat_b200_mod *mod, int dimension, const double *param, double gmst,
+                                        gwat_b200_source *out)
+{
+	MethodDesc desc;
+	if (parse_method(method, desc) != 0 || desc.mcmc) return -1;
+	RepackPlan plan;
+	std::memset(&plan, 0, sizeof(plan));
+	plan.dimension = dimension;
+	plan.pv2 = desc.pv2;
+	plan.nrt = desc.nrt;
+	plan.ppe = desc.ppe || desc.theory != THEORY_NONE;
+	plan.gimr = desc.gimr && !plan.ppe;
+	plan.alpha_unit_fix = theory_alpha_units(desc.theory);
+	plan.mcmc = 1;
+	plan.sky = 1;
+	plan.mod = *mod;
+	repack_mcmc_walker(param, plan, gmst, 0.0, *out);
+	return 0;
+}
+
 // which words of WalkerCoef each family defines (the others stay poisoned in both flows): offsets for the test
 extern "C" void hh_walkercoef_layout(int *out)
 {
@@ -230,9 +251,14 @@ int fisher_t(int theory, bool mcmc, const MethodDesc &desc, const gwat_b200_sour
 	const int npts = order == 4 ? 4 : 2;
 	const size_t L = g.f.size();
 	const double eps = 1e-8;
-	if (src->sky_average) {
+	if (src->sky_average && Fam::base == BASE_P) {
+		// the reference's amplitude / phase branch is for the IMRPhenomD family (src/fisher.cpp:183); a sky-averaged IMRPhenomPv2 record takes the
+		// response branch below with the 8 intrinsic parameters (the "MCMC_" set; the physical one prints "not supported", :1993)
+		if (!mcmc) return -5;
+		plan.sky = 1;
+	} else if (src->sky_average) {
 		// sky-averaged branch (src/fisher.cpp:183-338): amplitude / phase derivatives in the 7-parameter set
-		if (Fam::base != BASE_D || Fam::nrt) return -5;
+		if (Fam::nrt) return -5;
 		plan.sky = 1;
 		double v0s[GWAT_B200_MAX_DIM];
 		int logf_[GWAT_B200_MAX_DIM];

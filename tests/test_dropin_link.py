@@ -97,3 +97,11 @@ def test_same_program_same_numbers_through_the_gpu_library():
     for i in range(11):
         a, b = ref["fisher_sum_diag[%d]" % i], got["MCMC_fisher_wrapper_diag[%d]" % i]
         assert abs(a - b) <= 2e-5 * abs(a), (i, a, b)
+    # ... and in an intrinsic run: the tc/phic-maximised likelihood and the sky-averaged Fisher of the 4-parameter set
+    assert abs(got["MCMC_likelihood_wrapper_intrinsic"] - ref["intrinsic_callback_chain"]) <= 1e-9 * abs(ref["intrinsic_callback_chain"])
+    for i in range(4):
+        a, b = ref["intrinsic_fisher_sum_diag[%d]" % i], got["MCMC_fisher_wrapper_intrinsic_diag[%d]" % i]
+        assert abs(a - b) <= 2e-5 * abs(a), (i, a, b)
+    assert ref["intrinsic_fisher_sum_diag[1]"] == 4.0 and got["MCMC_fisher_wrapper_intrinsic_diag[2]"] == 0.25  # the prior terms replace these
+    # (entry (1,1) is a prior term now, so the ln Mc - eta entry is compared with itself: the two are 90 % correlated)
+    assert abs(ref["intrinsic_fisher_sum_offdiag_0_1"] - got["MCMC_fisher_wrapper_intrinsic_offdiag_0_1"]) <= 2e-5 * abs(ref["intrinsic_fisher_sum_offdiag_0_1"])
