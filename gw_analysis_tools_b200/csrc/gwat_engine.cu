@@ -467,16 +467,25 @@ __device__ __forceinline__ bool fisher_deriv_bin(const WalkerCoef *w, const doub
 {
 	const double epsilon = 1e-8;
 	PolParts pp[4];
+	// The "above the cutoff" and "invalid record" flags of the points live in two bit masks: as members of pp[] the compiler kept them
+	// in LOCAL memory (byte loads and stores, one 32-byte sector each, 44 % of them missing L1: 5.5 GB of L2 traffic per 5000 sources
+	// and 5.5 % of the kernel's stall samples on the tests below; profiles/r02_j_*)
+	unsigned zero_mask = 0, invalid_mask = 0;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {  // (unrolled with a guard so that pp[] and r[] live in registers)
 		if (k >= npts) continue;
-		if (k > 0 && shared_parts) pp[k] = pp[0];
-		else polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
+		if (!w[k].valid) invalid_mask |= 1u << k;
+		if (k > 0 && shared_parts) {
+			pp[k] = pp[0];
+			zero_mask |= (zero_mask & 1u) << k;
+		} else {
+			polarization_parts<Fam>(w[k], f, hi, lo, lg, pp[k]);
+			if (pp[k].zero) zero_mask |= 1u << k;
+		}
+		pp[k].zero = false;  // (read through the mask from here on)
 	}
-	bool live = false;
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		if (k < npts) live = live || !w[k].valid || !pp[k].zero;
+	const unsigned all_points = (1u << npts) - 1u;
+	const bool live = ((invalid_mask | ~zero_mask) & all_points) != 0;
 	if (!live) {
 		for (int d = 0; d < nd; d++) store(d, cplx{0.0, 0.0});
 		return false;
@@ -486,8 +495,12 @@ __device__ __forceinline__ bool fisher_deriv_bin(const WalkerCoef *w, const doub
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			if (k >= npts) continue;
-			if (!w[k].valid) {
+			if ((invalid_mask >> k) & 1u) {
 				r[k] = cplx{NAN, NAN};
+				continue;
+			}
+			if ((zero_mask >> k) & 1u) {  // zero polarisations project to zero
+				r[k] = cplx{0.0, 0.0};
 				continue;
 			}
 			// (keeping each point's finished polarisations and re-finishing only when the time coefficient changes -- 8
@@ -660,7 +673,10 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 	const bool bc = (eta_bc[(size_t)s * dim + param] & 1) != 0;
 	const double sc = scale[(size_t)s * dim + param];
 	// inner-product ownership: thread -> (pair, slice); the threads of a warp hold consecutive pairs of one slice, so the
-	// reads of a k-row are broadcasts out of one or two 128-byte lines
+	// reads of a k-row are broadcasts out of one or two 128-byte lines.  (Measured and rejected in round 2, tools/gpu_runs/gpurun_r2_29/30/33:
+	// four accumulators per thread +1 %; 2 x 2 register blocks of pairs -- half the shared loads -- -1 %; the products of tile t - 1 formed
+	// by the warps of RA, DEC, psi while the others differentiate tile t: +-0.  The loop shows up with 17 % of the stall samples, but the
+	// other CTA of the SM fills those slots.)
 	const int gp = threadIdx.x % lay.npairs, gs = threadIdx.x / lay.npairs;
 	int pj = 0, pk = gp;
 	while (pk > pj) {
@@ -681,7 +697,7 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_fisher_fused(const WalkerCo
 		double *zrow = Zt + (size_t)param * lay.Kp;
 		auto store = [&](int d, const cplx &dv) {
 			// sqrt(w) on both factors of the product: w >= 0 (quadrature coefficient / PSD); bins of the last tile beyond L weigh 0
-			const double rw = in_grid ? sqrt(wq[(size_t)d * g.ld + bin]) : 0.0;
+			const double rw = in_grid ? wq[(size_t)d * g.ld + bin] : 0.0;  // (wq: the table of square roots)
 			zrow[(d * 2 + 0) * kFusedTileBins + lane] = in_grid ? rw * dv.re : 0.0;
 			zrow[(d * 2 + 1) * kFusedTileBins + lane] = in_grid ? rw * dv.im : 0.0;
 		};
@@ -1184,7 +1200,8 @@ int launch_fisher_fused(gwat_b200_ctx *ctx, const FisherPlan &fp, int ns, const 
 		CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));                              \
 		kern<<<ns, dim * 32, lay.bytes, st>>>(ctx->d_coef, ctx->d_tcoef, g, wq, fp.npts, fp.nd, dim, ctx->d_scale, ctx->d_bc, ctx->pref_fisher, d_out); \
 	} while (0)
-	if (dim <= 12) GWAT_FUSED_LAUNCH(12, 2);
+	static const bool wide = getenv("GWAT_B200_FISHER_WIDE") != nullptr;  // experiments only: 128 registers, one CTA per SM
+	if (dim <= 12 && !wide) GWAT_FUSED_LAUNCH(12, 2);
 	else GWAT_FUSED_LAUNCH(16, 1);
 #undef GWAT_FUSED_LAUNCH
 	return 0;
@@ -1215,7 +1232,8 @@ int fisher_chunk(gwat_b200_ctx *ctx, const MethodDesc &desc, FisherPlan &fp, int
 	                                                                                        ctx->d_scale, ctx->d_bc));
 	static const bool no_fused = getenv("GWAT_B200_FISHER_UNFUSED") != nullptr;  // experiments / A-B tests only
 	if (!no_fused && fisher_fused_fits(dim, fp.npts, nd)) {
-		GWAT_DISPATCH_FAMILY(desc, if (int rc = launch_fisher_fused<Fam>(ctx, fp, ns, g, wq_fisher_all + (size_t)d0 * ctx->ld, d_out, st)) return rc);
+		const double *rwq_fisher_all = ctx->d_net + 4 * (size_t)ctx->D * ctx->ld;  // sqrt(wq_fisher), see gwat_b200_set_network
+		GWAT_DISPATCH_FAMILY(desc, if (int rc = launch_fisher_fused<Fam>(ctx, fp, ns, g, rwq_fisher_all + (size_t)d0 * ctx->ld, d_out, st)) return rc);
 		ctx->launches += 2;
 		CUDA_TRY(ctx, cudaGetLastError());
 		return 0;
@@ -1436,7 +1454,7 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 		grid[3 * (size_t)ld + i] = in ? lg[i] : 0.0;
 	}
 	const size_t DL = (size_t)D * ld;
-	std::vector<double> netbuf(4 * DL, 0.0);
+	std::vector<double> netbuf(5 * DL, 0.0);
 	for (int d = 0; d < D; d++)
 		for (int i = 0; i < L; i++) {
 			const size_t k = (size_t)d * ld + i, kin = (size_t)d * L + i;
@@ -1447,6 +1465,8 @@ int gwat_b200_set_network(gwat_b200_ctx *ctx, int D, const char *const *detector
 			}
 			// the Fisher routines always integrate with Simpson's rule (src/fisher.cpp:128-131)
 			netbuf[3 * DL + k] = quadrature_coefficient(i, L, false, false, nullptr, f) / psd[kin];
+			// its square root, for the fused Fisher kernel (one factor on each side of the product; IEEE sqrt: the same bits as on the device)
+			netbuf[4 * DL + k] = std::sqrt(netbuf[3 * DL + k]);
 		}
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	if (ctx->d_grid) cudaFree(ctx->d_grid);
