@@ -127,7 +127,8 @@ __device__ __forceinline__ bool coef_is_finite(const WalkerCoef &w, int D, bool 
 // Per-walker setup, cooperative (gwat_setup_coop.h): one CTA sets up kSetupWalkers walkers, lane = walker, warp = role; the
 // finished records leave with coalesced stores.  params != NULL: sampling vectors (repack_mcmc_walker), else physical records.
 constexpr int kSetupWalkers = 32;
-constexpr size_t kSetupSmemBytes = sizeof(SetupRec) * kSetupWalkers;  // 49.6 KB: dynamic shared memory, opted in once per instantiation (setup_smem_opt_in)
+constexpr size_t kSetupSmemBytes = (sizeof(SetupRec) + sizeof(RepackHeavy)) * kSetupWalkers;  // 53 KB: dynamic shared memory, opted in once per instantiation (setup_smem_opt_in)
+static_assert(sizeof(RepackHeavy) % 16 == 8, "an odd number of doubles per record keeps lane-strided accesses free of bank conflicts");
 static_assert(kSetupSmemBytes <= 96 * 1024, "shared memory of k_setup");
 
 // kernel experiments only (-DGWAT_SETUP_PROFILE): clock64 stamps of lane 0 of every role of block 0
@@ -153,15 +154,26 @@ __global__ void __launch_bounds__(kSetupWalkers * setup_roles<Fam>()) k_setup(co
 	const int w = blockIdx.x * kSetupWalkers + lane;
 	const bool active = w < W;
 	SetupRec &r = recs[lane];
+	RepackHeavy *heavy = reinterpret_cast<RepackHeavy *>(setup_smem + sizeof(SetupRec) * kSetupWalkers);
 	const Tables t = device_tables();
 	gwat_b200_source s;
 	SetupCarry k;
 	GWAT_KSTAMP(0);
+	// step 0 (sampling vectors): the ~20 libm calls of the repack, a quarter per role (masses / distance and angles / spin 1 / spin 2);
+	// every role used to make all of them -- 20-25 k of the kernel's ~83 k cycles (profiles/r02_c_setup_roles_coop.json).  The
+	// assembly of the record from these values is cheap and stays with every role.
+	// IMRPhenomPv2 only (43.5 -> 39.5 us): the aligned-spin repack has 7 such calls, and splitting them costs more in the extra barrier
+	// and the second code stream than it saves (measured: 31.4 -> 33.0 us), so those families keep one copy of the repack for all roles
+	const bool split = kP && params && !plan.sky;
+	if (split) {
+		if (active) repack_heavy_part(role, params + (size_t)w * plan.dimension, plan, heavy[lane]);
+		__syncthreads();
+	}
 	if (active) {
-		// (ONE copy of the repack for all roles: the kernel is bound by instruction fetch, and a copy per role -- each keeping only
-		// what its role reads -- was measured 70 % slower: four code streams per SM instead of one shared one)
-		if (params) repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, T_segment, s);
-		else s = src_in[w];
+		if (params) {
+			if (split) repack_mcmc_assemble(params + (size_t)w * plan.dimension, plan, gmst, T_segment, heavy[lane], s);
+			else repack_mcmc_walker(params + (size_t)w * plan.dimension, plan, gmst, T_segment, s);
+		} else s = src_in[w];
 		setup_step1<Fam>(role, s, net, t, theory, k, r);
 		GWAT_KSTAMP(1);
 	}

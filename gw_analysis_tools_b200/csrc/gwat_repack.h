@@ -78,6 +78,16 @@ GWAT_HD double mass2_of(double chirpmass, double eta)
 	return 1. / 2 * (chirpmass / etapow - sqrt(1. - 4 * eta) * chirpmass / etapow);
 }
 
+// both at once: one exponent-3/5 power and one root instead of two of each (the expressions -- and so the bits -- are those of
+// mass1_of / mass2_of; in a latency-bound setup thread every libm call is ~1.3 k cycles)
+GWAT_HD void masses_of(double chirpmass, double eta, double &m1, double &m2)
+{
+	const double etapow = sm::pow(eta, 3. / 5);
+	const double a = chirpmass / etapow, b = sqrt(1. - 4 * eta) * chirpmass / etapow;
+	m1 = 1. / 2 * (a + b);
+	m2 = 1. / 2 * (a - b);
+}
+
 GWAT_HD double clamped_acos(double x)
 {
 	// "Fishers don't necessarily respect the bounds of acos" (src/fisher.cpp:2190-2213)
@@ -141,8 +151,7 @@ GWAT_HD void apply_mod_options(const RepackPlan &plan, gwat_b200_source &s)
 // Everything the set does not hold is a constant of the reference's choosing (the maximised likelihoods override most of them).
 GWAT_HD void repack_intrinsic_physical(const double *v, bool pv2, gwat_b200_source &s)
 {
-	s.mass1 = mass1_of(sm::exp(v[0]), v[1]);
-	s.mass2 = mass2_of(sm::exp(v[0]), v[1]);
+	masses_of(sm::exp(v[0]), v[1], s.mass1, s.mass2);
 	if (pv2) {
 		const double th1 = clamped_acos(v[4]), th2 = clamped_acos(v[5]);
 		// transform_sph_cart (src/util.cpp:1909-1914)
@@ -169,13 +178,44 @@ GWAT_HD void repack_intrinsic_physical(const double *v, bool pv2, gwat_b200_sour
 	}
 }
 
-// One walker of MCMC_likelihood_wrapper's parameter handling: param[dimension] -> record with tc = T_segment - tc.
-GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, double gmst, double T_segment,
-                                gwat_b200_source &s)
+// The transcendental part of the extrinsic repack below, cut into four independent PARTS so that the cooperative setup kernel can give
+// each to another warp (k_setup: the repack was 20-25 k of the kernel's ~83 k cycles, the same ~20 libm calls made by every role):
+//   part 0: the masses           part 1: distance, declination, inclination, NRT tidal parameters
+//   part 2: spin 1 (Pv2)         part 3: spin 2 (Pv2)
+// The expressions are the ones repack_mcmc_walker has always used (it now calls all four parts itself): same bits.
+struct RepackHeavy {
+	double mass1, mass2, DL, DEC, incl, spin1[3], spin2[3], tidal[2];
+};
+GWAT_HD void repack_heavy_part(int part, const double *v, const RepackPlan &plan, RepackHeavy &h)
+{
+	if (part == 0) {
+		masses_of(sm::exp(v[7]), v[8], h.mass1, h.mass2);
+	} else if (part == 1) {
+		h.DL = sm::exp(v[6]);
+		h.DEC = sm::asin(v[1]);
+		h.incl = sm::acos(v[3]);
+		if (plan.nrt && !plan.pv2) {  // repack_tails: tidal_s, or tidal1 and tidal2
+			h.tidal[0] = sm::exp(v[11]);
+			if (!plan.mod.tidal_love) h.tidal[1] = sm::exp(v[12]);
+		}
+	} else if (plan.pv2) {
+		// transform_sph_cart (src/util.cpp:1909-1914)
+		const int a = part == 2 ? 9 : 10, ct = part == 2 ? 11 : 12, ph = part == 2 ? 13 : 14;
+		double *sp = part == 2 ? h.spin1 : h.spin2;
+		const double th = clamped_acos(v[ct]);
+		sp[0] = v[a] * sm::sin(th) * sm::cos(v[ph]);
+		sp[1] = v[a] * sm::sin(th) * sm::sin(v[ph]);
+		sp[2] = v[a] * sm::cos(th);
+	}
+}
+
+// The rest of the extrinsic repack: flags, copies and the values of `h`.
+GWAT_HD void repack_mcmc_assemble(const double *param, const RepackPlan &plan, double gmst, double T_segment, const RepackHeavy &h,
+                                  gwat_b200_source &s)
 {
 	source_defaults(s);
 	// MCMC_prep_params
-	s.sky_average = plan.sky ? 1 : 0;  // mcmc_intrinsic (src/mcmc_gw.cpp:2494)
+	s.sky_average = 0;
 	s.f_ref = 20;
 	s.shift_time = 1;
 	s.shift_phase = 1;
@@ -183,44 +223,83 @@ GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, dou
 	s.equatorial_orientation = 0;
 	s.horizon_coord = 0;
 	apply_mod_options(plan, s);
-	double v[GWAT_B200_MAX_DIM];
-	for (int i = 0; i < plan.dimension; i++) v[i] = param[i];
-	if (plan.alpha_unit_fix) {
-		const int base = plan.dimension - plan.mod.ppE_Nmod;
-		const double x = v[base] / (GWAT_C_SI / 1000.);
-		v[base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
+	// repack_parameters, "MCMC_" branch, sky_average = false
+	s.mass1 = h.mass1;
+	s.mass2 = h.mass2;
+	s.Luminosity_Distance = h.DL;
+	s.RA = param[0];
+	s.DEC = h.DEC;
+	s.psi = param[2];
+	s.incl_angle = h.incl;
+	s.phiRef = param[4];
+	s.tc = param[5];
+	if (plan.pv2) {
+		for (int i = 0; i < 3; i++) {
+			s.spin1[i] = h.spin1[i];
+			s.spin2[i] = h.spin2[i];
+		}
+	} else {
+		s.spin1[2] = param[9];
+		s.spin2[2] = param[10];
 	}
+	if (plan.nrt && !plan.pv2) {
+		if (s.tidal_love) s.tidal_s = h.tidal[0];
+		else {
+			s.tidal1 = h.tidal[0];
+			s.tidal2 = h.tidal[1];
+		}
+	}
+	// the modification tails (repack_tails) with the dCS / EdGB unit change of MCMC_prep_params
+	const int dim = plan.dimension;
+	if (plan.ppe) {
+		const int base = dim - s.Nmod;
+		for (int i = 0; i < s.Nmod; i++) s.betappe[i] = param[base + i];
+		if (plan.alpha_unit_fix) {
+			const int ab = dim - plan.mod.ppE_Nmod;
+			const double x = param[ab] / (GWAT_C_SI / 1000.);
+			s.betappe[ab - base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
+		}
+	} else if (plan.gimr) {
+		const int mods = s.Nmod_phi + s.Nmod_sigma + s.Nmod_beta + s.Nmod_alpha;
+		int at = dim - mods;
+		for (int i = 0; i < s.Nmod_phi; i++) s.delta_phi[i] = param[at++];
+		for (int i = 0; i < s.Nmod_sigma; i++) s.delta_sigma[i] = param[at++];
+		for (int i = 0; i < s.Nmod_beta; i++) s.delta_beta[i] = param[at++];
+		for (int i = 0; i < s.Nmod_alpha; i++) s.delta_alpha[i] = param[at++];
+	}
+	// MCMC_likelihood_extrinsic: tc is measured back from the end of the segment (src/mcmc_gw.cpp:2467,2473)
+	s.tc = T_segment - s.tc;
+}
+
+// One walker of MCMC_likelihood_wrapper's parameter handling: param[dimension] -> record with tc = T_segment - tc.
+GWAT_HD void repack_mcmc_walker(const double *param, const RepackPlan &plan, double gmst, double T_segment,
+                                gwat_b200_source &s)
+{
 	if (plan.sky) {  // the intrinsic sets: no T_segment (the maximised likelihoods set tc themselves, src/mcmc_gw.cpp:2613-2619)
+		source_defaults(s);
+		// MCMC_prep_params
+		s.sky_average = 1;  // mcmc_intrinsic (src/mcmc_gw.cpp:2494)
+		s.f_ref = 20;
+		s.shift_time = 1;
+		s.shift_phase = 1;
+		s.gmst = gmst;
+		s.equatorial_orientation = 0;
+		s.horizon_coord = 0;
+		apply_mod_options(plan, s);
+		double v[GWAT_B200_MAX_DIM];
+		for (int i = 0; i < plan.dimension; i++) v[i] = param[i];
+		if (plan.alpha_unit_fix) {
+			const int base = plan.dimension - plan.mod.ppE_Nmod;
+			const double x = v[base] / (GWAT_C_SI / 1000.);
+			v[base] = ((x * x) * x) * x;  // pow_int(x, 4): sequential product (src/util.cpp:1585-1597)
+		}
 		repack_intrinsic_physical(v, plan.pv2 != 0, s);
 		repack_tails(v, plan, s);
 		return;
 	}
-	// repack_parameters, "MCMC_" branch, sky_average = false
-	s.mass1 = mass1_of(sm::exp(v[7]), v[8]);
-	s.mass2 = mass2_of(sm::exp(v[7]), v[8]);
-	s.Luminosity_Distance = sm::exp(v[6]);
-	s.RA = v[0];
-	s.DEC = sm::asin(v[1]);
-	s.psi = v[2];
-	s.incl_angle = sm::acos(v[3]);
-	s.phiRef = v[4];
-	s.tc = v[5];
-	if (plan.pv2) {
-		const double th1 = clamped_acos(v[11]), th2 = clamped_acos(v[12]);
-		// transform_sph_cart (src/util.cpp:1909-1914)
-		s.spin1[0] = v[9] * sm::sin(th1) * sm::cos(v[13]);
-		s.spin1[1] = v[9] * sm::sin(th1) * sm::sin(v[13]);
-		s.spin1[2] = v[9] * sm::cos(th1);
-		s.spin2[0] = v[10] * sm::sin(th2) * sm::cos(v[14]);
-		s.spin2[1] = v[10] * sm::sin(th2) * sm::sin(v[14]);
-		s.spin2[2] = v[10] * sm::cos(th2);
-	} else {
-		s.spin1[2] = v[9];
-		s.spin2[2] = v[10];
-	}
-	repack_tails(v, plan, s);
-	// MCMC_likelihood_extrinsic: tc is measured back from the end of the segment (src/mcmc_gw.cpp:2467,2473)
-	s.tc = T_segment - s.tc;
+	RepackHeavy h;
+	for (int part = 0; part < 4; part++) repack_heavy_part(part, param, plan, h);
+	repack_mcmc_assemble(param, plan, gmst, T_segment, h, s);
 }
 
 // ---- Fisher stencil: physical record <-> parameter vector ------------------------------------------------------------
@@ -400,8 +479,7 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 		return;
 	}
 	if (plan.sky) {  // src/fisher.cpp:2379-2393
-		s.mass1 = mass1_of(v[3], v[4]);
-		s.mass2 = mass2_of(v[3], v[4]);
+		masses_of(v[3], v[4], s.mass1, s.mass2);
 		s.Luminosity_Distance = a0_dl_conversion(v[3] * GWAT_MSOL_SEC, v[0], s.sky_average != 0) / GWAT_MPC_SEC;
 		s.tc = v[2];
 		s.phiRef = v[1];
@@ -420,14 +498,12 @@ GWAT_HD void repack_fisher_point(const double *v, const gwat_b200_source &orig, 
 	s.phiRef = v[4];
 	s.tc = v[5];
 	if (plan.mcmc) {
-		s.mass1 = mass1_of(sm::exp(v[7]), v[8]);
-		s.mass2 = mass2_of(sm::exp(v[7]), v[8]);
+		masses_of(sm::exp(v[7]), v[8], s.mass1, s.mass2);
 		s.Luminosity_Distance = sm::exp(v[6]);
 		s.DEC = sm::asin(v[1]);
 		if (!eq) s.incl_angle = sm::acos(v[3]);
 	} else {
-		s.mass1 = mass1_of(v[7], v[8]);
-		s.mass2 = mass2_of(v[7], v[8]);
+		masses_of(v[7], v[8], s.mass1, s.mass2);
 		s.Luminosity_Distance = v[6];
 		s.DEC = v[1];
 		if (!eq) s.incl_angle = v[3];

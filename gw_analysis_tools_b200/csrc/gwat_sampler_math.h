@@ -102,7 +102,8 @@ GWAT_HD double log_prior_base(const gwat_b200_prior &PD, bool pv2, const double 
 	const double chirp = exp(pos[7]);
 	const double eta = pos[8];
 	if (eta < .0 || eta > .25) return a;
-	const double m1 = mass1_of(chirp, eta), m2 = mass2_of(chirp, eta);
+	double m1, m2;
+	masses_of(chirp, eta, m1, m2);
 	if (outside(m1, PD.mass1_prior)) return a;
 	if (outside(m2, PD.mass2_prior)) return a;
 	if (outside(pos[0], PD.RA_bounds)) return a;
@@ -135,7 +136,8 @@ GWAT_HD double standard_log_prior(const gwat_b200_prior &PD, const PriorPlan &pp
 	double factor = 0;
 	if (pp.nrt) {
 		const double chirp = exp(pos[7]);
-		const double m1 = mass1_of(chirp, pos[8]), m2 = mass2_of(chirp, pos[8]);
+		double m1, m2;
+		masses_of(chirp, pos[8], m1, m2);
 		const double q = m2 / m1;
 		const int t0 = pp.pv2 ? 15 : 11;
 		if (PD.tidal_love) {
