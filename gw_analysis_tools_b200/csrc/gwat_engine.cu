@@ -1763,7 +1763,7 @@ int gwat_b200_mcmc_fisher_intrinsic_batch(gwat_b200_ctx *ctx, const char *method
 			F[6 * dimension + 6] = 1. / (4 * GWAT_PI * GWAT_PI);
 			F[7 * dimension + 7] = 1. / (4 * GWAT_PI * GWAT_PI);
 		}
-		if (alpha_fix) {
+		if (alpha_fix && src[w].Nmod > 0) {
 			const int base = dimension - src[w].Nmod;
 			double factor = 4 * std::pow(src[w].betappe[0], 3. / 4.);  // temp_params[base]: alpha^2 in s^4 after the unit change
 			factor *= 1000 / GWAT_C_SI;
