@@ -24,6 +24,7 @@ EXPORTS = [
     "gwat_b200_sampler_last_swap_accepts", "gwat_b200_sampler_dynamic_temperatures",
     # chain output (bound in chain_io.py)
     "gwat_b200_dump_create", "gwat_b200_dump_write", "gwat_b200_dump_close", "gwat_b200_write_data_dump", "gwat_b200_write_flat_thin_output",
+    "gwat_b200_autocorrelation_lengths",
 ]
 NCCL_UNIQUE_ID_BYTES = 128
 
@@ -116,6 +117,18 @@ def mcmc_fisher_intrinsic_batch(ctx, method, params, gmst, order=4, mod=None):
     ctx._check(ctx._lib.gwat_b200_mcmc_fisher_intrinsic_batch(ctx._h, method.encode(), C.byref(mod) if mod is not None else None, P, int(order), W,
                                                               _p(params), C.c_double(gmst), _p(F)))
     return F
+
+
+def autocorrelation_lengths(ctx, positions, begin=0):
+    """(ac_values, tau) of ``positions[n_chains][steps][dimension]`` from step ``begin`` on: the lags ``calc_ac_vals`` feeds the thinning
+    with (emcee's windowed estimator, truncated), and the estimator itself."""
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    n_chains, steps, dim = pos.shape
+    ac = np.zeros((n_chains, dim), dtype=np.int32)
+    tau = np.zeros((n_chains, dim))
+    ctx._check(ctx._lib.gwat_b200_autocorrelation_lengths(ctx._h, n_chains, dim, C.c_longlong(steps), _p(pos), C.c_longlong(begin),
+                                                          ac.ctypes.data_as(C.POINTER(C.c_int)), _p(tau)))
+    return ac, tau
 
 
 class Sampler:

@@ -173,8 +173,7 @@ int gwat_b200_sampler_dynamic_temperatures(gwat_b200_sampler *s, int N_steps, in
  * built, so the datasets go into a flat self-describing container (layout at the top of gwat_chain_io.cpp: magic, then per record
  * the HDF5-style path, dtype 0 = float64 / 1 = int32, rank, dims, row-major payload).
  *   positions [n_chains][steps][dimension]; logl_logp [n_chains][steps][2] or NULL; trim_lengths [n_chains] or NULL;
- *   ac_values [n_cold][dimension] autocorrelation lengths (NULL: dataset omitted; the autocorrelation tools themselves are outside
- *   this path).
+ *   ac_values [n_cold][dimension] autocorrelation lengths (NULL: dataset omitted), e.g. from gwat_b200_autocorrelation_lengths below.
  */
 typedef struct gwat_b200_dump gwat_b200_dump;
 int gwat_b200_dump_create(const char *path, gwat_b200_dump **out);
@@ -184,6 +183,19 @@ int gwat_b200_write_data_dump(const char *path, int n_chains, int dimension, lon
                               const double *positions, const double *logl_logp, const int *trim_lengths, int n_cold, const int *ac_values);
 int gwat_b200_write_flat_thin_output(const char *path, int n_cold, int dimension, long long steps, const double *positions,
                                      const int *trim_lengths, const int *ac_values, long long *n_rows);
+
+/*
+ * The autocorrelation lengths the thinning needs, as mcmc_sampler_output::calc_ac_vals obtains them (src/mcmc_io_util.cpp:434-520:
+ * auto_corr_from_data_batch with one cumulative segment, src/autocorrelation.cpp:152-332): for every (chain, dimension) row of
+ * positions[n_chains][steps][dimension], from step `begin` (the trim) on, emcee's windowed estimator
+ * (auto_correlation_spectral_windowed, :401-462: x - mean zero-padded to L = 2 * 2^ceil(log2 n), rho = IFFT(|FFT x|^2) / rho_0,
+ * tau_i = 2 sum_{j<=i} rho_j - 1, window = first i > 5 tau_i) and lag = int(tau_window) (:334-347).  All rows of a pass go through
+ * two batched cuFFT transforms on the context's device.  ac_values[n_chains][dimension]; tau (same shape, the estimator before
+ * truncation) may be NULL.  Rows of one or two steps give 2, as the reference's brute-force branch does (MAX_SERIAL = 2, :8).
+ * The reference passes ONE length for all chains -- that of the first cold chain minus the trim of the last (:474) -- hence one `begin`.
+ */
+int gwat_b200_autocorrelation_lengths(gwat_b200_ctx *ctx, int n_chains, int dimension, long long steps, const double *positions,
+                                      long long begin, int *ac_values, double *tau);
 
 /* Building blocks, exposed for tests and for callers that keep their own sampler loop:
  * log prior of W sampling vectors (host arrays) with the standard prior of the method's family */

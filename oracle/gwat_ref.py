@@ -244,6 +244,17 @@ def repack_mcmc_intrinsic(method, mod, params, gmst):
     return out
 
 
+def autocorrelation_lengths(positions, begin=0, target=0.01, nthreads=0):
+    """calc_ac_vals' lags (auto_corr_from_data_batch, one cumulative segment) and the windowed estimator behind them."""
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    n_chains, steps, dim = pos.shape
+    ac = np.zeros((n_chains, dim), dtype=np.int32)
+    tau = np.zeros((n_chains, dim))
+    lib().oracle_ref_autocorrelation_lengths(n_chains, dim, steps, _p(pos), int(begin), C.c_double(target), int(nthreads),
+                                             ac.ctypes.data_as(C.POINTER(C.c_int)), _p(tau))
+    return ac, tau
+
+
 def pack_local_mod_structure(min_dim, max_dim, status, waveform_extended, full_mod):
     """pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476): (counts[4], indices[4][MAX_MOD]) of the local structure."""
     status = np.ascontiguousarray(status, dtype=np.int32)

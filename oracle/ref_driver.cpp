@@ -28,6 +28,7 @@
 #include "detector_util.h"
 #include "io_util.h"
 #include "mcmc_gw.h"
+#include "autocorrelation.h"
 #include "fisher.h"
 #include "ortho_basis.h"
 #include "ppE_utilities.h"
@@ -654,6 +655,46 @@ int oracle_ref_repack_mcmc_intrinsic(const char *method, const gwat_b200_mod *mo
 		repack_parameters(temp.data(), &gp, "MCMC_" + m, dimension, (gen_params_base<double> *)NULL);
 		from_gen_params(gp, sources_out[w]);
 		free_prepped(gp, local_gen, mb.m);
+	}
+	return 0;
+}
+
+// The autocorrelation lengths of calc_ac_vals (src/mcmc_io_util.cpp:434-520): auto_corr_from_data_batch with one cumulative segment
+// (src/autocorrelation.cpp:152-217), positions[n_chains][steps][dimension] from step `begin` on; ac[n_chains][dimension].  tau (may be
+// NULL) receives the estimator before truncation, from auto_correlation_spectral_windowed itself (:401-462) with the plan pair of :292-297.
+int oracle_ref_autocorrelation_lengths(int n_chains, int dimension, int steps, const double *positions, int begin, double target, int nthreads,
+                                       int *ac, double *tau)
+{
+	const int n = steps - begin;
+	std::vector<std::vector<double *>> rows(n_chains, std::vector<double *>(n));
+	std::vector<double **> data(n_chains);
+	for (int c = 0; c < n_chains; c++) {
+		for (int i = 0; i < n; i++) rows[c][i] = const_cast<double *>(positions) + ((size_t)c * steps + begin + i) * dimension;
+		data[c] = rows[c].data();
+	}
+	std::vector<std::vector<int>> seg((size_t)n_chains * dimension, std::vector<int>(1));
+	std::vector<std::vector<int *>> outp(n_chains, std::vector<int *>(dimension));
+	std::vector<int **> out(n_chains);
+	for (int c = 0; c < n_chains; c++) {
+		for (int d = 0; d < dimension; d++) outp[c][d] = seg[(size_t)c * dimension + d].data();
+		out[c] = outp[c].data();
+	}
+	auto_corr_from_data_batch(data.data(), n, dimension, n_chains, out.data(), 1, target, nthreads > 0 ? nthreads : omp_get_max_threads(), true);
+	for (int c = 0; c < n_chains; c++)
+		for (int d = 0; d < dimension; d++) ac[(size_t)c * dimension + d] = seg[(size_t)c * dimension + d][0];
+	if (tau && n > 2) {
+		const int L = 2 * std::pow(2, std::ceil(std::log2(n)));
+		fftw_outline pf, pr;
+		allocate_FFTW_mem_forward(&pf, L);
+		allocate_FFTW_mem_reverse(&pr, L);
+		std::vector<double> chain(n);
+		for (int c = 0; c < n_chains; c++)
+			for (int d = 0; d < dimension; d++) {
+				for (int i = 0; i < n; i++) chain[i] = rows[c][i][d];
+				auto_correlation_spectral_windowed(chain.data(), n, 0, &tau[(size_t)c * dimension + d], &pf, &pr);
+			}
+		deallocate_FFTW_mem(&pf);
+		deallocate_FFTW_mem(&pr);
 	}
 	return 0;
 }

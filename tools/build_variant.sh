@@ -11,5 +11,5 @@ mkdir -p $out
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 --diag-suppress 128 -Xptxas -v \
      -DGWAT_EXPERIMENT_SLIM "$@" -c -o $out/gwat_engine.o $src/gwat_engine.cu 2> $out/ptxas.log || { tail -30 $out/ptxas.log; exit 1; }
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libgwat_b200.so $out/gwat_engine.o \
-     $src/_obj/gwat_sampler.o $src/_obj/gwat_maximized.o $src/_obj/gwat_grids.o $src/_obj/gwat_losc.o $src/_obj/gwat_queue.o $src/_obj/gwat_noise.o $src/_obj/gwat_chain_io.o -lcufft
+     $src/_obj/gwat_sampler.o $src/_obj/gwat_maximized.o $src/_obj/gwat_grids.o $src/_obj/gwat_losc.o $src/_obj/gwat_autocorr.o $src/_obj/gwat_queue.o $src/_obj/gwat_noise.o $src/_obj/gwat_chain_io.o -lcufft
 echo built $out/libgwat_b200.so
