@@ -57,6 +57,10 @@ def main():
                         swp_freq=3, history_length=12, history_update=2, fisher_update_number=4, check_stepsize_freq=5)
     s.run(12)
     print("sampler ran", flush=True)
+    # autocorrelation lengths: ragged length (L = 2048 for 1025 steps), a trim, a row count that is not a multiple of anything
+    rng = np.random.default_rng(2)
+    ac, tau = sampler.autocorrelation_lengths(ctx, np.cumsum(rng.standard_normal((3, 1030, 5)), axis=1), begin=5)
+    print("autocorrelation lags:", ac.min(), ac.max(), flush=True)
     ctx.close()
     print("sanitize_small done", flush=True)
 
