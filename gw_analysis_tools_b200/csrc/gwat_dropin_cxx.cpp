@@ -435,17 +435,26 @@ double MCMC_likelihood_wrapper(double *param, mcmc_data_interface *interface, vo
 
 void MCMC_fisher_wrapper(double *param, double **output, mcmc_data_interface *interface, void *parameters)
 {
-	(void)parameters;
+	const MCMC_user_param *user_param = (const MCMC_user_param *)parameters;
 	const int dimension = interface->max_dim;
 	for (int j = 0; j < dimension; j++)
 		for (int k = 0; k < dimension; k++) output[j][k] = kNaN;
-	if (!mcmc_frequencies || !same_length(mcmc_data_length, mcmc_num_detectors)) return;
+	// the Fisher matrices may have a grid of their own (user_param->fisher_freq / fisher_PSD / fisher_length, src/mcmc_gw.cpp:2257-2275:
+	// typically a short Gauss-Legendre grid); fisher_numerical applies Simpson's rule to whatever grid it is given (src/fisher.cpp:128-131),
+	// and so does the C ABI.  fisher_AD asks for ADOL-C derivatives, which are outside this path: the numerical stencil answers instead.
+	double **local_freq = mcmc_frequencies, **local_noise = mcmc_noise;
+	int *local_lengths = mcmc_data_length;
+	if (user_param && user_param->fisher_freq) local_freq = user_param->fisher_freq;
+	if (user_param && user_param->fisher_PSD) local_noise = user_param->fisher_PSD;
+	if (user_param && user_param->fisher_length) local_lengths = user_param->fisher_length;
+	if (!local_freq || !local_noise || !local_lengths || !same_length(local_lengths, mcmc_num_detectors)) return;
+	const bool own_grid = local_freq != mcmc_frequencies || local_lengths != mcmc_data_length;
 	Session &S = session();
 	std::lock_guard<std::mutex> lock(S.mu);
 	gwat_b200::Engine *e = engine_locked(S);
 	if (!e) return;
-	if (!ensure_network(S, e, mcmc_detectors, mcmc_num_detectors, mcmc_data_length[0], mcmc_frequencies, mcmc_noise, mcmc_data, nullptr, "SIMPSONS",
-	                    false))
+	if (!ensure_network(S, e, mcmc_detectors, mcmc_num_detectors, local_lengths[0], local_freq, local_noise, own_grid ? nullptr : mcmc_data, nullptr,
+	                    "SIMPSONS", false))
 		return;
 	gwat_b200_mod mod;
 	bool ok;

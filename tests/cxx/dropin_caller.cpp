@@ -192,6 +192,63 @@ int main()
 		deallocate_2D_array(Ft, dim, dim);
 	}
 
+	// ---- the Fisher matrices on a grid of their own: user_param->fisher_freq / fisher_PSD / fisher_length (src/mcmc_gw.cpp:2257-2275) --
+	{
+		const int dim = 11, Lf = 384;
+		double chirp = calculate_chirpmass(36.4, 29.3), eta = calculate_eta(36.4, 29.3);
+		double param[dim] = {.275, std::sin(-.44), .2, std::cos(.51), 2., 3., std::log(500.), std::log(chirp * 1.0003), eta, .3, .2};
+		MCMC_modification_struct mod;
+		double temp[dim];
+		std::vector<double> ffb((size_t)D * Lf), fpb((size_t)D * Lf);
+		double *ff[3], *fp[3];
+		int fl[3] = {Lf, Lf, Lf};
+		for (int d = 0; d < D; d++) {
+			ff[d] = ffb.data() + (size_t)d * Lf;
+			fp[d] = fpb.data() + (size_t)d * Lf;
+			for (int i = 0; i < Lf; i++) ff[d][i] = 20. * std::pow(50., (double)i / (Lf - 1));  // 20 Hz ... 1000 Hz, geometric: not uniform
+			populate_noise(ff[d], "aLIGO_analytic", fp[d], Lf, 48);
+			for (int i = 0; i < Lf; i++) fp[d][i] *= fp[d][i] * (1. + .5 * d);
+		}
+		double **F = allocate_2D_array(dim, dim), **Ft = allocate_2D_array(dim, dim);
+		for (int i = 0; i < dim; i++)
+			for (int j = 0; j < dim; j++) F[i][j] = 0;
+		gen_params_base<double> g2;
+		MCMC_prep_params(param, temp, &g2, dim, "IMRPhenomD", &mod);
+		g2.gmst = 2.1;
+		repack_parameters(temp, &g2, "MCMC_" + std::string("IMRPhenomD"), dim, (gen_params_base<double> *)NULL);
+		for (int d = 0; d < D; d++) {
+			fisher_numerical(ff[d], Lf, "MCMC_IMRPhenomD", detectors[d], detectors[0], Ft, dim, &g2, 4, NULL, NULL, fp[d]);
+			for (int i = 0; i < dim; i++)
+				for (int j = 0; j < dim; j++) F[i][j] += Ft[i][j];
+		}
+		{
+			mcmc_data_interface iface2;
+			iface2.min_dim = iface2.max_dim = dim;
+			MCMC_fisher_transformations(temp, F, dim, "IMRPhenomD", false, &iface2, &mod, NULL);
+		}
+		for (int i = 0; i < dim; i++) put("fisher_owngrid_sum_diag", i, F[i][i]);
+		deallocate_2D_array(F, dim, dim);
+		deallocate_2D_array(Ft, dim, dim);
+		if (gwat_b200_dropin_bind_mcmc) {
+			gwat_b200_dropin_bind_mcmc(data, psd, freq, lengths, detectors, D, "IMRPhenomD", &mod, 2.1, 4);
+			mcmc_data_interface iface;
+			iface.min_dim = iface.max_dim = dim;
+			iface.chain_id = 0;
+			iface.chain_number = 1;
+			iface.nested_model_number = 0;
+			MCMC_user_param up;
+			up.fisher_freq = ff;
+			up.fisher_PSD = fp;
+			up.fisher_length = fl;
+			double **Fw = allocate_2D_array(dim, dim);
+			MCMC_fisher_wrapper(param, Fw, &iface, (void *)&up);
+			for (int i = 0; i < dim; i++) put("MCMC_fisher_wrapper_owngrid_diag", i, Fw[i][i]);
+			deallocate_2D_array(Fw, dim, dim);
+			// ... and the likelihood afterwards is the data grid's again
+			put("MCMC_likelihood_wrapper_after_owngrid", MCMC_likelihood_wrapper(param, &iface, (void *)&up));
+		}
+	}
+
 	// ---- an INTRINSIC run (ln Mc, eta, chi1, chi2): the wrappers' maximised likelihood and sky-averaged Fisher ------------------
 	{
 		const int dim = 4;

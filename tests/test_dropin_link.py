@@ -97,6 +97,12 @@ def test_same_program_same_numbers_through_the_gpu_library():
     for i in range(11):
         a, b = ref["fisher_sum_diag[%d]" % i], got["MCMC_fisher_wrapper_diag[%d]" % i]
         assert abs(a - b) <= 2e-5 * abs(a), (i, a, b)
+    # ... on a Fisher grid of its own (user_param->fisher_freq, fisher_PSD, fisher_length; here geometric, 384 bins), and back on the data grid
+    for i in range(11):
+        a, b = ref["fisher_owngrid_sum_diag[%d]" % i], got["MCMC_fisher_wrapper_owngrid_diag[%d]" % i]
+        assert abs(a - b) <= 2e-5 * abs(a), (i, a, b)
+    assert abs(ref["fisher_owngrid_sum_diag[7]"] - ref["fisher_sum_diag[7]"]) > 1e-3 * abs(ref["fisher_sum_diag[7]"])  # (another grid, another matrix)
+    assert got["MCMC_likelihood_wrapper_after_owngrid"] == got["MCMC_likelihood_wrapper"]
     # ... and in an intrinsic run: the tc/phic-maximised likelihood and the sky-averaged Fisher of the 4-parameter set
     assert abs(got["MCMC_likelihood_wrapper_intrinsic"] - ref["intrinsic_callback_chain"]) <= 1e-9 * abs(ref["intrinsic_callback_chain"])
     for i in range(4):
