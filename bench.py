@@ -183,15 +183,38 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def physical_core_groups(cpus):
+    """The logical CPUs of `cpus` grouped by physical core (hyperthread siblings together), in core order."""
+    groups, seen = [], set()
+    for c in sorted(cpus):
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            txt = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                sib.update(range(int(lo), int(hi or lo) + 1))
+        except (OSError, ValueError):
+            pass
+        g = sorted(x for x in sib if x in cpus)
+        seen.update(g)
+        groups.append(g)
+    return groups
+
+
 def pin_rank_cores(local, world):
-    """Give every rank of a multi-GPU run its own, disjoint share of the host cores (eight ranks on the
-    same 32 cores made the host-buffer path's max-over-ranks time a scheduler lottery).  Returns the cores kept."""
+    """Give every rank of a multi-GPU run its own, disjoint share of the host's PHYSICAL cores, hyperthread siblings together
+    (eight ranks on the same 32 logical CPUs made the host-buffer path's max-over-ranks time a scheduler
+    lottery -- measured again in round 2: 54-58 M evals/s through host buffers on 8 GPUs unpinned, 60 M pinned; a split by logical
+    CPU number alone had put the two ranks of a 2-GPU box on sibling threads of the same cores and cost 8 %).  Returns the CPUs kept."""
     try:
-        cores = sorted(os.sched_getaffinity(0))
-        if world <= 1 or len(cores) < world:
-            return cores
-        share = len(cores) // world
-        mine = cores[local * share:(local + 1) * share]
+        cpus = set(os.sched_getaffinity(0))
+        groups = physical_core_groups(cpus)
+        if world <= 1 or len(groups) < world:
+            return sorted(cpus)
+        share = len(groups) // world
+        mine = sorted(c for g in groups[local * share:(local + 1) * share] for c in g)
         os.sched_setaffinity(0, mine)
         return mine
     except (AttributeError, OSError):
@@ -536,9 +559,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    # (measured on a 2-GPU box: splitting the 32 host threads into two halves made one rank's host-buffer path 8 % SLOWER than
-    # leaving the scheduler alone -- the halves are hyperthread siblings -- so pinning is opt-in)
-    cores = pin_rank_cores(local, world) if args.pin_cores else sorted(os.sched_getaffinity(0))
+    # several ranks: each gets its own physical cores unless --no-pin-cores (the reference arm never pins: it runs on all host threads)
+    pin = args.pin_cores if args.pin_cores is not None else world > 1
+    cores = pin_rank_cores(local, world) if pin else sorted(os.sched_getaffinity(0))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -730,7 +753,9 @@ def main():
     ap.add_argument("--fisher-sources", type=int, default=100000, help="config 3: sources per GPU and step")
     ap.add_argument("--fisher-cpu-sample", type=int, default=256)
     ap.add_argument("--sustain-seconds", type=float, default=1.0)
-    ap.add_argument("--pin-cores", action="store_true", help="give every rank a disjoint share of the host cores")
+    ap.add_argument("--pin-cores", dest="pin_cores", action="store_true", default=None,
+                    help="give every rank a disjoint share of the host's physical cores (default when there are several ranks)")
+    ap.add_argument("--no-pin-cores", dest="pin_cores", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained figure and the other configs' lines")
     args = ap.parse_args()
