@@ -773,6 +773,42 @@ int calculate_mass2_vectorized_py(double *chirpmass, double *eta, double *out, i
 	return 0;
 }
 
+// Small closed-form helpers of the gwatpy API (host arithmetic with the reference's expressions; src/gwatpy_wrapping.cpp:77-84, 832-836)
+// f_0PN / t_0PN (src/pn_waveform_util.cpp:36-52): frequency at a time before merger at leading order, and its inverse
+double f_0PN_py(double t, double chirpmass)
+{
+	const double factor = 0.07275685064;  // 5^(3/8) / (8 pi)
+	return factor * std::pow(chirpmass, -5. / 8.) * std::pow(t, -3. / 8);
+}
+double t_0PN_py(double f, double chirpmass)
+{
+	const double factor = 0.07275685064;
+	return std::pow(f / factor * std::pow(chirpmass, 5. / 8.), -8. / 3.);
+}
+// DL_from_Z (src/util.cpp:422-450): luminosity distance in Mpc from the redshift, the piecewise half-power series of D_Z_Config.h;
+// -1 for an unknown cosmology or a redshift outside the tables, as the reference returns it
+#include "gwat_tables_zd.inc"
+int DL_from_Z_py(double z, char *COSMOLOGY, double *out)
+{
+	*out = -1;
+	const int c = gwat_b200_cosmology_index(COSMOLOGY);
+	if (c < 0) return 0;
+	for (int i = 0; i < 3; i++)
+		if (z < gwat_zd_boundaries[c][i + 1]) {
+			const double *k = gwat_zd_coeffs[c][i];
+			const double rootx = std::sqrt(z);
+			double sum = k[0];
+			for (int j = 1; j < 12; j++) {  // cosmology_interpolation_function with pow_int's sequential product (src/util.cpp:1585-1597)
+				double prod = 1;
+				for (int m = 0; m < j; m++) prod = prod * rootx;
+				sum += k[j] * prod;
+			}
+			*out = sum;
+			return 0;
+		}
+	return 0;
+}
+
 // Forget the cached network: the next call re-uploads its arrays.  Needed only by callers that overwrite their frequency /
 // PSD / data arrays IN PLACE between calls (the cache key samples each array, see array_key).
 void gwat_b200_gwatpy_invalidate_network(void)

@@ -30,6 +30,7 @@
 #include "mcmc_gw.h"
 #include "autocorrelation.h"
 #include "fisher.h"
+#include "pn_waveform_util.h"
 #include "ortho_basis.h"
 #include "ppE_utilities.h"
 #include "IMRPhenomD.h"
@@ -698,6 +699,11 @@ int oracle_ref_autocorrelation_lengths(int n_chains, int dimension, int steps, c
 	}
 	return 0;
 }
+
+// small helpers behind gwatpy's DL_from_Z_py, t_0PN_py, f_0PN_py (src/util.cpp:422, src/pn_waveform_util.cpp:36-52)
+double oracle_ref_dl_from_z(double z, const char *cosmology) { return DL_from_Z(z, std::string(cosmology)); }
+double oracle_ref_t_0pn(double f, double chirpmass) { return t_0PN<double>(f, chirpmass); }
+double oracle_ref_f_0pn(double t, double chirpmass) { return f_0PN<double>(t, chirpmass); }
 
 // pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476); counts[4] and idx[4][GWAT_B200_MAX_MOD] receive the local structure.
 int oracle_ref_pack_local_mod_structure(int min_dim, int max_dim, const int *status, const char *waveform_extended, const gwat_b200_mod *full,

@@ -23,7 +23,7 @@ ON_PATH_SYMBOLS = ["gen_params_base_py", "gen_params_base_py_destructor", "MCMC_
                    "calculate_mass1_vectorized_py", "calculate_mass2_vectorized_py", "MCMC_likelihood_extrinsic_batch_py",
                    "fourier_waveform_full_py", "populate_noise_py", "calculate_snr_py", "gps_to_GMST_radian_py",
                    "fourier_waveformC", "fourier_amplitudeC", "fourier_phaseC", "MCMC_prep_params_py", "mcmc_data_interface_py",
-                   "pack_local_mod_structure_py", "match_py"]
+                   "pack_local_mod_structure_py", "match_py", "DL_from_Z_py", "t_0PN_py", "f_0PN_py"]
 
 
 def _lib():
@@ -340,3 +340,27 @@ def test_match_py_and_log_likelihood_internal_vs_reference(ctx, oracle):
     ref = oracle.log_likelihood_internal(0.8 * rg, pg, fg, wg, rg, log10F=True, integ="GAUSSLEG")
     got = ctx.log_likelihood_internal(0.8 * rg, pg, fg, rg, weights=wg, integration_method="GAUSSLEG", log10F=True)
     assert abs(got - ref) <= 1e-11 * abs(ref), (got, ref)
+
+
+
+def test_small_helpers_vs_reference(oracle):
+    """DL_from_Z_py, t_0PN_py, f_0PN_py (src/gwatpy_wrapping.cpp:77-84, 832-836): host arithmetic, no GPU."""
+    lib = _lib()
+    ref = oracle.lib()
+    ref.oracle_ref_dl_from_z.restype = ref.oracle_ref_t_0pn.restype = ref.oracle_ref_f_0pn.restype = C.c_double
+    ref.oracle_ref_dl_from_z.argtypes = [C.c_double, C.c_char_p]
+    ref.oracle_ref_t_0pn.argtypes = ref.oracle_ref_f_0pn.argtypes = [C.c_double, C.c_double]
+    lib.t_0PN_py.restype = lib.f_0PN_py.restype = C.c_double
+    lib.t_0PN_py.argtypes = lib.f_0PN_py.argtypes = [C.c_double, C.c_double]
+    lib.DL_from_Z_py.argtypes = [C.c_double, C.c_char_p, _dp]
+    out = C.c_double()
+    for cosmo in (b"PLANCK15", b"planck13", b"WMAP9", b"WMAP7", b"WMAP5", b"NO_SUCH_COSMOLOGY"):
+        for z in (2e-6, 1e-4, 3e-3, 0.05, 0.3, 1.0, 7.5, 19.9, 25.0):
+            assert lib.DL_from_Z_py(z, cosmo, C.byref(out)) == 0
+            want = ref.oracle_ref_dl_from_z(z, cosmo)
+            assert out.value == want or abs(out.value - want) <= 1e-14 * abs(want), (cosmo, z, out.value, want)
+    assert ref.oracle_ref_dl_from_z(0.3, b"PLANCK15") > 1000 and ref.oracle_ref_dl_from_z(25.0, b"PLANCK15") == -1
+    for f, mc in ((20.0, 1.2e-4), (0.01, 3e-3), (150.0, 6e-6)):
+        t = lib.t_0PN_py(f, mc)
+        assert abs(t - ref.oracle_ref_t_0pn(f, mc)) <= 1e-15 * t
+        assert abs(lib.f_0PN_py(t, mc) - ref.oracle_ref_f_0pn(t, mc)) <= 1e-15 * f and abs(lib.f_0PN_py(t, mc) - f) <= 1e-9 * f

@@ -16,7 +16,8 @@ import os
 import re
 import sys
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+REF = _args[0] if _args else "/root/reference"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gw_analysis_tools_b200", "csrc", "gwat_tables.inc")
 
 
@@ -176,5 +177,38 @@ def main():
     print("wrote", os.path.normpath(OUT))
 
 
+def write_zd_tables():
+    """D_L(z) for the gwatpy helper DL_from_Z_py (host code only, so a file of its own: regenerating it does not touch the kernels'
+    tables): include/gwat/D_Z_Config.h boundaries_Z and COEFF_VEC_ZD, evaluated by DL_from_Z (src/util.cpp:422-450)."""
+    dz = strip_comments(open(os.path.join(REF, "include/gwat/D_Z_Config.h")).read())
+    bZ = numbers(array_body(dz, "boundaries_Z"))
+    cZD = numbers(array_body(dz, "COEFF_VEC_ZD"))
+    ncos = int(re.search(r"num_cosmologies\s*=\s*(\d+)", dz).group(1))
+    nseg, ndeg = 3, 12
+    assert len(bZ) == ncos * (nseg + 1) and len(cZD) == ncos * nseg * ndeg, (len(bZ), len(cZD))
+    out = os.path.join(os.path.dirname(OUT), "gwat_tables_zd.inc")
+    r = repr
+    with open(out, "w") as o:
+        o.write("// GENERATED by tools/gen_tables.py (write_zd_tables) from the reference's include/gwat/D_Z_Config.h -- do not edit.\n")
+        o.write("// D_L(z)/Mpc per cosmology: segment boundaries in z and, per segment, coefficients of sum_k c_k (sqrt z)^k\n")
+        o.write("static const double gwat_zd_boundaries[%d][%d] = {\n" % (ncos, nseg + 1))
+        for c in range(ncos):
+            o.write("{" + ",".join(r(x) for x in bZ[c * (nseg + 1):(c + 1) * (nseg + 1)]) + "},\n")
+        o.write("};\n")
+        o.write("static const double gwat_zd_coeffs[%d][%d][%d] = {\n" % (ncos, nseg, ndeg))
+        for c in range(ncos):
+            o.write("{")
+            for i in range(nseg):
+                base = (c * nseg + i) * ndeg
+                o.write("{" + ",".join(r(x) for x in cZD[base:base + ndeg]) + "},")
+            o.write("},\n")
+        o.write("};\n")
+    print("wrote", os.path.normpath(out))
+
+
 if __name__ == "__main__":
-    main()
+    if "--zd-only" in sys.argv:
+        write_zd_tables()
+    else:
+        main()
+        write_zd_tables()
