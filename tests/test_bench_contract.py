@@ -37,3 +37,21 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                          timeout=600, cwd=ROOT)
     assert out.returncode != 0  # no CPU fallback: the product arm fails loudly
     assert "reference" not in out.stdout
+
+
+def test_core_groups_partition_the_affinity_mask():
+    """bench.py deals the host's physical cores out over the ranks of a multi-GPU run: the groups (hyperthread siblings together)
+    must partition the CPUs this process may run on, and eight ranks must get disjoint, non-empty shares when there are enough cores."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    bench = importlib.import_module("bench")
+    cpus = set(os.sched_getaffinity(0))
+    groups = bench.physical_core_groups(cpus)
+    flat = [c for g in groups for c in g]
+    assert sorted(flat) == sorted(cpus) and len(flat) == len(set(flat))
+    world = min(8, len(groups))
+    share = len(groups) // world
+    shares = [set(c for g in groups[r * share:(r + 1) * share] for c in g) for r in range(world)]
+    assert all(shares) and sum(len(s) for s in shares) == len(set().union(*shares))
