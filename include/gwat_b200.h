@@ -154,7 +154,10 @@ int gwat_b200_loglike_mcmc_batch(gwat_b200_ctx *ctx, const char *generation_meth
 /* Same, with params/logL already in device memory of ctx's GPU; asynchronous on `stream` (NULL = the context's own stream).
  * The per-walker coefficient scratch belongs to the context: calls on ONE context must be ordered on one stream (or separated
  * by stream synchronisation); independent streams need independent contexts.  The host-buffer entry points of this header
- * are safe to call concurrently from several threads on one context (each call is one critical section). */
+ * are safe to call concurrently from several threads on one context (each call is one critical section, held from the upload of its
+ * inputs to the download of its results: concurrent callers are SERIALISED, not overlapped -- a pool of threads with one walker per
+ * call gets its throughput from gwat_b200_queue_* below, which merges the calls in flight into one batch, or from one context per
+ * thread). */
 int gwat_b200_loglike_mcmc_batch_dev(gwat_b200_ctx *ctx, const char *generation_method, const gwat_b200_mod *mod,
                                      int dimension, int W, const double *d_params, double gmst, double T_segment,
                                      double *d_logL, void *stream);
