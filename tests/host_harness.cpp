@@ -415,7 +415,7 @@ extern "C" int hh_loglike(const char *method, int W, const gwat_b200_source *src
 	if (parse_method(method, desc) != 0) return -2;
 	Network net{};
 	if (make_network(D, dets, net) != 0) return -1;
-	if (D != 2 && D != 3) return -3;
+	if (D < 1 || D > 5) return -3;
 	const Grid g = make_grid(f, L);
 	std::vector<double> wq((size_t)D * L);
 	for (int d = 0; d < D; d++)
@@ -425,10 +425,12 @@ extern "C" int hh_loglike(const char *method, int W, const gwat_b200_source *src
 	bool uni = df > 0;
 	for (int i = 0; i < L && uni; i++) uni = std::fabs(f[i] - (f[0] + i * df)) <= 1e-9 * df;
 	for (int wi = 0; wi < W; wi++) {
-		if (D == 2) {
-			DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 2>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta));
-		} else {
-			DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 3>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta));
+		switch (D) {  // (the kernels are instantiated per detector count, and so is this)
+		case 1: DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 1>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta)); break;
+		case 2: DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 2>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta)); break;
+		case 3: DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 3>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta)); break;
+		case 4: DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 4>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta)); break;
+		default: DISPATCH_FAMILY(desc, out[wi] = loglike_t<Fam, 5>(desc.theory, src + wi, net, g, wq, dre, dim, uni, df, pref, bins_per_cta)); break;
 		}
 	}
 	return 0;

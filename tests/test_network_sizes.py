@@ -66,3 +66,31 @@ def test_networks_beyond_five_detectors_are_refused(ctx):
         # ... while one detector of the big network at a time is fine
         F = ctx.fisher_numerical_batch("IMRPhenomD", workloads.fisher_sources(2), 11, order=2, detector_index=D - 1)
         assert F.shape == (2, 11, 11)
+
+
+@pytest.mark.parametrize("name,method", [("D_bbh", "IMRPhenomD"), ("P_full", "IMRPhenomPv2")])
+@pytest.mark.parametrize("D", [1, 4, 5])
+def test_likelihood_math_for_every_network_size(oracle, name, method, D):
+    """CPU tier: the fused per-bin likelihood of gwat_like.h compiled as C++ (tests/host_harness.cpp), instantiated for 1, 4 and 5
+    detectors like the kernel, against the compiled reference."""
+    import ctypes as C
+    import os
+
+    import cases
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hh = C.CDLL(os.path.join(root, "tests", "_build", "libgwat_host_harness.so"))
+    gold = np.load(os.path.join(root, "tests", "golden", "waveforms_v1.npz"))
+    f = cases.grid([c for c in cases.CASES if c[0] == name][0][3])
+    src = cases.source_from_bytes(gold[name + "/src"])
+    dets = ALL[:D]
+    psd = np.ascontiguousarray(workloads.aligo_analytic_psd(f)[None, :] * (1.0 + 0.4 * np.arange(D))[:, None])
+    tmpl = cases.source_from_bytes(gold[name + "/src"])
+    tmpl.mass1 *= 1.0004  # the data are another source's responses: a mismatched template
+    data = 0.9 * np.exp(0.3j) * oracle.coherent_response(method, tmpl, dets, f)
+    ref = oracle.loglike_batch(method, [src], dets, f, psd, data)[0]
+    dre, dim = np.ascontiguousarray(data.real), np.ascontiguousarray(data.imag)
+    names = (C.c_char_p * D)(*[d.encode() for d in dets])
+    out = np.zeros(1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert hh.hh_loglike(method.encode(), 1, C.byref(src), D, names, p(f), f.size, p(psd), p(dre), p(dim), None, 0, 0, 0, p(out)) == 0
+    assert abs(out[0] - ref) <= 1e-9 * abs(ref), (D, out[0], ref)
