@@ -1351,6 +1351,18 @@ int gwat_b200_cosmology_index(const char *name)
 	return -1;
 }
 
+#include "gwat_tables_sites.inc"
+int gwat_b200_detector_site(const char *detector, double *latitude, double *longitude, double *location, double *response_tensor)
+{
+	const int id = detector_index(detector);
+	if (id < 0 || !latitude || !longitude || !location || !response_tensor) return GWAT_B200_ERR_ARG;
+	*latitude = gwat_site_lat_long[id][0];
+	*longitude = gwat_site_lat_long[id][1];
+	std::memcpy(response_tensor, hosttab::gwat_detector_table[id], sizeof(double) * 9);
+	std::memcpy(location, hosttab::gwat_detector_table[id] + 9, sizeof(double) * 3);
+	return GWAT_B200_OK;
+}
+
 void gwat_b200_mod_init(gwat_b200_mod *mod)
 {
 	if (!mod) return;

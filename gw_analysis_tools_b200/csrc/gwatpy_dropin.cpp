@@ -15,6 +15,7 @@
 //  * the detector letters are mapped letter by letter ("H","L","V","K","C"); the reference compares the REST of the string
 //    (src/gwatpy_wrapping.cpp:131-140), which only works for the default order "HLV".
 //  * unknown detectors / methods return NaN (or a negative status) instead of calling exit(1).
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdint>
@@ -727,6 +728,64 @@ void detector_response_equatorial_py(char *detector, double ra, double dec, doub
 	if (report(S, gwat_b200_antenna_batch(S.ctx, 1, &ra, &dec, &psi, gmst, &fp, &fc, &dt))) return;
 	response_functions[0] = fp;
 	response_functions[1] = fc;
+}
+
+// get_detector_parameters (src/gwatpy_wrapping.cpp:743-831): site constants by name.  The reference matches SUBSTRINGS, in this order,
+// and knows the sites up to ET1 only (ET2 / ET3 fall through to "Unsupported detector", -1): kept, so the two libraries answer alike.
+int get_detector_parameters(char *detector, double *LAT, double *LON, double *location, double *response_tensor)
+{
+	static const struct { const char *a, *b, *c, *canonical; } sites[] = {
+		{"Hanford", "hanford", nullptr, "Hanford"},   {"Livingston", "livingston", nullptr, "Livingston"},
+		{"Virgo", "virgo", nullptr, "Virgo"},         {"Kagra", "kagra", nullptr, "Kagra"},
+		{"Indigo", "indigo", nullptr, "Indigo"},      {"CosmicExplorer", "cosmicexplorer", "CE", "CE"},
+		{"Einstein Telescope 1", "einstein telescope 1", "ET1", "ET1"},
+	};
+	const std::string name(detector ? detector : "");
+	for (const auto &s : sites)
+		if (name.find(s.a) != std::string::npos || name.find(s.b) != std::string::npos || (s.c && name.find(s.c) != std::string::npos))
+			return gwat_b200_detector_site(s.canonical, LAT, LON, location, response_tensor) == GWAT_B200_OK ? 0 : -1;
+	std::fprintf(stderr, "Unsupported detector\n");
+	return -1;
+}
+
+// ---- time-domain entry points (src/gwatpy_wrapping.cpp:389-407, 428-480) -----------------------------------------------------------
+// The reference's time_waveform (src/waveform_generator.cpp:31-71) knows one model, TaylorT2, which is outside this library's path
+// (DESIGN section 7): refused with status -1 and NaN outputs.  For every other method name the reference computes nothing -- status 1
+// and the zero-initialised arrays -- and so does this, so that gwatpy.waveform_generator, which binds both symbols when it is imported,
+// loads against this library and behaves alike wherever the reference has a defined answer.
+static int time_domain_status(const char *generation_method, double fill[1])
+{
+	const bool taylor = generation_method && std::strstr(generation_method, "Taylor") != nullptr;
+	fill[0] = taylor ? NaN : 0.0;
+	if (taylor) std::fprintf(stderr, "gwat_b200: time-domain TaylorT2 waveforms are not part of this library\n");
+	return taylor ? -1 : 1;
+}
+int time_waveform_full_py(double *times, int length, double *wf_plus_real, double *wf_plus_imaginary, double *wf_cross_real,
+                          double *wf_cross_imaginary, double *wf_x_real, double *wf_x_imaginary, double *wf_y_real, double *wf_y_imaginary,
+                          double *wf_b_real, double *wf_b_imaginary, double *wf_l_real, double *wf_l_imaginary, char *generation_method,
+                          void *parameters)
+{
+	(void)times;
+	(void)parameters;
+	double fill;
+	const int status = time_domain_status(generation_method, &fill);
+	double *const outs[12] = {wf_plus_real, wf_plus_imaginary, wf_cross_real, wf_cross_imaginary, wf_x_real, wf_x_imaginary,
+	                          wf_y_real,    wf_y_imaginary,    wf_b_real,     wf_b_imaginary,     wf_l_real, wf_l_imaginary};
+	for (double *o : outs)
+		if (o) std::fill(o, o + (length > 0 ? length : 0), fill);
+	return status;
+}
+int time_detector_response_py(double *times, int length, double *response_real, double *response_imaginary, char *detector,
+                              char *generation_method, void *parameters)
+{
+	(void)times;
+	(void)detector;
+	(void)parameters;
+	double fill;
+	const int status = time_domain_status(generation_method, &fill);
+	for (double *o : {response_real, response_imaginary})
+		if (o) std::fill(o, o + (length > 0 ? length : 0), fill);
+	return status;
 }
 
 // ---- scalar conveniences gwatpy exposes (not on the hot path; plain host arithmetic, src/util.cpp:1492-1540) --------------------

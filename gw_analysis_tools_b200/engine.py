@@ -17,7 +17,7 @@ _dp = C.POINTER(C.c_double)
 _lib = None
 
 EXPORTS = [
-    "gwat_b200_abi_version", "gwat_b200_cosmology_index", "gwat_b200_transform_orientation_coords", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
+    "gwat_b200_abi_version", "gwat_b200_cosmology_index", "gwat_b200_detector_site", "gwat_b200_transform_orientation_coords", "gwat_b200_source_init", "gwat_b200_mod_init", "gwat_b200_ctx_create",
     "gwat_b200_ctx_destroy", "gwat_b200_last_error", "gwat_b200_set_network", "gwat_b200_loglike_mcmc_batch",
     "gwat_b200_loglike_mcmc_batch_dev", "gwat_b200_loglike_batch", "gwat_b200_loglike_maximized_batch", "gwat_b200_loglike_maximized_mcmc_batch",
     "gwat_b200_fourier_waveform_batch", "gwat_b200_fourier_amplitude_phase_batch",

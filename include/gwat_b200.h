@@ -110,6 +110,10 @@ void gwat_b200_source_init(gwat_b200_source *src);
 int gwat_b200_transform_orientation_coords(const char *generation_method, int n, gwat_b200_source *sources);
 /* Index of a cosmology name as Z_from_DL reads it (case-insensitive, src/util.cpp:356-365); -1 for a name the reference does not know. */
 int gwat_b200_cosmology_index(const char *name);
+/* Site constants of a GWAT detector (include/gwat/detector_util.h:29-157; what gwatpy's get_detector_parameters returns,
+ * src/gwatpy_wrapping.cpp:743-831): latitude and longitude [rad], vertex location[3] [m], response_tensor[9] row-major.  The name is
+ * one set_network takes; GWAT_B200_ERR_ARG for an unknown name or a NULL pointer.  Host constants: no context, no GPU. */
+int gwat_b200_detector_site(const char *detector, double *latitude, double *longitude, double *location, double *response_tensor);
 void gwat_b200_mod_init(gwat_b200_mod *mod);
 
 /* One context per GPU and per submitting thread group.  Owns the device copies of the frequency grid, PSDs, data and

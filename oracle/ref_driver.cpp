@@ -705,6 +705,45 @@ double oracle_ref_dl_from_z(double z, const char *cosmology) { return DL_from_Z(
 double oracle_ref_t_0pn(double f, double chirpmass) { return t_0PN<double>(f, chirpmass); }
 double oracle_ref_f_0pn(double t, double chirpmass) { return f_0PN<double>(t, chirpmass); }
 
+// The reference's own site constants (include/gwat/detector_util.h) in the order get_detector_parameters knows them
+// (src/gwatpy_wrapping.cpp:743-831): 0 Hanford, 1 Livingston, 2 Virgo, 3 Kagra, 4 Indigo, 5 Cosmic Explorer, 6 ET1.
+int oracle_ref_detector_site(int which, double *lat, double *lon, double *location, double *response_tensor)
+{
+	const double lats[7] = {H_LAT, L_LAT, V_LAT, K_LAT, I_LAT, CE_LAT, ET1_LAT};
+	const double lons[7] = {H_LONG, L_LONG, V_LONG, K_LONG, I_LONG, CE_LONG, ET1_LONG};
+	const double *locs[7] = {H_location, L_location, V_location, K_location, I_location, CE_location, ET1_location};
+	const double(*tens[7])[3] = {Hanford_D, Livingston_D, Virgo_D, Kagra_D, Indigo_D, CE_D, ET1_D};
+	if (which < 0 || which > 6) return -1;
+	*lat = lats[which];
+	*lon = lons[which];
+	for (int i = 0; i < 3; i++) {
+		location[i] = locs[which][i];
+		for (int j = 0; j < 3; j++) response_tensor[3 * i + j] = tens[which][i][j];
+	}
+	return 0;
+}
+
+// time_waveform (src/waveform_generator.cpp:31-71) the way time_waveform_full_py calls it (src/gwatpy_wrapping.cpp:428-480): zeroed arrays in,
+// status out; hplus/hcross receive whatever the reference wrote.
+int oracle_ref_time_waveform(const char *method, const gwat_b200_source *src, const double *times, int length, double *hp_re, double *hp_im,
+                             double *hc_re, double *hc_im)
+{
+	ParamBox b;
+	to_gen_params(*src, b);
+	std::vector<std::complex<double>> hp(length, 0.0), hc(length, 0.0);
+	waveform_polarizations<double> wp;
+	wp.hplus = hp.data();
+	wp.hcross = hc.data();
+	const int status = time_waveform<double>(const_cast<double *>(times), length, &wp, std::string(method), &b.gp);
+	for (int i = 0; i < length; i++) {
+		hp_re[i] = hp[i].real();
+		hp_im[i] = hp[i].imag();
+		hc_re[i] = hc[i].real();
+		hc_im[i] = hc[i].imag();
+	}
+	return status;
+}
+
 // pack_local_mod_structure (src/mcmc_gw.cpp:3401-3476); counts[4] and idx[4][GWAT_B200_MAX_MOD] receive the local structure.
 int oracle_ref_pack_local_mod_structure(int min_dim, int max_dim, const int *status, const char *waveform_extended, const gwat_b200_mod *full,
                                         int *counts, int *idx)

@@ -206,9 +206,30 @@ def write_zd_tables():
     print("wrote", os.path.normpath(out))
 
 
+def write_site_tables():
+    """Latitude / longitude of the detector sites for the gwatpy helper get_detector_parameters (host code only): include/gwat/detector_util.h
+    *_LAT / *_LONG, rows in the order of gwat_detector_table."""
+    det = strip_comments(open(os.path.join(REF, "include/gwat/detector_util.h")).read())
+    out = os.path.join(os.path.dirname(OUT), "gwat_tables_sites.inc")
+    with open(out, "w") as o:
+        o.write("// GENERATED by tools/gen_tables.py (write_site_tables) from the reference's include/gwat/detector_util.h -- do not edit.\n")
+        o.write("// per detector (rows as gwat_detector_table): latitude, longitude [rad]\n")
+        o.write("static const double gwat_site_lat_long[9][2] = {\n")
+        for name, pre in [("Hanford", "H"), ("Livingston", "L"), ("Virgo", "V"), ("Kagra", "K"), ("Indigo", "I"), ("CE", "CE"),
+                          ("ET1", "ET1"), ("ET2", "ET2"), ("ET3", "ET3")]:
+            lat = float(re.search(r"\b" + pre + r"_LAT\s*=\s*([-+0-9.eE]+)", det).group(1))
+            lon = float(re.search(r"\b" + pre + r"_LONG\s*=\s*([-+0-9.eE]+)", det).group(1))
+            o.write("/* %s */ {%r,%r},\n" % (name, lat, lon))
+        o.write("};\n")
+    print("wrote", os.path.normpath(out))
+
+
 if __name__ == "__main__":
     if "--zd-only" in sys.argv:
         write_zd_tables()
+    elif "--sites-only" in sys.argv:
+        write_site_tables()
     else:
+        write_site_tables()
         main()
         write_zd_tables()
