@@ -260,6 +260,35 @@ int fourier_detector_response<double>(double *frequencies, int length, std::comp
 	return st;
 }
 
+// calculate_snr(sensitivity_curve, detector, generation_method, params, frequencies, length, integration_method, weights, log10_freq),
+// src/waveform_util.cpp:290-344: sqrt(4 int |response|^2 / S_n) with S_n = populate_noise(curve)^2 (the curve's tables, if it is a tabulated
+// one, from the directory GWAT_B200_NOISE_DIR names -- this library does not carry the reference's data files).  Like the reference, a
+// source given by the equatorial direction of L has incl_angle and psi written into the caller's object.
+double calculate_snr(std::string sensitivity_curve, std::string detector, std::string generation_method, gen_params_base<double> *params,
+                     double *frequencies, int length, std::string integration_method, double *weights, bool log10_freq)
+{
+	Session &S = session();
+	std::lock_guard<std::mutex> lock(S.mu);
+	gwat_b200::Engine *e = engine_locked(S);
+	if (!e || length < 1) return kNaN;
+	std::vector<double> psd(length);
+	if (gwat_b200_populate_noise(frequencies, sensitivity_curve.c_str(), std::getenv("GWAT_B200_NOISE_DIR"), length, psd.data()) != 0) return kNaN;
+	for (double &v : psd) v *= v;
+	S.net_key = 0;
+	double *f1[1] = {frequencies}, *p1[1] = {psd.data()}, *w1[1] = {weights};
+	if (e->set_network(&detector, 1, length, f1, p1, nullptr, w1, integration_method, log10_freq) != 0) return kNaN;
+	gwat_b200_source s;
+	if (!gwat_b200::flatten(*params, s)) return kNaN;
+	double snr = kNaN;
+	if (gwat_b200_snr_batch(e->ctx(), generation_method.c_str(), 1, &s, &snr) != 0) return kNaN;
+	if (params->equatorial_orientation && !params->horizon_coord &&
+	    gwat_b200_transform_orientation_coords(generation_method.c_str(), 1, &s) == 0) {
+		params->incl_angle = s.incl_angle;
+		params->psi = s.psi;
+	}
+	return snr;
+}
+
 template <>
 void create_coherent_GW_detection_reuse_WF<double>(std::string *detectors, int detector_N, double *frequencies, int lengths,
                                                    gen_params_base<double> *gen_params, std::string generation_method,

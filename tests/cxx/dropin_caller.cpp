@@ -5,6 +5,7 @@
 //   dropin_caller_b200   -> libgwat_b200_dropin.so first, then libgwat_ref.so: the hot-path symbols resolve to the GPU library, the
 //                           rest (populate_noise, MCMC_prep_params, repack_parameters, allocate_2D_array ...) to the reference
 // Each run prints "name value" lines with 17 significant digits; the test compares the two outputs.
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include <gwat/detector_util.h>
 #include <gwat/fisher.h>
 #include <gwat/mcmc_gw.h>
+#include <gwat/ortho_basis.h>
 #include <gwat/util.h>
 #include <gwat/waveform_generator.h>
 #include <gwat/waveform_util.h>
@@ -106,6 +108,24 @@ int main()
 				put(std::string("legacy_split_im_") + method, i, im[i]);
 			}
 		}
+	}
+
+	// ---- calculate_snr (noise curve by name; Simpson on the data grid, and Gauss-Legendre in log10 f with its own weights) ------
+	for (const char *method : {"IMRPhenomD", "IMRPhenomPv2"}) {
+		gen_params g = gp;
+		if (std::string(method) == "IMRPhenomPv2") {
+			g.spin1[0] = .3;
+			g.spin1[1] = .1;
+			g.spin2[1] = -.2;
+		}
+		put((std::string("calculate_snr_") + method).c_str(),
+		    calculate_snr("aLIGO_analytic", "Hanford", std::string(method), &g, freq[0], L, "SIMPSONS", (double *)NULL, false));
+		const int NG = 400;
+		std::vector<double> fg(NG), wg(NG);
+		gauleg(std::log10(20.), std::log10(900.), fg.data(), wg.data(), NG);
+		for (int i = 0; i < NG; i++) fg[i] = std::pow(10., fg[i]);
+		put((std::string("calculate_snr_gl_") + method).c_str(),
+		    calculate_snr("Hanford_O1_fitted", "Virgo", std::string(method), &g, fg.data(), NG, "GAUSSLEG", wg.data(), true));
 	}
 
 	// ---- responses -------------------------------------------------------------------------------------------------------

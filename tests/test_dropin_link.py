@@ -22,7 +22,8 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 HOT_PATH = ["fourier_waveform<double>(", "fourier_waveform(double*, int, std::complex<double>*", "fourier_waveform(double*, int, double*, double*, std::",
             "fourier_waveform(double*, int, double*, double*, double*, double*, double*", "fourier_detector_response<double>(",
             "create_coherent_GW_detection<double>(", "create_coherent_GW_detection_reuse_WF<double>(", "Log_Likelihood_internal(",
-            "MCMC_likelihood_extrinsic(", "MCMC_likelihood_wrapper(", "MCMC_fisher_wrapper(", "fisher_numerical("]
+            "MCMC_likelihood_extrinsic(", "MCMC_likelihood_wrapper(", "MCMC_fisher_wrapper(", "fisher_numerical(",
+            "calculate_snr(std::"]
 
 
 def _defined(path):
